@@ -1,0 +1,61 @@
+// Launchers for the CUDA-core (HBM-bound) kernels of the NAFNet hot path.
+// Layout everywhere: NHWC, i.e. row-major [M = N*H*W pixels, C channels].
+// fp32 = residual stream / statistics / parameters / gradients of parameters,
+// bf16 = branch-internal activations that feed the tensor-core GEMMs.
+#pragma once
+#include "common.cuh"
+
+// LayerNorm2d over channels (reference: nafnet_arch.py:25-64).
+int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, float* stats, int M, int C, float eps,
+                  cudaStream_t st);
+// dx = dres + LNbwd(dn); also dx mirror in bf16, sum_m dn*yhat -> dw, sum_m dn -> db, sum_m dx -> colsum (all +=).
+int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const float* w, const float* dres, float* dx,
+                  bf16* dx_bf16, float* dw, float* db, float* colsum, int M, int C, cudaStream_t st);
+
+// depthwise 3x3 (+bias, zero pad) on 2C channels followed by SimpleGate; pool[n,c] += sum_px g.
+int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, float* pool, int N, int H, int W, int C,
+                      cudaStream_t st);
+// backward part a: dg = dgs*s + t; du2 = SimpleGate'(dg); dW2 += du2 (*) u; db2 += sum du2.
+int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const bf16* u, const float* w2, const float* b2,
+                        bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st);
+// backward part b: du = dwconv^T(du2); colsum[c] += sum_px du.
+int dwconv_bwd_data_launch(const bf16* du2, const float* w2, bf16* du, float* colsum, int N, int H, int W, int C2,
+                           cudaStream_t st);
+
+// Simplified channel attention (nafnet_arch.py:116-127).
+int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, int N, int C, int HW, cudaStream_t st);
+int scale_rows_launch(const bf16* g, const float* s, bf16* gs, int N, int HW, int C, cudaStream_t st);
+int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int HW, int C, cudaStream_t st);
+int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t, float* dw, float* db, int N, int C, int HW,
+                   cudaStream_t st);
+
+int colsum_bf16_launch(const bf16* x, float* out, int M, int C, cudaStream_t st);
+// out = a + b (either nullable -> treated as 0): fp32 (nullable), bf16 mirror (nullable), colsum += column sums (nullable).
+int grad_prepare_launch(const float* a, const float* b, float* out, bf16* out_bf16, float* colsum, int M, int C,
+                        cudaStream_t st);
+int axpy_launch(float* dst, const float* src, int n, cudaStream_t st);
+int cast_f32_bf16_launch(const float* x, bf16* y, long long n, cudaStream_t st);
+// fp32 NHWC [N, 2H, 2W, C] -> bf16 [N*H*W, 4C], column = (i*2+j)*C + c for sub-pixel (i, j).
+int unshuffle_cast_launch(const float* x, bf16* y, int N, int H, int W, int C, cudaStream_t st);
+
+// Weight packing (fp32 parameter -> bf16 GEMM operand), see nafnet.cu for the modes.
+enum PackMode { PACK_PLAIN = 0, PACK_T = 1, PACK_PAIR = 2, PACK_UP = 3, PACK_UP_T = 4, PACK_DOWN = 5, PACK_DOWN_T = 6 };
+int pack_weight_launch(const float* w, const float* row_scale, bf16* out, int O, int I, int mode, cudaStream_t st);
+// small fp32 vectors: out[p] = bias[src(p)] * scale[src(p)] (mode PACK_PLAIN or PACK_PAIR)
+int pack_bias_launch(const float* bias, const float* scale, float* out, int O, int mode, cudaStream_t st);
+
+// wgrad finishing: scratch G (fp32, from the split-K GEMM) -> parameter gradients (+=).
+enum FinishMode { FIN_RESID = 0, FIN_UP = 1, FIN_DOWN = 2, FIN_C3_TO_CN = 3, FIN_CN_TO_C3 = 4 };
+int wgrad_finish_resid_launch(const float* G, const float* w, const float* bias, const float* scale, const float* colsum,
+                              float* dw, float* dbias, float* dscale, int O, int I, cudaStream_t st);
+int wgrad_finish_perm_launch(const float* G, float* dw, int O, int I, int mode, cudaStream_t st);
+
+// 3x3 convs touching the 3-channel image (intro / ending), direct CUDA-core kernels.
+// img: fp32 NCHW [N,3,H,W]; feat: fp32 NHWC [N*H*W, C].
+int conv3x3_img_to_feat_launch(const float* img, const float* w, const float* bias, int transpose_flip, float* out_f32,
+                               bf16* out_bf16, float* colsum, int N, int H, int W, int C, cudaStream_t st);
+int conv3x3_feat_to_img_launch(const float* feat, const float* w, const float* bias, const float* resid_img, float* out_img,
+                               int N, int H, int W, int C, cudaStream_t st);
+// G[c][j] (+)= sum_px feat[px][c] * patch_j(img)[px], j = ci*9 + ky*3 + kx (27 columns); flip mirrors the taps.
+int conv3x3_small_wgrad_launch(const float* feat, const float* img, float* G, float* img_sum, int flip, int N, int H, int W,
+                               int C, cudaStream_t st);

@@ -1,0 +1,310 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a — the tensor-core engine behind every
+// pointwise (1x1) convolution, the 2x2-stride-2 down convs, the 1x1+PixelShuffle
+// up convs and all their dgrad / wgrad contractions on the NAFNet hot path
+// (reference: nafnet_arch.py:87-150 conv1/3/4/5, :230 downs, :238-242 ups; the
+// reference runs these through cuDNN/cuBLAS fp32).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1   : MMA issuer     (one elected lane issues tcgen05.mma, fp32 accum in TMEM)
+//   warps 2-5: epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop
+// of tile i+1.  Tile = 128 x BN (BN in {64,128,256}), BK = 64 bf16 (= one 128-byte
+// swizzle row).  MN-major operands (wgrad) are loaded as 64x64 boxes, which
+// the UMMA descriptor addresses with LBO = 8 KiB / SBO = 1 KiB.
+#include <mutex>
+
+#include "gemm.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two >= 32)
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+};
+
+// UMMA shared-memory descriptor (sm_100): start addr [0,14), LBO [16,30), SBO [32,46) (all >>4),
+// version=1 at [46,48), layout type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), a/b major (15/16),
+// N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN, int EPI, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+               int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)C::STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (K + BK - 1) / BK;
+  const int total_tiles = tiles_m * tiles_n * splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_t = tile % tiles_n;
+        const int m_t = (tile / tiles_n) % tiles_m;
+        const int sp = tile / (tiles_n * tiles_m);
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(num_kb, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          uint8_t* a_dst = sA + (size_t)stage * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + (size_t)stage * C::B_STAGE_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_t * BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * 8192, &tmA, &full[stage], m_t * BM + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, n_t * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, &tmB, &full[stage], n_t * BN + c * 64, kb * BK);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int sp = tile / (tiles_n * tiles_m);
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(num_kb, kb0 + kb_per_split);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + (size_t)stage * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 elements = 32 B inside the 128 B swizzle row; SBO = 1 KiB between 8-row groups.
+            // MN-major: 16 k-rows = 2 KiB; LBO = 8 KiB between 64-wide MN chunks, SBO = 1 KiB between 8-k groups.
+            const uint64_t adesc = A_MN ? make_smem_desc(a_addr + k * 2048, 8192, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * 2048, 8192, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // -------------------------------- epilogue --------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % tiles_n;
+      const int m_t = (tile / tiles_n) % tiles_m;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_t * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_t * BN + c * 32;
+        if (n0 < N) {  // warp-uniform
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (m < M) epilogue_chunk<EPI>(ep, m, n0, N, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------ host side -------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// Row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = 64 x box_rows, 128B swizzle.
+int make_tmap(CUtensorMap* tm, const bf16* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  DCPT_CHECK_ARG(fn != nullptr, DCPT_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  DCPT_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0, DCPT_E_ALIGN,
+                 "GEMM operand must be 16-byte aligned with ld %% 8 == 0 (ptr=%p ld=%lld)", (const void*)ptr, ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCPT_CHECK_ARG(r == CUDA_SUCCESS, DCPT_E_DRIVER, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%d",
+                 (int)r, rows, cols, ld, box_rows);
+  return 0;
+}
+
+template <int BN, int EPI, bool A_MN, bool B_MN>
+int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  if (!g.a_mn) DCPT_TRY(make_tmap(&tmA, g.A, g.M, g.K, g.lda, BM));
+  else DCPT_TRY(make_tmap(&tmA, g.A, g.K, g.M, g.lda, 64));
+  if (!g.b_mn) DCPT_TRY(make_tmap(&tmB, g.B, g.N, g.K, g.ldb, BN));
+  else DCPT_TRY(make_tmap(&tmB, g.B, g.K, g.N, g.ldb, 64));
+
+  const int tiles_m = ceil_div(g.M, BM), tiles_n = ceil_div(g.N, BN);
+  const int num_kb = ceil_div(g.K, BK);
+  int splits = g.splits < 1 ? 1 : g.splits;
+  if (splits > num_kb) splits = num_kb;
+  int kbps = ceil_div(num_kb, splits);
+  splits = ceil_div(num_kb, kbps);  // every split gets >= 1 k-block
+  const int total = tiles_m * tiles_n * splits;
+  const int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
+
+  auto kern = gemm_tc_kernel<BN, EPI, A_MN, B_MN>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    DCPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, g.M, g.N, g.K, tiles_m, tiles_n, splits, kbps, g.ep);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int EPI, bool A_MN, bool B_MN>
+int launch_bn(const GemmArgs& g, cudaStream_t stream) {
+  // Largest tile that N fills; small-N GEMMs (C = 64 levels) are HBM-bound and want more, smaller tiles.
+  if (g.N > 128) return launch_cfg<256, EPI, A_MN, B_MN>(g, stream);
+  if (g.N > 64) return launch_cfg<128, EPI, A_MN, B_MN>(g, stream);
+  return launch_cfg<64, EPI, A_MN, B_MN>(g, stream);
+}
+
+}  // namespace
+
+int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
+  DCPT_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, DCPT_E_SHAPE, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  DCPT_CHECK_ARG(g.N % 8 == 0, DCPT_E_SHAPE, "gemm: N=%d must be a multiple of 8", g.N);
+  DCPT_CHECK_ARG(g.splits <= 1 || g.epi == EPI_ATOMIC, DCPT_E_ARG, "gemm: split-K needs the atomic epilogue");
+  if (g.a_mn != g.b_mn) {
+    dcpt_set_error("gemm: mixed operand majorness is not instantiated");
+    return DCPT_E_UNSUPPORTED;
+  }
+  if (g.a_mn) {
+    DCPT_CHECK_ARG(g.epi == EPI_ATOMIC, DCPT_E_UNSUPPORTED, "gemm: MN-major operands are only used by wgrad (atomic epilogue)");
+    return launch_bn<EPI_ATOMIC, true, true>(g, stream);
+  }
+  switch (g.epi) {
+    case EPI_STORE: return launch_bn<EPI_STORE, false, false>(g, stream);
+    case EPI_GATE: return launch_bn<EPI_GATE, false, false>(g, stream);
+    case EPI_GATE_BWD: return launch_bn<EPI_GATE_BWD, false, false>(g, stream);
+    case EPI_PIXSHUF: return launch_bn<EPI_PIXSHUF, false, false>(g, stream);
+    case EPI_ATOMIC: return launch_bn<EPI_ATOMIC, false, false>(g, stream);
+  }
+  dcpt_set_error("gemm: unknown epilogue %d", g.epi);
+  return DCPT_E_ARG;
+}

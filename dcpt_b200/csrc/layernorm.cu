@@ -1,0 +1,214 @@
+// Channel LayerNorm (LayerNorm2d) forward / backward for NHWC rows.
+// Reference math: basicsr/archs/nafnet_arch.py:25-53 (LayerNormFunction):
+//   fwd: mu = mean_c x; var = mean_c (x-mu)^2 (biased); y = (x-mu)/sqrt(var+eps); out = w*y + b
+//   bwd: g = dout*w; dx = (g - y*mean_c(g*y) - mean_c(g)) / sqrt(var+eps); dw = sum dout*y; db = sum dout
+// One row (pixel) is owned by `lpr` lanes of a warp (lpr = 2..32, power of two), so the
+// reductions over C are xor-shuffles; each lane keeps its NV float4 slices in registers.
+// HBM-bound: fwd reads 4C and writes 2C (+8) bytes per pixel.
+#include "elementwise.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ float group_sum(float v, int lpr) {
+  for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarps * 32)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
+              float* __restrict__ stats, int M, int C, int lpr, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rpw = 32 / lpr;  // rows per warp
+  const int sub = lane % lpr, gr = lane / lpr;
+  const int nvec = C >> 2;
+  const float invC = 1.f / (float)C;
+  const long long row_stride = (long long)gridDim.x * kWarps * rpw;
+  for (long long row = ((long long)blockIdx.x * kWarps + warp) * rpw + gr; row - gr < M; row += row_stride) {
+    const bool valid = row < M;
+    float4 xv[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = sub + i * lpr;
+      xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && v < nvec) xv[i] = __ldg(reinterpret_cast<const float4*>(x + row * C) + v);
+      sum += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+    }
+    const float mean = group_sum(sum, lpr) * invC;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = sub + i * lpr;
+      if (v < nvec) {
+        const float a = xv[i].x - mean, bb = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+        sq += a * a + bb * bb + c * c + d * d;
+      }
+    }
+    const float var = group_sum(sq, lpr) * invC;
+    const float rstd = 1.f / sqrtf(var + eps);
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = sub + i * lpr;
+        if (v < nvec) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + v);
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(b) + v);
+          const float o0 = (xv[i].x - mean) * rstd * wv.x + bv.x;
+          const float o1 = (xv[i].y - mean) * rstd * wv.y + bv.y;
+          const float o2 = (xv[i].z - mean) * rstd * wv.z + bv.z;
+          const float o3 = (xv[i].w - mean) * rstd * wv.w + bv.w;
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          *(reinterpret_cast<uint2*>(out + row * C) + v) = pk;
+        }
+      }
+      if (sub == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarps * 32)
+ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ stats,
+              const float* __restrict__ w, const float* __restrict__ dres, float* __restrict__ dx, bf16* __restrict__ dx_bf16,
+              float* __restrict__ dw, float* __restrict__ db, float* __restrict__ colsum, int M, int C, int lpr) {
+  extern __shared__ float s_acc[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rpw = 32 / lpr;
+  const int sub = lane % lpr, gr = lane / lpr;
+  const int nvec = C >> 2;
+  const float invC = 1.f / (float)C;
+  float4 a_dw[NV], a_db[NV], a_cs[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a_dw[i] = a_db[i] = a_cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long row_stride = (long long)gridDim.x * kWarps * rpw;
+  for (long long row = ((long long)blockIdx.x * kWarps + warp) * rpw + gr; row - gr < M; row += row_stride) {
+    const bool valid = row < M;
+    float2 st = make_float2(0.f, 0.f);
+    if (valid) st = __ldg(reinterpret_cast<const float2*>(stats + row * 2));
+    const float mean = st.x, rstd = st.y;
+    float4 yh[NV], g[NV], d[NV];
+    float sg = 0.f, sgy = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = sub + i * lpr;
+      yh[i] = g[i] = d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && v < nvec) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * C) + v);
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(dn + row * C) + v);
+        const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+        const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + v);
+        d[i] = make_float4(d01.x, d01.y, d23.x, d23.y);
+        yh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[i] = make_float4(d[i].x * wv.x, d[i].y * wv.y, d[i].z * wv.z, d[i].w * wv.w);
+        sg += g[i].x + g[i].y + g[i].z + g[i].w;
+        sgy += g[i].x * yh[i].x + g[i].y * yh[i].y + g[i].z * yh[i].z + g[i].w * yh[i].w;
+      }
+    }
+    const float mean_g = group_sum(sg, lpr) * invC;
+    const float mean_gy = group_sum(sgy, lpr) * invC;
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = sub + i * lpr;
+        if (v < nvec) {
+          float4 o;
+          o.x = rstd * (g[i].x - yh[i].x * mean_gy - mean_g);
+          o.y = rstd * (g[i].y - yh[i].y * mean_gy - mean_g);
+          o.z = rstd * (g[i].z - yh[i].z * mean_gy - mean_g);
+          o.w = rstd * (g[i].w - yh[i].w * mean_gy - mean_g);
+          if (dres) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(dres + row * C) + v);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          }
+          *(reinterpret_cast<float4*>(dx + row * C) + v) = o;
+          if (dx_bf16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *(reinterpret_cast<uint2*>(dx_bf16 + row * C) + v) = pk;
+          }
+          a_dw[i].x += d[i].x * yh[i].x; a_dw[i].y += d[i].y * yh[i].y; a_dw[i].z += d[i].z * yh[i].z; a_dw[i].w += d[i].w * yh[i].w;
+          a_db[i].x += d[i].x; a_db[i].y += d[i].y; a_db[i].z += d[i].z; a_db[i].w += d[i].w;
+          a_cs[i].x += o.x; a_cs[i].y += o.y; a_cs[i].z += o.z; a_cs[i].w += o.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = sub + i * lpr;
+    if (v < nvec) {
+      const int c = v * 4;
+      atomicAdd(&s_acc[c + 0], a_dw[i].x); atomicAdd(&s_acc[c + 1], a_dw[i].y);
+      atomicAdd(&s_acc[c + 2], a_dw[i].z); atomicAdd(&s_acc[c + 3], a_dw[i].w);
+      atomicAdd(&s_acc[C + c + 0], a_db[i].x); atomicAdd(&s_acc[C + c + 1], a_db[i].y);
+      atomicAdd(&s_acc[C + c + 2], a_db[i].z); atomicAdd(&s_acc[C + c + 3], a_db[i].w);
+      atomicAdd(&s_acc[2 * C + c + 0], a_cs[i].x); atomicAdd(&s_acc[2 * C + c + 1], a_cs[i].y);
+      atomicAdd(&s_acc[2 * C + c + 2], a_cs[i].z); atomicAdd(&s_acc[2 * C + c + 3], a_cs[i].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (dw) atomicAdd(dw + c, s_acc[c]);
+    if (db) atomicAdd(db + c, s_acc[C + c]);
+    if (colsum) atomicAdd(colsum + c, s_acc[2 * C + c]);
+  }
+}
+
+inline int pick_lpr(int C) {
+  const int nvec = C / 4;
+  int lpr = 2;
+  while (lpr < 32 && lpr < nvec) lpr <<= 1;
+  return lpr;
+}
+
+}  // namespace
+
+int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, float* stats, int M, int C, float eps,
+                  cudaStream_t st) {
+  DCPT_CHECK_ARG(M > 0 && C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "layernorm: need C %% 8 == 0 and 8 <= C <= 1024 (C=%d M=%d)",
+                 C, M);
+  const int lpr = pick_lpr(C);
+  const int nv = ceil_div(C / 4, lpr);
+  const int rows_per_block = kWarps * (32 / lpr);
+  const int grid = (int)ceil_div_ll(M, rows_per_block);
+#define LN_FWD(NVV) ln_fwd_kernel<NVV><<<grid, kWarps * 32, 0, st>>>(x, w, b, n_out, stats, M, C, lpr, eps)
+  if (nv <= 1) LN_FWD(1);
+  else if (nv <= 2) LN_FWD(2);
+  else if (nv <= 4) LN_FWD(4);
+  else LN_FWD(8);
+#undef LN_FWD
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const float* w, const float* dres, float* dx,
+                  bf16* dx_bf16, float* dw, float* db, float* colsum, int M, int C, cudaStream_t st) {
+  DCPT_CHECK_ARG(M > 0 && C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "layernorm bwd: need C %% 8 == 0 and 8 <= C <= 1024 (C=%d)", C);
+  const int lpr = pick_lpr(C);
+  const int nv = ceil_div(C / 4, lpr);
+  const int rows_per_block = kWarps * (32 / lpr);
+  long long grid = ceil_div_ll(M, rows_per_block);
+  const long long cap = (long long)dcpt_num_sms() * 4;  // few blocks -> few partial-sum flushes
+  if (grid > cap) grid = cap;
+  const size_t smem = (size_t)3 * C * sizeof(float);
+#define LN_BWD(NVV) \
+  ln_bwd_kernel<NVV><<<(int)grid, kWarps * 32, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr)
+  if (nv <= 1) LN_BWD(1);
+  else if (nv <= 2) LN_BWD(2);
+  else if (nv <= 4) LN_BWD(4);
+  else LN_BWD(8);
+#undef LN_BWD
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}

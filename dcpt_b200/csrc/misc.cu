@@ -1,0 +1,407 @@
+// Small CUDA-core kernels of the NAFNet hot path: simplified channel attention (SCA),
+// per-image channel scaling, column sums, casts, pixel-unshuffle, weight packing and the
+// wgrad finishing steps.  References: nafnet_arch.py:116-127 (sca), :173 (x * sca(x)),
+// :230 (downs, 2x2 stride 2), :238-242 (ups, 1x1 + PixelShuffle(2)).
+#include "elementwise.cuh"
+
+namespace {
+
+// ------------------------------- SCA -------------------------------------------
+// s[n][co] = b[co] + (1/HW) * sum_ci W[co][ci] * pool[n][ci]           (one warp per output)
+__global__ void sca_fwd_kernel(const float* __restrict__ pool, const float* __restrict__ w, const float* __restrict__ b,
+                               float* __restrict__ s, int N, int C, float inv_hw) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= N * C) return;
+  const int n = gw / C, co = gw - n * C;
+  float acc = 0.f;
+  for (int ci = lane; ci < C; ci += 32) acc = fmaf(w[(size_t)co * C + ci], pool[(size_t)n * C + ci], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) s[gw] = b[co] + acc * inv_hw;
+}
+
+__global__ void scale_rows_kernel(const bf16* __restrict__ g, const float* __restrict__ s, bf16* __restrict__ gs, long long nvec,
+                                  int HW, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const int CV = C >> 3;
+  const long long px = i / CV;
+  const int c = (int)(i - px * CV) * 8;
+  const int n = (int)(px / HW);
+  float v[8];
+  unpack8(ldg16(g + i * 8), v);
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (size_t)n * C + c));
+  const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + (size_t)n * C + c + 4));
+  v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+  v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+  stg16(gs + i * 8, pack8(v));
+}
+
+// ds[n][c] += sum_{px in image n} dgs[px][c] * g[px][c]
+__global__ void __launch_bounds__(256)
+sca_ds_reduce_kernel(const bf16* __restrict__ dgs, const bf16* __restrict__ g, float* __restrict__ ds, int HW, int C, int cvb) {
+  extern __shared__ float s_red[];  // [cvb*8]
+  for (int i = threadIdx.x; i < cvb * 8; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.z, CV = C >> 3;
+  const int cvl = threadIdx.x % cvb, pl = threadIdx.x / cvb, npl = blockDim.x / cvb;
+  const int cv = blockIdx.y * cvb + cvl;
+  if (cv < CV) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int px = blockIdx.x * npl + pl; px < HW; px += gridDim.x * npl) {
+      const size_t off = ((size_t)n * HW + px) * C + cv * 8;
+      float a[8], b[8];
+      unpack8(ldg16(dgs + off), a);
+      unpack8(ldg16(g + off), b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(a[i], b[i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&s_red[cvl * 8 + i], acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cvb * 8; i += blockDim.x) {
+    const int c = blockIdx.y * cvb * 8 + i;
+    if (c < C) atomicAdd(ds + (size_t)n * C + c, s_red[i]);
+  }
+}
+
+// t[n][ci] = (1/HW) sum_co W[co][ci] ds[n][co];  dW[co][ci] += (1/HW) sum_n ds[n][co] pool[n][ci];  db[co] += sum_n ds[n][co]
+__global__ void sca_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ pool, const float* __restrict__ w,
+                               float* __restrict__ t, float* __restrict__ dw, float* __restrict__ db, int N, int C, float inv_hw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long CC = (long long)C * C;
+  if (i < CC) {
+    const int co = (int)(i / C), ci = (int)(i - (long long)co * C);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc = fmaf(ds[(size_t)n * C + co], pool[(size_t)n * C + ci], acc);
+    dw[i] += acc * inv_hw;
+  } else if (i < CC + (long long)N * C) {
+    const long long j = i - CC;
+    const int n = (int)(j / C), ci = (int)(j - (long long)n * C);
+    float acc = 0.f;
+    for (int co = 0; co < C; ++co) acc = fmaf(w[(size_t)co * C + ci], ds[(size_t)n * C + co], acc);
+    t[j] = acc * inv_hw;
+  } else if (i < CC + (long long)N * C + C) {
+    const int co = (int)(i - CC - (long long)N * C);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc += ds[(size_t)n * C + co];
+    db[co] += acc;
+  }
+}
+
+// ------------------------------ column sums ------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ out, int M, int C, int cvb) {
+  extern __shared__ float s_red[];
+  for (int i = threadIdx.x; i < cvb * 8; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  const int CV = C >> 3;
+  const int cvl = threadIdx.x % cvb, pl = threadIdx.x / cvb, npl = blockDim.x / cvb;
+  const int cv = blockIdx.y * cvb + cvl;
+  if (cv < CV) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long m = (long long)blockIdx.x * npl + pl; m < M; m += (long long)gridDim.x * npl) {
+      float a[8];
+      unpack8(ldg16(x + (size_t)m * C + cv * 8), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&s_red[cvl * 8 + i], acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cvb * 8; i += blockDim.x) {
+    const int c = blockIdx.y * cvb * 8 + i;
+    if (c < C) atomicAdd(out + c, s_red[i]);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long nvec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  stg16(y + i * 8, pack8(v));
+}
+
+// x: fp32 [N, 2H, 2W, C]  ->  y: bf16 [N*H*W, 4C], y[m][(i*2+j)*C + c] = x[n][2h+i][2w+j][c]
+__global__ void unshuffle_cast_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long nvec, int H, int W, int C) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nvec) return;
+  const int CV = C >> 3;
+  const int cv = (int)(idx % CV);
+  const int q = (int)((idx / CV) & 3);
+  const long long m = idx / (4 * CV);
+  const int w = (int)(m % W);
+  const long long tmp = m / W;
+  const int h = (int)(tmp % H);
+  const long long n = tmp / H;
+  const size_t src = (((size_t)n * 2 * H + 2 * h + (q >> 1)) * (size_t)(2 * W) + 2 * w + (q & 1)) * C + cv * 8;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x + src));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(x + src + 4));
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  stg16(y + idx * 8, pack8(v));
+}
+
+// ------------------------------ weight packing ----------------------------------
+// out is row-major bf16 [R, Cc]; (r, c) -> source element of the fp32 parameter w (and its out-channel o for row_scale).
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ row_scale, bf16* __restrict__ out,
+                                   int O, int I, int mode) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)O * I;
+  if (idx >= total) return;
+  int o, i;  // source coordinates: w viewed as [O][I] (I = all input-side dims flattened as stored)
+  switch (mode) {
+    case PACK_PLAIN: {  // out[o][i]
+      o = (int)(idx / I); i = (int)(idx % I);
+    } break;
+    case PACK_T: {  // out[i][o]
+      i = (int)(idx / O); o = (int)(idx % O);
+    } break;
+    case PACK_PAIR: {  // out[p][i], p = 16*pp + h*8 + e  <->  o = h*C + 8*pp + e  (C = O/2)
+      const int p = (int)(idx / I); i = (int)(idx % I);
+      o = ((p & 15) >> 3) * (O >> 1) + (p >> 4) * 8 + (p & 7);
+    } break;
+    case PACK_UP: {  // out[p][i], p = q*Cseg + c'  <->  o = c'*4 + q  (Cseg = O/4)
+      const int p = (int)(idx / I); i = (int)(idx % I);
+      const int cseg = O >> 2;
+      o = (p % cseg) * 4 + p / cseg;
+    } break;
+    case PACK_UP_T: {  // out[i][p]
+      i = (int)(idx / O);
+      const int p = (int)(idx % O);
+      const int cseg = O >> 2;
+      o = (p % cseg) * 4 + p / cseg;
+    } break;
+    case PACK_DOWN: {  // w [O][C][2][2] (I = 4C): out[o][k], k = (dy*2+dx)*C + c  <->  i = c*4 + dy*2 + dx
+      o = (int)(idx / I);
+      const int k = (int)(idx % I);
+      const int c4 = I >> 2;
+      i = (k % c4) * 4 + k / c4;
+    } break;
+    default: {  // PACK_DOWN_T: out[k][o]
+      const int k = (int)(idx / O);
+      o = (int)(idx % O);
+      const int c4 = I >> 2;
+      i = (k % c4) * 4 + k / c4;
+    } break;
+  }
+  float v = w[(size_t)o * I + i];
+  if (row_scale) v *= row_scale[o];
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+__global__ void pack_bias_kernel(const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ out, int O,
+                                 int mode) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= O) return;
+  int o = p;
+  if (mode == PACK_PAIR) o = ((p & 15) >> 3) * (O >> 1) + (p >> 4) * 8 + (p & 7);
+  float v = bias[o];
+  if (scale) v *= scale[o];
+  out[p] = v;
+}
+
+// ------------------------------ wgrad finishing ----------------------------------
+// Residual-scaled conv (conv3 with beta, conv5 with gamma): forward used W' = diag(scale) W, b' = scale*b.
+// G = dYres^T X is the wgrad w.r.t. W' rows *before* the scale.  One warp per out-channel o:
+//   dW[o][i] += scale[o] G[o][i];  dscale[o] += sum_i W[o][i] G[o][i] + b[o] S[o];  db[o] += scale[o] S[o]
+__global__ void wgrad_finish_resid_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ bias,
+                                          const float* __restrict__ scale, const float* __restrict__ colsum, float* __restrict__ dw,
+                                          float* __restrict__ dbias, float* __restrict__ dscale, int O, int I) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (o >= O) return;
+  const float sc = scale[o];
+  float dot = 0.f;
+  for (int i = lane; i < I; i += 32) {
+    const float gv = G[(size_t)o * I + i];
+    dot = fmaf(w[(size_t)o * I + i], gv, dot);
+    dw[(size_t)o * I + i] += sc * gv;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    const float S = colsum[o];
+    dscale[o] += dot + bias[o] * S;
+    dbias[o] += sc * S;
+  }
+}
+
+__global__ void wgrad_finish_perm_kernel(const float* __restrict__ G, float* __restrict__ dw, int O, int I, int mode) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)O * I) return;
+  const int p = (int)(idx / I), k = (int)(idx % I);
+  int o = p, i = k;
+  if (mode == FIN_UP) {  // G rows in packed order p = q*Cseg + c'
+    const int cseg = O >> 2;
+    o = (p % cseg) * 4 + p / cseg;
+  } else if (mode == FIN_DOWN) {  // G cols k = (dy*2+dx)*C + c  ->  i = c*4 + dy*2+dx
+    const int c4 = I >> 2;
+    i = (k % c4) * 4 + k / c4;
+  } else if (mode == FIN_CN_TO_C3) {  // G [C=O][27 = I], k = oc*9 + t  ->  dw[oc][c][t] (ending conv weight [3][C][3][3])
+    const int oc = k / 9, t = k % 9;
+    dw[((size_t)oc * O + p) * 9 + t] += G[idx];
+    return;
+  }
+  dw[(size_t)o * I + i] += G[idx];
+}
+
+// out = a (+ b): fp32 copy, bf16 mirror and column sums of a residual-stream gradient.
+__global__ void __launch_bounds__(256)
+grad_prepare_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, bf16* __restrict__ out_bf16,
+                    float* __restrict__ colsum, int M, int C, int cvb) {
+  extern __shared__ float s_red[];
+  for (int i = threadIdx.x; i < cvb * 8; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  const int CV = C >> 3;
+  const int cvl = threadIdx.x % cvb, pl = threadIdx.x / cvb, npl = blockDim.x / cvb;
+  const int cv = blockIdx.y * cvb + cvl;
+  if (cv < CV) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long m = (long long)blockIdx.x * npl + pl; m < M; m += (long long)gridDim.x * npl) {
+      const size_t off = (size_t)m * C + cv * 8;
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+      if (a) {
+        x0 = __ldg(reinterpret_cast<const float4*>(a + off));
+        x1 = __ldg(reinterpret_cast<const float4*>(a + off + 4));
+      }
+      if (b) {
+        const float4 y0 = __ldg(reinterpret_cast<const float4*>(b + off));
+        const float4 y1 = __ldg(reinterpret_cast<const float4*>(b + off + 4));
+        x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
+        x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+      }
+      const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      if (out) {
+        *reinterpret_cast<float4*>(out + off) = x0;
+        *reinterpret_cast<float4*>(out + off + 4) = x1;
+      }
+      if (out_bf16) stg16(out_bf16 + off, pack8(v));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&s_red[cvl * 8 + i], acc[i]);
+  }
+  __syncthreads();
+  if (colsum)
+    for (int i = threadIdx.x; i < cvb * 8; i += blockDim.x) {
+      const int c = blockIdx.y * cvb * 8 + i;
+      if (c < C) atomicAdd(colsum + c, s_red[i]);
+    }
+}
+
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+}  // namespace
+
+int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, int N, int C, int HW, cudaStream_t st) {
+  const long long threads = (long long)N * C * 32;
+  sca_fwd_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, st>>>(pool, w, b, s, N, C, 1.f / (float)HW);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int scale_rows_launch(const bf16* g, const float* s, bf16* gs, int N, int HW, int C, cudaStream_t st) {
+  const long long nvec = (long long)N * HW * (C / 8);
+  scale_rows_kernel<<<(unsigned)ceil_div_ll(nvec, 256), 256, 0, st>>>(g, s, gs, nvec, HW, C);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+static inline int pick_cvb(int CV) {
+  int cvb = 1;
+  while (cvb < CV && cvb < 32) cvb <<= 1;
+  return cvb;
+}
+
+int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int HW, int C, cudaStream_t st) {
+  const int CV = C / 8, cvb = pick_cvb(CV), npl = 256 / cvb;
+  int gx = ceil_div(HW, npl * 16);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, ceil_div(CV, cvb), N);
+  sca_ds_reduce_kernel<<<grid, 256, cvb * 8 * sizeof(float), st>>>(dgs, g, ds, HW, C, cvb);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t, float* dw, float* db, int N, int C, int HW,
+                   cudaStream_t st) {
+  const long long total = (long long)C * C + (long long)N * C + C;
+  sca_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(ds, pool, w, t, dw, db, N, C, 1.f / (float)HW);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int colsum_bf16_launch(const bf16* x, float* out, int M, int C, cudaStream_t st) {
+  const int CV = C / 8, cvb = pick_cvb(CV), npl = 256 / cvb;
+  long long gx = ceil_div_ll(M, (long long)npl * 32);
+  if (gx < 1) gx = 1;
+  if (gx > 4096) gx = 4096;
+  dim3 grid((unsigned)gx, ceil_div(CV, cvb));
+  colsum_bf16_kernel<<<grid, 256, cvb * 8 * sizeof(float), st>>>(x, out, M, C, cvb);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cast_f32_bf16_launch(const float* x, bf16* y, long long n, cudaStream_t st) {
+  DCPT_CHECK_ARG(n % 8 == 0, DCPT_E_SHAPE, "cast: element count %lld must be a multiple of 8", n);
+  cast_f32_bf16_kernel<<<(unsigned)ceil_div_ll(n / 8, 256), 256, 0, st>>>(x, y, n / 8);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int unshuffle_cast_launch(const float* x, bf16* y, int N, int H, int W, int C, cudaStream_t st) {
+  const long long nvec = (long long)N * H * W * 4 * (C / 8);
+  unshuffle_cast_kernel<<<(unsigned)ceil_div_ll(nvec, 256), 256, 0, st>>>(x, y, nvec, H, W, C);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int pack_weight_launch(const float* w, const float* row_scale, bf16* out, int O, int I, int mode, cudaStream_t st) {
+  const long long total = (long long)O * I;
+  pack_weight_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(w, row_scale, out, O, I, mode);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int pack_bias_launch(const float* bias, const float* scale, float* out, int O, int mode, cudaStream_t st) {
+  pack_bias_kernel<<<ceil_div(O, 256), 256, 0, st>>>(bias, scale, out, O, mode);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int wgrad_finish_resid_launch(const float* G, const float* w, const float* bias, const float* scale, const float* colsum,
+                              float* dw, float* dbias, float* dscale, int O, int I, cudaStream_t st) {
+  wgrad_finish_resid_kernel<<<ceil_div(O * 32, 256), 256, 0, st>>>(G, w, bias, scale, colsum, dw, dbias, dscale, O, I);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int wgrad_finish_perm_launch(const float* G, float* dw, int O, int I, int mode, cudaStream_t st) {
+  const long long total = (long long)O * I;
+  wgrad_finish_perm_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(G, dw, O, I, mode);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int grad_prepare_launch(const float* a, const float* b, float* out, bf16* out_bf16, float* colsum, int M, int C,
+                        cudaStream_t st) {
+  const int CV = C / 8, cvb = pick_cvb(CV), npl = 256 / cvb;
+  long long gx = ceil_div_ll(M, (long long)npl * 16);
+  if (gx < 1) gx = 1;
+  if (gx > 8192) gx = 8192;
+  dim3 grid((unsigned)gx, ceil_div(CV, cvb));
+  grad_prepare_kernel<<<grid, 256, cvb * 8 * sizeof(float), st>>>(a, b, out, out_bf16, colsum, M, C, cvb);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int axpy_launch(float* dst, const float* src, int n, cudaStream_t st) {
+  axpy_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dst, src, n);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,760 @@
+// Host-side orchestration of the NAFNet hot path and the C ABI (include/dcpt_ops.h).
+//
+// NAFBlock (reference basicsr/archs/nafnet_arch.py:83-186) is executed as
+//   LN1 -> [GEMM conv1 +bias] -> dw3x3+SimpleGate(+pool) -> SCA -> g*s -> [GEMM conv3 (beta folded) +bias +inp = y]
+//   -> LN2 -> [GEMM conv4 +bias, SimpleGate epilogue] -> [GEMM conv5 (gamma folded) +bias +y = out]
+// with fp32 residual stream (x, y, out), bf16 branch tensors, fp32 accumulation everywhere.
+// beta / gamma are folded into the packed bf16 weights (W' = diag(beta) W), so the residual
+// update is a plain epilogue add; their gradients are recovered from the wgrad GEMM of the
+// *unscaled* weight (see wgrad_finish_resid_kernel in misc.cu).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/dcpt_ops.h"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+// ------------------------------------------------------------------------------------
+// error state / device info
+// ------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void dcpt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int dcpt_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+namespace {
+
+// bump allocator over a caller-provided arena (base == nullptr: size computation only)
+struct Arena {
+  char* base;
+  size_t off;
+  explicit Arena(void* b) : base(static_cast<char*>(b)), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+  size_t size() const { return (off + 255) & ~(size_t)255; }
+};
+
+enum {  // NAFBlock parameter indices (named_parameters() order)
+  P_BETA = 0, P_GAMMA, P_C1W, P_C1B, P_C2W, P_C2B, P_C3W, P_C3B, P_SCAW, P_SCAB, P_C4W, P_C4B, P_C5W, P_C5B,
+  P_N1W, P_N1B, P_N2W, P_N2B
+};
+
+struct BlockPacked {
+  bf16 *w1, *w1t, *w3b, *w3bt, *w4p, *w4t, *w5g, *w5gt;
+  float *b3b, *b4p, *b5g;
+  BlockPacked(Arena& a, int C) {
+    const size_t cc = (size_t)C * C;
+    w1 = a.take<bf16>(2 * cc); w1t = a.take<bf16>(2 * cc);
+    w3b = a.take<bf16>(cc); w3bt = a.take<bf16>(cc);
+    w4p = a.take<bf16>(2 * cc); w4t = a.take<bf16>(2 * cc);
+    w5g = a.take<bf16>(cc); w5gt = a.take<bf16>(cc);
+    b3b = a.take<float>(C); b4p = a.take<float>(2 * C); b5g = a.take<float>(C);
+  }
+};
+
+struct BlockSaved {
+  bf16 *n1, *u, *g, *gs, *n2, *x4, *sg;
+  float *stats1, *stats2, *pool, *s, *y;
+  BlockSaved(Arena& a, int N, int H, int W, int C) {
+    const size_t M = (size_t)N * H * W;
+    n1 = a.take<bf16>(M * C); stats1 = a.take<float>(M * 2);
+    u = a.take<bf16>(M * 2 * C); g = a.take<bf16>(M * C);
+    pool = a.take<float>((size_t)N * C); s = a.take<float>((size_t)N * C);
+    gs = a.take<bf16>(M * C); y = a.take<float>(M * C);
+    n2 = a.take<bf16>(M * C); stats2 = a.take<float>(M * 2);
+    x4 = a.take<bf16>(M * 2 * C); sg = a.take<bf16>(M * C);
+  }
+};
+
+struct BlockWork {
+  float *G, *dy, *Sy, *ds, *t;
+  bf16 *dx4, *dn, *dyT, *dgs, *du2, *du;
+  BlockWork(Arena& a, int N, int H, int W, int C) {
+    const size_t M = (size_t)N * H * W;
+    G = a.take<float>((size_t)C * C);
+    dx4 = a.take<bf16>(M * 2 * C); dn = a.take<bf16>(M * C);
+    dy = a.take<float>(M * C); dyT = a.take<bf16>(M * C); Sy = a.take<float>(C);
+    dgs = a.take<bf16>(M * C); ds = a.take<float>((size_t)N * C); t = a.take<float>((size_t)N * C);
+    du2 = a.take<bf16>(M * 2 * C); du = a.take<bf16>(M * 2 * C);
+  }
+};
+
+GemmArgs gemm_args(int M, int N, int K, const bf16* A, int lda, const bf16* B, int ldb, int epi) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.splits = 1; g.epi = epi;
+  return g;
+}
+
+// wgrad: out[O, I] += dY[Mpx, O]^T * X[Mpx, I]   (both operands MN-major, split-K over pixels, fp32 atomics)
+int wgrad_gemm(const bf16* dY, int O, const bf16* X, int I, float* out, int Mpx, cudaStream_t st) {
+  GemmArgs g = gemm_args(O, I, Mpx, dY, O, X, I, EPI_ATOMIC);
+  g.a_mn = 1; g.b_mn = 1;
+  const int bn = I > 128 ? 256 : (I > 64 ? 128 : 64);
+  const int tiles = ceil_div(O, 128) * ceil_div(I, bn);
+  const int num_kb = ceil_div(Mpx, 64);
+  int splits = ceil_div(dcpt_num_sms(), tiles);
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  g.splits = splits;
+  g.ep.out_f32 = out; g.ep.ldo = I;
+  return gemm_launch(g, st);
+}
+
+int nafblock_pack_impl(const float* const* P, BlockPacked& pk, int C, cudaStream_t st) {
+  DCPT_TRY(pack_weight_launch(P[P_C1W], nullptr, pk.w1, 2 * C, C, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[P_C1W], nullptr, pk.w1t, 2 * C, C, PACK_T, st));
+  DCPT_TRY(pack_weight_launch(P[P_C3W], P[P_BETA], pk.w3b, C, C, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[P_C3W], P[P_BETA], pk.w3bt, C, C, PACK_T, st));
+  DCPT_TRY(pack_weight_launch(P[P_C4W], nullptr, pk.w4p, 2 * C, C, PACK_PAIR, st));
+  DCPT_TRY(pack_weight_launch(P[P_C4W], nullptr, pk.w4t, 2 * C, C, PACK_T, st));
+  DCPT_TRY(pack_weight_launch(P[P_C5W], P[P_GAMMA], pk.w5g, C, C, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[P_C5W], P[P_GAMMA], pk.w5gt, C, C, PACK_T, st));
+  DCPT_TRY(pack_bias_launch(P[P_C3B], P[P_BETA], pk.b3b, C, PACK_PLAIN, st));
+  DCPT_TRY(pack_bias_launch(P[P_C4B], nullptr, pk.b4p, 2 * C, PACK_PAIR, st));
+  DCPT_TRY(pack_bias_launch(P[P_C5B], P[P_GAMMA], pk.b5g, C, PACK_PLAIN, st));
+  return 0;
+}
+
+int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float* x, float* out, bf16* out_bf16,
+                      const BlockSaved& sv, int N, int H, int W, int C, cudaStream_t st) {
+  const int HW = H * W, M = N * HW;
+  constexpr float eps = 1e-6f;  // LayerNorm2d default (nafnet_arch.py:57)
+  // norm1 -> conv1 (+bias)
+  DCPT_TRY(ln_fwd_launch(x, P[P_N1W], P[P_N1B], sv.n1, sv.stats1, M, C, eps, st));
+  {
+    GemmArgs g = gemm_args(M, 2 * C, C, sv.n1, C, pk.w1, C, EPI_STORE);
+    g.ep.out_bf16 = sv.u; g.ep.ldo = 2 * C; g.ep.bias = P[P_C1B];
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // conv2 (dw 3x3) + SimpleGate, global average pool partial sums
+  DCPT_CUDA(cudaMemsetAsync(sv.pool, 0, (size_t)N * C * sizeof(float), st));
+  DCPT_TRY(dwgate_fwd_launch(sv.u, P[P_C2W], P[P_C2B], sv.g, sv.pool, N, H, W, C, st));
+  // sca, x * sca(x)
+  DCPT_TRY(sca_fwd_launch(sv.pool, P[P_SCAW], P[P_SCAB], sv.s, N, C, HW, st));
+  DCPT_TRY(scale_rows_launch(sv.g, sv.s, sv.gs, N, HW, C, st));
+  // conv3, y = inp + x*beta
+  {
+    GemmArgs g = gemm_args(M, C, C, sv.gs, C, pk.w3b, C, EPI_STORE);
+    g.ep.out_f32 = sv.y; g.ep.ldo = C; g.ep.bias = pk.b3b; g.ep.resid = x; g.ep.ldr = C;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // norm2 -> conv4 -> SimpleGate
+  DCPT_TRY(ln_fwd_launch(sv.y, P[P_N2W], P[P_N2B], sv.n2, sv.stats2, M, C, eps, st));
+  {
+    GemmArgs g = gemm_args(M, 2 * C, C, sv.n2, C, pk.w4p, C, EPI_GATE);
+    g.ep.out_bf16 = sv.x4; g.ep.ldo = 2 * C; g.ep.out2 = sv.sg; g.ep.ldo2 = C; g.ep.C = C; g.ep.bias = pk.b4p;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // conv5, out = y + x*gamma
+  {
+    GemmArgs g = gemm_args(M, C, C, sv.sg, C, pk.w5g, C, EPI_STORE);
+    g.ep.out_f32 = out; g.ep.out_bf16 = out_bf16; g.ep.ldo = C; g.ep.bias = pk.b5g; g.ep.resid = sv.y; g.ep.ldr = C;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  return 0;
+}
+
+int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockSaved& sv, const float* x, const float* dout,
+                      const bf16* doutT, const float* Sout, float* dx, bf16* dxT, float* Sx, float* const* G, const BlockWork& wk,
+                      int N, int H, int W, int C, cudaStream_t st) {
+  const int HW = H * W, M = N * HW;
+  const size_t cc = (size_t)C * C;
+  // ---- conv5 (gamma folded): wgrad, dgamma, dbias; dgrad fused with SimpleGate backward ----
+  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), st));
+  DCPT_TRY(wgrad_gemm(doutT, C, sv.sg, C, wk.G, M, st));
+  DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C5W], P[P_C5B], P[P_GAMMA], Sout, G[P_C5W], G[P_C5B], G[P_GAMMA], C, C, st));
+  {
+    GemmArgs g = gemm_args(M, C, C, doutT, C, pk.w5gt, C, EPI_GATE_BWD);
+    g.ep.out_bf16 = wk.dx4; g.ep.ldo = 2 * C; g.ep.aux = sv.x4; g.ep.ldaux = 2 * C; g.ep.C = C;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // ---- conv4: dbias, wgrad, dgrad ----
+  DCPT_TRY(colsum_bf16_launch(wk.dx4, G[P_C4B], M, 2 * C, st));
+  DCPT_TRY(wgrad_gemm(wk.dx4, 2 * C, sv.n2, C, G[P_C4W], M, st));
+  {
+    GemmArgs g = gemm_args(M, C, 2 * C, wk.dx4, 2 * C, pk.w4t, 2 * C, EPI_STORE);
+    g.ep.out_bf16 = wk.dn; g.ep.ldo = C;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // ---- norm2 backward + residual: dy = dout + LN'(dn2) ----
+  DCPT_CUDA(cudaMemsetAsync(wk.Sy, 0, C * sizeof(float), st));
+  DCPT_TRY(ln_bwd_launch(wk.dn, sv.y, sv.stats2, P[P_N2W], dout, wk.dy, wk.dyT, G[P_N2W], G[P_N2B], wk.Sy, M, C, st));
+  // ---- conv3 (beta folded) ----
+  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), st));
+  DCPT_TRY(wgrad_gemm(wk.dyT, C, sv.gs, C, wk.G, M, st));
+  DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C3W], P[P_C3B], P[P_BETA], wk.Sy, G[P_C3W], G[P_C3B], G[P_BETA], C, C, st));
+  {
+    GemmArgs g = gemm_args(M, C, C, wk.dyT, C, pk.w3bt, C, EPI_STORE);
+    g.ep.out_bf16 = wk.dgs; g.ep.ldo = C;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // ---- SCA backward ----
+  DCPT_CUDA(cudaMemsetAsync(wk.ds, 0, (size_t)N * C * sizeof(float), st));
+  DCPT_TRY(sca_ds_reduce_launch(wk.dgs, sv.g, wk.ds, N, HW, C, st));
+  DCPT_TRY(sca_bwd_launch(wk.ds, sv.pool, P[P_SCAW], wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st));
+  // ---- SimpleGate + depthwise conv backward ----
+  DCPT_TRY(dwgate_bwd_a_launch(wk.dgs, sv.s, wk.t, sv.u, P[P_C2W], P[P_C2B], wk.du2, G[P_C2W], G[P_C2B], N, H, W, C, st));
+  DCPT_TRY(dwconv_bwd_data_launch(wk.du2, P[P_C2W], wk.du, G[P_C1B], N, H, W, 2 * C, st));
+  // ---- conv1 ----
+  DCPT_TRY(wgrad_gemm(wk.du, 2 * C, sv.n1, C, G[P_C1W], M, st));
+  {
+    GemmArgs g = gemm_args(M, C, 2 * C, wk.du, 2 * C, pk.w1t, 2 * C, EPI_STORE);
+    g.ep.out_bf16 = wk.dn; g.ep.ldo = C;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // ---- norm1 backward + residual: dx = dy + LN'(dn1) ----
+  DCPT_TRY(ln_bwd_launch(wk.dn, x, sv.stats1, P[P_N1W], wk.dy, dx, dxT, G[P_N1W], G[P_N1B], Sx, M, C, st));
+  return 0;
+}
+
+int check_block_shape(int N, int H, int W, int C) {
+  DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "nafblock: bad spatial shape N=%d H=%d W=%d", N, H, W);
+  DCPT_CHECK_ARG(C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "nafblock: C=%d must be a multiple of 8 in [8, 1024]", C);
+  DCPT_CHECK_ARG((long long)N * H * W * 2 * C < (1ll << 31), DCPT_E_SHAPE, "nafblock: tensor too large for 32-bit pixel index");
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// NAFNetBaseline plan
+// ------------------------------------------------------------------------------------
+struct dcpt_nafnet_plan {
+  int img_channel, width, middle_blk_num;
+  std::vector<int> enc, dec;
+  struct ParamInfo { int dims[4]; long long numel; };
+  std::vector<ParamInfo> params;
+  struct Blk { int pidx; int C; int level; };  // level: resolution level (0 = full res)
+  std::vector<std::vector<Blk>> enc_blks, dec_blks;
+  std::vector<Blk> mid_blks;
+  std::vector<int> up_pidx, down_pidx;  // ups.i.0.weight ; downs.i.weight (bias = +1)
+  int mid_C;
+};
+
+namespace {
+
+void add_param(dcpt_nafnet_plan* p, int d0, int d1 = 1, int d2 = 1, int d3 = 1) {
+  dcpt_nafnet_plan::ParamInfo pi;
+  pi.dims[0] = d0; pi.dims[1] = d1; pi.dims[2] = d2; pi.dims[3] = d3;
+  pi.numel = (long long)d0 * d1 * d2 * d3;
+  p->params.push_back(pi);
+}
+
+int add_block_params(dcpt_nafnet_plan* p, int c) {
+  const int idx = (int)p->params.size();
+  add_param(p, 1, c, 1, 1); add_param(p, 1, c, 1, 1);                // beta, gamma
+  add_param(p, 2 * c, c, 1, 1); add_param(p, 2 * c);                 // conv1
+  add_param(p, 2 * c, 1, 3, 3); add_param(p, 2 * c);                 // conv2
+  add_param(p, c, c, 1, 1); add_param(p, c);                         // conv3
+  add_param(p, c, c, 1, 1); add_param(p, c);                         // sca.1
+  add_param(p, 2 * c, c, 1, 1); add_param(p, 2 * c);                 // conv4
+  add_param(p, c, c, 1, 1); add_param(p, c);                         // conv5
+  add_param(p, c); add_param(p, c); add_param(p, c); add_param(p, c);  // norm1, norm2
+  return idx;
+}
+
+// Device-side layout of everything the forward keeps for the backward.
+struct NetSaved {
+  float* x0;                                   // intro output
+  std::vector<std::vector<BlockSaved>> enc_sv, dec_sv;
+  std::vector<std::vector<float*>> enc_out, dec_out;  // block outputs (fp32)
+  std::vector<BlockSaved> mid_sv;
+  std::vector<float*> mid_out;
+  std::vector<bf16*> xu;                       // unshuffled down-conv inputs (bf16 [M/4, 4C])
+  std::vector<float*> xd;                      // down-conv outputs
+  std::vector<bf16*> up_in;                    // bf16 mirror of each up-conv input
+  std::vector<float*> xup;                     // up-conv outputs (after skip add)
+  NetSaved(const dcpt_nafnet_plan* p, Arena& a, int N, int H, int W) {
+    int C = p->width, h = H, w = W;
+    x0 = a.take<float>((size_t)N * h * w * C);
+    const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
+    enc_sv.resize(ne); enc_out.resize(ne);
+    for (int i = 0; i < ne; ++i) {
+      for (int j = 0; j < p->enc[i]; ++j) {
+        enc_sv[i].emplace_back(a, N, h, w, C);
+        enc_out[i].push_back(a.take<float>((size_t)N * h * w * C));
+      }
+      xu.push_back(a.take<bf16>((size_t)N * h * w * C));
+      h /= 2; w /= 2; C *= 2;
+      xd.push_back(a.take<float>((size_t)N * h * w * C));
+    }
+    for (int j = 0; j < p->middle_blk_num; ++j) {
+      mid_sv.emplace_back(a, N, h, w, C);
+      mid_out.push_back(a.take<float>((size_t)N * h * w * C));
+    }
+    dec_sv.resize(nd); dec_out.resize(nd);
+    for (int i = 0; i < nd; ++i) {
+      up_in.push_back(a.take<bf16>((size_t)N * h * w * C));
+      h *= 2; w *= 2; C /= 2;
+      xup.push_back(a.take<float>((size_t)N * h * w * C));
+      for (int j = 0; j < p->dec[i]; ++j) {
+        dec_sv[i].emplace_back(a, N, h, w, C);
+        dec_out[i].push_back(a.take<float>((size_t)N * h * w * C));
+      }
+    }
+  }
+};
+
+struct NetPacked {
+  std::vector<std::vector<BlockPacked>> enc_pk, dec_pk;
+  std::vector<BlockPacked> mid_pk;
+  std::vector<bf16*> down, down_t, up, up_t;
+  NetPacked(const dcpt_nafnet_plan* p, Arena& a) {
+    int C = p->width;
+    const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
+    enc_pk.resize(ne); dec_pk.resize(nd);
+    for (int i = 0; i < ne; ++i) {
+      for (int j = 0; j < p->enc[i]; ++j) enc_pk[i].emplace_back(a, C);
+      down.push_back(a.take<bf16>((size_t)2 * C * 4 * C));
+      down_t.push_back(a.take<bf16>((size_t)2 * C * 4 * C));
+      C *= 2;
+    }
+    for (int j = 0; j < p->middle_blk_num; ++j) mid_pk.emplace_back(a, C);
+    for (int i = 0; i < nd; ++i) {
+      up.push_back(a.take<bf16>((size_t)2 * C * C));
+      up_t.push_back(a.take<bf16>((size_t)2 * C * C));
+      C /= 2;
+      for (int j = 0; j < p->dec[i]; ++j) dec_pk[i].emplace_back(a, C);
+    }
+  }
+};
+
+struct NetWork {
+  char* blk_base;   // BlockWork arena (sized for the largest level)
+  size_t blk_bytes;
+  float* dxa; float* dxb; bf16* dta; bf16* dtb; float* Sa; float* Sb;  // ping-pong gradient stream
+  std::vector<float*> dskip;                                          // per encoder level
+  bf16* dconv;      // unshuffled up-conv output gradient
+  float* G;         // wgrad scratch for up/down/ending convs
+  NetWork(const dcpt_nafnet_plan* p, Arena& a, int N, int H, int W) {
+    int C = p->width, h = H, w = W;
+    size_t max_act = 0, max_blk = 0, max_g = (size_t)27 * C;
+    const int ne = (int)p->enc.size();
+    std::vector<size_t> lvl_act;
+    int maxC = C;
+    for (int i = 0; i <= ne; ++i) {
+      const size_t act = (size_t)N * h * w * C;
+      lvl_act.push_back(act);
+      if (act > max_act) max_act = act;
+      Arena probe(nullptr);
+      BlockWork bw(probe, N, h, w, C);
+      (void)bw;
+      if (probe.size() > max_blk) max_blk = probe.size();
+      if (i < ne) {
+        const size_t g = (size_t)2 * C * 4 * C;  // down weight [2C, 4C]; up weight of the mirrored level has the same count
+        if (g > max_g) max_g = g;
+        h /= 2; w /= 2; C *= 2;
+        if (C > maxC) maxC = C;
+      }
+    }
+    blk_bytes = max_blk;
+    blk_base = a.take<char>(max_blk);
+    dxa = a.take<float>(max_act); dxb = a.take<float>(max_act);
+    dta = a.take<bf16>(max_act); dtb = a.take<bf16>(max_act);
+    Sa = a.take<float>(maxC); Sb = a.take<float>(maxC);
+    for (int i = 0; i < ne; ++i) dskip.push_back(a.take<float>(lvl_act[i]));
+    dconv = a.take<bf16>(max_act);
+    G = a.take<float>(max_g);
+  }
+};
+
+int check_net_shape(const dcpt_nafnet_plan* p, int N, int H, int W) {
+  const int f = 1 << (int)p->enc.size();
+  DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % f == 0 && W % f == 0, DCPT_E_SHAPE,
+                 "nafnet: H=%d W=%d must be positive multiples of %d (pad with SRModel.pre_test's window_size)", H, W, f);
+  DCPT_CHECK_ARG(p->img_channel == 3, DCPT_E_UNSUPPORTED, "nafnet: img_channel=%d (only 3 is built)", p->img_channel);
+  DCPT_CHECK_ARG((long long)N * H * W * 2 * p->width < (1ll << 31), DCPT_E_SHAPE, "nafnet: batch too large for 32-bit pixel index");
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+int dcpt_abi_version(void) { return DCPT_ABI_VERSION; }
+const char* dcpt_last_error(void) { return g_err; }
+
+int dcpt_layernorm2d_fwd(const float* x, const float* weight, const float* bias, void* out_bf16, float* stats, int M, int C,
+                         float eps, dcpt_stream_t stream) {
+  return ln_fwd_launch(x, weight, bias, static_cast<bf16*>(out_bf16), stats, M, C, eps, static_cast<cudaStream_t>(stream));
+}
+
+int dcpt_layernorm2d_bwd(const void* dn_bf16, const float* x, const float* stats, const float* weight, const float* dres,
+                         float* dx, void* dx_bf16, float* dweight, float* dbias, float* colsum, int M, int C,
+                         dcpt_stream_t stream) {
+  return ln_bwd_launch(static_cast<const bf16*>(dn_bf16), x, stats, weight, dres, dx, static_cast<bf16*>(dx_bf16), dweight, dbias,
+                       colsum, M, C, static_cast<cudaStream_t>(stream));
+}
+
+int dcpt_gemm_ex(const dcpt_gemm_desc* d, int impl, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(d != nullptr, DCPT_E_ARG, "gemm_ex: null descriptor");
+  GemmArgs g = gemm_args(d->M, d->N, d->K, static_cast<const bf16*>(d->A), d->lda, static_cast<const bf16*>(d->B), d->ldb,
+                         d->epilogue);
+  g.a_mn = d->a_mn; g.b_mn = d->b_mn; g.splits = d->splits < 1 ? 1 : d->splits;
+  g.ep.out_f32 = d->out_f32; g.ep.out_bf16 = static_cast<bf16*>(d->out_bf16); g.ep.ldo = d->ldo;
+  g.ep.bias = d->bias; g.ep.resid = d->resid; g.ep.ldr = d->ldr;
+  g.ep.out2 = static_cast<bf16*>(d->out2_bf16); g.ep.ldo2 = d->ldo2;
+  g.ep.aux = static_cast<const bf16*>(d->aux_bf16); g.ep.ldaux = d->ldaux;
+  g.ep.C = d->C; g.ep.H = d->H; g.ep.W = d->W; g.ep.Cseg = d->Cseg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return impl == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
+}
+
+int dcpt_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, float* out_f32,
+                   void* out_bf16, int ldo, const float* bias, const float* resid, int splits, int accumulate, int impl,
+                   dcpt_stream_t stream) {
+  dcpt_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = M; d.N = N; d.K = K; d.A = A; d.lda = lda; d.a_mn = a_mn; d.B = B; d.ldb = ldb; d.b_mn = b_mn;
+  d.splits = splits; d.epilogue = (splits > 1 || accumulate) ? EPI_ATOMIC : EPI_STORE;
+  d.out_f32 = out_f32; d.out_bf16 = out_bf16; d.ldo = ldo; d.bias = bias; d.resid = resid; d.ldr = ldo;
+  return dcpt_gemm_ex(&d, impl, stream);
+}
+
+int dcpt_dwconv3x3_gate_fwd(const void* u_bf16, const float* weight, const float* bias, void* g_bf16, float* pool, int N, int H,
+                            int W, int C, dcpt_stream_t stream) {
+  return dwgate_fwd_launch(static_cast<const bf16*>(u_bf16), weight, bias, static_cast<bf16*>(g_bf16), pool, N, H, W, C,
+                           static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------- NAFBlock ---------------------------------------
+size_t dcpt_nafblock_packed_bytes(int C) {
+  Arena a(nullptr);
+  BlockPacked pk(a, C);
+  (void)pk;
+  return a.size();
+}
+size_t dcpt_nafblock_saved_bytes(int N, int H, int W, int C) {
+  Arena a(nullptr);
+  BlockSaved sv(a, N, H, W, C);
+  (void)sv;
+  return a.size();
+}
+size_t dcpt_nafblock_workspace_bytes(int N, int H, int W, int C) {
+  Arena a(nullptr);
+  BlockWork wk(a, N, H, W, C);
+  (void)wk;
+  return a.size();
+}
+
+int dcpt_nafblock_pack(const float* const* host_params, void* packed, int C, dcpt_stream_t stream) {
+  DCPT_TRY(check_block_shape(1, 1, 1, C));
+  Arena a(packed);
+  BlockPacked pk(a, C);
+  return nafblock_pack_impl(host_params, pk, C, static_cast<cudaStream_t>(stream));
+}
+
+int dcpt_nafblock_fwd(const float* const* host_params, const void* packed, const float* x, float* out, void* out_bf16, void* saved,
+                      int N, int H, int W, int C, dcpt_stream_t stream) {
+  DCPT_TRY(check_block_shape(N, H, W, C));
+  Arena ap(const_cast<void*>(packed));
+  BlockPacked pk(ap, C);
+  Arena as(saved);
+  BlockSaved sv(as, N, H, W, C);
+  return nafblock_fwd_impl(host_params, pk, x, out, static_cast<bf16*>(out_bf16), sv, N, H, W, C, static_cast<cudaStream_t>(stream));
+}
+
+int dcpt_nafblock_bwd(const float* const* host_params, const void* packed, const void* saved, const float* x, const float* dout,
+                      const void* dout_bf16, const float* dout_colsum, float* dx, void* dx_bf16, float* dx_colsum,
+                      float* const* host_grads, void* workspace, int N, int H, int W, int C, dcpt_stream_t stream) {
+  DCPT_TRY(check_block_shape(N, H, W, C));
+  Arena ap(const_cast<void*>(packed));
+  BlockPacked pk(ap, C);
+  Arena as(const_cast<void*>(saved));
+  BlockSaved sv(as, N, H, W, C);
+  Arena aw(workspace);
+  BlockWork wk(aw, N, H, W, C);
+  return nafblock_bwd_impl(host_params, pk, sv, x, dout, static_cast<const bf16*>(dout_bf16), dout_colsum, dx,
+                           static_cast<bf16*>(dx_bf16), dx_colsum, host_grads, wk, N, H, W, C, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------- NAFNetBaseline ---------------------------------
+dcpt_nafnet_plan* dcpt_nafnet_create(int img_channel, int width, int middle_blk_num, const int* enc_blk_nums, int n_enc,
+                                     const int* dec_blk_nums, int n_dec) {
+  if (img_channel <= 0 || width < 8 || width % 8 != 0 || middle_blk_num < 0 || n_enc < 0 || n_dec != n_enc) {
+    dcpt_set_error("nafnet_create: need width %% 8 == 0 (>= 8) and len(enc_blk_nums) == len(dec_blk_nums) (width=%d n_enc=%d n_dec=%d)",
+                   width, n_enc, n_dec);
+    return nullptr;
+  }
+  if ((long long)width << n_enc > 1024) {
+    dcpt_set_error("nafnet_create: bottleneck width %lld exceeds 1024", (long long)width << n_enc);
+    return nullptr;
+  }
+  dcpt_nafnet_plan* p = new dcpt_nafnet_plan();
+  p->img_channel = img_channel; p->width = width; p->middle_blk_num = middle_blk_num;
+  p->enc.assign(enc_blk_nums, enc_blk_nums + n_enc);
+  p->dec.assign(dec_blk_nums, dec_blk_nums + n_dec);
+  // named_parameters() order of the reference module (nafnet_arch.py:202-248)
+  add_param(p, width, img_channel, 3, 3); add_param(p, width);       // intro
+  add_param(p, img_channel, width, 3, 3); add_param(p, img_channel); // ending
+  int C = width;
+  p->enc_blks.resize(n_enc);
+  for (int i = 0; i < n_enc; ++i) {
+    for (int j = 0; j < p->enc[i]; ++j) p->enc_blks[i].push_back({add_block_params(p, C), C, i});
+    C *= 2;
+  }
+  p->mid_C = C;
+  for (int j = 0; j < middle_blk_num; ++j) p->mid_blks.push_back({add_block_params(p, C), C, n_enc});
+  for (int i = 0; i < n_dec; ++i) {
+    p->up_pidx.push_back((int)p->params.size());
+    add_param(p, 2 * C, C, 1, 1);
+    C /= 2;
+  }
+  C = width;
+  for (int i = 0; i < n_enc; ++i) {
+    p->down_pidx.push_back((int)p->params.size());
+    add_param(p, 2 * C, C, 2, 2); add_param(p, 2 * C);
+    C *= 2;
+  }
+  p->dec_blks.resize(n_dec);
+  for (int i = 0; i < n_dec; ++i) {
+    C /= 2;
+    for (int j = 0; j < p->dec[i]; ++j) p->dec_blks[i].push_back({add_block_params(p, C), C, n_enc - 1 - i});
+  }
+  return p;
+}
+
+void dcpt_nafnet_destroy(dcpt_nafnet_plan* plan) { delete plan; }
+int dcpt_nafnet_num_params(const dcpt_nafnet_plan* plan) { return (int)plan->params.size(); }
+long long dcpt_nafnet_param_shape(const dcpt_nafnet_plan* plan, int i, int dims[4]) {
+  if (i < 0 || i >= (int)plan->params.size()) return -1;
+  for (int k = 0; k < 4; ++k) dims[k] = plan->params[i].dims[k];
+  return plan->params[i].numel;
+}
+size_t dcpt_nafnet_packed_bytes(const dcpt_nafnet_plan* plan) {
+  Arena a(nullptr);
+  NetPacked pk(plan, a);
+  return a.size();
+}
+size_t dcpt_nafnet_saved_bytes(const dcpt_nafnet_plan* plan, int N, int H, int W) {
+  Arena a(nullptr);
+  NetSaved sv(plan, a, N, H, W);
+  return a.size();
+}
+size_t dcpt_nafnet_workspace_bytes(const dcpt_nafnet_plan* plan, int N, int H, int W) {
+  Arena a(nullptr);
+  NetWork wk(plan, a, N, H, W);
+  return a.size();
+}
+
+int dcpt_nafnet_pack(const dcpt_nafnet_plan* p, const float* const* P, void* packed, dcpt_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(packed);
+  NetPacked pk(p, a);
+  const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
+  int C = p->width;
+  for (int i = 0; i < ne; ++i) {
+    for (int j = 0; j < p->enc[i]; ++j) DCPT_TRY(nafblock_pack_impl(P + p->enc_blks[i][j].pidx, pk.enc_pk[i][j], C, st));
+    DCPT_TRY(pack_weight_launch(P[p->down_pidx[i]], nullptr, pk.down[i], 2 * C, 4 * C, PACK_DOWN, st));
+    DCPT_TRY(pack_weight_launch(P[p->down_pidx[i]], nullptr, pk.down_t[i], 2 * C, 4 * C, PACK_DOWN_T, st));
+    C *= 2;
+  }
+  for (int j = 0; j < p->middle_blk_num; ++j) DCPT_TRY(nafblock_pack_impl(P + p->mid_blks[j].pidx, pk.mid_pk[j], C, st));
+  for (int i = 0; i < nd; ++i) {
+    DCPT_TRY(pack_weight_launch(P[p->up_pidx[i]], nullptr, pk.up[i], 2 * C, C, PACK_UP, st));
+    DCPT_TRY(pack_weight_launch(P[p->up_pidx[i]], nullptr, pk.up_t[i], 2 * C, C, PACK_UP_T, st));
+    C /= 2;
+    for (int j = 0; j < p->dec[i]; ++j) DCPT_TRY(nafblock_pack_impl(P + p->dec_blks[i][j].pidx, pk.dec_pk[i][j], C, st));
+  }
+  return 0;
+}
+
+int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void* packed, const float* inp, float* out, void* saved,
+                    float* const* host_feats, int hook, int N, int H, int W, dcpt_stream_t stream) {
+  DCPT_TRY(check_net_shape(p, N, H, W));
+  DCPT_CHECK_ARG(hook || out != nullptr, DCPT_E_ARG, "nafnet_fwd: out is NULL but hook == 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena ap(const_cast<void*>(packed));
+  NetPacked pk(p, ap);
+  Arena as(saved);
+  NetSaved sv(p, as, N, H, W);
+  const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
+  int C = p->width, h = H, w = W;
+
+  // intro (nafnet_arch.py:252)
+  DCPT_TRY(conv3x3_img_to_feat_launch(inp, P[0], P[1], 0, sv.x0, nullptr, nullptr, N, h, w, C, st));
+  const float* x = sv.x0;
+  // encoders + downs (:256-259)
+  for (int i = 0; i < ne; ++i) {
+    for (int j = 0; j < p->enc[i]; ++j) {
+      DCPT_TRY(nafblock_fwd_impl(P + p->enc_blks[i][j].pidx, pk.enc_pk[i][j], x, sv.enc_out[i][j], nullptr, sv.enc_sv[i][j], N, h,
+                                 w, C, st));
+      x = sv.enc_out[i][j];
+    }
+    DCPT_TRY(unshuffle_cast_launch(x, sv.xu[i], N, h / 2, w / 2, C, st));
+    h /= 2; w /= 2;
+    GemmArgs g = gemm_args(N * h * w, 2 * C, 4 * C, sv.xu[i], 4 * C, pk.down[i], 4 * C, EPI_STORE);
+    g.ep.out_f32 = sv.xd[i]; g.ep.ldo = 2 * C; g.ep.bias = P[p->down_pidx[i] + 1];
+    if (i == ne - 1 && p->middle_blk_num == 0 && nd > 0) g.ep.out_bf16 = sv.up_in[0];
+    DCPT_TRY(gemm_launch(g, st));
+    C *= 2;
+    x = sv.xd[i];
+  }
+  // middle (:261)
+  for (int j = 0; j < p->middle_blk_num; ++j) {
+    bf16* mirror = (j == p->middle_blk_num - 1 && nd > 0) ? sv.up_in[0] : nullptr;
+    DCPT_TRY(nafblock_fwd_impl(P + p->mid_blks[j].pidx, pk.mid_pk[j], x, sv.mid_out[j], mirror, sv.mid_sv[j], N, h, w, C, st));
+    x = sv.mid_out[j];
+  }
+  if (ne == 0 && p->middle_blk_num == 0 && nd > 0) { dcpt_set_error("nafnet_fwd: degenerate network"); return DCPT_E_UNSUPPORTED; }
+  // ups + skip + decoders (:263-267)
+  for (int i = 0; i < nd; ++i) {
+    const float* skip = p->enc[ne - 1 - i] > 0 ? sv.enc_out[ne - 1 - i].back() : (ne - 1 - i > 0 ? sv.xd[ne - 2 - i] : sv.x0);
+    GemmArgs g = gemm_args(N * h * w, 2 * C, C, sv.up_in[i], C, pk.up[i], C, EPI_PIXSHUF);
+    g.ep.out_f32 = sv.xup[i]; g.ep.resid = skip; g.ep.H = h; g.ep.W = w; g.ep.Cseg = C / 2;
+    if (p->dec[i] == 0 && i + 1 < nd) g.ep.out_bf16 = sv.up_in[i + 1];
+    DCPT_TRY(gemm_launch(g, st));
+    h *= 2; w *= 2; C /= 2;
+    x = sv.xup[i];
+    for (int j = 0; j < p->dec[i]; ++j) {
+      bf16* mirror = (j == p->dec[i] - 1 && i + 1 < nd) ? sv.up_in[i + 1] : nullptr;
+      DCPT_TRY(nafblock_fwd_impl(P + p->dec_blks[i][j].pidx, pk.dec_pk[i][j], x, sv.dec_out[i][j], mirror, sv.dec_sv[i][j], N, h, w,
+                                 C, st));
+      x = sv.dec_out[i][j];
+    }
+    if (host_feats && host_feats[i])
+      DCPT_CUDA(cudaMemcpyAsync(host_feats[i], x, (size_t)N * h * w * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  // ending + global residual (:271-272)
+  if (!hook) DCPT_TRY(conv3x3_feat_to_img_launch(x, P[2], P[3], inp, out, N, h, w, C, st));
+  return 0;
+}
+
+int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void* packed, const void* saved, const float* inp,
+                    const float* dout, const float* const* host_dfeats, float* const* G, void* workspace, int N, int H, int W,
+                    dcpt_stream_t stream) {
+  DCPT_TRY(check_net_shape(p, N, H, W));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena ap(const_cast<void*>(packed));
+  NetPacked pk(p, ap);
+  Arena as(const_cast<void*>(saved));
+  NetSaved sv(p, as, N, H, W);
+  Arena aw(workspace);
+  NetWork wk(p, aw, N, H, W);
+  const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
+
+  // Gradient stream: d(loss)/d(current residual tensor) as fp32, its bf16 mirror (GEMM operand) and its
+  // column sums (bias / beta / gamma gradients).  Two slots, ping-pong.
+  struct Slot { float* f; bf16* t; float* s; };
+  Slot slot[2] = {{wk.dxa, wk.dta, wk.Sa}, {wk.dxb, wk.dtb, wk.Sb}};
+  int ci = 0;
+  bool have = false;
+#define CUR slot[ci]
+#define NXT slot[ci ^ 1]
+
+  int C = p->width, h = H, w = W;  // the last decoder level runs at full resolution (n_enc == n_dec)
+  const float* x_last = nd > 0 ? (p->dec[nd - 1] > 0 ? sv.dec_out[nd - 1].back() : sv.xup[nd - 1])
+                               : (p->middle_blk_num > 0 ? sv.mid_out.back() : sv.x0);
+  if (dout) {
+    // ending conv: wgrad, bias grad, dgrad (nafnet_arch.py:271)
+    DCPT_CUDA(cudaMemsetAsync(wk.G, 0, (size_t)27 * C * sizeof(float), st));
+    DCPT_TRY(conv3x3_small_wgrad_launch(x_last, dout, wk.G, G[3], 1, N, h, w, C, st));
+    DCPT_TRY(wgrad_finish_perm_launch(wk.G, G[2], C, 27, FIN_CN_TO_C3, st));
+    DCPT_CUDA(cudaMemsetAsync(CUR.s, 0, C * sizeof(float), st));
+    DCPT_TRY(conv3x3_img_to_feat_launch(dout, P[2], nullptr, 1, CUR.f, CUR.t, CUR.s, N, h, w, C, st));
+    have = true;
+  }
+  auto block_bwd = [&](const dcpt_nafnet_plan::Blk& b, const BlockPacked& bpk, const BlockSaved& bsv, const float* x, int hh,
+                       int ww) -> int {
+    DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient reaches a block (dout and dfeats all NULL?)");
+    Arena a(wk.blk_base);
+    BlockWork bw(a, N, hh, ww, b.C);
+    DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, b.C * sizeof(float), st));
+    DCPT_TRY(nafblock_bwd_impl(P + b.pidx, bpk, bsv, x, CUR.f, CUR.t, CUR.s, NXT.f, NXT.t, NXT.s, G + b.pidx, bw, N, hh, ww, b.C, st));
+    ci ^= 1;
+    return 0;
+  };
+
+  // ---------------- decoders (reverse) ----------------
+  for (int i = nd - 1; i >= 0; --i) {
+    const float* ext = host_dfeats ? host_dfeats[i] : nullptr;
+    if (ext) {  // gradient injected by the DCPT head into this decoder level's output
+      DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, C * sizeof(float), st));
+      DCPT_TRY(grad_prepare_launch(have ? CUR.f : nullptr, ext, NXT.f, NXT.t, NXT.s, N * h * w, C, st));
+      ci ^= 1;
+      have = true;
+    }
+    DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient at decoder level %d", i);
+    for (int j = p->dec[i] - 1; j >= 0; --j)
+      DCPT_TRY(block_bwd(p->dec_blks[i][j], pk.dec_pk[i][j], sv.dec_sv[i][j], j > 0 ? sv.dec_out[i][j - 1] : sv.xup[i], h, w));
+    // CUR = d(xup_i): it is also the gradient of the encoder skip (x = up(x) + enc_skip, :264-265)
+    const int lvl = ne - 1 - i;
+    DCPT_CUDA(cudaMemcpyAsync(wk.dskip[lvl], CUR.f, (size_t)N * h * w * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // up conv backward (1x1, no bias, + PixelShuffle(2))
+    const int Cin = 2 * C, hin = h / 2, win = w / 2, Min = N * hin * win;
+    DCPT_TRY(unshuffle_cast_launch(CUR.f, wk.dconv, N, hin, win, C, st));  // [Min, 2*Cin] in packed column order
+    DCPT_CUDA(cudaMemsetAsync(wk.G, 0, (size_t)2 * Cin * Cin * sizeof(float), st));
+    DCPT_TRY(wgrad_gemm(wk.dconv, 2 * Cin, sv.up_in[i], Cin, wk.G, Min, st));
+    DCPT_TRY(wgrad_finish_perm_launch(wk.G, G[p->up_pidx[i]], 2 * Cin, Cin, FIN_UP, st));
+    {
+      GemmArgs g = gemm_args(Min, Cin, 2 * Cin, wk.dconv, 2 * Cin, pk.up_t[i], 2 * Cin, EPI_STORE);
+      g.ep.out_f32 = NXT.f; g.ep.out_bf16 = NXT.t; g.ep.ldo = Cin;
+      DCPT_TRY(gemm_launch(g, st));
+      DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, Cin * sizeof(float), st));
+      DCPT_TRY(grad_prepare_launch(NXT.f, nullptr, nullptr, nullptr, NXT.s, Min, Cin, st));
+      ci ^= 1;
+    }
+    h = hin; w = win; C = Cin;
+  }
+  // ---------------- middle (reverse) ----------------
+  for (int j = p->middle_blk_num - 1; j >= 0; --j)
+    DCPT_TRY(block_bwd(p->mid_blks[j], pk.mid_pk[j], sv.mid_sv[j], j > 0 ? sv.mid_out[j - 1] : (ne > 0 ? sv.xd[ne - 1] : sv.x0), h, w));
+  // ---------------- encoders (reverse) ----------------
+  for (int i = ne - 1; i >= 0; --i) {
+    DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient at encoder level %d", i);
+    // CUR = d(xd_i) [N, h, w, C]; down conv (2x2 stride 2, C/2 -> C, bias) backward (:230, :259)
+    const int Cl = C / 2, hl = h * 2, wl = w * 2, Mh = N * h * w;
+    DCPT_TRY(axpy_launch(G[p->down_pidx[i] + 1], CUR.s, C, st));
+    DCPT_CUDA(cudaMemsetAsync(wk.G, 0, (size_t)C * 4 * Cl * sizeof(float), st));
+    DCPT_TRY(wgrad_gemm(CUR.t, C, sv.xu[i], 4 * Cl, wk.G, Mh, st));
+    DCPT_TRY(wgrad_finish_perm_launch(wk.G, G[p->down_pidx[i]], C, 4 * Cl, FIN_DOWN, st));
+    {
+      GemmArgs g = gemm_args(Mh, 4 * Cl, C, CUR.t, C, pk.down_t[i], C, EPI_PIXSHUF);
+      g.ep.out_f32 = NXT.f; g.ep.out_bf16 = NXT.t; g.ep.resid = wk.dskip[i];  // + gradient of the decoder skip
+      g.ep.H = h; g.ep.W = w; g.ep.Cseg = Cl;
+      DCPT_TRY(gemm_launch(g, st));
+      DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, Cl * sizeof(float), st));
+      DCPT_TRY(grad_prepare_launch(NXT.f, nullptr, nullptr, nullptr, NXT.s, N * hl * wl, Cl, st));
+      ci ^= 1;
+    }
+    h = hl; w = wl; C = Cl;
+    for (int j = p->enc[i] - 1; j >= 0; --j)
+      DCPT_TRY(block_bwd(p->enc_blks[i][j], pk.enc_pk[i][j], sv.enc_sv[i][j],
+                         j > 0 ? sv.enc_out[i][j - 1] : (i > 0 ? sv.xd[i - 1] : sv.x0), h, w));
+  }
+  // ---------------- intro: wgrad + bias grad (the input image needs no gradient) ----------------
+  DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient reached the intro conv");
+  DCPT_TRY(conv3x3_small_wgrad_launch(CUR.f, inp, G[0], nullptr, 0, N, h, w, C, st));
+  DCPT_TRY(axpy_launch(G[1], CUR.s, C, st));
+#undef CUR
+#undef NXT
+  return 0;
+}
+
+}  // extern "C"

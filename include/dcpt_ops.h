@@ -1,0 +1,161 @@
+/* dcpt_ops.h — C ABI of the B200 (sm_100a) hot-path library `libdcpt_sm100.so`.
+ *
+ * This is the drop-in boundary for the image-restoration forward/backward hot path of
+ * MILab-PKU/dcpt (basicsr/archs).  The reference has no native code on this path — every op is an
+ * eager PyTorch call — so each entry point cites the *Python* interface it replaces; the packaging
+ * mirrors the reference's own native-op pattern (basicsr/ops/layernorm/layernorm.py:7-67:
+ * autograd.Function over a compiled extension).  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds under basicsr/ops/.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless its name says `host_`.
+ *   - activations are NHWC ("channels_last"): row-major [M = N*H*W pixels, C channels], C % 8 == 0,
+ *     16-byte aligned.  fp32 = residual stream / parameters / parameter gradients / statistics,
+ *     bf16 = branch-internal activations (tensor-core operands).
+ *   - the caller owns every buffer (outputs, saved-for-backward arenas, workspaces); the library
+ *     never allocates device memory, never synchronises, and launches everything on `stream`
+ *     (CUDA-graph capturable).
+ *   - return value: 0 on success, negative DCPT_E_* for argument errors, positive = cudaError_t.
+ *     dcpt_last_error() returns a thread-local message.  No C++ exception crosses this boundary.
+ *   - parameter gradients are ACCUMULATED (+=) into the caller's fp32 buffers, like autograd.
+ */
+#ifndef DCPT_OPS_H_
+#define DCPT_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCPT_ABI_VERSION 1
+
+#define DCPT_E_ARG (-1)
+#define DCPT_E_SHAPE (-2)
+#define DCPT_E_ALIGN (-3)
+#define DCPT_E_DRIVER (-4)
+#define DCPT_E_UNSUPPORTED (-5)
+
+typedef void* dcpt_stream_t; /* cudaStream_t */
+
+int dcpt_abi_version(void);
+const char* dcpt_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Standalone ops (used by the tests and by callers that keep their own block structure).
+ * ------------------------------------------------------------------------------------------ */
+
+/* LayerNorm2d.forward — basicsr/archs/nafnet_arch.py:27-35 (LayerNormFunction.forward), :56-64.
+ * x fp32 [M,C] -> out bf16 [M,C]; stats fp32 [M,2] = (mean, 1/sqrt(var+eps)) saved for backward. */
+int dcpt_layernorm2d_fwd(const float* x, const float* weight, const float* bias, void* out_bf16, float* stats, int M,
+                         int C, float eps, dcpt_stream_t stream);
+
+/* LayerNormFunction.backward — nafnet_arch.py:38-53.  dx = dres + LN'(dn) (dres nullable);
+ * dx_bf16 (nullable) is a bf16 mirror of dx; dweight/dbias/colsum (nullable) are accumulated:
+ * dweight += sum_m dn*yhat, dbias += sum_m dn, colsum += sum_m dx. */
+int dcpt_layernorm2d_bwd(const void* dn_bf16, const float* x, const float* stats, const float* weight, const float* dres,
+                         float* dx, void* dx_bf16, float* dweight, float* dbias, float* colsum, int M, int C,
+                         dcpt_stream_t stream);
+
+/* Pointwise-convolution GEMM: D[M,N] = A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulate
+ * (nn.Conv2d(k=1) at nafnet_arch.py:87-95,105-113,133-150 seen as [pixels,Cin]x[Cout,Cin]^T).
+ *   a_mn/b_mn = 1: operand stored [K, M] / [K, N] (wgrad, where K = pixels).
+ *   out_f32 / out_bf16 nullable; bias[N] / resid fp32 [M,ldo] nullable; splits > 1 or accumulate = 1
+ *   selects the split-K path that atomically ADDS into out_f32.
+ *   impl: 0 = tcgen05/TMA (product), 1 = CUDA-core cross-check (tests only). */
+int dcpt_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, float* out_f32,
+                   void* out_bf16, int ldo, const float* bias, const float* resid, int splits, int accumulate, int impl,
+                   dcpt_stream_t stream);
+
+/* Full-control variant used by the tests to exercise every fused epilogue of the GEMM engine.
+ * epilogue: 0 STORE (bias/resid -> fp32 and/or bf16), 1 GATE (conv4 -> x4 + SimpleGate, nafnet_arch.py:180-181),
+ * 2 GATE_BWD (SimpleGate backward), 3 PIXSHUF (PixelShuffle(2) scatter + skip add, nafnet_arch.py:238-242,264-265),
+ * 4 ATOMIC (split-K wgrad accumulate). */
+typedef struct dcpt_gemm_desc {
+  int M, N, K;
+  const void* A; int lda; int a_mn;
+  const void* B; int ldb; int b_mn;
+  int splits;
+  int epilogue;
+  float* out_f32; void* out_bf16; int ldo;
+  const float* bias;
+  const float* resid; int ldr;
+  void* out2_bf16; int ldo2;
+  const void* aux_bf16; int ldaux;
+  int C;
+  int H, W, Cseg;
+} dcpt_gemm_desc;
+int dcpt_gemm_ex(const dcpt_gemm_desc* desc, int impl, dcpt_stream_t stream);
+
+/* conv2 (depthwise 3x3, pad 1, bias) + SimpleGate — nafnet_arch.py:96-104,:171-172,:77-80.
+ * u bf16 [N,H,W,2C] -> g bf16 [N,H,W,C]; pool fp32 [N,C] += sum_px g (must be zeroed by the caller). */
+int dcpt_dwconv3x3_gate_fwd(const void* u_bf16, const float* weight, const float* bias, void* g_bf16, float* pool, int N,
+                            int H, int W, int C, dcpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * NAFBlock — basicsr/archs/nafnet_arch.py:83-186 (NAFBlock.__init__/forward) and its autograd.
+ * ------------------------------------------------------------------------------------------ */
+
+/* The 18 parameters in the reference's named_parameters() order:
+ *  0 beta  1 gamma  2 conv1.weight  3 conv1.bias  4 conv2.weight  5 conv2.bias  6 conv3.weight
+ *  7 conv3.bias  8 sca.1.weight  9 sca.1.bias  10 conv4.weight  11 conv4.bias  12 conv5.weight
+ * 13 conv5.bias  14 norm1.weight  15 norm1.bias  16 norm2.weight  17 norm2.bias                 */
+#define DCPT_NAFBLOCK_NPARAMS 18
+
+size_t dcpt_nafblock_packed_bytes(int C);                     /* bf16 weight cache              */
+size_t dcpt_nafblock_saved_bytes(int N, int H, int W, int C); /* saved-for-backward arena       */
+size_t dcpt_nafblock_workspace_bytes(int N, int H, int W, int C); /* backward scratch            */
+
+/* Refresh the bf16 operand cache from the fp32 parameters (call after load_state_dict / optimizer step). */
+int dcpt_nafblock_pack(const float* const* host_params, void* packed, int C, dcpt_stream_t stream);
+
+/* x fp32 [N,H,W,C] -> out fp32 [N,H,W,C]; out_bf16 (nullable) mirrors out for a following GEMM. */
+int dcpt_nafblock_fwd(const float* const* host_params, const void* packed, const float* x, float* out, void* out_bf16,
+                      void* saved, int N, int H, int W, int C, dcpt_stream_t stream);
+
+/* dout fp32 + its bf16 mirror + its column sums (fp32 [C]) -> dx fp32, dx_bf16 mirror (nullable),
+ * dx_colsum (fp32 [C], accumulated; nullable); host_grads[i] accumulates d(param i). */
+int dcpt_nafblock_bwd(const float* const* host_params, const void* packed, const void* saved, const float* x,
+                      const float* dout, const void* dout_bf16, const float* dout_colsum, float* dx, void* dx_bf16,
+                      float* dx_colsum, float* const* host_grads, void* workspace, int N, int H, int W, int C,
+                      dcpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * NAFNetBaseline — basicsr/archs/nafnet_arch.py:189-274.
+ * Parameters / gradients are arrays of device pointers in named_parameters() order
+ * (intro.weight, intro.bias, ending.weight, ending.bias, encoders.*, middle_blks.*, ups.*.0.weight,
+ *  downs.*.{weight,bias}, decoder{i}.*), see dcpt_nafnet_num_params().
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dcpt_nafnet_plan dcpt_nafnet_plan;
+
+dcpt_nafnet_plan* dcpt_nafnet_create(int img_channel, int width, int middle_blk_num, const int* enc_blk_nums, int n_enc,
+                                     const int* dec_blk_nums, int n_dec);
+void dcpt_nafnet_destroy(dcpt_nafnet_plan* plan);
+int dcpt_nafnet_num_params(const dcpt_nafnet_plan* plan);
+/* shape of parameter i as up to 4 dims (unused dims = 1); returns number of elements */
+long long dcpt_nafnet_param_shape(const dcpt_nafnet_plan* plan, int i, int dims[4]);
+size_t dcpt_nafnet_packed_bytes(const dcpt_nafnet_plan* plan);
+size_t dcpt_nafnet_saved_bytes(const dcpt_nafnet_plan* plan, int N, int H, int W);
+size_t dcpt_nafnet_workspace_bytes(const dcpt_nafnet_plan* plan, int N, int H, int W);
+
+int dcpt_nafnet_pack(const dcpt_nafnet_plan* plan, const float* const* host_params, void* packed, dcpt_stream_t stream);
+
+/* inp fp32 NCHW [N,3,H,W] -> out fp32 NCHW [N,3,H,W] (out = ending(...) + inp).
+ * hook != 0: skip `ending` (nafnet_arch.py:269-274), `out` may be NULL.
+ * host_feats (nullable): n_dec device pointers receiving the decoder-level outputs as fp32 NHWC
+ * (what DCPT's forward hooks capture, degradation_classification_pretrain_model.py:60-72). */
+int dcpt_nafnet_fwd(const dcpt_nafnet_plan* plan, const float* const* host_params, const void* packed, const float* inp,
+                    float* out, void* saved, float* const* host_feats, int hook, int N, int H, int W,
+                    dcpt_stream_t stream);
+
+/* dout fp32 NCHW (NULL when the forward ran with hook != 0); host_dfeats (nullable): gradients flowing
+ * into the decoder-level outputs (fp32 NHWC, entries may be NULL).  Accumulates into host_grads. */
+int dcpt_nafnet_bwd(const dcpt_nafnet_plan* plan, const float* const* host_params, const void* packed, const void* saved,
+                    const float* inp, const float* dout, const float* const* host_dfeats, float* const* host_grads,
+                    void* workspace, int N, int H, int W, dcpt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCPT_OPS_H_ */

@@ -1,0 +1,203 @@
+"""GPU parity tests for the individual sm_100a kernels, called through the C ABI
+(dcpt_b200.ops -> libdcpt_sm100.so) and checked against the CPU oracle / plain torch fp32 math.
+
+Tolerances (written next to each check):
+  * fp32 outputs of a GEMM with bf16 operands and fp32 accumulation: rel-L2 <= 2e-5 against an
+    fp32 matmul of the SAME bf16-rounded operands (only summation order differs);
+  * bf16 outputs: one final rounding, rel-L2 <= 4e-3 (bf16 eps = 2^-8);
+  * LayerNorm statistics / fp32 elementwise math: rel-L2 <= 1e-5.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import nafnet_oracle as O  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dcpt_b200 import ops as _ops
+    _ops._lib()
+    return _ops
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------ GEMM engine
+GEMM_SHAPES = [(128, 64, 64), (256, 128, 64), (384, 256, 128), (1000, 512, 512), (4096, 1024, 512), (130, 72, 40),
+               (64, 16, 8), (16384, 128, 64)]
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_store(ops, impl, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = bf(torch.randn(M, K, device="cuda", generator=g))
+    B = bf(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    ref = A.float() @ B.float().t()
+    out = ops.gemm(A, B, out_dtype=torch.float32, impl=impl)
+    assert rel(out, ref) < 2e-5
+    out = ops.gemm(A, B, bias=bias, resid=resid, out_dtype=torch.float32, impl=impl)
+    assert rel(out, ref + bias + resid) < 2e-5
+    out = ops.gemm(A, B, bias=bias, impl=impl)
+    assert out.dtype == torch.bfloat16 and rel(out.float(), ref + bias) < 4e-3
+
+
+WGRAD_SHAPES = [(128, 64, 4096), (256, 128, 1000), (1024, 512, 16384), (64, 64, 65536), (16, 8, 200), (512, 2048, 4096)]
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("O_,I_,Mpx", WGRAD_SHAPES)
+def test_gemm_wgrad_mn_major(ops, impl, O_, I_, Mpx):
+    """dW[O,I] = dY[Mpx,O]^T X[Mpx,I]: MN-major operands, split-K, fp32 atomics (accumulates)."""
+    if impl == 1 and O_ * I_ * Mpx > 2 ** 31:
+        pytest.skip("too slow on CUDA cores")
+    g = torch.Generator(device="cuda").manual_seed(O_ + I_)
+    dY = bf(torch.randn(Mpx, O_, device="cuda", generator=g))
+    X = bf(torch.randn(Mpx, I_, device="cuda", generator=g))
+    ref = dY.float().t() @ X.float()
+    for splits in (1, 7):
+        acc = torch.ones(O_, I_, device="cuda")
+        ops.gemm(dY, X, a_mn=True, b_mn=True, splits=splits, accumulate_into=acc, impl=impl)
+        assert rel(acc - 1.0, ref) < 3e-5, splits
+
+
+def _desc(ops, **kw):
+    from dcpt_b200.lib import GemmDesc
+    d = GemmDesc()
+    for k, v in kw.items():
+        if torch.is_tensor(v):
+            v = v.data_ptr()
+        setattr(d, k, v)
+    return d
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("M,C", [(256, 64), (1000, 16), (512, 512), (130, 8)])
+def test_gemm_gate_epilogue(ops, impl, M, C):
+    """conv4 + SimpleGate (nafnet_arch.py:180-181): pair-interleaved weights, x4 and sg outputs."""
+    g = torch.Generator(device="cuda").manual_seed(C)
+    n2 = bf(torch.randn(M, C, device="cuda", generator=g))
+    W4 = bf(torch.randn(2 * C, C, device="cuda", generator=g) / C ** 0.5)
+    b4 = torch.randn(2 * C, device="cuda", generator=g)
+    p = torch.arange(2 * C, device="cuda")
+    orig = ((p % 16) // 8) * C + (p // 16) * 8 + (p % 8)  # packed row -> original out-channel
+    W4p, b4p = W4[orig].contiguous(), b4[orig].contiguous()
+    x4 = torch.empty(M, 2 * C, dtype=torch.bfloat16, device="cuda")
+    sg = torch.empty(M, C, dtype=torch.bfloat16, device="cuda")
+    d = _desc(ops, M=M, N=2 * C, K=C, A=n2, lda=C, B=W4p, ldb=C, splits=1, epilogue=1, out_bf16=x4, ldo=2 * C, bias=b4p,
+              out2_bf16=sg, ldo2=C, C=C)
+    ops.gemm_ex(d, impl)
+    ref = n2.float() @ W4.float().t() + b4
+    assert rel(x4.float(), ref) < 4e-3
+    x4r = x4.float()
+    assert rel(sg.float(), x4r[:, :C] * x4r[:, C:]) < 4e-3
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("M,C", [(256, 64), (1000, 16), (512, 512)])
+def test_gemm_gate_bwd_epilogue(ops, impl, M, C):
+    g = torch.Generator(device="cuda").manual_seed(C + 1)
+    dout = bf(torch.randn(M, C, device="cuda", generator=g))
+    W5t = bf(torch.randn(C, C, device="cuda", generator=g) / C ** 0.5)  # [in, out]
+    x4 = bf(torch.randn(M, 2 * C, device="cuda", generator=g))
+    dx4 = torch.empty(M, 2 * C, dtype=torch.bfloat16, device="cuda")
+    d = _desc(ops, M=M, N=C, K=C, A=dout, lda=C, B=W5t, ldb=C, splits=1, epilogue=2, out_bf16=dx4, ldo=2 * C, aux_bf16=x4,
+              ldaux=2 * C, C=C)
+    ops.gemm_ex(d, impl)
+    dsg = dout.float() @ W5t.float().t()
+    ref = torch.cat([dsg * x4.float()[:, C:], dsg * x4.float()[:, :C]], 1)
+    assert rel(dx4.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("N,H,W,Cin", [(2, 8, 8, 64), (1, 5, 7, 32), (2, 16, 16, 256)])
+def test_gemm_pixshuf_epilogue(ops, impl, N, H, W, Cin):
+    """ups[i] = 1x1 conv (no bias) + PixelShuffle(2), then + skip (nafnet_arch.py:238-242,264-265)."""
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(Cin)
+    x = bf(torch.randn(N, H, W, Cin, device="cuda", generator=g))
+    Wu = bf(torch.randn(2 * Cin, Cin, device="cuda", generator=g) / Cin ** 0.5)
+    Cseg = Cin // 2
+    skip = torch.randn(N, 2 * H, 2 * W, Cseg, device="cuda", generator=g)
+    p = torch.arange(2 * Cin, device="cuda")
+    orig = (p % Cseg) * 4 + p // Cseg
+    Wp = Wu[orig].contiguous()
+    out = torch.empty_like(skip)
+    mirror = torch.empty(skip.shape, dtype=torch.bfloat16, device="cuda")
+    d = _desc(ops, M=N * H * W, N=2 * Cin, K=Cin, A=x, lda=Cin, B=Wp, ldb=Cin, splits=1, epilogue=3, out_f32=out,
+              out_bf16=mirror, resid=skip, H=H, W=W, Cseg=Cseg)
+    ops.gemm_ex(d, impl)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), Wu.float()[:, :, None, None])
+    ref = F.pixel_shuffle(y, 2).permute(0, 2, 3, 1) + skip
+    assert rel(out, ref) < 2e-5
+    assert rel(mirror.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("M,C", [(70, 24), (1000, 64), (4096, 128), (777, 512), (300, 1024), (5, 8)])
+def test_layernorm_fwd_bwd(ops, M, C):
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(M, C, generator=g) * 1.7 + 0.4
+    w = 1 + 0.2 * torch.randn(C, generator=g)
+    b = 0.2 * torch.randn(C, generator=g)
+    dn = torch.randn(M, C, generator=g).bfloat16()
+    dres = torch.randn(M, C, generator=g)
+    x4 = x.t().reshape(1, C, M, 1)  # NCHW view of the same rows
+    y, y_hat, var = O.layernorm2d_fwd(x4, w, b)
+    dx_ref, dw_ref, db_ref = O.layernorm2d_bwd(dn.float().t().reshape(1, C, M, 1), y_hat, var, w)
+    out, stats = ops.layernorm2d_fwd(x.cuda(), w.cuda(), b.cuda())
+    assert rel(out.float(), y[0, :, :, 0].t()) < 4e-3                      # bf16 output
+    assert rel(stats[:, 0], x.mean(1)) < 1e-5
+    assert rel(stats[:, 1], 1 / torch.sqrt(x.var(1, unbiased=False) + 1e-6)) < 1e-5
+    dx, dxb, dw, db, cs = ops.layernorm2d_bwd(dn.cuda(), x.cuda(), stats, w.cuda(), dres.cuda())
+    ref = dx_ref[0, :, :, 0].t() + dres
+    assert rel(dx, ref) < 1e-5
+    assert rel(dxb.float(), ref) < 4e-3
+    assert rel(dw, dw_ref) < 1e-4 and rel(db, db_ref) < 1e-4
+    assert rel(cs, ref.sum(0)) < 1e-4
+
+
+def test_layernorm_golden(ops, golden_dir):
+    z = np.load(os.path.join(golden_dir, "layernorm2d.npz"))
+    x = torch.from_numpy(z["x"])
+    N, C, H, W = x.shape
+    rows = lambda t: torch.as_tensor(t).permute(0, 2, 3, 1).reshape(-1, C).contiguous().cuda()
+    out, stats = ops.layernorm2d_fwd(rows(x), torch.from_numpy(z["weight"]).cuda(), torch.from_numpy(z["bias"]).cuda())
+    assert rel(out.float(), rows(z["y"])) < 4e-3
+    dy = rows(z["dy"]).bfloat16()
+    dx, _, dw, db, _ = ops.layernorm2d_bwd(dy, rows(x), stats, torch.from_numpy(z["weight"]).cuda())
+    # dy was rounded to bf16 (the kernel's input type) -> compare against the oracle on the rounded dy
+    dyr = dy.float().reshape(N, H, W, C).permute(0, 3, 1, 2).cpu()
+    _, y_hat, var = O.layernorm2d_fwd(x, torch.from_numpy(z["weight"]), torch.from_numpy(z["bias"]))
+    dx_ref, dw_ref, db_ref = O.layernorm2d_bwd(dyr, y_hat, var, torch.from_numpy(z["weight"]))
+    assert rel(dx, rows(dx_ref)) < 1e-5 and rel(dw, dw_ref) < 1e-4 and rel(db, db_ref) < 1e-4
+    assert rel(dx, rows(z["dx"])) < 4e-3  # vs the reference's own output (bf16-rounded dy)
+
+
+# ------------------------------------------------------------------ dw3x3 + SimpleGate
+@pytest.mark.parametrize("N,H,W,C", [(2, 9, 7, 16), (1, 16, 16, 64), (2, 5, 33, 8), (1, 3, 3, 512)])
+def test_dwconv_gate_fwd(ops, N, H, W, C):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(C + H)
+    u = torch.randn(N, H, W, 2 * C, generator=g).bfloat16()
+    w2 = torch.randn(2 * C, 1, 3, 3, generator=g) / 3
+    b2 = torch.randn(2 * C, generator=g) * 0.1
+    v = F.conv2d(u.float().permute(0, 3, 1, 2), w2, b2, padding=1, groups=2 * C)
+    gref = O.simple_gate(v).permute(0, 2, 3, 1)
+    gk, pool = ops.dwconv3x3_gate_fwd(u.cuda(), w2.cuda(), b2.cuda())
+    assert rel(gk.float(), gref) < 4e-3
+    assert rel(pool, gk.float().sum((1, 2))) < 1e-5     # pool sums the stored (rounded) g
