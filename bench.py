@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — MPix/s of the NAFNet-w64 256x256 forward+backward hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = one pass of the hot path over one synthetic batch: NAFNetBaseline-w64
+(enc [1,1,1,28], mid 1, dec [1,1,1,1]; options/all_in_one/test/test_NAFNet_5d.yml:50-56) forward,
+L1 loss to a random target, backward producing the gradient of every parameter (the body of
+SRModel.optimize_parameters, basicsr/models/sr_model.py:132-164, without the optimizer) on a batch of
+16 x 3 x 256 x 256 per GPU (BASELINE.json configs[1]); for N > 1 the per-rank gradients are
+all-reduced over NCCL (the path's one exchange step) inside the step.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput through the C-ABI engine;
+`e2e` = the same metric through the public API (registry-built nn.Module + autograd) with pinned
+host inputs copied H2D and the loss read back D2H every step.  `roofline` describes the dominant
+kernel class measured live with CUDA events (dcpt_prof_*), `cpu_baseline` is the oracle port timed
+on this box's host cores on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(width=64, enc_blk_nums=[1, 1, 1, 28], middle_blk_num=1, dec_blk_nums=[1, 1, 1, 1])
+H = W = 256
+FLOP_PER_IMG_FWD = 126.11e9          # SURVEY.md §8(d), 2*MAC, per 256x256 image
+METRIC = "MPix/s NAFNet-w64 256x256 fwd+bwd"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples drawing more than half of the peak observed power
+        thr = 0.5 * max(pw)
+        load = sorted(s for s, p in zip(sm, pw) if p >= thr) or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+def oracle_step_fn(batch):
+    """The reference's CPU PyTorch path, as restated by oracle/ (the reference is pure Python and cannot
+    travel to the GPU box; oracle/ is pinned to it by tests/golden)."""
+    import torch
+    from oracle import nafnet_oracle as O
+    sd = O.random_nafnet_state_dict(seed=0, **CFG)
+    g = torch.Generator().manual_seed(1)
+    inp = torch.rand(batch, 3, H, W, generator=g)
+    gt = torch.rand(batch, 3, H, W, generator=g)
+
+    def step():
+        O.nafnet_fwd_bwd(inp, gt, sd, CFG["enc_blk_nums"], CFG["middle_blk_num"], CFG["dec_blk_nums"])
+    return step
+
+
+def cpu_baseline(budget_s=12.0, max_steps=8):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = oracle_step_fn(1)
+    step()                                    # warm-up
+    ts = []
+    t_all = time.perf_counter()
+    while len(ts) < max_steps and (time.perf_counter() - t_all) < budget_s:
+        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": round(H * W / med / 1e6, 5), "unit": "MPix/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/nafnet_oracle.py NAFNet-w64 fwd+bwd, batch 1 x 256x256 fp32 on CPU, median of {len(ts)} steps "
+                      f"({med * 1e3:.0f} ms/step), torch {torch.__version__} threads={torch.get_num_threads()}"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 1                                  # bounded sample of the workload (the CPU path is ~1 s / image)
+    step = oracle_step_fn(batch)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 8))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = batch * H * W / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 5), "unit": "MPix/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "NAFNet-w64 fwd+bwd (L1 loss), bounded sample: batch 1 x 3x256x256 per step on host CPU",
+                       "net": CFG},
+            "cpu_baseline": {"value": round(val, 5), "unit": "MPix/s", "cores": cores, "kind": "port",
+                             "sample": f"batch {batch} x 256x256 per step, {steps} steps, torch CPU fp32, {cores} threads"},
+            "e2e": {"value": round(val, 5), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def prof_table(lib):
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.dcpt_prof_dump(buf, len(buf))
+    rows = []
+    for ln in buf.value.decode().splitlines():
+        tag, n, ms, fl, by = ln.split("\t")
+        rows.append(dict(tag=tag, launches=int(n), ms=float(ms), flops=float(fl), bytes=float(by)))
+    return rows
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dcpt_b200.lib import load_library
+    from dcpt_b200.nafnet import NAFNetEngine
+    from oracle import nafnet_oracle as O  # only for the synthetic weight generator + cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load_library()
+    B = args.batch
+    pk = peaks()
+
+    # ---------------- device-resident arm (`value`) ----------------
+    sd = O.random_nafnet_state_dict(seed=0, **CFG)
+    params = [v.to(dev).contiguous() for v in sd.values()]
+    eng = NAFNetEngine(3, CFG["width"], CFG["middle_blk_num"], CFG["enc_blk_nums"], CFG["dec_blk_nums"])
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    inp = torch.rand(B, 3, H, W, device=dev, generator=g)
+    gt = torch.rand(B, 3, H, W, device=dev, generator=g)
+    flat, grads = eng.alloc_flat_grads(params)
+    inv_numel = 1.0 / inp.numel()
+
+    def step():
+        flat.zero_()
+        out, _, saved = eng.forward(params, inp)
+        dout = torch.sign(out - gt).mul_(inv_numel)       # d L1(mean) / d out
+        eng.backward(params, inp, saved, dout, grads=grads)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.dcpt_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = lib.dcpt_launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * H * W / (ms * 1e-3) / 1e6
+
+    # ---------------- per-kernel attribution (one extra, untimed, profiled step) ----------------
+    roof = None
+    if rank == 0:
+        lib.dcpt_prof_enable(1)
+        step()
+        rows = prof_table(lib)
+        lib.dcpt_prof_enable(0)
+        tot = sum(r["ms"] for r in rows) or 1.0
+        rows.sort(key=lambda r: -r["ms"])
+        top = rows[0]
+        is_gemm = top["tag"].startswith("gemm")
+        if is_gemm:
+            ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
+            roof = {"kernel": top["tag"], "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tc_sust"], "unit": "TFLOP/s",
+                    "frac": round(ach / pk["tc_sust"], 4), "traffic": None}
+        else:
+            ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+            roof = {"kernel": top["tag"], "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": round(ach / pk["hbm"], 4), "traffic": None}
+        roof.update({"peak_source": pk["src"] + (", sustained (kernel timed inside the step)" if is_gemm else ""),
+                     "share_of_step": round(top["ms"] / tot, 4), "launches_per_step": top["launches"],
+                     "avg_launch_us": round(top["ms"] * 1e3 / top["launches"], 2),
+                     "how": "CUDA events around every launch of one extra step (dcpt_prof_*), algorithmic 2MNK flops / bytes"})
+        gemm_ms = sum(r["ms"] for r in rows if r["tag"].startswith("gemm"))
+        gemm_fl = sum(r["flops"] for r in rows if r["tag"].startswith("gemm"))
+        roof["all_gemms"] = {"share_of_step": round(gemm_ms / tot, 4), "tflops": round(gemm_fl / (gemm_ms * 1e-3) / 1e12, 1)}
+        roof["whole_step"] = {"model_tflops": round(3 * FLOP_PER_IMG_FWD * B / (ms * 1e-3) / 1e12, 1),
+                              "frac_of_tensor_peak": round(3 * FLOP_PER_IMG_FWD * B / (ms * 1e-3) / 1e12 / pk["tc_sust"], 4),
+                              "lower_bound_ms": round(B * 0.2885, 3), "frac_of_lower_bound": round(B * 0.2885 / ms, 4)}
+        if args.breakdown:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "kernel_breakdown.tsv"), "w") as f:
+                f.write("tag\tlaunches\tms\tshare\tTFLOP/s\tGB/s\n")
+                for r in rows:
+                    f.write(f"{r['tag']}\t{r['launches']}\t{r['ms']:.3f}\t{r['ms'] / tot:.4f}\t"
+                            f"{r['flops'] / (r['ms'] * 1e-3 + 1e-12) / 1e12:.1f}\t{r['bytes'] / (r['ms'] * 1e-3 + 1e-12) / 1e9:.0f}\n")
+
+    # ---------------- end-to-end arm (`e2e`): public API, host buffers ----------------
+    from basicsr.archs import build_network
+    net = build_network(dict(type="NAFNetBaseline", window_size=16, **CFG)).to(dev)
+    net.load_state_dict(sd, strict=True)
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
+    gcpu = torch.Generator().manual_seed(7 + rank)
+    h_inp = torch.rand(B, 3, H, W, generator=gcpu).pin_memory()
+    h_gt = torch.rand(B, 3, H, W, generator=gcpu).pin_memory()
+    del flat, grads
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        lq = h_inp.to(dev, non_blocking=True)
+        tgt = h_gt.to(dev, non_blocking=True)
+        model.zero_grad(set_to_none=True)
+        out = model(lq)
+        loss = torch.nn.functional.l1_loss(out, tgt)
+        loss.backward()
+        return float(loss.item())                          # D2H read of the step's result
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e = {"value": round(world * B * H * W / (ms_e2e * 1e-3) / 1e6, 3), "unit": "MPix/s",
+           "h2d_bytes_per_step": int(2 * h_inp.numel() * 4), "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3),
+           "api": "basicsr.archs.build_network(NAFNetBaseline) -> net(lq); l1_loss; loss.backward(); loss.item()"
+                  + ("; DistributedDataParallel" if world > 1 else "")}
+
+    if rank == 0:
+        cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        line = {"metric": METRIC, "value": round(value, 3), "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"NAFNet-w64 (enc [1,1,1,28], mid 1, dec [1,1,1,1]) fwd + L1 loss + bwd, "
+                                       f"batch {B}x3x256x256 per GPU, all parameter gradients"
+                                       + (", NCCL all-reduce(avg) of the flat fp32 gradient buffer" if world > 1 else ""),
+                           "net": CFG, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "precision": "bf16 tensor-core operands, fp32 accumulate, fp32 residual stream / params / grads",
+                           "l2": "per-step working set (~10 GB of activations) >> 126 MB L2; no explicit flush needed"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE.json configs[1]: 16)")
+    ap.add_argument("--breakdown", action="store_true", help="write gpurun_out/kernel_breakdown.tsv")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "prof.h"
+
 typedef __nv_bfloat16 bf16;
 
 // ----------------------------------------------------------------------------

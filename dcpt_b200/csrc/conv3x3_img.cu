@@ -221,6 +221,7 @@ int conv3x3_img_to_feat_launch(const float* img, const float* w, const float* bi
   if (blocks > cap) blocks = cap;
   // keep gridDim.x*blockDim.x a multiple of CV so each thread keeps one channel vector (column sums stay per-thread)
   while ((blocks * 256) % CV != 0) ++blocks;
+  DCPT_PROF("conv3x3_img_to_feat", 54.0 * N * H * W * C, (12.0 + (out_f32 ? 4.0 : 0.0) * C + (out_bf16 ? 2.0 : 0.0) * C) * N * H * W, st);
   conv3x3_img_to_feat_kernel<<<(unsigned)blocks, 256, smem, st>>>(img, w, bias, transpose_flip, out_f32, out_bf16, colsum, N, H,
                                                                  W, C);
   DCPT_LAUNCH_CHECK();
@@ -237,6 +238,7 @@ int conv3x3_feat_to_img_launch(const float* feat, const float* w, const float* b
   long long blocks = ceil_div_ll(total, 8);
   const long long cap = (long long)dcpt_num_sms() * 16;
   if (blocks > cap) blocks = cap;
+  DCPT_PROF("conv3x3_feat_to_img", 54.0 * N * H * W * C, (4.0 * C + 24.0) * N * H * W, st);
   conv3x3_feat_to_img_kernel<<<(unsigned)blocks, 256, smem, st>>>(feat, w, bias, resid_img, out_img, N, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -253,6 +255,7 @@ int conv3x3_small_wgrad_launch(const float* feat, const float* img, float* G, fl
   int cpb = (int)ceil_div_ll(chunks, (long long)dcpt_num_sms() * 4);
   if (cpb < 1) cpb = 1;
   const long long blocks = ceil_div_ll(chunks, cpb);
+  DCPT_PROF("conv3x3_small_wgrad", 54.0 * N * H * W * C, (4.0 * C + 12.0) * N * H * W, st);
   conv3x3_small_wgrad_kernel<<<(unsigned)blocks, 256, smem, st>>>(feat, img, G, flip, N, H, W, C, cpb);
   DCPT_LAUNCH_CHECK();
   if (img_sum) {

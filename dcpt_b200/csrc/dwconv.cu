@@ -303,6 +303,7 @@ int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, 
   DCPT_TRY(set_smem(dwgate_fwd_kernel, smem));
   const long long items = (long long)H * ceil_div(W, PX) * (C / 8);
   dim3 grid((unsigned)ceil_div_ll(items, 256), N);
+  DCPT_PROF("dwgate_fwd", 38.0 * N * H * W * C, 6.0 * N * H * W * C, st);
   dwgate_fwd_kernel<<<grid, 256, smem, st>>>(u, w2, b2, g, pool, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -322,6 +323,7 @@ int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const b
   const size_t smem = ((size_t)9 * 2 * C + 2 * C + (size_t)cvb * 160) * sizeof(float);
   DCPT_TRY(set_smem(dwgate_bwd_a_kernel, smem));
   dim3 grid(gx, ceil_div(CV, cvb), N);
+  DCPT_PROF("dwgate_bwd_a", 80.0 * N * H * W * C, 10.0 * N * H * W * C, st);
   dwgate_bwd_a_kernel<<<grid, 128, smem, st>>>(dgs, s, t, u, w2, b2, du2, dw2, db2, H, W, C, cvb);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -334,6 +336,7 @@ int dwconv_bwd_data_launch(const bf16* du2, const float* w2, bf16* du, float* co
   DCPT_TRY(set_smem(dwconv_bwd_data_kernel, smem));
   const long long items = (long long)H * ceil_div(W, PX) * (C2 / 8);
   dim3 grid((unsigned)ceil_div_ll(items, 256), N);
+  DCPT_PROF("dwconv_bwd_data", 18.0 * N * H * W * C2, 4.0 * N * H * W * C2, st);
   dwconv_bwd_data_kernel<<<grid, 256, smem, st>>>(du2, w2, du, colsum, H, W, C2);
   DCPT_LAUNCH_CHECK();
   return 0;

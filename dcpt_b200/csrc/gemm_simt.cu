@@ -37,6 +37,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   const long long total = (long long)g.M * chunks_n;
   const int splits = g.splits < 1 ? 1 : g.splits;
   const int kps = ceil_div(g.K, splits);
+  DCPT_PROF("gemm_simt", 2.0 * g.M * g.N * g.K, 0.0, stream);
   for (int s = 0; s < splits; ++s) {
     const int k0 = s * kps, k1 = (k0 + kps < g.K) ? k0 + kps : g.K;
     if (k0 >= k1) break;

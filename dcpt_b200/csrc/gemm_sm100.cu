@@ -271,6 +271,14 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     DCPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     attr_set = true;
   }
+  static char tag[48] = "";
+  if (!tag[0]) {
+    static const char* epi_names[] = {"store", "gate", "gate_bwd", "pixshuf", "atomic"};
+    snprintf(tag, sizeof(tag), "gemm_tc<%d,%s,%s>", BN, epi_names[EPI], A_MN ? "mn" : "k");
+  }
+  const double out_bytes = (double)g.M * g.N * ((g.ep.out_f32 ? 4.0 : 0.0) + (g.ep.out_bf16 ? 2.0 : 0.0) + (g.ep.resid ? 4.0 : 0.0) +
+                                                (EPI == EPI_GATE ? 1.0 : 0.0) + (EPI == EPI_GATE_BWD ? 4.0 : 0.0));
+  DCPT_PROF(tag, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes, stream);
   kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, g.M, g.N, g.K, tiles_m, tiles_n, splits, kbps, g.ep);
   DCPT_LAUNCH_CHECK();
   return 0;

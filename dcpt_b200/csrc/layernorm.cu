@@ -182,6 +182,7 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
   const int nv = ceil_div(C / 4, lpr);
   const int rows_per_block = kWarps * (32 / lpr);
   const int grid = (int)ceil_div_ll(M, rows_per_block);
+  DCPT_PROF("ln_fwd", 8.0 * M * C, 6.0 * M * C, st);
 #define LN_FWD(NVV) ln_fwd_kernel<NVV><<<grid, kWarps * 32, 0, st>>>(x, w, b, n_out, stats, M, C, lpr, eps)
   if (nv <= 1) LN_FWD(1);
   else if (nv <= 2) LN_FWD(2);
@@ -202,6 +203,7 @@ int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const floa
   const long long cap = (long long)dcpt_num_sms() * 4;  // few blocks -> few partial-sum flushes
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)3 * C * sizeof(float);
+  DCPT_PROF("ln_bwd", 20.0 * M * C, (2.0 + 4.0 + (dres ? 4.0 : 0.0) + 4.0 + (dx_bf16 ? 2.0 : 0.0)) * M * C, st);
 #define LN_BWD(NVV) \
   ln_bwd_kernel<NVV><<<(int)grid, kWarps * 32, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr)
   if (nv <= 1) LN_BWD(1);

@@ -300,6 +300,7 @@ __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ s
 
 int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, int N, int C, int HW, cudaStream_t st) {
   const long long threads = (long long)N * C * 32;
+  DCPT_PROF("sca_fwd", 2.0 * N * C * C, 4.0 * C * C, st);
   sca_fwd_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, st>>>(pool, w, b, s, N, C, 1.f / (float)HW);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -307,6 +308,7 @@ int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, 
 
 int scale_rows_launch(const bf16* g, const float* s, bf16* gs, int N, int HW, int C, cudaStream_t st) {
   const long long nvec = (long long)N * HW * (C / 8);
+  DCPT_PROF("scale_rows", (double)N * HW * C, 4.0 * N * HW * C, st);
   scale_rows_kernel<<<(unsigned)ceil_div_ll(nvec, 256), 256, 0, st>>>(g, s, gs, nvec, HW, C);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -323,6 +325,7 @@ int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int H
   int gx = ceil_div(HW, npl * 16);
   if (gx < 1) gx = 1;
   dim3 grid(gx, ceil_div(CV, cvb), N);
+  DCPT_PROF("sca_ds_reduce", 2.0 * N * HW * C, 4.0 * N * HW * C, st);
   sca_ds_reduce_kernel<<<grid, 256, cvb * 8 * sizeof(float), st>>>(dgs, g, ds, HW, C, cvb);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -331,6 +334,7 @@ int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int H
 int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t, float* dw, float* db, int N, int C, int HW,
                    cudaStream_t st) {
   const long long total = (long long)C * C + (long long)N * C + C;
+  DCPT_PROF("sca_bwd", 4.0 * N * C * C, 12.0 * C * C, st);
   sca_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(ds, pool, w, t, dw, db, N, C, 1.f / (float)HW);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -342,6 +346,7 @@ int colsum_bf16_launch(const bf16* x, float* out, int M, int C, cudaStream_t st)
   if (gx < 1) gx = 1;
   if (gx > 4096) gx = 4096;
   dim3 grid((unsigned)gx, ceil_div(CV, cvb));
+  DCPT_PROF("colsum_bf16", (double)M * C, 2.0 * M * C, st);
   colsum_bf16_kernel<<<grid, 256, cvb * 8 * sizeof(float), st>>>(x, out, M, C, cvb);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -349,6 +354,7 @@ int colsum_bf16_launch(const bf16* x, float* out, int M, int C, cudaStream_t st)
 
 int cast_f32_bf16_launch(const float* x, bf16* y, long long n, cudaStream_t st) {
   DCPT_CHECK_ARG(n % 8 == 0, DCPT_E_SHAPE, "cast: element count %lld must be a multiple of 8", n);
+  DCPT_PROF("cast_f32_bf16", 0.0, 6.0 * n, st);
   cast_f32_bf16_kernel<<<(unsigned)ceil_div_ll(n / 8, 256), 256, 0, st>>>(x, y, n / 8);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -356,6 +362,7 @@ int cast_f32_bf16_launch(const float* x, bf16* y, long long n, cudaStream_t st) 
 
 int unshuffle_cast_launch(const float* x, bf16* y, int N, int H, int W, int C, cudaStream_t st) {
   const long long nvec = (long long)N * H * W * 4 * (C / 8);
+  DCPT_PROF("unshuffle_cast", 0.0, 6.0 * nvec * 8, st);
   unshuffle_cast_kernel<<<(unsigned)ceil_div_ll(nvec, 256), 256, 0, st>>>(x, y, nvec, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -363,12 +370,14 @@ int unshuffle_cast_launch(const float* x, bf16* y, int N, int H, int W, int C, c
 
 int pack_weight_launch(const float* w, const float* row_scale, bf16* out, int O, int I, int mode, cudaStream_t st) {
   const long long total = (long long)O * I;
+  DCPT_PROF("pack_weight", 0.0, 6.0 * total, st);
   pack_weight_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(w, row_scale, out, O, I, mode);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
 
 int pack_bias_launch(const float* bias, const float* scale, float* out, int O, int mode, cudaStream_t st) {
+  DCPT_PROF("pack_bias", 0.0, 8.0 * O, st);
   pack_bias_kernel<<<ceil_div(O, 256), 256, 0, st>>>(bias, scale, out, O, mode);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -376,6 +385,7 @@ int pack_bias_launch(const float* bias, const float* scale, float* out, int O, i
 
 int wgrad_finish_resid_launch(const float* G, const float* w, const float* bias, const float* scale, const float* colsum,
                               float* dw, float* dbias, float* dscale, int O, int I, cudaStream_t st) {
+  DCPT_PROF("wgrad_finish_resid", 4.0 * O * I, 16.0 * O * I, st);
   wgrad_finish_resid_kernel<<<ceil_div(O * 32, 256), 256, 0, st>>>(G, w, bias, scale, colsum, dw, dbias, dscale, O, I);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -383,6 +393,7 @@ int wgrad_finish_resid_launch(const float* G, const float* w, const float* bias,
 
 int wgrad_finish_perm_launch(const float* G, float* dw, int O, int I, int mode, cudaStream_t st) {
   const long long total = (long long)O * I;
+  DCPT_PROF("wgrad_finish_perm", (double)total, 12.0 * total, st);
   wgrad_finish_perm_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(G, dw, O, I, mode);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -395,12 +406,14 @@ int grad_prepare_launch(const float* a, const float* b, float* out, bf16* out_bf
   if (gx < 1) gx = 1;
   if (gx > 8192) gx = 8192;
   dim3 grid((unsigned)gx, ceil_div(CV, cvb));
+  DCPT_PROF("grad_prepare", (double)M * C, ((a ? 4.0 : 0.0) + (b ? 4.0 : 0.0) + (out ? 4.0 : 0.0) + (out_bf16 ? 2.0 : 0.0)) * M * C, st);
   grad_prepare_kernel<<<grid, 256, cvb * 8 * sizeof(float), st>>>(a, b, out, out_bf16, colsum, M, C, cvb);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
 
 int axpy_launch(float* dst, const float* src, int n, cudaStream_t st) {
+  DCPT_PROF("axpy", (double)n, 12.0 * n, st);
   axpy_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dst, src, n);
   DCPT_LAUNCH_CHECK();
   return 0;

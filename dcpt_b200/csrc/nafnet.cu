@@ -10,6 +10,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <string>
 #include <vector>
 
 #include "../../include/dcpt_ops.h"
@@ -27,6 +29,25 @@ void dcpt_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// ---- profiling (prof.h) ----
+bool g_dcpt_prof_on = false;
+long long g_dcpt_launches = 0;
+namespace {
+struct ProfRec { const char* tag; double flops, bytes; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void dcpt_prof_begin(const char* tag, double flops, double bytes, cudaStream_t st) {
+  ProfRec r{tag, flops, bytes, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+void dcpt_prof_end(cudaStream_t st) { if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, st); }
 
 int dcpt_num_sms() {
   static int sms = 0;
@@ -230,6 +251,8 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   return 0;
 }
 
+int check_ptrs16(const void* const* ptrs, int n, const char* what);
+
 int check_block_shape(int N, int H, int W, int C) {
   DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "nafblock: bad spatial shape N=%d H=%d W=%d", N, H, W);
   DCPT_CHECK_ARG(C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "nafblock: C=%d must be a multiple of 8 in [8, 1024]", C);
@@ -381,6 +404,14 @@ struct NetWork {
   }
 };
 
+int check_ptrs16(const void* const* ptrs, int n, const char* what) {
+  DCPT_CHECK_ARG(ptrs != nullptr, DCPT_E_ARG, "%s: null pointer table", what);
+  for (int i = 0; i < n; ++i)
+    DCPT_CHECK_ARG(ptrs[i] != nullptr && (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, DCPT_E_ALIGN,
+                   "%s[%d] = %p must be non-null and 16-byte aligned", what, i, ptrs[i]);
+  return 0;
+}
+
 int check_net_shape(const dcpt_nafnet_plan* p, int N, int H, int W) {
   const int f = 1 << (int)p->enc.size();
   DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % f == 0 && W % f == 0, DCPT_E_SHAPE,
@@ -398,6 +429,43 @@ int check_net_shape(const dcpt_nafnet_plan* p, int N, int H, int W) {
 extern "C" {
 
 int dcpt_abi_version(void) { return DCPT_ABI_VERSION; }
+
+long long dcpt_launch_count(void) { return g_dcpt_launches; }
+
+int dcpt_prof_enable(int on) {
+  g_dcpt_prof_on = on != 0;
+  return 0;
+}
+
+// Synchronises the device, aggregates the recorded launches by tag and writes one line per tag:
+//   tag <TAB> launches <TAB> total_ms <TAB> total_flops <TAB> total_bytes
+// Returns the number of bytes written (truncated to cap), clears the records.
+long long dcpt_prof_dump(char* buf, long long cap) {
+  cudaDeviceSynchronize();
+  struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      Agg& a = agg[r.tag];
+      a.n++; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    }
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  (void)cudaGetLastError();
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s\t%lld\t%.6f\t%.6e\t%.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops,
+             kv.second.bytes);
+    out += line;
+  }
+  long long n = (long long)out.size() < cap - 1 ? (long long)out.size() : cap - 1;
+  if (buf && cap > 0) { memcpy(buf, out.data(), n); buf[n] = 0; }
+  return n;
+}
 const char* dcpt_last_error(void) { return g_err; }
 
 int dcpt_layernorm2d_fwd(const float* x, const float* weight, const float* bias, void* out_bf16, float* stats, int M, int C,
@@ -465,6 +533,7 @@ size_t dcpt_nafblock_workspace_bytes(int N, int H, int W, int C) {
 
 int dcpt_nafblock_pack(const float* const* host_params, void* packed, int C, dcpt_stream_t stream) {
   DCPT_TRY(check_block_shape(1, 1, 1, C));
+  DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(host_params), DCPT_NAFBLOCK_NPARAMS, "params"));
   Arena a(packed);
   BlockPacked pk(a, C);
   return nafblock_pack_impl(host_params, pk, C, static_cast<cudaStream_t>(stream));
@@ -473,6 +542,7 @@ int dcpt_nafblock_pack(const float* const* host_params, void* packed, int C, dcp
 int dcpt_nafblock_fwd(const float* const* host_params, const void* packed, const float* x, float* out, void* out_bf16, void* saved,
                       int N, int H, int W, int C, dcpt_stream_t stream) {
   DCPT_TRY(check_block_shape(N, H, W, C));
+  DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(host_params), DCPT_NAFBLOCK_NPARAMS, "params"));
   Arena ap(const_cast<void*>(packed));
   BlockPacked pk(ap, C);
   Arena as(saved);
@@ -484,6 +554,8 @@ int dcpt_nafblock_bwd(const float* const* host_params, const void* packed, const
                       const void* dout_bf16, const float* dout_colsum, float* dx, void* dx_bf16, float* dx_colsum,
                       float* const* host_grads, void* workspace, int N, int H, int W, int C, dcpt_stream_t stream) {
   DCPT_TRY(check_block_shape(N, H, W, C));
+  DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(host_params), DCPT_NAFBLOCK_NPARAMS, "params"));
+  DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(host_grads), DCPT_NAFBLOCK_NPARAMS, "grads"));
   Arena ap(const_cast<void*>(packed));
   BlockPacked pk(ap, C);
   Arena as(const_cast<void*>(saved));
@@ -564,6 +636,7 @@ size_t dcpt_nafnet_workspace_bytes(const dcpt_nafnet_plan* plan, int N, int H, i
 }
 
 int dcpt_nafnet_pack(const dcpt_nafnet_plan* p, const float* const* P, void* packed, dcpt_stream_t stream) {
+  DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(P), (int)p->params.size(), "params"));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena a(packed);
   NetPacked pk(p, a);
@@ -589,6 +662,7 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
                     float* const* host_feats, int hook, int N, int H, int W, dcpt_stream_t stream) {
   DCPT_TRY(check_net_shape(p, N, H, W));
   DCPT_CHECK_ARG(hook || out != nullptr, DCPT_E_ARG, "nafnet_fwd: out is NULL but hook == 0");
+  DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(P), (int)p->params.size(), "params"));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena ap(const_cast<void*>(packed));
   NetPacked pk(p, ap);
@@ -650,6 +724,8 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
                     const float* dout, const float* const* host_dfeats, float* const* G, void* workspace, int N, int H, int W,
                     dcpt_stream_t stream) {
   DCPT_TRY(check_net_shape(p, N, H, W));
+  DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(P), (int)p->params.size(), "params"));
+  DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(G), (int)p->params.size(), "grads"));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena ap(const_cast<void*>(packed));
   NetPacked pk(p, ap);

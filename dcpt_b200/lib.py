@@ -34,6 +34,9 @@ _PP = C.POINTER(C.c_void_p)
 PROTOTYPES = {
     "dcpt_abi_version": (_I, []),
     "dcpt_last_error": (C.c_char_p, []),
+    "dcpt_launch_count": (_LL, []),
+    "dcpt_prof_enable": (_I, [_I]),
+    "dcpt_prof_dump": (_LL, [C.c_char_p, _LL]),
     "dcpt_layernorm2d_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _F, _VP]),
     "dcpt_layernorm2d_bwd": (_I, [_VP] * 10 + [_I, _I, _VP]),
     "dcpt_gemm_bf16": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _I, _I, _VP]),

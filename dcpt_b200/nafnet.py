@@ -66,6 +66,17 @@ class NAFNetEngine:
             self._packed_key = key
         return self._packed
 
+    @staticmethod
+    def alloc_flat_grads(params, align=64):
+        """One zeroed fp32 buffer holding every parameter gradient (each view starts on a 256-byte
+        boundary: the kernels use 16-byte vector loads / reductions), returned as (flat, views)."""
+        offs, off = [], 0
+        for p in params:
+            offs.append(off)
+            off += (p.numel() + align - 1) // align * align
+        flat = torch.zeros(off, dtype=torch.float32, device=params[0].device)
+        return flat, [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
+
     # ---- forward / backward -------------------------------------------------------------------
     def forward(self, params, inp, hook=False, want_feats=False, keep_for_backward=True):
         """inp fp32 NCHW [N,3,H,W].  Returns (out or None, feats list (NHWC fp32) or None, saved arena)."""
@@ -102,11 +113,7 @@ class NAFNetEngine:
         N, _, H, W = inp.shape
         dev = inp.device
         if grads is None:
-            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-            grads, off = [], 0
-            for p in params:
-                grads.append(flat[off:off + p.numel()].view(p.shape))
-                off += p.numel()
+            grads = self.alloc_flat_grads(params)[1]
         k = ("work", N, H, W, dev)
         if k not in self._scratch:
             self._scratch[k] = torch.empty(self.lib.dcpt_nafnet_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8,

@@ -42,6 +42,15 @@ typedef void* dcpt_stream_t; /* cudaStream_t */
 int dcpt_abi_version(void);
 const char* dcpt_last_error(void);
 
+/* Instrumentation for bench.py (no reference counterpart; the reference's SRModel.nondist_profile,
+ * basicsr/models/sr_model.py:520-568, times whole forwards with CUDA events).
+ * dcpt_launch_count: kernels launched by this library so far (process-wide).
+ * dcpt_prof_enable(1): record CUDA events around every launch; dcpt_prof_dump aggregates them by kernel tag
+ * into "tag\tlaunches\ttotal_ms\tflops\tbytes" lines (synchronises the device), returns bytes written. */
+long long dcpt_launch_count(void);
+int dcpt_prof_enable(int on);
+long long dcpt_prof_dump(char* host_buf, long long cap);
+
 /* ------------------------------------------------------------------------------------------
  * Standalone ops (used by the tests and by callers that keep their own block structure).
  * ------------------------------------------------------------------------------------------ */

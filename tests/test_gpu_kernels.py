@@ -72,7 +72,8 @@ def test_gemm_wgrad_mn_major(ops, impl, O_, I_, Mpx):
     for splits in (1, 7):
         acc = torch.ones(O_, I_, device="cuda")
         ops.gemm(dY, X, a_mn=True, b_mn=True, splits=splits, accumulate_into=acc, impl=impl)
-        assert rel(acc - 1.0, ref) < 3e-5, splits
+        # fp32 accumulation over Mpx terms in a different order than torch: error grows ~ sqrt(Mpx) * 2^-24
+        assert rel(acc - 1.0, ref) < max(3e-5, 6e-7 * Mpx ** 0.5), splits
 
 
 def _desc(ops, **kw):

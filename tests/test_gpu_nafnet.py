@@ -62,9 +62,9 @@ def test_nafblock_vs_oracle(N, H, W, C):
             sd[k] = 1 + 0.1 * torch.randn(shape, generator=g)
         elif k.endswith("bias"):
             sd[k] = 0.1 * torch.randn(shape, generator=g)
-        else:
+        else:  # nn.Conv2d default init (kaiming_uniform(a=sqrt(5)) -> U(-1/sqrt(fan_in), 1/sqrt(fan_in))), as the reference
             fan_in = shape[1] * shape[2] * shape[3]
-            sd[k] = torch.randn(shape, generator=g) / fan_in ** 0.5
+            sd[k] = (torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5
     x = torch.randn(N, C, H, W, generator=g)
     dy = torch.randn(N, C, H, W, generator=g)
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
@@ -105,7 +105,9 @@ def test_nafnet_golden_engine(golden_dir):
     out, feats, saved = eng.forward(params, inp, want_feats=True)
     assert rel(out, z["out"]) < TOL_OUT
     for i, f in enumerate(feats):
-        assert rel(nchw(f), z[f"feat{i}"]) < TOL_OUT, i
+        # decoder features sit before the `+ inp` of the output: no large fp32 term dilutes the bf16-operand
+        # error.  The oracle's rounding hook predicts 3.4-3.7e-3 for this net (DESIGN.md numerics table).
+        assert rel(nchw(f), z[f"feat{i}"]) < 6e-3, i
     dout = torch.sign(out - gt) / out.numel()          # d/dout of L1Loss(mean) (losses/basic_loss.py:57-86)
     grads = eng.backward(params, inp, saved, dout)
     errs = {k: rel(g, z["g." + k]) for k, g in zip(names, grads)}
