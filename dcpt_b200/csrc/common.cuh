@@ -52,6 +52,12 @@ static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 
 
 int dcpt_num_sms();
 
+// Host-side TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point; gemm_sm100.cu).
+// 2-D: row-major bf16 [rows, cols], box 64 x box_rows, 128-byte swizzle (UMMA operand tiles).
+int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+// 4-D: bf16 NHWC [N, H, W, CH], box 64 x box_w x box_h x 1, no swizzle (stencil tiles, zero-filled halo).
+int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h);
+
 // ----------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------
@@ -146,6 +152,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// 4-D tiled load (NHWC activation tile with halo): coordinates (c, w, h, n); out-of-range -> zero fill.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

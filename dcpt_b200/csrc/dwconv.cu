@@ -1,291 +1,376 @@
-// Depthwise 3x3 convolution + SimpleGate (forward / backward), NHWC bf16.
+// Depthwise 3x3 convolution + SimpleGate (forward / backward), NHWC bf16, TMA-staged tiles.
 // Reference: NAFBlock.conv2 (nafnet_arch.py:96-104, groups = 2C, padding 1, bias) followed by
 // SimpleGate (nafnet_arch.py:77-80): g[:, j] = v[:, j] * v[:, j + C].
-// CUDA-core by design (36 FLOP/byte-pair at most; HBM/L1-bound).  Each thread owns one
-// 8-channel vector (16 bytes) — for the gate, the vector j and its partner j+C — and 4
-// neighbouring pixels along W, so each 16-byte load feeds up to three taps.
+//
+// CUDA-core by design (<= 36 FLOP per 4 bytes moved: HBM-bound, tensor cores have nothing to contract).
+// All three kernels share one structure:
+//   * persistent CTAs (8 warps); a CTA is bound to one 64-channel group, so the nine taps of its two
+//     channels per lane stay in registers for the whole launch, and walks a contiguous range of
+//     8 x 16-pixel tiles;
+//   * each tile (+1-pixel halo) is brought into shared memory by ONE 4-D TMA box per operand
+//     (cp.async.bulk.tensor, zero fill outside the image = the conv's zero padding, no bounds checks),
+//     double-buffered on mbarriers so the load of tile i+1 overlaps the math of tile i;
+//   * warp = one tile row, lane = 2 channels: the row is swept left to right with a 3x3 register window
+//     (3 conflict-free 128-byte LDS per operand per pixel), stores are 128-byte coalesced;
+//   * column sums (SCA pool, bias / weight gradients) live in registers across tiles and are reduced once
+//     per CTA (once per image for the pool).
 #include "elementwise.cuh"
 
 namespace {
 
-constexpr int PX = 4;  // pixels along W per thread
+constexpr int TH = 8, TW = 16, NWARP = 8;
+constexpr int HH = TH + 2, HWD = TW + 2;
+constexpr int BOX_ELEMS = HH * HWD * 64;       // one halo box: 10 x 18 pixels x 64 channels
+constexpr int BOX_BYTES = BOX_ELEMS * 2;       // 23040
+constexpr int DG_ELEMS = TH * TW * 64;         // interior box (no halo)
+constexpr int DG_BYTES = DG_ELEMS * 2;         // 16384
 
-// weights in smem as [tap][channel] fp32, bias [channel]
-__device__ __forceinline__ void load_dw_weights(float* s_w, float* s_b, const float* __restrict__ w, const float* __restrict__ b,
-                                                int CH) {
-  for (int i = threadIdx.x; i < CH * 9; i += blockDim.x) {
-    const int c = i / 9, tap = i - c * 9;
-    s_w[tap * CH + c] = w[i];
+__device__ __forceinline__ float2 lds_bf2(const bf16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ void st_bf2(bf16* p, float2 v) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+}
+__device__ __forceinline__ float2 round_bf2(float2 v) { return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y)); }
+__device__ __forceinline__ void fma2(float2& acc, float2 a, float2 b) {
+  acc.x = fmaf(a.x, b.x, acc.x);
+  acc.y = fmaf(a.y, b.y, acc.y);
+}
+// nine taps of two consecutive channels: w[c][tap] fp32, c = c0, c0+1
+__device__ __forceinline__ void load_taps(float2 (&wt)[9], const float* __restrict__ w, int c0) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wt[k] = make_float2(__ldg(w + (size_t)c0 * 9 + k), __ldg(w + (size_t)(c0 + 1) * 9 + k));
+}
+
+struct Tiles {
+  int tiles_w, tiles_h, per_img, total, t0, t1;
+  __device__ Tiles(int N, int H, int W) {
+    tiles_w = (W + TW - 1) / TW;
+    tiles_h = (H + TH - 1) / TH;
+    per_img = tiles_w * tiles_h;
+    total = N * per_img;
+    const int chunk = (total + gridDim.x - 1) / gridDim.x;  // contiguous range per CTA
+    t0 = min(total, (int)blockIdx.x * chunk);
+    t1 = min(total, t0 + chunk);
   }
-  if (s_b)
-    for (int i = threadIdx.x; i < CH; i += blockDim.x) s_b[i] = b[i];
-}
-
-__device__ __forceinline__ void fma8(float (&acc)[8], const float (&x)[8], const float* wp) {
-  const float4 w0 = *reinterpret_cast<const float4*>(wp);
-  const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
-  acc[0] = fmaf(x[0], w0.x, acc[0]); acc[1] = fmaf(x[1], w0.y, acc[1]);
-  acc[2] = fmaf(x[2], w0.z, acc[2]); acc[3] = fmaf(x[3], w0.w, acc[3]);
-  acc[4] = fmaf(x[4], w1.x, acc[4]); acc[5] = fmaf(x[5], w1.y, acc[5]);
-  acc[6] = fmaf(x[6], w1.z, acc[6]); acc[7] = fmaf(x[7], w1.w, acc[7]);
-}
+  __device__ void decode(int t, int& n, int& h0, int& w0) const {
+    n = t / per_img;
+    const int r = t - n * per_img;
+    h0 = (r / tiles_w) * TH;
+    w0 = (r % tiles_w) * TW;
+  }
+};
 
 // ------------------------------- forward --------------------------------------
-__global__ void __launch_bounds__(256)
-dwgate_fwd_kernel(const bf16* __restrict__ u, const float* __restrict__ w2, const float* __restrict__ b2, bf16* __restrict__ g,
-                  float* __restrict__ pool, int H, int W, int C) {
-  extern __shared__ float smem[];
-  const int C2 = 2 * C, CV = C / 8, WQ = (W + PX - 1) / PX;
-  float* s_w = smem;             // [9][2C]
-  float* s_b = s_w + 9 * C2;     // [2C]
-  float* s_pool = s_b + C2;      // [C]
-  load_dw_weights(s_w, s_b, w2, b2, C2);
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_pool[i] = 0.f;
+__global__ void __launch_bounds__(NWARP * 32)
+dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restrict__ w2, const float* __restrict__ b2,
+                  bf16* __restrict__ g, float* __restrict__ pool, int N, int H, int W, int C) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  __shared__ uint64_t full[2];
+  __shared__ float2 s_pool[NWARP][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = blockIdx.y, c2 = cg * 64 + lane * 2;
+  const bool chan_ok = c2 < C;
+  const int ca = chan_ok ? c2 : 0, cb = C + ca;
+  float2 wa[9], wb[9];
+  load_taps(wa, w2, ca);
+  load_taps(wb, w2, cb);
+  const float2 ba = make_float2(__ldg(b2 + ca), __ldg(b2 + ca + 1)), bb = make_float2(__ldg(b2 + cb), __ldg(b2 + cb + 1));
+  const Tiles T(N, H, W);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmU);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
-
-  const int n = blockIdx.y;
-  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long items = (long long)H * WQ * CV;
-  if (item < items) {
-    const int cv = (int)(item % CV);
-    const int wq = (int)((item / CV) % WQ);
-    const int h = (int)(item / ((long long)CV * WQ));
-    const int w0 = wq * PX;
-    const int ca = cv * 8, cb = C + cv * 8;
-    float a[PX][8], b[PX][8];
+  auto issue = [&](int t, int s) {
+    int n, h0, w0;
+    T.decode(t, n, h0, w0);
+    uint8_t* dst = smem + (size_t)s * 2 * BOX_BYTES;
+    mbar_arrive_expect_tx(&full[s], 2 * BOX_BYTES);
+    tma_load_4d(dst, &tmU, &full[s], cg * 64, w0 - 1, h0 - 1, n);
+    tma_load_4d(dst + BOX_BYTES, &tmU, &full[s], C + cg * 64, w0 - 1, h0 - 1, n);
+  };
+  if (threadIdx.x == 0 && T.t0 < T.t1) issue(T.t0, 0);
+  float2 psum = make_float2(0.f, 0.f);
+  int cur_n = -1;
+  auto flush_pool = [&](int n) {  // CTA-uniform
+    s_pool[warp][lane] = psum;
+    __syncthreads();
+    if (warp == 0 && chan_ok) {
+      float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int p = 0; p < PX; ++p)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a[p][i] = s_b[ca + i];
-        b[p][i] = s_b[cb + i];
+      for (int k = 0; k < NWARP; ++k) {
+        t.x += s_pool[k][lane].x;
+        t.y += s_pool[k][lane].y;
       }
-    const bf16* un = u + (size_t)n * H * W * C2;
+      atomicAdd(pool + (size_t)n * C + c2, t.x);
+      atomicAdd(pool + (size_t)n * C + c2 + 1, t.y);
+    }
+    psum = make_float2(0.f, 0.f);
+  };
+  int it = 0;
+  for (int t = T.t0; t < T.t1; ++t, ++it) {
+    const int s = it & 1;
+    if (threadIdx.x == 0 && t + 1 < T.t1) issue(t + 1, s ^ 1);
+    int n, h0, w0;
+    T.decode(t, n, h0, w0);
+    if (n != cur_n) {
+      if (cur_n >= 0) flush_pool(cur_n);
+      cur_n = n;
+    }
+    mbar_wait(&full[s], (it >> 1) & 1);
+    const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * 2 * BOX_BYTES) + lane * 2;
+    const bf16* sB = sA + BOX_ELEMS;
+    const int h = h0 + warp;  // warp = tile row (TH == NWARP)
+    bf16* grow = g + (((size_t)n * H + h) * W + w0) * C + ca;
+    float2 A[3][3], B[3][3];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int hh = h + r - 1;
-      if (hh < 0 || hh >= H) continue;
+    for (int x = 0; x < HWD; ++x) {
 #pragma unroll
-      for (int col = 0; col < PX + 2; ++col) {
-        const int ww = w0 + col - 1;
-        if (ww < 0 || ww >= W) continue;
-        const bf16* up = un + ((size_t)hh * W + ww) * C2;
-        float xa[8], xb[8];
-        unpack8(ldg16(up + ca), xa);
-        unpack8(ldg16(up + cb), xb);
+      for (int r = 0; r < 3; ++r) {
+        A[r][x % 3] = lds_bf2(sA + ((warp + r) * HWD + x) * 64);
+        B[r][x % 3] = lds_bf2(sB + ((warp + r) * HWD + x) * 64);
+      }
+      if (x >= 2) {
+        float2 a = ba, b = bb;
 #pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          const int kx = col - p;  // tap column for output pixel p
-          if (kx >= 0 && kx <= 2) {
-            const float* wp = s_w + (r * 3 + kx) * C2;
-            fma8(a[p], xa, wp + ca);
-            fma8(b[p], xb, wp + cb);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            fma2(a, A[r][(x - 2 + d) % 3], wa[r * 3 + d]);
+            fma2(b, B[r][(x - 2 + d) % 3], wb[r * 3 + d]);
           }
+        const int ox = x - 2;
+        if (chan_ok && h < H && w0 + ox < W) {
+          const float2 gv = round_bf2(make_float2(a.x * b.x, a.y * b.y));
+          st_bf2(grow + (size_t)ox * C, gv);
+          psum.x += gv.x;
+          psum.y += gv.y;
         }
       }
     }
-    float psum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int p = 0; p < PX; ++p) {
-      if (w0 + p < W) {
-        float gv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          gv[i] = bf16_round(a[p][i] * b[p][i]);
-          psum[i] += gv[i];
-        }
-        stg16(g + (((size_t)n * H + h) * W + w0 + p) * C + ca, pack8(gv));
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&s_pool[ca + i], psum[i]);
+    __syncthreads();  // stage s may be refilled by the next-but-one issue
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    const float v = s_pool[i];
-    if (v != 0.f) atomicAdd(pool + (size_t)n * C + i, v);
-  }
+  if (cur_n >= 0) flush_pool(cur_n);
 }
 
 // --------------------------- backward, part a ---------------------------------
-// One thread: a fixed channel-vector pair (j, j+C) and a strided set of pixels of one image.
-// dg = dgs*s + t;  a,b = dwconv(u)+bias (recomputed);  du2_a = dg*b, du2_b = dg*a;
+// dg = dgs*s + t;  a,b = dwconv(u)+bias (recomputed);  du2_a = dg*b, du2_b = dg*a  (stored bf16);
 // dW2[c][tap] += du2[c] * u[px+tap][c];  db2[c] += du2[c].
-__global__ void __launch_bounds__(128)
-dwgate_bwd_a_kernel(const bf16* __restrict__ dgs, const float* __restrict__ s, const float* __restrict__ t,
-                    const bf16* __restrict__ u, const float* __restrict__ w2, const float* __restrict__ b2,
-                    bf16* __restrict__ du2, float* __restrict__ dw2, float* __restrict__ db2, int H, int W, int C, int cvb) {
-  extern __shared__ float smem[];
-  const int C2 = 2 * C, CV = C / 8;
-  float* s_w = smem;            // [9][2C]
-  float* s_b = s_w + 9 * C2;    // [2C]
-  float* s_red = s_b + C2;      // [cvb][160]
-  load_dw_weights(s_w, s_b, w2, b2, C2);
-  for (int i = threadIdx.x; i < cvb * 160; i += blockDim.x) s_red[i] = 0.f;
+__global__ void __launch_bounds__(NWARP * 32)
+dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmD, const float* __restrict__ s_sca,
+                    const float* __restrict__ t_sca, const float* __restrict__ w2, const float* __restrict__ b2,
+                    bf16* __restrict__ du2, float* __restrict__ dw2, float* __restrict__ db2, int N, int H, int W, int C) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  constexpr int STAGE_BYTES = 2 * BOX_BYTES + DG_BYTES;
+  float2* s_red = reinterpret_cast<float2*>(smem + 2 * STAGE_BYTES);  // [NWARP][20][32]
+  __shared__ uint64_t full[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = blockIdx.y, c2 = cg * 64 + lane * 2;
+  const bool chan_ok = c2 < C;
+  const int ca = chan_ok ? c2 : 0, cb = C + ca;
+  const int C2 = 2 * C;
+  float2 wa[9], wb[9], gA[9], gB[9];
+  load_taps(wa, w2, ca);
+  load_taps(wb, w2, cb);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) gA[k] = gB[k] = make_float2(0.f, 0.f);
+  float2 dbA = make_float2(0.f, 0.f), dbB = dbA;
+  const float2 ba = make_float2(__ldg(b2 + ca), __ldg(b2 + ca + 1)), bb = make_float2(__ldg(b2 + cb), __ldg(b2 + cb + 1));
+  const Tiles T(N, H, W);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmU);
+    tma_prefetch_desc(&tmD);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
-
-  const int n = blockIdx.z;
-  const int cvl = threadIdx.x % cvb;
-  const int pl = threadIdx.x / cvb;
-  const int npl = blockDim.x / cvb;
-  const int cv = blockIdx.y * cvb + cvl;
-  const int HW = H * W;
-  float accA[9][8], accB[9][8], dbA[8], dbB[8];
+  auto issue = [&](int t, int s) {
+    int n, h0, w0;
+    T.decode(t, n, h0, w0);
+    uint8_t* dst = smem + (size_t)s * STAGE_BYTES;
+    mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+    tma_load_4d(dst, &tmU, &full[s], cg * 64, w0 - 1, h0 - 1, n);
+    tma_load_4d(dst + BOX_BYTES, &tmU, &full[s], C + cg * 64, w0 - 1, h0 - 1, n);
+    tma_load_4d(dst + 2 * BOX_BYTES, &tmD, &full[s], cg * 64, w0, h0, n);
+  };
+  if (threadIdx.x == 0 && T.t0 < T.t1) issue(T.t0, 0);
+  int it = 0;
+  for (int t = T.t0; t < T.t1; ++t, ++it) {
+    const int s = it & 1;
+    if (threadIdx.x == 0 && t + 1 < T.t1) issue(t + 1, s ^ 1);
+    int n, h0, w0;
+    T.decode(t, n, h0, w0);
+    const float2 sv = make_float2(__ldg(s_sca + (size_t)n * C + ca), __ldg(s_sca + (size_t)n * C + ca + 1));
+    const float2 tv = make_float2(__ldg(t_sca + (size_t)n * C + ca), __ldg(t_sca + (size_t)n * C + ca + 1));
+    mbar_wait(&full[s], (it >> 1) & 1);
+    const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * STAGE_BYTES) + lane * 2;
+    const bf16* sB = sA + BOX_ELEMS;
+    const bf16* sD = sA + 2 * BOX_ELEMS;
+    const int h = h0 + warp;
+    bf16* orow = du2 + (((size_t)n * H + h) * W + w0) * C2;
+    float2 A[3][3], B[3][3];
 #pragma unroll
-  for (int k = 0; k < 9; ++k)
+    for (int x = 0; x < HWD; ++x) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) accA[k][i] = accB[k][i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) dbA[i] = dbB[i] = 0.f;
-
-  if (cv < CV) {
-    const int ca = cv * 8, cb = C + cv * 8;
-    float sv[8], tv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sv[i] = s[(size_t)n * C + ca + i];
-      tv[i] = t[(size_t)n * C + ca + i];
-    }
-    const bf16* un = u + (size_t)n * HW * C2;
-    for (int px = blockIdx.x * npl + pl; px < HW; px += gridDim.x * npl) {
-      const int h = px / W, w = px - h * W;
-      float a[8], b[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a[i] = s_b[ca + i];
-        b[i] = s_b[cb + i];
+      for (int r = 0; r < 3; ++r) {
+        A[r][x % 3] = lds_bf2(sA + ((warp + r) * HWD + x) * 64);
+        B[r][x % 3] = lds_bf2(sB + ((warp + r) * HWD + x) * 64);
       }
+      if (x >= 2) {
+        const int ox = x - 2;
+        float2 a = ba, b = bb;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
-        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-        const bf16* up = un + ((size_t)hh * W + ww) * C2;
-        float xa[8], xb[8];
-        unpack8(ldg16(up + ca), xa);
-        unpack8(ldg16(up + cb), xb);
-        fma8(a, xa, s_w + k * C2 + ca);
-        fma8(b, xb, s_w + k * C2 + cb);
-      }
-      float dg[8], da[8], db[8];
-      unpack8(ldg16(dgs + ((size_t)n * HW + px) * C + ca), dg);
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = fmaf(dg[i], sv[i], tv[i]);
-        da[i] = d * b[i];
-        db[i] = d * a[i];
-        dbA[i] += da[i];
-        dbB[i] += db[i];
-      }
-      bf16* op = du2 + ((size_t)n * HW + px) * C2;
-      stg16(op + ca, pack8(da));
-      stg16(op + cb, pack8(db));
+          for (int d = 0; d < 3; ++d) {
+            fma2(a, A[r][(x - 2 + d) % 3], wa[r * 3 + d]);
+            fma2(b, B[r][(x - 2 + d) % 3], wb[r * 3 + d]);
+          }
+        if (chan_ok && h < H && w0 + ox < W) {
+          const float2 dgv = lds_bf2(sD + (warp * TW + ox) * 64);
+          const float2 dg = make_float2(fmaf(dgv.x, sv.x, tv.x), fmaf(dgv.y, sv.y, tv.y));
+          const float2 da = make_float2(dg.x * b.x, dg.y * b.y), db = make_float2(dg.x * a.x, dg.y * a.y);
+          st_bf2(orow + (size_t)ox * C2 + ca, da);
+          st_bf2(orow + (size_t)ox * C2 + cb, db);
+          dbA.x += da.x; dbA.y += da.y;
+          dbB.x += db.x; dbB.y += db.y;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
-        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-        const bf16* up = un + ((size_t)hh * W + ww) * C2;
-        float xa[8], xb[8];
-        unpack8(ldg16(up + ca), xa);
-        unpack8(ldg16(up + cb), xb);
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          accA[k][i] = fmaf(da[i], xa[i], accA[k][i]);
-          accB[k][i] = fmaf(db[i], xb[i], accB[k][i]);
+            for (int d = 0; d < 3; ++d) {
+              fma2(gA[r * 3 + d], da, A[r][(x - 2 + d) % 3]);
+              fma2(gB[r * 3 + d], db, B[r][(x - 2 + d) % 3]);
+            }
         }
       }
     }
-    float* red = s_red + cvl * 160;
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&red[k * 8 + i], accA[k][i]);
-        atomicAdd(&red[72 + k * 8 + i], accB[k][i]);
-      }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&red[144 + i], dbA[i]);
-      atomicAdd(&red[152 + i], dbB[i]);
-    }
+    __syncthreads();
   }
+  // CTA reduction of the 20 x 64 channel sums, then one atomic per value
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    s_red[(warp * 20 + k) * 32 + lane] = gA[k];
+    s_red[(warp * 20 + 9 + k) * 32 + lane] = gB[k];
+  }
+  s_red[(warp * 20 + 18) * 32 + lane] = dbA;
+  s_red[(warp * 20 + 19) * 32 + lane] = dbB;
   __syncthreads();
-  for (int idx = threadIdx.x; idx < cvb * 160; idx += blockDim.x) {
-    const int l = idx / 160, e = idx - l * 160;
-    const int cvg = blockIdx.y * cvb + l;
-    if (cvg >= CV) continue;
-    const float v = s_red[idx];
-    if (e < 144) {
-      const int half = e / 72, k = (e % 72) / 8, i = e % 8;
-      const int c = half * C + cvg * 8 + i;
-      atomicAdd(dw2 + (size_t)c * 9 + k, v);
+  for (int idx = threadIdx.x; idx < 20 * 32; idx += blockDim.x) {
+    const int item = idx >> 5, ln = idx & 31;
+    const int cc = cg * 64 + ln * 2;
+    if (cc >= C) continue;
+    float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < NWARP; ++k) {
+      const float2 e = s_red[(k * 20 + item) * 32 + ln];
+      v.x += e.x;
+      v.y += e.y;
+    }
+    if (item < 18) {
+      const int half = item / 9, tap = item % 9;
+      const int c = half * C + cc;
+      atomicAdd(dw2 + (size_t)c * 9 + tap, v.x);
+      atomicAdd(dw2 + (size_t)(c + 1) * 9 + tap, v.y);
     } else {
-      const int half = (e - 144) / 8, i = e % 8;
-      atomicAdd(db2 + half * C + cvg * 8 + i, v);
+      const int c = (item - 18) * C + cc;
+      atomicAdd(db2 + c, v.x);
+      atomicAdd(db2 + c + 1, v.y);
     }
   }
 }
 
 // --------------------------- backward, part b ---------------------------------
 // du[px][c] = sum_{ky,kx} du2[h-(ky-1), w-(kx-1)][c] * w2[c][ky][kx]; colsum[c] += sum_px du.
-__global__ void __launch_bounds__(256)
-dwconv_bwd_data_kernel(const bf16* __restrict__ du2, const float* __restrict__ w2, bf16* __restrict__ du,
-                       float* __restrict__ colsum, int H, int W, int CH) {
-  extern __shared__ float smem[];
-  const int CV = CH / 8, WQ = (W + PX - 1) / PX;
-  float* s_w = smem;            // [9][CH]
-  float* s_cs = s_w + 9 * CH;   // [CH]
-  load_dw_weights(s_w, nullptr, w2, nullptr, CH);
-  for (int i = threadIdx.x; i < CH; i += blockDim.x) s_cs[i] = 0.f;
+__global__ void __launch_bounds__(NWARP * 32)
+dwconv_bwd_data_kernel(const __grid_constant__ CUtensorMap tmG, const float* __restrict__ w2, bf16* __restrict__ du,
+                       float* __restrict__ colsum, int N, int H, int W, int CH) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  __shared__ uint64_t full[2];
+  __shared__ float2 s_cs[NWARP][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = blockIdx.y, c2 = cg * 64 + lane * 2;
+  const bool chan_ok = c2 < CH;
+  const int c0 = chan_ok ? c2 : 0;
+  float2 wt[9], wf[9];
+  load_taps(wt, w2, c0);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wf[k] = wt[8 - k];  // window offset (r, d) pairs with tap (2-r, 2-d)
+  const Tiles T(N, H, W);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmG);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
-  const int n = blockIdx.y;
-  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long items = (long long)H * WQ * CV;
-  if (item < items) {
-    const int cv = (int)(item % CV);
-    const int wq = (int)((item / CV) % WQ);
-    const int h = (int)(item / ((long long)CV * WQ));
-    const int w0 = wq * PX, c0 = cv * 8;
-    float acc[PX][8];
+  auto issue = [&](int t, int s) {
+    int n, h0, w0;
+    T.decode(t, n, h0, w0);
+    mbar_arrive_expect_tx(&full[s], BOX_BYTES);
+    tma_load_4d(smem + (size_t)s * BOX_BYTES, &tmG, &full[s], cg * 64, w0 - 1, h0 - 1, n);
+  };
+  if (threadIdx.x == 0 && T.t0 < T.t1) issue(T.t0, 0);
+  float2 cs = make_float2(0.f, 0.f);
+  int it = 0;
+  for (int t = T.t0; t < T.t1; ++t, ++it) {
+    const int s = it & 1;
+    if (threadIdx.x == 0 && t + 1 < T.t1) issue(t + 1, s ^ 1);
+    int n, h0, w0;
+    T.decode(t, n, h0, w0);
+    mbar_wait(&full[s], (it >> 1) & 1);
+    const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * BOX_BYTES) + lane * 2;
+    const int h = h0 + warp;
+    bf16* orow = du + (((size_t)n * H + h) * W + w0) * CH + c0;
+    float2 A[3][3];
 #pragma unroll
-    for (int p = 0; p < PX; ++p)
+    for (int x = 0; x < HWD; ++x) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
-    const bf16* dn = du2 + (size_t)n * H * W * CH;
+      for (int r = 0; r < 3; ++r) A[r][x % 3] = lds_bf2(sA + ((warp + r) * HWD + x) * 64);
+      if (x >= 2) {
+        const int ox = x - 2;
+        float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int hh = h + r - 1;  // source row; uses tap ky = 2 - r  (h = hh + ky - 1)
-      if (hh < 0 || hh >= H) continue;
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int col = 0; col < PX + 2; ++col) {
-        const int ww = w0 + col - 1;
-        if (ww < 0 || ww >= W) continue;
-        float x[8];
-        unpack8(ldg16(dn + ((size_t)hh * W + ww) * CH + c0), x);
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          const int d = col - p;  // source col offset + 1 in [0,2]  -> tap kx = 2 - d
-          if (d >= 0 && d <= 2) fma8(acc[p], x, s_w + ((2 - r) * 3 + (2 - d)) * CH + c0);
+          for (int d = 0; d < 3; ++d) fma2(a, A[r][(x - 2 + d) % 3], wf[r * 3 + d]);
+        if (chan_ok && h < H && w0 + ox < W) {
+          st_bf2(orow + (size_t)ox * CH, a);
+          cs.x += a.x;
+          cs.y += a.y;
         }
       }
     }
-    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int p = 0; p < PX; ++p) {
-      if (w0 + p < W) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cs[i] += acc[p][i];
-        stg16(du + (((size_t)n * H + h) * W + w0 + p) * CH + c0, pack8(acc[p]));
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&s_cs[c0 + i], cs[i]);
+    __syncthreads();
   }
+  s_cs[warp][lane] = cs;
   __syncthreads();
-  if (colsum)
-    for (int i = threadIdx.x; i < CH; i += blockDim.x) {
-      const float v = s_cs[i];
-      if (v != 0.f) atomicAdd(colsum + i, v);
+  if (colsum && warp == 0 && chan_ok) {
+    float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < NWARP; ++k) {
+      v.x += s_cs[k][lane].x;
+      v.y += s_cs[k][lane].y;
     }
+    atomicAdd(colsum + c2, v.x);
+    atomicAdd(colsum + c2 + 1, v.y);
+  }
+}
+
+// persistent grid: x = CTAs per channel group, y = channel groups
+dim3 pick_grid(int N, int H, int W, int CHpair, int ctas_per_sm) {
+  const int groups = ceil_div(CHpair, 64);
+  const int tiles = N * ceil_div(H, TH) * ceil_div(W, TW);
+  int slots = (dcpt_num_sms() * ctas_per_sm) / groups;
+  if (slots < 1) slots = 1;
+  if (slots > tiles) slots = tiles;
+  return dim3(slots, groups, 1);
 }
 
 template <typename K>
@@ -299,12 +384,12 @@ int set_smem(K kern, size_t bytes) {
 int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, float* pool, int N, int H, int W, int C,
                       cudaStream_t st) {
   DCPT_CHECK_ARG(C % 8 == 0 && C >= 8 && N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "dwgate_fwd: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
-  const size_t smem = ((size_t)9 * 2 * C + 2 * C + C) * sizeof(float);
+  CUtensorMap tmU;
+  DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
+  const size_t smem = 128 + (size_t)2 * 2 * BOX_BYTES;
   DCPT_TRY(set_smem(dwgate_fwd_kernel, smem));
-  const long long items = (long long)H * ceil_div(W, PX) * (C / 8);
-  dim3 grid((unsigned)ceil_div_ll(items, 256), N);
   DCPT_PROF("dwgate_fwd", 38.0 * N * H * W * C, 6.0 * N * H * W * C, st);
-  dwgate_fwd_kernel<<<grid, 256, smem, st>>>(u, w2, b2, g, pool, H, W, C);
+  dwgate_fwd_kernel<<<pick_grid(N, H, W, C, 2), NWARP * 32, smem, st>>>(tmU, w2, b2, g, pool, N, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -312,19 +397,13 @@ int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, 
 int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const bf16* u, const float* w2, const float* b2,
                         bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st) {
   DCPT_CHECK_ARG(C % 8 == 0 && C >= 8 && N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "dwgate_bwd_a: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
-  const int CV = C / 8;
-  int cvb = 1;
-  while (cvb < CV && cvb < 32) cvb <<= 1;  // channel vectors per block (power of two <= 32)
-  const int npl = 128 / cvb;
-  const int HW = H * W;
-  // ~32 pixels per thread keeps the partial-sum flush small without starving the SMs.
-  int gx = ceil_div(HW, npl * 32);
-  if (gx < 1) gx = 1;
-  const size_t smem = ((size_t)9 * 2 * C + 2 * C + (size_t)cvb * 160) * sizeof(float);
+  CUtensorMap tmU, tmD;
+  DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
+  DCPT_TRY(make_tmap_nhwc(&tmD, dgs, N, H, W, C, TW, TH));
+  const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
   DCPT_TRY(set_smem(dwgate_bwd_a_kernel, smem));
-  dim3 grid(gx, ceil_div(CV, cvb), N);
   DCPT_PROF("dwgate_bwd_a", 80.0 * N * H * W * C, 10.0 * N * H * W * C, st);
-  dwgate_bwd_a_kernel<<<grid, 128, smem, st>>>(dgs, s, t, u, w2, b2, du2, dw2, db2, H, W, C, cvb);
+  dwgate_bwd_a_kernel<<<pick_grid(N, H, W, C, 1), NWARP * 32, smem, st>>>(tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -332,12 +411,12 @@ int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const b
 int dwconv_bwd_data_launch(const bf16* du2, const float* w2, bf16* du, float* colsum, int N, int H, int W, int C2,
                            cudaStream_t st) {
   DCPT_CHECK_ARG(C2 % 8 == 0 && C2 >= 8, DCPT_E_SHAPE, "dwconv_bwd_data: bad channel count %d", C2);
-  const size_t smem = ((size_t)9 * C2 + C2) * sizeof(float);
+  CUtensorMap tmG;
+  DCPT_TRY(make_tmap_nhwc(&tmG, du2, N, H, W, C2, HWD, HH));
+  const size_t smem = 128 + (size_t)2 * BOX_BYTES;
   DCPT_TRY(set_smem(dwconv_bwd_data_kernel, smem));
-  const long long items = (long long)H * ceil_div(W, PX) * (C2 / 8);
-  dim3 grid((unsigned)ceil_div_ll(items, 256), N);
   DCPT_PROF("dwconv_bwd_data", 18.0 * N * H * W * C2, 4.0 * N * H * W * C2, st);
-  dwconv_bwd_data_kernel<<<grid, 256, smem, st>>>(du2, w2, du, colsum, H, W, C2);
+  dwconv_bwd_data_kernel<<<pick_grid(N, H, W, C2, 4), NWARP * 32, smem, st>>>(tmG, w2, du, colsum, N, H, W, C2);
   DCPT_LAUNCH_CHECK();
   return 0;
 }

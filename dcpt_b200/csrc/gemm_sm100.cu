@@ -229,17 +229,19 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+}  // namespace
+
 // Row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = 64 x box_rows, 128B swizzle.
-int make_tmap(CUtensorMap* tm, const bf16* ptr, long long rows, long long cols, long long ld, int box_rows) {
+int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   DCPT_CHECK_ARG(fn != nullptr, DCPT_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   DCPT_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0, DCPT_E_ALIGN,
-                 "GEMM operand must be 16-byte aligned with ld %% 8 == 0 (ptr=%p ld=%lld)", (const void*)ptr, ld);
+                 "GEMM operand must be 16-byte aligned with ld %% 8 == 0 (ptr=%p ld=%lld)", ptr, ld);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCPT_CHECK_ARG(r == CUDA_SUCCESS, DCPT_E_DRIVER, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%d",
@@ -247,14 +249,33 @@ int make_tmap(CUtensorMap* tm, const bf16* ptr, long long rows, long long cols, 
   return 0;
 }
 
+int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  DCPT_CHECK_ARG(fn != nullptr, DCPT_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  DCPT_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (CH % 8) == 0, DCPT_E_ALIGN,
+                 "NHWC tensor must be 16-byte aligned with C %% 8 == 0 (ptr=%p C=%d)", ptr, CH);
+  cuuint64_t dims[4] = {(cuuint64_t)CH, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)CH * 2, (cuuint64_t)W * CH * 2, (cuuint64_t)H * W * CH * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCPT_CHECK_ARG(r == CUDA_SUCCESS, DCPT_E_DRIVER, "cuTensorMapEncodeTiled(4d) failed (%d): N=%d H=%d W=%d C=%d box=%dx%d", (int)r, N,
+                 H, W, CH, box_w, box_h);
+  return 0;
+}
+
+namespace {
+
 template <int BN, int EPI, bool A_MN, bool B_MN>
 int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   using C = Cfg<BN>;
   CUtensorMap tmA, tmB;
-  if (!g.a_mn) DCPT_TRY(make_tmap(&tmA, g.A, g.M, g.K, g.lda, BM));
-  else DCPT_TRY(make_tmap(&tmA, g.A, g.K, g.M, g.lda, 64));
-  if (!g.b_mn) DCPT_TRY(make_tmap(&tmB, g.B, g.N, g.K, g.ldb, BN));
-  else DCPT_TRY(make_tmap(&tmB, g.B, g.K, g.N, g.ldb, 64));
+  if (!g.a_mn) DCPT_TRY(make_tmap_2d(&tmA, g.A, g.M, g.K, g.lda, BM));
+  else DCPT_TRY(make_tmap_2d(&tmA, g.A, g.K, g.M, g.lda, 64));
+  if (!g.b_mn) DCPT_TRY(make_tmap_2d(&tmB, g.B, g.N, g.K, g.ldb, BN));
+  else DCPT_TRY(make_tmap_2d(&tmB, g.B, g.K, g.N, g.ldb, 64));
 
   const int tiles_m = ceil_div(g.M, BM), tiles_n = ceil_div(g.N, BN);
   const int num_kb = ceil_div(g.K, BK);

@@ -65,27 +65,40 @@ sca_ds_reduce_kernel(const bf16* __restrict__ dgs, const bf16* __restrict__ g, f
   }
 }
 
-// t[n][ci] = (1/HW) sum_co W[co][ci] ds[n][co];  dW[co][ci] += (1/HW) sum_n ds[n][co] pool[n][ci];  db[co] += sum_n ds[n][co]
-__global__ void sca_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ pool, const float* __restrict__ w,
-                               float* __restrict__ t, float* __restrict__ dw, float* __restrict__ db, int N, int C, float inv_hw) {
+// dW[co][ci] += (1/HW) sum_n ds[n][co] pool[n][ci];  db[co] += sum_n ds[n][co]
+__global__ void sca_bwd_w_kernel(const float* __restrict__ ds, const float* __restrict__ pool, float* __restrict__ dw,
+                                 float* __restrict__ db, int N, int C, float inv_hw) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long CC = (long long)C * C;
   if (i < CC) {
     const int co = (int)(i / C), ci = (int)(i - (long long)co * C);
     float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc = fmaf(ds[(size_t)n * C + co], pool[(size_t)n * C + ci], acc);
+    for (int n = 0; n < N; ++n) acc = fmaf(__ldg(ds + (size_t)n * C + co), __ldg(pool + (size_t)n * C + ci), acc);
     dw[i] += acc * inv_hw;
-  } else if (i < CC + (long long)N * C) {
-    const long long j = i - CC;
-    const int n = (int)(j / C), ci = (int)(j - (long long)n * C);
-    float acc = 0.f;
-    for (int co = 0; co < C; ++co) acc = fmaf(w[(size_t)co * C + ci], ds[(size_t)n * C + co], acc);
-    t[j] = acc * inv_hw;
-  } else if (i < CC + (long long)N * C + C) {
-    const int co = (int)(i - CC - (long long)N * C);
+  } else if (i < CC + C) {
+    const int co = (int)(i - CC);
     float acc = 0.f;
     for (int n = 0; n < N; ++n) acc += ds[(size_t)n * C + co];
     db[co] += acc;
+  }
+}
+
+// t[n][ci] = (1/HW) sum_co W[co][ci] ds[n][co]: block = 32 ci x 8 warps splitting co; grid (C/32, N)
+__global__ void __launch_bounds__(256)
+sca_bwd_t_kernel(const float* __restrict__ ds, const float* __restrict__ w, float* __restrict__ t, int C, float inv_hw) {
+  __shared__ float s_part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ci = blockIdx.x * 32 + lane, n = blockIdx.y;
+  float acc = 0.f;
+  if (ci < C)
+    for (int co = warp; co < C; co += 8) acc = fmaf(__ldg(w + (size_t)co * C + ci), __ldg(ds + (size_t)n * C + co), acc);
+  s_part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && ci < C) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += s_part[k][lane];
+    t[(size_t)n * C + ci] = v * inv_hw;
   }
 }
 
@@ -333,9 +346,12 @@ int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int H
 
 int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t, float* dw, float* db, int N, int C, int HW,
                    cudaStream_t st) {
-  const long long total = (long long)C * C + (long long)N * C + C;
+  const long long total = (long long)C * C + C;
   DCPT_PROF("sca_bwd", 4.0 * N * C * C, 12.0 * C * C, st);
-  sca_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(ds, pool, w, t, dw, db, N, C, 1.f / (float)HW);
+  sca_bwd_w_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(ds, pool, dw, db, N, C, 1.f / (float)HW);
+  DCPT_LAUNCH_CHECK();
+  dim3 grid(ceil_div(C, 32), N);
+  sca_bwd_t_kernel<<<grid, 256, 0, st>>>(ds, w, t, C, 1.f / (float)HW);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
