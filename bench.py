@@ -233,7 +233,7 @@ def run_ours(args):
     # ---------------- per-kernel attribution (one extra, untimed, profiled step) ----------------
     roof = None
     if rank == 0:
-        lib.dcpt_prof_enable(1)
+        lib.dcpt_prof_enable(2 if args.shapes else 1)
         step()
         rows = prof_table(lib)
         lib.dcpt_prof_enable(0)
@@ -333,6 +333,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE.json configs[1]: 16)")
     ap.add_argument("--breakdown", action="store_true", help="write gpurun_out/kernel_breakdown.tsv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shapes", action="store_true", help="per-shape GEMM tags in the breakdown")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

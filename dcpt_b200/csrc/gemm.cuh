@@ -52,124 +52,114 @@ int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);  // CUDA-core cros
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);       // dispatch (DCPT_GEMM_SIMT=1 selects simt)
 
 #ifdef __CUDACC__
-// Epilogue for one row `m` and 32 consecutive accumulator columns [n0, n0+32).
-// Column validity is checked in groups of 8 (every N on this path is a multiple of 8).
+// ---------------------------------------------------------------------------------------------
+// Fused epilogues.  The tensor-core kernel transposes each 32x32 accumulator chunk through shared
+// memory, so a lane owns 4 CONSECUTIVE columns of one row and 8 lanes cover 128 contiguous bytes
+// of fp32 output: every global access below is coalesced.  All N on this path are multiples of 8.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&p0);
+  u.y = *reinterpret_cast<uint32_t*>(&p1);
+  return u;
+}
+__device__ __forceinline__ float4 unpack4_bf16(uint2 u) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// The epilogue of a 4-column piece is split into a LOAD phase (everything read from global memory) and a
+// STORE phase, so the caller can issue all loads of a chunk before the first store: the output pointers are
+// not provably distinct from the inputs, and a load placed after a store would wait for it (measured: 2x).
+struct EpiExtra {
+  float4 a, b;
+};
+
+// piece = 4 consecutive columns [n, n+4) of row m (valid).  For EPI_GATE, n is the packed column `na` of the
+// a-piece (see epilogue_store); its b-piece is 8 columns further.
+template <int EPI>
+__device__ __forceinline__ EpiExtra epilogue_load(const EpiParams& p, int m, int n) {
+  EpiExtra e;
+  e.a = e.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (EPI == EPI_STORE) {
+    if (p.bias) e.a = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    if (p.resid) e.b = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)m * p.ldr + n));
+  } else if constexpr (EPI == EPI_GATE) {
+    e.a = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    e.b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8));
+  } else if constexpr (EPI == EPI_GATE_BWD) {
+    const bf16* x4 = p.aux + (size_t)m * p.ldaux;
+    e.a = unpack4_bf16(__ldg(reinterpret_cast<const uint2*>(x4 + n)));
+    e.b = unpack4_bf16(__ldg(reinterpret_cast<const uint2*>(x4 + p.C + n)));
+  } else if constexpr (EPI == EPI_PIXSHUF) {
+    if (p.resid) {
+      const int w = m % p.W, t = m / p.W, h = t % p.H, img = t / p.H;
+      const int q = n / p.Cseg, c = n - q * p.Cseg;
+      const size_t pix = ((size_t)img * (2 * p.H) + 2 * h + (q >> 1)) * (size_t)(2 * p.W) + 2 * w + (q & 1);
+      e.a = __ldg(reinterpret_cast<const float4*>(p.resid + pix * p.Cseg + c));
+    }
+  }
+  return e;
+}
+
+// v = the 4 accumulators of the piece; for EPI_GATE, v = a-piece and vb = b-piece accumulators.
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const EpiParams& p, int m, int n, float4 v, float4 vb, const EpiExtra& e) {
+  if constexpr (EPI == EPI_STORE) {
+    v.x += e.a.x + e.b.x; v.y += e.a.y + e.b.y; v.z += e.a.z + e.b.z; v.w += e.a.w + e.b.w;
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + n) = v;
+    if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)m * p.ldo + n) = pack4_bf16(v.x, v.y, v.z, v.w);
+  } else if constexpr (EPI == EPI_GATE) {
+    // packed column p = 16*pp + h*8 + i  <->  channel h*C + 8*pp + i  (h = 0 first half, 1 second half);
+    // (n % 16) in {0, 4}: a-piece at n, b-piece at n + 8.
+    float4 a = v, b = vb;
+    a.x = bf16_round(a.x + e.a.x); a.y = bf16_round(a.y + e.a.y); a.z = bf16_round(a.z + e.a.z); a.w = bf16_round(a.w + e.a.w);
+    b.x = bf16_round(b.x + e.b.x); b.y = bf16_round(b.y + e.b.y); b.z = bf16_round(b.z + e.b.z); b.w = bf16_round(b.w + e.b.w);
+    const int j = (n >> 4) * 8 + (n & 15);
+    bf16* x4 = p.out_bf16 + (size_t)m * p.ldo;
+    *reinterpret_cast<uint2*>(x4 + j) = pack4_bf16(a.x, a.y, a.z, a.w);
+    *reinterpret_cast<uint2*>(x4 + p.C + j) = pack4_bf16(b.x, b.y, b.z, b.w);
+    *reinterpret_cast<uint2*>(p.out2 + (size_t)m * p.ldo2 + j) = pack4_bf16(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+  } else if constexpr (EPI == EPI_GATE_BWD) {
+    bf16* o = p.out_bf16 + (size_t)m * p.ldo;
+    *reinterpret_cast<uint2*>(o + n) = pack4_bf16(v.x * e.b.x, v.y * e.b.y, v.z * e.b.z, v.w * e.b.w);
+    *reinterpret_cast<uint2*>(o + p.C + n) = pack4_bf16(v.x * e.a.x, v.y * e.a.y, v.z * e.a.z, v.w * e.a.w);
+  } else if constexpr (EPI == EPI_PIXSHUF) {
+    const int w = m % p.W, t = m / p.W, h = t % p.H, img = t / p.H;
+    const int q = n / p.Cseg, c = n - q * p.Cseg;
+    const size_t pix = ((size_t)img * (2 * p.H) + 2 * h + (q >> 1)) * (size_t)(2 * p.W) + 2 * w + (q & 1);
+    const size_t off = pix * p.Cseg + c;
+    v.x += e.a.x; v.y += e.a.y; v.z += e.a.z; v.w += e.a.w;
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = v;
+    if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + off) = pack4_bf16(v.x, v.y, v.z, v.w);
+  } else if constexpr (EPI == EPI_ATOMIC) {
+    float* o = p.out_f32 + (size_t)m * p.ldo + n;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
+// Row-per-thread form (CUDA-core cross-check kernel): 32 consecutive accumulator columns of row m.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int m, int n0, int N, const float (&acc)[32]) {
-  if constexpr (EPI == EPI_STORE) {
+  if constexpr (EPI == EPI_GATE) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int n = n0 + g * 8;
-      if (n < N) {
-        float v[8];
+    for (int g = 0; g < 2; ++g)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = acc[g * 8 + i];
-        if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (p.resid) {
-          const float* r = p.resid + (size_t)m * p.ldr + n;
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(r));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(r + 4));
-          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        }
-        if (p.out_f32) {
-          float* o = p.out_f32 + (size_t)m * p.ldo + n;
-          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (p.out_bf16) stg16(p.out_bf16 + (size_t)m * p.ldo + n, pack8(v));
+      for (int q = 0; q < 2; ++q) {
+        const int na = n0 + g * 16 + q * 4, o = g * 16 + q * 4;
+        if (na < N)
+          epilogue_store<EPI>(p, m, na, make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]),
+                              make_float4(acc[o + 8], acc[o + 9], acc[o + 10], acc[o + 11]), epilogue_load<EPI>(p, m, na));
       }
-    }
-  } else if constexpr (EPI == EPI_GATE) {
-    // packed column p = 16*pp + h*8 + i  <->  channel h*C + 8*pp + i   (h = 0: first half, 1: second half)
+  } else {
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int n = n0 + g * 16;
-      if (n < N) {
-        float a[8], b[8], s[8];
-        const float4 ba0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-        const float4 ba1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-        const float4 bb0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8));
-        const float4 bb1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 12));
-        const float ba[8] = {ba0.x, ba0.y, ba0.z, ba0.w, ba1.x, ba1.y, ba1.z, ba1.w};
-        const float bb[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          a[i] = bf16_round(acc[g * 16 + i] + ba[i]);
-          b[i] = bf16_round(acc[g * 16 + 8 + i] + bb[i]);
-          s[i] = a[i] * b[i];
-        }
-        const int j = (n >> 4) * 8;
-        bf16* x4 = p.out_bf16 + (size_t)m * p.ldo;
-        stg16(x4 + j, pack8(a));
-        stg16(x4 + p.C + j, pack8(b));
-        stg16(p.out2 + (size_t)m * p.ldo2 + j, pack8(s));
-      }
-    }
-  } else if constexpr (EPI == EPI_GATE_BWD) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int n = n0 + g * 8;
-      if (n < N) {
-        const bf16* x4 = p.aux + (size_t)m * p.ldaux;
-        float a[8], b[8], da[8], db[8];
-        unpack8(ldg16(x4 + n), a);
-        unpack8(ldg16(x4 + p.C + n), b);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float d = acc[g * 8 + i];
-          da[i] = d * b[i];
-          db[i] = d * a[i];
-        }
-        bf16* o = p.out_bf16 + (size_t)m * p.ldo;
-        stg16(o + n, pack8(da));
-        stg16(o + p.C + n, pack8(db));
-      }
-    }
-  } else if constexpr (EPI == EPI_PIXSHUF) {
-    const int w = m % p.W;
-    const int t = m / p.W;
-    const int h = t % p.H;
-    const int img = t / p.H;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int n = n0 + g * 8;
-      if (n < N) {
-        const int q = n / p.Cseg;
-        const int c = n - q * p.Cseg;
-        const size_t pix = ((size_t)img * (2 * p.H) + 2 * h + (q >> 1)) * (size_t)(2 * p.W) + 2 * w + (q & 1);
-        const size_t off = pix * p.Cseg + c;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = acc[g * 8 + i];
-        if (p.resid) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.resid + off));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.resid + off + 4));
-          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        }
-        if (p.out_f32) {
-          *reinterpret_cast<float4*>(p.out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(p.out_f32 + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (p.out_bf16) stg16(p.out_bf16 + off, pack8(v));
-      }
-    }
-  } else if constexpr (EPI == EPI_ATOMIC) {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int n = n0 + g * 4;
-      if (n < N) {
-        float* o = p.out_f32 + (size_t)m * p.ldo + n;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(acc[g * 4 + 0]), "f"(acc[g * 4 + 1]),
-                     "f"(acc[g * 4 + 2]), "f"(acc[g * 4 + 3])
-                     : "memory");
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + j * 4;
+      if (n < N)
+        epilogue_store<EPI>(p, m, n, make_float4(acc[j * 4], acc[j * 4 + 1], acc[j * 4 + 2], acc[j * 4 + 3]),
+                            make_float4(0.f, 0.f, 0.f, 0.f), epilogue_load<EPI>(p, m, n));
     }
   }
 }

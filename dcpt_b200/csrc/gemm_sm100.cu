@@ -4,14 +4,16 @@
 // (reference: nafnet_arch.py:87-150 conv1/3/4/5, :230 downs, :238-242 ups; the
 // reference runs these through cuDNN/cuBLAS fp32).
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1   : MMA issuer     (one elected lane issues tcgen05.mma, fp32 accum in TMEM)
-//   warps 2-5: epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+//   warps 2-9: epilogue       (tcgen05.ld TMEM -> registers -> smem transpose -> fused epilogue -> coalesced global I/O)
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop
 // of tile i+1.  Tile = 128 x BN (BN in {64,128,256}), BK = 64 bf16 (= one 128-byte
 // swizzle row).  MN-major operands (wgrad) are loaded as 64x64 boxes, which
 // the UMMA descriptor addresses with LBO = 8 KiB / SBO = 1 KiB.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "gemm.cuh"
@@ -20,7 +22,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 
 template <int BN>
@@ -29,7 +31,7 @@ struct Cfg {
   static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two >= 32)
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 4096 /*epilogue staging, 4 KiB per epilogue warp*/;
 };
 
 // UMMA shared-memory descriptor (sm_100): start addr [0,14), LBO [16,30), SBO [32,46) (all >>4),
@@ -81,7 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[b], 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -99,6 +101,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      constexpr int PF_DIST = 12;
+      auto prefetch_kb = [&](int pk, int m_t, int n_t) {
+        if constexpr (!A_MN) {
+          tma_prefetch_2d(&tmA, pk * BK, m_t * BM);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_prefetch_2d(&tmA, m_t * BM + c * 64, pk * BK);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_prefetch_2d(&tmB, n_t * BN + c * 64, pk * BK);
+        }
+      };
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_t = tile % tiles_n;
         const int m_t = (tile / tiles_n) % tiles_m;
@@ -106,6 +119,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = sp * kb_per_split;
         const int kb1 = min(num_kb, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
+          // L2 prefetch of the HBM-streamed operand(s), PF_DIST k-blocks ahead of the smem ring (which can hold
+          // only STAGES blocks in flight: not enough to cover DRAM latency for a short-K tile).
+          if (kb == kb0) {
+            for (int pk = kb0; pk < min(kb1, kb0 + PF_DIST); ++pk) prefetch_kb(pk, m_t, n_t);
+          } else if (kb + PF_DIST - 1 < kb1) {
+            prefetch_kb(kb + PF_DIST - 1, m_t, n_t);
+          }
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
           uint8_t* a_dst = sA + (size_t)stage * A_STAGE_BYTES;
@@ -173,25 +193,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else {
     // -------------------------------- epilogue --------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // Eight epilogue warps: warp w may touch TMEM lanes [32*(w%4), +32); the two warps of a lane quarter take
+    // alternate 32-column chunks.  Each chunk is transposed through a private 4 KiB smem tile (float4 index
+    // XOR-swizzled by row & 7: conflict-free both ways) so that a lane owns 4 consecutive columns of one row and
+    // 8 lanes cover 128 contiguous bytes: all global traffic of the fused epilogues is coalesced.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int chalf = ew >> 2;
+    float4* stage = reinterpret_cast<float4*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256) + ew * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_t = tile % tiles_n;
       const int m_t = (tile / tiles_n) % tiles_m;
+      const int m_base = m_t * BM + q * 32;
+      // While the tensor core works on this tile, pull the epilogue's global inputs into L2.
+      if constexpr (EPI == EPI_STORE) {
+        if (ep.resid) {
+          for (int i = lane + chalf * 32; i < 32 * (BN / 32); i += 64) {
+            const int r = i / (BN / 32), l = i % (BN / 32);
+            if (m_base + r < M && n_t * BN + l * 32 < N) prefetch_l2(ep.resid + (size_t)(m_base + r) * ep.ldr + n_t * BN + l * 32);
+          }
+        }
+      } else if constexpr (EPI == EPI_GATE_BWD) {
+        for (int i = lane + chalf * 32; i < 32 * (BN / 64) * 2; i += 64) {
+          const int r = i / (BN / 32), l = i % (BN / 32), hf = l / (BN / 64), ll = l % (BN / 64);
+          const int n = n_t * BN + ll * 64;
+          if (m_base + r < M && n < N) prefetch_l2(ep.aux + (size_t)(m_base + r) * ep.ldaux + hf * ep.C + n);
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int m = m_t * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf; c < BN / 32; c += 2) {
         const int n0 = n_t * BN + c * 32;
-        if (n0 < N) {  // warp-uniform
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (m < M) epilogue_chunk<EPI>(ep, m, n0, N, v);
+        if (n0 >= N) break;  // warp-uniform
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stage[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        if constexpr (EPI == EPI_GATE) {
+          // 4 lanes per row: lane -> (group g, quarter qq) = the a-piece / b-piece pair of 4 channels
+          const int pc = lane & 3, g = pc >> 1, qq = pc & 1;
+          const int na = n0 + g * 16 + qq * 4;
+          const int r0 = lane >> 2;
+          EpiExtra ex[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (m_base + it * 8 + r0 < M && na < N) ex[it] = epilogue_load<EPI>(ep, m_base + it * 8 + r0, na);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + r0;
+            const float4 a = stage[r * 8 + ((g * 4 + qq) ^ (r & 7))];
+            const float4 b = stage[r * 8 + ((g * 4 + 2 + qq) ^ (r & 7))];
+            if (m_base + r < M && na < N) epilogue_store<EPI>(ep, m_base + r, na, a, b, ex[it]);
+          }
+        } else {
+          const int cc = lane & 7, r0 = lane >> 3;
+          const int n = n0 + cc * 4;
+          EpiExtra ex[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (m_base + it * 4 + r0 < M && n < N) ex[it] = epilogue_load<EPI>(ep, m_base + it * 4 + r0, n);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r0;
+            const float4 x = stage[r * 8 + (cc ^ (r & 7))];
+            if (m_base + r < M && n < N) epilogue_store<EPI>(ep, m_base + r, n, x, x, ex[it]);
+          }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -292,10 +366,16 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     DCPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     attr_set = true;
   }
-  static char tag[48] = "";
-  if (!tag[0]) {
+  static char base_tag[48] = "";
+  if (!base_tag[0]) {
     static const char* epi_names[] = {"store", "gate", "gate_bwd", "pixshuf", "atomic"};
-    snprintf(tag, sizeof(tag), "gemm_tc<%d,%s,%s>", BN, epi_names[EPI], A_MN ? "mn" : "k");
+    snprintf(base_tag, sizeof(base_tag), "gemm_tc<%d,%s,%s>", BN, epi_names[EPI], A_MN ? "mn" : "k");
+  }
+  const char* tag = base_tag;
+  if (g_dcpt_prof_on && g_dcpt_prof_shapes) {
+    char buf[96];
+    snprintf(buf, sizeof(buf), "%s %dx%dx%d s%d", base_tag, g.M, g.N, g.K, splits);
+    tag = dcpt_prof_intern(buf);
   }
   const double out_bytes = (double)g.M * g.N * ((g.ep.out_f32 ? 4.0 : 0.0) + (g.ep.out_bf16 ? 2.0 : 0.0) + (g.ep.resid ? 4.0 : 0.0) +
                                                 (EPI == EPI_GATE ? 1.0 : 0.0) + (EPI == EPI_GATE_BWD ? 4.0 : 0.0));

@@ -32,6 +32,7 @@ void dcpt_set_error(const char* fmt, ...) {
 
 // ---- profiling (prof.h) ----
 bool g_dcpt_prof_on = false;
+bool g_dcpt_prof_shapes = false;
 long long g_dcpt_launches = 0;
 namespace {
 struct ProfRec { const char* tag; double flops, bytes; cudaEvent_t e0, e1; };
@@ -42,6 +43,10 @@ cudaEvent_t prof_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 }  // namespace
+const char* dcpt_prof_intern(const char* s) {
+  static std::map<std::string, int> pool;
+  return pool.emplace(s, 0).first->first.c_str();
+}
 void dcpt_prof_begin(const char* tag, double flops, double bytes, cudaStream_t st) {
   ProfRec r{tag, flops, bytes, prof_event(), prof_event()};
   cudaEventRecord(r.e0, st);
@@ -434,6 +439,7 @@ long long dcpt_launch_count(void) { return g_dcpt_launches; }
 
 int dcpt_prof_enable(int on) {
   g_dcpt_prof_on = on != 0;
+  g_dcpt_prof_shapes = on == 2;
   return 0;
 }
 

@@ -7,6 +7,8 @@
 void dcpt_prof_begin(const char* tag, double flops, double bytes, cudaStream_t st);
 void dcpt_prof_end(cudaStream_t st);
 extern bool g_dcpt_prof_on;
+extern bool g_dcpt_prof_shapes;  // dcpt_prof_enable(2): GEMM tags carry MxNxK
+const char* dcpt_prof_intern(const char* s);
 extern long long g_dcpt_launches;
 
 struct DcptProfScope {

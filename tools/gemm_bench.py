@@ -1,0 +1,86 @@
+"""Micro-benchmark of the tcgen05 GEMM engine on the NAFNet-w64 shapes (CUDA events, L2 flushed between launches).
+    python tools/gemm_bench.py [--ncu]     (--ncu: one launch per shape, for profiling)
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from dcpt_b200 import ops  # noqa: E402
+from dcpt_b200.lib import GemmDesc  # noqa: E402
+
+dev = torch.device("cuda", 0)
+ncu = "--ncu" in sys.argv
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def bench(name, fn, flops, nbytes, iters=10):
+    fn()
+    torch.cuda.synchronize()
+    if ncu:
+        return
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    t = ts[len(ts) // 2] * 1e-3
+    print(f"{name:44s} {t * 1e6:8.1f} us  {flops / t / 1e12:7.1f} TFLOP/s  {nbytes / t / 1e9:7.0f} GB/s", flush=True)
+
+
+def desc(**kw):
+    d = GemmDesc()
+    for k, v in kw.items():
+        setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+    return d
+
+
+def run(M, N, K, kind):
+    A = torch.randn(M, K, device=dev).bfloat16()
+    B = torch.randn(N, K, device=dev).bfloat16()
+    if kind == "store_bf16":
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        d = desc(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_bf16=out, ldo=N)
+        nb = 2 * (M * K + N * K + M * N)
+    elif kind == "store_resid":
+        out = torch.empty(M, N, dtype=torch.float32, device=dev)
+        res = torch.randn(M, N, device=dev)
+        bias = torch.randn(N, device=dev)
+        d = desc(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=out, ldo=N, resid=res, ldr=N, bias=bias)
+        nb = 2 * (M * K + N * K) + 8 * M * N
+    elif kind == "gate":
+        C = N // 2
+        x4 = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        sg = torch.empty(M, C, dtype=torch.bfloat16, device=dev)
+        bias = torch.randn(N, device=dev)
+        d = desc(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=1, out_bf16=x4, ldo=N, out2_bf16=sg, ldo2=C, C=C, bias=bias)
+        nb = 2 * (M * K + N * K) + 3 * M * N
+    elif kind == "gate_bwd":
+        x4 = torch.randn(M, 2 * N, device=dev).bfloat16()
+        dx4 = torch.empty(M, 2 * N, dtype=torch.bfloat16, device=dev)
+        d = desc(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=2, out_bf16=dx4, ldo=2 * N, aux_bf16=x4, ldaux=2 * N, C=N)
+        nb = 2 * (M * K + N * K) + 8 * M * N
+    elif kind.startswith("wgrad"):
+        splits = int(kind[5:])
+        A = torch.randn(K, M, device=dev).bfloat16()
+        B = torch.randn(K, N, device=dev).bfloat16()
+        out = torch.zeros(M, N, device=dev)
+        d = desc(M=M, N=N, K=K, A=A, lda=M, a_mn=1, B=B, ldb=N, b_mn=1, splits=splits, epilogue=4, out_f32=out, ldo=N)
+        nb = 2 * (M * K + N * K) + 4 * M * N * splits
+    keep = (A, B, d)
+    bench(f"{kind} {M}x{N}x{K}", lambda: ops.gemm_ex(d), 2.0 * M * N * K, nb)
+    return keep
+
+
+shapes = [(16384, 512, 512, "store_resid"), (16384, 512, 512, "store_bf16"), (16384, 1024, 512, "store_bf16"),
+          (16384, 512, 1024, "store_bf16"), (16384, 1024, 512, "gate"), (16384, 512, 512, "gate_bwd"),
+          (1024, 512, 16384, "wgrad10"), (512, 512, 16384, "wgrad19"), (8192, 8192, 8192, "store_bf16"),
+          (1048576, 64, 64, "store_resid"), (1048576, 128, 64, "store_bf16"), (262144, 128, 128, "store_resid")]
+if ncu:
+    shapes = shapes[:4]
+for s in shapes:
+    run(*s)
