@@ -265,3 +265,254 @@ int conv3x3_small_wgrad_launch(const float* feat, const float* img, float* G, fl
   }
   return 0;
 }
+
+// =====================================================================================================
+// Tensor-core route for the two image-side 3x3 convs (used when the feature width allows it):
+// the 27-term stencil of the 3-channel image is materialised once as a bf16 "patch" matrix
+// P[px][32] (27 taps + 5 zero columns, 64 bytes per pixel -- small next to the 4*C bytes per pixel of the
+// feature map), after which
+//   intro forward          x0   = P  * Wi^T + b          (GEMM  M = pixels, N = C, K = 32)
+//   intro wgrad            dWi  = dX0^T * P              (wgrad GEMM, K = pixels)
+//   ending dgrad           dF   = Pd * Wd^T              (Pd = flipped patches of dout)
+//   ending wgrad           dWe  = F^T * Pd
+// all run on the tcgen05 engine of gemm_sm100.cu.  Patch column j = ci*9 + ky*3 + kx holds
+//   flip = 0: img[ci][h+ky-1][w+kx-1]        flip = 1: img[ci][h-ky+1][w-kx+1]      (zero outside the image)
+// =====================================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256)
+im2col3_kernel(const float* __restrict__ img, bf16* __restrict__ P, float* __restrict__ colsum, int flip, int dup, int N, int H, int W) {
+  __shared__ float s_sum[32];
+  if (threadIdx.x < 32) s_sum[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  float loc[27];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) loc[j] = 0.f;
+  for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < total; px += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(px / HW);
+    const int rem = (int)(px - (long long)n * HW);
+    const int h = rem / W, w = rem - h * W;
+    float v[32];
+#pragma unroll
+    for (int j = 27; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      const float* plane = img + ((size_t)n * 3 + ci) * HW;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const int hh = flip ? h - dy : h + dy, ww = flip ? w - dx : w + dx;
+        float x = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) x = __ldg(plane + (size_t)hh * W + ww);
+        x = bf16_round(x);
+        v[ci * 9 + t] = x;
+        loc[ci * 9 + t] += x;
+      }
+    }
+    // dup: row = [patches | patches] (64 columns): the intro GEMM multiplies the copy by the low half of a
+    // hi/lo-split weight, which restores fp32-grade weights on the image-side conv at no extra MMA cost.
+    uint4* dst = reinterpret_cast<uint4*>(P + (size_t)px * (dup ? 64 : 32));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float f[8] = {v[q * 8], v[q * 8 + 1], v[q * 8 + 2], v[q * 8 + 3], v[q * 8 + 4], v[q * 8 + 5], v[q * 8 + 6], v[q * 8 + 7]};
+      const uint4 pk = pack8(f);
+      dst[q] = pk;
+      if (dup) dst[4 + q] = pk;
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int j = 0; j < 27; ++j) {
+      const float s = warp_sum(loc[j]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum[j], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) atomicAdd(colsum + threadIdx.x, s_sum[threadIdx.x]);
+  }
+}
+
+// mode 0: out [C][64] = [hi | lo] split of the intro weight w[r][j] ([C][27]): hi = bf16(w), lo = bf16(w - hi)
+// mode 1: out [C][32],  out[r][o*9+t] = w[o][r][t] (ending weight [3][C][9]) -- dgrad operand
+__global__ void pack_w27_kernel(const float* __restrict__ w, bf16* __restrict__ out, int C, int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 0) {
+    if (i >= C * 64) return;
+    const int r = i >> 6, jj = i & 63, j = jj & 31;
+    float v = 0.f;
+    if (j < 27) {
+      const float wv = w[(size_t)r * 27 + j];
+      const float hi = bf16_round(wv);
+      v = jj < 32 ? hi : wv - hi;
+    }
+    out[i] = __float2bfloat16_rn(v);
+  } else {
+    if (i >= C * 32) return;
+    const int r = i >> 5, j = i & 31;
+    float v = 0.f;
+    if (j < 27) v = w[((size_t)(j / 9) * C + r) * 9 + (j % 9)];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// mode 0 (intro):  dw[c][j] += G[c*32 + j]                      (dw is [C][27])
+// mode 1 (ending): dw[o][c][t] += G[c*32 + o*9 + t]; db[o] += psum[o*9 + 4]  (centre tap = plain sum of dout[o])
+__global__ void finish_w27_kernel(const float* __restrict__ G, float* __restrict__ dw, const float* __restrict__ psum,
+                                  float* __restrict__ db, int C, int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * 27) {
+    const int c = i / 27, j = i - c * 27;
+    if (mode == 0) dw[i] += G[c * 32 + j];
+    else dw[((size_t)(j / 9) * C + c) * 9 + (j % 9)] += G[c * 32 + j];
+  } else if (mode == 1 && i < C * 27 + 3) {
+    const int o = i - C * 27;
+    db[o] += psum[o * 9 + 4];
+  }
+}
+
+// colsum[c] += sum_j w[o][c][t] * psum[o*9+t]   (column sums of dF = Pd * Wd^T without touching dF)
+__global__ void ending_colsum_kernel(const float* __restrict__ w, const float* __restrict__ psum, float* __restrict__ colsum, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int j = 0; j < 27; ++j) acc = fmaf(w[((size_t)(j / 9) * C + c) * 9 + (j % 9)], psum[j], acc);
+  colsum[c] += acc;
+}
+
+// ---- ending forward from the bf16 mirror of the last feature map: TMA tile (8x16 px + halo) x 64 channels ----
+constexpr int ETH = 8, ETW = 16, EHH = ETH + 2, EHW = ETW + 2;
+constexpr int EBOX_BYTES = EHH * EHW * 64 * 2;
+
+__global__ void __launch_bounds__(256)
+ending_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF, const float* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ resid, float* __restrict__ out, int N, int H, int W, int C) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  __shared__ uint64_t full[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c2 = lane * 2;
+  const bool chan_ok = c2 < C;
+  const int c0 = chan_ok ? c2 : 0;
+  float2 wt[3][9];  // taps of this lane's two channels for the 3 outputs
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      wt[o][t] = chan_ok ? make_float2(__ldg(w + ((size_t)o * C + c0) * 9 + t), __ldg(w + ((size_t)o * C + c0 + 1) * 9 + t))
+                         : make_float2(0.f, 0.f);
+  const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+  const int tiles_w = (W + ETW - 1) / ETW, tiles_h = (H + ETH - 1) / ETH, per_img = tiles_w * tiles_h, total = N * per_img;
+  const int chunk = (total + gridDim.x - 1) / gridDim.x;
+  const int t0 = min(total, (int)blockIdx.x * chunk), t1 = min(total, t0 + chunk);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmF);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t, int s) {
+    const int n = t / per_img, r = t - n * per_img;
+    mbar_arrive_expect_tx(&full[s], EBOX_BYTES);
+    tma_load_4d(smem + (size_t)s * EBOX_BYTES, &tmF, &full[s], 0, (r % tiles_w) * ETW - 1, (r / tiles_w) * ETH - 1, n);
+  };
+  if (threadIdx.x == 0 && t0 < t1) issue(t0, 0);
+  const size_t HW = (size_t)H * W;
+  int it = 0;
+  for (int t = t0; t < t1; ++t, ++it) {
+    const int s = it & 1;
+    if (threadIdx.x == 0 && t + 1 < t1) issue(t + 1, s ^ 1);
+    const int n = t / per_img, r = t - n * per_img;
+    const int h = (r / tiles_w) * ETH + warp, w0 = (r % tiles_w) * ETW;
+    mbar_wait(&full[s], (it >> 1) & 1);
+    const bf16* sF = reinterpret_cast<const bf16*>(smem + (size_t)s * EBOX_BYTES) + lane * 2;
+    float2 A[3][3];
+    float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f;  // lane ox keeps pixel ox's three outputs
+#pragma unroll
+    for (int x = 0; x < EHW; ++x) {
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr)
+        A[rr][x % 3] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sF + ((warp + rr) * EHW + x) * 64));
+      if (x >= 2) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const float2 v = A[rr][(x - 2 + d) % 3];
+            const int tp = rr * 3 + d;
+            a0 = fmaf(v.x, wt[0][tp].x, fmaf(v.y, wt[0][tp].y, a0));
+            a1 = fmaf(v.x, wt[1][tp].x, fmaf(v.y, wt[1][tp].y, a1));
+            a2 = fmaf(v.x, wt[2][tp].x, fmaf(v.y, wt[2][tp].y, a2));
+          }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == x - 2) {
+          keep0 = a0; keep1 = a1; keep2 = a2;
+        }
+      }
+    }
+    if (lane < ETW && h < H && w0 + lane < W) {
+      const size_t o = (size_t)n * 3 * HW + (size_t)h * W + w0 + lane;
+      out[o] = keep0 + b0 + (resid ? resid[o] : 0.f);
+      out[o + HW] = keep1 + b1 + (resid ? resid[o + HW] : 0.f);
+      out[o + 2 * HW] = keep2 + b2 + (resid ? resid[o + 2 * HW] : 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int im2col3_launch(const float* img, bf16* P, float* colsum, int flip, int dup, int N, int H, int W, cudaStream_t st) {
+  const long long total = (long long)N * H * W;
+  long long blocks = ceil_div_ll(total, 256);
+  const long long cap = (long long)dcpt_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  DCPT_PROF("im2col3", 0.0, 76.0 * total, st);
+  im2col3_kernel<<<(unsigned)blocks, 256, 0, st>>>(img, P, colsum, flip, dup, N, H, W);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int pack_w27_launch(const float* w, bf16* out, int C, int mode, cudaStream_t st) {
+  DCPT_PROF("pack_w27", 0.0, 200.0 * C, st);
+  pack_w27_kernel<<<ceil_div(C * 64, 256), 256, 0, st>>>(w, out, C, mode);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int finish_w27_launch(const float* G, float* dw, const float* psum, float* db, int C, int mode, cudaStream_t st) {
+  DCPT_PROF("finish_w27", 0.0, 240.0 * C, st);
+  finish_w27_kernel<<<ceil_div(C * 27 + 3, 256), 256, 0, st>>>(G, dw, psum, db, C, mode);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int ending_colsum_launch(const float* w, const float* psum, float* colsum, int C, cudaStream_t st) {
+  DCPT_PROF("ending_colsum", 0.0, 120.0 * C, st);
+  ending_colsum_kernel<<<ceil_div(C, 128), 128, 0, st>>>(w, psum, colsum, C);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int ending_fwd_tma_launch(const bf16* feat, const float* w, const float* bias, const float* resid_img, float* out_img, int N, int H,
+                          int W, int C, cudaStream_t st) {
+  DCPT_CHECK_ARG(C % 8 == 0 && C <= 64, DCPT_E_SHAPE, "ending (TMA path): C=%d must be a multiple of 8 and <= 64", C);
+  CUtensorMap tmF;
+  DCPT_TRY(make_tmap_nhwc(&tmF, feat, N, H, W, C, EHW, EHH));
+  const size_t smem = 128 + (size_t)2 * EBOX_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    DCPT_CUDA(cudaFuncSetAttribute(ending_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int tiles = N * ceil_div(H, ETH) * ceil_div(W, ETW);
+  int grid = dcpt_num_sms() * 3;
+  if (grid > tiles) grid = tiles;
+  DCPT_PROF("ending_fwd_tma", 54.0 * N * H * W * C, (2.0 * C + 24.0) * N * H * W, st);
+  ending_fwd_tma_kernel<<<grid, 256, smem, st>>>(tmF, w, bias, resid_img, out_img, N, H, W, C);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}

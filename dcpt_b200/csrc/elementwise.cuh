@@ -59,3 +59,11 @@ int conv3x3_feat_to_img_launch(const float* feat, const float* w, const float* b
 // G[c][j] (+)= sum_px feat[px][c] * patch_j(img)[px], j = ci*9 + ky*3 + kx (27 columns); flip mirrors the taps.
 int conv3x3_small_wgrad_launch(const float* feat, const float* img, float* G, float* img_sum, int flip, int N, int H, int W,
                                int C, cudaStream_t st);
+
+// Tensor-core route for the image-side 3x3 convs (conv3x3_img.cu, second half): bf16 patch matrix P [pixels, 32].
+int im2col3_launch(const float* img, bf16* P, float* colsum32, int flip, int dup, int N, int H, int W, cudaStream_t st);
+int pack_w27_launch(const float* w, bf16* out, int C, int mode, cudaStream_t st);  // mode 0 intro [C][27], 1 ending [3][C][9]
+int finish_w27_launch(const float* G, float* dw, const float* psum, float* db, int C, int mode, cudaStream_t st);
+int ending_colsum_launch(const float* w, const float* psum, float* colsum, int C, cudaStream_t st);
+int ending_fwd_tma_launch(const bf16* feat, const float* w, const float* bias, const float* resid_img, float* out_img, int N, int H,
+                          int W, int C, cudaStream_t st);

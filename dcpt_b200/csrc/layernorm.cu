@@ -72,8 +72,9 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(kWarps * 32)
+// NV <= 2: 16-warp blocks (few, fat blocks -> few partial-sum flushes); NV >= 4 needs > 128 registers -> 8 warps.
+template <int NV, int kBwdWarps>
+__global__ void __launch_bounds__(kBwdWarps * 32)
 ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ stats,
               const float* __restrict__ w, const float* __restrict__ dres, float* __restrict__ dx, bf16* __restrict__ dx_bf16,
               float* __restrict__ dw, float* __restrict__ db, float* __restrict__ colsum, int M, int C, int lpr) {
@@ -88,14 +89,35 @@ ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const fl
   float4 a_dw[NV], a_db[NV], a_cs[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) a_dw[i] = a_db[i] = a_cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long row_stride = (long long)gridDim.x * kWarps * rpw;
-  for (long long row = ((long long)blockIdx.x * kWarps + warp) * rpw + gr; row - gr < M; row += row_stride) {
+  const long long row_stride = (long long)gridDim.x * kBwdWarps * rpw;
+  for (long long row = ((long long)blockIdx.x * kBwdWarps + warp) * rpw + gr; row - gr < M; row += row_stride) {
     const bool valid = row < M;
     float2 st = make_float2(0.f, 0.f);
     if (valid) st = __ldg(reinterpret_cast<const float2*>(stats + row * 2));
     const float mean = st.x, rstd = st.y;
-    float4 yh[NV], g[NV], d[NV];
+    float4 yh[NV], g[NV], d[NV], rs[NV];
     float sg = 0.f, sgy = 0.f;
+    {  // pull the warp's NEXT row towards L2 while this one is processed (the loop body is one long dependency chain)
+      const long long nrow = row + row_stride;
+      if (nrow < M) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int v = sub + i * lpr;
+          if (v < nvec) {
+            prefetch_l2(reinterpret_cast<const float4*>(x + nrow * C) + v);
+            if (dres) prefetch_l2(reinterpret_cast<const float4*>(dres + nrow * C) + v);
+            if ((v & 1) == 0) prefetch_l2(reinterpret_cast<const uint2*>(dn + nrow * C) + v);
+          }
+        }
+      }
+    }
+    // every global load of the row is issued before the first dependent use: one memory round trip per row
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = sub + i * lpr;
+      rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dres && valid && v < nvec) rs[i] = __ldg(reinterpret_cast<const float4*>(dres + row * C) + v);
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = sub + i * lpr;
@@ -125,10 +147,7 @@ ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const fl
           o.y = rstd * (g[i].y - yh[i].y * mean_gy - mean_g);
           o.z = rstd * (g[i].z - yh[i].z * mean_gy - mean_g);
           o.w = rstd * (g[i].w - yh[i].w * mean_gy - mean_g);
-          if (dres) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(dres + row * C) + v);
-            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-          }
+          o.x += rs[i].x; o.y += rs[i].y; o.z += rs[i].z; o.w += rs[i].w;
           *(reinterpret_cast<float4*>(dx + row * C) + v) = o;
           if (dx_bf16) {
             __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
@@ -198,18 +217,19 @@ int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const floa
   DCPT_CHECK_ARG(M > 0 && C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "layernorm bwd: need C %% 8 == 0 and 8 <= C <= 1024 (C=%d)", C);
   const int lpr = pick_lpr(C);
   const int nv = ceil_div(C / 4, lpr);
-  const int rows_per_block = kWarps * (32 / lpr);
+  const int warps = nv <= 2 ? 16 : 8;
+  const int rows_per_block = warps * (32 / lpr);
   long long grid = ceil_div_ll(M, rows_per_block);
-  const long long cap = (long long)dcpt_num_sms() * 4;  // few blocks -> few partial-sum flushes
+  const long long cap = (long long)dcpt_num_sms() * (nv <= 1 ? 2 : 1);  // register-limited to 1 block / SM beyond NV = 1
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)3 * C * sizeof(float);
   DCPT_PROF("ln_bwd", 20.0 * M * C, (2.0 + 4.0 + (dres ? 4.0 : 0.0) + 4.0 + (dx_bf16 ? 2.0 : 0.0)) * M * C, st);
-#define LN_BWD(NVV) \
-  ln_bwd_kernel<NVV><<<(int)grid, kWarps * 32, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr)
-  if (nv <= 1) LN_BWD(1);
-  else if (nv <= 2) LN_BWD(2);
-  else if (nv <= 4) LN_BWD(4);
-  else LN_BWD(8);
+#define LN_BWD(NVV, WW) \
+  ln_bwd_kernel<NVV, WW><<<(int)grid, WW * 32, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr)
+  if (nv <= 1) LN_BWD(1, 16);
+  else if (nv <= 2) LN_BWD(2, 16);
+  else if (nv <= 4) LN_BWD(4, 8);
+  else LN_BWD(8, 8);
 #undef LN_BWD
   DCPT_LAUNCH_CHECK();
   return 0;

@@ -135,8 +135,8 @@ GemmArgs gemm_args(int M, int N, int K, const bf16* A, int lda, const bf16* B, i
 }
 
 // wgrad: out[O, I] += dY[Mpx, O]^T * X[Mpx, I]   (both operands MN-major, split-K over pixels, fp32 atomics)
-int wgrad_gemm(const bf16* dY, int O, const bf16* X, int I, float* out, int Mpx, cudaStream_t st) {
-  GemmArgs g = gemm_args(O, I, Mpx, dY, O, X, I, EPI_ATOMIC);
+int wgrad_gemm(const bf16* dY, int O, const bf16* X, int I, float* out, int Mpx, cudaStream_t st, int ldx = 0) {
+  GemmArgs g = gemm_args(O, I, Mpx, dY, O, X, ldx > 0 ? ldx : I, EPI_ATOMIC);
   g.a_mn = 1; g.b_mn = 1;
   const int bn = I > 128 ? 256 : (I > 64 ? 128 : 64);
   const int tiles = ceil_div(O, 128) * ceil_div(I, bn);
@@ -307,6 +307,8 @@ int add_block_params(dcpt_nafnet_plan* p, int c) {
 // Device-side layout of everything the forward keeps for the backward.
 struct NetSaved {
   float* x0;                                   // intro output
+  bf16* P;                                     // intro patch matrix [M0, 32] (im2col of the input image)
+  bf16* xlast_bf16;                            // bf16 mirror of the last decoder output (ending conv operand)
   std::vector<std::vector<BlockSaved>> enc_sv, dec_sv;
   std::vector<std::vector<float*>> enc_out, dec_out;  // block outputs (fp32)
   std::vector<BlockSaved> mid_sv;
@@ -318,6 +320,8 @@ struct NetSaved {
   NetSaved(const dcpt_nafnet_plan* p, Arena& a, int N, int H, int W) {
     int C = p->width, h = H, w = W;
     x0 = a.take<float>((size_t)N * h * w * C);
+    P = a.take<bf16>((size_t)N * h * w * 64);
+    xlast_bf16 = a.take<bf16>((size_t)N * h * w * C);
     const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
     enc_sv.resize(ne); enc_out.resize(ne);
     for (int i = 0; i < ne; ++i) {
@@ -350,8 +354,11 @@ struct NetPacked {
   std::vector<std::vector<BlockPacked>> enc_pk, dec_pk;
   std::vector<BlockPacked> mid_pk;
   std::vector<bf16*> down, down_t, up, up_t;
+  bf16 *wi_p, *wd_p;  // intro weight [C][32] and ending weight as dgrad operand [C][32] (27 taps + zero pad)
   NetPacked(const dcpt_nafnet_plan* p, Arena& a) {
     int C = p->width;
+    wi_p = a.take<bf16>((size_t)C * 64);
+    wd_p = a.take<bf16>((size_t)C * 32);
     const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
     enc_pk.resize(ne); dec_pk.resize(nd);
     for (int i = 0; i < ne; ++i) {
@@ -377,9 +384,11 @@ struct NetWork {
   std::vector<float*> dskip;                                          // per encoder level
   bf16* dconv;      // unshuffled up-conv output gradient
   float* G;         // wgrad scratch for up/down/ending convs
+  bf16* Pd;         // flipped patch matrix of dout [M0, 32]
+  float* psum;      // column sums of Pd [32]
   NetWork(const dcpt_nafnet_plan* p, Arena& a, int N, int H, int W) {
     int C = p->width, h = H, w = W;
-    size_t max_act = 0, max_blk = 0, max_g = (size_t)27 * C;
+    size_t max_act = 0, max_blk = 0, max_g = (size_t)32 * C;
     const int ne = (int)p->enc.size();
     std::vector<size_t> lvl_act;
     int maxC = C;
@@ -406,6 +415,8 @@ struct NetWork {
     for (int i = 0; i < ne; ++i) dskip.push_back(a.take<float>(lvl_act[i]));
     dconv = a.take<bf16>(max_act);
     G = a.take<float>(max_g);
+    Pd = a.take<bf16>((size_t)N * H * W * 32);
+    psum = a.take<float>(32);
   }
 };
 
@@ -648,6 +659,8 @@ int dcpt_nafnet_pack(const dcpt_nafnet_plan* p, const float* const* P, void* pac
   NetPacked pk(p, a);
   const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
   int C = p->width;
+  DCPT_TRY(pack_w27_launch(P[0], pk.wi_p, C, 0, st));
+  DCPT_TRY(pack_w27_launch(P[2], pk.wd_p, C, 1, st));
   for (int i = 0; i < ne; ++i) {
     for (int j = 0; j < p->enc[i]; ++j) DCPT_TRY(nafblock_pack_impl(P + p->enc_blks[i][j].pidx, pk.enc_pk[i][j], C, st));
     DCPT_TRY(pack_weight_launch(P[p->down_pidx[i]], nullptr, pk.down[i], 2 * C, 4 * C, PACK_DOWN, st));
@@ -678,7 +691,12 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   int C = p->width, h = H, w = W;
 
   // intro (nafnet_arch.py:252)
-  DCPT_TRY(conv3x3_img_to_feat_launch(inp, P[0], P[1], 0, sv.x0, nullptr, nullptr, N, h, w, C, st));
+  {  // x0 = im2col(inp) * Wi^T + b on the tensor cores
+    DCPT_TRY(im2col3_launch(inp, sv.P, nullptr, 0, 1, N, h, w, st));
+    GemmArgs g = gemm_args(N * h * w, C, 64, sv.P, 64, pk.wi_p, 64, EPI_STORE);  // [P | P] x [W_hi | W_lo]
+    g.ep.out_f32 = sv.x0; g.ep.ldo = C; g.ep.bias = P[1];
+    DCPT_TRY(gemm_launch(g, st));
+  }
   const float* x = sv.x0;
   // encoders + downs (:256-259)
   for (int i = 0; i < ne; ++i) {
@@ -713,7 +731,7 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     h *= 2; w *= 2; C /= 2;
     x = sv.xup[i];
     for (int j = 0; j < p->dec[i]; ++j) {
-      bf16* mirror = (j == p->dec[i] - 1 && i + 1 < nd) ? sv.up_in[i + 1] : nullptr;
+      bf16* mirror = (j == p->dec[i] - 1) ? (i + 1 < nd ? sv.up_in[i + 1] : sv.xlast_bf16) : nullptr;
       DCPT_TRY(nafblock_fwd_impl(P + p->dec_blks[i][j].pidx, pk.dec_pk[i][j], x, sv.dec_out[i][j], mirror, sv.dec_sv[i][j], N, h, w,
                                  C, st));
       x = sv.dec_out[i][j];
@@ -722,7 +740,11 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
       DCPT_CUDA(cudaMemcpyAsync(host_feats[i], x, (size_t)N * h * w * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   // ending + global residual (:271-272)
-  if (!hook) DCPT_TRY(conv3x3_feat_to_img_launch(x, P[2], P[3], inp, out, N, h, w, C, st));
+  if (!hook) {
+    const bool mirrored = nd > 0 && p->dec[nd - 1] > 0 && C <= 64;  // the last block wrote sv.xlast_bf16
+    if (mirrored) DCPT_TRY(ending_fwd_tma_launch(sv.xlast_bf16, P[2], P[3], inp, out, N, h, w, C, st));
+    else DCPT_TRY(conv3x3_feat_to_img_launch(x, P[2], P[3], inp, out, N, h, w, C, st));
+  }
   return 0;
 }
 
@@ -755,11 +777,27 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
                                : (p->middle_blk_num > 0 ? sv.mid_out.back() : sv.x0);
   if (dout) {
     // ending conv: wgrad, bias grad, dgrad (nafnet_arch.py:271)
-    DCPT_CUDA(cudaMemsetAsync(wk.G, 0, (size_t)27 * C * sizeof(float), st));
-    DCPT_TRY(conv3x3_small_wgrad_launch(x_last, dout, wk.G, G[3], 1, N, h, w, C, st));
-    DCPT_TRY(wgrad_finish_perm_launch(wk.G, G[2], C, 27, FIN_CN_TO_C3, st));
-    DCPT_CUDA(cudaMemsetAsync(CUR.s, 0, C * sizeof(float), st));
-    DCPT_TRY(conv3x3_img_to_feat_launch(dout, P[2], nullptr, 1, CUR.f, CUR.t, CUR.s, N, h, w, C, st));
+    const bool mirrored = nd > 0 && p->dec[nd - 1] > 0 && C <= 64;
+    if (mirrored) {
+      // Pd = flipped patches of dout;  dWe = F^T Pd (wgrad GEMM),  dF = Pd Wd^T (GEMM),  colsum(dF) = Wd * colsum(Pd)
+      const int M0 = N * h * w;
+      DCPT_CUDA(cudaMemsetAsync(wk.psum, 0, 32 * sizeof(float), st));
+      DCPT_TRY(im2col3_launch(dout, wk.Pd, wk.psum, 1, 0, N, h, w, st));
+      DCPT_CUDA(cudaMemsetAsync(wk.G, 0, (size_t)32 * C * sizeof(float), st));
+      DCPT_TRY(wgrad_gemm(sv.xlast_bf16, C, wk.Pd, 32, wk.G, M0, st));
+      DCPT_TRY(finish_w27_launch(wk.G, G[2], wk.psum, G[3], C, 1, st));
+      GemmArgs g = gemm_args(M0, C, 32, wk.Pd, 32, pk.wd_p, 32, EPI_STORE);
+      g.ep.out_f32 = CUR.f; g.ep.out_bf16 = CUR.t; g.ep.ldo = C;
+      DCPT_TRY(gemm_launch(g, st));
+      DCPT_CUDA(cudaMemsetAsync(CUR.s, 0, C * sizeof(float), st));
+      DCPT_TRY(ending_colsum_launch(P[2], wk.psum, CUR.s, C, st));
+    } else {
+      DCPT_CUDA(cudaMemsetAsync(wk.G, 0, (size_t)27 * C * sizeof(float), st));
+      DCPT_TRY(conv3x3_small_wgrad_launch(x_last, dout, wk.G, G[3], 1, N, h, w, C, st));
+      DCPT_TRY(wgrad_finish_perm_launch(wk.G, G[2], C, 27, FIN_CN_TO_C3, st));
+      DCPT_CUDA(cudaMemsetAsync(CUR.s, 0, C * sizeof(float), st));
+      DCPT_TRY(conv3x3_img_to_feat_launch(dout, P[2], nullptr, 1, CUR.f, CUR.t, CUR.s, N, h, w, C, st));
+    }
     have = true;
   }
   auto block_bwd = [&](const dcpt_nafnet_plan::Blk& b, const BlockPacked& bpk, const BlockSaved& bsv, const float* x, int hh,
@@ -832,7 +870,9 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   }
   // ---------------- intro: wgrad + bias grad (the input image needs no gradient) ----------------
   DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient reached the intro conv");
-  DCPT_TRY(conv3x3_small_wgrad_launch(CUR.f, inp, G[0], nullptr, 0, N, h, w, C, st));
+  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, (size_t)32 * C * sizeof(float), st));
+  DCPT_TRY(wgrad_gemm(CUR.t, C, sv.P, 32, wk.G, N * h * w, st, 64));  // dWi = dX0^T * im2col(inp)
+  DCPT_TRY(finish_w27_launch(wk.G, G[0], nullptr, nullptr, C, 0, st));
   DCPT_TRY(axpy_launch(G[1], CUR.s, C, st));
 #undef CUR
 #undef NXT

@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 from oracle import nafnet_oracle as O  # noqa: E402
 
 TOL_OUT, TOL_DX, TOL_G = 1e-3, 3e-3, 2e-2
+TOL_NET = 2e-3   # whole-network output: the per-block bf16-operand error accumulates over the depth (DESIGN.md numerics)
 
 
 def rel(a, b):
@@ -103,7 +104,7 @@ def test_nafnet_golden_engine(golden_dir):
     inp = torch.from_numpy(z["inp"]).cuda()
     gt = torch.from_numpy(z["gt"]).cuda()
     out, feats, saved = eng.forward(params, inp, want_feats=True)
-    assert rel(out, z["out"]) < TOL_OUT
+    assert rel(out, z["out"]) < TOL_NET
     for i, f in enumerate(feats):
         # decoder features sit before the `+ inp` of the output: no large fp32 term dilutes the bf16-operand
         # error.  The oracle's rounding hook predicts 3.4-3.7e-3 for this net (DESIGN.md numerics table).
@@ -131,7 +132,7 @@ def test_nafnet_module_matches_oracle_and_trains(golden_dir):
     net.load_state_dict(sd, strict=True)
     inp, gt = torch.from_numpy(z["inp"]).cuda(), torch.from_numpy(z["gt"]).cuda()
     out = net(inp)
-    assert rel(out, z["out"]) < TOL_OUT
+    assert rel(out, z["out"]) < TOL_NET
     loss = (out - gt).abs().mean()
     loss.backward()
     errs = {k: rel(p.grad, z["g." + k]) for k, p in net.named_parameters()}
