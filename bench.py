@@ -169,6 +169,7 @@ def prof_table(lib):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from dcpt_b200.dist import allreduce_mean_
     from dcpt_b200.lib import load_library
     from dcpt_b200.nafnet import NAFNetEngine
     from oracle import nafnet_oracle as O  # only for the synthetic weight generator + cpu_baseline leg
@@ -180,7 +181,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = load_library()
     B = args.batch
     pk = peaks()
@@ -195,13 +197,13 @@ def run_ours(args):
     flat, grads = eng.alloc_flat_grads(params)
     inv_numel = 1.0 / inp.numel()
 
-    def step():
+    def step(comm=True):
         flat.zero_()
         out, _, saved = eng.forward(params, inp)
         dout = torch.sign(out - gt).mul_(inv_numel)       # d L1(mean) / d out
         eng.backward(params, inp, saved, dout, grads=grads)
-        if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        if world > 1 and comm:
+            allreduce_mean_(flat)                           # the path's one exchange step (dcpt_b200/dist.py)
 
     def barrier():
         if world > 1:
@@ -234,7 +236,7 @@ def run_ours(args):
     roof = None
     if rank == 0:
         lib.dcpt_prof_enable(2 if args.shapes else 1)
-        step()
+        step(comm=False)                                   # rank-0 only: must not enter a collective
         rows = prof_table(lib)
         lib.dcpt_prof_enable(0)
         tot = sum(r["ms"] for r in rows) or 1.0

@@ -1,0 +1,95 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads, exports exactly what include/dcpt_ops.h
+declares, argument errors come back as codes + messages (no exceptions, no CUDA needed), and the product package
+never touches oracle/ or falls back to CPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dcpt_b200.build import build
+    build()
+    from dcpt_b200.lib import load_library
+    return load_library()
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "dcpt_ops.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcpt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from dcpt_b200.lib import LIB_PATH, PROTOTYPES
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (dcpt_[a-z0-9_]+)", out))
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in dcpt_ops.h but not exported: {missing}"
+    extra = sorted(exported - set(declared))
+    assert not extra, f"exported but undeclared: {extra}"
+    assert sorted(PROTOTYPES) == declared, "ctypes prototypes out of sync with the header"
+    assert lib.dcpt_abi_version() == 1
+
+
+def test_plan_and_size_queries_need_no_gpu(lib):
+    enc = (ctypes.c_int * 4)(1, 1, 1, 28)
+    dec = (ctypes.c_int * 4)(1, 1, 1, 1)
+    plan = ctypes.c_void_p(lib.dcpt_nafnet_create(3, 64, 1, enc, 4, dec, 4))
+    assert plan.value
+    assert lib.dcpt_nafnet_num_params(plan) == 664                       # NAFNet-w64 has 664 tensors
+    dims = (ctypes.c_int * 4)()
+    total = sum(lib.dcpt_nafnet_param_shape(plan, i, dims) for i in range(664))
+    assert total == 67_888_835                                            # SURVEY.md §2c parameter count
+    assert lib.dcpt_nafnet_saved_bytes(plan, 16, 256, 256) > lib.dcpt_nafnet_saved_bytes(plan, 1, 256, 256) > 0
+    assert lib.dcpt_nafnet_workspace_bytes(plan, 1, 256, 256) > 0 and lib.dcpt_nafnet_packed_bytes(plan) > 0
+    lib.dcpt_nafnet_destroy(plan)
+    assert lib.dcpt_nafblock_saved_bytes(2, 8, 8, 64) > 0 and lib.dcpt_nafblock_packed_bytes(64) > 0
+
+
+def test_argument_errors_are_codes_not_exceptions(lib):
+    enc = (ctypes.c_int * 1)(1)
+    assert not lib.dcpt_nafnet_create(3, 12, 1, enc, 1, enc, 1)           # width % 8 != 0
+    assert b"width" in lib.dcpt_last_error()
+    rc = lib.dcpt_layernorm2d_fwd(None, None, None, None, None, 16, 12, 1e-6, None)   # C % 8 != 0 -> rejected before any launch
+    assert rc == -2 and b"layernorm" in lib.dcpt_last_error()
+    rc = lib.dcpt_gemm_bf16(None, 8, 0, None, 8, 0, 0, 8, 8, None, None, 8, None, None, 1, 0, 0, None)
+    assert rc == -2
+
+
+def test_product_never_imports_oracle_or_falls_back():
+    for pkg in ("dcpt_b200", "basicsr"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{pkg}/{f} imports oracle"
+    code = ("import torch, sys; sys.path.insert(0, %r)\n"
+            "from basicsr.archs import build_network\n"
+            "net = build_network(dict(type='NAFNetBaseline', width=8, enc_blk_nums=[1], middle_blk_num=1, dec_blk_nums=[1]))\n"
+            "try:\n    net(torch.rand(1, 3, 8, 8)); print('RAN')\n"
+            "except Exception as e:\n    print(type(e).__name__)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "DcptError" in r.stdout and "RAN" not in r.stdout, r.stdout + r.stderr
+
+
+def test_registry_surface():
+    from basicsr.archs import build_network
+    from basicsr.utils.registry import ARCH_REGISTRY
+    from oracle.nafnet_oracle import nafnet_state_dict_keys
+    assert "NAFNetBaseline" in ARCH_REGISTRY
+    kw = dict(width=64, enc_blk_nums=[1, 1, 1, 28], middle_blk_num=1, dec_blk_nums=[1, 1, 1, 1], window_size=16)
+    net = build_network(dict(type="NAFNetBaseline", **kw))                # options/all_in_one/test/test_NAFNet_5d.yml:50-56
+    got = [(k, tuple(v.shape)) for k, v in net.named_parameters()]
+    assert got == nafnet_state_dict_keys(64, [1, 1, 1, 28], 1, [1, 1, 1, 1])
+    assert list(net.state_dict().keys()) == [k for k, _ in got]
+    with pytest.raises(AssertionError):
+        ARCH_REGISTRY.register(type(net))                                 # duplicate names rejected (registry.py:42-45)
