@@ -55,8 +55,8 @@ int dcpt_num_sms();
 // Host-side TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point; gemm_sm100.cu).
 // 2-D: row-major bf16 [rows, cols], box 64 x box_rows, 128-byte swizzle (UMMA operand tiles).
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
-// 4-D: bf16 NHWC [N, H, W, CH], box 64 x box_w x box_h x 1, no swizzle (stencil tiles, zero-filled halo).
-int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h);
+// 4-D: bf16 NHWC [N, H, W, CH], box 64 x box_w x box_h x 1 (stencil tiles / implicit-GEMM conv operands, zero-filled halo).
+int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h, int swizzle128 = 0);
 
 // ----------------------------------------------------------------------------
 // device helpers

@@ -67,3 +67,20 @@ int finish_w27_launch(const float* G, float* dw, const float* psum, float* db, i
 int ending_colsum_launch(const float* w, const float* psum, float* colsum, int C, cudaStream_t st);
 int ending_fwd_tma_launch(const bf16* feat, const float* w, const float* bias, const float* resid_img, float* out_img, int N, int H,
                           int W, int C, cudaStream_t st);
+
+// Degradation-classifier head glue kernels (dchead.cu), bf16 NHWC trunk.
+int ln_act_fwd_launch(const bf16* x, const float* w, const float* b, const bf16* resid, bf16* y, float* stats, int M, int C, int relu,
+                      float eps, cudaStream_t st);
+int ln_act_bwd_launch(const float* dy, const bf16* y, const bf16* x, const float* stats, const float* w, bf16* dx, float* dres,
+                      float* dw, float* db, int M, int C, int relu, cudaStream_t st);
+int mix_fwd_launch(const bf16* prev, const float* feat, const float* mw, bf16* z, long long n, cudaStream_t st);
+int mix_bwd_launch(const float* dz, const float* feat, const float* mw, float* dfeat, float* dmw, long long n, cudaStream_t st);
+int maxpool2_relu_fwd_launch(const bf16* x, bf16* y, int N, int Ho, int Wo, int C, cudaStream_t st);
+int maxpool2_relu_bwd_launch(const bf16* x, const float* dy, bf16* dx, int N, int Ho, int Wo, int C, cudaStream_t st);
+int meanpool_fc_fwd_launch(const bf16* x, const float* w, const float* b, float* pooled, float* logits, int N, int HW, int C, int K,
+                           cudaStream_t st);
+int meanpool_fc_bwd_launch(const float* dlogits, const float* pooled, const float* w, float* dw, float* db, float* dx, int N, int HW,
+                           int C, int K, cudaStream_t st);
+int add_bf16_launch(const bf16* a, const bf16* b, bf16* out, long long n, cudaStream_t st);
+int pack_conv3x3_launch(const float* w, bf16* out, int Cout, int Cin, int dgrad, cudaStream_t st);
+int finish_conv3x3_launch(const float* G, float* dw, int Cout, int Cin, cudaStream_t st);

@@ -47,6 +47,29 @@ struct GemmArgs {
   EpiParams ep;
 };
 
+// Geometry of the implicit-GEMM 3x3 convolution modes of the tensor-core kernel (gemm_sm100.cu).
+struct ConvGeom {
+  int H, W;
+  int tw_log2;  // pixel patch = th x (1 << tw_log2)
+  int th;
+  int tiles_w, tiles_h;
+  int cblocks;  // ceil(Cin / 64)
+};
+
+// Dense 3x3 convolution, stride 1, zero pad 1, NHWC bf16 (reference: BottleneckBlock.conv2,
+// archs/degrad_classify_arch.py:178-188): out[px][co] = sum_{tap,ci} X[px + tap][ci] * Wp[co][tap * cin_pad + ci],
+// cin_pad = Cin rounded up to 64, tap = ky*3 + kx.  The epilogue is EPI_STORE (ep.out_* indexed by linear pixel).
+struct Conv3x3Args {
+  const bf16* X;
+  int N, H, W, Cin;
+  const bf16* Wp;
+  int Cout;
+  EpiParams ep;
+};
+int conv3x3_tc_launch(const Conv3x3Args& a, cudaStream_t stream);
+// G[co][tap * cin_pad + ci] += sum_px dY[px][co] * X[px + tap][ci]   (fp32, split-K over pixel patches)
+int conv3x3_wgrad_tc_launch(const bf16* dY, const bf16* X, float* G, int N, int H, int W, int Cin, int Cout, cudaStream_t stream);
+
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream);    // tcgen05 + TMA (product path)
 int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);  // CUDA-core cross-check (tests only)
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);       // dispatch (DCPT_GEMM_SIMT=1 selects simt)

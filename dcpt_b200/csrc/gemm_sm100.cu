@@ -13,6 +13,7 @@
 // swizzle row).  MN-major operands (wgrad) are loaded as 64x64 boxes, which
 // the UMMA descriptor addresses with LBO = 8 KiB / SBO = 1 KiB.
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -53,10 +54,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN, int EPI, bool A_MN, bool B_MN>
+// CONV = 0: plain GEMM.  CONV = 1: implicit-GEMM 3x3 convolution (pad 1, stride 1), A = NHWC activation through a 4-D
+// tensor map: the M tile is a TH x TW pixel patch of one image and k-block kb = (tap, 64-channel block) loads the
+// patch shifted by the tap, zero-filled outside the image.  CONV = 2: its wgrad, contracting over 64-pixel patches
+// (A = dY patch, B = X patch shifted by the tap of this N tile), MN-major operands.
+template <int BN, int EPI, bool A_MN, bool B_MN, int CONV>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep) {
+               int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep, ConvGeom cg) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -121,26 +126,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           // L2 prefetch of the HBM-streamed operand(s), PF_DIST k-blocks ahead of the smem ring (which can hold
           // only STAGES blocks in flight: not enough to cover DRAM latency for a short-K tile).
-          if (kb == kb0) {
-            for (int pk = kb0; pk < min(kb1, kb0 + PF_DIST); ++pk) prefetch_kb(pk, m_t, n_t);
-          } else if (kb + PF_DIST - 1 < kb1) {
-            prefetch_kb(kb + PF_DIST - 1, m_t, n_t);
+          if constexpr (CONV == 0) {
+            if (kb == kb0) {
+              for (int pk = kb0; pk < min(kb1, kb0 + PF_DIST); ++pk) prefetch_kb(pk, m_t, n_t);
+            } else if (kb + PF_DIST - 1 < kb1) {
+              prefetch_kb(kb + PF_DIST - 1, m_t, n_t);
+            }
           }
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
           uint8_t* a_dst = sA + (size_t)stage * A_STAGE_BYTES;
           uint8_t* b_dst = sB + (size_t)stage * C::B_STAGE_BYTES;
-          if constexpr (!A_MN) {
-            tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_t * BM);
-          } else {
-#pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * 8192, &tmA, &full[stage], m_t * BM + c * 64, kb * BK);
-          }
-          if constexpr (!B_MN) {
+          if constexpr (CONV == 1) {
+            const int per_img = cg.tiles_h * cg.tiles_w;
+            const int img = m_t / per_img, rem = m_t - img * per_img;
+            const int h0 = (rem / cg.tiles_w) * cg.th, w0 = (rem % cg.tiles_w) << cg.tw_log2;
+            const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
+            tma_load_4d(a_dst, &tmA, &full[stage], cb * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, img);
             tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, n_t * BN);
-          } else {
+          } else if constexpr (CONV == 2) {
+            const int per_img = cg.tiles_h * cg.tiles_w;
+            const int img = kb / per_img, rem = kb - img * per_img;
+            const int h0 = (rem / cg.tiles_w) * cg.th, w0 = (rem % cg.tiles_w) << cg.tw_log2;
+            const int cin_pad = cg.cblocks * 64;
+            const int tap = (n_t * BN) / cin_pad, ci0 = n_t * BN - tap * cin_pad;
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, &tmB, &full[stage], n_t * BN + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * 8192, &tmA, &full[stage], m_t * BM + c * 64, w0, h0, img);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_4d(b_dst + c * 8192, &tmB, &full[stage], ci0 + c * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, img);
+          } else {
+            if constexpr (!A_MN) {
+              tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_t * BM);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * 8192, &tmA, &full[stage], m_t * BM + c * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, n_t * BN);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, &tmB, &full[stage], n_t * BN + c * 64, kb * BK);
+            }
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -207,8 +234,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_t = tile % tiles_n;
       const int m_t = (tile / tiles_n) % tiles_m;
       const int m_base = m_t * BM + q * 32;
+      // row r of this warp's 32-row slab -> global output row (or -1): linear for GEMMs, patch pixel for CONV == 1
+      int cv_img = 0, cv_h0 = 0, cv_w0 = 0;
+      if constexpr (CONV == 1) {
+        const int per_img = cg.tiles_h * cg.tiles_w;
+        cv_img = m_t / per_img;
+        const int rem = m_t - cv_img * per_img;
+        cv_h0 = (rem / cg.tiles_w) * cg.th;
+        cv_w0 = (rem % cg.tiles_w) << cg.tw_log2;
+      }
+      auto out_row = [&](int r) -> int {
+        if constexpr (CONV == 1) {
+          const int rt = q * 32 + r;
+          const int h = cv_h0 + (rt >> cg.tw_log2), w = cv_w0 + (rt & ((1 << cg.tw_log2) - 1));
+          return (h < cg.H && w < cg.W) ? (cv_img * cg.H + h) * cg.W + w : -1;
+        } else {
+          return m_base + r < M ? m_base + r : -1;
+        }
+      };
       // While the tensor core works on this tile, pull the epilogue's global inputs into L2.
-      if constexpr (EPI == EPI_STORE) {
+      if constexpr (EPI == EPI_STORE && CONV == 0) {
         if (ep.resid) {
           for (int i = lane + chalf * 32; i < 32 * (BN / 32); i += 64) {
             const int r = i / (BN / 32), l = i % (BN / 32);
@@ -242,27 +287,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int r0 = lane >> 2;
           EpiExtra ex[4];
 #pragma unroll
-          for (int it = 0; it < 4; ++it)
-            if (m_base + it * 8 + r0 < M && na < N) ex[it] = epilogue_load<EPI>(ep, m_base + it * 8 + r0, na);
+          for (int it = 0; it < 4; ++it) {
+            const int m = out_row(it * 8 + r0);
+            if (m >= 0 && na < N) ex[it] = epilogue_load<EPI>(ep, m, na);
+          }
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int r = it * 8 + r0;
             const float4 a = stage[r * 8 + ((g * 4 + qq) ^ (r & 7))];
             const float4 b = stage[r * 8 + ((g * 4 + 2 + qq) ^ (r & 7))];
-            if (m_base + r < M && na < N) epilogue_store<EPI>(ep, m_base + r, na, a, b, ex[it]);
+            const int m = out_row(r);
+            if (m >= 0 && na < N) epilogue_store<EPI>(ep, m, na, a, b, ex[it]);
           }
         } else {
           const int cc = lane & 7, r0 = lane >> 3;
           const int n = n0 + cc * 4;
           EpiExtra ex[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it)
-            if (m_base + it * 4 + r0 < M && n < N) ex[it] = epilogue_load<EPI>(ep, m_base + it * 4 + r0, n);
+          for (int it = 0; it < 8; ++it) {
+            const int m = out_row(it * 4 + r0);
+            if (m >= 0 && n < N) ex[it] = epilogue_load<EPI>(ep, m, n);
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + r0;
             const float4 x = stage[r * 8 + (cc ^ (r & 7))];
-            if (m_base + r < M && n < N) epilogue_store<EPI>(ep, m_base + r, n, x, x, ex[it]);
+            const int m = out_row(r);
+            if (m >= 0 && n < N) epilogue_store<EPI>(ep, m, n, x, x, ex[it]);
           }
         }
         __syncwarp();
@@ -323,7 +374,7 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long rows, long long col
   return 0;
 }
 
-int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h) {
+int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h, int swizzle128) {
   EncodeTiledFn fn = get_encode_fn();
   DCPT_CHECK_ARG(fn != nullptr, DCPT_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   DCPT_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (CH % 8) == 0, DCPT_E_ALIGN,
@@ -333,8 +384,8 @@ int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH
   cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCPT_CHECK_ARG(r == CUDA_SUCCESS, DCPT_E_DRIVER, "cuTensorMapEncodeTiled(4d) failed (%d): N=%d H=%d W=%d C=%d box=%dx%d", (int)r, N,
                  H, W, CH, box_w, box_h);
   return 0;
@@ -344,6 +395,7 @@ namespace {
 
 template <int BN, int EPI, bool A_MN, bool B_MN>
 int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
+  const ConvGeom cg0 = {};
   using C = Cfg<BN>;
   CUtensorMap tmA, tmB;
   if (!g.a_mn) DCPT_TRY(make_tmap_2d(&tmA, g.A, g.M, g.K, g.lda, BM));
@@ -360,7 +412,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   const int total = tiles_m * tiles_n * splits;
   const int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
 
-  auto kern = gemm_tc_kernel<BN, EPI, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, EPI, A_MN, B_MN, 0>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     DCPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
@@ -380,7 +432,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   const double out_bytes = (double)g.M * g.N * ((g.ep.out_f32 ? 4.0 : 0.0) + (g.ep.out_bf16 ? 2.0 : 0.0) + (g.ep.resid ? 4.0 : 0.0) +
                                                 (EPI == EPI_GATE ? 1.0 : 0.0) + (EPI == EPI_GATE_BWD ? 4.0 : 0.0));
   DCPT_PROF(tag, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes, stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, g.M, g.N, g.K, tiles_m, tiles_n, splits, kbps, g.ep);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, g.M, g.N, g.K, tiles_m, tiles_n, splits, kbps, g.ep, cg0);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -393,7 +445,93 @@ int launch_bn(const GemmArgs& g, cudaStream_t stream) {
   return launch_cfg<64, EPI, A_MN, B_MN>(g, stream);
 }
 
+ConvGeom conv_geom(int H, int W, int cin_pad, int rows_per_tile) {
+  ConvGeom cg;
+  cg.H = H; cg.W = W;
+  cg.tw_log2 = W >= 16 ? 4 : (W >= 8 ? 3 : 2);
+  cg.th = rows_per_tile >> cg.tw_log2;
+  cg.tiles_w = ceil_div(W, 1 << cg.tw_log2);
+  cg.tiles_h = ceil_div(H, cg.th);
+  cg.cblocks = cin_pad / 64;
+  return cg;
+}
+
+template <int BN>
+int conv_fwd_cfg(const Conv3x3Args& a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  const int cin_pad = ceil_div(a.Cin, 64) * 64;
+  const ConvGeom cg = conv_geom(a.H, a.W, cin_pad, BM);
+  CUtensorMap tmA, tmB;
+  DCPT_TRY(make_tmap_nhwc(&tmA, a.X, a.N, a.H, a.W, a.Cin, 1 << cg.tw_log2, cg.th, 1));
+  DCPT_TRY(make_tmap_2d(&tmB, a.Wp, a.Cout, 9 * cin_pad, 9 * cin_pad, BN));
+  const int tiles_m = a.N * cg.tiles_h * cg.tiles_w, tiles_n = ceil_div(a.Cout, BN), num_kb = 9 * cg.cblocks;
+  const int total = tiles_m * tiles_n;
+  const int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
+  auto kern = gemm_tc_kernel<BN, EPI_STORE, false, false, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DCPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const double Mpx = (double)a.N * a.H * a.W;
+  DCPT_PROF(BN == 256 ? "conv3x3_tc<256>" : (BN == 128 ? "conv3x3_tc<128>" : "conv3x3_tc<64>"), 2.0 * Mpx * a.Cout * 9 * a.Cin,
+            2.0 * Mpx * (a.Cin + a.Cout), stream);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, a.N * a.H * a.W, a.Cout, num_kb * BK, tiles_m, tiles_n, 1, num_kb, a.ep, cg);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int conv_wgrad_cfg(const bf16* dY, const bf16* X, float* G, int N, int H, int W, int Cin, int Cout, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  const int cin_pad = ceil_div(Cin, 64) * 64;
+  const ConvGeom cg = conv_geom(H, W, cin_pad, 64);
+  CUtensorMap tmA, tmB;
+  DCPT_TRY(make_tmap_nhwc(&tmA, dY, N, H, W, Cout, 1 << cg.tw_log2, cg.th, 1));
+  DCPT_TRY(make_tmap_nhwc(&tmB, X, N, H, W, Cin, 1 << cg.tw_log2, cg.th, 1));
+  const int tiles_m = ceil_div(Cout, BM), tiles_n = 9 * cin_pad / BN, num_kb = N * cg.tiles_h * cg.tiles_w;
+  int splits = ceil_div(dcpt_num_sms(), tiles_m * tiles_n);
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  const int kbps = ceil_div(num_kb, splits);
+  splits = ceil_div(num_kb, kbps);
+  const int total = tiles_m * tiles_n * splits;
+  const int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.out_f32 = G; ep.ldo = 9 * cin_pad;
+  auto kern = gemm_tc_kernel<BN, EPI_ATOMIC, true, true, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DCPT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const double Mpx = (double)N * H * W;
+  DCPT_PROF("conv3x3_wgrad_tc", 2.0 * Mpx * Cout * 9 * Cin, 2.0 * Mpx * (Cin + Cout), stream);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, Cout, 9 * cin_pad, num_kb * BK, tiles_m, tiles_n, splits, kbps, ep, cg);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
+
+int conv3x3_tc_launch(const Conv3x3Args& a, cudaStream_t stream) {
+  DCPT_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.Cin % 8 == 0 && a.Cout % 8 == 0 && a.Cin >= 8 && a.Cout >= 8, DCPT_E_SHAPE,
+                 "conv3x3: need Cin, Cout multiples of 8 (N=%d H=%d W=%d Cin=%d Cout=%d)", a.N, a.H, a.W, a.Cin, a.Cout);
+  DCPT_CHECK_ARG((long long)a.N * a.H * a.W < (1ll << 31) / 1024, DCPT_E_SHAPE, "conv3x3: too many pixels");
+  if (a.Cout > 128) return conv_fwd_cfg<256>(a, stream);
+  if (a.Cout > 64) return conv_fwd_cfg<128>(a, stream);
+  return conv_fwd_cfg<64>(a, stream);
+}
+
+int conv3x3_wgrad_tc_launch(const bf16* dY, const bf16* X, float* G, int N, int H, int W, int Cin, int Cout, cudaStream_t stream) {
+  DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cout % 8 == 0, DCPT_E_SHAPE, "conv3x3 wgrad: bad shape");
+  const int cin_pad = ceil_div(Cin, 64) * 64;
+  // one N tile must stay inside one tap: BN divides cin_pad
+  if (cin_pad % 256 == 0) return conv_wgrad_cfg<256>(dY, X, G, N, H, W, Cin, Cout, stream);
+  if (cin_pad % 128 == 0) return conv_wgrad_cfg<128>(dY, X, G, N, H, W, Cin, Cout, stream);
+  return conv_wgrad_cfg<64>(dY, X, G, N, H, W, Cin, Cout, stream);
+}
 
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   DCPT_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, DCPT_E_SHAPE, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);

@@ -502,6 +502,11 @@ int dcpt_gemm_ex(const dcpt_gemm_desc* d, int impl, dcpt_stream_t stream) {
   GemmArgs g = gemm_args(d->M, d->N, d->K, static_cast<const bf16*>(d->A), d->lda, static_cast<const bf16*>(d->B), d->ldb,
                          d->epilogue);
   g.a_mn = d->a_mn; g.b_mn = d->b_mn; g.splits = d->splits < 1 ? 1 : d->splits;
+  if (d->splits == 0 && d->epilogue == EPI_ATOMIC) {  // auto split-K: fill the machine
+    const int bn = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
+    const int tiles = ceil_div(d->M, 128) * ceil_div(d->N, bn);
+    g.splits = ceil_div(dcpt_num_sms(), tiles);
+  }
   g.ep.out_f32 = d->out_f32; g.ep.out_bf16 = static_cast<bf16*>(d->out_bf16); g.ep.ldo = d->ldo;
   g.ep.bias = d->bias; g.ep.resid = d->resid; g.ep.ldr = d->ldr;
   g.ep.out2 = static_cast<bf16*>(d->out2_bf16); g.ep.ldo2 = d->ldo2;
@@ -878,5 +883,70 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
 #undef NXT
   return 0;
 }
+
+// ------------------------------- DC head building blocks -------------------------
+#define ST(s) static_cast<cudaStream_t>(s)
+#define BF(p) static_cast<bf16*>(p)
+#define CBF(p) static_cast<const bf16*>(p)
+
+int dcpt_pack_matrix(const float* w, void* out_bf16, int O, int I, int transpose, dcpt_stream_t stream) {
+  return pack_weight_launch(w, nullptr, BF(out_bf16), O, I, transpose ? PACK_T : PACK_PLAIN, ST(stream));
+}
+size_t dcpt_conv3x3_packed_elems(int Cout, int Cin, int dgrad) {
+  const int R = dgrad ? Cin : Cout, Cc = dgrad ? Cout : Cin;
+  return (size_t)R * 9 * (ceil_div(Cc, 64) * 64);
+}
+int dcpt_conv3x3_pack(const float* w, void* out_bf16, int Cout, int Cin, int dgrad, dcpt_stream_t stream) {
+  return pack_conv3x3_launch(w, BF(out_bf16), Cout, Cin, dgrad, ST(stream));
+}
+int dcpt_conv3x3_fwd(const void* x_bf16, const void* w_packed, void* out_bf16, float* out_f32, int N, int H, int W, int Cin, int Cout,
+                     dcpt_stream_t stream) {
+  Conv3x3Args a;
+  memset(&a, 0, sizeof(a));
+  a.X = CBF(x_bf16); a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Wp = CBF(w_packed); a.Cout = Cout;
+  a.ep.out_bf16 = BF(out_bf16); a.ep.out_f32 = out_f32; a.ep.ldo = Cout;
+  return conv3x3_tc_launch(a, ST(stream));
+}
+int dcpt_conv3x3_wgrad(const void* dy_bf16, const void* x_bf16, float* scratch, float* dw, int N, int H, int W, int Cin, int Cout,
+                       dcpt_stream_t stream) {
+  const size_t n = (size_t)Cout * 9 * (ceil_div(Cin, 64) * 64);
+  DCPT_CUDA(cudaMemsetAsync(scratch, 0, n * sizeof(float), ST(stream)));
+  DCPT_TRY(conv3x3_wgrad_tc_launch(CBF(dy_bf16), CBF(x_bf16), scratch, N, H, W, Cin, Cout, ST(stream)));
+  return finish_conv3x3_launch(scratch, dw, Cout, Cin, ST(stream));
+}
+int dcpt_ln_act_fwd(const void* x_bf16, const float* weight, const float* bias, const void* resid_bf16, void* y_bf16, float* stats,
+                    int M, int C, int relu, float eps, dcpt_stream_t stream) {
+  return ln_act_fwd_launch(CBF(x_bf16), weight, bias, CBF(resid_bf16), BF(y_bf16), stats, M, C, relu, eps, ST(stream));
+}
+int dcpt_ln_act_bwd(const float* dy, const void* y_bf16, const void* x_bf16, const float* stats, const float* weight,
+                    void* dx_bf16, float* dres, float* dweight, float* dbias, int M, int C, int relu, dcpt_stream_t stream) {
+  return ln_act_bwd_launch(dy, CBF(y_bf16), CBF(x_bf16), stats, weight, BF(dx_bf16), dres, dweight, dbias, M, C, relu, ST(stream));
+}
+int dcpt_mix_fwd(const void* prev_bf16, const float* feat, const float* mw, void* z_bf16, long long n, dcpt_stream_t stream) {
+  return mix_fwd_launch(CBF(prev_bf16), feat, mw, BF(z_bf16), n, ST(stream));
+}
+int dcpt_mix_bwd(const float* dz, const float* feat, const float* mw, float* dfeat, float* dmw, long long n, dcpt_stream_t stream) {
+  return mix_bwd_launch(dz, feat, mw, dfeat, dmw, n, ST(stream));
+}
+int dcpt_maxpool2_relu_fwd(const void* x_bf16, void* y_bf16, int N, int Ho, int Wo, int C, dcpt_stream_t stream) {
+  return maxpool2_relu_fwd_launch(CBF(x_bf16), BF(y_bf16), N, Ho, Wo, C, ST(stream));
+}
+int dcpt_maxpool2_relu_bwd(const void* x_bf16, const float* dy, void* dx_bf16, int N, int Ho, int Wo, int C, dcpt_stream_t stream) {
+  return maxpool2_relu_bwd_launch(CBF(x_bf16), dy, BF(dx_bf16), N, Ho, Wo, C, ST(stream));
+}
+int dcpt_meanpool_fc_fwd(const void* x_bf16, const float* weight, const float* bias, float* pooled, float* logits, int N, int HW, int C,
+                         int K, dcpt_stream_t stream) {
+  return meanpool_fc_fwd_launch(CBF(x_bf16), weight, bias, pooled, logits, N, HW, C, K, ST(stream));
+}
+int dcpt_meanpool_fc_bwd(const float* dlogits, const float* pooled, const float* weight, float* dweight, float* dbias, float* dx,
+                         int N, int HW, int C, int K, dcpt_stream_t stream) {
+  return meanpool_fc_bwd_launch(dlogits, pooled, weight, dweight, dbias, dx, N, HW, C, K, ST(stream));
+}
+int dcpt_add_bf16(const void* a, const void* b, void* out, long long n, dcpt_stream_t stream) {
+  return add_bf16_launch(CBF(a), CBF(b), BF(out), n, ST(stream));
+}
+#undef ST
+#undef BF
+#undef CBF
 
 }  // extern "C"

@@ -1,0 +1,223 @@
+"""Host-side engine for the degradation-classifier head ``PromptIR_NoImg_DC`` (reference:
+basicsr/archs/degrad_classify_arch.py:558-641) on the sm_100a kernels.
+
+Trunk tensors are bf16 NHWC; every convolution runs on the tcgen05 GEMM engine (1x1: ``dcpt_gemm_bf16``; dense 3x3:
+``dcpt_conv3x3_fwd`` implicit GEMM; weight gradients: split-K MN-major GEMM / ``dcpt_conv3x3_wgrad``); LayerNorm+ReLU,
+feature mixing, max-pool and the pooled classifier are CUDA-core kernels of ``csrc/dchead.cu``.  The Python here only
+sequences C-ABI calls and owns the buffers (the reference's host side is Python too); ``dchead_apply`` wraps a whole
+forward / backward in ONE ``autograd.Function`` so it composes with the NAFNet function under ``loss.backward()``.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as _l
+from .ops import _p, _stream, gemm
+
+BF = torch.bfloat16
+
+
+def _bottleneck_names(prefix):
+    return [prefix + n for n in ("conv1.weight", "conv1.norm.weight", "conv1.norm.bias", "conv2.weight", "conv2.norm.weight",
+                                 "conv2.norm.bias", "conv3.weight", "conv3.norm.weight", "conv3.norm.bias")]
+
+
+class DCHeadEngine:
+    def __init__(self, feature_dims, num_res_blocks=2, num_classes=3):
+        self.lib = _l.load_library()
+        self.dims = list(feature_dims)
+        self.nb = num_res_blocks
+        self.k = num_classes
+        # parameter order == reference named_parameters() (degrad_classify_arch.py:577-620)
+        names = ["mixing_weights"]
+        for i in range(len(self.dims)):
+            for j in range(self.nb):
+                names += _bottleneck_names(f"bottleneck_layers.{i}.{j}.")
+        names += [f"downsample_layers.{i}.0.weight" for i in range(len(self.dims))]
+        for j in range(self.nb):
+            names += _bottleneck_names(f"last_stage.{j}.")
+        names += ["fc.weight", "fc.bias"]
+        self.names = names
+        self.index = {n: i for i, n in enumerate(names)}
+        self._packed = None
+        self._packed_key = None
+
+    # ---- packed bf16 operand cache ---------------------------------------------------------------
+    def _pack(self, params):
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key == self._packed_key:
+            return self._packed
+        dev = params[0].device
+        P = lambda n: params[self.index[n]]
+        pk = {}
+
+        def mat(name):
+            w = P(name)
+            O, I = w.shape[0], w.shape[1]
+            a = torch.empty(O, I, dtype=BF, device=dev)
+            b = torch.empty(I, O, dtype=BF, device=dev)
+            _l.check(self.lib.dcpt_pack_matrix(_p(w), _p(a), O, I, 0, _stream()), "pack_matrix")
+            _l.check(self.lib.dcpt_pack_matrix(_p(w), _p(b), O, I, 1, _stream()), "pack_matrix")
+            pk[name] = (a, b)
+
+        def conv3(name):
+            w = P(name)
+            O, I = w.shape[0], w.shape[1]
+            a = torch.empty(self.lib.dcpt_conv3x3_packed_elems(O, I, 0), dtype=BF, device=dev)
+            b = torch.empty(self.lib.dcpt_conv3x3_packed_elems(O, I, 1), dtype=BF, device=dev)
+            _l.check(self.lib.dcpt_conv3x3_pack(_p(w), _p(a), O, I, 0, _stream()), "conv3x3_pack")
+            _l.check(self.lib.dcpt_conv3x3_pack(_p(w), _p(b), O, I, 1, _stream()), "conv3x3_pack")
+            pk[name] = (a, b)
+
+        for n in self.names:
+            if n.endswith("conv2.weight"):
+                conv3(n)
+            elif n.endswith("conv1.weight") or n.endswith("conv3.weight") or n.startswith("downsample_layers"):
+                mat(n)
+        self._packed, self._packed_key = pk, key
+        return pk
+
+    # ---- one BottleneckBlock (degrad_classify_arch.py:227-243) ------------------------------------
+    def _ln(self, x, w, b, resid, relu):
+        M, Cc = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(M, 2, dtype=torch.float32, device=x.device)
+        _l.check(self.lib.dcpt_ln_act_fwd(_p(x), _p(w), _p(b), _p(resid), _p(y), _p(stats), M, Cc, int(relu), 1e-6, _stream()),
+                 "ln_act_fwd")
+        return y, stats
+
+    def _ln_bwd(self, dy, y, x, stats, w, gw, gb, want_dres):
+        M, Cc = x.shape
+        dx = torch.empty_like(x)                                   # bf16: operand of the following dgrad / wgrad GEMMs
+        dres = torch.empty(M, Cc, dtype=torch.float32, device=x.device) if want_dres else None
+        _l.check(self.lib.dcpt_ln_act_bwd(_p(dy), _p(y), _p(x), _p(stats), _p(w), _p(dx), _p(dres), _p(gw), _p(gb), M, Cc, 1,
+                                          _stream()), "ln_act_bwd")
+        return dx, dres
+
+    def _block_fwd(self, x, shp, params, pk, prefix):
+        N, H, W, f = shp
+        P = lambda n: params[self.index[prefix + n]]
+        t1 = gemm(x, pk[prefix + "conv1.weight"][0])
+        a, s1 = self._ln(t1, P("conv1.norm.weight"), P("conv1.norm.bias"), None, True)
+        t2 = torch.empty_like(a)
+        _l.check(self.lib.dcpt_conv3x3_fwd(_p(a), _p(pk[prefix + "conv2.weight"][0]), _p(t2), None, N, H, W, 2 * f, 2 * f, _stream()),
+                 "conv3x3_fwd")
+        b, s2 = self._ln(t2, P("conv2.norm.weight"), P("conv2.norm.bias"), None, True)
+        t3 = gemm(b, pk[prefix + "conv3.weight"][0])
+        out, s3 = self._ln(t3, P("conv3.norm.weight"), P("conv3.norm.bias"), x, True)
+        return out, (x, t1, a, s1, t2, b, s2, t3, out, s3)
+
+    def _block_bwd(self, dout, shp, saved, params, grads, pk, prefix, scratch):
+        N, H, W, f = shp
+        x, t1, a, s1, t2, b, s2, t3, out, s3 = saved
+        P = lambda n: params[self.index[prefix + n]]
+        G = lambda n: grads[self.index[prefix + n]]
+        dt3, dres = self._ln_bwd(dout, out, t3, s3, P("conv3.norm.weight"), G("conv3.norm.weight"), G("conv3.norm.bias"), True)
+        gemm(dt3, b, a_mn=True, b_mn=True, accumulate_into=G("conv3.weight").view(f, 2 * f), splits=0)
+        db = gemm(dt3, pk[prefix + "conv3.weight"][1], out_dtype=torch.float32)      # gradients entering LN' stay fp32
+        dt2, _ = self._ln_bwd(db, b, t2, s2, P("conv2.norm.weight"), G("conv2.norm.weight"), G("conv2.norm.bias"), False)
+        _l.check(self.lib.dcpt_conv3x3_wgrad(_p(dt2), _p(a), _p(scratch), _p(G("conv2.weight")), N, H, W, 2 * f, 2 * f, _stream()),
+                 "conv3x3_wgrad")
+        da = torch.empty(a.shape, dtype=torch.float32, device=a.device)
+        _l.check(self.lib.dcpt_conv3x3_fwd(_p(dt2), _p(pk[prefix + "conv2.weight"][1]), None, _p(da), N, H, W, 2 * f, 2 * f,
+                                           _stream()), "conv3x3_dgrad")
+        dt1, _ = self._ln_bwd(da, a, t1, s1, P("conv1.norm.weight"), G("conv1.norm.weight"), G("conv1.norm.bias"), False)
+        gemm(dt1, x, a_mn=True, b_mn=True, accumulate_into=G("conv1.weight").view(2 * f, f), splits=0)
+        return gemm(dt1, pk[prefix + "conv1.weight"][1], resid=dres, out_dtype=torch.float32)   # + shortcut gradient, fused
+
+    # ---- whole head ---------------------------------------------------------------------------------
+    def forward(self, params, feats):
+        """feats[i]: fp32 NHWC [N, H>>i, W>>i, dims[i]] (contiguous).  Returns (logits fp32 [N, K], ctx)."""
+        for p in params:
+            if not p.is_cuda:
+                raise _l.DcptError("dcpt_b200 has no CPU path: move the classifier head to a CUDA device")
+        pk = self._pack(params)
+        mw = torch.softmax(params[0].detach().float(), dim=0).contiguous()     # 1-D softmax of len(dims) scalars (:633)
+        ctx = {"mw": mw, "stages": [], "feats": feats}
+        z = None
+        for i, f in enumerate(feats):
+            N, H, W, Cc = f.shape
+            assert Cc == self.dims[i] and f.dtype == torch.float32 and f.is_contiguous()
+            zin = torch.empty(N * H * W, Cc, dtype=BF, device=f.device)
+            _l.check(self.lib.dcpt_mix_fwd(_p(z), _p(f), _p(mw[i:i + 1]), _p(zin), f.numel(), _stream()), "mix_fwd")
+            x, blocks = zin, []
+            for j in range(self.nb):
+                x, sv = self._block_fwd(x, (N, H, W, Cc), params, pk, f"bottleneck_layers.{i}.{j}.")
+                blocks.append(sv)
+            wname = f"downsample_layers.{i}.0.weight"
+            t = gemm(x, pk[wname][0])
+            Cn = t.shape[1]
+            y = torch.empty(N * (H // 2) * (W // 2), Cn, dtype=BF, device=f.device)
+            _l.check(self.lib.dcpt_maxpool2_relu_fwd(_p(t), _p(y), N, H // 2, W // 2, Cn, _stream()), "maxpool_fwd")
+            ctx["stages"].append((blocks, x, t, (N, H, W, Cc, Cn)))
+            z = y
+        N, H, W, Cc, Cn = ctx["stages"][-1][3]
+        shp = (N, H // 2, W // 2, Cn)
+        last = []
+        x = z
+        for j in range(self.nb):
+            x, sv = self._block_fwd(x, shp, params, pk, f"last_stage.{j}.")
+            last.append(sv)
+        HW = shp[1] * shp[2]
+        pooled = torch.empty(N, Cn, dtype=torch.float32, device=x.device)
+        logits = torch.empty(N, self.k, dtype=torch.float32, device=x.device)
+        _l.check(self.lib.dcpt_meanpool_fc_fwd(_p(x), _p(params[self.index["fc.weight"]]), _p(params[self.index["fc.bias"]]),
+                                               _p(pooled), _p(logits), N, HW, Cn, self.k, _stream()), "meanpool_fc_fwd")
+        ctx.update(last=last, shp=shp, pooled=pooled, xlast=x)
+        return logits, ctx
+
+    def backward(self, params, ctx, dlogits):
+        """Returns (dfeats list of fp32 NHWC, grads list in parameter order)."""
+        pk = self._pack(params)
+        dev = dlogits.device
+        grads = [torch.zeros_like(p, dtype=torch.float32) for p in params]
+        maxw = max(2 * d for d in self.dims)
+        scratch = torch.empty(self.lib.dcpt_conv3x3_packed_elems(maxw, maxw, 0), dtype=torch.float32, device=dev)
+        N, h, w, Cn = ctx["shp"]
+        dx = torch.empty(N * h * w, Cn, dtype=torch.float32, device=dev)
+        _l.check(self.lib.dcpt_meanpool_fc_bwd(_p(dlogits.contiguous().float()), _p(ctx["pooled"]), _p(params[self.index["fc.weight"]]),
+                                               _p(grads[self.index["fc.weight"]]), _p(grads[self.index["fc.bias"]]), _p(dx), N, h * w,
+                                               Cn, self.k, _stream()), "meanpool_fc_bwd")
+        for j in reversed(range(self.nb)):
+            dx = self._block_bwd(dx, ctx["shp"], ctx["last"][j], params, grads, pk, f"last_stage.{j}.", scratch)
+        dmw = torch.zeros(len(self.dims), dtype=torch.float32, device=dev)
+        dfeats = [None] * len(self.dims)
+        for i in reversed(range(len(self.dims))):
+            blocks, xs, t, (N, H, W, Cc, Cn) = ctx["stages"][i]
+            dt = torch.empty_like(t)
+            _l.check(self.lib.dcpt_maxpool2_relu_bwd(_p(t), _p(dx), _p(dt), N, H // 2, W // 2, Cn, _stream()), "maxpool_bwd")
+            wname = f"downsample_layers.{i}.0.weight"
+            gemm(dt, xs, a_mn=True, b_mn=True, accumulate_into=grads[self.index[wname]].view(Cn, Cc), splits=0)
+            dx = gemm(dt, pk[wname][1], out_dtype=torch.float32)
+            for j in reversed(range(self.nb)):
+                dx = self._block_bwd(dx, (N, H, W, Cc), blocks[j], params, grads, pk, f"bottleneck_layers.{i}.{j}.", scratch)
+            f = ctx["feats"][i]
+            dfeats[i] = torch.empty_like(f)
+            _l.check(self.lib.dcpt_mix_bwd(_p(dx), _p(f), _p(ctx["mw"][i:i + 1]), _p(dfeats[i]), _p(dmw[i:i + 1]), f.numel(), _stream()),
+                     "mix_bwd")
+            # dx (= d z_in) is also the gradient of the previous stage's pooled output (z = prev + mw * feat)
+        mw = ctx["mw"]
+        grads[0] = (mw * (dmw - (dmw * mw).sum())).to(grads[0].dtype)          # softmax backward on len(dims) scalars
+        return dfeats, grads
+
+
+class _DCHeadFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, n_feats, *args):
+        feats, params = args[:n_feats], args[n_feats:]
+        # features arrive as logical NCHW (channels_last memory from the NAFNet function, or plain NCHW): make NHWC fp32
+        fh = [f.detach().permute(0, 2, 3, 1).contiguous().float() for f in feats]
+        dparams = [p.detach().contiguous() for p in params]
+        logits, c = engine.forward(dparams, fh)
+        ctx.engine, ctx.c, ctx.params, ctx.n_feats = engine, c, dparams, n_feats
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        dfeats, grads = ctx.engine.backward(ctx.params, ctx.c, dlogits)
+        ctx.c = None
+        return (None, None) + tuple(d.permute(0, 3, 1, 2) for d in dfeats) + tuple(grads)
+
+
+def dchead_apply(engine, feats, params):
+    return _DCHeadFunction.apply(engine, len(feats), *feats, *params)

@@ -58,6 +58,20 @@ PROTOTYPES = {
     "dcpt_nafnet_pack": (_I, [_VP, _PP, _VP, _VP]),
     "dcpt_nafnet_fwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _I, _I, _I, _I, _VP]),
     "dcpt_nafnet_bwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _PP, _VP, _I, _I, _I, _VP]),
+    "dcpt_pack_matrix": (_I, [_VP, _VP, _I, _I, _I, _VP]),
+    "dcpt_conv3x3_packed_elems": (_SZ, [_I, _I, _I]),
+    "dcpt_conv3x3_pack": (_I, [_VP, _VP, _I, _I, _I, _VP]),
+    "dcpt_conv3x3_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "dcpt_conv3x3_wgrad": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "dcpt_ln_act_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _F, _VP]),
+    "dcpt_ln_act_bwd": (_I, [_VP] * 9 + [_I, _I, _I, _VP]),
+    "dcpt_mix_fwd": (_I, [_VP, _VP, _VP, _VP, _LL, _VP]),
+    "dcpt_mix_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _LL, _VP]),
+    "dcpt_maxpool2_relu_fwd": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "dcpt_maxpool2_relu_bwd": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "dcpt_meanpool_fc_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "dcpt_meanpool_fc_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "dcpt_add_bf16": (_I, [_VP, _VP, _VP, _LL, _VP]),
 }
 
 

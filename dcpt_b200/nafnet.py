@@ -137,8 +137,10 @@ class _NAFNetFunction(torch.autograd.Function):
     """out, feat_0..feat_{n-1} = NAFNet(inp; params).  feats are NHWC storage viewed as logical NCHW."""
 
     @staticmethod
-    def forward(ctx, engine, inp, hook, want_feats, *params):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, engine, inp, hook, want_feats, need_grad, *params):
+        # need_grad is decided by the caller: grad mode is always OFF inside Function.forward, and a forward whose
+        # activations are needed by a later backward must own its saved-activation arena (DCPT runs two forwards
+        # before one backward).
         dparams = [p.detach() for p in params]
         inp_c = inp.detach().contiguous().float()
         out, feats, saved = engine.forward(dparams, inp_c, hook=hook, want_feats=want_feats, keep_for_backward=need_grad)
@@ -161,10 +163,11 @@ class _NAFNetFunction(torch.autograd.Function):
             dfe = [None if d is None else d.permute(0, 2, 3, 1).contiguous() for d in dfeats]
         grads = eng.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
         ctx.saved = None
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None) + tuple(grads)
 
 
 def nafnet_apply(engine, inp, params, hook=False, want_feats=False):
-    res = _NAFNetFunction.apply(engine, inp, hook, want_feats, *params)
+    need_grad = torch.is_grad_enabled() and (inp.requires_grad or any(p.requires_grad for p in params))
+    res = _NAFNetFunction.apply(engine, inp, hook, want_feats, need_grad, *params)
     out = None if hook else res[0]
     return out, list(res[1:])

@@ -71,7 +71,7 @@ int dcpt_layernorm2d_bwd(const void* dn_bf16, const float* x, const float* stats
  * (nn.Conv2d(k=1) at nafnet_arch.py:87-95,105-113,133-150 seen as [pixels,Cin]x[Cout,Cin]^T).
  *   a_mn/b_mn = 1: operand stored [K, M] / [K, N] (wgrad, where K = pixels).
  *   out_f32 / out_bf16 nullable; bias[N] / resid fp32 [M,ldo] nullable; splits > 1 or accumulate = 1
- *   selects the split-K path that atomically ADDS into out_f32.
+ *   selects the split-K path that atomically ADDS into out_f32 (splits = 0: chosen to fill the SMs).
  *   impl: 0 = tcgen05/TMA (product), 1 = CUDA-core cross-check (tests only). */
 int dcpt_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, float* out_f32,
                    void* out_bf16, int ldo, const float* bias, const float* resid, int splits, int accumulate, int impl,
@@ -163,6 +163,54 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* plan, const float* const* host_param
 int dcpt_nafnet_bwd(const dcpt_nafnet_plan* plan, const float* const* host_params, const void* packed, const void* saved,
                     const float* inp, const float* dout, const float* const* host_dfeats, float* const* host_grads,
                     void* workspace, int N, int H, int W, dcpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Degradation-classifier head building blocks — basicsr/archs/degrad_classify_arch.py
+ * (PromptIR_NoImg_DC :558-641, BottleneckBlock :132-243, channels-first LayerNorm :17-44).
+ * Trunk tensors are bf16 NHWC [M = N*H*W, C]; 1x1 convs use dcpt_gemm_bf16 / dcpt_gemm_ex.
+ * ------------------------------------------------------------------------------------------ */
+
+/* fp32 [O, I] parameter -> bf16 GEMM operand ([O, I], or [I, O] when transpose != 0). */
+int dcpt_pack_matrix(const float* w, void* out_bf16, int O, int I, int transpose, dcpt_stream_t stream);
+
+/* Dense 3x3 conv, stride 1, pad 1, no bias (BottleneckBlock.conv2, :178-188) as an implicit GEMM on tcgen05.
+ * dcpt_conv3x3_pack: weight [Cout, Cin, 3, 3] -> bf16 operand; dgrad = 0: forward operand [Cout, 9*pad64(Cin)],
+ * dgrad = 1: the flipped/transposed operand [Cin, 9*pad64(Cout)] that turns dcpt_conv3x3_fwd into the data gradient
+ * (call it with x = dy and Cin/Cout swapped).  dcpt_conv3x3_packed_elems gives the operand size in elements.
+ * dcpt_conv3x3_wgrad: dweight[Cout, Cin, 3, 3] += dy^T (*) x; scratch = fp32 [Cout * 9 * pad64(Cin)]. */
+size_t dcpt_conv3x3_packed_elems(int Cout, int Cin, int dgrad);
+int dcpt_conv3x3_pack(const float* w, void* out_bf16, int Cout, int Cin, int dgrad, dcpt_stream_t stream);
+int dcpt_conv3x3_fwd(const void* x_bf16, const void* w_packed, void* out_bf16, float* out_f32, int N, int H, int W, int Cin,
+                     int Cout, dcpt_stream_t stream);
+int dcpt_conv3x3_wgrad(const void* dy_bf16, const void* x_bf16, float* scratch, float* dweight, int N, int H, int W, int Cin,
+                       int Cout, dcpt_stream_t stream);
+
+/* y = act(LN_c(x) * weight + bias (+ resid)), act = ReLU when relu != 0: `Conv2d.norm` + `F.relu_` (+ `out += shortcut`)
+ * (:98-103, :227-243; LayerNorm channels_first :39-44, eps 1e-6).  stats fp32 [M, 2] = (mean, rstd).
+ * Backward: g = dy * (y > 0); dx = LN'(g) (bf16: the next GEMM's operand), dres = g (fp32, nullable); dweight / dbias
+ * accumulated.  dy and dres are fp32: LN' cancels the per-pixel mean, which would amplify a bf16 rounding of dy. */
+int dcpt_ln_act_fwd(const void* x_bf16, const float* weight, const float* bias, const void* resid_bf16, void* y_bf16, float* stats,
+                    int M, int C, int relu, float eps, dcpt_stream_t stream);
+int dcpt_ln_act_bwd(const float* dy, const void* y_bf16, const void* x_bf16, const float* stats, const float* weight,
+                    void* dx_bf16, float* dres, float* dweight, float* dbias, int M, int C, int relu, dcpt_stream_t stream);
+
+/* z = prev + mw[0] * feat (prev nullable; feat fp32, n elements): `lq_feats + mixing_weights[i] * feature` (:637).
+ * Backward: dfeat = mw * dz (nullable), dmw[0] += sum dz * feat. */
+int dcpt_mix_fwd(const void* prev_bf16, const float* feat, const float* mw, void* z_bf16, long long n, dcpt_stream_t stream);
+int dcpt_mix_bwd(const float* dz, const float* feat, const float* mw, float* dfeat, float* dmw, long long n, dcpt_stream_t stream);
+
+/* y = relu(maxpool2x2(x)): `nn.MaxPool2d(2, 2)`, `nn.ReLU()` of downsample_layers (:596-602). x is [N, 2Ho, 2Wo, C]. */
+int dcpt_maxpool2_relu_fwd(const void* x_bf16, void* y_bf16, int N, int Ho, int Wo, int C, dcpt_stream_t stream);
+int dcpt_maxpool2_relu_bwd(const void* x_bf16, const float* dy, void* dx_bf16, int N, int Ho, int Wo, int C, dcpt_stream_t stream);
+
+/* logits = fc(mean over H,W of x): `.mean(dim=[-1, -2])` + `self.fc` (:639-640). pooled fp32 [N, C], logits fp32 [N, K]. */
+int dcpt_meanpool_fc_fwd(const void* x_bf16, const float* weight, const float* bias, float* pooled, float* logits, int N, int HW,
+                         int C, int K, dcpt_stream_t stream);
+int dcpt_meanpool_fc_bwd(const float* dlogits, const float* pooled, const float* weight, float* dweight, float* dbias, float* dx,
+                         int N, int HW, int C, int K, dcpt_stream_t stream);
+
+/* out = a + b (bf16, n elements): sums the two gradient paths of a residual block. */
+int dcpt_add_bf16(const void* a, const void* b, void* out, long long n, dcpt_stream_t stream);
 
 #ifdef __cplusplus
 }

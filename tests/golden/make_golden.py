@@ -102,6 +102,28 @@ def main():
         arrays[f"feat{i}"] = f
     npz(os.path.join(HERE, "nafnet_w8.npz"), **arrays)
 
+    # ---- degradation-classifier head (PromptIR_NoImg_DC): logits + CE-loss gradients -------------------
+    from basicsr.archs.degrad_classify_arch import PromptIR_NoImg_DC
+    torch.manual_seed(5)
+    dims = [8, 16, 32]
+    head = PromptIR_NoImg_DC(feature_dims=dims, num_res_blocks=2, num_classes=5)
+    perturb(head, 6)
+    with torch.no_grad():
+        head.mixing_weights.copy_(1.0 + 0.3 * torch.randn(3))
+    feats = [torch.randn(2, c, 32 >> i, 48 >> i).requires_grad_(True) for i, c in enumerate(dims)]
+    logits = head(None, list(feats))
+    labels = torch.tensor([1, 3])
+    loss = torch.nn.functional.cross_entropy(logits, labels)   # CrossEntropyLoss (losses/basic_loss.py:39-55)
+    loss.backward()
+    arrays = {"logits": logits, "labels": labels, "loss": loss, "dims": dims, "seed": 5}
+    for i, f in enumerate(feats):
+        arrays[f"feat{i}"] = f
+        arrays[f"dfeat{i}"] = f.grad
+    for k, p in head.named_parameters():
+        arrays["p." + k] = p
+        arrays["g." + k] = p.grad
+    npz(os.path.join(HERE, "dchead.npz"), **arrays)
+
 
 if __name__ == "__main__":
     main()

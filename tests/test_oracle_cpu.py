@@ -112,3 +112,21 @@ print("OK")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_dchead_golden(golden_dir):
+    from oracle import dchead_oracle as D
+    z = load(golden_dir, "dchead.npz")
+    dims = z["dims"].tolist()
+    sd = {k[2:]: v.clone().requires_grad_(True) for k, v in z.items() if k.startswith("p.")}
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == D.dchead_param_shapes(dims, 2, 5)
+    feats = [z[f"feat{i}"].clone().requires_grad_(True) for i in range(len(dims))]
+    logits = D.dchead_fwd(feats, sd)
+    assert rel(logits, z["logits"]) < RTOL
+    loss = torch.nn.functional.cross_entropy(logits, z["labels"])
+    assert abs(float(loss) - float(z["loss"])) < 1e-6
+    loss.backward()
+    for i, f in enumerate(feats):
+        assert rel(f.grad, z[f"dfeat{i}"]) < 1e-4, i
+    for k, v in sd.items():
+        assert rel(v.grad, z["g." + k]) < 2e-4, k
