@@ -70,6 +70,16 @@ int conv3x3_tc_launch(const Conv3x3Args& a, cudaStream_t stream);
 // G[co][tap * cin_pad + ci] += sum_px dY[px][co] * X[px + tap][ci]   (fp32, split-K over pixel patches)
 int conv3x3_wgrad_tc_launch(const bf16* dY, const bf16* X, float* G, int N, int H, int W, int Cin, int Cout, cudaStream_t stream);
 
+// Split-K factor for a wgrad-style GEMM with `tiles` output tiles and `num_kb` 64-wide k-blocks: the largest split
+// whose tile count still fits ONE wave of the persistent grid (tiles * splits <= SMs).  Rounding up instead costs a
+// whole second wave for a handful of tiles (measured: 152 tiles on 148 SMs ran 1.9x slower than 144).
+inline int gemm_auto_splits(int tiles, int num_kb) {
+  int splits = dcpt_num_sms() / (tiles > 0 ? tiles : 1);
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream);    // tcgen05 + TMA (product path)
 int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);  // CUDA-core cross-check (tests only)
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);       // dispatch (DCPT_GEMM_SIMT=1 selects simt)
@@ -96,34 +106,61 @@ __device__ __forceinline__ float4 unpack4_bf16(uint2 u) {
 // The epilogue of a 4-column piece is split into a LOAD phase (everything read from global memory) and a
 // STORE phase, so the caller can issue all loads of a chunk before the first store: the output pointers are
 // not provably distinct from the inputs, and a load placed after a store would wait for it (measured: 2x).
-struct EpiExtra {
+// The loads are further split into a per-COLUMN part (bias: the same for every row a lane handles) and a per-ROW
+// part (residual / gate operands), so the tensor-core kernel can keep the row part of the NEXT chunk in flight
+// while it finishes the current one.
+struct EpiCol {
   float4 a, b;
 };
+struct EpiRow {
+  float4 r;     // STORE / PIXSHUF: residual
+  uint2 xa, xb;  // GATE_BWD: the two x4 halves (raw bf16)
+};
+struct EpiExtra {
+  EpiCol c;
+  EpiRow r;
+};
 
-// piece = 4 consecutive columns [n, n+4) of row m (valid).  For EPI_GATE, n is the packed column `na` of the
-// a-piece (see epilogue_store); its b-piece is 8 columns further.
+// piece = 4 consecutive columns [n, n+4).  For EPI_GATE, n is the packed column `na` of the a-piece (see
+// epilogue_store); its b-piece is 8 columns further.
 template <int EPI>
-__device__ __forceinline__ EpiExtra epilogue_load(const EpiParams& p, int m, int n) {
-  EpiExtra e;
+__device__ __forceinline__ EpiCol epilogue_load_col(const EpiParams& p, int n) {
+  EpiCol e;
   e.a = e.b = make_float4(0.f, 0.f, 0.f, 0.f);
   if constexpr (EPI == EPI_STORE) {
     if (p.bias) e.a = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-    if (p.resid) e.b = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)m * p.ldr + n));
   } else if constexpr (EPI == EPI_GATE) {
     e.a = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     e.b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8));
+  }
+  return e;
+}
+template <int EPI>
+__device__ __forceinline__ EpiRow epilogue_load_row(const EpiParams& p, int m, int n) {
+  EpiRow e;
+  e.r = make_float4(0.f, 0.f, 0.f, 0.f);
+  e.xa = e.xb = make_uint2(0u, 0u);
+  if constexpr (EPI == EPI_STORE) {
+    if (p.resid) e.r = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)m * p.ldr + n));
   } else if constexpr (EPI == EPI_GATE_BWD) {
     const bf16* x4 = p.aux + (size_t)m * p.ldaux;
-    e.a = unpack4_bf16(__ldg(reinterpret_cast<const uint2*>(x4 + n)));
-    e.b = unpack4_bf16(__ldg(reinterpret_cast<const uint2*>(x4 + p.C + n)));
+    e.xa = __ldg(reinterpret_cast<const uint2*>(x4 + n));
+    e.xb = __ldg(reinterpret_cast<const uint2*>(x4 + p.C + n));
   } else if constexpr (EPI == EPI_PIXSHUF) {
     if (p.resid) {
       const int w = m % p.W, t = m / p.W, h = t % p.H, img = t / p.H;
       const int q = n / p.Cseg, c = n - q * p.Cseg;
       const size_t pix = ((size_t)img * (2 * p.H) + 2 * h + (q >> 1)) * (size_t)(2 * p.W) + 2 * w + (q & 1);
-      e.a = __ldg(reinterpret_cast<const float4*>(p.resid + pix * p.Cseg + c));
+      e.r = __ldg(reinterpret_cast<const float4*>(p.resid + pix * p.Cseg + c));
     }
   }
+  return e;
+}
+template <int EPI>
+__device__ __forceinline__ EpiExtra epilogue_load(const EpiParams& p, int m, int n) {
+  EpiExtra e;
+  e.c = epilogue_load_col<EPI>(p, n);
+  e.r = epilogue_load_row<EPI>(p, m, n);
   return e;
 }
 
@@ -131,15 +168,15 @@ __device__ __forceinline__ EpiExtra epilogue_load(const EpiParams& p, int m, int
 template <int EPI>
 __device__ __forceinline__ void epilogue_store(const EpiParams& p, int m, int n, float4 v, float4 vb, const EpiExtra& e) {
   if constexpr (EPI == EPI_STORE) {
-    v.x += e.a.x + e.b.x; v.y += e.a.y + e.b.y; v.z += e.a.z + e.b.z; v.w += e.a.w + e.b.w;
+    v.x += e.c.a.x + e.r.r.x; v.y += e.c.a.y + e.r.r.y; v.z += e.c.a.z + e.r.r.z; v.w += e.c.a.w + e.r.r.w;
     if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.ldo + n) = v;
     if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)m * p.ldo + n) = pack4_bf16(v.x, v.y, v.z, v.w);
   } else if constexpr (EPI == EPI_GATE) {
     // packed column p = 16*pp + h*8 + i  <->  channel h*C + 8*pp + i  (h = 0 first half, 1 second half);
     // (n % 16) in {0, 4}: a-piece at n, b-piece at n + 8.
     float4 a = v, b = vb;
-    a.x = bf16_round(a.x + e.a.x); a.y = bf16_round(a.y + e.a.y); a.z = bf16_round(a.z + e.a.z); a.w = bf16_round(a.w + e.a.w);
-    b.x = bf16_round(b.x + e.b.x); b.y = bf16_round(b.y + e.b.y); b.z = bf16_round(b.z + e.b.z); b.w = bf16_round(b.w + e.b.w);
+    a.x = bf16_round(a.x + e.c.a.x); a.y = bf16_round(a.y + e.c.a.y); a.z = bf16_round(a.z + e.c.a.z); a.w = bf16_round(a.w + e.c.a.w);
+    b.x = bf16_round(b.x + e.c.b.x); b.y = bf16_round(b.y + e.c.b.y); b.z = bf16_round(b.z + e.c.b.z); b.w = bf16_round(b.w + e.c.b.w);
     const int j = (n >> 4) * 8 + (n & 15);
     bf16* x4 = p.out_bf16 + (size_t)m * p.ldo;
     *reinterpret_cast<uint2*>(x4 + j) = pack4_bf16(a.x, a.y, a.z, a.w);
@@ -147,14 +184,15 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int m, int n,
     *reinterpret_cast<uint2*>(p.out2 + (size_t)m * p.ldo2 + j) = pack4_bf16(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
   } else if constexpr (EPI == EPI_GATE_BWD) {
     bf16* o = p.out_bf16 + (size_t)m * p.ldo;
-    *reinterpret_cast<uint2*>(o + n) = pack4_bf16(v.x * e.b.x, v.y * e.b.y, v.z * e.b.z, v.w * e.b.w);
-    *reinterpret_cast<uint2*>(o + p.C + n) = pack4_bf16(v.x * e.a.x, v.y * e.a.y, v.z * e.a.z, v.w * e.a.w);
+    const float4 xa = unpack4_bf16(e.r.xa), xb = unpack4_bf16(e.r.xb);
+    *reinterpret_cast<uint2*>(o + n) = pack4_bf16(v.x * xb.x, v.y * xb.y, v.z * xb.z, v.w * xb.w);
+    *reinterpret_cast<uint2*>(o + p.C + n) = pack4_bf16(v.x * xa.x, v.y * xa.y, v.z * xa.z, v.w * xa.w);
   } else if constexpr (EPI == EPI_PIXSHUF) {
     const int w = m % p.W, t = m / p.W, h = t % p.H, img = t / p.H;
     const int q = n / p.Cseg, c = n - q * p.Cseg;
     const size_t pix = ((size_t)img * (2 * p.H) + 2 * h + (q >> 1)) * (size_t)(2 * p.W) + 2 * w + (q & 1);
     const size_t off = pix * p.Cseg + c;
-    v.x += e.a.x; v.y += e.a.y; v.z += e.a.z; v.w += e.a.w;
+    v.x += e.r.r.x; v.y += e.r.r.y; v.z += e.r.r.z; v.w += e.r.r.w;
     if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = v;
     if (p.out_bf16) *reinterpret_cast<uint2*>(p.out_bf16 + off) = pack4_bf16(v.x, v.y, v.z, v.w);
   } else if constexpr (EPI == EPI_ATOMIC) {

@@ -227,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 2;
     const int q = warp & 3;
     const int chalf = ew >> 2;
-    float4* stage = reinterpret_cast<float4*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256) + ew * 256;
+    const uint32_t stage = smem_u32(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256) + (uint32_t)ew * 4096u;  // float4 index * 16
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -267,56 +267,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (m_base + r < M && n < N) prefetch_l2(ep.aux + (size_t)(m_base + r) * ep.ldaux + hf * ep.C + n);
         }
       }
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (EPI == EPI_GATE) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = chalf; c < BN / 32; c += 2) {
-        const int n0 = n_t * BN + c * 32;
-        if (n0 >= N) break;  // warp-uniform
-        float v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) stage[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        if constexpr (EPI == EPI_GATE) {
+        for (int c = chalf; c < BN / 32; c += 2) {
+          const int n0 = n_t * BN + c * 32;
+          if (n0 >= N) break;  // warp-uniform
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
           // 4 lanes per row: lane -> (group g, quarter qq) = the a-piece / b-piece pair of 4 channels
           const int pc = lane & 3, g = pc >> 1, qq = pc & 1;
           const int na = n0 + g * 16 + qq * 4;
           const int r0 = lane >> 2;
-          EpiExtra ex[4];
+          EpiExtra ex;
+          ex.c = epilogue_load_col<EPI>(ep, na < N ? na : n0);
+          ex.r = EpiRow();
+          tmem_ld_wait();
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int m = out_row(it * 8 + r0);
-            if (m >= 0 && na < N) ex[it] = epilogue_load<EPI>(ep, m, na);
-          }
+          for (int j = 0; j < 8; ++j)
+            sts_f4(stage + (uint32_t)(lane * 8 + (j ^ (lane & 7))) * 16u, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          __syncwarp();
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int r = it * 8 + r0;
-            const float4 a = stage[r * 8 + ((g * 4 + qq) ^ (r & 7))];
-            const float4 b = stage[r * 8 + ((g * 4 + 2 + qq) ^ (r & 7))];
+            const float4 a = lds_f4(stage + (uint32_t)(r * 8 + ((g * 4 + qq) ^ (r & 7))) * 16u);
+            const float4 b = lds_f4(stage + (uint32_t)(r * 8 + ((g * 4 + 2 + qq) ^ (r & 7))) * 16u);
             const int m = out_row(r);
-            if (m >= 0 && na < N) epilogue_store<EPI>(ep, m, na, a, b, ex[it]);
+            if (m >= 0 && na < N) epilogue_store<EPI>(ep, m, na, a, b, ex);
           }
-        } else {
-          const int cc = lane & 7, r0 = lane >> 3;
-          const int n = n0 + cc * 4;
-          EpiExtra ex[8];
+          __syncwarp();
+        }
+      } else {
+        // a lane owns 4 consecutive columns (cc) of rows r0, r0 + 4, ...: 8 lanes cover 128 contiguous bytes.
+        // The per-row global inputs (residual / gate operands) of the NEXT chunk are requested before the current
+        // chunk is finished, and those of the first chunk before the accumulator is even ready: their latency
+        // (the longest in the epilogue) is hidden behind the TMEM load, the transpose and the stores.
+        const int cc = lane & 7, r0 = lane >> 3;
+        constexpr bool kRowLoads = (EPI == EPI_STORE || EPI == EPI_GATE_BWD || EPI == EPI_PIXSHUF);
+        EpiRow cur[8];
+        auto load_rows = [&](int c, EpiRow (&rw)[8]) {
+          const int n = n_t * BN + c * 32 + cc * 4;
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int m = out_row(it * 4 + r0);
-            if (m >= 0 && n < N) ex[it] = epilogue_load<EPI>(ep, m, n);
+            if (m >= 0 && n < N) rw[it] = epilogue_load_row<EPI>(ep, m, n);
+            else rw[it] = EpiRow();
+          }
+        };
+        if constexpr (kRowLoads) load_rows(chalf, cur);
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = chalf; c < BN / 32; c += 2) {
+          const int n0 = n_t * BN + c * 32;
+          if (n0 >= N) break;  // warp-uniform
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          const int n = n0 + cc * 4;
+          EpiExtra ex;
+          ex.c = epilogue_load_col<EPI>(ep, n < N ? n : n0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts_f4(stage + (uint32_t)(lane * 8 + (j ^ (lane & 7))) * 16u, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          __syncwarp();
+          EpiRow nxt[8];
+          if constexpr (kRowLoads) {
+            if (c + 2 < BN / 32) load_rows(c + 2, nxt);
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + r0;
-            const float4 x = stage[r * 8 + (cc ^ (r & 7))];
+            const float4 x = lds_f4(stage + (uint32_t)(r * 8 + (cc ^ (r & 7))) * 16u);
             const int m = out_row(r);
-            if (m >= 0 && n < N) epilogue_store<EPI>(ep, m, n, x, x, ex[it]);
+            ex.r = cur[it];
+            if (m >= 0 && n < N) epilogue_store<EPI>(ep, m, n, x, x, ex);
+          }
+          __syncwarp();
+          if constexpr (kRowLoads) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) cur[it] = nxt[it];
           }
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -490,9 +524,7 @@ int conv_wgrad_cfg(const bf16* dY, const bf16* X, float* G, int N, int H, int W,
   DCPT_TRY(make_tmap_nhwc(&tmA, dY, N, H, W, Cout, 1 << cg.tw_log2, cg.th, 1));
   DCPT_TRY(make_tmap_nhwc(&tmB, X, N, H, W, Cin, 1 << cg.tw_log2, cg.th, 1));
   const int tiles_m = ceil_div(Cout, BM), tiles_n = 9 * cin_pad / BN, num_kb = N * cg.tiles_h * cg.tiles_w;
-  int splits = ceil_div(dcpt_num_sms(), tiles_m * tiles_n);
-  if (splits > num_kb) splits = num_kb;
-  if (splits < 1) splits = 1;
+  int splits = gemm_auto_splits(tiles_m * tiles_n, num_kb);
   const int kbps = ceil_div(num_kb, splits);
   splits = ceil_div(num_kb, kbps);
   const int total = tiles_m * tiles_n * splits;

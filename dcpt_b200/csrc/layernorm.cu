@@ -72,9 +72,11 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   }
 }
 
-// NV <= 2: 16-warp blocks (few, fat blocks -> few partial-sum flushes); NV >= 4 needs > 128 registers -> 8 warps.
-template <int NV, int kBwdWarps>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+// NV <= 2: 16-warp blocks (few, fat blocks -> few partial-sum flushes).  NV >= 4 keeps 3 * NV float4 column
+// accumulators per lane: 4-warp blocks capped at 128 registers so that 4 of them (16 warps) share an SM - with one
+// 8-warp block per SM the kernel had too few bytes in flight (2.7 TB/s at C = 512).
+template <int NV, int kBwdWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
 ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ stats,
               const float* __restrict__ w, const float* __restrict__ dres, float* __restrict__ dx, bf16* __restrict__ dx_bf16,
               float* __restrict__ dw, float* __restrict__ db, float* __restrict__ colsum, int M, int C, int lpr) {
@@ -217,19 +219,19 @@ int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const floa
   DCPT_CHECK_ARG(M > 0 && C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "layernorm bwd: need C %% 8 == 0 and 8 <= C <= 1024 (C=%d)", C);
   const int lpr = pick_lpr(C);
   const int nv = ceil_div(C / 4, lpr);
-  const int warps = nv <= 2 ? 16 : 8;
+  const int warps = nv <= 2 ? 16 : 4;
   const int rows_per_block = warps * (32 / lpr);
   long long grid = ceil_div_ll(M, rows_per_block);
-  const long long cap = (long long)dcpt_num_sms() * (nv <= 1 ? 2 : 1);  // register-limited to 1 block / SM beyond NV = 1
+  const long long cap = (long long)dcpt_num_sms() * (nv <= 1 ? 2 : (nv <= 2 ? 1 : (nv <= 4 ? 4 : 2)));  // resident blocks / SM
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)3 * C * sizeof(float);
   DCPT_PROF("ln_bwd", 20.0 * M * C, (2.0 + 4.0 + (dres ? 4.0 : 0.0) + 4.0 + (dx_bf16 ? 2.0 : 0.0)) * M * C, st);
-#define LN_BWD(NVV, WW) \
-  ln_bwd_kernel<NVV, WW><<<(int)grid, WW * 32, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr)
-  if (nv <= 1) LN_BWD(1, 16);
-  else if (nv <= 2) LN_BWD(2, 16);
-  else if (nv <= 4) LN_BWD(4, 8);
-  else LN_BWD(8, 8);
+#define LN_BWD(NVV, WW, MB) \
+  ln_bwd_kernel<NVV, WW, MB><<<(int)grid, WW * 32, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr)
+  if (nv <= 1) LN_BWD(1, 16, 2);
+  else if (nv <= 2) LN_BWD(2, 16, 1);
+  else if (nv <= 4) LN_BWD(4, 4, 4);
+  else LN_BWD(8, 4, 2);
 #undef LN_BWD
   DCPT_LAUNCH_CHECK();
   return 0;

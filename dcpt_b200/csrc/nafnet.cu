@@ -141,10 +141,7 @@ int wgrad_gemm(const bf16* dY, int O, const bf16* X, int I, float* out, int Mpx,
   const int bn = I > 128 ? 256 : (I > 64 ? 128 : 64);
   const int tiles = ceil_div(O, 128) * ceil_div(I, bn);
   const int num_kb = ceil_div(Mpx, 64);
-  int splits = ceil_div(dcpt_num_sms(), tiles);
-  if (splits > num_kb) splits = num_kb;
-  if (splits < 1) splits = 1;
-  g.splits = splits;
+  g.splits = gemm_auto_splits(tiles, num_kb);
   g.ep.out_f32 = out; g.ep.ldo = I;
   return gemm_launch(g, st);
 }
@@ -505,7 +502,7 @@ int dcpt_gemm_ex(const dcpt_gemm_desc* d, int impl, dcpt_stream_t stream) {
   if (d->splits == 0 && d->epilogue == EPI_ATOMIC) {  // auto split-K: fill the machine
     const int bn = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
     const int tiles = ceil_div(d->M, 128) * ceil_div(d->N, bn);
-    g.splits = ceil_div(dcpt_num_sms(), tiles);
+    g.splits = gemm_auto_splits(tiles, ceil_div(d->K, 64));
   }
   g.ep.out_f32 = d->out_f32; g.ep.out_bf16 = static_cast<bf16*>(d->out_bf16); g.ep.ldo = d->ldo;
   g.ep.bias = d->bias; g.ep.resid = d->resid; g.ep.ldr = d->ldr;
