@@ -1,0 +1,87 @@
+"""Pin oracle/restormer_oracle.py to the reference: against the committed golden vectors (outputs of the real
+reference, tests/golden/make_golden_restormer.py) and against the live reference when /root/reference exists.
+fp32 CPU, same ATen kernels, different op grouping -> 3e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restormer_oracle as RO
+
+RTOL = 3e-5
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    return {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+
+
+@pytest.mark.parametrize("dim", [48, 96, 32])
+def test_transformer_block_golden(golden_dir, dim):
+    z = load(golden_dir, f"restormer_block_d{dim}.npz")
+    sd = {"blk." + k[2:]: v.clone().requires_grad_(True) for k, v in z.items() if k.startswith("p.")}
+    x = z["x"].clone().requires_grad_(True)
+    y = RO.transformer_block(x, sd, "blk", int(z["heads"]))
+    assert rel(y, z["y"]) < RTOL
+    y.backward(z["dy"])
+    assert rel(x.grad, z["dx"]) < RTOL
+    for k, v in sd.items():
+        assert rel(v.grad, z["g." + k[4:]]) < 1e-4, k
+
+
+def test_restormer_tiny_golden(golden_dir):
+    z = load(golden_dir, "restormer_tiny.npz")
+    cfg = dict(dim=int(z["cfg_dim"]), num_blocks=z["cfg_blocks"].tolist(), num_refinement_blocks=int(z["cfg_refine"]),
+               heads=z["cfg_heads"].tolist())
+    sd = {k: v.requires_grad_(True) for k, v in RO.random_restormer_state_dict(seed=int(z["seed"]), **cfg).items()}
+    out, feats = RO.restormer_fwd(z["inp"], sd, cfg["num_blocks"], cfg["num_refinement_blocks"], cfg["heads"], return_feats=True)
+    assert rel(out, z["out"]) < RTOL
+    for i, f in enumerate(feats):
+        assert rel(f, z[f"feat{i}"]) < RTOL
+    loss = (out - z["gt"]).abs().mean()
+    assert abs(float(loss) - float(z["loss"])) < 1e-6
+    loss.backward()
+    for k, v in sd.items():
+        assert rel(v.grad, z["g." + k]) < 2e-4, k
+    assert RO.restormer_fwd(z["inp"], sd, cfg["num_blocks"], cfg["num_refinement_blocks"], cfg["heads"], hook=True) is None
+
+
+def test_restormer_shapes_default():
+    shapes = RO.restormer_param_shapes()
+    assert len(shapes) == 406 and sum(int(np.prod(s)) for s in shapes.values()) == 26111668  # SURVEY.md §5 / §8(a9) [probe]
+    assert shapes["encoder_level1.body.0.ffn.project_in.weight"] == (254, 48, 1, 1)
+    assert shapes["reduce_chan_level3.weight"] == (192, 384, 1, 1)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/basicsr"), reason="reference not present")
+def test_restormer_live_reference():
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from oracle._ref_import import import_reference
+from oracle import restormer_oracle as RO
+import_reference()
+from basicsr.archs.restormer_arch import Restormer
+cfg = dict(dim=24, num_blocks=[1, 1, 1, 2], num_refinement_blocks=2, heads=[1, 2, 4, 8], LayerNorm_type="WithBias", bias=True)
+net = Restormer(**cfg)
+sd = RO.random_restormer_state_dict(seed=3, **cfg)
+net.load_state_dict(sd, strict=True)
+x = torch.rand(1, 3, 16, 24)
+with torch.no_grad():
+    a = net(x)
+    b = RO.restormer_fwd(x, sd, cfg["num_blocks"], cfg["num_refinement_blocks"], cfg["heads"])
+print("REL", float((a - b).norm() / b.norm()))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    v = float(r.stdout.strip().split("REL")[-1])
+    assert v < RTOL, v
