@@ -123,7 +123,7 @@ conv3x3_feat_to_img_kernel(const float* __restrict__ feat, const float* __restri
     if (lane < 3) {
       const float a = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
       const size_t o = ((size_t)n * 3 + lane) * HW + rem;
-      out[o] = a + bias[lane] + (resid ? resid[o] : 0.f);
+      out[o] = a + (bias ? bias[lane] : 0.f) + (resid ? resid[o] : 0.f);
     }
   }
 }

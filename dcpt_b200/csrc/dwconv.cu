@@ -62,6 +62,9 @@ struct Tiles {
 };
 
 // ------------------------------- forward --------------------------------------
+// GELU = 0: SimpleGate a * b (NAFBlock).  GELU = 1: gelu(a) * b with the exact erf GELU (Restormer GDFN,
+// restormer_arch.py:97-98; its dw conv has no bias and nothing is pooled: b2 == pool == nullptr).
+template <int GELU>
 __global__ void __launch_bounds__(NWARP * 32)
 dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restrict__ w2, const float* __restrict__ b2,
                   bf16* __restrict__ g, float* __restrict__ pool, int N, int H, int W, int C) {
@@ -76,7 +79,9 @@ dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restri
   float2 wa[9], wb[9];
   load_taps(wa, w2, ca);
   load_taps(wb, w2, cb);
-  const float2 ba = make_float2(__ldg(b2 + ca), __ldg(b2 + ca + 1)), bb = make_float2(__ldg(b2 + cb), __ldg(b2 + cb + 1));
+  const float2 zero2 = make_float2(0.f, 0.f);
+  const float2 ba = b2 ? make_float2(__ldg(b2 + ca), __ldg(b2 + ca + 1)) : zero2;
+  const float2 bb = b2 ? make_float2(__ldg(b2 + cb), __ldg(b2 + cb + 1)) : zero2;
   const Tiles T(N, H, W);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmU);
@@ -118,7 +123,7 @@ dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restri
     int n, h0, w0;
     T.decode(t, n, h0, w0);
     if (n != cur_n) {
-      if (cur_n >= 0) flush_pool(cur_n);
+      if (pool && cur_n >= 0) flush_pool(cur_n);
       cur_n = n;
     }
     mbar_wait(&full[s], (it >> 1) & 1);
@@ -145,6 +150,10 @@ dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restri
           }
         const int ox = x - 2;
         if (chan_ok && h < H && w0 + ox < W) {
+          if constexpr (GELU) {
+            a.x = 0.5f * a.x * (1.f + erff(a.x * 0.70710678118654752f));
+            a.y = 0.5f * a.y * (1.f + erff(a.y * 0.70710678118654752f));
+          }
           const float2 gv = round_bf2(make_float2(a.x * b.x, a.y * b.y));
           st_bf2(grow + (size_t)ox * C, gv);
           psum.x += gv.x;
@@ -154,7 +163,97 @@ dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restri
     }
     __syncthreads();  // stage s may be refilled by the next-but-one issue
   }
-  if (cur_n >= 0) flush_pool(cur_n);
+  if (pool && cur_n >= 0) flush_pool(cur_n);
+}
+
+// ------------------- plain depthwise 3x3 forward (+ row norms) ------------------
+// out[px][c] = sum_{ky,kx} x[h+ky-1, w+kx-1][c] * w[c][ky][kx]   (no bias: Restormer qkv_dwconv, restormer_arch.py:110-118)
+// sumsq[n][c] += sum_px out^2 for c < sq_ch: the squared L2 norms over all pixels that MDTA's F.normalize needs
+// (restormer_arch.py:131-132), taken from the bf16-rounded values the attention GEMMs will read.
+__global__ void __launch_bounds__(NWARP * 32)
+dwconv3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w, bf16* __restrict__ out,
+                   float* __restrict__ sumsq, int sq_ch, int N, int H, int W, int CH) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  __shared__ uint64_t full[2];
+  __shared__ float2 s_sq[NWARP][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = blockIdx.y, c2 = cg * 64 + lane * 2;
+  const bool chan_ok = c2 < CH;
+  const int c0 = chan_ok ? c2 : 0;
+  const bool want_sq = sumsq != nullptr && cg * 64 < sq_ch;  // CTA-uniform
+  float2 wt[9];
+  load_taps(wt, w, c0);
+  const Tiles T(N, H, W);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t, int s) {
+    int n, h0, w0;
+    T.decode(t, n, h0, w0);
+    mbar_arrive_expect_tx(&full[s], BOX_BYTES);
+    tma_load_4d(smem + (size_t)s * BOX_BYTES, &tmX, &full[s], cg * 64, w0 - 1, h0 - 1, n);
+  };
+  if (threadIdx.x == 0 && T.t0 < T.t1) issue(T.t0, 0);
+  float2 sq = make_float2(0.f, 0.f);
+  int cur_n = -1;
+  auto flush_sq = [&](int n) {  // CTA-uniform
+    s_sq[warp][lane] = sq;
+    __syncthreads();
+    if (warp == 0 && chan_ok) {
+      float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < NWARP; ++k) {
+        t.x += s_sq[k][lane].x;
+        t.y += s_sq[k][lane].y;
+      }
+      if (c2 < sq_ch) atomicAdd(sumsq + (size_t)n * sq_ch + c2, t.x);
+      if (c2 + 1 < sq_ch) atomicAdd(sumsq + (size_t)n * sq_ch + c2 + 1, t.y);
+    }
+    __syncthreads();
+    sq = make_float2(0.f, 0.f);
+  };
+  int it = 0;
+  for (int t = T.t0; t < T.t1; ++t, ++it) {
+    const int s = it & 1;
+    if (threadIdx.x == 0 && t + 1 < T.t1) issue(t + 1, s ^ 1);
+    int n, h0, w0;
+    T.decode(t, n, h0, w0);
+    if (n != cur_n) {
+      if (want_sq && cur_n >= 0) flush_sq(cur_n);
+      cur_n = n;
+    }
+    mbar_wait(&full[s], (it >> 1) & 1);
+    const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * BOX_BYTES) + lane * 2;
+    const int h = h0 + warp;
+    bf16* orow = out + (((size_t)n * H + h) * W + w0) * CH + c0;
+    float2 A[3][3];
+#pragma unroll
+    for (int x = 0; x < HWD; ++x) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) A[r][x % 3] = lds_bf2(sA + ((warp + r) * HWD + x) * 64);
+      if (x >= 2) {
+        const int ox = x - 2;
+        float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) fma2(a, A[r][(x - 2 + d) % 3], wt[r * 3 + d]);
+        if (chan_ok && h < H && w0 + ox < W) {
+          a = round_bf2(a);
+          st_bf2(orow + (size_t)ox * CH, a);
+          sq.x = fmaf(a.x, a.x, sq.x);
+          sq.y = fmaf(a.y, a.y, sq.y);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (want_sq && cur_n >= 0) flush_sq(cur_n);
 }
 
 // --------------------------- backward, part a ---------------------------------
@@ -387,9 +486,34 @@ int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, 
   CUtensorMap tmU;
   DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
   const size_t smem = 128 + (size_t)2 * 2 * BOX_BYTES;
-  DCPT_TRY(set_smem(dwgate_fwd_kernel, smem));
+  DCPT_TRY(set_smem(dwgate_fwd_kernel<0>, smem));
   DCPT_PROF("dwgate_fwd", 38.0 * N * H * W * C, 6.0 * N * H * W * C, st);
-  dwgate_fwd_kernel<<<pick_grid(N, H, W, C, 2), NWARP * 32, smem, st>>>(tmU, w2, b2, g, pool, N, H, W, C);
+  dwgate_fwd_kernel<0><<<pick_grid(N, H, W, C, 2), NWARP * 32, smem, st>>>(tmU, w2, b2, g, pool, N, H, W, C);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int dwgelu_fwd_launch(const bf16* u, const float* w2, bf16* g, int N, int H, int W, int C, cudaStream_t st) {
+  DCPT_CHECK_ARG(C % 8 == 0 && C >= 8 && N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "dwgelu_fwd: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  CUtensorMap tmU;
+  DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
+  const size_t smem = 128 + (size_t)2 * 2 * BOX_BYTES;
+  DCPT_TRY(set_smem(dwgate_fwd_kernel<1>, smem));
+  DCPT_PROF("dwgelu_fwd", 60.0 * N * H * W * C, 6.0 * N * H * W * C, st);
+  dwgate_fwd_kernel<1><<<pick_grid(N, H, W, C, 2), NWARP * 32, smem, st>>>(tmU, w2, nullptr, g, nullptr, N, H, W, C);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int dwconv3_fwd_launch(const bf16* x, const float* w, bf16* out, float* sumsq, int sq_ch, int N, int H, int W, int CH,
+                       cudaStream_t st) {
+  DCPT_CHECK_ARG(CH % 8 == 0 && CH >= 8 && N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "dwconv3_fwd: bad shape N=%d H=%d W=%d CH=%d", N, H, W, CH);
+  CUtensorMap tmX;
+  DCPT_TRY(make_tmap_nhwc(&tmX, x, N, H, W, CH, HWD, HH));
+  const size_t smem = 128 + (size_t)2 * BOX_BYTES;
+  DCPT_TRY(set_smem(dwconv3_fwd_kernel, smem));
+  DCPT_PROF("dwconv3_fwd", 20.0 * N * H * W * CH, 4.0 * N * H * W * CH, st);
+  dwconv3_fwd_kernel<<<pick_grid(N, H, W, CH, 4), NWARP * 32, smem, st>>>(tmX, w, out, sumsq, sq_ch, N, H, W, CH);
   DCPT_LAUNCH_CHECK();
   return 0;
 }

@@ -5,9 +5,10 @@
 #pragma once
 #include "common.cuh"
 
-// LayerNorm2d over channels (reference: nafnet_arch.py:25-64).
+// LayerNorm2d over channels (reference: nafnet_arch.py:25-64).  b and stats are nullable; center = 0 is Restormer's
+// BiasFree_LayerNorm (restormer_arch.py:38-40: x / sqrt(var + eps) * w with the variance taken about the mean).
 int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, float* stats, int M, int C, float eps,
-                  cudaStream_t st);
+                  cudaStream_t st, int center = 1);
 // dx = dres + LNbwd(dn); also dx mirror in bf16, sum_m dn*yhat -> dw, sum_m dn -> db, sum_m dx -> colsum (all +=).
 int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const float* w, const float* dres, float* dx,
                   bf16* dx_bf16, float* dw, float* db, float* colsum, int M, int C, cudaStream_t st);
@@ -15,6 +16,11 @@ int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const floa
 // depthwise 3x3 (+bias, zero pad) on 2C channels followed by SimpleGate; pool[n,c] += sum_px g.
 int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, float* pool, int N, int H, int W, int C,
                       cudaStream_t st);
+// Restormer GDFN gate (restormer_arch.py:97-98): g = gelu(dw3x3(u)[:, :C]) * dw3x3(u)[:, C:], no bias; w2 is [2C][9].
+int dwgelu_fwd_launch(const bf16* u, const float* w2, bf16* g, int N, int H, int W, int C, cudaStream_t st);
+// plain depthwise 3x3 (no bias) on CH channels; sumsq[n][c] += sum_px out^2 for c < sq_ch (nullable).
+int dwconv3_fwd_launch(const bf16* x, const float* w, bf16* out, float* sumsq, int sq_ch, int N, int H, int W, int CH,
+                       cudaStream_t st);
 // backward part a: dg = dgs*s + t; du2 = SimpleGate'(dg); dW2 += du2 (*) u; db2 += sum du2.
 int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const bf16* u, const float* w2, const float* b2,
                         bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st);

@@ -80,6 +80,12 @@ inline int gemm_auto_splits(int tiles, int num_kb) {
   return splits;
 }
 
+inline GemmArgs make_gemm_args(int M, int N, int K, const bf16* A, int lda, const bf16* B, int ldb, int epi) {
+  GemmArgs g = {};
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.splits = 1; g.epi = epi;
+  return g;
+}
+
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream);    // tcgen05 + TMA (product path)
 int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream);  // CUDA-core cross-check (tests only)
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);       // dispatch (DCPT_GEMM_SIMT=1 selects simt)

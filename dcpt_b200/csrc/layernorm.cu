@@ -19,7 +19,7 @@ __device__ __forceinline__ float group_sum(float v, int lpr) {
 template <int NV>
 __global__ void __launch_bounds__(kWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
-              float* __restrict__ stats, int M, int C, int lpr, float eps) {
+              float* __restrict__ stats, int M, int C, int lpr, float eps, int center) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rpw = 32 / lpr;  // rows per warp
   const int sub = lane % lpr, gr = lane / lpr;
@@ -49,17 +49,19 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
     }
     const float var = group_sum(sq, lpr) * invC;
     const float rstd = 1.f / sqrtf(var + eps);
+    // center == 0: Restormer's BiasFree_LayerNorm (restormer_arch.py:38-40) - variance about the mean, numerator NOT centred
+    const float shift = center ? mean : 0.f;
     if (valid) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int v = sub + i * lpr;
         if (v < nvec) {
           const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + v);
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(b) + v);
-          const float o0 = (xv[i].x - mean) * rstd * wv.x + bv.x;
-          const float o1 = (xv[i].y - mean) * rstd * wv.y + bv.y;
-          const float o2 = (xv[i].z - mean) * rstd * wv.z + bv.z;
-          const float o3 = (xv[i].w - mean) * rstd * wv.w + bv.w;
+          const float4 bv = b ? __ldg(reinterpret_cast<const float4*>(b) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float o0 = (xv[i].x - shift) * rstd * wv.x + bv.x;
+          const float o1 = (xv[i].y - shift) * rstd * wv.y + bv.y;
+          const float o2 = (xv[i].z - shift) * rstd * wv.z + bv.z;
+          const float o3 = (xv[i].w - shift) * rstd * wv.w + bv.w;
           __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
           uint2 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&p0);
@@ -67,7 +69,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
           *(reinterpret_cast<uint2*>(out + row * C) + v) = pk;
         }
       }
-      if (sub == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
+      if (stats && sub == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
     }
   }
 }
@@ -196,7 +198,7 @@ inline int pick_lpr(int C) {
 }  // namespace
 
 int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, float* stats, int M, int C, float eps,
-                  cudaStream_t st) {
+                  cudaStream_t st, int center) {
   DCPT_CHECK_ARG(M > 0 && C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "layernorm: need C %% 8 == 0 and 8 <= C <= 1024 (C=%d M=%d)",
                  C, M);
   const int lpr = pick_lpr(C);
@@ -204,7 +206,7 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
   const int rows_per_block = kWarps * (32 / lpr);
   const int grid = (int)ceil_div_ll(M, rows_per_block);
   DCPT_PROF("ln_fwd", 8.0 * M * C, 6.0 * M * C, st);
-#define LN_FWD(NVV) ln_fwd_kernel<NVV><<<grid, kWarps * 32, 0, st>>>(x, w, b, n_out, stats, M, C, lpr, eps)
+#define LN_FWD(NVV) ln_fwd_kernel<NVV><<<grid, kWarps * 32, 0, st>>>(x, w, b, n_out, stats, M, C, lpr, eps, center)
   if (nv <= 1) LN_FWD(1);
   else if (nv <= 2) LN_FWD(2);
   else if (nv <= 4) LN_FWD(4);

@@ -1,0 +1,506 @@
+// Restormer forward on sm_100a (reference: basicsr/archs/restormer_arch.py:103-159 MDTA / GDFN / TransformerBlock,
+// :175-202 Down/Upsample, :376-422 Restormer.forward).  Inference path of BASELINE.json configs[2].
+//
+// Layout as for NAFNet: NHWC rows [M = N*H*W, C]; fp32 residual stream, bf16 branch tensors, fp32 accumulation.
+// TransformerBlock = 11 launches (+2 per image for the attention contractions):
+//   LN -> [GEMM qkv d->3d] -> dw3x3 (+ sum q^2, sum k^2 per image/channel)
+//      -> per image: [GEMM  G = q^T k, contraction over ALL pixels, split-K, tcgen05]           (restormer_arch.py:134)
+//      -> attn = relu(temperature * G / (|q_i| |k_j|)) per head, folded into the output projection:
+//         W_eff[n] = W_out * blockdiag_h(attn[n, h])      (a d x d matrix per image)                 (:131-144)
+//      -> per image: [GEMM  x2 = x + v * W_eff[n]^T]
+//   LN -> [GEMM project_in d->2*hid] -> dw3x3 + gelu gate -> [GEMM project_out hid->d, + x2]        (:95-99)
+// L2-normalising q and k (F.normalize over the pixel axis) commutes with the contraction, so one pass over the
+// pixels yields the Gram matrix and both norms; attn @ v followed by project_out is a per-image linear map of v.
+// hidden = int(2.66 d) is odd-sized (127/255/510/1021): padded to a multiple of 8 with zero weights in the packed
+// operand cache, never in the state_dict.
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/dcpt_ops.h"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+namespace {
+
+struct Arena {
+  char* base;
+  size_t off;
+  explicit Arena(void* b) : base(static_cast<char*>(b)), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+  size_t size() const { return (off + 255) & ~(size_t)255; }
+};
+
+// ------------------------------------ kernels ------------------------------------
+// rows of a [2*hid, I] parameter (two halves x1 | x2) -> [2*hidp, I] with each half zero-padded to hidp rows
+template <typename T>
+__global__ void pack_halves_kernel(const float* __restrict__ w, T* __restrict__ out, int hid, int hidp, int I) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)2 * hidp * I) return;
+  const int r = (int)(idx / I), i = (int)(idx % I);
+  const int half = r / hidp, rr = r % hidp;
+  const float v = rr < hid ? w[((size_t)half * hid + rr) * I + i] : 0.f;
+  out[idx] = static_cast<T>(v);
+}
+// [O, hid] -> bf16 [O, hidp] (zero-padded columns)
+__global__ void pack_cols_kernel(const float* __restrict__ w, bf16* __restrict__ out, int O, int hid, int hidp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)O * hidp) return;
+  const int o = (int)(idx / hidp), c = (int)(idx % hidp);
+  out[idx] = __float2bfloat16_rn(c < hid ? w[(size_t)o * hid + c] : 0.f);
+}
+
+// W_eff[n][o][h*c + j] = sum_i Wout[o][h*c + i] * relu(temp[h] * G[n][h*c+i][h*c+j] / (max(|q_i|, eps) * max(|k_j|, eps)))
+// block = (head, image); the c x c attention tile lives in shared memory.
+__global__ void __launch_bounds__(256)
+mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, const float* __restrict__ temp,
+                 const float* __restrict__ wout, bf16* __restrict__ weff, int d, int heads) {
+  extern __shared__ float s_attn[];  // [c][c + 1]
+  const int c = d / heads, h = blockIdx.x, n = blockIdx.y;
+  const float* Gn = G + (size_t)n * d * d;
+  const float* sqn = sq + (size_t)n * 2 * d;
+  const float t = __ldg(temp + h);
+  for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
+    const int i = idx / c, j = idx - i * c;
+    const float nq = fmaxf(sqrtf(sqn[h * c + i]), 1e-12f), nk = fmaxf(sqrtf(sqn[d + h * c + j]), 1e-12f);  // F.normalize eps
+    const float a = Gn[(size_t)(h * c + i) * d + h * c + j] / (nq * nk) * t;
+    s_attn[i * (c + 1) + j] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  bf16* out = weff + (size_t)n * d * d;
+  for (int idx = threadIdx.x; idx < d * c; idx += blockDim.x) {
+    const int o = idx / c, j = idx - o * c;
+    const float* wr = wout + (size_t)o * d + h * c;
+    float acc = 0.f;
+    for (int i = 0; i < c; ++i) acc = fmaf(__ldg(wr + i), s_attn[i * (c + 1) + j], acc);
+    out[(size_t)o * d + h * c + j] = __float2bfloat16_rn(acc);
+  }
+}
+
+// PixelUnshuffle(2) in NHWC: in [N, H, W, Cc] -> out [N, H/2, W/2, 4*Cc], out channel = c*4 + i*2 + j  (restormer_arch.py:186)
+__global__ void pixel_unshuffle_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int H, int W, int Cc) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C4 = 4 * Cc;
+  const int co = (int)(idx % C4);
+  const long long px = idx / C4;
+  const int W2 = W >> 1, H2 = H >> 1;
+  const int w2 = (int)(px % W2);
+  const long long t = px / W2;
+  const int h2 = (int)(t % H2), n = (int)(t / H2);
+  const int c = co >> 2, i = (co >> 1) & 1, j = co & 1;
+  out[idx] = __ldg(in + (((size_t)n * H + 2 * h2 + i) * W + 2 * w2 + j) * Cc + c);
+}
+
+// PixelShuffle(2) + channel concat in NHWC (restormer_arch.py:200, :389, :394, :399):
+//   out[n, 2h+i, 2w+j, 0:Cs]    = conv[n, h, w, c*4 + i*2 + j]      (conv has 4*Cs channels)
+//   out[n, 2h+i, 2w+j, Cs:2*Cs] = skip[n, 2h+i, 2w+j, :]
+__global__ void pixel_shuffle_cat_kernel(const float* __restrict__ conv, const float* __restrict__ skip, float* __restrict__ out_f32,
+                                         bf16* __restrict__ out_bf16, long long total, int h, int w, int Cs) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C2 = 2 * Cs;
+  const int co = (int)(idx % C2);
+  const long long px = idx / C2;
+  const int W2 = 2 * w, H2 = 2 * h;
+  const int x = (int)(px % W2);
+  const long long t = px / W2;
+  const int y = (int)(t % H2), n = (int)(t / H2);
+  float v;
+  if (co < Cs) v = __ldg(conv + (((size_t)n * h + (y >> 1)) * w + (x >> 1)) * (4 * Cs) + co * 4 + (y & 1) * 2 + (x & 1));
+  else v = __ldg(skip + (size_t)px * Cs + (co - Cs));
+  if (out_f32) out_f32[idx] = v;
+  if (out_bf16) out_bf16[idx] = __float2bfloat16_rn(v);
+}
+
+inline unsigned blocks_for(long long total, int threads = 256) { return (unsigned)((total + threads - 1) / threads); }
+
+}  // namespace
+
+// ------------------------------------ plan ------------------------------------
+struct dcpt_restormer_plan {
+  int inp_ch, out_ch, dim, nref, bias, ln_bias;
+  int nb[4], heads[4];
+  double ffn;
+  struct ParamInfo { int dims[4]; long long numel; };
+  std::vector<ParamInfo> params;
+  struct Blk { int pidx, d, heads, hid, hidp; };
+  std::vector<Blk> stage[8];  // enc1, enc2, enc3, latent, dec3, dec2, dec1, refinement
+  int p_embed, p_down[3], p_up[3], p_reduce[2], p_out;
+};
+
+namespace {
+
+enum { ST_ENC1 = 0, ST_ENC2, ST_ENC3, ST_LAT, ST_DEC3, ST_DEC2, ST_DEC1, ST_REF };
+
+int add_param(dcpt_restormer_plan* p, int d0, int d1 = 1, int d2 = 1, int d3 = 1) {
+  dcpt_restormer_plan::ParamInfo pi;
+  pi.dims[0] = d0; pi.dims[1] = d1; pi.dims[2] = d2; pi.dims[3] = d3;
+  pi.numel = (long long)d0 * d1 * d2 * d3;
+  p->params.push_back(pi);
+  return (int)p->params.size() - 1;
+}
+
+// named_parameters() order of TransformerBlock (restormer_arch.py:148-154): norm1, attn{temperature, qkv, qkv_dwconv,
+// project_out}, norm2, ffn{project_in, dwconv, project_out}; the block's convs never carry a bias (:109-119, :81-93).
+struct BlkIdx { int n1w, n1b, temp, qkv, qkv_dw, pout, n2w, n2b, pin, dw, ffn_out; };
+BlkIdx blk_idx(const dcpt_restormer_plan* p, int pidx) {
+  BlkIdx b;
+  int i = pidx;
+  b.n1w = i++; b.n1b = p->ln_bias ? i++ : -1;
+  b.temp = i++; b.qkv = i++; b.qkv_dw = i++; b.pout = i++;
+  b.n2w = i++; b.n2b = p->ln_bias ? i++ : -1;
+  b.pin = i++; b.dw = i++; b.ffn_out = i++;
+  return b;
+}
+
+void add_stage(dcpt_restormer_plan* p, int s, int d, int heads, int n) {
+  for (int j = 0; j < n; ++j) {
+    dcpt_restormer_plan::Blk b;
+    b.d = d; b.heads = heads;
+    b.hid = (int)(d * p->ffn);  // int(dim * ffn_expansion_factor), restormer_arch.py:79
+    b.hidp = (b.hid + 7) / 8 * 8;
+    b.pidx = add_param(p, d);
+    if (p->ln_bias) add_param(p, d);
+    add_param(p, heads, 1, 1);
+    add_param(p, 3 * d, d, 1, 1);
+    add_param(p, 3 * d, 1, 3, 3);
+    add_param(p, d, d, 1, 1);
+    add_param(p, d);
+    if (p->ln_bias) add_param(p, d);
+    add_param(p, 2 * b.hid, d, 1, 1);
+    add_param(p, 2 * b.hid, 1, 3, 3);
+    add_param(p, d, b.hid, 1, 1);
+    p->stage[s].push_back(b);
+  }
+}
+
+struct BlkPacked {
+  bf16 *wqkv, *wpin, *wpout;
+  float* dwp;
+  BlkPacked(Arena& a, const dcpt_restormer_plan::Blk& b) {
+    wqkv = a.take<bf16>((size_t)3 * b.d * b.d);
+    wpin = a.take<bf16>((size_t)2 * b.hidp * b.d);
+    wpout = a.take<bf16>((size_t)b.d * b.hidp);
+    dwp = a.take<float>((size_t)2 * b.hidp * 9);
+  }
+};
+
+struct NetPacked {
+  std::vector<BlkPacked> blk[8];
+  bf16 *down[3], *up[3], *reduce[2];
+  NetPacked(const dcpt_restormer_plan* p, Arena& a) {
+    for (int s = 0; s < 8; ++s)
+      for (auto& b : p->stage[s]) blk[s].emplace_back(a, b);
+    int d = p->dim;
+    for (int i = 0; i < 3; ++i) {  // down_i: d -> d/2 ; up_i (from level i+1 to i): 2d -> 4d
+      down[i] = a.take<bf16>(dcpt_conv3x3_packed_elems(d / 2, d, 0));
+      up[i] = a.take<bf16>(dcpt_conv3x3_packed_elems(4 * d, 2 * d, 0));
+      d *= 2;
+    }
+    reduce[0] = a.take<bf16>((size_t)4 * p->dim * 8 * p->dim);  // level 3: 8dim -> 4dim
+    reduce[1] = a.take<bf16>((size_t)2 * p->dim * 4 * p->dim);  // level 2: 4dim -> 2dim
+  }
+};
+
+struct NetWork {
+  float *e[4], *t[4], *d1, *t1;  // residual stream: encoder level outputs (also decoder levels 3, 2), temporaries
+  bf16 *n, *a, *b, *xm;
+  float *conv, *G, *sq;
+  bf16* weff;
+  NetWork(const dcpt_restormer_plan* p, Arena& ar, int N, int H, int W) {
+    size_t maxn = 0, maxa = 0, maxb = 0, maxconv = 0, maxg = 0, maxsq = 0;
+    int d = p->dim, h = H, w = W;
+    for (int l = 0; l < 4; ++l) {
+      const size_t M = (size_t)N * h * w;
+      e[l] = ar.take<float>(M * d);
+      t[l] = ar.take<float>(M * d);
+      const int dd = l == 0 ? 2 * d : d;  // level 1 also runs the 2*dim decoder / refinement stages
+      const int hidp = ((int)(dd * p->ffn) + 7) / 8 * 8;
+      const size_t wa = (size_t)(3 * dd > 2 * hidp ? 3 * dd : 2 * hidp), wb = (size_t)(3 * dd > hidp ? 3 * dd : hidp);
+      if (M * dd > maxn) maxn = M * dd;
+      if (M * wa > maxa) maxa = M * wa;
+      if (M * wb > maxb) maxb = M * wb;
+      if (M * 2 * d > maxconv) maxconv = M * 2 * d;  // up conv output (2d ch at this level's resolution); down conv needs d/2
+      if ((size_t)N * dd * dd > maxg) maxg = (size_t)N * dd * dd;
+      if ((size_t)N * 2 * dd > maxsq) maxsq = (size_t)N * 2 * dd;
+      d *= 2; h /= 2; w /= 2;
+    }
+    const size_t M0 = (size_t)N * H * W;
+    d1 = ar.take<float>(M0 * 2 * p->dim);
+    t1 = ar.take<float>(M0 * 2 * p->dim);
+    n = ar.take<bf16>(maxn); a = ar.take<bf16>(maxa); b = ar.take<bf16>(maxb); xm = ar.take<bf16>(maxn);
+    conv = ar.take<float>(maxconv); G = ar.take<float>(maxg); sq = ar.take<float>(maxsq);
+    weff = ar.take<bf16>(maxg);
+  }
+};
+
+int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, const float* const* P, const BlkPacked& pk, float* x,
+              float* x2, const NetWork& ws, int N, int H, int W, cudaStream_t st) {
+  const int d = b.d, HW = H * W, M = N * HW;
+  const BlkIdx ix = blk_idx(p, b.pidx);
+  constexpr float eps = 1e-6f;
+  // ---- x2 = x + MDTA(LN(x)) ----
+  DCPT_TRY(ln_fwd_launch(x, P[ix.n1w], ix.n1b >= 0 ? P[ix.n1b] : nullptr, ws.n, nullptr, M, d, eps, st, p->ln_bias));
+  {
+    GemmArgs g = make_gemm_args(M, 3 * d, d, ws.n, d, pk.wqkv, d, EPI_STORE);
+    g.ep.out_bf16 = ws.a; g.ep.ldo = 3 * d;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  DCPT_CUDA(cudaMemsetAsync(ws.sq, 0, (size_t)N * 2 * d * sizeof(float), st));
+  DCPT_TRY(dwconv3_fwd_launch(ws.a, P[ix.qkv_dw], ws.b, ws.sq, 2 * d, N, H, W, 3 * d, st));
+  DCPT_CUDA(cudaMemsetAsync(ws.G, 0, (size_t)N * d * d * sizeof(float), st));
+  for (int n = 0; n < N; ++n) {  // G[n] = q^T k over the HW pixels of image n (both operands MN-major, split-K)
+    const bf16* q = ws.b + (size_t)n * HW * 3 * d;
+    GemmArgs g = make_gemm_args(d, d, HW, q, 3 * d, q + d, 3 * d, EPI_ATOMIC);
+    g.a_mn = 1; g.b_mn = 1;
+    const int bn = d > 128 ? 256 : (d > 64 ? 128 : 64);
+    g.splits = gemm_auto_splits(ceil_div(d, 128) * ceil_div(d, bn), ceil_div(HW, 64));
+    g.ep.out_f32 = ws.G + (size_t)n * d * d; g.ep.ldo = d;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  {
+    const int c = d / b.heads;
+    const size_t smem = (size_t)c * (c + 1) * sizeof(float);
+    DCPT_CHECK_ARG(d % b.heads == 0 && smem <= 200 * 1024, DCPT_E_SHAPE, "mdta: dim %d / heads %d unsupported", d, b.heads);
+    if (smem > 48 * 1024) DCPT_CUDA(cudaFuncSetAttribute(mdta_weff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DCPT_PROF("mdta_weff", 2.0 * N * d * d * c, 4.0 * N * d * d, st);
+    mdta_weff_kernel<<<dim3(b.heads, N), 256, smem, st>>>(ws.G, ws.sq, P[ix.temp], P[ix.pout], ws.weff, d, b.heads);
+    DCPT_LAUNCH_CHECK();
+  }
+  for (int n = 0; n < N; ++n) {  // x2[n] = x[n] + v[n] * W_eff[n]^T
+    const size_t r0 = (size_t)n * HW;
+    GemmArgs g = make_gemm_args(HW, d, d, ws.b + r0 * 3 * d + 2 * d, 3 * d, ws.weff + (size_t)n * d * d, d, EPI_STORE);
+    g.ep.out_f32 = x2 + r0 * d; g.ep.ldo = d; g.ep.resid = x + r0 * d; g.ep.ldr = d;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // ---- x = x2 + GDFN(LN(x2)) ----
+  DCPT_TRY(ln_fwd_launch(x2, P[ix.n2w], ix.n2b >= 0 ? P[ix.n2b] : nullptr, ws.n, nullptr, M, d, eps, st, p->ln_bias));
+  {
+    GemmArgs g = make_gemm_args(M, 2 * b.hidp, d, ws.n, d, pk.wpin, d, EPI_STORE);
+    g.ep.out_bf16 = ws.a; g.ep.ldo = 2 * b.hidp;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  DCPT_TRY(dwgelu_fwd_launch(ws.a, pk.dwp, ws.b, N, H, W, b.hidp, st));
+  {
+    GemmArgs g = make_gemm_args(M, d, b.hidp, ws.b, b.hidp, pk.wpout, b.hidp, EPI_STORE);
+    g.ep.out_f32 = x; g.ep.ldo = d; g.ep.resid = x2; g.ep.ldr = d;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  return 0;
+}
+
+int stage_fwd(const dcpt_restormer_plan* p, int s, const float* const* P, const NetPacked& pk, float* x, float* tmp, const NetWork& ws,
+              int N, int H, int W, cudaStream_t st) {
+  for (size_t j = 0; j < p->stage[s].size(); ++j) DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, tmp, ws, N, H, W, st));
+  return 0;
+}
+
+// 3x3 conv (no bias) of the fp32 residual tensor x [N,H,W,Cin] -> ws.conv fp32 [N,H,W,Cout] on the tensor cores
+int conv_fwd(const float* x, const bf16* wp, const NetWork& ws, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  DCPT_TRY(cast_f32_bf16_launch(x, ws.xm, (long long)N * H * W * Cin, st));
+  Conv3x3Args a;
+  memset(&a, 0, sizeof(a));
+  a.X = ws.xm; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Wp = wp; a.Cout = Cout;
+  a.ep.out_f32 = ws.conv; a.ep.ldo = Cout;
+  return conv3x3_tc_launch(a, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dcpt_layernorm_rows_fwd(const float* x, const float* weight, const float* bias, void* out_bf16, float* stats, int M, int C,
+                            float eps, int center, dcpt_stream_t stream) {
+  return ln_fwd_launch(x, weight, bias, static_cast<bf16*>(out_bf16), stats, M, C, eps, static_cast<cudaStream_t>(stream), center);
+}
+int dcpt_dwconv3x3_fwd(const void* x_bf16, const float* weight, void* out_bf16, float* sumsq, int sq_ch, int N, int H, int W, int CH,
+                       dcpt_stream_t stream) {
+  return dwconv3_fwd_launch(static_cast<const bf16*>(x_bf16), weight, static_cast<bf16*>(out_bf16), sumsq, sq_ch, N, H, W, CH,
+                            static_cast<cudaStream_t>(stream));
+}
+int dcpt_dwconv3x3_gelu_gate_fwd(const void* u_bf16, const float* weight, void* g_bf16, int N, int H, int W, int C,
+                                 dcpt_stream_t stream) {
+  return dwgelu_fwd_launch(static_cast<const bf16*>(u_bf16), weight, static_cast<bf16*>(g_bf16), N, H, W, C,
+                           static_cast<cudaStream_t>(stream));
+}
+
+dcpt_restormer_plan* dcpt_restormer_create(int inp_channels, int out_channels, int dim, const int* num_blocks, int num_refinement_blocks,
+                                           const int* heads, double ffn_expansion_factor, int bias, int ln_with_bias) {
+  if (inp_channels != 3 || out_channels != 3 || dim < 16 || dim % 16 != 0 || !num_blocks || !heads || num_refinement_blocks < 0 ||
+      ffn_expansion_factor <= 0) {
+    dcpt_set_error("restormer_create: need inp/out channels 3 and dim %% 16 == 0 (dim=%d inp=%d out=%d)", dim, inp_channels, out_channels);
+    return nullptr;
+  }
+  for (int l = 0; l < 4; ++l)
+    if (heads[l] <= 0 || ((dim << l) % heads[l]) != 0 || num_blocks[l] < 0 || (dim << l) > 1024) {
+      dcpt_set_error("restormer_create: level %d: dim %d not divisible by heads %d (or > 1024)", l, dim << l, heads[l]);
+      return nullptr;
+    }
+  dcpt_restormer_plan* p = new dcpt_restormer_plan();
+  p->inp_ch = inp_channels; p->out_ch = out_channels; p->dim = dim; p->nref = num_refinement_blocks;
+  p->bias = bias != 0; p->ln_bias = ln_with_bias != 0; p->ffn = ffn_expansion_factor;
+  for (int l = 0; l < 4; ++l) { p->nb[l] = num_blocks[l]; p->heads[l] = heads[l]; }
+  // named_parameters() order of the reference module (restormer_arch.py:254-368)
+  p->p_embed = add_param(p, dim, inp_channels, 3, 3);
+  add_stage(p, ST_ENC1, dim, heads[0], num_blocks[0]);
+  p->p_down[0] = add_param(p, dim / 2, dim, 3, 3);
+  add_stage(p, ST_ENC2, dim * 2, heads[1], num_blocks[1]);
+  p->p_down[1] = add_param(p, dim, dim * 2, 3, 3);
+  add_stage(p, ST_ENC3, dim * 4, heads[2], num_blocks[2]);
+  p->p_down[2] = add_param(p, dim * 2, dim * 4, 3, 3);
+  add_stage(p, ST_LAT, dim * 8, heads[3], num_blocks[3]);
+  p->p_up[2] = add_param(p, dim * 16, dim * 8, 3, 3);
+  p->p_reduce[0] = add_param(p, dim * 4, dim * 8, 1, 1);
+  if (p->bias) add_param(p, dim * 4);
+  add_stage(p, ST_DEC3, dim * 4, heads[2], num_blocks[2]);
+  p->p_up[1] = add_param(p, dim * 8, dim * 4, 3, 3);
+  p->p_reduce[1] = add_param(p, dim * 2, dim * 4, 1, 1);
+  if (p->bias) add_param(p, dim * 2);
+  add_stage(p, ST_DEC2, dim * 2, heads[1], num_blocks[1]);
+  p->p_up[0] = add_param(p, dim * 4, dim * 2, 3, 3);
+  add_stage(p, ST_DEC1, dim * 2, heads[0], num_blocks[0]);
+  add_stage(p, ST_REF, dim * 2, heads[0], num_refinement_blocks);
+  p->p_out = add_param(p, out_channels, dim * 2, 3, 3);
+  if (p->bias) add_param(p, out_channels);
+  return p;
+}
+
+void dcpt_restormer_destroy(dcpt_restormer_plan* plan) { delete plan; }
+int dcpt_restormer_num_params(const dcpt_restormer_plan* plan) { return (int)plan->params.size(); }
+long long dcpt_restormer_param_shape(const dcpt_restormer_plan* plan, int i, int dims[4]) {
+  if (i < 0 || i >= (int)plan->params.size()) return -1;
+  for (int k = 0; k < 4; ++k) dims[k] = plan->params[i].dims[k];
+  return plan->params[i].numel;
+}
+size_t dcpt_restormer_packed_bytes(const dcpt_restormer_plan* plan) {
+  Arena a(nullptr);
+  NetPacked pk(plan, a);
+  return a.size();
+}
+size_t dcpt_restormer_workspace_bytes(const dcpt_restormer_plan* plan, int N, int H, int W) {
+  Arena a(nullptr);
+  NetWork ws(plan, a, N, H, W);
+  return a.size();
+}
+
+int dcpt_restormer_pack(const dcpt_restormer_plan* p, const float* const* P, void* packed, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(P != nullptr && packed != nullptr, DCPT_E_ARG, "restormer_pack: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(packed);
+  NetPacked pk(p, a);
+  for (int s = 0; s < 8; ++s)
+    for (size_t j = 0; j < p->stage[s].size(); ++j) {
+      const auto& b = p->stage[s][j];
+      const BlkIdx ix = blk_idx(p, b.pidx);
+      const BlkPacked& bp = pk.blk[s][j];
+      DCPT_TRY(pack_weight_launch(P[ix.qkv], nullptr, bp.wqkv, 3 * b.d, b.d, PACK_PLAIN, st));
+      pack_halves_kernel<bf16><<<blocks_for((long long)2 * b.hidp * b.d), 256, 0, st>>>(P[ix.pin], bp.wpin, b.hid, b.hidp, b.d);
+      pack_halves_kernel<float><<<blocks_for((long long)2 * b.hidp * 9), 256, 0, st>>>(P[ix.dw], bp.dwp, b.hid, b.hidp, 9);
+      pack_cols_kernel<<<blocks_for((long long)b.d * b.hidp), 256, 0, st>>>(P[ix.ffn_out], bp.wpout, b.d, b.hid, b.hidp);
+      DCPT_LAUNCH_CHECK();
+    }
+  int d = p->dim;
+  for (int i = 0; i < 3; ++i) {
+    DCPT_TRY(pack_conv3x3_launch(P[p->p_down[i]], pk.down[i], d / 2, d, 0, st));
+    DCPT_TRY(pack_conv3x3_launch(P[p->p_up[i]], pk.up[i], 4 * d, 2 * d, 0, st));
+    d *= 2;
+  }
+  DCPT_TRY(pack_weight_launch(P[p->p_reduce[0]], nullptr, pk.reduce[0], 4 * p->dim, 8 * p->dim, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[p->p_reduce[1]], nullptr, pk.reduce[1], 2 * p->dim, 4 * p->dim, PACK_PLAIN, st));
+  return 0;
+}
+
+int dcpt_restormer_block_fwd(const dcpt_restormer_plan* p, int stage, int j, const float* const* P, const void* packed, float* x,
+                             void* workspace, int N, int H, int W, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(stage >= 0 && stage < 8 && j >= 0 && j < (int)p->stage[stage].size(), DCPT_E_ARG, "restormer_block_fwd: no block %d in stage %d",
+                 j, stage);
+  DCPT_CHECK_ARG(P && packed && x && workspace && N > 0 && H > 0 && W > 0, DCPT_E_ARG, "restormer_block_fwd: bad argument");
+  Arena ap(const_cast<void*>(packed));
+  NetPacked pk(p, ap);
+  // The workspace is laid out per resolution level of a full-size input: a block of level l run on N x H x W pixels uses
+  // the level-l buffers of a virtual N x (H << l) x (W << l) input.
+  static const int kLevel[8] = {0, 1, 2, 3, 2, 1, 0, 0};
+  const int l = kLevel[stage];
+  Arena aw(workspace);
+  NetWork ws(p, aw, N, H << l, W << l);
+  return block_fwd(p, p->stage[stage][j], P, pk.blk[stage][j], x, l == 0 ? ws.t1 : ws.t[l], ws, N, H, W, static_cast<cudaStream_t>(stream));
+}
+
+int dcpt_restormer_fwd(const dcpt_restormer_plan* p, const float* const* P, const void* packed, const float* inp, float* out,
+                       void* workspace, float* const* host_feats, int hook, int N, int H, int W, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, DCPT_E_SHAPE,
+                 "restormer: H=%d W=%d must be positive multiples of 8 (SRModel.pre_test pads to window_size)", H, W);
+  DCPT_CHECK_ARG((long long)N * H * W * 6 * p->dim < (1ll << 31), DCPT_E_SHAPE, "restormer: batch too large for 32-bit pixel index");
+  DCPT_CHECK_ARG(hook || out != nullptr, DCPT_E_ARG, "restormer_fwd: out is NULL but hook == 0");
+  DCPT_CHECK_ARG(P && packed && inp && workspace, DCPT_E_ARG, "restormer_fwd: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena ap(const_cast<void*>(packed));
+  NetPacked pk(p, ap);
+  Arena aw(workspace);
+  NetWork ws(p, aw, N, H, W);
+  const int dim = p->dim;
+  // patch_embed (:377): 3x3, 3 -> dim, no bias (fp32 CUDA-core stencil, K = 27)
+  DCPT_TRY(conv3x3_img_to_feat_launch(inp, P[p->p_embed], nullptr, 0, ws.e[0], nullptr, nullptr, N, H, W, dim, st));
+  DCPT_TRY(stage_fwd(p, ST_ENC1, P, pk, ws.e[0], ws.t[0], ws, N, H, W, st));
+  // encoder: Downsample = 3x3 conv d -> d/2 + PixelUnshuffle(2) (:175-188)
+  int d = dim, h = H, w = W;
+  for (int l = 0; l < 3; ++l) {
+    DCPT_TRY(conv_fwd(ws.e[l], pk.down[l], ws, N, h, w, d, d / 2, st));
+    const long long total = (long long)N * h * w * (d / 2);
+    pixel_unshuffle_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, ws.e[l + 1], total, h, w, d / 2);
+    DCPT_LAUNCH_CHECK();
+    d *= 2; h /= 2; w /= 2;
+    DCPT_TRY(stage_fwd(p, ST_ENC2 + l, P, pk, ws.e[l + 1], ws.t[l + 1], ws, N, h, w, st));
+  }
+  // decoder: Upsample = 3x3 conv d -> 2d + PixelShuffle(2) (:191-202), cat with the encoder skip, 1x1 reduce (levels 3, 2)
+  float* x = ws.e[3];  // latent
+  float* feats[3] = {nullptr, nullptr, nullptr};
+  for (int l = 2; l >= 0; --l) {
+    DCPT_TRY(conv_fwd(x, pk.up[l], ws, N, h, w, d, 2 * d, st));
+    const int Cs = d / 2;  // channels of the shuffled tensor = channels of the skip
+    const long long total = (long long)N * h * w * 4 * 2 * Cs;
+    if (l > 0) {
+      pixel_shuffle_cat_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, ws.e[l], nullptr, ws.a, total, h, w, Cs);
+      DCPT_LAUNCH_CHECK();
+      h *= 2; w *= 2; d /= 2;
+      // reduce_chan_level{3,2} (:391, :396): 1x1, 2d -> d.  The decoder level reuses the temporaries of its encoder level;
+      // its output must not overwrite the skip (still needed? no: the skip was consumed by the cat) -> write into t[l], swap roles.
+      const int ri = l == 2 ? 0 : 1;
+      GemmArgs g = make_gemm_args(N * h * w, d, 2 * d, ws.a, 2 * d, pk.reduce[ri], 2 * d, EPI_STORE);
+      g.ep.out_f32 = ws.t[l]; g.ep.ldo = d;
+      if (p->bias) g.ep.bias = P[p->p_reduce[ri] + 1];
+      DCPT_TRY(gemm_launch(g, st));
+      DCPT_TRY(stage_fwd(p, l == 2 ? ST_DEC3 : ST_DEC2, P, pk, ws.t[l], ws.e[l], ws, N, h, w, st));
+      x = ws.t[l];
+      feats[2 - l] = x;
+    } else {
+      pixel_shuffle_cat_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, ws.e[0], ws.d1, nullptr, total, h, w, Cs);
+      DCPT_LAUNCH_CHECK();
+      h *= 2; w *= 2;  // d stays 2 * dim: level 1 has no reduce conv (:398-400)
+      DCPT_TRY(stage_fwd(p, ST_DEC1, P, pk, ws.d1, ws.t1, ws, N, h, w, st));
+      x = ws.d1;
+      feats[2] = x;
+    }
+  }
+  if (host_feats) {
+    // decoder_level3 [N, H/4, W/4, 4dim], decoder_level2 [N, H/2, W/2, 2dim], decoder_level1 [N, H, W, 2dim]
+    const int fd[3] = {4 * dim, 2 * dim, 2 * dim}, fs[3] = {4, 2, 1};
+    for (int i = 0; i < 3; ++i)
+      if (host_feats[i])
+        DCPT_CUDA(cudaMemcpyAsync(host_feats[i], feats[i], (size_t)N * (H / fs[i]) * (W / fs[i]) * fd[i] * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  if (hook) return 0;  // :403 - the DCPT pretraining pass stops here
+  DCPT_TRY(stage_fwd(p, ST_REF, P, pk, ws.d1, ws.t1, ws, N, H, W, st));
+  // output conv + global residual (:413)
+  return conv3x3_feat_to_img_launch(ws.d1, P[p->p_out], p->bias ? P[p->p_out + 1] : nullptr, inp, out, N, H, W, 2 * dim, st);
+}
+
+}  // extern "C"

@@ -72,6 +72,18 @@ PROTOTYPES = {
     "dcpt_meanpool_fc_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "dcpt_meanpool_fc_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "dcpt_add_bf16": (_I, [_VP, _VP, _VP, _LL, _VP]),
+    "dcpt_layernorm_rows_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _F, _I, _VP]),
+    "dcpt_dwconv3x3_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "dcpt_dwconv3x3_gelu_gate_fwd": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "dcpt_restormer_create": (_VP, [_I, _I, _I, C.POINTER(_I), _I, C.POINTER(_I), C.c_double, _I, _I]),
+    "dcpt_restormer_destroy": (None, [_VP]),
+    "dcpt_restormer_num_params": (_I, [_VP]),
+    "dcpt_restormer_param_shape": (_LL, [_VP, _I, C.POINTER(_I)]),
+    "dcpt_restormer_packed_bytes": (_SZ, [_VP]),
+    "dcpt_restormer_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
+    "dcpt_restormer_pack": (_I, [_VP, _PP, _VP, _VP]),
+    "dcpt_restormer_block_fwd": (_I, [_VP, _I, _I, _PP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "dcpt_restormer_fwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _I, _I, _I, _I, _VP]),
 }
 
 

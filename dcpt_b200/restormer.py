@@ -1,0 +1,86 @@
+"""Host-side engine for Restormer (reference: basicsr/archs/restormer_arch.py:234-422), forward / inference path.
+
+``RestormerEngine`` owns the C plan, the packed bf16 operand cache and a per-shape workspace; the ``basicsr``
+mirror's ``Restormer`` module calls ``forward``.  No PyTorch implementation of the math lives here and there is
+no CPU path.  Training (backward) of the Restormer blocks is not built yet: calling the module with gradients
+enabled on its parameters raises ``DcptError`` instead of silently returning a graph-less tensor.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as _l
+from .ops import _p, _stream
+
+
+class RestormerEngine:
+    def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=(4, 6, 6, 8), num_refinement_blocks=4, heads=(1, 2, 4, 8),
+                 ffn_expansion_factor=2.66, bias=False, ln_with_bias=False):
+        self.lib = _l.load_library()
+        nb = (C.c_int * 4)(*num_blocks)
+        hd = (C.c_int * 4)(*heads)
+        plan = self.lib.dcpt_restormer_create(inp_channels, out_channels, dim, nb, num_refinement_blocks, hd,
+                                              float(ffn_expansion_factor), int(bool(bias)), int(bool(ln_with_bias)))
+        if not plan:
+            raise _l.DcptError("dcpt_restormer_create: " + self.lib.dcpt_last_error().decode())
+        self.plan = C.c_void_p(plan)
+        self.dim = dim
+        self.num_params = self.lib.dcpt_restormer_num_params(self.plan)
+        dims = (C.c_int * 4)()
+        self.numels = [self.lib.dcpt_restormer_param_shape(self.plan, i, dims) for i in range(self.num_params)]
+        self._packed = None
+        self._packed_key = None
+        self._work = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.lib.dcpt_restormer_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    def _check_params(self, params):
+        if len(params) != self.num_params or [p.numel() for p in params] != self.numels:
+            raise _l.DcptError(f"parameter layout mismatch between module and C plan ({len(params)} vs {self.num_params} tensors)")
+        for p in params:
+            if not p.is_cuda:
+                raise _l.DcptError("dcpt_b200 has no CPU path: move the network to a CUDA device (B200)")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise _l.DcptError("parameters must be contiguous fp32")
+
+    def packed_for(self, params):
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or self._packed.device != params[0].device:
+            self._packed = torch.empty(self.lib.dcpt_restormer_packed_bytes(self.plan), dtype=torch.uint8, device=params[0].device)
+            self._packed_key = None
+        if key != self._packed_key:
+            pp = _l.ptr_array([p.data_ptr() for p in params])
+            _l.check(self.lib.dcpt_restormer_pack(self.plan, pp, _p(self._packed), _stream()), "restormer_pack")
+            self._packed_key = key
+        return self._packed
+
+    def forward(self, params, inp, hook=False, want_feats=False):
+        """inp fp32 NCHW [N,3,H,W] -> (out or None, feats [decoder_level3, 2, 1] as NHWC fp32 or None)."""
+        self._check_params(params)
+        if not inp.is_cuda:
+            raise _l.DcptError("dcpt_b200 has no CPU path: input is on %s" % inp.device)
+        inp = inp.contiguous().float()
+        N, _, H, W = inp.shape
+        dev = inp.device
+        packed = self.packed_for(params)
+        k = (N, H, W, dev)
+        if k not in self._work:
+            self._work[k] = torch.empty(self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
+        out = None if hook else torch.empty_like(inp)
+        feats = fp = None
+        if want_feats:
+            d = self.dim
+            feats = [torch.empty(N, H // 4, W // 4, 4 * d, dtype=torch.float32, device=dev),
+                     torch.empty(N, H // 2, W // 2, 2 * d, dtype=torch.float32, device=dev),
+                     torch.empty(N, H, W, 2 * d, dtype=torch.float32, device=dev)]
+            fp = _l.ptr_array([f.data_ptr() for f in feats])
+        pp = _l.ptr_array([p.data_ptr() for p in params])
+        _l.check(self.lib.dcpt_restormer_fwd(self.plan, pp, _p(packed), _p(inp), _p(out), _p(self._work[k]), fp, int(bool(hook)),
+                                             N, H, W, _stream()), "restormer_fwd")
+        return out, feats

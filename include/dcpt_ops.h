@@ -212,6 +212,57 @@ int dcpt_meanpool_fc_bwd(const float* dlogits, const float* pooled, const float*
 /* out = a + b (bf16, n elements): sums the two gradient paths of a residual block. */
 int dcpt_add_bf16(const void* a, const void* b, void* out, long long n, dcpt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Restormer — basicsr/archs/restormer_arch.py (TransformerBlock :148-159 = MDTA :103-145 + GDFN :75-100,
+ * Downsample/Upsample :175-202, Restormer.forward :376-422).  Forward (inference) path.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Channel LayerNorm of the Restormer blocks (restormer_arch.py:26-72) on NHWC rows: x fp32 [M,C] -> out bf16 [M,C].
+ * bias == NULL and center == 0: BiasFree_LayerNorm (:38-40), x / sqrt(var + 1e-6) * weight with var about the mean;
+ * center != 0: WithBias_LayerNorm (:56-59).  stats (nullable) receives (mean, rstd) per row. */
+int dcpt_layernorm_rows_fwd(const float* x, const float* weight, const float* bias, void* out_bf16, float* stats, int M, int C,
+                            float eps, int center, dcpt_stream_t stream);
+
+/* Depthwise 3x3, stride 1, zero pad 1, no bias (Attention.qkv_dwconv, restormer_arch.py:110-118) on bf16 NHWC
+ * [N,H,W,CH]; weight fp32 [CH,1,3,3].  sumsq (nullable) fp32 [N, sq_ch] += sum over pixels of out^2 for the first
+ * sq_ch channels: the squared norms F.normalize(q / k, dim=-1) divides by (:131-132). */
+int dcpt_dwconv3x3_fwd(const void* x_bf16, const float* weight, void* out_bf16, float* sumsq, int sq_ch, int N, int H, int W, int CH,
+                       dcpt_stream_t stream);
+
+/* FeedForward gate (restormer_arch.py:97-98): g = gelu(dw3x3(u)[:, :C]) * dw3x3(u)[:, C:], exact erf GELU, no bias.
+ * u bf16 [N,H,W,2C], weight fp32 [2C,1,3,3], g bf16 [N,H,W,C]. */
+int dcpt_dwconv3x3_gelu_gate_fwd(const void* u_bf16, const float* weight, void* g_bf16, int N, int H, int W, int C,
+                                 dcpt_stream_t stream);
+
+typedef struct dcpt_restormer_plan dcpt_restormer_plan;
+
+/* Restormer.__init__ (restormer_arch.py:236-250); num_blocks and heads have 4 entries.  inp/out channels must be 3,
+ * scale 1, dual_pixel_task False.  Parameters travel in the module's named_parameters() order. */
+dcpt_restormer_plan* dcpt_restormer_create(int inp_channels, int out_channels, int dim, const int* num_blocks,
+                                           int num_refinement_blocks, const int* heads, double ffn_expansion_factor, int bias,
+                                           int ln_with_bias);
+void dcpt_restormer_destroy(dcpt_restormer_plan* plan);
+int dcpt_restormer_num_params(const dcpt_restormer_plan* plan);
+long long dcpt_restormer_param_shape(const dcpt_restormer_plan* plan, int i, int dims[4]);
+size_t dcpt_restormer_packed_bytes(const dcpt_restormer_plan* plan);
+size_t dcpt_restormer_workspace_bytes(const dcpt_restormer_plan* plan, int N, int H, int W);
+int dcpt_restormer_pack(const dcpt_restormer_plan* plan, const float* const* host_params, void* packed, dcpt_stream_t stream);
+
+/* Restormer.forward(inp_img, hook): inp fp32 NCHW [N,3,H,W] (H, W multiples of 8) -> out fp32 NCHW = output(...) + inp.
+ * hook != 0: stop after decoder_level1 (:403), `out` may be NULL.  host_feats (nullable): 3 device pointers receiving
+ * decoder_level3 / 2 / 1 outputs as fp32 NHWC ([N,H/4,W/4,4dim], [N,H/2,W/2,2dim], [N,H,W,2dim]) - what DCPT's hooks on
+ * `decoder_level{k}.body` capture (degradation_classification_pretrain_model.py:60-68). */
+int dcpt_restormer_fwd(const dcpt_restormer_plan* plan, const float* const* host_params, const void* packed, const float* inp,
+                       float* out, void* workspace, float* const* host_feats, int hook, int N, int H, int W,
+                       dcpt_stream_t stream);
+
+/* One TransformerBlock (restormer_arch.py:156-159) of the plan, in place on x fp32 NHWC [N,H,W,d] where d is the width of
+ * block j of `stage` (0..7 = encoder_level1, 2, 3, latent, decoder_level3, 2, 1, refinement).  `workspace` must be at least
+ * dcpt_restormer_workspace_bytes(plan, N, H << l, W << l), l = the stage's resolution level (0,1,2,3,2,1,0,0).  Used by the
+ * parity tests against the reference's TransformerBlock. */
+int dcpt_restormer_block_fwd(const dcpt_restormer_plan* plan, int stage, int j, const float* const* host_params, const void* packed,
+                             float* x, void* workspace, int N, int H, int W, dcpt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

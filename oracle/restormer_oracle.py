@@ -20,6 +20,31 @@ import torch.nn.functional as F
 
 Tensor = torch.Tensor
 
+# Rounding hook (as in nafnet_oracle.py): the CUDA path stores branch tensors as bf16.  Tests that want to separate
+# "operand rounding" from "wrong math" pass q = lambda t: t.bfloat16().float(), which rounds at the same points the
+# kernels do (LN output, qkv / dw-conv outputs, the folded attention-projection matrix, GDFN intermediates, conv inputs
+# and packed weights).  q = None (default) is the exact fp32 reference math.
+_Q = None
+
+
+class rounding:
+    """Context manager: ``with rounding(q): ...`` runs the oracle with the rounding hook q."""
+
+    def __init__(self, q):
+        self.q = q
+
+    def __enter__(self):
+        global _Q
+        self.prev, _Q = _Q, self.q
+
+    def __exit__(self, *a):
+        global _Q
+        _Q = self.prev
+
+
+def _q(t: Tensor) -> Tensor:
+    return t if _Q is None else _Q(t)
+
 
 # --------------------------------------------------------------------------
 # LayerNorm over channels — restormer_arch.py:26-72
@@ -39,7 +64,7 @@ def layernorm_chan(x: Tensor, weight: Tensor, bias: Optional[Tensor], eps: float
 
 
 def _ln(x: Tensor, P: Dict[str, Tensor], prefix: str) -> Tensor:
-    return layernorm_chan(x, P[prefix + ".body.weight"], P.get(prefix + ".body.bias"))
+    return _q(layernorm_chan(x, P[prefix + ".body.weight"], P.get(prefix + ".body.bias")))
 
 
 # --------------------------------------------------------------------------
@@ -48,9 +73,9 @@ def _ln(x: Tensor, P: Dict[str, Tensor], prefix: str) -> Tensor:
 def mdta(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int) -> Tensor:
     """Transposed (channel) attention with ReLU instead of softmax (:135-136)."""
     b, c, h, w = x.shape
-    qkv = F.conv2d(x, P[prefix + ".qkv.weight"], P.get(prefix + ".qkv.bias"))                         # :124 1x1, d -> 3d
-    qkv = F.conv2d(qkv, P[prefix + ".qkv_dwconv.weight"], P.get(prefix + ".qkv_dwconv.bias"), padding=1,
-                   groups=3 * c)                                                                       # :124 dw 3x3
+    qkv = _q(F.conv2d(x, _q(P[prefix + ".qkv.weight"]), P.get(prefix + ".qkv.bias")))                 # :124 1x1, d -> 3d
+    qkv = _q(F.conv2d(qkv, P[prefix + ".qkv_dwconv.weight"], P.get(prefix + ".qkv_dwconv.bias"), padding=1,
+                      groups=3 * c))                                                                   # :124 dw 3x3
     q, k, v = qkv.chunk(3, dim=1)                                                                      # :125
     ch = c // heads
     q = q.reshape(b, heads, ch, h * w)                                                                 # :127-129
@@ -60,6 +85,10 @@ def mdta(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int) -> Tensor:
     k = F.normalize(k, dim=-1)
     attn = (q @ k.transpose(-2, -1)) * P[prefix + ".temperature"].view(1, heads, 1, 1)                 # :134
     attn = F.relu(attn)                                                                                # :136
+    if _Q is not None:  # the kernels fold attn into the projection: W_eff = W_out * blockdiag(attn), rounded to bf16
+        wo = P[prefix + ".project_out.weight"].reshape(c, heads, ch)                                   # [o, head, i]
+        weff = _q(torch.einsum("ohi,bhij->bohj", wo, attn).reshape(b, c, c))
+        return torch.einsum("boj,bjp->bop", weff, v.reshape(b, c, h * w)).reshape(b, c, h, w)
     out = (attn @ v).reshape(b, c, h, w)                                                               # :138-142
     return F.conv2d(out, P[prefix + ".project_out.weight"], P.get(prefix + ".project_out.bias"))       # :144
 
@@ -68,12 +97,12 @@ def mdta(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int) -> Tensor:
 # GDFN — restormer_arch.py:75-100
 # --------------------------------------------------------------------------
 def gdfn(x: Tensor, P: Dict[str, Tensor], prefix: str) -> Tensor:
-    y = F.conv2d(x, P[prefix + ".project_in.weight"], P.get(prefix + ".project_in.bias"))              # :96
+    y = _q(F.conv2d(x, _q(P[prefix + ".project_in.weight"]), P.get(prefix + ".project_in.bias")))      # :96
     hid2 = y.shape[1]
     y = F.conv2d(y, P[prefix + ".dwconv.weight"], P.get(prefix + ".dwconv.bias"), padding=1, groups=hid2)  # :97
     x1, x2 = y.chunk(2, dim=1)
-    y = F.gelu(x1) * x2                                                                                # :98 (exact erf GELU)
-    return F.conv2d(y, P[prefix + ".project_out.weight"], P.get(prefix + ".project_out.bias"))         # :99
+    y = _q(F.gelu(x1) * x2)                                                                            # :98 (exact erf GELU)
+    return F.conv2d(y, _q(P[prefix + ".project_out.weight"]), P.get(prefix + ".project_out.bias"))     # :99
 
 
 def transformer_block(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int) -> Tensor:
@@ -90,11 +119,11 @@ def _stage(x: Tensor, P: Dict[str, Tensor], name: str, nblk: int, heads: int) ->
 
 
 def _down(x, P, name):   # Downsample :175-188: 3x3 conv C -> C/2 (no bias) + PixelUnshuffle(2)
-    return F.pixel_unshuffle(F.conv2d(x, P[name + ".body.0.weight"], None, padding=1), 2)
+    return F.pixel_unshuffle(F.conv2d(_q(x), _q(P[name + ".body.0.weight"]), None, padding=1), 2)
 
 
 def _up(x, P, name):     # Upsample :191-202: 3x3 conv C -> 2C (no bias) + PixelShuffle(2)
-    return F.pixel_shuffle(F.conv2d(x, P[name + ".body.0.weight"], None, padding=1), 2)
+    return F.pixel_shuffle(F.conv2d(_q(x), _q(P[name + ".body.0.weight"]), None, padding=1), 2)
 
 
 def restormer_fwd(inp: Tensor, P: Dict[str, Tensor], num_blocks: Sequence[int] = (4, 6, 6, 8), num_refinement_blocks: int = 4,
@@ -110,10 +139,10 @@ def restormer_fwd(inp: Tensor, P: Dict[str, Tensor], num_blocks: Sequence[int] =
     e3 = _stage(_down(e2, P, "down2_3"), P, "encoder_level3", num_blocks[2], heads[2])
     lat = _stage(_down(e3, P, "down3_4"), P, "latent", num_blocks[3], heads[3])
     d3 = torch.cat([_up(lat, P, "up4_3"), e3], 1)                                                      # :389-390
-    d3 = F.conv2d(d3, P["reduce_chan_level3.weight"], P.get("reduce_chan_level3.bias"))
+    d3 = F.conv2d(_q(d3), _q(P["reduce_chan_level3.weight"]), P.get("reduce_chan_level3.bias"))
     d3 = _stage(d3, P, "decoder_level3", num_blocks[2], heads[2])
     d2 = torch.cat([_up(d3, P, "up3_2"), e2], 1)
-    d2 = F.conv2d(d2, P["reduce_chan_level2.weight"], P.get("reduce_chan_level2.bias"))
+    d2 = F.conv2d(_q(d2), _q(P["reduce_chan_level2.weight"]), P.get("reduce_chan_level2.bias"))
     d2 = _stage(d2, P, "decoder_level2", num_blocks[1], heads[1])
     d1 = torch.cat([_up(d2, P, "up2_1"), e1], 1)                                                       # :398-399 (no reduce)
     d1 = _stage(d1, P, "decoder_level1", num_blocks[0], heads[0])
