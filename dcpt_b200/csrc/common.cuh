@@ -55,6 +55,9 @@ int dcpt_num_sms();
 // Host-side TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point; gemm_sm100.cu).
 // 2-D: row-major bf16 [rows, cols], box 64 x box_rows, 128-byte swizzle (UMMA operand tiles).
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+// Epilogue tiles: row-major [rows, cols] of fp32 (elem_bytes 4, 128-byte swizzle) or bf16 (elem_bytes 2, 64-byte swizzle),
+// box = 32 columns x 32 rows.
+int make_tmap_epi(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int elem_bytes);
 // 4-D: bf16 NHWC [N, H, W, CH], box 64 x box_w x box_h x 1 (stencil tiles / implicit-GEMM conv operands, zero-filled halo).
 int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h, int swizzle128 = 0);
 
@@ -161,6 +164,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// 2-D tiled store shared -> global (bulk async group); out-of-range parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before a bulk store reads them
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // L2 prefetch of a 2-D box (no shared-memory destination, no barrier).

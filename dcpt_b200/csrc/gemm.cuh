@@ -17,6 +17,7 @@ enum GemmEpilogue {
   EPI_GATE_BWD = 2,  // acc = d(sg); reads x4, writes d(x4) (bf16, 2C)
   EPI_PIXSHUF = 3,   // pixel-shuffle(2) scatter + residual add -> fp32 (+bf16 mirror)
   EPI_ATOMIC = 4,    // split-K wgrad: red.add.f32 into out_f32
+  EPI_STORE_TMA = 5, // internal: EPI_STORE with the residual tile TMA-loaded and the output tile TMA-stored (gemm_sm100.cu)
 };
 
 struct EpiParams {

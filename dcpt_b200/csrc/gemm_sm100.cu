@@ -21,18 +21,26 @@
 
 namespace {
 
+struct EpiMaps {
+  CUtensorMap o32, o16, r32;  // fp32 output, bf16 output, fp32 residual (EPI_STORE_TMA; unused otherwise)
+};
+
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 
-template <int BN>
+// EPI_STORE_TMA keeps two 4 KiB epilogue tiles per epilogue warp (residual tile in, output tile out, in place), so it
+// runs with one pipeline stage fewer than the register-staged epilogues (one 4 KiB transpose tile per warp).
+template <int BN, int EPI>
 struct Cfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr bool TMA_EPI = EPI == EPI_STORE_TMA;
+  static constexpr int STAGES = TMA_EPI ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two >= 32)
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 4096 /*epilogue staging, 4 KiB per epilogue warp*/;
+  static constexpr uint32_t EPI_BYTES = 8 * (TMA_EPI ? 8192 : 4096);  // starts 1024-byte aligned (STAGE_BYTES % 1024 == 0)
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 512 /*barriers*/;
 };
 
 // UMMA shared-memory descriptor (sm_100): start addr [0,14), LBO [16,30), SBO [32,46) (all >>4),
@@ -60,19 +68,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 // (A = dY patch, B = X patch shifted by the tap of this N tile), MN-major operands.
 template <int BN, int EPI, bool A_MN, bool B_MN, int CONV>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep, ConvGeom cg) {
-  using C = Cfg<BN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ EpiMaps em,
+               int M, int N, int K, int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep, ConvGeom cg) {
+  using C = Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)C::STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+  uint8_t* sEpi = smem + (size_t)C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = tempty + 2;  // [8 epilogue warps][2]: residual tile landed (EPI_STORE_TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +99,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 8);  // one arrive per epilogue warp
+    }
+    for (int b = 0; b < 16; ++b) mbar_init(&rfull[b], 1);
+    if constexpr (C::TMA_EPI) {
+      tma_prefetch_desc(&em.o32);
+      tma_prefetch_desc(&em.o16);
+      tma_prefetch_desc(&em.r32);
     }
     fence_mbar_init();
   }
@@ -227,9 +243,123 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 2;
     const int q = warp & 3;
     const int chalf = ew >> 2;
-    const uint32_t stage = smem_u32(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256) + (uint32_t)ew * 4096u;  // float4 index * 16
+    const uint32_t stage = smem_u32(sEpi) + (uint32_t)ew * 4096u;  // float4 index * 16
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (C::TMA_EPI) {
+      // ---- TMA epilogue (EPI_STORE_TMA) ----
+      // Per warp and 32 x 32 chunk: the fp32 residual tile is TMA-loaded into a 128B-swizzled 4 KiB buffer (requested one
+      // chunk ahead), each lane adds its accumulator row (tcgen05.ld gives lane = row) and the bias in place, and ONE
+      // bulk tensor store writes the tile back (clipped at the matrix edge): no per-element address arithmetic, bounds
+      // checks or uncoalesced accesses in the warp, all global traffic is asynchronous.  bf16 outputs are packed into a
+      // 64B-swizzled 2 KiB tile of the same buffer.
+      uint8_t* ebuf = sEpi + (size_t)ew * 8192;
+      uint64_t* rf = rfull + ew * 2;
+      uint32_t rphase = 0;  // bit b: parity of the next completion of rf[b]
+      int ci = 0;           // chunks handled by this warp so far (buffer = ci & 1)
+      const bool has_r = ep.resid != nullptr;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_t = tile % tiles_n;
+        const int m_t = (tile / tiles_n) % tiles_m;
+        const int m0 = m_t * BM + q * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        bool first = true;
+#pragma unroll 1
+        for (int c = chalf; c < BN / 32; c += 2) {
+          const int n0 = n_t * BN + c * 32;
+          if (n0 >= N) break;  // warp-uniform
+          const int b = ci & 1;
+          if (first) {
+            if (lane == 0) {
+              bulk_wait_read<0>();
+              if (has_r) {
+                mbar_arrive_expect_tx(&rf[b], 4096);
+                tma_load_2d(ebuf + b * 4096, &em.r32, &rf[b], n0, m0);
+              }
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            first = false;
+          }
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          if (lane == 0) {
+            bulk_wait_read<0>();  // the store that read buffer b ^ 1 (previous chunk) has drained it
+            const int nn = n0 + 64;
+            if (has_r && c + 2 < BN / 32 && nn < N) {
+              mbar_arrive_expect_tx(&rf[b ^ 1], 4096);
+              tma_load_2d(ebuf + (b ^ 1) * 4096, &em.r32, &rf[b ^ 1], nn, m0);
+            }
+          }
+          __syncwarp();
+          const uint32_t buf = smem_u32(ebuf + b * 4096);
+          if (has_r) {
+            mbar_wait(&rf[b], (rphase >> b) & 1u);
+            rphase ^= 1u << b;
+          }
+          tmem_ld_wait();
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (n0 + 4 * j < N) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+                v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
+              }
+            }
+          }
+          if (has_r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = lds_f4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)));
+              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            }
+          }
+          if (ep.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts_f4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&em.o32, ebuf + b * 4096, n0, m0);
+              bulk_commit();
+              if (ep.out_bf16) bulk_wait_read<0>();  // the mirror below reuses the buffer
+            }
+            __syncwarp();
+          }
+          if (ep.out_bf16) {
+            __syncwarp();  // bf16 row t overlays the residual rows t / 2 of other lanes: every lane has read its row
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              const uint2 lo = pack4_bf16(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]);
+              const uint2 hi = pack4_bf16(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]);
+              pk.x = lo.x; pk.y = lo.y; pk.z = hi.x; pk.w = hi.y;
+              sts_u4(buf + (uint32_t)(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)), pk);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&em.o16, ebuf + b * 4096, n0, m0);
+              bulk_commit();
+            }
+          }
+          ++ci;
+        }
+        if (first) {  // no chunk of this tile belongs to the warp (N edge): still follow the accumulator hand-shake in step
+          mbar_wait(&tfull[acc], acc_phase);
+          tc_fence_after();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (lane == 0) bulk_wait_all();
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_t = tile % tiles_n;
       const int m_t = (tile / tiles_n) % tiles_m;
@@ -408,6 +538,24 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long rows, long long col
   return 0;
 }
 
+int make_tmap_epi(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int elem_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  DCPT_CHECK_ARG(fn != nullptr, DCPT_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  DCPT_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * elem_bytes) % 16 == 0, DCPT_E_ALIGN,
+                 "GEMM epilogue tensor must be 16-byte aligned with a 16-byte row pitch (ptr=%p ld=%lld)", ptr, ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCPT_CHECK_ARG(r == CUDA_SUCCESS, DCPT_E_DRIVER, "cuTensorMapEncodeTiled(epilogue) failed (%d): rows=%lld cols=%lld ld=%lld", (int)r,
+                 rows, cols, ld);
+  return 0;
+}
+
 int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h, int swizzle128) {
   EncodeTiledFn fn = get_encode_fn();
   DCPT_CHECK_ARG(fn != nullptr, DCPT_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
@@ -430,8 +578,15 @@ namespace {
 template <int BN, int EPI, bool A_MN, bool B_MN>
 int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   const ConvGeom cg0 = {};
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
   CUtensorMap tmA, tmB;
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  if constexpr (EPI == EPI_STORE_TMA) {
+    if (g.ep.out_f32) DCPT_TRY(make_tmap_epi(&em.o32, g.ep.out_f32, g.M, g.N, g.ep.ldo, 4));
+    if (g.ep.out_bf16) DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, g.N, g.ep.ldo, 2));
+    if (g.ep.resid) DCPT_TRY(make_tmap_epi(&em.r32, g.ep.resid, g.M, g.N, g.ep.ldr, 4));
+  }
   if (!g.a_mn) DCPT_TRY(make_tmap_2d(&tmA, g.A, g.M, g.K, g.lda, BM));
   else DCPT_TRY(make_tmap_2d(&tmA, g.A, g.K, g.M, g.lda, 64));
   if (!g.b_mn) DCPT_TRY(make_tmap_2d(&tmB, g.B, g.N, g.K, g.ldb, BN));
@@ -454,7 +609,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   }
   static char base_tag[48] = "";
   if (!base_tag[0]) {
-    static const char* epi_names[] = {"store", "gate", "gate_bwd", "pixshuf", "atomic"};
+    static const char* epi_names[] = {"store", "gate", "gate_bwd", "pixshuf", "atomic", "store_tma"};
     snprintf(base_tag, sizeof(base_tag), "gemm_tc<%d,%s,%s>", BN, epi_names[EPI], A_MN ? "mn" : "k");
   }
   const char* tag = base_tag;
@@ -466,7 +621,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   const double out_bytes = (double)g.M * g.N * ((g.ep.out_f32 ? 4.0 : 0.0) + (g.ep.out_bf16 ? 2.0 : 0.0) + (g.ep.resid ? 4.0 : 0.0) +
                                                 (EPI == EPI_GATE ? 1.0 : 0.0) + (EPI == EPI_GATE_BWD ? 4.0 : 0.0));
   DCPT_PROF(tag, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes, stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, g.M, g.N, g.K, tiles_m, tiles_n, splits, kbps, g.ep, cg0);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, g.M, g.N, g.K, tiles_m, tiles_n, splits, kbps, g.ep, cg0);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -492,7 +647,9 @@ ConvGeom conv_geom(int H, int W, int cin_pad, int rows_per_tile) {
 
 template <int BN>
 int conv_fwd_cfg(const Conv3x3Args& a, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI_STORE>;
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
   const int cin_pad = ceil_div(a.Cin, 64) * 64;
   const ConvGeom cg = conv_geom(a.H, a.W, cin_pad, BM);
   CUtensorMap tmA, tmB;
@@ -510,14 +667,16 @@ int conv_fwd_cfg(const Conv3x3Args& a, cudaStream_t stream) {
   const double Mpx = (double)a.N * a.H * a.W;
   DCPT_PROF(BN == 256 ? "conv3x3_tc<256>" : (BN == 128 ? "conv3x3_tc<128>" : "conv3x3_tc<64>"), 2.0 * Mpx * a.Cout * 9 * a.Cin,
             2.0 * Mpx * (a.Cin + a.Cout), stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, a.N * a.H * a.W, a.Cout, num_kb * BK, tiles_m, tiles_n, 1, num_kb, a.ep, cg);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, a.N * a.H * a.W, a.Cout, num_kb * BK, tiles_m, tiles_n, 1, num_kb, a.ep, cg);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
 
 template <int BN>
 int conv_wgrad_cfg(const bf16* dY, const bf16* X, float* G, int N, int H, int W, int Cin, int Cout, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI_ATOMIC>;
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
   const int cin_pad = ceil_div(Cin, 64) * 64;
   const ConvGeom cg = conv_geom(H, W, cin_pad, 64);
   CUtensorMap tmA, tmB;
@@ -540,7 +699,7 @@ int conv_wgrad_cfg(const bf16* dY, const bf16* X, float* G, int N, int H, int W,
   }
   const double Mpx = (double)N * H * W;
   DCPT_PROF("conv3x3_wgrad_tc", 2.0 * Mpx * Cout * 9 * Cin, 2.0 * Mpx * (Cin + Cout), stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, Cout, 9 * cin_pad, num_kb * BK, tiles_m, tiles_n, splits, kbps, ep, cg);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, Cout, 9 * cin_pad, num_kb * BK, tiles_m, tiles_n, splits, kbps, ep, cg);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -578,7 +737,15 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     return launch_bn<EPI_ATOMIC, true, true>(g, stream);
   }
   switch (g.epi) {
-    case EPI_STORE: return launch_bn<EPI_STORE, false, false>(g, stream);
+    case EPI_STORE: {
+      // TMA epilogue whenever the output / residual rows are 16-byte pitched (always true on the hot path)
+      static const bool no_tma = getenv("DCPT_GEMM_NO_TMA_EPI") != nullptr;
+      auto ok = [](const void* p, long long ld, int eb) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * eb) % 16 == 0); };
+      const bool tma = !no_tma && (g.ep.out_f32 || g.ep.out_bf16) && ok(g.ep.out_f32, g.ep.ldo, 4) && ok(g.ep.out_bf16, g.ep.ldo, 2) &&
+                       ok(g.ep.resid, g.ep.ldr, 4) && (g.ep.bias == nullptr || (reinterpret_cast<uintptr_t>(g.ep.bias) & 15) == 0);
+      if (tma) return launch_bn<EPI_STORE_TMA, false, false>(g, stream);
+      return launch_bn<EPI_STORE, false, false>(g, stream);
+    }
     case EPI_GATE: return launch_bn<EPI_GATE, false, false>(g, stream);
     case EPI_GATE_BWD: return launch_bn<EPI_GATE_BWD, false, false>(g, stream);
     case EPI_PIXSHUF: return launch_bn<EPI_PIXSHUF, false, false>(g, stream);

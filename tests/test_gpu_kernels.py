@@ -36,7 +36,7 @@ def bf(t):
 
 # ------------------------------------------------------------------ GEMM engine
 GEMM_SHAPES = [(128, 64, 64), (256, 128, 64), (384, 256, 128), (1000, 512, 512), (4096, 1024, 512), (130, 72, 40),
-               (64, 16, 8), (16384, 128, 64)]
+               (64, 16, 8), (16384, 128, 64), (40000, 264, 72), (33000, 512, 256)]
 
 
 @pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
@@ -54,6 +54,31 @@ def test_gemm_store(ops, impl, M, N, K):
     assert rel(out, ref + bias + resid) < 2e-5
     out = ops.gemm(A, B, bias=bias, impl=impl)
     assert out.dtype == torch.bfloat16 and rel(out.float(), ref + bias) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 512), (130, 72, 40), (33000, 96, 48)])
+def test_gemm_store_both_outputs(ops, M, N, K):
+    """fp32 output + bf16 mirror + residual in one launch (the level-boundary GEMMs of the networks)."""
+    from dcpt_b200.lib import GemmDesc
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = bf(torch.randn(M, K, device="cuda", generator=g))
+    B = bf(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    d = GemmDesc()
+    for k, v in dict(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=o32, out_bf16=o16, ldo=N, bias=bias,
+                     resid=resid, ldr=N).items():
+        setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+    ops.gemm_ex(d)
+    ref = A.float() @ B.float().t() + bias + resid
+    assert rel(o32, ref) < 2e-5 and rel(o16.float(), ref) < 4e-3
+    # bf16 output with a residual and no fp32 output
+    d.out_f32 = None
+    o16.zero_()
+    ops.gemm_ex(d)
+    assert rel(o16.float(), ref) < 4e-3
 
 
 WGRAD_SHAPES = [(128, 64, 4096), (256, 128, 1000), (1024, 512, 16384), (64, 64, 65536), (16, 8, 200), (512, 2048, 4096)]

@@ -194,15 +194,18 @@ def test_restormer_full_vs_oracle():
     print(f"Restormer 128x128, reference init: rel-L2 of (out - inp) {e0:.2e}, of out {rel(out0, ref0):.2e}, "
           f"|dPSNR| {abs(psnr_db(out0, gt) - psnr_db(ref0, gt)):.5f} dB")
     assert rel(out0, ref0) < 1e-3 and e0 < 2e-2 and abs(psnr_db(out0, gt) - psnr_db(ref0, gt)) < 0.01
-    # batch independence (per-image attention statistics): a batch of two equals two single runs (up to the order of the
-    # split-K atomics; checked on the well-conditioned weights - under (b) a 1e-7 perturbation grows to 1e-2)
+    # batch independence (per-image attention statistics): a batch of two equals two single runs up to the bf16 rounding
+    # noise floor.  Two runs are never bit-identical (split-K fp32 atomics differ by ~1e-7), and a 1e-7 perturbation is
+    # enough to decorrelate the bf16 rounding decisions of 48 blocks: the CPU oracle with bf16 rounding hooks moves by the
+    # same 1e-4 (out) / 2.6e-3 (out - inp) under a 1e-7 input perturbation, while the exact fp32 oracle moves by 1e-7.
     inp2 = torch.cat([inp, torch.rand(1, 3, 128, 128, generator=g)], 0).cuda()
     with torch.no_grad():
         o2 = net(inp2)
         o1 = net(inp2[1:2].contiguous())
-    eb = max(rel(o2[0:1].cpu() - inp, out0 - inp), rel((o2[1:2] - inp2[1:2]), (o1 - inp2[1:2])))
-    print(f"Restormer batch independence: rel-L2 of (out - inp) {eb:.2e}")
-    assert eb < 2e-3
+    eb = max(rel(o2[0:1].cpu(), out0), rel(o2[1:2], o1))
+    ebd = max(rel(o2[0:1].cpu() - inp, out0 - inp), rel((o2[1:2] - inp2[1:2]), (o1 - inp2[1:2])))
+    print(f"Restormer batch independence: rel-L2 of out {eb:.2e}, of (out - inp) {ebd:.2e}")
+    assert eb < 5e-4 and ebd < 1e-2
     # (b)
     sd = RO.random_restormer_state_dict(seed=11, gain=0.7, **cfg)
     net.load_state_dict(sd, strict=True)
