@@ -487,7 +487,7 @@ int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, 
   DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
   const size_t smem = 128 + (size_t)2 * 2 * BOX_BYTES;
   DCPT_TRY(set_smem(dwgate_fwd_kernel<0>, smem));
-  DCPT_PROF("dwgate_fwd", 38.0 * N * H * W * C, 6.0 * N * H * W * C, st);
+  DCPT_PROF(dcpt_prof_tag2("dwgate_fwd", (long long)N * H * W, C), 38.0 * N * H * W * C, 6.0 * N * H * W * C, st);
   dwgate_fwd_kernel<0><<<pick_grid(N, H, W, C, 2), NWARP * 32, smem, st>>>(tmU, w2, b2, g, pool, N, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -526,7 +526,7 @@ int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const b
   DCPT_TRY(make_tmap_nhwc(&tmD, dgs, N, H, W, C, TW, TH));
   const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
   DCPT_TRY(set_smem(dwgate_bwd_a_kernel, smem));
-  DCPT_PROF("dwgate_bwd_a", 80.0 * N * H * W * C, 10.0 * N * H * W * C, st);
+  DCPT_PROF(dcpt_prof_tag2("dwgate_bwd_a", (long long)N * H * W, C), 80.0 * N * H * W * C, 10.0 * N * H * W * C, st);
   dwgate_bwd_a_kernel<<<pick_grid(N, H, W, C, 1), NWARP * 32, smem, st>>>(tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
@@ -539,7 +539,7 @@ int dwconv_bwd_data_launch(const bf16* du2, const float* w2, bf16* du, float* co
   DCPT_TRY(make_tmap_nhwc(&tmG, du2, N, H, W, C2, HWD, HH));
   const size_t smem = 128 + (size_t)2 * BOX_BYTES;
   DCPT_TRY(set_smem(dwconv_bwd_data_kernel, smem));
-  DCPT_PROF("dwconv_bwd_data", 18.0 * N * H * W * C2, 4.0 * N * H * W * C2, st);
+  DCPT_PROF(dcpt_prof_tag2("dwconv_bwd_data", (long long)N * H * W, C2), 18.0 * N * H * W * C2, 4.0 * N * H * W * C2, st);
   dwconv_bwd_data_kernel<<<pick_grid(N, H, W, C2, 4), NWARP * 32, smem, st>>>(tmG, w2, du, colsum, N, H, W, C2);
   DCPT_LAUNCH_CHECK();
   return 0;

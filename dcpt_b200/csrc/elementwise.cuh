@@ -45,7 +45,7 @@ int cast_f32_bf16_launch(const float* x, bf16* y, long long n, cudaStream_t st);
 int unshuffle_cast_launch(const float* x, bf16* y, int N, int H, int W, int C, cudaStream_t st);
 
 // Weight packing (fp32 parameter -> bf16 GEMM operand), see nafnet.cu for the modes.
-enum PackMode { PACK_PLAIN = 0, PACK_T = 1, PACK_PAIR = 2, PACK_UP = 3, PACK_UP_T = 4, PACK_DOWN = 5, PACK_DOWN_T = 6 };
+enum PackMode { PACK_PLAIN = 0, PACK_T = 1, PACK_PAIR = 2, PACK_UP = 3, PACK_UP_T = 4, PACK_DOWN = 5, PACK_DOWN_T = 6, PACK_PAIR32 = 7 };
 int pack_weight_launch(const float* w, const float* row_scale, bf16* out, int O, int I, int mode, cudaStream_t st);
 // small fp32 vectors: out[p] = bias[src(p)] * scale[src(p)] (mode PACK_PLAIN or PACK_PAIR)
 int pack_bias_launch(const float* bias, const float* scale, float* out, int O, int mode, cudaStream_t st);

@@ -18,6 +18,8 @@ enum GemmEpilogue {
   EPI_PIXSHUF = 3,   // pixel-shuffle(2) scatter + residual add -> fp32 (+bf16 mirror)
   EPI_ATOMIC = 4,    // split-K wgrad: red.add.f32 into out_f32
   EPI_STORE_TMA = 5, // internal: EPI_STORE with the residual tile TMA-loaded and the output tile TMA-stored (gemm_sm100.cu)
+  EPI_GATE_BWD_TMA = 6,  // internal: EPI_GATE_BWD with x4 tiles TMA-loaded and d(x4) tiles TMA-stored (C % 32 == 0)
+  EPI_GATE_TMA = 7,      // internal: EPI_GATE on 32-wide pair packing (PACK_PAIR32), x4 / sg tiles TMA-stored (C % 32 == 0)
 };
 
 struct EpiParams {

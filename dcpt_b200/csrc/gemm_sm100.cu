@@ -22,7 +22,9 @@
 namespace {
 
 struct EpiMaps {
-  CUtensorMap o32, o16, r32;  // fp32 output, bf16 output, fp32 residual (EPI_STORE_TMA; unused otherwise)
+  // EPI_STORE_TMA: fp32 output, bf16 output, fp32 residual.  EPI_GATE_BWD_TMA: o16 = d(x4), r32 = x4 (bf16 [M, 2C]).
+  // EPI_GATE_TMA: o16 = x4 (bf16 [M, 2C]), o2 = sg (bf16 [M, C]).  Unused by the register-staged epilogues.
+  CUtensorMap o32, o16, r32, o2;
 };
 
 constexpr int BM = 128;
@@ -34,7 +36,7 @@ constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 // runs with one pipeline stage fewer than the register-staged epilogues (one 4 KiB transpose tile per warp).
 template <int BN, int EPI>
 struct Cfg {
-  static constexpr bool TMA_EPI = EPI == EPI_STORE_TMA;
+  static constexpr bool TMA_EPI = EPI == EPI_STORE_TMA || EPI == EPI_GATE_BWD_TMA || EPI == EPI_GATE_TMA;
   static constexpr int STAGES = TMA_EPI ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -105,6 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&em.o32);
       tma_prefetch_desc(&em.o16);
       tma_prefetch_desc(&em.r32);
+      tma_prefetch_desc(&em.o2);
     }
     fence_mbar_init();
   }
@@ -257,7 +260,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint64_t* rf = rfull + ew * 2;
       uint32_t rphase = 0;  // bit b: parity of the next completion of rf[b]
       int ci = 0;           // chunks handled by this warp so far (buffer = ci & 1)
-      const bool has_r = ep.resid != nullptr;
+      const bool has_r = EPI == EPI_GATE_BWD_TMA || (EPI == EPI_STORE_TMA && ep.resid != nullptr);
+      // the epilogue's input tile(s) of chunk n0 of row slab m0 -> 4 KiB buffer: one fp32 residual box, or the two bf16
+      // x4 boxes (columns n0 and C + n0) of the SimpleGate backward
+      auto issue_in = [&](uint8_t* dst, uint64_t* bar, int n0, int m0) {
+        mbar_arrive_expect_tx(bar, 4096);
+        if constexpr (EPI == EPI_GATE_BWD_TMA) {
+          tma_load_2d(dst, &em.r32, bar, n0, m0);
+          tma_load_2d(dst + 2048, &em.r32, bar, ep.C + n0, m0);
+        } else {
+          tma_load_2d(dst, &em.r32, bar, n0, m0);
+        }
+      };
+      if constexpr (EPI == EPI_GATE_TMA) {
+        // ---- SimpleGate forward on 32-wide pair packing: accumulator chunks (2p, 2p + 1) = (a, b) halves of channels
+        // [32p, 32p + 32): x4[:, 32p..] = a, x4[:, C + 32p..] = b, sg[:, 32p..] = a * b (all bf16, rounded before the product
+        // like the register-staged epilogue).  A warp takes alternate chunk PAIRS; three 2 KiB tiles per pair.
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int n_t = tile % tiles_n;
+          const int m_t = (tile / tiles_n) % tiles_m;
+          const int m0 = m_t * BM + q * 32;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+          mbar_wait(&tfull[acc], acc_phase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int pr = chalf; pr < BN / 64; pr += 2) {
+            const int n0 = n_t * BN + pr * 64;  // packed column of the a-chunk
+            if (n0 >= N) break;                 // warp-uniform
+            const int j0 = n0 >> 1;             // first channel of the pair
+            float va[32], vb[32];
+            tmem_ld32(taddr + pr * 64, va);
+            tmem_ld32(taddr + pr * 64 + 32, vb);
+            if (lane == 0) bulk_wait_read<0>();  // previous stores of this warp have drained the buffers
+            __syncwarp();
+            tmem_ld_wait();
+            const uint32_t buf = smem_u32(ebuf);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a[8], b[8];
+#pragma unroll
+              for (int k = 0; k < 8; k += 4) {
+                const float4 ba = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + 8 * j + k));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + 32 + 8 * j + k));
+                a[k] = bf16_round(va[8 * j + k] + ba.x); a[k + 1] = bf16_round(va[8 * j + k + 1] + ba.y);
+                a[k + 2] = bf16_round(va[8 * j + k + 2] + ba.z); a[k + 3] = bf16_round(va[8 * j + k + 3] + ba.w);
+                b[k] = bf16_round(vb[8 * j + k] + bb.x); b[k + 1] = bf16_round(vb[8 * j + k + 1] + bb.y);
+                b[k + 2] = bf16_round(vb[8 * j + k + 2] + bb.z); b[k + 3] = bf16_round(vb[8 * j + k + 3] + bb.w);
+              }
+              float sgv[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) sgv[k] = a[k] * b[k];
+              const uint32_t off = (uint32_t)(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+              sts_u4(buf + off, pack8(a));
+              sts_u4(buf + 2048 + off, pack8(b));
+              sts_u4(buf + 4096 + off, pack8(sgv));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&em.o16, ebuf, j0, m0);
+              tma_store_2d(&em.o16, ebuf + 2048, ep.C + j0, m0);
+              tma_store_2d(&em.o2, ebuf + 4096, j0, m0);
+              bulk_commit();
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_t = tile % tiles_n;
         const int m_t = (tile / tiles_n) % tiles_m;
@@ -272,10 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (first) {
             if (lane == 0) {
               bulk_wait_read<0>();
-              if (has_r) {
-                mbar_arrive_expect_tx(&rf[b], 4096);
-                tma_load_2d(ebuf + b * 4096, &em.r32, &rf[b], n0, m0);
-              }
+              if (has_r) issue_in(ebuf + b * 4096, &rf[b], n0, m0);
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
@@ -286,10 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) {
             bulk_wait_read<0>();  // the store that read buffer b ^ 1 (previous chunk) has drained it
             const int nn = n0 + 64;
-            if (has_r && c + 2 < BN / 32 && nn < N) {
-              mbar_arrive_expect_tx(&rf[b ^ 1], 4096);
-              tma_load_2d(ebuf + (b ^ 1) * 4096, &em.r32, &rf[b ^ 1], nn, m0);
-            }
+            if (has_r && c + 2 < BN / 32 && nn < N) issue_in(ebuf + (b ^ 1) * 4096, &rf[b ^ 1], nn, m0);
           }
           __syncwarp();
           const uint32_t buf = smem_u32(ebuf + b * 4096);
@@ -298,6 +367,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             rphase ^= 1u << b;
           }
           tmem_ld_wait();
+          if constexpr (EPI == EPI_GATE_BWD_TMA) {
+            // d(x4)[:, n] = d(sg) * x4[:, C + n],  d(x4)[:, C + n] = d(sg) * x4[:, n]  (nafnet_arch.py:77-80), in place
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t off = (uint32_t)(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+              float xa[8], xb[8], da[8], db[8];
+              const float4 ra = lds_f4(buf + off), rb = lds_f4(buf + 2048 + off);
+              unpack8(*reinterpret_cast<const uint4*>(&ra), xa);
+              unpack8(*reinterpret_cast<const uint4*>(&rb), xb);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                da[k] = v[8 * j + k] * xb[k];
+                db[k] = v[8 * j + k] * xa[k];
+              }
+              sts_u4(buf + off, pack8(da));
+              sts_u4(buf + 2048 + off, pack8(db));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&em.o16, ebuf + b * 4096, n0, m0);
+              tma_store_2d(&em.o16, ebuf + b * 4096 + 2048, ep.C + n0, m0);
+              bulk_commit();
+            }
+            ++ci;
+            continue;
+          }
           if (ep.bias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -586,6 +682,12 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     if (g.ep.out_f32) DCPT_TRY(make_tmap_epi(&em.o32, g.ep.out_f32, g.M, g.N, g.ep.ldo, 4));
     if (g.ep.out_bf16) DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, g.N, g.ep.ldo, 2));
     if (g.ep.resid) DCPT_TRY(make_tmap_epi(&em.r32, g.ep.resid, g.M, g.N, g.ep.ldr, 4));
+  } else if constexpr (EPI == EPI_GATE_BWD_TMA) {
+    DCPT_TRY(make_tmap_epi(&em.r32, g.ep.aux, g.M, 2 * g.ep.C, g.ep.ldaux, 2));
+    DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, 2 * g.ep.C, g.ep.ldo, 2));
+  } else if constexpr (EPI == EPI_GATE_TMA) {
+    DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, 2 * g.ep.C, g.ep.ldo, 2));
+    DCPT_TRY(make_tmap_epi(&em.o2, g.ep.out2, g.M, g.ep.C, g.ep.ldo2, 2));
   }
   if (!g.a_mn) DCPT_TRY(make_tmap_2d(&tmA, g.A, g.M, g.K, g.lda, BM));
   else DCPT_TRY(make_tmap_2d(&tmA, g.A, g.K, g.M, g.lda, 64));
@@ -609,7 +711,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   }
   static char base_tag[48] = "";
   if (!base_tag[0]) {
-    static const char* epi_names[] = {"store", "gate", "gate_bwd", "pixshuf", "atomic", "store_tma"};
+    static const char* epi_names[] = {"store", "gate", "gate_bwd", "pixshuf", "atomic", "store_tma", "gate_bwd_tma", "gate_tma"};
     snprintf(base_tag, sizeof(base_tag), "gemm_tc<%d,%s,%s>", BN, epi_names[EPI], A_MN ? "mn" : "k");
   }
   const char* tag = base_tag;
@@ -619,7 +721,8 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     tag = dcpt_prof_intern(buf);
   }
   const double out_bytes = (double)g.M * g.N * ((g.ep.out_f32 ? 4.0 : 0.0) + (g.ep.out_bf16 ? 2.0 : 0.0) + (g.ep.resid ? 4.0 : 0.0) +
-                                                (EPI == EPI_GATE ? 1.0 : 0.0) + (EPI == EPI_GATE_BWD ? 4.0 : 0.0));
+                                                (EPI == EPI_GATE || EPI == EPI_GATE_TMA ? 1.0 : 0.0) +
+                                                (EPI == EPI_GATE_BWD || EPI == EPI_GATE_BWD_TMA ? 4.0 : 0.0));
   DCPT_PROF(tag, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes, stream);
   kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, g.M, g.N, g.K, tiles_m, tiles_n, splits, kbps, g.ep, cg0);
   DCPT_LAUNCH_CHECK();
@@ -747,7 +850,17 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
       return launch_bn<EPI_STORE, false, false>(g, stream);
     }
     case EPI_GATE: return launch_bn<EPI_GATE, false, false>(g, stream);
-    case EPI_GATE_BWD: return launch_bn<EPI_GATE_BWD, false, false>(g, stream);
+    case EPI_GATE_TMA:  // SimpleGate forward on 32-wide pair packing (PACK_PAIR32 weights / bias)
+      DCPT_CHECK_ARG(g.ep.C % 32 == 0 && g.N == 2 * g.ep.C && g.ep.bias && g.ep.out_bf16 && g.ep.out2, DCPT_E_ARG,
+                     "gemm: the 32-wide gate epilogue needs C %% 32 == 0, N = 2C, bias and both outputs (C=%d N=%d)", g.ep.C, g.N);
+      return launch_bn<EPI_GATE_TMA, false, false>(g, stream);
+    case EPI_GATE_BWD: {
+      static const bool no_tma = getenv("DCPT_GEMM_NO_TMA_EPI") != nullptr;
+      if (!no_tma && g.ep.C % 32 == 0 && g.N == g.ep.C && (g.ep.ldo % 8) == 0 && (g.ep.ldaux % 8) == 0 &&
+          ((reinterpret_cast<uintptr_t>(g.ep.out_bf16) | reinterpret_cast<uintptr_t>(g.ep.aux)) & 15) == 0)
+        return launch_bn<EPI_GATE_BWD_TMA, false, false>(g, stream);
+      return launch_bn<EPI_GATE_BWD, false, false>(g, stream);
+    }
     case EPI_PIXSHUF: return launch_bn<EPI_PIXSHUF, false, false>(g, stream);
     case EPI_ATOMIC: return launch_bn<EPI_ATOMIC, false, false>(g, stream);
   }

@@ -5,6 +5,8 @@
 // One row (pixel) is owned by `lpr` lanes of a warp (lpr = 2..32, power of two), so the
 // reductions over C are xor-shuffles; each lane keeps its NV float4 slices in registers.
 // HBM-bound: fwd reads 4C and writes 2C (+8) bytes per pixel.
+#include <stdlib.h>
+
 #include "elementwise.cuh"
 
 namespace {
@@ -188,6 +190,126 @@ ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const fl
   }
 }
 
+// ---- wide rows (C >= 512): bulk-copy pipelined backward ----
+// With one warp per 2-4 KB row the register-resident kernel above keeps only ~16 rows per SM in flight and its
+// per-row load -> reduce -> store chain is exposed (3.2 TB/s at C = 512, 16 K rows).  Here a CTA streams tiles of R
+// consecutive rows (x, dres, dn are contiguous in memory: three 1-D bulk copies per tile, completion on an mbarrier)
+// through a two-stage shared-memory ring, 8 warps x 1 row per tile, 2 CTAs per SM: ~160 KB per SM is always in flight
+// and the warps read their operands from shared memory.
+template <int NV>
+__global__ void __launch_bounds__(256, 2)
+ln_bwd_wide_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ stats,
+                   const float* __restrict__ w, const float* __restrict__ dres, float* __restrict__ dx, bf16* __restrict__ dx_bf16,
+                   float* __restrict__ dw, float* __restrict__ db, float* __restrict__ colsum, int M, int C, int R) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  __shared__ uint64_t full[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t xb = (uint32_t)R * C * 4, nb = (uint32_t)R * C * 2;
+  const uint32_t stage_bytes = 2 * xb + nb;  // [x | dres | dn]
+  float* s_acc = reinterpret_cast<float*>(smem + 2 * stage_bytes);  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_acc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int tiles = (M + R - 1) / R;
+  auto issue = [&](int t, int s) {
+    const int r0 = t * R;
+    const int valid = min(R, M - r0);
+    uint8_t* dst = smem + (size_t)s * stage_bytes;
+    const uint32_t vx = (uint32_t)valid * C * 4, vn = (uint32_t)valid * C * 2;
+    mbar_arrive_expect_tx(&full[s], vx + (dres ? vx : 0u) + vn);
+    bulk_load_1d(dst, x + (size_t)r0 * C, vx, &full[s]);
+    if (dres) bulk_load_1d(dst + xb, dres + (size_t)r0 * C, vx, &full[s]);
+    bulk_load_1d(dst + 2 * xb, dn + (size_t)r0 * C, vn, &full[s]);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < tiles) issue(blockIdx.x, 0);
+  const float invC = 1.f / (float)C;
+  float4 wv[NV], a_dw[NV], a_db[NV], a_cs[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    wv[i] = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+    a_dw[i] = a_db[i] = a_cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+    const int s = it & 1;
+    if (threadIdx.x == 0 && t + (int)gridDim.x < tiles) issue(t + gridDim.x, s ^ 1);
+    const long long row = (long long)t * R + warp;
+    const bool valid = warp < R && row < M;
+    float2 st = make_float2(0.f, 0.f);
+    if (valid) st = __ldg(reinterpret_cast<const float2*>(stats + row * 2));
+    mbar_wait(&full[s], (it >> 1) & 1);
+    if (valid) {
+      const uint8_t* base = smem + (size_t)s * stage_bytes;
+      const float4* sx = reinterpret_cast<const float4*>(base) + (size_t)warp * (C >> 2);
+      const float4* sr = reinterpret_cast<const float4*>(base + xb) + (size_t)warp * (C >> 2);
+      const uint2* sd = reinterpret_cast<const uint2*>(base + 2 * xb) + (size_t)warp * (C >> 2);
+      const float mean = st.x, rstd = st.y;
+      float4 yh[NV], g[NV];
+      float sg = 0.f, sgy = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+        const float4 xv = sx[v];
+        const uint2 pk = sd[v];
+        const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+        const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+        yh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[i] = make_float4(d01.x * wv[i].x, d01.y * wv[i].y, d23.x * wv[i].z, d23.y * wv[i].w);
+        sg += g[i].x + g[i].y + g[i].z + g[i].w;
+        sgy += g[i].x * yh[i].x + g[i].y * yh[i].y + g[i].z * yh[i].z + g[i].w * yh[i].w;
+        a_dw[i].x += d01.x * yh[i].x; a_dw[i].y += d01.y * yh[i].y; a_dw[i].z += d23.x * yh[i].z; a_dw[i].w += d23.y * yh[i].w;
+        a_db[i].x += d01.x; a_db[i].y += d01.y; a_db[i].z += d23.x; a_db[i].w += d23.y;
+      }
+      const float mean_g = warp_sum(sg) * invC;
+      const float mean_gy = warp_sum(sgy) * invC;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+        float4 o;
+        o.x = rstd * (g[i].x - yh[i].x * mean_gy - mean_g);
+        o.y = rstd * (g[i].y - yh[i].y * mean_gy - mean_g);
+        o.z = rstd * (g[i].z - yh[i].z * mean_gy - mean_g);
+        o.w = rstd * (g[i].w - yh[i].w * mean_gy - mean_g);
+        if (dres) {
+          const float4 rs = sr[v];
+          o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+        }
+        *(reinterpret_cast<float4*>(dx + row * C) + v) = o;
+        if (dx_bf16) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          *(reinterpret_cast<uint2*>(dx_bf16 + row * C) + v) = pk;
+        }
+        a_cs[i].x += o.x; a_cs[i].y += o.y; a_cs[i].z += o.z; a_cs[i].w += o.w;
+      }
+    }
+    __syncthreads();  // stage s is refilled by the next-but-one issue
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    atomicAdd(&s_acc[c + 0], a_dw[i].x); atomicAdd(&s_acc[c + 1], a_dw[i].y);
+    atomicAdd(&s_acc[c + 2], a_dw[i].z); atomicAdd(&s_acc[c + 3], a_dw[i].w);
+    atomicAdd(&s_acc[C + c + 0], a_db[i].x); atomicAdd(&s_acc[C + c + 1], a_db[i].y);
+    atomicAdd(&s_acc[C + c + 2], a_db[i].z); atomicAdd(&s_acc[C + c + 3], a_db[i].w);
+    atomicAdd(&s_acc[2 * C + c + 0], a_cs[i].x); atomicAdd(&s_acc[2 * C + c + 1], a_cs[i].y);
+    atomicAdd(&s_acc[2 * C + c + 2], a_cs[i].z); atomicAdd(&s_acc[2 * C + c + 3], a_cs[i].w);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (dw) atomicAdd(dw + c, s_acc[c]);
+    if (db) atomicAdd(db + c, s_acc[C + c]);
+    if (colsum) atomicAdd(colsum + c, s_acc[2 * C + c]);
+  }
+}
+
 inline int pick_lpr(int C) {
   const int nvec = C / 4;
   int lpr = 2;
@@ -205,7 +327,7 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
   const int nv = ceil_div(C / 4, lpr);
   const int rows_per_block = kWarps * (32 / lpr);
   const int grid = (int)ceil_div_ll(M, rows_per_block);
-  DCPT_PROF("ln_fwd", 8.0 * M * C, 6.0 * M * C, st);
+  DCPT_PROF(dcpt_prof_tag2("ln_fwd", M, C), 8.0 * M * C, 6.0 * M * C, st);
 #define LN_FWD(NVV) ln_fwd_kernel<NVV><<<grid, kWarps * 32, 0, st>>>(x, w, b, n_out, stats, M, C, lpr, eps, center)
   if (nv <= 1) LN_FWD(1);
   else if (nv <= 2) LN_FWD(2);
@@ -219,6 +341,21 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
 int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const float* w, const float* dres, float* dx,
                   bf16* dx_bf16, float* dw, float* db, float* colsum, int M, int C, cudaStream_t st) {
   DCPT_CHECK_ARG(M > 0 && C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "layernorm bwd: need C %% 8 == 0 and 8 <= C <= 1024 (C=%d)", C);
+  if (C == 512 && M >= 2048 && getenv("DCPT_LN_BWD_NARROW") == nullptr) {
+    const int R = 8;  // rows per tile: 40 KB per stage
+    const size_t smem = 128 + (size_t)2 * R * C * 10 + (size_t)3 * C * sizeof(float);
+    const int tiles = ceil_div(M, R);
+    int grid = 2 * dcpt_num_sms();
+    if (grid > tiles) grid = tiles;
+    DCPT_PROF(dcpt_prof_tag2("ln_bwd", M, C), 20.0 * M * C, (2.0 + 4.0 + (dres ? 4.0 : 0.0) + 4.0 + (dx_bf16 ? 2.0 : 0.0)) * M * C, st);
+    if (C == 512) {
+      static bool once = false;
+      if (!once) { DCPT_CUDA(cudaFuncSetAttribute(ln_bwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
+      ln_bwd_wide_kernel<4><<<grid, 256, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, R);
+    }
+    DCPT_LAUNCH_CHECK();
+    return 0;
+  }
   const int lpr = pick_lpr(C);
   const int nv = ceil_div(C / 4, lpr);
   const int warps = nv <= 2 ? 16 : 4;
@@ -227,7 +364,7 @@ int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const floa
   const long long cap = (long long)dcpt_num_sms() * (nv <= 1 ? 2 : (nv <= 2 ? 1 : (nv <= 4 ? 4 : 2)));  // resident blocks / SM
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)3 * C * sizeof(float);
-  DCPT_PROF("ln_bwd", 20.0 * M * C, (2.0 + 4.0 + (dres ? 4.0 : 0.0) + 4.0 + (dx_bf16 ? 2.0 : 0.0)) * M * C, st);
+  DCPT_PROF(dcpt_prof_tag2("ln_bwd", M, C), 20.0 * M * C, (2.0 + 4.0 + (dres ? 4.0 : 0.0) + 4.0 + (dx_bf16 ? 2.0 : 0.0)) * M * C, st);
 #define LN_BWD(NVV, WW, MB) \
   ln_bwd_kernel<NVV, WW, MB><<<(int)grid, WW * 32, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr)
   if (nv <= 1) LN_BWD(1, 16, 2);

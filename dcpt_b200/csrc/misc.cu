@@ -176,6 +176,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
       const int p = (int)(idx / I); i = (int)(idx % I);
       o = ((p & 15) >> 3) * (O >> 1) + (p >> 4) * 8 + (p & 7);
     } break;
+    case PACK_PAIR32: {  // out[p][i], p = 64*pp + h*32 + e  <->  o = h*C + 32*pp + e  (C = O/2, C % 32 == 0)
+      const int p = (int)(idx / I); i = (int)(idx % I);
+      o = ((p & 63) >> 5) * (O >> 1) + (p >> 6) * 32 + (p & 31);
+    } break;
     case PACK_UP: {  // out[p][i], p = q*Cseg + c'  <->  o = c'*4 + q  (Cseg = O/4)
       const int p = (int)(idx / I); i = (int)(idx % I);
       const int cseg = O >> 2;
@@ -211,6 +215,7 @@ __global__ void pack_bias_kernel(const float* __restrict__ bias, const float* __
   if (p >= O) return;
   int o = p;
   if (mode == PACK_PAIR) o = ((p & 15) >> 3) * (O >> 1) + (p >> 4) * 8 + (p & 7);
+  if (mode == PACK_PAIR32) o = ((p & 63) >> 5) * (O >> 1) + (p >> 6) * 32 + (p & 31);
   float v = bias[o];
   if (scale) v *= scale[o];
   out[p] = v;

@@ -151,12 +151,15 @@ int nafblock_pack_impl(const float* const* P, BlockPacked& pk, int C, cudaStream
   DCPT_TRY(pack_weight_launch(P[P_C1W], nullptr, pk.w1t, 2 * C, C, PACK_T, st));
   DCPT_TRY(pack_weight_launch(P[P_C3W], P[P_BETA], pk.w3b, C, C, PACK_PLAIN, st));
   DCPT_TRY(pack_weight_launch(P[P_C3W], P[P_BETA], pk.w3bt, C, C, PACK_T, st));
-  DCPT_TRY(pack_weight_launch(P[P_C4W], nullptr, pk.w4p, 2 * C, C, PACK_PAIR, st));
+  // conv4's output columns are interleaved so that the SimpleGate halves of a channel land in the same accumulator tile:
+  // 32-wide pairs (TMA-tiled epilogue) when C % 32 == 0, else 8-wide pairs (register-staged epilogue)
+  const int pair_mode = C % 32 == 0 ? PACK_PAIR32 : PACK_PAIR;
+  DCPT_TRY(pack_weight_launch(P[P_C4W], nullptr, pk.w4p, 2 * C, C, pair_mode, st));
   DCPT_TRY(pack_weight_launch(P[P_C4W], nullptr, pk.w4t, 2 * C, C, PACK_T, st));
   DCPT_TRY(pack_weight_launch(P[P_C5W], P[P_GAMMA], pk.w5g, C, C, PACK_PLAIN, st));
   DCPT_TRY(pack_weight_launch(P[P_C5W], P[P_GAMMA], pk.w5gt, C, C, PACK_T, st));
   DCPT_TRY(pack_bias_launch(P[P_C3B], P[P_BETA], pk.b3b, C, PACK_PLAIN, st));
-  DCPT_TRY(pack_bias_launch(P[P_C4B], nullptr, pk.b4p, 2 * C, PACK_PAIR, st));
+  DCPT_TRY(pack_bias_launch(P[P_C4B], nullptr, pk.b4p, 2 * C, pair_mode, st));
   DCPT_TRY(pack_bias_launch(P[P_C5B], P[P_GAMMA], pk.b5g, C, PACK_PLAIN, st));
   return 0;
 }
@@ -187,7 +190,7 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
   // norm2 -> conv4 -> SimpleGate
   DCPT_TRY(ln_fwd_launch(sv.y, P[P_N2W], P[P_N2B], sv.n2, sv.stats2, M, C, eps, st));
   {
-    GemmArgs g = gemm_args(M, 2 * C, C, sv.n2, C, pk.w4p, C, EPI_GATE);
+    GemmArgs g = gemm_args(M, 2 * C, C, sv.n2, C, pk.w4p, C, C % 32 == 0 ? EPI_GATE_TMA : EPI_GATE);
     g.ep.out_bf16 = sv.x4; g.ep.ldo = 2 * C; g.ep.out2 = sv.sg; g.ep.ldo2 = C; g.ep.C = C; g.ep.bias = pk.b4p;
     DCPT_TRY(gemm_launch(g, st));
   }

@@ -3,6 +3,7 @@
 // (there is no nsys in this image).  Also counts launches for bench.py's `gpu_launches`.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdio.h>
 
 void dcpt_prof_begin(const char* tag, double flops, double bytes, cudaStream_t st);
 void dcpt_prof_end(cudaStream_t st);
@@ -23,3 +24,10 @@ struct DcptProfScope {
   }
 };
 #define DCPT_PROF(tag, flops, bytes, st) DcptProfScope _prof_scope((tag), (double)(flops), (double)(bytes), (st))
+// tag + " <a>x<b>" when per-shape tags are requested (dcpt_prof_enable(2)); a, b = rows / channels of the launch
+inline const char* dcpt_prof_tag2(const char* tag, long long a, long long b) {
+  if (!(g_dcpt_prof_on && g_dcpt_prof_shapes)) return tag;
+  char buf[96];
+  snprintf(buf, sizeof(buf), "%s %lldx%lld", tag, a, b);
+  return dcpt_prof_intern(buf);
+}

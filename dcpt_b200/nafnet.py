@@ -5,6 +5,8 @@
 ``autograd.Function``), so ``loss.backward()``, DDP and optimizers work as with the reference.
 """
 import ctypes as C
+import os
+import weakref
 
 import torch
 
@@ -34,6 +36,9 @@ class NAFNetEngine:
         self._packed = None
         self._packed_key = None
         self._scratch = {}
+        # CUDA-graph replay of the autograd path (nafnet_apply): DCPT_CUDA_GRAPH=0 launches every kernel from the host
+        self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0"
+        self._gslots = {}
 
     def __del__(self):
         try:
@@ -133,6 +138,122 @@ class NAFNetEngine:
         return grads
 
 
+class _GraphSlot:
+    """Static buffers and captured CUDA graphs of one (shape, hook, feats, parameter storage) signature.
+
+    A whole forward (~140 launches) or backward (~360 launches) of the w64 network is one graph launch: the host cost of
+    encoding the TMA descriptors and launching each kernel (several ms per step, during which the GPU idles) is paid once at
+    capture.  The slot owns the saved-activation arena, so it is ``busy`` from a forward that needs gradients until its
+    backward ran (DCPT runs two forwards before one backward: it gets two slots)."""
+
+    MAX_PER_KEY = 3
+
+    def __init__(self, eng, params, N, H, W, dev, hook, want_feats):
+        self.N, self.H, self.W, self.hook = N, H, W, hook
+        self.inp = torch.empty(N, 3, H, W, dtype=torch.float32, device=dev)
+        self.out = None if hook else torch.empty_like(self.inp)
+        self.saved = torch.empty(eng.lib.dcpt_nafnet_saved_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
+        self.feats = None
+        if want_feats:
+            self.feats, c, h, w = [], eng.width << eng.n_enc, H >> eng.n_enc, W >> eng.n_enc
+            for _ in range(eng.n_dec):
+                c, h, w = c // 2, h * 2, w * 2
+                self.feats.append(torch.empty(N, h, w, c, dtype=torch.float32, device=dev))
+        self.dout = None
+        self.dfeats = None
+        self.flat = self.grads = None
+        self.fgraph = None
+        self.bgraphs = {}
+        self.busy = False
+
+    def release(self):
+        self.busy = False
+
+
+def _graph_forward(eng, params, inp, hook, want_feats, need_grad):
+    """Returns (out, feats, slot) or None when no slot is free (caller falls back to eager launches)."""
+    inp = inp.contiguous().float()
+    N, _, H, W = inp.shape
+    key = (N, H, W, inp.device, bool(hook), bool(want_feats), tuple(p.data_ptr() for p in params))
+    slots = eng._gslots.setdefault(key, [])
+    slot = next((s for s in slots if not s.busy), None)
+    if slot is None:
+        if len(slots) >= _GraphSlot.MAX_PER_KEY:
+            return None
+        slot = _GraphSlot(eng, params, N, H, W, inp.device, bool(hook), bool(want_feats))
+        slots.append(slot)
+    packed = eng.packed_for(params)   # re-packed eagerly when a parameter changed; its address is static
+    slot.inp.copy_(inp)
+    pp = _l.ptr_array([p.data_ptr() for p in params])
+    fp = _l.ptr_array([f.data_ptr() for f in slot.feats]) if slot.feats else None
+
+    def run():
+        _l.check(eng.lib.dcpt_nafnet_fwd(eng.plan, pp, _p(packed), _p(slot.inp), _p(slot.out), _p(slot.saved), fp, int(slot.hook),
+                                         N, H, W, _stream()), "nafnet_fwd")
+    if slot.fgraph is None:
+        run()                           # eager once: lazy one-time initialisation inside the library must not be captured
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            run()
+        slot.fgraph = g
+    else:
+        slot.fgraph.replay()
+    slot.busy = bool(need_grad)
+    out = None if hook else slot.out.clone()
+    feats = [f.clone() for f in slot.feats] if slot.feats else None
+    return out, feats, slot
+
+
+def _graph_backward(eng, params, slot, dout, dfeats):
+    N, H, W = slot.N, slot.H, slot.W
+    dev = slot.inp.device
+    if slot.flat is None:
+        slot.offs, off = [], 0
+        for p in params:
+            slot.offs.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        slot.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        slot.grads = [slot.flat[o:o + p.numel()].view(p.shape) for o, p in zip(slot.offs, params)]
+    mask = (dout is not None, tuple(d is not None for d in dfeats) if dfeats else None)
+    if dout is not None:
+        if slot.dout is None:
+            slot.dout = torch.empty_like(slot.inp)
+        slot.dout.copy_(dout)
+    if dfeats and any(d is not None for d in dfeats):
+        if slot.dfeats is None:
+            slot.dfeats = [torch.empty_like(f) for f in slot.feats]
+        for s_, d in zip(slot.dfeats, dfeats):
+            if d is not None:
+                s_.copy_(d)
+    k = ("work", N, H, W, dev)
+    if k not in eng._scratch:
+        eng._scratch[k] = torch.empty(eng.lib.dcpt_nafnet_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
+    work = eng._scratch[k]
+    packed = eng.packed_for(params)
+    pp = _l.ptr_array([p.data_ptr() for p in params])
+    gp = _l.ptr_array([g.data_ptr() for g in slot.grads])
+    dfp = None
+    if mask[1] and any(mask[1]):
+        dfp = _l.ptr_array([s_.data_ptr() if m else 0 for s_, m in zip(slot.dfeats, mask[1])])
+    dptr = _p(slot.dout) if mask[0] else None
+
+    def run():
+        slot.flat.zero_()
+        _l.check(eng.lib.dcpt_nafnet_bwd(eng.plan, pp, _p(packed), _p(slot.saved), _p(slot.inp), dptr, dfp, gp, _p(work), N, H, W,
+                                         _stream()), "nafnet_bwd")
+    if mask not in slot.bgraphs:
+        run()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            run()
+        slot.bgraphs[mask] = g
+    else:
+        slot.bgraphs[mask].replay()
+    slot.busy = False
+    flat = slot.flat.clone()            # autograd owns the returned gradients; the slot's buffer is rewritten next step
+    return [flat[o:o + p.numel()].view(p.shape) for o, p in zip(slot.offs, params)]
+
+
 class _NAFNetFunction(torch.autograd.Function):
     """out, feat_0..feat_{n-1} = NAFNet(inp; params).  feats are NHWC storage viewed as logical NCHW."""
 
@@ -143,7 +264,19 @@ class _NAFNetFunction(torch.autograd.Function):
         # before one backward).
         dparams = [p.detach() for p in params]
         inp_c = inp.detach().contiguous().float()
-        out, feats, saved = engine.forward(dparams, inp_c, hook=hook, want_feats=want_feats, keep_for_backward=need_grad)
+        res = None
+        if engine.use_graphs and inp_c.is_cuda and not torch.cuda.is_current_stream_capturing():
+            engine._check_params(dparams)
+            res = _graph_forward(engine, dparams, inp_c, hook, want_feats, need_grad)
+        if res is not None:
+            out, feats, saved = res
+            if need_grad:
+                try:
+                    weakref.finalize(ctx, saved.release)   # a forward whose backward never runs must not pin the slot
+                except TypeError:
+                    pass
+        else:
+            out, feats, saved = engine.forward(dparams, inp_c, hook=hook, want_feats=want_feats, keep_for_backward=need_grad)
         ctx.engine, ctx.hook, ctx.n_feats = engine, hook, len(feats) if feats else 0
         ctx.inp, ctx.saved, ctx.params = inp_c, saved, dparams
         outs = []
@@ -161,7 +294,10 @@ class _NAFNetFunction(torch.autograd.Function):
         dfe = None
         if ctx.n_feats:
             dfe = [None if d is None else d.permute(0, 2, 3, 1).contiguous() for d in dfeats]
-        grads = eng.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
+        if isinstance(ctx.saved, _GraphSlot):
+            grads = _graph_backward(eng, ctx.params, ctx.saved, None if ctx.hook else dout, dfe)
+        else:
+            grads = eng.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
         ctx.saved = None
         return (None, None, None, None, None) + tuple(grads)
 

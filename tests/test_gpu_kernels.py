@@ -174,7 +174,7 @@ def test_gemm_pixshuf_epilogue(ops, impl, N, H, W, Cin):
 
 
 # ------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("M,C", [(70, 24), (1000, 64), (4096, 128), (777, 512), (300, 1024), (5, 8)])
+@pytest.mark.parametrize("M,C", [(70, 24), (1000, 64), (4096, 128), (777, 512), (300, 1024), (5, 8), (4099, 512), (16384, 512)])
 def test_layernorm_fwd_bwd(ops, M, C):
     g = torch.Generator().manual_seed(C)
     x = torch.randn(M, C, generator=g) * 1.7 + 0.4
@@ -195,6 +195,9 @@ def test_layernorm_fwd_bwd(ops, M, C):
     assert rel(dxb.float(), ref) < 4e-3
     assert rel(dw, dw_ref) < 1e-4 and rel(db, db_ref) < 1e-4
     assert rel(cs, ref.sum(0)) < 1e-4
+    if M >= 2048:  # no residual gradient (dres = NULL) through the same (wide-row, bulk-copy pipelined) kernel
+        dx2 = ops.layernorm2d_bwd(dn.cuda(), x.cuda(), stats, w.cuda(), None)[0]
+        assert rel(dx2, dx_ref[0, :, :, 0].t()) < 1e-5
 
 
 def test_layernorm_golden(ops, golden_dir):
