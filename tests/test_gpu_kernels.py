@@ -133,8 +133,29 @@ def test_gemm_gate_epilogue(ops, impl, M, C):
     assert rel(sg.float(), x4r[:, :C] * x4r[:, C:]) < 4e-3
 
 
+@pytest.mark.parametrize("M,C", [(256, 64), (1000, 32), (512, 512), (33000, 128), (130, 96), (4099, 1024)])
+def test_gemm_gate32_epilogue(ops, M, C):
+    """conv4 + SimpleGate with 32-wide pair packing and the TMA-tiled epilogue (epilogue id 7, C % 32 == 0)."""
+    g = torch.Generator(device="cuda").manual_seed(C + 7)
+    n2 = bf(torch.randn(M, C, device="cuda", generator=g))
+    W4 = bf(torch.randn(2 * C, C, device="cuda", generator=g) / C ** 0.5)
+    b4 = torch.randn(2 * C, device="cuda", generator=g)
+    p = torch.arange(2 * C, device="cuda")
+    orig = ((p % 64) // 32) * C + (p // 64) * 32 + (p % 32)  # packed row -> original out-channel
+    W4p, b4p = W4[orig].contiguous(), b4[orig].contiguous()
+    x4 = torch.full((M, 2 * C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    sg = torch.full((M, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    d = _desc(ops, M=M, N=2 * C, K=C, A=n2, lda=C, B=W4p, ldb=C, splits=1, epilogue=7, out_bf16=x4, ldo=2 * C, bias=b4p,
+              out2_bf16=sg, ldo2=C, C=C)
+    ops.gemm_ex(d, 0)
+    ref = n2.float() @ W4.float().t() + b4
+    assert rel(x4.float(), ref) < 4e-3
+    x4r = x4.float()
+    assert rel(sg.float(), x4r[:, :C] * x4r[:, C:]) < 4e-3
+
+
 @pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
-@pytest.mark.parametrize("M,C", [(256, 64), (1000, 16), (512, 512)])
+@pytest.mark.parametrize("M,C", [(256, 64), (1000, 16), (512, 512), (33000, 128), (130, 96)])
 def test_gemm_gate_bwd_epilogue(ops, impl, M, C):
     g = torch.Generator(device="cuda").manual_seed(C + 1)
     dout = bf(torch.randn(M, C, device="cuda", generator=g))
