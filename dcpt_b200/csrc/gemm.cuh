@@ -35,6 +35,14 @@ struct EpiParams {
   int ldaux;
   int C;               // GATE / GATE_BWD: half width (x4 has 2C columns)
   int H, W, Cseg;      // PIXSHUF: input spatial dims and channels per output pixel (N = 4*Cseg)
+  // Fused column reductions (TMA-tiled epilogues; gemm_tc_launch runs the separate reduction kernel otherwise):
+  //   GATE_BWD: colsum[2C] += column sums of d(x4)                          (conv4's bias gradient)
+  //   STORE   : with gaux (bf16 [M, ldgaux]) and rows_per_img: colsum[(m / rows_per_img) * N + n] += out[m, n] * gaux[m, n]
+  //             (SCA backward: ds[img, c] = sum_px d(g*s) * g, nafnet_arch.py:116-127)
+  float* colsum;
+  const bf16* gaux;
+  int ldgaux;
+  int rows_per_img;
 };
 
 struct GemmArgs {

@@ -4,6 +4,7 @@
 // the environment variable DCPT_GEMM_SIMT=1 is set, or through dcpt_gemm_bf16(..., impl=1).
 #include <stdlib.h>
 
+#include "elementwise.cuh"
 #include "gemm.cuh"
 
 namespace {
@@ -54,9 +55,16 @@ int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream) {
                  g.K);
   DCPT_CHECK_ARG(g.splits <= 1 || g.epi == EPI_ATOMIC, DCPT_E_ARG, "gemm(simt): split-K needs the atomic epilogue");
   switch (g.epi) {
-    case EPI_STORE: return launch<EPI_STORE>(g, stream);
+    case EPI_STORE:
+      DCPT_TRY(launch<EPI_STORE>(g, stream));
+      if (g.ep.gaux && g.ep.colsum)  // the tensor-core kernel reduces this in its epilogue
+        return sca_ds_reduce_launch(g.ep.out_bf16, g.ep.gaux, g.ep.colsum, g.M / g.ep.rows_per_img, g.ep.rows_per_img, g.N, stream);
+      return 0;
     case EPI_GATE: return launch<EPI_GATE>(g, stream);
-    case EPI_GATE_BWD: return launch<EPI_GATE_BWD>(g, stream);
+    case EPI_GATE_BWD:
+      DCPT_TRY(launch<EPI_GATE_BWD>(g, stream));
+      if (g.ep.colsum) return colsum_bf16_launch(g.ep.out_bf16, g.ep.colsum, g.M, 2 * g.ep.C, stream);
+      return 0;
     case EPI_PIXSHUF: return launch<EPI_PIXSHUF>(g, stream);
     case EPI_ATOMIC: return launch<EPI_ATOMIC>(g, stream);
   }

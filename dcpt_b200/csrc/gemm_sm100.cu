@@ -17,6 +17,7 @@
 
 #include <mutex>
 
+#include "elementwise.cuh"
 #include "gemm.cuh"
 
 namespace {
@@ -42,7 +43,8 @@ struct Cfg {
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two >= 32)
   static constexpr uint32_t EPI_BYTES = 8 * (TMA_EPI ? 8192 : 4096);  // starts 1024-byte aligned (STAGE_BYTES % 1024 == 0)
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 512 /*barriers*/;
+  static constexpr uint32_t COLSUM_BYTES = EPI == EPI_GATE_BWD_TMA ? 8192 : 0;  // per-CTA column sums of d(x4): 2C <= 2048 floats
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 512 /*barriers*/ + COLSUM_BYTES;
 };
 
 // UMMA shared-memory descriptor (sm_100): start addr [0,14), LBO [16,30), SBO [32,46) (all >>4),
@@ -62,6 +64,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// Column sums of a 32 x 32 tile held one row per lane: 31 shuffles; afterwards v[0] of lane l = sum over the 32 rows of column l.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
 }
 
 // CONV = 0: plain GEMM.  CONV = 1: implicit-GEMM 3x3 convolution (pad 1, stride 1), A = NHWC activation through a 4-D
@@ -85,6 +102,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = tfull + 2;
   uint64_t* rfull = tempty + 2;  // [8 epilogue warps][2]: residual tile landed (EPI_STORE_TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 16);
+  float* s_colsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  if constexpr (EPI == EPI_GATE_BWD_TMA) {
+    if (ep.colsum)
+      for (int i = threadIdx.x; i < 2 * ep.C; i += kThreads) s_colsum[i] = 0.f;
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -260,15 +282,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint64_t* rf = rfull + ew * 2;
       uint32_t rphase = 0;  // bit b: parity of the next completion of rf[b]
       int ci = 0;           // chunks handled by this warp so far (buffer = ci & 1)
-      const bool has_r = EPI == EPI_GATE_BWD_TMA || (EPI == EPI_STORE_TMA && ep.resid != nullptr);
+      const bool has_g = EPI == EPI_STORE_TMA && ep.gaux != nullptr;  // fused SCA-backward reduction (bf16 output, no residual)
+      const bool has_r = EPI == EPI_GATE_BWD_TMA || (EPI == EPI_STORE_TMA && (ep.resid != nullptr || has_g));
       // the epilogue's input tile(s) of chunk n0 of row slab m0 -> 4 KiB buffer: one fp32 residual box, or the two bf16
       // x4 boxes (columns n0 and C + n0) of the SimpleGate backward
       auto issue_in = [&](uint8_t* dst, uint64_t* bar, int n0, int m0) {
-        mbar_arrive_expect_tx(bar, 4096);
         if constexpr (EPI == EPI_GATE_BWD_TMA) {
+          mbar_arrive_expect_tx(bar, 4096);
           tma_load_2d(dst, &em.r32, bar, n0, m0);
           tma_load_2d(dst + 2048, &em.r32, bar, ep.C + n0, m0);
+        } else if (has_g) {  // bf16 g tile into the upper half of the buffer (the bf16 output tile uses the lower half)
+          mbar_arrive_expect_tx(bar, 2048);
+          tma_load_2d(dst + 2048, &em.o2, bar, n0, m0);
         } else {
+          mbar_arrive_expect_tx(bar, 4096);
           tma_load_2d(dst, &em.r32, bar, n0, m0);
         }
       };
@@ -369,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
           if constexpr (EPI == EPI_GATE_BWD_TMA) {
             // d(x4)[:, n] = d(sg) * x4[:, C + n],  d(x4)[:, C + n] = d(sg) * x4[:, n]  (nafnet_arch.py:77-80), in place
+            float da32[32];  // d(x4) first half (kept for the column sums); v is overwritten with the second half
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t off = (uint32_t)(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
@@ -380,6 +408,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int k = 0; k < 8; ++k) {
                 da[k] = v[8 * j + k] * xb[k];
                 db[k] = v[8 * j + k] * xa[k];
+                da32[8 * j + k] = da[k];
+                v[8 * j + k] = db[k];
               }
               sts_u4(buf + off, pack8(da));
               sts_u4(buf + 2048 + off, pack8(db));
@@ -390,6 +420,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_store_2d(&em.o16, ebuf + b * 4096, n0, m0);
               tma_store_2d(&em.o16, ebuf + b * 4096 + 2048, ep.C + n0, m0);
               bulk_commit();
+            }
+            if (ep.colsum) {  // conv4 bias gradient: rows beyond M hold zeros (zero-filled operands), columns are all valid (C % 32 == 0)
+              const float sa = warp_colsum32(da32, lane);
+              const float sb = warp_colsum32(v, lane);
+              atomicAdd(&s_colsum[n0 + lane], sa);
+              atomicAdd(&s_colsum[ep.C + n0 + lane], sb);
             }
             ++ci;
             continue;
@@ -403,7 +439,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          if (has_r) {
+          if (has_r && !has_g) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 r = lds_f4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)));
@@ -438,6 +474,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) {
               tma_store_2d(&em.o16, ebuf + b * 4096, n0, m0);
               bulk_commit();
+            }
+            if (has_g) {  // ds[img, n] += sum_rows bf16(out) * g   (one image per 32-row slab: rows_per_img % 32 == 0)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float gv[8];
+                const float4 rg = lds_f4(buf + 2048 + (uint32_t)(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)));
+                unpack8(*reinterpret_cast<const uint4*>(&rg), gv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[8 * j + k] = bf16_round(v[8 * j + k]) * gv[k];
+              }
+              const float sgd = warp_colsum32(v, lane);
+              if (m0 < M && n0 + lane < N) atomicAdd(ep.colsum + (size_t)(m0 / ep.rows_per_img) * N + n0 + lane, sgd);
             }
           }
           ++ci;
@@ -590,6 +638,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (EPI == EPI_GATE_BWD_TMA) {
+    if (ep.colsum)
+      for (int i = threadIdx.x; i < 2 * ep.C; i += kThreads) {
+        const float sv = s_colsum[i];
+        if (sv != 0.f) atomicAdd(ep.colsum + i, sv);
+      }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -682,6 +737,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     if (g.ep.out_f32) DCPT_TRY(make_tmap_epi(&em.o32, g.ep.out_f32, g.M, g.N, g.ep.ldo, 4));
     if (g.ep.out_bf16) DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, g.N, g.ep.ldo, 2));
     if (g.ep.resid) DCPT_TRY(make_tmap_epi(&em.r32, g.ep.resid, g.M, g.N, g.ep.ldr, 4));
+    if (g.ep.gaux) DCPT_TRY(make_tmap_epi(&em.o2, g.ep.gaux, g.M, g.N, g.ep.ldgaux, 2));
   } else if constexpr (EPI == EPI_GATE_BWD_TMA) {
     DCPT_TRY(make_tmap_epi(&em.r32, g.ep.aux, g.M, 2 * g.ep.C, g.ep.ldaux, 2));
     DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, 2 * g.ep.C, g.ep.ldo, 2));
@@ -846,8 +902,20 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
       auto ok = [](const void* p, long long ld, int eb) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * eb) % 16 == 0); };
       const bool tma = !no_tma && (g.ep.out_f32 || g.ep.out_bf16) && ok(g.ep.out_f32, g.ep.ldo, 4) && ok(g.ep.out_bf16, g.ep.ldo, 2) &&
                        ok(g.ep.resid, g.ep.ldr, 4) && (g.ep.bias == nullptr || (reinterpret_cast<uintptr_t>(g.ep.bias) & 15) == 0);
-      if (tma) return launch_bn<EPI_STORE_TMA, false, false>(g, stream);
-      return launch_bn<EPI_STORE, false, false>(g, stream);
+      // fused SCA-backward reduction ds[img, c] += out * gaux: needs the TMA epilogue, a bf16-only output and whole
+      // 32-row slabs per image; otherwise the separate reduction kernel runs after the GEMM
+      const bool want_g = g.ep.gaux != nullptr && g.ep.colsum != nullptr;
+      const bool fuse_g = want_g && tma && !g.ep.resid && !g.ep.out_f32 && g.ep.out_bf16 && g.ep.rows_per_img > 0 &&
+                          g.ep.rows_per_img % 32 == 0 && ok(g.ep.gaux, g.ep.ldgaux, 2);
+      GemmArgs gg = g;
+      if (!fuse_g) gg.ep.gaux = nullptr;
+      DCPT_TRY(tma ? (launch_bn<EPI_STORE_TMA, false, false>(gg, stream)) : (launch_bn<EPI_STORE, false, false>(gg, stream)));
+      if (want_g && !fuse_g) {
+        DCPT_CHECK_ARG(g.ep.out_bf16 && g.ep.ldo == g.N && g.ep.ldgaux == g.N && g.ep.rows_per_img > 0 && g.M % g.ep.rows_per_img == 0,
+                       DCPT_E_ARG, "gemm: the SCA-backward reduction needs a dense bf16 output and whole images");
+        return sca_ds_reduce_launch(g.ep.out_bf16, g.ep.gaux, g.ep.colsum, g.M / g.ep.rows_per_img, g.ep.rows_per_img, g.N, stream);
+      }
+      return 0;
     }
     case EPI_GATE: return launch_bn<EPI_GATE, false, false>(g, stream);
     case EPI_GATE_TMA:  // SimpleGate forward on 32-wide pair packing (PACK_PAIR32 weights / bias)
@@ -857,9 +925,14 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     case EPI_GATE_BWD: {
       static const bool no_tma = getenv("DCPT_GEMM_NO_TMA_EPI") != nullptr;
       if (!no_tma && g.ep.C % 32 == 0 && g.N == g.ep.C && (g.ep.ldo % 8) == 0 && (g.ep.ldaux % 8) == 0 &&
-          ((reinterpret_cast<uintptr_t>(g.ep.out_bf16) | reinterpret_cast<uintptr_t>(g.ep.aux)) & 15) == 0)
-        return launch_bn<EPI_GATE_BWD_TMA, false, false>(g, stream);
-      return launch_bn<EPI_GATE_BWD, false, false>(g, stream);
+          ((reinterpret_cast<uintptr_t>(g.ep.out_bf16) | reinterpret_cast<uintptr_t>(g.ep.aux)) & 15) == 0 && g.ep.C <= 1024)
+        return launch_bn<EPI_GATE_BWD_TMA, false, false>(g, stream);  // conv4's bias gradient (ep.colsum) is reduced in the epilogue
+      DCPT_TRY((launch_bn<EPI_GATE_BWD, false, false>(g, stream)));
+      if (g.ep.colsum) {
+        DCPT_CHECK_ARG(g.ep.ldo == 2 * g.ep.C, DCPT_E_ARG, "gemm: the fused d(x4) column sums need a dense output");
+        return colsum_bf16_launch(g.ep.out_bf16, g.ep.colsum, g.M, 2 * g.ep.C, stream);
+      }
+      return 0;
     }
     case EPI_PIXSHUF: return launch_bn<EPI_PIXSHUF, false, false>(g, stream);
     case EPI_ATOMIC: return launch_bn<EPI_ATOMIC, false, false>(g, stream);

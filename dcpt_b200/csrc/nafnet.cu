@@ -215,10 +215,10 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   {
     GemmArgs g = gemm_args(M, C, C, doutT, C, pk.w5gt, C, EPI_GATE_BWD);
     g.ep.out_bf16 = wk.dx4; g.ep.ldo = 2 * C; g.ep.aux = sv.x4; g.ep.ldaux = 2 * C; g.ep.C = C;
+    g.ep.colsum = G[P_C4B];  // conv4's bias gradient = column sums of d(x4), reduced in the GEMM epilogue
     DCPT_TRY(gemm_launch(g, st));
   }
-  // ---- conv4: dbias, wgrad, dgrad ----
-  DCPT_TRY(colsum_bf16_launch(wk.dx4, G[P_C4B], M, 2 * C, st));
+  // ---- conv4: wgrad, dgrad ----
   DCPT_TRY(wgrad_gemm(wk.dx4, 2 * C, sv.n2, C, G[P_C4W], M, st));
   {
     GemmArgs g = gemm_args(M, C, 2 * C, wk.dx4, 2 * C, pk.w4t, 2 * C, EPI_STORE);
@@ -232,14 +232,14 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), st));
   DCPT_TRY(wgrad_gemm(wk.dyT, C, sv.gs, C, wk.G, M, st));
   DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C3W], P[P_C3B], P[P_BETA], wk.Sy, G[P_C3W], G[P_C3B], G[P_BETA], C, C, st));
-  {
+  DCPT_CUDA(cudaMemsetAsync(wk.ds, 0, (size_t)N * C * sizeof(float), st));
+  {  // dgrad, with the SCA backward's ds[n, c] = sum_px d(g*s) * g reduced in the GEMM epilogue
     GemmArgs g = gemm_args(M, C, C, wk.dyT, C, pk.w3bt, C, EPI_STORE);
     g.ep.out_bf16 = wk.dgs; g.ep.ldo = C;
+    g.ep.gaux = sv.g; g.ep.ldgaux = C; g.ep.colsum = wk.ds; g.ep.rows_per_img = HW;
     DCPT_TRY(gemm_launch(g, st));
   }
   // ---- SCA backward ----
-  DCPT_CUDA(cudaMemsetAsync(wk.ds, 0, (size_t)N * C * sizeof(float), st));
-  DCPT_TRY(sca_ds_reduce_launch(wk.dgs, sv.g, wk.ds, N, HW, C, st));
   DCPT_TRY(sca_bwd_launch(wk.ds, sv.pool, P[P_SCAW], wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st));
   // ---- SimpleGate + depthwise conv backward ----
   DCPT_TRY(dwgate_bwd_a_launch(wk.dgs, sv.s, wk.t, sv.u, P[P_C2W], P[P_C2B], wk.du2, G[P_C2W], G[P_C2B], N, H, W, C, st));
