@@ -52,6 +52,28 @@ static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 
 
 int dcpt_num_sms();
 
+// Programmatic dependent launch (PDL): a kernel launched through dcpt_launch_pdl may become resident while its predecessor
+// in the stream is still draining; it must call pdl_sync() (device) before its first access to global memory that another
+// kernel produces or still reads.  The launch latency and the prologue (barrier init, TMEM allocation, descriptor
+// prefetch) of kernel i+1 then overlap the tail of kernel i.  Opt-in with DCPT_PDL=1 (default: plain stream order).
+bool dcpt_pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t dcpt_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = dcpt_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Host-side TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point; gemm_sm100.cu).
 // 2-D: row-major bf16 [rows, cols], box 64 x box_rows, 128-byte swizzle (UMMA operand tiles).
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
@@ -65,6 +87,13 @@ int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH
 // device helpers
 // ----------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// let the next kernel in the stream start launching, then wait until every kernel this one depends on has completed and
+// its memory is visible (no-op when the kernel was launched without the PDL attribute)
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -68,6 +68,7 @@ template <int GELU>
 __global__ void __launch_bounds__(NWARP * 32)
 dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restrict__ w2, const float* __restrict__ b2,
                   bf16* __restrict__ g, float* __restrict__ pool, int N, int H, int W, int C) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   __shared__ uint64_t full[2];
@@ -173,6 +174,7 @@ dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restri
 __global__ void __launch_bounds__(NWARP * 32)
 dwconv3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w, bf16* __restrict__ out,
                    float* __restrict__ sumsq, int sq_ch, int N, int H, int W, int CH) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   __shared__ uint64_t full[2];
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(NWARP * 32)
 dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmD, const float* __restrict__ s_sca,
                     const float* __restrict__ t_sca, const float* __restrict__ w2, const float* __restrict__ b2,
                     bf16* __restrict__ du2, float* __restrict__ dw2, float* __restrict__ db2, int N, int H, int W, int C) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   constexpr int STAGE_BYTES = 2 * BOX_BYTES + DG_BYTES;
@@ -389,6 +392,7 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
 __global__ void __launch_bounds__(NWARP * 32)
 dwconv_bwd_data_kernel(const __grid_constant__ CUtensorMap tmG, const float* __restrict__ w2, bf16* __restrict__ du,
                        float* __restrict__ colsum, int N, int H, int W, int CH) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   __shared__ uint64_t full[2];
@@ -488,7 +492,7 @@ int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, 
   const size_t smem = 128 + (size_t)2 * 2 * BOX_BYTES;
   DCPT_TRY(set_smem(dwgate_fwd_kernel<0>, smem));
   DCPT_PROF(dcpt_prof_tag2("dwgate_fwd", (long long)N * H * W, C), 38.0 * N * H * W * C, 6.0 * N * H * W * C, st);
-  dwgate_fwd_kernel<0><<<pick_grid(N, H, W, C, 2), NWARP * 32, smem, st>>>(tmU, w2, b2, g, pool, N, H, W, C);
+  DCPT_CUDA(dcpt_launch_pdl(dwgate_fwd_kernel<0>, pick_grid(N, H, W, C, 2), dim3(NWARP * 32), smem, st, tmU, w2, b2, g, pool, N, H, W, C));
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -527,7 +531,7 @@ int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const b
   const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
   DCPT_TRY(set_smem(dwgate_bwd_a_kernel, smem));
   DCPT_PROF(dcpt_prof_tag2("dwgate_bwd_a", (long long)N * H * W, C), 80.0 * N * H * W * C, 10.0 * N * H * W * C, st);
-  dwgate_bwd_a_kernel<<<pick_grid(N, H, W, C, 1), NWARP * 32, smem, st>>>(tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C);
+  DCPT_CUDA(dcpt_launch_pdl(dwgate_bwd_a_kernel, pick_grid(N, H, W, C, 1), dim3(NWARP * 32), smem, st, tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C));
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -540,7 +544,7 @@ int dwconv_bwd_data_launch(const bf16* du2, const float* w2, bf16* du, float* co
   const size_t smem = 128 + (size_t)2 * BOX_BYTES;
   DCPT_TRY(set_smem(dwconv_bwd_data_kernel, smem));
   DCPT_PROF(dcpt_prof_tag2("dwconv_bwd_data", (long long)N * H * W, C2), 18.0 * N * H * W * C2, 4.0 * N * H * W * C2, st);
-  dwconv_bwd_data_kernel<<<pick_grid(N, H, W, C2, 4), NWARP * 32, smem, st>>>(tmG, w2, du, colsum, N, H, W, C2);
+  DCPT_CUDA(dcpt_launch_pdl(dwconv_bwd_data_kernel, pick_grid(N, H, W, C2, 4), dim3(NWARP * 32), smem, st, tmG, w2, du, colsum, N, H, W, C2));
   DCPT_LAUNCH_CHECK();
   return 0;
 }

@@ -141,6 +141,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's tail
+  pdl_sync();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -780,7 +782,8 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
                                                 (EPI == EPI_GATE || EPI == EPI_GATE_TMA ? 1.0 : 0.0) +
                                                 (EPI == EPI_GATE_BWD || EPI == EPI_GATE_BWD_TMA ? 4.0 : 0.0));
   DCPT_PROF(tag, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes, stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, g.M, g.N, g.K, tiles_m, tiles_n, splits, kbps, g.ep, cg0);
+  DCPT_CUDA(dcpt_launch_pdl(kern, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, em, g.M, g.N, g.K, tiles_m, tiles_n, splits,
+                            kbps, g.ep, cg0));
   DCPT_LAUNCH_CHECK();
   return 0;
 }

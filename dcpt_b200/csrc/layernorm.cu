@@ -22,6 +22,7 @@ template <int NV>
 __global__ void __launch_bounds__(kWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
               float* __restrict__ stats, int M, int C, int lpr, float eps, int center) {
+  pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rpw = 32 / lpr;  // rows per warp
   const int sub = lane % lpr, gr = lane / lpr;
@@ -87,6 +88,7 @@ ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const fl
   extern __shared__ float s_acc[];  // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
+  pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rpw = 32 / lpr;
   const int sub = lane % lpr, gr = lane / lpr;
@@ -215,6 +217,7 @@ ln_bwd_wide_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, con
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_sync();
   const int tiles = (M + R - 1) / R;
   auto issue = [&](int t, int s) {
     const int r0 = t * R;
@@ -328,7 +331,7 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
   const int rows_per_block = kWarps * (32 / lpr);
   const int grid = (int)ceil_div_ll(M, rows_per_block);
   DCPT_PROF(dcpt_prof_tag2("ln_fwd", M, C), 8.0 * M * C, 6.0 * M * C, st);
-#define LN_FWD(NVV) ln_fwd_kernel<NVV><<<grid, kWarps * 32, 0, st>>>(x, w, b, n_out, stats, M, C, lpr, eps, center)
+#define LN_FWD(NVV) DCPT_CUDA(dcpt_launch_pdl(ln_fwd_kernel<NVV>, dim3(grid), dim3(kWarps * 32), 0, st, x, w, b, n_out, stats, M, C, lpr, eps, center))
   if (nv <= 1) LN_FWD(1);
   else if (nv <= 2) LN_FWD(2);
   else if (nv <= 4) LN_FWD(4);
@@ -351,7 +354,7 @@ int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const floa
     if (C == 512) {
       static bool once = false;
       if (!once) { DCPT_CUDA(cudaFuncSetAttribute(ln_bwd_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
-      ln_bwd_wide_kernel<4><<<grid, 256, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, R);
+      DCPT_CUDA(dcpt_launch_pdl(ln_bwd_wide_kernel<4>, dim3(grid), dim3(256), smem, st, dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, R));
     }
     DCPT_LAUNCH_CHECK();
     return 0;
@@ -366,7 +369,7 @@ int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const floa
   const size_t smem = (size_t)3 * C * sizeof(float);
   DCPT_PROF(dcpt_prof_tag2("ln_bwd", M, C), 20.0 * M * C, (2.0 + 4.0 + (dres ? 4.0 : 0.0) + 4.0 + (dx_bf16 ? 2.0 : 0.0)) * M * C, st);
 #define LN_BWD(NVV, WW, MB) \
-  ln_bwd_kernel<NVV, WW, MB><<<(int)grid, WW * 32, smem, st>>>(dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr)
+  DCPT_CUDA(dcpt_launch_pdl(ln_bwd_kernel<NVV, WW, MB>, dim3((unsigned)grid), dim3(WW * 32), smem, st, dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr))
   if (nv <= 1) LN_BWD(1, 16, 2);
   else if (nv <= 2) LN_BWD(2, 16, 1);
   else if (nv <= 4) LN_BWD(4, 4, 4);

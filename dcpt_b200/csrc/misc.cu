@@ -10,6 +10,7 @@ namespace {
 // s[n][co] = b[co] + (1/HW) * sum_ci W[co][ci] * pool[n][ci]           (one warp per output)
 __global__ void sca_fwd_kernel(const float* __restrict__ pool, const float* __restrict__ w, const float* __restrict__ b,
                                float* __restrict__ s, int N, int C, float inv_hw) {
+  pdl_sync();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= N * C) return;
   const int n = gw / C, co = gw - n * C;
@@ -21,6 +22,7 @@ __global__ void sca_fwd_kernel(const float* __restrict__ pool, const float* __re
 
 __global__ void scale_rows_kernel(const bf16* __restrict__ g, const float* __restrict__ s, bf16* __restrict__ gs, long long nvec,
                                   int HW, int C) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   const int CV = C >> 3;
@@ -68,6 +70,7 @@ sca_ds_reduce_kernel(const bf16* __restrict__ dgs, const bf16* __restrict__ g, f
 // dW[co][ci] += (1/HW) sum_n ds[n][co] pool[n][ci];  db[co] += sum_n ds[n][co]
 __global__ void sca_bwd_w_kernel(const float* __restrict__ ds, const float* __restrict__ pool, float* __restrict__ dw,
                                  float* __restrict__ db, int N, int C, float inv_hw) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long CC = (long long)C * C;
   if (i < CC) {
@@ -87,6 +90,7 @@ __global__ void sca_bwd_w_kernel(const float* __restrict__ ds, const float* __re
 __global__ void __launch_bounds__(256)
 sca_bwd_t_kernel(const float* __restrict__ ds, const float* __restrict__ w, float* __restrict__ t, int C, float inv_hw) {
   __shared__ float s_part[8][32];
+  pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ci = blockIdx.x * 32 + lane, n = blockIdx.y;
   float acc = 0.f;
@@ -228,6 +232,7 @@ __global__ void pack_bias_kernel(const float* __restrict__ bias, const float* __
 __global__ void wgrad_finish_resid_kernel(const float* __restrict__ G, const float* __restrict__ w, const float* __restrict__ bias,
                                           const float* __restrict__ scale, const float* __restrict__ colsum, float* __restrict__ dw,
                                           float* __restrict__ dbias, float* __restrict__ dscale, int O, int I) {
+  pdl_sync();
   const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (o >= O) return;
   const float sc = scale[o];
@@ -319,7 +324,7 @@ __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ s
 int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, int N, int C, int HW, cudaStream_t st) {
   const long long threads = (long long)N * C * 32;
   DCPT_PROF("sca_fwd", 2.0 * N * C * C, 4.0 * C * C, st);
-  sca_fwd_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, st>>>(pool, w, b, s, N, C, 1.f / (float)HW);
+  DCPT_CUDA(dcpt_launch_pdl(sca_fwd_kernel, dim3((unsigned)ceil_div_ll(threads, 256)), dim3(256), 0, st, pool, w, b, s, N, C, 1.f / (float)HW));
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -327,7 +332,7 @@ int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, 
 int scale_rows_launch(const bf16* g, const float* s, bf16* gs, int N, int HW, int C, cudaStream_t st) {
   const long long nvec = (long long)N * HW * (C / 8);
   DCPT_PROF("scale_rows", (double)N * HW * C, 4.0 * N * HW * C, st);
-  scale_rows_kernel<<<(unsigned)ceil_div_ll(nvec, 256), 256, 0, st>>>(g, s, gs, nvec, HW, C);
+  DCPT_CUDA(dcpt_launch_pdl(scale_rows_kernel, dim3((unsigned)ceil_div_ll(nvec, 256)), dim3(256), 0, st, g, s, gs, nvec, HW, C));
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -353,10 +358,10 @@ int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t,
                    cudaStream_t st) {
   const long long total = (long long)C * C + C;
   DCPT_PROF("sca_bwd", 4.0 * N * C * C, 12.0 * C * C, st);
-  sca_bwd_w_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(ds, pool, dw, db, N, C, 1.f / (float)HW);
+  DCPT_CUDA(dcpt_launch_pdl(sca_bwd_w_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, st, ds, pool, dw, db, N, C, 1.f / (float)HW));
   DCPT_LAUNCH_CHECK();
   dim3 grid(ceil_div(C, 32), N);
-  sca_bwd_t_kernel<<<grid, 256, 0, st>>>(ds, w, t, C, 1.f / (float)HW);
+  DCPT_CUDA(dcpt_launch_pdl(sca_bwd_t_kernel, grid, dim3(256), 0, st, ds, w, t, C, 1.f / (float)HW));
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -407,7 +412,7 @@ int pack_bias_launch(const float* bias, const float* scale, float* out, int O, i
 int wgrad_finish_resid_launch(const float* G, const float* w, const float* bias, const float* scale, const float* colsum,
                               float* dw, float* dbias, float* dscale, int O, int I, cudaStream_t st) {
   DCPT_PROF("wgrad_finish_resid", 4.0 * O * I, 16.0 * O * I, st);
-  wgrad_finish_resid_kernel<<<ceil_div(O * 32, 256), 256, 0, st>>>(G, w, bias, scale, colsum, dw, dbias, dscale, O, I);
+  DCPT_CUDA(dcpt_launch_pdl(wgrad_finish_resid_kernel, dim3(ceil_div(O * 32, 256)), dim3(256), 0, st, G, w, bias, scale, colsum, dw, dbias, dscale, O, I));
   DCPT_LAUNCH_CHECK();
   return 0;
 }
