@@ -43,6 +43,7 @@ struct EpiParams {
   const bf16* gaux;
   int ldgaux;
   int rows_per_img;
+  long long out_batch_stride;  // ATOMIC with GemmArgs::k_per_batch: element offset of out_f32 between batches
 };
 
 struct GemmArgs {
@@ -56,6 +57,13 @@ struct GemmArgs {
   int splits;  // >1 only with EPI_ATOMIC
   int epi;
   EpiParams ep;
+  // Batched forms (Restormer MDTA, one problem per image in ONE launch):
+  //  * K-major STORE: B is a stack of per-batch [N, K] matrices; the M tile starting at row m reads the matrix of batch
+  //    m / m_per_batch, i.e. B rows offset by (m / m_per_batch) * b_rows_per_batch (m_per_batch % 128 == 0).
+  //  * MN-major ATOMIC: the K axis is a concatenation of batches of k_per_batch (multiple of 64) contraction indices; every
+  //    split stays inside one batch and accumulates into out_f32 + batch * ep.out_batch_stride.  `splits` = splits per batch.
+  int m_per_batch, b_rows_per_batch;
+  int k_per_batch;
 };
 
 // Geometry of the implicit-GEMM 3x3 convolution modes of the tensor-core kernel (gemm_sm100.cu).

@@ -51,6 +51,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
 }  // namespace
 
 int gemm_simt_launch(const GemmArgs& g, cudaStream_t stream) {
+  DCPT_CHECK_ARG(g.m_per_batch == 0 && g.k_per_batch == 0, DCPT_E_UNSUPPORTED, "gemm(simt): batched forms are tensor-core only");
   DCPT_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0 && g.N % 8 == 0, DCPT_E_SHAPE, "gemm(simt): bad shape M=%d N=%d K=%d", g.M, g.N,
                  g.K);
   DCPT_CHECK_ARG(g.splits <= 1 || g.epi == EPI_ATOMIC, DCPT_E_ARG, "gemm(simt): split-K needs the atomic epilogue");

@@ -22,6 +22,12 @@
 
 namespace {
 
+// batched problems in one launch (GemmArgs::m_per_batch / k_per_batch); all zero = plain GEMM
+struct BatchGeom {
+  int m_per_batch, b_rows_per_batch;  // K-major: B row offset per batch of M rows
+  int kb_per_batch, splits_per_batch; // MN-major split-K: k-blocks and splits per batch
+};
+
 struct EpiMaps {
   // EPI_STORE_TMA: fp32 output, bf16 output, fp32 residual.  EPI_GATE_BWD_TMA: o16 = d(x4), r32 = x4 (bf16 [M, 2C]).
   // EPI_GATE_TMA: o16 = x4 (bf16 [M, 2C]), o2 = sg (bf16 [M, C]).  Unused by the register-staged epilogues.
@@ -88,7 +94,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 template <int BN, int EPI, bool A_MN, bool B_MN, int CONV>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ EpiMaps em,
-               int M, int N, int K, int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep, ConvGeom cg) {
+               int M, int N, int K, int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep, ConvGeom cg, BatchGeom bg) {
   using C = Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -164,8 +170,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_t = tile % tiles_n;
         const int m_t = (tile / tiles_n) % tiles_m;
         const int sp = tile / (tiles_n * tiles_m);
-        const int kb0 = sp * kb_per_split;
-        const int kb1 = min(num_kb, kb0 + kb_per_split);
+        int kb0 = sp * kb_per_split;
+        int kb1 = min(num_kb, kb0 + kb_per_split);
+        if (bg.kb_per_batch > 0) {  // splits never straddle a batch
+          const int bi = sp / bg.splits_per_batch, ls = sp - bi * bg.splits_per_batch;
+          kb0 = bi * bg.kb_per_batch + ls * kb_per_split;
+          kb1 = min((bi + 1) * bg.kb_per_batch, kb0 + kb_per_split);
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           // L2 prefetch of the HBM-streamed operand(s), PF_DIST k-blocks ahead of the smem ring (which can hold
           // only STAGES blocks in flight: not enough to cover DRAM latency for a short-K tile).
@@ -206,7 +217,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * 8192, &tmA, &full[stage], m_t * BM + c * 64, kb * BK);
             }
             if constexpr (!B_MN) {
-              tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, n_t * BN);
+              const int brow = bg.m_per_batch > 0 ? (m_t * BM / bg.m_per_batch) * bg.b_rows_per_batch : 0;
+              tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, brow + n_t * BN);
             } else {
 #pragma unroll
               for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, &tmB, &full[stage], n_t * BN + c * 64, kb * BK);
@@ -229,8 +241,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int sp = tile / (tiles_n * tiles_m);
-        const int kb0 = sp * kb_per_split;
-        const int kb1 = min(num_kb, kb0 + kb_per_split);
+        int kb0 = sp * kb_per_split;
+        int kb1 = min(num_kb, kb0 + kb_per_split);
+        if (bg.kb_per_batch > 0) {  // splits never straddle a batch
+          const int bi = sp / bg.splits_per_batch, ls = sp - bi * bg.splits_per_batch;
+          kb0 = bi * bg.kb_per_batch + ls * kb_per_split;
+          kb1 = min((bi + 1) * bg.kb_per_batch, kb0 + kb_per_split);
+        }
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -510,6 +527,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_t = tile % tiles_n;
       const int m_t = (tile / tiles_n) % tiles_m;
       const int m_base = m_t * BM + q * 32;
+      EpiParams ept = ep;  // per-tile view of the epilogue parameters (batched split-K: output of this split's batch)
+      if constexpr (EPI == EPI_ATOMIC) {
+        if (bg.kb_per_batch > 0) ept.out_f32 += (size_t)((tile / (tiles_n * tiles_m)) / bg.splits_per_batch) * ep.out_batch_stride;
+      }
       // row r of this warp's 32-row slab -> global output row (or -1): linear for GEMMs, patch pixel for CONV == 1
       int cv_img = 0, cv_h0 = 0, cv_w0 = 0;
       if constexpr (CONV == 1) {
@@ -619,7 +640,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float4 x = lds_f4(stage + (uint32_t)(r * 8 + (cc ^ (r & 7))) * 16u);
             const int m = out_row(r);
             ex.r = cur[it];
-            if (m >= 0 && n < N) epilogue_store<EPI>(ep, m, n, x, x, ex);
+            if (m >= 0 && n < N) epilogue_store<EPI>(ept, m, n, x, x, ex);
           }
           __syncwarp();
           if constexpr (kRowLoads) {
@@ -749,15 +770,33 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   }
   if (!g.a_mn) DCPT_TRY(make_tmap_2d(&tmA, g.A, g.M, g.K, g.lda, BM));
   else DCPT_TRY(make_tmap_2d(&tmA, g.A, g.K, g.M, g.lda, 64));
-  if (!g.b_mn) DCPT_TRY(make_tmap_2d(&tmB, g.B, g.N, g.K, g.ldb, BN));
+  if (!g.b_mn) DCPT_TRY(make_tmap_2d(&tmB, g.B, g.m_per_batch > 0 ? (long long)(g.M / g.m_per_batch) * g.b_rows_per_batch : g.N, g.K, g.ldb, BN));
   else DCPT_TRY(make_tmap_2d(&tmB, g.B, g.K, g.N, g.ldb, 64));
 
   const int tiles_m = ceil_div(g.M, BM), tiles_n = ceil_div(g.N, BN);
   const int num_kb = ceil_div(g.K, BK);
   int splits = g.splits < 1 ? 1 : g.splits;
-  if (splits > num_kb) splits = num_kb;
-  int kbps = ceil_div(num_kb, splits);
-  splits = ceil_div(num_kb, kbps);  // every split gets >= 1 k-block
+  BatchGeom bg = {};
+  int kbps;
+  if (g.k_per_batch > 0) {  // batched split-K: `splits` per batch, none straddles a batch
+    DCPT_CHECK_ARG(g.a_mn && g.b_mn && EPI == EPI_ATOMIC && g.k_per_batch % BK == 0 && g.K % g.k_per_batch == 0, DCPT_E_ARG,
+                   "gemm: batched split-K needs MN-major operands, the atomic epilogue and k_per_batch %% 64 == 0");
+    bg.kb_per_batch = g.k_per_batch / BK;
+    if (splits > bg.kb_per_batch) splits = bg.kb_per_batch;
+    kbps = ceil_div(bg.kb_per_batch, splits);
+    bg.splits_per_batch = ceil_div(bg.kb_per_batch, kbps);
+    splits = bg.splits_per_batch * (g.K / g.k_per_batch);
+  } else {
+    if (splits > num_kb) splits = num_kb;
+    kbps = ceil_div(num_kb, splits);
+    splits = ceil_div(num_kb, kbps);  // every split gets >= 1 k-block
+  }
+  if (g.m_per_batch > 0) {
+    DCPT_CHECK_ARG(!g.a_mn && !g.b_mn && g.m_per_batch % BM == 0 && g.M % g.m_per_batch == 0, DCPT_E_ARG,
+                   "gemm: batched B needs K-major operands and m_per_batch %% 128 == 0 (m_per_batch=%d)", g.m_per_batch);
+    bg.m_per_batch = g.m_per_batch;
+    bg.b_rows_per_batch = g.b_rows_per_batch;
+  }
   const int total = tiles_m * tiles_n * splits;
   const int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
 
@@ -783,7 +822,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
                                                 (EPI == EPI_GATE_BWD || EPI == EPI_GATE_BWD_TMA ? 4.0 : 0.0));
   DCPT_PROF(tag, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes, stream);
   DCPT_CUDA(dcpt_launch_pdl(kern, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, em, g.M, g.N, g.K, tiles_m, tiles_n, splits,
-                            kbps, g.ep, cg0));
+                            kbps, g.ep, cg0, bg));
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -829,7 +868,7 @@ int conv_fwd_cfg(const Conv3x3Args& a, cudaStream_t stream) {
   const double Mpx = (double)a.N * a.H * a.W;
   DCPT_PROF(BN == 256 ? "conv3x3_tc<256>" : (BN == 128 ? "conv3x3_tc<128>" : "conv3x3_tc<64>"), 2.0 * Mpx * a.Cout * 9 * a.Cin,
             2.0 * Mpx * (a.Cin + a.Cout), stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, a.N * a.H * a.W, a.Cout, num_kb * BK, tiles_m, tiles_n, 1, num_kb, a.ep, cg);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, a.N * a.H * a.W, a.Cout, num_kb * BK, tiles_m, tiles_n, 1, num_kb, a.ep, cg, BatchGeom{});
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -861,7 +900,7 @@ int conv_wgrad_cfg(const bf16* dY, const bf16* X, float* G, int N, int H, int W,
   }
   const double Mpx = (double)N * H * W;
   DCPT_PROF("conv3x3_wgrad_tc", 2.0 * Mpx * Cout * 9 * Cin, 2.0 * Mpx * (Cin + Cout), stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, Cout, 9 * cin_pad, num_kb * BK, tiles_m, tiles_n, splits, kbps, ep, cg);
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, Cout, 9 * cin_pad, num_kb * BK, tiles_m, tiles_n, splits, kbps, ep, cg, BatchGeom{});
   DCPT_LAUNCH_CHECK();
   return 0;
 }

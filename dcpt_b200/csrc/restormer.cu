@@ -256,7 +256,17 @@ int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
   DCPT_CUDA(cudaMemsetAsync(ws.sq, 0, (size_t)N * 2 * d * sizeof(float), st));
   DCPT_TRY(dwconv3_fwd_launch(ws.a, P[ix.qkv_dw], ws.b, ws.sq, 2 * d, N, H, W, 3 * d, st));
   DCPT_CUDA(cudaMemsetAsync(ws.G, 0, (size_t)N * d * d * sizeof(float), st));
-  for (int n = 0; n < N; ++n) {  // G[n] = q^T k over the HW pixels of image n (both operands MN-major, split-K)
+  const bool batched = N > 1 && HW % 128 == 0;  // one launch for all images (tiles / splits never straddle an image)
+  if (batched) {
+    GemmArgs g = make_gemm_args(d, d, N * HW, ws.b, 3 * d, ws.b + d, 3 * d, EPI_ATOMIC);
+    g.a_mn = 1; g.b_mn = 1;
+    g.k_per_batch = HW;
+    const int bn = d > 128 ? 256 : (d > 64 ? 128 : 64);
+    g.splits = gemm_auto_splits(ceil_div(d, 128) * ceil_div(d, bn) * N, ceil_div(HW, 64));
+    g.ep.out_f32 = ws.G; g.ep.ldo = d; g.ep.out_batch_stride = (long long)d * d;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  for (int n = 0; n < N && !batched; ++n) {  // G[n] = q^T k over the HW pixels of image n (both operands MN-major, split-K)
     const bf16* q = ws.b + (size_t)n * HW * 3 * d;
     GemmArgs g = make_gemm_args(d, d, HW, q, 3 * d, q + d, 3 * d, EPI_ATOMIC);
     g.a_mn = 1; g.b_mn = 1;
@@ -274,7 +284,13 @@ int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
     mdta_weff_kernel<<<dim3(b.heads, N), 256, smem, st>>>(ws.G, ws.sq, P[ix.temp], P[ix.pout], ws.weff, d, b.heads);
     DCPT_LAUNCH_CHECK();
   }
-  for (int n = 0; n < N; ++n) {  // x2[n] = x[n] + v[n] * W_eff[n]^T
+  if (batched) {  // x2 = x + v * W_eff[image]^T, the B operand switches with the image of the M tile
+    GemmArgs g = make_gemm_args(M, d, d, ws.b + 2 * d, 3 * d, ws.weff, d, EPI_STORE);
+    g.m_per_batch = HW; g.b_rows_per_batch = d;
+    g.ep.out_f32 = x2; g.ep.ldo = d; g.ep.resid = x; g.ep.ldr = d;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  for (int n = 0; n < N && !batched; ++n) {  // x2[n] = x[n] + v[n] * W_eff[n]^T
     const size_t r0 = (size_t)n * HW;
     GemmArgs g = make_gemm_args(HW, d, d, ws.b + r0 * 3 * d + 2 * d, 3 * d, ws.weff + (size_t)n * d * d, d, EPI_STORE);
     g.ep.out_f32 = x2 + r0 * d; g.ep.ldo = d; g.ep.resid = x + r0 * d; g.ep.ldr = d;

@@ -6,6 +6,7 @@ no CPU path.  Training (backward) of the Restormer blocks is not built yet: call
 enabled on its parameters raises ``DcptError`` instead of silently returning a graph-less tensor.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -31,6 +32,9 @@ class RestormerEngine:
         self._packed = None
         self._packed_key = None
         self._work = {}
+        # whole-forward CUDA-graph replay (~700 launches per 128x128 tile become one); DCPT_CUDA_GRAPH=0 launches eagerly
+        self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0"
+        self._graphs = {}
 
     def __del__(self):
         try:
@@ -72,6 +76,8 @@ class RestormerEngine:
         k = (N, H, W, dev)
         if k not in self._work:
             self._work[k] = torch.empty(self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
+        if self.use_graphs and not torch.cuda.is_current_stream_capturing():
+            return self._graph_forward(params, packed, inp, bool(hook), bool(want_feats))
         out = None if hook else torch.empty_like(inp)
         feats = fp = None
         if want_feats:
@@ -83,4 +89,37 @@ class RestormerEngine:
         pp = _l.ptr_array([p.data_ptr() for p in params])
         _l.check(self.lib.dcpt_restormer_fwd(self.plan, pp, _p(packed), _p(inp), _p(out), _p(self._work[k]), fp, int(bool(hook)),
                                              N, H, W, _stream()), "restormer_fwd")
+        return out, feats
+
+    def _graph_forward(self, params, packed, inp, hook, want_feats):
+        N, _, H, W = inp.shape
+        dev = inp.device
+        key = (N, H, W, dev, hook, want_feats, tuple(p.data_ptr() for p in params))
+        ent = self._graphs.get(key)
+        if ent is None:
+            d = self.dim
+            ent = {"inp": torch.empty_like(inp), "out": None if hook else torch.empty_like(inp), "feats": None, "graph": None}
+            if want_feats:
+                ent["feats"] = [torch.empty(N, H // 4, W // 4, 4 * d, dtype=torch.float32, device=dev),
+                                torch.empty(N, H // 2, W // 2, 2 * d, dtype=torch.float32, device=dev),
+                                torch.empty(N, H, W, 2 * d, dtype=torch.float32, device=dev)]
+            self._graphs[key] = ent
+        ent["inp"].copy_(inp)
+        work = self._work[(N, H, W, dev)]
+        pp = _l.ptr_array([p.data_ptr() for p in params])
+        fp = _l.ptr_array([f.data_ptr() for f in ent["feats"]]) if ent["feats"] else None
+
+        def run():
+            _l.check(self.lib.dcpt_restormer_fwd(self.plan, pp, _p(packed), _p(ent["inp"]), _p(ent["out"]), _p(work), fp, int(hook),
+                                                 N, H, W, _stream()), "restormer_fwd")
+        if ent["graph"] is None:
+            run()                       # eager once: one-time initialisation inside the library must not be captured
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                run()
+            ent["graph"] = g
+        else:
+            ent["graph"].replay()
+        out = None if hook else ent["out"].clone()
+        feats = [f.clone() for f in ent["feats"]] if ent["feats"] else None
         return out, feats
