@@ -273,6 +273,14 @@ def run_ours(args):
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"kernel": top["tag"], "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
                     "frac": round(ach / pk["hbm"], 4), "traffic": None}
+        try:  # DRAM traffic of the same kernel from the committed ncu --set full capture (per launch), else null
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            key = top["tag"].split(" ")[0]
+            if key in tr:
+                roof["traffic"] = tr[key]["bytes"]
+                roof["traffic_note"] = tr[key]["launch"] + "; " + tr["_how"]
+        except Exception:
+            pass
         roof.update({"peak_source": pk["src"] + (", sustained (kernel timed inside the step)" if is_gemm else ""),
                      "share_of_step": round(top["ms"] / tot, 4), "launches_per_step": top["launches"],
                      "avg_launch_us": round(top["ms"] * 1e3 / top["launches"], 2),

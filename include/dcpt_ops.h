@@ -80,7 +80,9 @@ int dcpt_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int
 /* Full-control variant used by the tests to exercise every fused epilogue of the GEMM engine.
  * epilogue: 0 STORE (bias/resid -> fp32 and/or bf16), 1 GATE (conv4 -> x4 + SimpleGate, nafnet_arch.py:180-181),
  * 2 GATE_BWD (SimpleGate backward), 3 PIXSHUF (PixelShuffle(2) scatter + skip add, nafnet_arch.py:238-242,264-265),
- * 4 ATOMIC (split-K wgrad accumulate). */
+ * 4 ATOMIC (split-K wgrad accumulate), 7 GATE on 32-wide pair packing (packed column 64p + 32h + i <-> channel h*C + 32p + i,
+ * C % 32 == 0; what the NAFBlock path uses: x4 / SimpleGate tiles leave through TMA bulk stores).  STORE and GATE_BWD
+ * pick their TMA-tiled epilogue automatically when rows are 16-byte pitched (and C % 32 == 0). */
 typedef struct dcpt_gemm_desc {
   int M, N, K;
   const void* A; int lda; int a_mn;
