@@ -18,8 +18,10 @@ __device__ __forceinline__ float group_sum(float v, int lpr) {
   return v;
 }
 
-template <int NV>
-__global__ void __launch_bounds__(kWarps * 32)
+// U independent row groups per warp iteration: with narrow rows (C <= 128) a lane moves only 16-32 bytes per row, and
+// one row per iteration leaves the kernel latency-bound (2.6 TB/s at C = 64); U = 4 keeps 4x the bytes in flight.
+template <int NV, int U>
+__global__ void __launch_bounds__(kWarps * 32, NV <= 4 ? 4 : 2)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
               float* __restrict__ stats, int M, int C, int lpr, float eps, int center) {
   pdl_sync();
@@ -29,50 +31,70 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   const int nvec = C >> 2;
   const float invC = 1.f / (float)C;
   const long long row_stride = (long long)gridDim.x * kWarps * rpw;
-  for (long long row = ((long long)blockIdx.x * kWarps + warp) * rpw + gr; row - gr < M; row += row_stride) {
-    const bool valid = row < M;
-    float4 xv[NV];
-    float sum = 0.f;
+  constexpr bool kHoist = NV <= 2;  // wide rows reload the affine parameters per row (L1 hits) to keep 4 blocks per SM
+  float4 wv[NV], bv[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = sub + i * lpr;
-      xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid && v < nvec) xv[i] = __ldg(reinterpret_cast<const float4*>(x + row * C) + v);
-      sum += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
-    }
-    const float mean = group_sum(sum, lpr) * invC;
-    float sq = 0.f;
+  for (int i = 0; i < NV; ++i) {
+    const int v = sub + i * lpr;
+    wv[i] = (kHoist && v < nvec) ? __ldg(reinterpret_cast<const float4*>(w) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bv[i] = (kHoist && b && v < nvec) ? __ldg(reinterpret_cast<const float4*>(b) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long row0 = ((long long)blockIdx.x * kWarps + warp) * rpw + gr; row0 - gr < M; row0 += row_stride * U) {
+    float4 xv[U][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = sub + i * lpr;
-      if (v < nvec) {
-        const float a = xv[i].x - mean, bb = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
-        sq += a * a + bb * bb + c * c + d * d;
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * row_stride;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = sub + i * lpr;
+        xv[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < M && v < nvec) xv[u][i] = __ldg(reinterpret_cast<const float4*>(x + row * C) + v);
       }
     }
-    const float var = group_sum(sq, lpr) * invC;
-    const float rstd = 1.f / sqrtf(var + eps);
-    // center == 0: Restormer's BiasFree_LayerNorm (restormer_arch.py:38-40) - variance about the mean, numerator NOT centred
-    const float shift = center ? mean : 0.f;
-    if (valid) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * row_stride;
+      if (row - gr >= M) break;  // warp-uniform: the whole row group is out of range
+      const bool valid = row < M;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sum += xv[u][i].x + xv[u][i].y + xv[u][i].z + xv[u][i].w;
+      const float mean = group_sum(sum, lpr) * invC;
+      float sq = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int v = sub + i * lpr;
         if (v < nvec) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + v);
-          const float4 bv = b ? __ldg(reinterpret_cast<const float4*>(b) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float o0 = (xv[i].x - shift) * rstd * wv.x + bv.x;
-          const float o1 = (xv[i].y - shift) * rstd * wv.y + bv.y;
-          const float o2 = (xv[i].z - shift) * rstd * wv.z + bv.z;
-          const float o3 = (xv[i].w - shift) * rstd * wv.w + bv.w;
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&p0);
-          pk.y = *reinterpret_cast<uint32_t*>(&p1);
-          *(reinterpret_cast<uint2*>(out + row * C) + v) = pk;
+          const float a = xv[u][i].x - mean, bb = xv[u][i].y - mean, c = xv[u][i].z - mean, d = xv[u][i].w - mean;
+          sq += a * a + bb * bb + c * c + d * d;
         }
       }
-      if (stats && sub == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
+      const float var = group_sum(sq, lpr) * invC;
+      const float rstd = 1.f / sqrtf(var + eps);
+      // center == 0: Restormer's BiasFree_LayerNorm (restormer_arch.py:38-40) - variance about the mean, numerator NOT centred
+      const float shift = center ? mean : 0.f;
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int v = sub + i * lpr;
+          if (v < nvec) {
+            if constexpr (!kHoist) {
+              wv[i] = __ldg(reinterpret_cast<const float4*>(w) + v);
+              if (b) bv[i] = __ldg(reinterpret_cast<const float4*>(b) + v);
+            }
+            const float o0 = (xv[u][i].x - shift) * rstd * wv[i].x + bv[i].x;
+            const float o1 = (xv[u][i].y - shift) * rstd * wv[i].y + bv[i].y;
+            const float o2 = (xv[u][i].z - shift) * rstd * wv[i].z + bv[i].z;
+            const float o3 = (xv[u][i].w - shift) * rstd * wv[i].w + bv[i].w;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *(reinterpret_cast<uint2*>(out + row * C) + v) = pk;
+          }
+        }
+        if (stats && sub == 0) *reinterpret_cast<float2*>(stats + row * 2) = make_float2(mean, rstd);
+      }
     }
   }
 }
@@ -329,13 +351,16 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
   const int lpr = pick_lpr(C);
   const int nv = ceil_div(C / 4, lpr);
   const int rows_per_block = kWarps * (32 / lpr);
-  const int grid = (int)ceil_div_ll(M, rows_per_block);
+  // U row groups per warp iteration (see the kernel); the grid is sized so that every warp gets its U groups
+  const int U = nv <= 1 ? 4 : (nv <= 2 ? 2 : 1);
+  long long grid = ceil_div_ll(M, (long long)rows_per_block * U);
+  if (grid < 1) grid = 1;
   DCPT_PROF(dcpt_prof_tag2("ln_fwd", M, C), 8.0 * M * C, 6.0 * M * C, st);
-#define LN_FWD(NVV) DCPT_CUDA(dcpt_launch_pdl(ln_fwd_kernel<NVV>, dim3(grid), dim3(kWarps * 32), 0, st, x, w, b, n_out, stats, M, C, lpr, eps, center))
-  if (nv <= 1) LN_FWD(1);
-  else if (nv <= 2) LN_FWD(2);
-  else if (nv <= 4) LN_FWD(4);
-  else LN_FWD(8);
+#define LN_FWD(NVV, UU) DCPT_CUDA(dcpt_launch_pdl(ln_fwd_kernel<NVV, UU>, dim3((unsigned)grid), dim3(kWarps * 32), 0, st, x, w, b, n_out, stats, M, C, lpr, eps, center))
+  if (nv <= 1) LN_FWD(1, 4);
+  else if (nv <= 2) LN_FWD(2, 2);
+  else if (nv <= 4) LN_FWD(4, 1);
+  else LN_FWD(8, 1);
 #undef LN_FWD
   DCPT_LAUNCH_CHECK();
   return 0;
