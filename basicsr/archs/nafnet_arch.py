@@ -159,3 +159,35 @@ class NAFNetBaseline(nn.Module):
         if not hook:
             return out
         return None
+
+
+@ARCH_REGISTRY.register()
+class NAFNet(NAFNetBaseline):
+    """nafnet_arch.py:277-288 - ``Local_Base`` + ``NAFNetBaseline``: the test-time local converter (TLC).  The reference
+    replaces every ``AdaptiveAvgPool2d(1)`` of the SCA branches by ``AvgPool2d(base_size = 1.5 x train_size)``
+    (arch_util.py:436-455) and fixes the per-level kernels with one forward on a ``train_size`` dummy input; here the same
+    kernels are computed in closed form and handed to the C plan (``dcpt_nafnet_set_tlc``).  Parameters and ``state_dict``
+    are those of ``NAFNetBaseline``.  Inference only (the reference constructs it in ``eval()`` mode)."""
+
+    def __init__(self, *args, train_size=(1, 3, 128, 128), fast_imp=False, **kwargs):
+        super().__init__(*args, **kwargs)
+        if fast_imp:
+            raise DcptError("NAFNet(fast_imp=True) (the non-equivalent strided approximation, arch_util.py:355-377) is not built")
+        self.train_size = tuple(train_size)
+        H, W = self.train_size[-2], self.train_size[-1]
+        bh, bw = int(H * 1.5), int(W * 1.5)                                   # nafnet_arch.py:284-285
+        n_levels = len(self._cfg[3]) + 1
+        # arch_util.py:341-347: kernel = feature-map size of the dummy forward * base_size // train_size, per level
+        self.tlc_kernels = [((H >> l) * bh // H, (W >> l) * bw // W) for l in range(n_levels)]
+        self.eval()
+
+    def engine(self):
+        eng = super().engine()
+        if not eng.tlc:
+            eng.set_tlc(self.tlc_kernels)
+        return eng
+
+    def forward(self, inp, hook=False):
+        if torch.is_grad_enabled() and (inp.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise DcptError("NAFNet (TLC) is a test-time converter: call it under torch.no_grad() (SRModel.test does)")
+        return super().forward(inp, hook=hook)

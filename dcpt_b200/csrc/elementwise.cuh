@@ -35,6 +35,9 @@ int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int H
 int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t, float* dw, float* db, int N, int C, int HW,
                    cudaStream_t st);
 
+// TLC (test-time local converter, arch_util.py:339-398): P = replicate-padded k1 x k2 box mean of g; I = fp32 scratch [N,H,W,C]
+int tlc_boxmean_launch(const bf16* g, float* I, bf16* P, int N, int H, int W, int C, int k1, int k2, cudaStream_t st);
+int mul_bf16_launch(const bf16* a, const bf16* b, bf16* out, long long n, cudaStream_t st);
 int colsum_bf16_launch(const bf16* x, float* out, int M, int C, cudaStream_t st);
 // out = a + b (either nullable -> treated as 0): fp32 (nullable), bf16 mirror (nullable), colsum += column sums (nullable).
 int grad_prepare_launch(const float* a, const float* b, float* out, bf16* out_bf16, float* colsum, int M, int C,

@@ -106,6 +106,91 @@ sca_bwd_t_kernel(const float* __restrict__ ds, const float* __restrict__ w, floa
   }
 }
 
+// ------------------------------ TLC local pooling --------------------------------
+// Test-time local converter (reference: AvgPool2d.forward, arch_util.py:339-398, non-fast path): the SCA pooling of the
+// `NAFNet` variant is a k1 x k2 box mean taken from a 2-D cumulative sum, replicate-padded back to H x W.  Same algorithm
+// here: fp32 inclusive prefix sums along W, then along H (in place), then the four-corner difference per pixel.
+// g bf16 [N,H,W,C] -> I fp32 [N,H,W,C]; thread = (n, y, 8-channel vector), sequential over x
+__global__ void tlc_rowsum_kernel(const bf16* __restrict__ g, float* __restrict__ I, long long total, int W, int C) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int CV = C >> 3;
+  const int cv = (int)(idx % CV);
+  const long long ny = idx / CV;
+  const size_t base = (size_t)ny * W * C + cv * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int x = 0; x < W; ++x) {
+    float v[8];
+    unpack8(ldg16(g + base + (size_t)x * C), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    float4* o = reinterpret_cast<float4*>(I + base + (size_t)x * C);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+// in-place prefix sums along H; thread = (n, x, 4-channel vector)
+__global__ void tlc_colsum_kernel(float* __restrict__ I, long long total, int H, int W, int C) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C4 = C >> 2;
+  const int c4 = (int)(idx % C4);
+  const long long nx = idx / C4;
+  const int x = (int)(nx % W);
+  const long long n = nx / W;
+  float4* p = reinterpret_cast<float4*>(I + ((size_t)n * H * W + x) * C) + c4;
+  const size_t stride = (size_t)W * C / 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int y = 0; y < H; ++y) {
+    const float4 v = p[(size_t)y * stride];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    p[(size_t)y * stride] = acc;
+  }
+}
+// P[n,y,x,:] = box mean with window start (clamp(y - pt, 0, H - k1), clamp(x - pl, 0, W - k2))   (replicate padding, :391-396)
+__global__ void tlc_box_kernel(const float* __restrict__ I, bf16* __restrict__ P, long long total, int H, int W, int C, int k1, int k2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int CV = C >> 3;
+  const int cv = (int)(idx % CV);
+  const long long px = idx / CV;
+  const int x = (int)(px % W);
+  const long long t = px / W;
+  const int y = (int)(t % H);
+  const long long n = t / H;
+  const int oh = H - k1 + 1, ow = W - k2 + 1;          // size of the un-padded box-mean map
+  const int pt = (H - oh) / 2, pl = (W - ow) / 2;      // replicate padding before (after = the rest)
+  const int ys = min(max(y - pt, 0), oh - 1), xs = min(max(x - pl, 0), ow - 1);
+  const int ye = ys + k1 - 1, xe = xs + k2 - 1;
+  const float* In = I + (size_t)n * H * W * C + cv * 8;
+  auto at = [&](int yy, int xx, float (&o)[8]) {
+    if (yy < 0 || xx < 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      return;
+    }
+    const float4* q = reinterpret_cast<const float4*>(In + ((size_t)yy * W + xx) * C);
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  };
+  float s4[8], s1[8], s2[8], s3[8], r[8];
+  at(ye, xe, s4); at(ys - 1, xs - 1, s1); at(ys - 1, xe, s2); at(ye, xs - 1, s3);
+  const float inv = 1.f / (float)(k1 * k2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = (s4[i] + s1[i] - s2[i] - s3[i]) * inv;
+  stg16(P + (size_t)px * C + cv * 8, pack8(r));
+}
+__global__ void mul_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long long nvec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  float x[8], y[8];
+  unpack8(ldg16(a + i * 8), x);
+  unpack8(ldg16(b + i * 8), y);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] *= y[k];
+  stg16(out + i * 8, pack8(x));
+}
+
 // ------------------------------ column sums ------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ out, int M, int C, int cvb) {
@@ -362,6 +447,26 @@ int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t,
   DCPT_LAUNCH_CHECK();
   dim3 grid(ceil_div(C, 32), N);
   DCPT_CUDA(dcpt_launch_pdl(sca_bwd_t_kernel, grid, dim3(256), 0, st, ds, w, t, C, 1.f / (float)HW));
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int tlc_boxmean_launch(const bf16* g, float* I, bf16* P, int N, int H, int W, int C, int k1, int k2, cudaStream_t st) {
+  DCPT_CHECK_ARG(C % 8 == 0 && k1 >= 1 && k2 >= 1 && k1 <= H && k2 <= W, DCPT_E_SHAPE, "tlc box mean: bad kernel %dx%d for %dx%d (C=%d)",
+                 k1, k2, H, W, C);
+  const long long t1 = (long long)N * H * (C / 8), t2 = (long long)N * W * (C / 4), t3 = (long long)N * H * W * (C / 8);
+  DCPT_PROF("tlc_boxmean", 3.0 * N * H * W * C, 16.0 * N * H * W * C, st);
+  tlc_rowsum_kernel<<<(unsigned)ceil_div_ll(t1, 128), 128, 0, st>>>(g, I, t1, W, C);
+  tlc_colsum_kernel<<<(unsigned)ceil_div_ll(t2, 128), 128, 0, st>>>(I, t2, H, W, C);
+  tlc_box_kernel<<<(unsigned)ceil_div_ll(t3, 256), 256, 0, st>>>(I, P, t3, H, W, C, k1, k2);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int mul_bf16_launch(const bf16* a, const bf16* b, bf16* out, long long n, cudaStream_t st) {
+  DCPT_CHECK_ARG(n % 8 == 0, DCPT_E_SHAPE, "mul: element count %lld must be a multiple of 8", n);
+  DCPT_PROF("mul_bf16", (double)n, 6.0 * n, st);
+  mul_bf16_kernel<<<(unsigned)ceil_div_ll(n / 8, 256), 256, 0, st>>>(a, b, out, n / 8);
   DCPT_LAUNCH_CHECK();
   return 0;
 }

@@ -98,7 +98,7 @@ enum {  // NAFBlock parameter indices (named_parameters() order)
 };
 
 struct BlockPacked {
-  bf16 *w1, *w1t, *w3b, *w3bt, *w4p, *w4t, *w5g, *w5gt;
+  bf16 *w1, *w1t, *w3b, *w3bt, *w4p, *w4t, *w5g, *w5gt, *wsca;
   float *b3b, *b4p, *b5g;
   BlockPacked(Arena& a, int C) {
     const size_t cc = (size_t)C * C;
@@ -107,6 +107,7 @@ struct BlockPacked {
     w4p = a.take<bf16>(2 * cc); w4t = a.take<bf16>(2 * cc);
     w5g = a.take<bf16>(cc); w5gt = a.take<bf16>(cc);
     b3b = a.take<float>(C); b4p = a.take<float>(2 * C); b5g = a.take<float>(C);
+    wsca = a.take<bf16>(cc);  // SCA matrix as a GEMM operand (TLC: per-pixel pooled vectors)
   }
 };
 
@@ -171,11 +172,12 @@ int nafblock_pack_impl(const float* const* P, BlockPacked& pk, int C, cudaStream
   DCPT_TRY(pack_bias_launch(P[P_C3B], P[P_BETA], pk.b3b, C, PACK_PLAIN, st));
   DCPT_TRY(pack_bias_launch(P[P_C4B], nullptr, pk.b4p, 2 * C, pair_mode, st));
   DCPT_TRY(pack_bias_launch(P[P_C5B], P[P_GAMMA], pk.b5g, C, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[P_SCAW], nullptr, pk.wsca, C, C, PACK_PLAIN, st));
   return 0;
 }
 
 int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float* x, float* out, bf16* out_bf16,
-                      const BlockSaved& sv, int N, int H, int W, int C, cudaStream_t st) {
+                      const BlockSaved& sv, int N, int H, int W, int C, cudaStream_t st, int tlc_kh = 0, int tlc_kw = 0) {
   const int HW = H * W, M = N * HW;
   constexpr float eps = 1e-6f;  // LayerNorm2d default (nafnet_arch.py:57)
   // norm1 -> conv1 (+bias)
@@ -188,9 +190,20 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
   // conv2 (dw 3x3) + SimpleGate, global average pool partial sums
   DCPT_CUDA(cudaMemsetAsync(sv.pool, 0, (size_t)N * C * sizeof(float), st));
   DCPT_TRY(dwgate_fwd_launch(sv.u, P[P_C2W], P[P_C2B], sv.g, sv.pool, N, H, W, C, st));
-  // sca, x * sca(x)
-  DCPT_TRY(sca_fwd_launch(sv.pool, P[P_SCAW], P[P_SCAB], sv.s, N, C, HW, st));
-  DCPT_TRY(scale_rows_launch(sv.g, sv.s, sv.gs, N, HW, C, st));
+  if (tlc_kh > 0 && (tlc_kh < H || tlc_kw < W)) {
+    // TLC inference (NAFNet / Local_Base, arch_util.py:339-398): the pooled vector is a per-pixel box mean, so SCA becomes
+    // a [pixels, C] x [C, C] GEMM and a per-element product.  Scratch: y (fp32 integral image), n1 (box means), u (s map).
+    const int k1 = tlc_kh < H ? tlc_kh : H, k2 = tlc_kw < W ? tlc_kw : W;
+    DCPT_TRY(tlc_boxmean_launch(sv.g, sv.y, sv.n1, N, H, W, C, k1, k2, st));
+    GemmArgs g = gemm_args(M, C, C, sv.n1, C, pk.wsca, C, EPI_STORE);
+    g.ep.out_bf16 = sv.u; g.ep.ldo = C; g.ep.bias = P[P_SCAB];
+    DCPT_TRY(gemm_launch(g, st));
+    DCPT_TRY(mul_bf16_launch(sv.g, sv.u, sv.gs, (long long)M * C, st));
+  } else {
+    // sca, x * sca(x)
+    DCPT_TRY(sca_fwd_launch(sv.pool, P[P_SCAW], P[P_SCAB], sv.s, N, C, HW, st));
+    DCPT_TRY(scale_rows_launch(sv.g, sv.s, sv.gs, N, HW, C, st));
+  }
   // conv3, y = inp + x*beta
   {
     GemmArgs g = gemm_args(M, C, C, sv.gs, C, pk.w3b, C, EPI_STORE);
@@ -282,6 +295,7 @@ int check_block_shape(int N, int H, int W, int C) {
 // ------------------------------------------------------------------------------------
 struct dcpt_nafnet_plan {
   int img_channel, width, middle_blk_num;
+  std::vector<int> tlc_kh, tlc_kw;  // per resolution level; empty = global SCA pooling (NAFNetBaseline)
   std::vector<int> enc, dec;
   struct ParamInfo { int dims[4]; long long numel; };
   std::vector<ParamInfo> params;
@@ -645,6 +659,15 @@ dcpt_nafnet_plan* dcpt_nafnet_create(int img_channel, int width, int middle_blk_
 }
 
 void dcpt_nafnet_destroy(dcpt_nafnet_plan* plan) { delete plan; }
+
+int dcpt_nafnet_set_tlc(dcpt_nafnet_plan* plan, const int* kh, const int* kw, int n_levels) {
+  DCPT_CHECK_ARG(plan != nullptr && n_levels >= 0 && (n_levels == 0 || (kh && kw)), DCPT_E_ARG, "nafnet_set_tlc: bad arguments");
+  plan->tlc_kh.assign(kh, kh + n_levels);
+  plan->tlc_kw.assign(kw, kw + n_levels);
+  for (int i = 0; i < n_levels; ++i)
+    DCPT_CHECK_ARG(kh[i] >= 1 && kw[i] >= 1, DCPT_E_ARG, "nafnet_set_tlc: kernel of level %d must be positive", i);
+  return 0;
+}
 int dcpt_nafnet_num_params(const dcpt_nafnet_plan* plan) { return (int)plan->params.size(); }
 long long dcpt_nafnet_param_shape(const dcpt_nafnet_plan* plan, int i, int dims[4]) {
   if (i < 0 || i >= (int)plan->params.size()) return -1;
@@ -704,6 +727,8 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   NetSaved sv(p, as, N, H, W);
   const int ne = (int)p->enc.size(), nd = (int)p->dec.size();
   int C = p->width, h = H, w = W;
+  auto tkh = [&](int lvl) { return lvl < (int)p->tlc_kh.size() ? p->tlc_kh[lvl] : 0; };
+  auto tkw = [&](int lvl) { return lvl < (int)p->tlc_kw.size() ? p->tlc_kw[lvl] : 0; };
 
   // intro (nafnet_arch.py:252)
   {  // x0 = im2col(inp) * Wi^T + b on the tensor cores
@@ -717,7 +742,7 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   for (int i = 0; i < ne; ++i) {
     for (int j = 0; j < p->enc[i]; ++j) {
       DCPT_TRY(nafblock_fwd_impl(P + p->enc_blks[i][j].pidx, pk.enc_pk[i][j], x, sv.enc_out[i][j], nullptr, sv.enc_sv[i][j], N, h,
-                                 w, C, st));
+                                 w, C, st, tkh(i), tkw(i)));
       x = sv.enc_out[i][j];
     }
     DCPT_TRY(unshuffle_cast_launch(x, sv.xu[i], N, h / 2, w / 2, C, st));
@@ -732,7 +757,8 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   // middle (:261)
   for (int j = 0; j < p->middle_blk_num; ++j) {
     bf16* mirror = (j == p->middle_blk_num - 1 && nd > 0) ? sv.up_in[0] : nullptr;
-    DCPT_TRY(nafblock_fwd_impl(P + p->mid_blks[j].pidx, pk.mid_pk[j], x, sv.mid_out[j], mirror, sv.mid_sv[j], N, h, w, C, st));
+    DCPT_TRY(nafblock_fwd_impl(P + p->mid_blks[j].pidx, pk.mid_pk[j], x, sv.mid_out[j], mirror, sv.mid_sv[j], N, h, w, C, st, tkh(ne),
+                               tkw(ne)));
     x = sv.mid_out[j];
   }
   if (ne == 0 && p->middle_blk_num == 0 && nd > 0) { dcpt_set_error("nafnet_fwd: degenerate network"); return DCPT_E_UNSUPPORTED; }
@@ -748,7 +774,7 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     for (int j = 0; j < p->dec[i]; ++j) {
       bf16* mirror = (j == p->dec[i] - 1) ? (i + 1 < nd ? sv.up_in[i + 1] : sv.xlast_bf16) : nullptr;
       DCPT_TRY(nafblock_fwd_impl(P + p->dec_blks[i][j].pidx, pk.dec_pk[i][j], x, sv.dec_out[i][j], mirror, sv.dec_sv[i][j], N, h, w,
-                                 C, st));
+                                 C, st, tkh(ne - 1 - i), tkw(ne - 1 - i)));
       x = sv.dec_out[i][j];
     }
     if (host_feats && host_feats[i])
@@ -767,6 +793,7 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
                     const float* dout, const float* const* host_dfeats, float* const* G, void* workspace, int N, int H, int W,
                     dcpt_stream_t stream) {
   DCPT_TRY(check_net_shape(p, N, H, W));
+  DCPT_CHECK_ARG(p->tlc_kh.empty(), DCPT_E_UNSUPPORTED, "nafnet_bwd: the TLC variant is a test-time converter (inference only)");
   DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(P), (int)p->params.size(), "params"));
   DCPT_TRY(check_ptrs16(reinterpret_cast<const void* const*>(G), (int)p->params.size(), "grads"));
   cudaStream_t st = static_cast<cudaStream_t>(stream);

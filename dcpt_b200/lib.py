@@ -50,6 +50,7 @@ PROTOTYPES = {
     "dcpt_nafblock_bwd": (_I, [_PP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _PP, _VP, _I, _I, _I, _I, _VP]),
     "dcpt_nafnet_create": (_VP, [_I, _I, _I, C.POINTER(_I), _I, C.POINTER(_I), _I]),
     "dcpt_nafnet_destroy": (None, [_VP]),
+    "dcpt_nafnet_set_tlc": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), _I]),
     "dcpt_nafnet_num_params": (_I, [_VP]),
     "dcpt_nafnet_param_shape": (_LL, [_VP, _I, C.POINTER(_I)]),
     "dcpt_nafnet_packed_bytes": (_SZ, [_VP]),

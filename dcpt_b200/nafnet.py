@@ -39,6 +39,16 @@ class NAFNetEngine:
         # CUDA-graph replay of the autograd path (nafnet_apply): DCPT_CUDA_GRAPH=0 launches every kernel from the host
         self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0"
         self._gslots = {}
+        self.tlc = False
+
+    def set_tlc(self, kernels):
+        """kernels: [(kh, kw)] per resolution level (0 = full resolution .. n_enc) - NAFNet's test-time local converter."""
+        n = len(kernels)
+        kh = (C.c_int * max(n, 1))(*[k[0] for k in kernels])
+        kw = (C.c_int * max(n, 1))(*[k[1] for k in kernels])
+        _l.check(self.lib.dcpt_nafnet_set_tlc(self.plan, kh, kw, n), "nafnet_set_tlc")
+        self.tlc = n > 0
+        self._gslots = {}
 
     def __del__(self):
         try:

@@ -143,6 +143,11 @@ typedef struct dcpt_nafnet_plan dcpt_nafnet_plan;
 dcpt_nafnet_plan* dcpt_nafnet_create(int img_channel, int width, int middle_blk_num, const int* enc_blk_nums, int n_enc,
                                      const int* dec_blk_nums, int n_dec);
 void dcpt_nafnet_destroy(dcpt_nafnet_plan* plan);
+/* `NAFNet` = Local_Base + NAFNetBaseline (nafnet_arch.py:277-288): test-time local converter.  kh / kw[l] = SCA pooling kernel
+ * of resolution level l (0 = full resolution .. n_enc = bottleneck), as fixed by Local_Base.convert on the train_size dummy
+ * input (arch_util.py:341-347, 450-455).  A level whose map fits inside its kernel keeps the global mean (:352-353); otherwise
+ * the pooled vector becomes a per-pixel replicate-padded box mean (:379-396).  Inference only; n_levels = 0 switches it off. */
+int dcpt_nafnet_set_tlc(dcpt_nafnet_plan* plan, const int* kh, const int* kw, int n_levels);
 int dcpt_nafnet_num_params(const dcpt_nafnet_plan* plan);
 /* shape of parameter i as up to 4 dims (unused dims = 1); returns number of elements */
 long long dcpt_nafnet_param_shape(const dcpt_nafnet_plan* plan, int i, int dims[4]);

@@ -9,6 +9,7 @@ DESIGN.md §numerics) that costs ~3e-4 rel-L2 on a block output and ~5e-3 on par
   parameter gradients        rel-L2 <= 2e-2   (bf16 gradient operands)
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -243,3 +244,30 @@ def test_nafnet_w64_full_config_properties():
     print(f"w64 b16 grads vs two b8 halves: worst rel-L2 {worst:.2e}")
     assert worst < 2e-2
     assert all(torch.isfinite(t).all() and float(t.abs().max()) > 0 for t in g1)
+
+
+def test_nafnet_tlc_golden(golden_dir):
+    """`NAFNet` (Local_Base test-time local converter, nafnet_arch.py:277-288 / arch_util.py:313-455) against the REAL
+    reference's output: every level pools locally on the 64x80 input; the 32x48 input falls back to the global mean at
+    every level.  The input / weights are chosen so that local and global pooling differ by 7e-3: the check also proves
+    that the local path was taken."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_tlc import tlc_state_dict
+    from basicsr.archs import build_network
+    z = np.load(os.path.join(golden_dir, "nafnet_tlc_w16.npz"))
+    cfg = dict(width=16, enc_blk_nums=[1, 1], middle_blk_num=1, dec_blk_nums=[1, 1])
+    sd = tlc_state_dict(cfg)
+    net = build_network(dict(type="NAFNet", train_size=tuple(int(v) for v in z["train_size"]), **cfg)).cuda()
+    net.load_state_dict(sd, strict=True)
+    assert net.tlc_kernels == O.tlc_kernels(tuple(z["train_size"]), 3) == [(48, 48), (24, 24), (12, 12)]
+    inp = z_t(z["inp"])
+    with torch.no_grad():
+        out = net(inp.cuda())
+        out_small = net(z_t(z["small"]).cuda())
+        base = O.nafnet_fwd(inp, sd, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"])   # global pooling
+    e, e_small, e_base = rel(out, z_t(z["out"])), rel(out_small, z_t(z["out_small"])), rel(out, base)
+    print(f"NAFNet TLC: rel-L2 {e:.2e} vs reference golden (global-pooling oracle: {e_base:.2e}); small input {e_small:.2e}")
+    assert e < 2.5e-3 and e_small < 2.5e-3 and e_base > 2 * e
+    from dcpt_b200.lib import DcptError
+    with pytest.raises(DcptError):
+        net(inp.cuda())                                  # gradients enabled: TLC is inference only

@@ -130,3 +130,21 @@ def test_dchead_golden(golden_dir):
         assert rel(f.grad, z[f"dfeat{i}"]) < 1e-4, i
     for k, v in sd.items():
         assert rel(v.grad, z["g." + k]) < 2e-4, k
+
+
+def test_nafnet_tlc_golden(golden_dir):
+    """oracle `tlc_avgpool` / `tlc_kernels` (NAFNet = Local_Base + NAFNetBaseline) against the real reference's output."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden_tlc import tlc_state_dict
+    z = load(golden_dir, "nafnet_tlc_w16.npz")
+    cfg = dict(width=16, enc_blk_nums=[1, 1], middle_blk_num=1, dec_blk_nums=[1, 1])
+    sd = tlc_state_dict(cfg)
+    ts = tuple(int(v) for v in z["train_size"])
+    with torch.no_grad():
+        out = O.nafnet_fwd(z["inp"], sd, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"], tlc_train_size=ts)
+        small = O.nafnet_fwd(z["small"], sd, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"], tlc_train_size=ts)
+        base = O.nafnet_fwd(z["inp"], sd, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"])
+    assert rel(out, z["out"]) < RTOL and rel(small, z["out_small"]) < RTOL
+    assert rel(base, z["out"]) > 5e-3          # the fixture separates local from global pooling
+    assert O.tlc_kernels((1, 3, 128, 128), 5) == [(192, 192), (96, 96), (48, 48), (24, 24), (12, 12)]
