@@ -261,6 +261,10 @@ dwconv3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
 // --------------------------- backward, part a ---------------------------------
 // dg = dgs*s + t;  a,b = dwconv(u)+bias (recomputed);  du2_a = dg*b, du2_b = dg*a  (stored bf16);
 // dW2[c][tap] += du2[c] * u[px+tap][c];  db2[c] += du2[c].
+// MODE 0: NAFBlock (SimpleGate, SCA scale / shift s, t, bias).  MODE 1: Restormer GDFN (gelu(a) * b, no bias, dg = dgs;
+// restormer_arch.py:97-98).  MODE 2: plain depthwise conv weight gradient (Restormer qkv_dwconv, :110-118): tmD holds the
+// output gradient of all 2C channels, nothing is recomputed or stored, only dW2 is accumulated.
+template <int MODE>
 __global__ void __launch_bounds__(NWARP * 32)
 dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmD, const float* __restrict__ s_sca,
                     const float* __restrict__ t_sca, const float* __restrict__ w2, const float* __restrict__ b2,
@@ -268,7 +272,7 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
   pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  constexpr int STAGE_BYTES = 2 * BOX_BYTES + DG_BYTES;
+  constexpr int STAGE_BYTES = 2 * BOX_BYTES + (MODE == 2 ? 2 : 1) * DG_BYTES;
   float2* s_red = reinterpret_cast<float2*>(smem + 2 * STAGE_BYTES);  // [NWARP][20][32]
   __shared__ uint64_t full[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -282,7 +286,9 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
 #pragma unroll
   for (int k = 0; k < 9; ++k) gA[k] = gB[k] = make_float2(0.f, 0.f);
   float2 dbA = make_float2(0.f, 0.f), dbB = dbA;
-  const float2 ba = make_float2(__ldg(b2 + ca), __ldg(b2 + ca + 1)), bb = make_float2(__ldg(b2 + cb), __ldg(b2 + cb + 1));
+  const float2 zero2 = make_float2(0.f, 0.f);
+  const float2 ba = b2 ? make_float2(__ldg(b2 + ca), __ldg(b2 + ca + 1)) : zero2;
+  const float2 bb = b2 ? make_float2(__ldg(b2 + cb), __ldg(b2 + cb + 1)) : zero2;
   const Tiles T(N, H, W);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmU);
@@ -300,6 +306,7 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
     tma_load_4d(dst, &tmU, &full[s], cg * 64, w0 - 1, h0 - 1, n);
     tma_load_4d(dst + BOX_BYTES, &tmU, &full[s], C + cg * 64, w0 - 1, h0 - 1, n);
     tma_load_4d(dst + 2 * BOX_BYTES, &tmD, &full[s], cg * 64, w0, h0, n);
+    if constexpr (MODE == 2) tma_load_4d(dst + 2 * BOX_BYTES + DG_BYTES, &tmD, &full[s], C + cg * 64, w0, h0, n);
   };
   if (threadIdx.x == 0 && T.t0 < T.t1) issue(T.t0, 0);
   int it = 0;
@@ -308,8 +315,11 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
     if (threadIdx.x == 0 && t + 1 < T.t1) issue(t + 1, s ^ 1);
     int n, h0, w0;
     T.decode(t, n, h0, w0);
-    const float2 sv = make_float2(__ldg(s_sca + (size_t)n * C + ca), __ldg(s_sca + (size_t)n * C + ca + 1));
-    const float2 tv = make_float2(__ldg(t_sca + (size_t)n * C + ca), __ldg(t_sca + (size_t)n * C + ca + 1));
+    float2 sv = make_float2(1.f, 1.f), tv = zero2;
+    if constexpr (MODE == 0) {
+      sv = make_float2(__ldg(s_sca + (size_t)n * C + ca), __ldg(s_sca + (size_t)n * C + ca + 1));
+      tv = make_float2(__ldg(t_sca + (size_t)n * C + ca), __ldg(t_sca + (size_t)n * C + ca + 1));
+    }
     mbar_wait(&full[s], (it >> 1) & 1);
     const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * STAGE_BYTES) + lane * 2;
     const bf16* sB = sA + BOX_ELEMS;
@@ -327,19 +337,36 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
       if (x >= 2) {
         const int ox = x - 2;
         float2 a = ba, b = bb;
+        if constexpr (MODE != 2) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            fma2(a, A[r][(x - 2 + d) % 3], wa[r * 3 + d]);
-            fma2(b, B[r][(x - 2 + d) % 3], wb[r * 3 + d]);
-          }
+            for (int d = 0; d < 3; ++d) {
+              fma2(a, A[r][(x - 2 + d) % 3], wa[r * 3 + d]);
+              fma2(b, B[r][(x - 2 + d) % 3], wb[r * 3 + d]);
+            }
+        }
         if (chan_ok && h < H && w0 + ox < W) {
           const float2 dgv = lds_bf2(sD + (warp * TW + ox) * 64);
-          const float2 dg = make_float2(fmaf(dgv.x, sv.x, tv.x), fmaf(dgv.y, sv.y, tv.y));
-          const float2 da = make_float2(dg.x * b.x, dg.y * b.y), db = make_float2(dg.x * a.x, dg.y * a.y);
-          st_bf2(orow + (size_t)ox * C2 + ca, da);
-          st_bf2(orow + (size_t)ox * C2 + cb, db);
+          float2 da, db;
+          if constexpr (MODE == 0) {
+            const float2 dg = make_float2(fmaf(dgv.x, sv.x, tv.x), fmaf(dgv.y, sv.y, tv.y));
+            da = make_float2(dg.x * b.x, dg.y * b.y);
+            db = make_float2(dg.x * a.x, dg.y * a.y);
+          } else if constexpr (MODE == 1) {
+            // g = gelu(a) * b, gelu(a) = a * Phi(a):  dg/da = b * (Phi(a) + a * phi(a)),  dg/db = a * Phi(a)
+            const float px_ = 0.5f * (1.f + erff(a.x * 0.70710678118654752f)), py_ = 0.5f * (1.f + erff(a.y * 0.70710678118654752f));
+            const float qx = 0.3989422804014327f * __expf(-0.5f * a.x * a.x), qy = 0.3989422804014327f * __expf(-0.5f * a.y * a.y);
+            da = make_float2(dgv.x * b.x * (px_ + a.x * qx), dgv.y * b.y * (py_ + a.y * qy));
+            db = make_float2(dgv.x * a.x * px_, dgv.y * a.y * py_);
+          } else {
+            da = dgv;
+            db = lds_bf2(sD + DG_ELEMS + (warp * TW + ox) * 64);
+          }
+          if constexpr (MODE != 2) {
+            st_bf2(orow + (size_t)ox * C2 + ca, da);
+            st_bf2(orow + (size_t)ox * C2 + cb, db);
+          }
           dbA.x += da.x; dbA.y += da.y;
           dbB.x += db.x; dbB.y += db.y;
 #pragma unroll
@@ -379,7 +406,7 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
       const int c = half * C + cc;
       atomicAdd(dw2 + (size_t)c * 9 + tap, v.x);
       atomicAdd(dw2 + (size_t)(c + 1) * 9 + tap, v.y);
-    } else {
+    } else if (db2) {
       const int c = (item - 18) * C + cc;
       atomicAdd(db2 + c, v.x);
       atomicAdd(db2 + c + 1, v.y);
@@ -529,9 +556,38 @@ int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const b
   DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
   DCPT_TRY(make_tmap_nhwc(&tmD, dgs, N, H, W, C, TW, TH));
   const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
-  DCPT_TRY(set_smem(dwgate_bwd_a_kernel, smem));
+  DCPT_TRY(set_smem(dwgate_bwd_a_kernel<0>, smem));
   DCPT_PROF(dcpt_prof_tag2("dwgate_bwd_a", (long long)N * H * W, C), 80.0 * N * H * W * C, 10.0 * N * H * W * C, st);
-  DCPT_CUDA(dcpt_launch_pdl(dwgate_bwd_a_kernel, pick_grid(N, H, W, C, 1), dim3(NWARP * 32), smem, st, tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C));
+  DCPT_CUDA(dcpt_launch_pdl(dwgate_bwd_a_kernel<0>, pick_grid(N, H, W, C, 1), dim3(NWARP * 32), smem, st, tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C));
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+// Restormer GDFN gate backward: dg bf16 [N,H,W,C], u bf16 [N,H,W,2C] -> du2 bf16 [N,H,W,2C]; dw2[2C][9] += (no bias).
+int dwgelu_bwd_a_launch(const bf16* dg, const bf16* u, const float* w2, bf16* du2, float* dw2, int N, int H, int W, int C, cudaStream_t st) {
+  DCPT_CHECK_ARG(C % 8 == 0 && C >= 8 && N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "dwgelu_bwd_a: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  CUtensorMap tmU, tmD;
+  DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
+  DCPT_TRY(make_tmap_nhwc(&tmD, dg, N, H, W, C, TW, TH));
+  const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
+  DCPT_TRY(set_smem(dwgate_bwd_a_kernel<1>, smem));
+  DCPT_PROF("dwgelu_bwd_a", 120.0 * N * H * W * C, 10.0 * N * H * W * C, st);
+  dwgate_bwd_a_kernel<1><<<pick_grid(N, H, W, C, 1), NWARP * 32, smem, st>>>(tmU, tmD, nullptr, nullptr, w2, nullptr, du2, dw2, nullptr, N, H, W, C);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+// Plain depthwise 3x3 weight gradient: dw[c][tap] += sum_px dy[px][c] * x[px + tap][c] for CH = 2 * Chalf channels.
+int dwconv3_wgrad_launch(const bf16* dy, const bf16* x, float* dw, int N, int H, int W, int CH, cudaStream_t st) {
+  DCPT_CHECK_ARG(CH % 16 == 0 && CH >= 16 && N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "dwconv3_wgrad: CH=%d must be a multiple of 16", CH);
+  const int C = CH / 2;
+  CUtensorMap tmU, tmD;
+  DCPT_TRY(make_tmap_nhwc(&tmU, x, N, H, W, CH, HWD, HH));
+  DCPT_TRY(make_tmap_nhwc(&tmD, dy, N, H, W, CH, TW, TH));
+  const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + 2 * DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
+  DCPT_TRY(set_smem(dwgate_bwd_a_kernel<2>, smem));
+  DCPT_PROF("dwconv3_wgrad", 36.0 * N * H * W * CH, 4.0 * N * H * W * CH, st);
+  dwgate_bwd_a_kernel<2><<<pick_grid(N, H, W, C, 1), NWARP * 32, smem, st>>>(tmU, tmD, nullptr, nullptr, dw, nullptr, nullptr, dw, nullptr, N, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
 }

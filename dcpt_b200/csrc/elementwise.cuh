@@ -11,7 +11,7 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
                   cudaStream_t st, int center = 1);
 // dx = dres + LNbwd(dn); also dx mirror in bf16, sum_m dn*yhat -> dw, sum_m dn -> db, sum_m dx -> colsum (all +=).
 int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const float* w, const float* dres, float* dx,
-                  bf16* dx_bf16, float* dw, float* db, float* colsum, int M, int C, cudaStream_t st);
+                  bf16* dx_bf16, float* dw, float* db, float* colsum, int M, int C, cudaStream_t st, int center = 1);
 
 // depthwise 3x3 (+bias, zero pad) on 2C channels followed by SimpleGate; pool[n,c] += sum_px g.
 int dwgate_fwd_launch(const bf16* u, const float* w2, const float* b2, bf16* g, float* pool, int N, int H, int W, int C,
@@ -24,6 +24,8 @@ int dwconv3_fwd_launch(const bf16* x, const float* w, bf16* out, float* sumsq, i
 // backward part a: dg = dgs*s + t; du2 = SimpleGate'(dg); dW2 += du2 (*) u; db2 += sum du2.
 int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const bf16* u, const float* w2, const float* b2,
                         bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st);
+int dwgelu_bwd_a_launch(const bf16* dg, const bf16* u, const float* w2, bf16* du2, float* dw2, int N, int H, int W, int C, cudaStream_t st);
+int dwconv3_wgrad_launch(const bf16* dy, const bf16* x, float* dw, int N, int H, int W, int CH, cudaStream_t st);
 // backward part b: du = dwconv^T(du2); colsum[c] += sum_px du.
 int dwconv_bwd_data_launch(const bf16* du2, const float* w2, bf16* du, float* colsum, int N, int H, int W, int C2,
                            cudaStream_t st);

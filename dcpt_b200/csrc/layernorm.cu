@@ -106,7 +106,7 @@ template <int NV, int kBwdWarps, int kMinBlocks>
 __global__ void __launch_bounds__(kBwdWarps * 32, kMinBlocks)
 ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const float* __restrict__ stats,
               const float* __restrict__ w, const float* __restrict__ dres, float* __restrict__ dx, bf16* __restrict__ dx_bf16,
-              float* __restrict__ dw, float* __restrict__ db, float* __restrict__ colsum, int M, int C, int lpr) {
+              float* __restrict__ dw, float* __restrict__ db, float* __restrict__ colsum, int M, int C, int lpr, int center) {
   extern __shared__ float s_acc[];  // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
@@ -165,8 +165,15 @@ ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const fl
         sgy += g[i].x * yh[i].x + g[i].y * yh[i].y + g[i].z * yh[i].z + g[i].w * yh[i].w;
       }
     }
-    const float mean_g = group_sum(sg, lpr) * invC;
-    const float mean_gy = group_sum(sgy, lpr) * invC;
+    float mean_g = group_sum(sg, lpr) * invC;
+    float mean_gy = group_sum(sgy, lpr) * invC;
+    // center == 0: Restormer's BiasFree LN, out = x * rstd * w (restormer_arch.py:38-40).  With xh = x * rstd = yh + mean * rstd:
+    //   dx = rstd * (g - yh * mean_c(g * xh)),  dw += dn * xh      (the mean is not an input of the numerator)
+    const float mr = center ? 0.f : mean * rstd;
+    if (!center) {
+      mean_gy += mr * mean_g;
+      mean_g = 0.f;
+    }
     if (valid) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -186,7 +193,8 @@ ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const fl
             pk.y = *reinterpret_cast<uint32_t*>(&p1);
             *(reinterpret_cast<uint2*>(dx_bf16 + row * C) + v) = pk;
           }
-          a_dw[i].x += d[i].x * yh[i].x; a_dw[i].y += d[i].y * yh[i].y; a_dw[i].z += d[i].z * yh[i].z; a_dw[i].w += d[i].w * yh[i].w;
+          a_dw[i].x += d[i].x * (yh[i].x + mr); a_dw[i].y += d[i].y * (yh[i].y + mr);
+          a_dw[i].z += d[i].z * (yh[i].z + mr); a_dw[i].w += d[i].w * (yh[i].w + mr);
           a_db[i].x += d[i].x; a_db[i].y += d[i].y; a_db[i].z += d[i].z; a_db[i].w += d[i].w;
           a_cs[i].x += o.x; a_cs[i].y += o.y; a_cs[i].z += o.z; a_cs[i].w += o.w;
         }
@@ -367,9 +375,9 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
 }
 
 int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const float* w, const float* dres, float* dx,
-                  bf16* dx_bf16, float* dw, float* db, float* colsum, int M, int C, cudaStream_t st) {
+                  bf16* dx_bf16, float* dw, float* db, float* colsum, int M, int C, cudaStream_t st, int center) {
   DCPT_CHECK_ARG(M > 0 && C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "layernorm bwd: need C %% 8 == 0 and 8 <= C <= 1024 (C=%d)", C);
-  if (C == 512 && M >= 2048 && getenv("DCPT_LN_BWD_NARROW") == nullptr) {
+  if (C == 512 && M >= 2048 && center && getenv("DCPT_LN_BWD_NARROW") == nullptr) {
     const int R = 8;  // rows per tile: 40 KB per stage
     const size_t smem = 128 + (size_t)2 * R * C * 10 + (size_t)3 * C * sizeof(float);
     const int tiles = ceil_div(M, R);
@@ -394,7 +402,7 @@ int ln_bwd_launch(const bf16* dn, const float* x, const float* stats, const floa
   const size_t smem = (size_t)3 * C * sizeof(float);
   DCPT_PROF(dcpt_prof_tag2("ln_bwd", M, C), 20.0 * M * C, (2.0 + 4.0 + (dres ? 4.0 : 0.0) + 4.0 + (dx_bf16 ? 2.0 : 0.0)) * M * C, st);
 #define LN_BWD(NVV, WW, MB) \
-  DCPT_CUDA(dcpt_launch_pdl(ln_bwd_kernel<NVV, WW, MB>, dim3((unsigned)grid), dim3(WW * 32), smem, st, dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr))
+  DCPT_CUDA(dcpt_launch_pdl(ln_bwd_kernel<NVV, WW, MB>, dim3((unsigned)grid), dim3(WW * 32), smem, st, dn, x, stats, w, dres, dx, dx_bf16, dw, db, colsum, M, C, lpr, center))
   if (nv <= 1) LN_BWD(1, 16, 2);
   else if (nv <= 2) LN_BWD(2, 16, 1);
   else if (nv <= 4) LN_BWD(4, 4, 4);

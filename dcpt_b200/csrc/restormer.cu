@@ -13,6 +13,7 @@
 // pixels yields the Gram matrix and both norms; attn @ v followed by project_out is a per-image linear map of v.
 // hidden = int(2.66 d) is odd-sized (127/255/510/1021): padded to a multiple of 8 with zero weights in the packed
 // operand cache, never in the state_dict.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -60,7 +61,7 @@ __global__ void pack_cols_kernel(const float* __restrict__ w, bf16* __restrict__
 // block = (head, image); the c x c attention tile lives in shared memory.
 __global__ void __launch_bounds__(256)
 mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, const float* __restrict__ temp,
-                 const float* __restrict__ wout, bf16* __restrict__ weff, int d, int heads) {
+                 const float* __restrict__ wout, bf16* __restrict__ weff, bf16* __restrict__ weffT, int d, int heads) {
   extern __shared__ float s_attn[];  // [c][c + 1]
   const int c = d / heads, h = blockIdx.x, n = blockIdx.y;
   const float* Gn = G + (size_t)n * d * d;
@@ -80,7 +81,135 @@ mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, cons
     float acc = 0.f;
     for (int i = 0; i < c; ++i) acc = fmaf(__ldg(wr + i), s_attn[i * (c + 1) + j], acc);
     out[(size_t)o * d + h * c + j] = __float2bfloat16_rn(acc);
+    if (weffT) weffT[(size_t)n * d * d + (size_t)(h * c + j) * d + o] = __float2bfloat16_rn(acc);  // dgrad operand (training)
   }
+}
+
+// Backward of the attention core (restormer_arch.py:131-144), one block per (head, image).  Inputs: dWeff = d(loss)/d(W_eff)
+// (fp32 [N,d,d], from the split-K GEMM dx2^T v), the forward's Gram matrix G and squared norms sq.  With
+//   Ghat_ij = G_ij / (nq_i nk_j),  A_ij = T_h Ghat_ij,  attn = relu(A),  W_eff[o, hc+j] = sum_i Wout[o, hc+i] attn_ij :
+//   dattn_ij = sum_o Wout[o,hc+i] dWeff[o,hc+j];   dWout[o,hc+i] += sum_j dWeff[o,hc+j] attn_ij
+//   dA = dattn * [A > 0];  dT_h += sum dA Ghat;  dGhat = dA T_h;  dG_ij = dGhat_ij / (nq_i nk_j)
+//   cq_i = -(sum_j dGhat_ij Ghat_ij) / nq_i^2,  ck_j = -(sum_i dGhat_ij Ghat_ij) / nk_j^2          (F.normalize backward)
+// so that dq[px,i] = sum_j dG_ij k[px,j] + cq_i q[px,i] and dk[px,j] = sum_i dG_ij q[px,i] + ck_j k[px,j]: both are ONE GEMM of
+// the [q | k] slab with Bmat[n] (bf16 [2d, 2d], rows = outputs [dq | dk], columns = [q | k] channels), written here.
+__global__ void __launch_bounds__(256)
+mdta_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, const float* __restrict__ sq,
+                const float* __restrict__ temp, const float* __restrict__ wout, float* __restrict__ dwout, float* __restrict__ dtemp,
+                bf16* __restrict__ Bmat, bf16* __restrict__ BmatLo, int d, int heads) {
+  extern __shared__ float sm[];
+  const int c = d / heads, h = blockIdx.x, n = blockIdx.y, hc = h * c;
+  float* s_gh = sm;                 // Ghat   [c][c]
+  float* s_at = s_gh + c * c;       // attn   [c][c]   (later: dGhat)
+  float* s_da = s_at + c * c;       // dattn  [c][c]
+  float* s_nq = s_da + c * c;       // [c]
+  float* s_nk = s_nq + c;           // [c]
+  float* s_w = s_nk + c;            // Wout chunk  [64][c]
+  float* s_e = s_w + 64 * c;        // dWeff chunk [64][c]
+  __shared__ float s_red[8];
+  const float* Gn = G + (size_t)n * d * d;
+  const float* sqn = sq + (size_t)n * 2 * d;
+  const float* dWn = dWeff + (size_t)n * d * d;
+  const float T = __ldg(temp + h);
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    s_nq[i] = fmaxf(sqrtf(sqn[hc + i]), 1e-12f);
+    s_nk[i] = fmaxf(sqrtf(sqn[d + hc + i]), 1e-12f);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
+    const int i = idx / c, j = idx - i * c;
+    const float gh = Gn[(size_t)(hc + i) * d + hc + j] / (s_nq[i] * s_nk[j]);
+    s_gh[idx] = gh;
+    s_at[idx] = fmaxf(gh * T, 0.f);
+    s_da[idx] = 0.f;
+  }
+  __syncthreads();
+  // dattn and dWout, streaming 64 output channels o at a time through shared memory
+  for (int o0 = 0; o0 < d; o0 += 64) {
+    const int no = min(64, d - o0);
+    for (int idx = threadIdx.x; idx < no * c; idx += blockDim.x) {
+      const int oo = idx / c, k = idx - oo * c;
+      s_w[idx] = __ldg(wout + (size_t)(o0 + oo) * d + hc + k);
+      s_e[idx] = dWn[(size_t)(o0 + oo) * d + hc + k];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
+      const int i = idx / c, j = idx - i * c;
+      float acc = 0.f;
+      for (int oo = 0; oo < no; ++oo) acc = fmaf(s_w[oo * c + i], s_e[oo * c + j], acc);
+      s_da[idx] += acc;
+    }
+    for (int idx = threadIdx.x; idx < no * c; idx += blockDim.x) {
+      const int oo = idx / c, i = idx - oo * c;
+      float acc = 0.f;
+      for (int j = 0; j < c; ++j) acc = fmaf(s_e[oo * c + j], s_at[i * c + j], acc);
+      atomicAdd(dwout + (size_t)(o0 + oo) * d + hc + i, acc);
+    }
+    __syncthreads();
+  }
+  // dA, dT, dGhat (in place of attn)
+  float dt = 0.f;
+  for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
+    const float dA = s_at[idx] > 0.f ? s_da[idx] : 0.f;
+    dt = fmaf(dA, s_gh[idx], dt);
+    s_at[idx] = dA * T;
+  }
+  dt = warp_sum(dt);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_red[k];
+    atomicAdd(dtemp + h, t);
+  }
+  // Bmat is stored as a bf16 hi + lo pair: dq_i = sum_j dG_ij k_j + cq_i q_i is the component of the first term orthogonal
+  // to q_i (the normalisation removes the rest), so with correlated channels the two terms nearly cancel and a plain bf16
+  // matrix costs 3-5e-2 on dq / dk (measured); q and k themselves are exact bf16 operands.
+  bf16* Bn = Bmat + (size_t)n * 4 * d * d;  // [2d][2d], zero-initialised by the caller
+  bf16* Bl = BmatLo + (size_t)n * 4 * d * d;
+  const int D2 = 2 * d;
+  auto put = [&](size_t off, float val) {
+    const bf16 hi = __float2bfloat16_rn(val);
+    Bn[off] = hi;
+    Bl[off] = __float2bfloat16_rn(val - __bfloat162float(hi));
+  };
+  for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
+    const int i = idx / c, j = idx - i * c;
+    const float dg = s_at[idx] / (s_nq[i] * s_nk[j]);
+    put((size_t)(hc + i) * D2 + d + hc + j, dg);      // dq_i <- k_j
+    put((size_t)(d + hc + j) * D2 + hc + i, dg);      // dk_j <- q_i
+  }
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    float aq = 0.f, ak = 0.f;
+    for (int j = 0; j < c; ++j) {
+      aq = fmaf(s_at[i * c + j], s_gh[i * c + j], aq);   // row i    : sum_j dGhat_ij Ghat_ij
+      ak = fmaf(s_at[j * c + i], s_gh[j * c + i], ak);   // column i : sum_j dGhat_ji Ghat_ji
+    }
+    const float nq = s_nq[i], nk = s_nk[i];
+    put((size_t)(hc + i) * D2 + hc + i, nq > 1e-12f ? -aq / (nq * nq) : 0.f);
+    put((size_t)(d + hc + i) * D2 + d + hc + i, nk > 1e-12f ? -ak / (nk * nk) : 0.f);
+  }
+}
+
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int Cc) {  // out[c][r] = in[r][c]
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * Cc) return;
+  const int c = (int)(idx / R), r = (int)(idx - (long long)c * R);
+  out[idx] = in[(size_t)r * Cc + c];
+}
+// dW [2*hid, I] += S [2*hidp, I] (rows of each half un-padded);  dW [O, hid] += S [O, hidp] (columns un-padded)
+__global__ void unpad_halves_add_kernel(const float* __restrict__ S, float* __restrict__ dW, int hid, int hidp, int I) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)2 * hid * I) return;
+  const int r = (int)(idx / I), i = (int)(idx - (long long)r * I);
+  const int half = r / hid, rr = r - half * hid;
+  dW[idx] += S[((size_t)half * hidp + rr) * I + i];
+}
+__global__ void unpad_cols_add_kernel(const float* __restrict__ S, float* __restrict__ dW, int O, int hid, int hidp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)O * hid) return;
+  const int o = (int)(idx / hid), c = (int)(idx - (long long)o * hid);
+  dW[idx] += S[(size_t)o * hidp + c];
 }
 
 // PixelUnshuffle(2) in NHWC: in [N, H, W, Cc] -> out [N, H/2, W/2, 4*Cc], out channel = c*4 + i*2 + j  (restormer_arch.py:186)
@@ -183,12 +312,48 @@ void add_stage(dcpt_restormer_plan* p, int s, int d, int heads, int n) {
 
 struct BlkPacked {
   bf16 *wqkv, *wpin, *wpout;
+  bf16 *wqkv_t, *wpin_t, *wpout_t;  // dgrad operands: [d, 3d], [d, 2 hidp], [hidp, d]
   float* dwp;
   BlkPacked(Arena& a, const dcpt_restormer_plan::Blk& b) {
     wqkv = a.take<bf16>((size_t)3 * b.d * b.d);
     wpin = a.take<bf16>((size_t)2 * b.hidp * b.d);
     wpout = a.take<bf16>((size_t)b.d * b.hidp);
     dwp = a.take<float>((size_t)2 * b.hidp * 9);
+    wqkv_t = a.take<bf16>((size_t)3 * b.d * b.d);
+    wpin_t = a.take<bf16>((size_t)2 * b.hidp * b.d);
+    wpout_t = a.take<bf16>((size_t)b.d * b.hidp);
+  }
+};
+
+// where a block's forward leaves its intermediates: shared scratch (inference) or the saved-for-backward arena (training)
+struct BlkBufs {
+  bf16 *n1, *qkv, *qkvd, *n2, *u, *g, *weff, *weffT;
+  float *G, *sq, *x2, *stats1, *stats2;
+};
+
+struct BlkSaved : BlkBufs {
+  BlkSaved(Arena& a, const dcpt_restormer_plan::Blk& b, int N, int H, int W) {
+    const size_t M = (size_t)N * H * W, d = b.d;
+    n1 = a.take<bf16>(M * d); qkv = a.take<bf16>(M * 3 * d); qkvd = a.take<bf16>(M * 3 * d);
+    n2 = a.take<bf16>(M * d); u = a.take<bf16>(M * 2 * b.hidp); g = a.take<bf16>(M * b.hidp);
+    weff = a.take<bf16>((size_t)N * d * d); weffT = a.take<bf16>((size_t)N * d * d);
+    G = a.take<float>((size_t)N * d * d); sq = a.take<float>((size_t)N * 2 * d);
+    x2 = a.take<float>(M * d); stats1 = a.take<float>(M * 2); stats2 = a.take<float>(M * 2);
+  }
+};
+
+struct BlkWork {
+  bf16 *doutT, *dg, *bufA, *bufB, *dn, *dx2T, *Bmat;  // Bmat: hi [N,2d,2d] followed by lo [N,2d,2d]
+  float *dx2, *dWeff, *scratch, *tmp32;
+  BlkWork(Arena& a, const dcpt_restormer_plan::Blk& b, int N, int H, int W) {
+    const size_t M = (size_t)N * H * W, d = b.d, wide = 2 * (size_t)b.hidp > 3 * d ? 2 * (size_t)b.hidp : 3 * d;
+    doutT = a.take<bf16>(M * d); dg = a.take<bf16>(M * b.hidp);
+    bufA = a.take<bf16>(M * wide); bufB = a.take<bf16>(M * wide);
+    dn = a.take<bf16>(M * d); dx2T = a.take<bf16>(M * d); Bmat = a.take<bf16>((size_t)N * 8 * d * d);
+    dx2 = a.take<float>(M * d); dWeff = a.take<float>((size_t)N * d * d); tmp32 = a.take<float>(M * 2 * d);
+    size_t sc = 2 * (size_t)b.hidp * d;
+    if (3 * d * d > sc) sc = 3 * d * d;
+    scratch = a.take<float>(sc + 2 * (size_t)b.hidp * 9);
   }
 };
 
@@ -241,80 +406,179 @@ struct NetWork {
   }
 };
 
-int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, const float* const* P, const BlkPacked& pk, float* x,
-              float* x2, const NetWork& ws, int N, int H, int W, cudaStream_t st) {
+// wgrad-style contraction over pixels: out[O, I] += dY[Mpx, O]^T X[Mpx, I]  (MN-major operands, one-wave split-K, fp32 atomics)
+int pix_gemm(const bf16* dY, int O, int ldy, const bf16* X, int I, int ldx, float* out, int Mpx, cudaStream_t st) {
+  GemmArgs g = make_gemm_args(O, I, Mpx, dY, ldy, X, ldx, EPI_ATOMIC);
+  g.a_mn = 1; g.b_mn = 1;
+  const int bn = I > 128 ? 256 : (I > 64 ? 128 : 64);
+  g.splits = gemm_auto_splits(ceil_div(O, 128) * ceil_div(I, bn), ceil_div(Mpx, 64));
+  g.ep.out_f32 = out; g.ep.ldo = I;
+  return gemm_launch(g, st);
+}
+
+// per-image contraction out[n][O, I] += A[n]^T B[n] over the HW pixels of image n (A, B slabs of [N*HW, ld] matrices)
+int pix_gemm_per_image(const bf16* A, int O, int lda, const bf16* B, int I, int ldb, float* out, int N, int HW, cudaStream_t st) {
+  const int bn = I > 128 ? 256 : (I > 64 ? 128 : 64);
+  const int tiles = ceil_div(O, 128) * ceil_div(I, bn);
+  if (N > 1 && HW % 128 == 0 && !getenv("DCPT_RESTORMER_NO_BATCH")) {  // one launch: splits never straddle an image
+    GemmArgs g = make_gemm_args(O, I, N * HW, A, lda, B, ldb, EPI_ATOMIC);
+    g.a_mn = 1; g.b_mn = 1;
+    g.k_per_batch = HW;
+    g.splits = gemm_auto_splits(tiles * N, ceil_div(HW, 64));
+    g.ep.out_f32 = out; g.ep.ldo = I; g.ep.out_batch_stride = (long long)O * I;
+    return gemm_launch(g, st);
+  }
+  for (int n = 0; n < N; ++n) {
+    GemmArgs g = make_gemm_args(O, I, HW, A + (size_t)n * HW * lda, lda, B + (size_t)n * HW * ldb, ldb, EPI_ATOMIC);
+    g.a_mn = 1; g.b_mn = 1;
+    g.splits = gemm_auto_splits(tiles, ceil_div(HW, 64));
+    g.ep.out_f32 = out + (size_t)n * O * I; g.ep.ldo = I;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  return 0;
+}
+
+// out[n] = A[n] * Bm[n]^T (+ resid) with a per-image [Nout, K] matrix Bm[n]; A rows [N*HW, lda]
+int gemm_per_image(const bf16* A, int lda, const bf16* Bm, int Nout, int K, float* out_f32, bf16* out_bf16, int ldo, const float* resid,
+                   int ldr, int N, int HW, cudaStream_t st) {
+  if (N > 1 && HW % 128 == 0 && !getenv("DCPT_RESTORMER_NO_BATCH")) {
+    GemmArgs g = make_gemm_args(N * HW, Nout, K, A, lda, Bm, K, EPI_STORE);
+    g.m_per_batch = HW; g.b_rows_per_batch = Nout;
+    g.ep.out_f32 = out_f32; g.ep.out_bf16 = out_bf16; g.ep.ldo = ldo; g.ep.resid = resid; g.ep.ldr = ldr;
+    return gemm_launch(g, st);
+  }
+  for (int n = 0; n < N; ++n) {
+    const size_t r0 = (size_t)n * HW;
+    GemmArgs g = make_gemm_args(HW, Nout, K, A + r0 * lda, lda, Bm + (size_t)n * Nout * K, K, EPI_STORE);
+    g.ep.out_f32 = out_f32 ? out_f32 + r0 * ldo : nullptr; g.ep.out_bf16 = out_bf16 ? out_bf16 + r0 * ldo : nullptr; g.ep.ldo = ldo;
+    g.ep.resid = resid ? resid + r0 * ldr : nullptr; g.ep.ldr = ldr;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  return 0;
+}
+
+// TransformerBlock forward (restormer_arch.py:156-159): xout = x2 + GDFN(LN(x2)), x2 = x + MDTA(LN(x)).  x == xout is allowed.
+int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, const float* const* P, const BlkPacked& pk, const float* x,
+              float* xout, const BlkBufs& bf, int N, int H, int W, cudaStream_t st) {
   const int d = b.d, HW = H * W, M = N * HW;
   const BlkIdx ix = blk_idx(p, b.pidx);
   constexpr float eps = 1e-6f;
+  float* x2 = bf.x2;
   // ---- x2 = x + MDTA(LN(x)) ----
-  DCPT_TRY(ln_fwd_launch(x, P[ix.n1w], ix.n1b >= 0 ? P[ix.n1b] : nullptr, ws.n, nullptr, M, d, eps, st, p->ln_bias));
+  DCPT_TRY(ln_fwd_launch(x, P[ix.n1w], ix.n1b >= 0 ? P[ix.n1b] : nullptr, bf.n1, bf.stats1, M, d, eps, st, p->ln_bias));
   {
-    GemmArgs g = make_gemm_args(M, 3 * d, d, ws.n, d, pk.wqkv, d, EPI_STORE);
-    g.ep.out_bf16 = ws.a; g.ep.ldo = 3 * d;
+    GemmArgs g = make_gemm_args(M, 3 * d, d, bf.n1, d, pk.wqkv, d, EPI_STORE);
+    g.ep.out_bf16 = bf.qkv; g.ep.ldo = 3 * d;
     DCPT_TRY(gemm_launch(g, st));
   }
-  DCPT_CUDA(cudaMemsetAsync(ws.sq, 0, (size_t)N * 2 * d * sizeof(float), st));
-  DCPT_TRY(dwconv3_fwd_launch(ws.a, P[ix.qkv_dw], ws.b, ws.sq, 2 * d, N, H, W, 3 * d, st));
-  DCPT_CUDA(cudaMemsetAsync(ws.G, 0, (size_t)N * d * d * sizeof(float), st));
-  const bool batched = N > 1 && HW % 128 == 0;  // one launch for all images (tiles / splits never straddle an image)
-  if (batched) {
-    GemmArgs g = make_gemm_args(d, d, N * HW, ws.b, 3 * d, ws.b + d, 3 * d, EPI_ATOMIC);
-    g.a_mn = 1; g.b_mn = 1;
-    g.k_per_batch = HW;
-    const int bn = d > 128 ? 256 : (d > 64 ? 128 : 64);
-    g.splits = gemm_auto_splits(ceil_div(d, 128) * ceil_div(d, bn) * N, ceil_div(HW, 64));
-    g.ep.out_f32 = ws.G; g.ep.ldo = d; g.ep.out_batch_stride = (long long)d * d;
-    DCPT_TRY(gemm_launch(g, st));
-  }
-  for (int n = 0; n < N && !batched; ++n) {  // G[n] = q^T k over the HW pixels of image n (both operands MN-major, split-K)
-    const bf16* q = ws.b + (size_t)n * HW * 3 * d;
-    GemmArgs g = make_gemm_args(d, d, HW, q, 3 * d, q + d, 3 * d, EPI_ATOMIC);
-    g.a_mn = 1; g.b_mn = 1;
-    const int bn = d > 128 ? 256 : (d > 64 ? 128 : 64);
-    g.splits = gemm_auto_splits(ceil_div(d, 128) * ceil_div(d, bn), ceil_div(HW, 64));
-    g.ep.out_f32 = ws.G + (size_t)n * d * d; g.ep.ldo = d;
-    DCPT_TRY(gemm_launch(g, st));
-  }
+  DCPT_CUDA(cudaMemsetAsync(bf.sq, 0, (size_t)N * 2 * d * sizeof(float), st));
+  DCPT_TRY(dwconv3_fwd_launch(bf.qkv, P[ix.qkv_dw], bf.qkvd, bf.sq, 2 * d, N, H, W, 3 * d, st));
+  DCPT_CUDA(cudaMemsetAsync(bf.G, 0, (size_t)N * d * d * sizeof(float), st));
+  DCPT_TRY(pix_gemm_per_image(bf.qkvd, d, 3 * d, bf.qkvd + d, d, 3 * d, bf.G, N, HW, st));  // G[n] = q^T k over the pixels of image n
   {
     const int c = d / b.heads;
     const size_t smem = (size_t)c * (c + 1) * sizeof(float);
     DCPT_CHECK_ARG(d % b.heads == 0 && smem <= 200 * 1024, DCPT_E_SHAPE, "mdta: dim %d / heads %d unsupported", d, b.heads);
     if (smem > 48 * 1024) DCPT_CUDA(cudaFuncSetAttribute(mdta_weff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DCPT_PROF("mdta_weff", 2.0 * N * d * d * c, 4.0 * N * d * d, st);
-    mdta_weff_kernel<<<dim3(b.heads, N), 256, smem, st>>>(ws.G, ws.sq, P[ix.temp], P[ix.pout], ws.weff, d, b.heads);
+    mdta_weff_kernel<<<dim3(b.heads, N), 256, smem, st>>>(bf.G, bf.sq, P[ix.temp], P[ix.pout], bf.weff, bf.weffT, d, b.heads);
     DCPT_LAUNCH_CHECK();
   }
-  if (batched) {  // x2 = x + v * W_eff[image]^T, the B operand switches with the image of the M tile
-    GemmArgs g = make_gemm_args(M, d, d, ws.b + 2 * d, 3 * d, ws.weff, d, EPI_STORE);
-    g.m_per_batch = HW; g.b_rows_per_batch = d;
-    g.ep.out_f32 = x2; g.ep.ldo = d; g.ep.resid = x; g.ep.ldr = d;
-    DCPT_TRY(gemm_launch(g, st));
-  }
-  for (int n = 0; n < N && !batched; ++n) {  // x2[n] = x[n] + v[n] * W_eff[n]^T
-    const size_t r0 = (size_t)n * HW;
-    GemmArgs g = make_gemm_args(HW, d, d, ws.b + r0 * 3 * d + 2 * d, 3 * d, ws.weff + (size_t)n * d * d, d, EPI_STORE);
-    g.ep.out_f32 = x2 + r0 * d; g.ep.ldo = d; g.ep.resid = x + r0 * d; g.ep.ldr = d;
-    DCPT_TRY(gemm_launch(g, st));
-  }
-  // ---- x = x2 + GDFN(LN(x2)) ----
-  DCPT_TRY(ln_fwd_launch(x2, P[ix.n2w], ix.n2b >= 0 ? P[ix.n2b] : nullptr, ws.n, nullptr, M, d, eps, st, p->ln_bias));
+  // x2 = x + v * W_eff[image]^T
+  DCPT_TRY(gemm_per_image(bf.qkvd + 2 * d, 3 * d, bf.weff, d, d, x2, nullptr, d, x, d, N, HW, st));
+  // ---- xout = x2 + GDFN(LN(x2)) ----
+  DCPT_TRY(ln_fwd_launch(x2, P[ix.n2w], ix.n2b >= 0 ? P[ix.n2b] : nullptr, bf.n2, bf.stats2, M, d, eps, st, p->ln_bias));
   {
-    GemmArgs g = make_gemm_args(M, 2 * b.hidp, d, ws.n, d, pk.wpin, d, EPI_STORE);
-    g.ep.out_bf16 = ws.a; g.ep.ldo = 2 * b.hidp;
+    GemmArgs g = make_gemm_args(M, 2 * b.hidp, d, bf.n2, d, pk.wpin, d, EPI_STORE);
+    g.ep.out_bf16 = bf.u; g.ep.ldo = 2 * b.hidp;
     DCPT_TRY(gemm_launch(g, st));
   }
-  DCPT_TRY(dwgelu_fwd_launch(ws.a, pk.dwp, ws.b, N, H, W, b.hidp, st));
+  DCPT_TRY(dwgelu_fwd_launch(bf.u, pk.dwp, bf.g, N, H, W, b.hidp, st));
   {
-    GemmArgs g = make_gemm_args(M, d, b.hidp, ws.b, b.hidp, pk.wpout, b.hidp, EPI_STORE);
-    g.ep.out_f32 = x; g.ep.ldo = d; g.ep.resid = x2; g.ep.ldr = d;
+    GemmArgs g = make_gemm_args(M, d, b.hidp, bf.g, b.hidp, pk.wpout, b.hidp, EPI_STORE);
+    g.ep.out_f32 = xout; g.ep.ldo = d; g.ep.resid = x2; g.ep.ldr = d;
     DCPT_TRY(gemm_launch(g, st));
   }
   return 0;
 }
 
+// inference: every block of the network shares one set of scratch buffers
+BlkBufs scratch_bufs(const NetWork& ws, float* tmp) {
+  BlkBufs bf;
+  bf.n1 = bf.n2 = ws.n; bf.qkv = bf.u = ws.a; bf.qkvd = bf.g = ws.b; bf.weff = ws.weff; bf.weffT = nullptr;
+  bf.G = ws.G; bf.sq = ws.sq; bf.x2 = tmp; bf.stats1 = bf.stats2 = nullptr;
+  return bf;
+}
+
+// TransformerBlock backward: dx = d(loss)/d(x) given dout = d(loss)/d(xout); parameter gradients are accumulated into G[].
+int block_bwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, const float* const* P, const BlkPacked& pk,
+              const BlkSaved& sv, const float* x, const float* dout, float* dx, float* const* G, const BlkWork& wk, int N, int H, int W,
+              cudaStream_t st) {
+  const int d = b.d, HW = H * W, M = N * HW, hid = b.hid, hidp = b.hidp;
+  const BlkIdx ix = blk_idx(p, b.pidx);
+  float* sc2 = wk.scratch + (2 * (size_t)hidp * d > 3 * (size_t)d * d ? 2 * (size_t)hidp * d : 3 * (size_t)d * d);  // [2 hidp][9]
+  // ================= GDFN: xout = x2 + g W_out^T,  g = gelu(a) b,  [a | b] = dw3x3(u),  u = n2 W_in^T =================
+  DCPT_TRY(cast_f32_bf16_launch(dout, wk.doutT, (long long)M * d, st));
+  DCPT_CUDA(cudaMemsetAsync(wk.scratch, 0, (size_t)d * hidp * sizeof(float), st));
+  DCPT_TRY(pix_gemm(wk.doutT, d, d, sv.g, hidp, hidp, wk.scratch, M, st));                       // dW_out (padded columns)
+  unpad_cols_add_kernel<<<blocks_for((long long)d * hid), 256, 0, st>>>(wk.scratch, G[ix.ffn_out], d, hid, hidp);
+  {
+    GemmArgs g = make_gemm_args(M, hidp, d, wk.doutT, d, pk.wpout_t, d, EPI_STORE);              // dg = dout W_out
+    g.ep.out_bf16 = wk.dg; g.ep.ldo = hidp;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  DCPT_CUDA(cudaMemsetAsync(sc2, 0, (size_t)2 * hidp * 9 * sizeof(float), st));
+  DCPT_TRY(dwgelu_bwd_a_launch(wk.dg, sv.u, pk.dwp, wk.bufA, sc2, N, H, W, hidp, st));            // d[a | b], dW_dw
+  unpad_halves_add_kernel<<<blocks_for((long long)2 * hid * 9), 256, 0, st>>>(sc2, G[ix.dw], hid, hidp, 9);
+  DCPT_TRY(dwconv_bwd_data_launch(wk.bufA, pk.dwp, wk.bufB, nullptr, N, H, W, 2 * hidp, st));     // du
+  DCPT_CUDA(cudaMemsetAsync(wk.scratch, 0, (size_t)2 * hidp * d * sizeof(float), st));
+  DCPT_TRY(pix_gemm(wk.bufB, 2 * hidp, 2 * hidp, sv.n2, d, d, wk.scratch, M, st));                // dW_in (padded rows)
+  unpad_halves_add_kernel<<<blocks_for((long long)2 * hid * d), 256, 0, st>>>(wk.scratch, G[ix.pin], hid, hidp, d);
+  DCPT_LAUNCH_CHECK();
+  {
+    GemmArgs g = make_gemm_args(M, d, 2 * hidp, wk.bufB, 2 * hidp, pk.wpin_t, 2 * hidp, EPI_STORE);  // dn2 = du W_in
+    g.ep.out_bf16 = wk.dn; g.ep.ldo = d;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // dx2 = dout + LN2'(dn2)
+  DCPT_TRY(ln_bwd_launch(wk.dn, sv.x2, sv.stats2, P[ix.n2w], dout, wk.dx2, wk.dx2T, G[ix.n2w], ix.n2b >= 0 ? G[ix.n2b] : nullptr, nullptr, M,
+                         d, st, p->ln_bias));
+  // ================= MDTA: x2 = x + v W_eff[n]^T =================
+  DCPT_TRY(gemm_per_image(wk.dx2T, d, sv.weffT, d, d, nullptr, wk.bufA + 2 * d, 3 * d, nullptr, 0, N, HW, st));  // dv = dx2 W_eff
+  DCPT_CUDA(cudaMemsetAsync(wk.dWeff, 0, (size_t)N * d * d * sizeof(float), st));
+  DCPT_TRY(pix_gemm_per_image(wk.dx2T, d, d, sv.qkvd + 2 * d, d, 3 * d, wk.dWeff, N, HW, st));    // dW_eff[n] = dx2[n]^T v[n]
+  DCPT_CUDA(cudaMemsetAsync(wk.Bmat, 0, (size_t)N * 8 * d * d * sizeof(bf16), st));
+  bf16* BmatLo = wk.Bmat + (size_t)N * 4 * d * d;
+  {
+    const int c = d / b.heads;
+    const size_t smem = ((size_t)3 * c * c + 2 * c + 2 * 64 * c) * sizeof(float);
+    DCPT_CHECK_ARG(smem <= 220 * 1024, DCPT_E_SHAPE, "mdta backward: head width %d too large", c);
+    if (smem > 48 * 1024) DCPT_CUDA(cudaFuncSetAttribute(mdta_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DCPT_PROF("mdta_bwd", 4.0 * N * d * d * c, 12.0 * N * d * d, st);
+    mdta_bwd_kernel<<<dim3(b.heads, N), 256, smem, st>>>(wk.dWeff, sv.G, sv.sq, P[ix.temp], P[ix.pout], G[ix.pout], G[ix.temp], wk.Bmat,
+                                                        BmatLo, d, b.heads);
+    DCPT_LAUNCH_CHECK();
+  }
+  // [dq | dk] = [q | k] (Bmat_hi + Bmat_lo)[n]^T: two passes, fp32 in between
+  DCPT_TRY(gemm_per_image(sv.qkvd, 3 * d, wk.Bmat, 2 * d, 2 * d, wk.tmp32, nullptr, 2 * d, nullptr, 0, N, HW, st));
+  DCPT_TRY(gemm_per_image(sv.qkvd, 3 * d, BmatLo, 2 * d, 2 * d, nullptr, wk.bufA, 3 * d, wk.tmp32, 2 * d, N, HW, st));
+  DCPT_TRY(dwconv3_wgrad_launch(wk.bufA, sv.qkv, G[ix.qkv_dw], N, H, W, 3 * d, st));               // dW of qkv_dwconv
+  DCPT_TRY(dwconv_bwd_data_launch(wk.bufA, P[ix.qkv_dw], wk.bufB, nullptr, N, H, W, 3 * d, st));   // d(qkv)
+  DCPT_TRY(pix_gemm(wk.bufB, 3 * d, 3 * d, sv.n1, d, d, G[ix.qkv], M, st));                         // dW_qkv
+  {
+    GemmArgs g = make_gemm_args(M, d, 3 * d, wk.bufB, 3 * d, pk.wqkv_t, 3 * d, EPI_STORE);         // dn1 = d(qkv) W_qkv
+    g.ep.out_bf16 = wk.dn; g.ep.ldo = d;
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  // dx = dx2 + LN1'(dn1)
+  return ln_bwd_launch(wk.dn, x, sv.stats1, P[ix.n1w], wk.dx2, dx, nullptr, G[ix.n1w], ix.n1b >= 0 ? G[ix.n1b] : nullptr, nullptr, M, d, st,
+                       p->ln_bias);
+}
+
 int stage_fwd(const dcpt_restormer_plan* p, int s, const float* const* P, const NetPacked& pk, float* x, float* tmp, const NetWork& ws,
               int N, int H, int W, cudaStream_t st) {
-  for (size_t j = 0; j < p->stage[s].size(); ++j) DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, tmp, ws, N, H, W, st));
+  const BlkBufs bf = scratch_bufs(ws, tmp);
+  for (size_t j = 0; j < p->stage[s].size(); ++j) DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, x, bf, N, H, W, st));
   return 0;
 }
 
@@ -420,6 +684,9 @@ int dcpt_restormer_pack(const dcpt_restormer_plan* p, const float* const* P, voi
       pack_halves_kernel<bf16><<<blocks_for((long long)2 * b.hidp * b.d), 256, 0, st>>>(P[ix.pin], bp.wpin, b.hid, b.hidp, b.d);
       pack_halves_kernel<float><<<blocks_for((long long)2 * b.hidp * 9), 256, 0, st>>>(P[ix.dw], bp.dwp, b.hid, b.hidp, 9);
       pack_cols_kernel<<<blocks_for((long long)b.d * b.hidp), 256, 0, st>>>(P[ix.ffn_out], bp.wpout, b.d, b.hid, b.hidp);
+      DCPT_TRY(pack_weight_launch(P[ix.qkv], nullptr, bp.wqkv_t, 3 * b.d, b.d, PACK_T, st));
+      transpose_bf16_kernel<<<blocks_for((long long)2 * b.hidp * b.d), 256, 0, st>>>(bp.wpin, bp.wpin_t, 2 * b.hidp, b.d);
+      transpose_bf16_kernel<<<blocks_for((long long)b.d * b.hidp), 256, 0, st>>>(bp.wpout, bp.wpout_t, b.d, b.hidp);
       DCPT_LAUNCH_CHECK();
     }
   int d = p->dim;
@@ -446,7 +713,49 @@ int dcpt_restormer_block_fwd(const dcpt_restormer_plan* p, int stage, int j, con
   const int l = kLevel[stage];
   Arena aw(workspace);
   NetWork ws(p, aw, N, H << l, W << l);
-  return block_fwd(p, p->stage[stage][j], P, pk.blk[stage][j], x, l == 0 ? ws.t1 : ws.t[l], ws, N, H, W, static_cast<cudaStream_t>(stream));
+  return block_fwd(p, p->stage[stage][j], P, pk.blk[stage][j], x, x, scratch_bufs(ws, l == 0 ? ws.t1 : ws.t[l]), N, H, W,
+                   static_cast<cudaStream_t>(stream));
+}
+
+static int check_block(const dcpt_restormer_plan* p, int stage, int j) {
+  DCPT_CHECK_ARG(p && stage >= 0 && stage < 8 && j >= 0 && j < (int)p->stage[stage].size(), DCPT_E_ARG, "restormer: no block %d in stage %d", j,
+                 stage);
+  return 0;
+}
+size_t dcpt_restormer_block_saved_bytes(const dcpt_restormer_plan* p, int stage, int j, int N, int H, int W) {
+  if (check_block(p, stage, j)) return 0;
+  Arena a(nullptr);
+  BlkSaved sv(a, p->stage[stage][j], N, H, W);
+  return a.size();
+}
+size_t dcpt_restormer_block_workspace_bytes(const dcpt_restormer_plan* p, int stage, int j, int N, int H, int W) {
+  if (check_block(p, stage, j)) return 0;
+  Arena a(nullptr);
+  BlkWork wk(a, p->stage[stage][j], N, H, W);
+  return a.size();
+}
+int dcpt_restormer_block_fwd_train(const dcpt_restormer_plan* p, int stage, int j, const float* const* P, const void* packed, const float* x,
+                                   float* xout, void* saved, int N, int H, int W, dcpt_stream_t stream) {
+  DCPT_TRY(check_block(p, stage, j));
+  DCPT_CHECK_ARG(P && packed && x && xout && saved && N > 0 && H > 0 && W > 0, DCPT_E_ARG, "restormer_block_fwd_train: bad argument");
+  Arena ap(const_cast<void*>(packed));
+  NetPacked pk(p, ap);
+  Arena as(saved);
+  BlkSaved sv(as, p->stage[stage][j], N, H, W);
+  return block_fwd(p, p->stage[stage][j], P, pk.blk[stage][j], x, xout, sv, N, H, W, static_cast<cudaStream_t>(stream));
+}
+int dcpt_restormer_block_bwd(const dcpt_restormer_plan* p, int stage, int j, const float* const* P, const void* packed, const void* saved,
+                             const float* x, const float* dout, float* dx, float* const* host_grads, void* workspace, int N, int H, int W,
+                             dcpt_stream_t stream) {
+  DCPT_TRY(check_block(p, stage, j));
+  DCPT_CHECK_ARG(P && packed && saved && x && dout && dx && host_grads && workspace, DCPT_E_ARG, "restormer_block_bwd: null argument");
+  Arena ap(const_cast<void*>(packed));
+  NetPacked pk(p, ap);
+  Arena as(const_cast<void*>(saved));
+  BlkSaved sv(as, p->stage[stage][j], N, H, W);
+  Arena aw(workspace);
+  BlkWork wk(aw, p->stage[stage][j], N, H, W);
+  return block_bwd(p, p->stage[stage][j], P, pk.blk[stage][j], sv, x, dout, dx, host_grads, wk, N, H, W, static_cast<cudaStream_t>(stream));
 }
 
 int dcpt_restormer_fwd(const dcpt_restormer_plan* p, const float* const* P, const void* packed, const float* inp, float* out,

@@ -270,6 +270,20 @@ int dcpt_restormer_fwd(const dcpt_restormer_plan* plan, const float* const* host
 int dcpt_restormer_block_fwd(const dcpt_restormer_plan* plan, int stage, int j, const float* const* host_params, const void* packed,
                              float* x, void* workspace, int N, int H, int W, dcpt_stream_t stream);
 
+/* Training form of one TransformerBlock: forward that keeps its intermediates in `saved`
+ * (dcpt_restormer_block_saved_bytes), and the backward through MDTA (F.normalize, ReLU attention, temperature,
+ * qkv / qkv_dwconv / project_out) and GDFN (GELU gate, dwconv, project_in / project_out) and both LayerNorms -
+ * what autograd does for restormer_arch.py:156-159.  x, xout, dout, dx: fp32 NHWC [N,H,W,d].  host_grads: one device
+ * pointer per plan parameter (named_parameters() order; only the block's own entries are touched, accumulated +=). */
+size_t dcpt_restormer_block_saved_bytes(const dcpt_restormer_plan* plan, int stage, int j, int N, int H, int W);
+size_t dcpt_restormer_block_workspace_bytes(const dcpt_restormer_plan* plan, int stage, int j, int N, int H, int W);
+int dcpt_restormer_block_fwd_train(const dcpt_restormer_plan* plan, int stage, int j, const float* const* host_params,
+                                   const void* packed, const float* x, float* xout, void* saved, int N, int H, int W,
+                                   dcpt_stream_t stream);
+int dcpt_restormer_block_bwd(const dcpt_restormer_plan* plan, int stage, int j, const float* const* host_params, const void* packed,
+                             const void* saved, const float* x, const float* dout, float* dx, float* const* host_grads,
+                             void* workspace, int N, int H, int W, dcpt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
