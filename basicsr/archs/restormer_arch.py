@@ -5,7 +5,8 @@ Same class names, ctor kwargs, sub-module / parameter names and ``state_dict`` s
 :162-231 patch embed / resampling / SequentialTransformerBlock, :234-422 Restormer), so the reference's
 ``options/all_in_one/test/test_Restormer_5d.yml`` ``network_g`` section and checkpoints load with
 ``strict=True``.  The modules are parameter containers; ``Restormer.forward`` hands the whole network to the
-sm_100a kernels through the C ABI (``dcpt_restormer_fwd``).  Forward / inference only in this round.
+sm_100a kernels through the C ABI (``dcpt_restormer_fwd`` for inference, ``dcpt_restormer_fwd_train`` /
+``dcpt_restormer_bwd`` under autograd).
 """
 import numbers
 
@@ -14,7 +15,7 @@ import torch.nn as nn
 
 from basicsr.utils.registry import ARCH_REGISTRY
 from dcpt_b200.lib import DcptError
-from dcpt_b200.restormer import RestormerEngine
+from dcpt_b200.restormer import RestormerEngine, restormer_apply
 
 
 def _trunc_normal_(w, std=0.02):  # arch_util.py:259-282 (the reference's own helper), a = -2, b = 2
@@ -162,11 +163,16 @@ class Restormer(nn.Module):
 
     def forward(self, inp_img, hook=None):
         params = list(self.parameters())
-        if torch.is_grad_enabled() and (inp_img.requires_grad or any(p.requires_grad for p in params)):
-            raise DcptError("Restormer backward is not built yet: run inference under torch.no_grad() "
-                            "(SRModel.test does, sr_model.py:176-185)")
         targets = self._hook_targets()
         want = any(len(t) > 0 for t in targets)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # training step (SRModel.optimize_parameters, sr_model.py:132-174): autograd Function over the C-ABI fwd / bwd
+            if hook or want:
+                raise DcptError("Restormer: gradients through the DCPT feature hooks (hook=True / forward hooks on "
+                                "decoder_level*) are not built yet; the DCPT pretraining step runs with the NAFNet backbone")
+            if not inp_img.is_cuda:
+                raise DcptError("dcpt_b200 has no CPU path: input is on %s" % inp_img.device)
+            return restormer_apply(self.engine(), inp_img, params)
         out, feats = self.engine().forward([p.detach() for p in params], inp_img, hook=bool(hook), want_feats=want)
         if want:
             for mods, f in zip(targets, feats):

@@ -248,6 +248,37 @@ __global__ void pixel_shuffle_cat_kernel(const float* __restrict__ conv, const f
   if (out_bf16) out_bf16[idx] = __float2bfloat16_rn(v);
 }
 
+// backward of pixel_shuffle_cat: dcat [N, 2h, 2w, 2Cs] -> dconv bf16 [N, h, w, 4Cs] (PixelShuffle^T), dskip fp32 [N, 2h, 2w, Cs]
+__global__ void pixel_shuffle_cat_bwd_kernel(const float* __restrict__ dcat, bf16* __restrict__ dconv, float* __restrict__ dskip,
+                                             long long total, int h, int w, int Cs) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C2 = 2 * Cs;
+  const int co = (int)(idx % C2);
+  const long long px = idx / C2;
+  const int W2 = 2 * w, H2 = 2 * h;
+  const int x = (int)(px % W2);
+  const long long t = px / W2;
+  const int y = (int)(t % H2), n = (int)(t / H2);
+  const float v = dcat[idx];
+  if (co < Cs) dconv[(((size_t)n * h + (y >> 1)) * w + (x >> 1)) * (4 * Cs) + co * 4 + (y & 1) * 2 + (x & 1)] = __float2bfloat16_rn(v);
+  else dskip[(size_t)px * Cs + (co - Cs)] = v;
+}
+// backward of pixel_unshuffle: dout [N, H/2, W/2, 4Cc] -> dconv bf16 [N, H, W, Cc]
+__global__ void pixel_unshuffle_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ dconv, long long total, int H, int W, int Cc) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int C4 = 4 * Cc;
+  const int co = (int)(idx % C4);
+  const long long px = idx / C4;
+  const int W2 = W >> 1, H2 = H >> 1;
+  const int w2 = (int)(px % W2);
+  const long long t = px / W2;
+  const int h2 = (int)(t % H2), n = (int)(t / H2);
+  const int c = co >> 2, i = (co >> 1) & 1, j = co & 1;
+  dconv[(((size_t)n * H + 2 * h2 + i) * W + 2 * w2 + j) * Cc + c] = __float2bfloat16_rn(dout[idx]);
+}
+
 inline unsigned blocks_for(long long total, int threads = 256) { return (unsigned)((total + threads - 1) / threads); }
 
 }  // namespace
@@ -360,6 +391,7 @@ struct BlkWork {
 struct NetPacked {
   std::vector<BlkPacked> blk[8];
   bf16 *down[3], *up[3], *reduce[2];
+  bf16 *down_d[3], *up_d[3], *reduce_t[2];  // dgrad operands (flipped / transposed), used by the backward
   NetPacked(const dcpt_restormer_plan* p, Arena& a) {
     for (int s = 0; s < 8; ++s)
       for (auto& b : p->stage[s]) blk[s].emplace_back(a, b);
@@ -371,6 +403,14 @@ struct NetPacked {
     }
     reduce[0] = a.take<bf16>((size_t)4 * p->dim * 8 * p->dim);  // level 3: 8dim -> 4dim
     reduce[1] = a.take<bf16>((size_t)2 * p->dim * 4 * p->dim);  // level 2: 4dim -> 2dim
+    d = p->dim;
+    for (int i = 0; i < 3; ++i) {
+      down_d[i] = a.take<bf16>(dcpt_conv3x3_packed_elems(d / 2, d, 1));
+      up_d[i] = a.take<bf16>(dcpt_conv3x3_packed_elems(4 * d, 2 * d, 1));
+      d *= 2;
+    }
+    reduce_t[0] = a.take<bf16>((size_t)4 * p->dim * 8 * p->dim);
+    reduce_t[1] = a.take<bf16>((size_t)2 * p->dim * 4 * p->dim);
   }
 };
 
@@ -693,8 +733,12 @@ int dcpt_restormer_pack(const dcpt_restormer_plan* p, const float* const* P, voi
   for (int i = 0; i < 3; ++i) {
     DCPT_TRY(pack_conv3x3_launch(P[p->p_down[i]], pk.down[i], d / 2, d, 0, st));
     DCPT_TRY(pack_conv3x3_launch(P[p->p_up[i]], pk.up[i], 4 * d, 2 * d, 0, st));
+    DCPT_TRY(pack_conv3x3_launch(P[p->p_down[i]], pk.down_d[i], d / 2, d, 1, st));
+    DCPT_TRY(pack_conv3x3_launch(P[p->p_up[i]], pk.up_d[i], 4 * d, 2 * d, 1, st));
     d *= 2;
   }
+  DCPT_TRY(pack_weight_launch(P[p->p_reduce[0]], nullptr, pk.reduce_t[0], 4 * p->dim, 8 * p->dim, PACK_T, st));
+  DCPT_TRY(pack_weight_launch(P[p->p_reduce[1]], nullptr, pk.reduce_t[1], 2 * p->dim, 4 * p->dim, PACK_T, st));
   DCPT_TRY(pack_weight_launch(P[p->p_reduce[0]], nullptr, pk.reduce[0], 4 * p->dim, 8 * p->dim, PACK_PLAIN, st));
   DCPT_TRY(pack_weight_launch(P[p->p_reduce[1]], nullptr, pk.reduce[1], 2 * p->dim, 4 * p->dim, PACK_PLAIN, st));
   return 0;
@@ -756,6 +800,96 @@ int dcpt_restormer_block_bwd(const dcpt_restormer_plan* p, int stage, int j, con
   Arena aw(workspace);
   BlkWork wk(aw, p->stage[stage][j], N, H, W);
   return block_bwd(p, p->stage[stage][j], P, pk.blk[stage][j], sv, x, dout, dx, host_grads, wk, N, H, W, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------- training path -------------------------------
+struct NetSavedR {
+  std::vector<BlkSaved> sv[8];
+  std::vector<float*> xout[8];   // block outputs (fp32 residual stream)
+  float* x_embed;                // patch_embed output [M0, dim]
+  float* xdown[3];               // stage inputs of encoder_level2 / 3 / latent
+  bf16 *xm_down[3], *xm_up[3];   // bf16 conv inputs (wgrad operands)
+  bf16* cat[2];                  // reduce_chan inputs: level 3 [M2, 8dim], level 2 [M1, 4dim]
+  float* dec_in[3];              // decoder stage inputs: level 3 [M2, 4dim], level 2 [M1, 2dim], level 1 [M0, 2dim]
+  NetSavedR(const dcpt_restormer_plan* p, Arena& a, int N, int H, int W) {
+    const int dim = p->dim;
+    const size_t M[4] = {(size_t)N * H * W, (size_t)N * H * W / 4, (size_t)N * H * W / 16, (size_t)N * H * W / 64};
+    static const int lvl[8] = {0, 1, 2, 3, 2, 1, 0, 0};
+    for (int s = 0; s < 8; ++s)
+      for (auto& b : p->stage[s]) {
+        sv[s].emplace_back(a, b, N, H >> lvl[s], W >> lvl[s]);
+        xout[s].push_back(a.take<float>(M[lvl[s]] * b.d));
+      }
+    x_embed = a.take<float>(M[0] * dim);
+    for (int l = 0; l < 3; ++l) {
+      xdown[l] = a.take<float>(M[l + 1] * (dim << (l + 1)));
+      xm_down[l] = a.take<bf16>(M[l] * (dim << l));
+      xm_up[l] = a.take<bf16>(M[l + 1] * (dim << (l + 1)));
+    }
+    cat[0] = a.take<bf16>(M[2] * 8 * dim); cat[1] = a.take<bf16>(M[1] * 4 * dim);
+    dec_in[0] = a.take<float>(M[2] * 4 * dim); dec_in[1] = a.take<float>(M[1] * 2 * dim); dec_in[2] = a.take<float>(M[0] * 2 * dim);
+  }
+};
+
+struct NetWorkB {  // backward scratch
+  float *ga[4], *gb[4], *dskip[3], *tmp32, *cscr;
+  bf16 *dconv, *dT;
+  char* blk;
+  NetWorkB(const dcpt_restormer_plan* p, Arena& a, int N, int H, int W) {
+    const int dim = p->dim;
+    size_t maxblk = 0, maxconv = 0, maxc = 0, maxw = 27 * 2 * (size_t)dim;
+    for (int l = 0; l < 4; ++l) {
+      const size_t M = (size_t)N * (H >> l) * (W >> l), dl = (size_t)dim << l, dw = l == 0 ? 2 * dl : dl;
+      ga[l] = a.take<float>(M * dw); gb[l] = a.take<float>(M * dw);
+      if (l < 3) dskip[l] = a.take<float>(M * dl);
+      if (M * 2 * dl > maxconv) maxconv = M * 2 * dl;   // conv outputs / cat gradients at this resolution
+      if (M * 2 * dl > maxc) maxc = M * 2 * dl;
+      const size_t wsz = 4 * dl * 9 * ((2 * dl + 63) / 64 * 64);  // largest conv weight (up conv of this level)
+      if (wsz > maxw) maxw = wsz;
+    }
+    static const int lvl[8] = {0, 1, 2, 3, 2, 1, 0, 0};
+    for (int s = 0; s < 8; ++s)
+      for (auto& b : p->stage[s]) {
+        Arena probe(nullptr);
+        BlkWork bw(probe, b, N, H >> lvl[s], W >> lvl[s]);
+        (void)bw;
+        if (probe.size() > maxblk) maxblk = probe.size();
+      }
+    tmp32 = a.take<float>(maxc); cscr = a.take<float>(maxw);
+    dconv = a.take<bf16>(maxconv); dT = a.take<bf16>(maxc);
+    blk = a.take<char>(maxblk);
+  }
+};
+
+int stage_fwd_train(const dcpt_restormer_plan* p, int s, const float* const* P, const NetPacked& pk, const float* xin, NetSavedR& sv, int N,
+                    int H, int W, cudaStream_t st) {
+  DCPT_CHECK_ARG(!p->stage[s].empty(), DCPT_E_UNSUPPORTED, "restormer training: stage %d has no blocks", s);
+  const float* x = xin;
+  for (size_t j = 0; j < p->stage[s].size(); ++j) {
+    DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, sv.xout[s][j], sv.sv[s][j], N, H, W, st));
+    x = sv.xout[s][j];
+  }
+  return 0;
+}
+
+// dcur (gradient of the stage output) -> gradient of the stage input; returns the buffer that holds it
+int stage_bwd(const dcpt_restormer_plan* p, int s, const float* const* P, const NetPacked& pk, const NetSavedR& sv, const float* xin,
+              float*& cur, float*& other, float* const* G, const NetWorkB& wk, int N, int H, int W, cudaStream_t st) {
+  for (int j = (int)p->stage[s].size() - 1; j >= 0; --j) {
+    Arena a(wk.blk);
+    BlkWork bw(a, p->stage[s][j], N, H, W);
+    DCPT_TRY(block_bwd(p, p->stage[s][j], P, pk.blk[s][j], sv.sv[s][j], j > 0 ? sv.xout[s][j - 1] : xin, cur, other, G, bw, N, H, W, st));
+    float* t = cur; cur = other; other = t;
+  }
+  return 0;
+}
+
+int conv3_fwd_from(const bf16* xb, const bf16* wp, float* out, int N, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  Conv3x3Args a;
+  memset(&a, 0, sizeof(a));
+  a.X = xb; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Wp = wp; a.Cout = Cout;
+  a.ep.out_f32 = out; a.ep.ldo = Cout;
+  return conv3x3_tc_launch(a, st);
 }
 
 int dcpt_restormer_fwd(const dcpt_restormer_plan* p, const float* const* P, const void* packed, const float* inp, float* out,
@@ -826,6 +960,148 @@ int dcpt_restormer_fwd(const dcpt_restormer_plan* p, const float* const* P, cons
   DCPT_TRY(stage_fwd(p, ST_REF, P, pk, ws.d1, ws.t1, ws, N, H, W, st));
   // output conv + global residual (:413)
   return conv3x3_feat_to_img_launch(ws.d1, P[p->p_out], p->bias ? P[p->p_out + 1] : nullptr, inp, out, N, H, W, 2 * dim, st);
+}
+
+size_t dcpt_restormer_saved_bytes(const dcpt_restormer_plan* plan, int N, int H, int W) {
+  Arena a(nullptr);
+  NetSavedR sv(plan, a, N, H, W);
+  return a.size();
+}
+size_t dcpt_restormer_bwd_workspace_bytes(const dcpt_restormer_plan* plan, int N, int H, int W) {
+  Arena a(nullptr);
+  NetWorkB wk(plan, a, N, H, W);
+  return a.size();
+}
+
+int dcpt_restormer_fwd_train(const dcpt_restormer_plan* p, const float* const* P, const void* packed, const float* inp, float* out,
+                             void* saved, void* workspace, int N, int H, int W, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, DCPT_E_SHAPE, "restormer: H=%d W=%d must be positive multiples of 8", H, W);
+  DCPT_CHECK_ARG((long long)N * H * W * 6 * p->dim < (1ll << 31), DCPT_E_SHAPE, "restormer: batch too large for 32-bit pixel index");
+  DCPT_CHECK_ARG(P && packed && inp && out && saved && workspace, DCPT_E_ARG, "restormer_fwd_train: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena ap(const_cast<void*>(packed));
+  NetPacked pk(p, ap);
+  Arena as(saved);
+  NetSavedR sv(p, as, N, H, W);
+  Arena aw(workspace);
+  NetWork ws(p, aw, N, H, W);  // the inference workspace: only its conv scratch is used here
+  const int dim = p->dim;
+  DCPT_TRY(conv3x3_img_to_feat_launch(inp, P[p->p_embed], nullptr, 0, sv.x_embed, nullptr, nullptr, N, H, W, dim, st));
+  DCPT_TRY(stage_fwd_train(p, ST_ENC1, P, pk, sv.x_embed, sv, N, H, W, st));
+  int d = dim, h = H, w = W;
+  const float* x = sv.xout[ST_ENC1].back();
+  for (int l = 0; l < 3; ++l) {
+    DCPT_TRY(cast_f32_bf16_launch(x, sv.xm_down[l], (long long)N * h * w * d, st));
+    DCPT_TRY(conv3_fwd_from(sv.xm_down[l], pk.down[l], ws.conv, N, h, w, d, d / 2, st));
+    const long long total = (long long)N * h * w * (d / 2);
+    pixel_unshuffle_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, sv.xdown[l], total, h, w, d / 2);
+    DCPT_LAUNCH_CHECK();
+    d *= 2; h /= 2; w /= 2;
+    DCPT_TRY(stage_fwd_train(p, ST_ENC2 + l, P, pk, sv.xdown[l], sv, N, h, w, st));
+    x = sv.xout[ST_ENC2 + l].back();
+  }
+  static const int enc_stage[3] = {ST_ENC1, ST_ENC2, ST_ENC3};
+  for (int l = 2; l >= 0; --l) {
+    DCPT_TRY(cast_f32_bf16_launch(x, sv.xm_up[l], (long long)N * h * w * d, st));
+    DCPT_TRY(conv3_fwd_from(sv.xm_up[l], pk.up[l], ws.conv, N, h, w, d, 2 * d, st));
+    const int Cs = d / 2;
+    const long long total = (long long)N * h * w * 4 * 2 * Cs;
+    const float* skip = sv.xout[enc_stage[l]].back();
+    if (l > 0) {
+      const int ri = l == 2 ? 0 : 1;
+      pixel_shuffle_cat_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, skip, nullptr, sv.cat[ri], total, h, w, Cs);
+      DCPT_LAUNCH_CHECK();
+      h *= 2; w *= 2; d /= 2;
+      GemmArgs g = make_gemm_args(N * h * w, d, 2 * d, sv.cat[ri], 2 * d, pk.reduce[ri], 2 * d, EPI_STORE);
+      g.ep.out_f32 = sv.dec_in[ri]; g.ep.ldo = d;
+      if (p->bias) g.ep.bias = P[p->p_reduce[ri] + 1];
+      DCPT_TRY(gemm_launch(g, st));
+      DCPT_TRY(stage_fwd_train(p, l == 2 ? ST_DEC3 : ST_DEC2, P, pk, sv.dec_in[ri], sv, N, h, w, st));
+      x = sv.xout[l == 2 ? ST_DEC3 : ST_DEC2].back();
+    } else {
+      pixel_shuffle_cat_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, skip, sv.dec_in[2], nullptr, total, h, w, Cs);
+      DCPT_LAUNCH_CHECK();
+      h *= 2; w *= 2;
+      DCPT_TRY(stage_fwd_train(p, ST_DEC1, P, pk, sv.dec_in[2], sv, N, h, w, st));
+      x = sv.xout[ST_DEC1].back();
+    }
+  }
+  if (p->nref > 0) {
+    DCPT_TRY(stage_fwd_train(p, ST_REF, P, pk, x, sv, N, H, W, st));
+    x = sv.xout[ST_REF].back();
+  }
+  return conv3x3_feat_to_img_launch(x, P[p->p_out], p->bias ? P[p->p_out + 1] : nullptr, inp, out, N, H, W, 2 * dim, st);
+}
+
+int dcpt_restormer_bwd(const dcpt_restormer_plan* p, const float* const* P, const void* packed, const void* saved, const float* inp,
+                       const float* dout, float* const* G, void* workspace, int N, int H, int W, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(P && packed && saved && inp && dout && G && workspace, DCPT_E_ARG, "restormer_bwd: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena ap(const_cast<void*>(packed));
+  NetPacked pk(p, ap);
+  Arena as(const_cast<void*>(saved));
+  NetSavedR sv(p, as, N, H, W);
+  Arena aw(workspace);
+  NetWorkB wk(p, aw, N, H, W);
+  const int dim = p->dim, C2 = 2 * dim;
+  // ---- output conv (restormer_arch.py:413): bias / weight gradients, gradient of its input ----
+  const float* xref = p->nref > 0 ? sv.xout[ST_REF].back() : sv.xout[ST_DEC1].back();
+  DCPT_CUDA(cudaMemsetAsync(wk.cscr, 0, (size_t)27 * C2 * sizeof(float), st));
+  DCPT_TRY(conv3x3_small_wgrad_launch(xref, dout, wk.cscr, p->bias ? G[p->p_out + 1] : nullptr, 1, N, H, W, C2, st));
+  DCPT_TRY(wgrad_finish_perm_launch(wk.cscr, G[p->p_out], C2, 27, FIN_CN_TO_C3, st));
+  float *cur = wk.ga[0], *other = wk.gb[0];
+  DCPT_TRY(conv3x3_img_to_feat_launch(dout, P[p->p_out], nullptr, 1, cur, nullptr, nullptr, N, H, W, C2, st));
+  if (p->nref > 0) DCPT_TRY(stage_bwd(p, ST_REF, P, pk, sv, sv.xout[ST_DEC1].back(), cur, other, G, wk, N, H, W, st));
+  DCPT_TRY(stage_bwd(p, ST_DEC1, P, pk, sv, sv.dec_in[2], cur, other, G, wk, N, H, W, st));
+  // ---- decoder: cat split, PixelShuffle^T, up conv dgrad / wgrad, reduce conv ----
+  int d = 2 * dim, h = H / 2, w = W / 2;  // d, h, w of the level that feeds the up conv (level l + 1)
+  static const int dec_stage[3] = {-1, ST_DEC2, ST_DEC3};
+  for (int l = 0; l < 3; ++l) {
+    // cur = gradient of the concatenated tensor at level l: [N, 2h, 2w, 2Cs], Cs = d / 2
+    const int Cs = d / 2;
+    const long long total = (long long)N * h * w * 4 * 2 * Cs;
+    pixel_shuffle_cat_bwd_kernel<<<blocks_for(total), 256, 0, st>>>(cur, wk.dconv, wk.dskip[l], total, h, w, Cs);
+    DCPT_LAUNCH_CHECK();
+    // up conv (d -> 2d at level l + 1): weight gradient, then gradient of its input
+    DCPT_TRY(dcpt_conv3x3_wgrad(wk.dconv, sv.xm_up[l], wk.cscr, G[p->p_up[l]], N, h, w, d, 2 * d, stream));
+    cur = wk.ga[l + 1]; other = wk.gb[l + 1];
+    DCPT_TRY(conv3_fwd_from(wk.dconv, pk.up_d[l], cur, N, h, w, 2 * d, d, st));
+    if (l == 2) break;  // cur = gradient of the latent stage output
+    DCPT_TRY(stage_bwd(p, dec_stage[l + 1], P, pk, sv, sv.dec_in[l == 0 ? 1 : 0], cur, other, G, wk, N, h, w, st));
+    // reduce_chan conv (2d -> d, 1x1) at level l + 1: cur = gradient of its output [M, d]
+    const int ri = l == 0 ? 1 : 0, Mh = N * h * w;
+    DCPT_TRY(cast_f32_bf16_launch(cur, wk.dT, (long long)Mh * d, st));
+    DCPT_TRY(pix_gemm(wk.dT, d, d, sv.cat[ri], 2 * d, 2 * d, G[p->p_reduce[ri]], Mh, st));
+    if (p->bias) DCPT_TRY(colsum_bf16_launch(wk.dT, G[p->p_reduce[ri] + 1], Mh, d, st));
+    {
+      GemmArgs g = make_gemm_args(Mh, 2 * d, d, wk.dT, d, pk.reduce_t[ri], d, EPI_STORE);
+      g.ep.out_f32 = wk.tmp32; g.ep.ldo = 2 * d;
+      DCPT_TRY(gemm_launch(g, st));
+    }
+    cur = wk.tmp32;  // gradient of the concatenated tensor at level l + 1: [N, h, w, 2d]
+    d *= 2; h /= 2; w /= 2;
+  }
+  // ---- latent + encoder: stages, PixelUnshuffle^T, down conv dgrad / wgrad, skip gradients ----
+  static const int enc_stage[4] = {ST_ENC1, ST_ENC2, ST_ENC3, ST_LAT};
+  for (int l = 3; l >= 1; --l) {
+    // cur = gradient of stage l's output; d, h, w = level l
+    DCPT_TRY(stage_bwd(p, enc_stage[l], P, pk, sv, sv.xdown[l - 1], cur, other, G, wk, N, h, w, st));
+    const int Cc = d / 4, hl = h * 2, wl = w * 2, dl = d / 2;  // down conv at level l - 1: dl -> dl / 2, then unshuffle -> 2 dl = d
+    const long long total = (long long)N * h * w * d;
+    pixel_unshuffle_bwd_kernel<<<blocks_for(total), 256, 0, st>>>(cur, wk.dconv, total, hl, wl, Cc);
+    DCPT_LAUNCH_CHECK();
+    DCPT_TRY(dcpt_conv3x3_wgrad(wk.dconv, sv.xm_down[l - 1], wk.cscr, G[p->p_down[l - 1]], N, hl, wl, dl, dl / 2, stream));
+    DCPT_TRY(conv3_fwd_from(wk.dconv, pk.down_d[l - 1], wk.tmp32, N, hl, wl, dl / 2, dl, st));
+    cur = wk.ga[l - 1]; other = wk.gb[l - 1];
+    // + the gradient that reached this encoder output through the decoder's skip concat
+    DCPT_TRY(grad_prepare_launch(wk.tmp32, wk.dskip[l - 1], cur, nullptr, nullptr, N * hl * wl, dl, st));
+    d = dl; h = hl; w = wl;
+  }
+  DCPT_TRY(stage_bwd(p, ST_ENC1, P, pk, sv, sv.x_embed, cur, other, G, wk, N, H, W, st));
+  // ---- patch_embed (restormer_arch.py:377): weight gradient only (the image needs none) ----
+  DCPT_CUDA(cudaMemsetAsync(wk.cscr, 0, (size_t)27 * dim * sizeof(float), st));
+  DCPT_TRY(conv3x3_small_wgrad_launch(cur, inp, wk.cscr, nullptr, 0, N, H, W, dim, st));
+  return wgrad_finish_perm_launch(wk.cscr, G[p->p_embed], dim, 27, FIN_C3_TO_CN, st);
 }
 
 }  // extern "C"

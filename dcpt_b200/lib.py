@@ -88,6 +88,10 @@ PROTOTYPES = {
     "dcpt_restormer_block_workspace_bytes": (_SZ, [_VP, _I, _I, _I, _I, _I]),
     "dcpt_restormer_block_fwd_train": (_I, [_VP, _I, _I, _PP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "dcpt_restormer_block_bwd": (_I, [_VP, _I, _I, _PP, _VP, _VP, _VP, _VP, _VP, _PP, _VP, _I, _I, _I, _VP]),
+    "dcpt_restormer_saved_bytes": (_SZ, [_VP, _I, _I, _I]),
+    "dcpt_restormer_bwd_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
+    "dcpt_restormer_fwd_train": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "dcpt_restormer_bwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _VP, _I, _I, _I, _VP]),
     "dcpt_restormer_fwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _I, _I, _I, _I, _VP]),
 }
 

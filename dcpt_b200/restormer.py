@@ -1,9 +1,9 @@
-"""Host-side engine for Restormer (reference: basicsr/archs/restormer_arch.py:234-422), forward / inference path.
+"""Host-side engine for Restormer (reference: basicsr/archs/restormer_arch.py:234-422).
 
-``RestormerEngine`` owns the C plan, the packed bf16 operand cache and a per-shape workspace; the ``basicsr``
-mirror's ``Restormer`` module calls ``forward``.  No PyTorch implementation of the math lives here and there is
-no CPU path.  Training (backward) of the Restormer blocks is not built yet: calling the module with gradients
-enabled on its parameters raises ``DcptError`` instead of silently returning a graph-less tensor.
+``RestormerEngine`` owns the C plan, the packed bf16 operand cache and per-shape workspaces; the ``basicsr`` mirror's
+``Restormer`` module calls ``forward`` (inference, CUDA-graph replayed) or ``restormer_apply`` (an ``autograd.Function``
+over ``dcpt_restormer_fwd_train`` / ``dcpt_restormer_bwd``).  No PyTorch implementation of the math lives here and there is
+no CPU path.
 """
 import ctypes as C
 import os
@@ -123,3 +123,60 @@ class RestormerEngine:
         out = None if hook else ent["out"].clone()
         feats = [f.clone() for f in ent["feats"]] if ent["feats"] else None
         return out, feats
+
+    # ---- training -----------------------------------------------------------------------------------------------
+    def forward_train(self, params, inp):
+        """Returns (out, saved arena).  inp fp32 NCHW on CUDA."""
+        self._check_params(params)
+        inp = inp.contiguous().float()
+        N, _, H, W = inp.shape
+        dev = inp.device
+        packed = self.packed_for(params)
+        k = (N, H, W, dev)
+        if k not in self._work:
+            self._work[k] = torch.empty(self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
+        saved = torch.empty(self.lib.dcpt_restormer_saved_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
+        out = torch.empty_like(inp)
+        pp = _l.ptr_array([p.data_ptr() for p in params])
+        _l.check(self.lib.dcpt_restormer_fwd_train(self.plan, pp, _p(packed), _p(inp), _p(out), _p(saved), _p(self._work[k]), N, H, W,
+                                                   _stream()), "restormer_fwd_train")
+        return out, saved
+
+    def backward(self, params, inp, saved, dout):
+        """Parameter gradients (one flat fp32 buffer, views per parameter) of a forward_train call."""
+        N, _, H, W = inp.shape
+        dev = inp.device
+        offs, off = [], 0
+        for p in params:
+            offs.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
+        k = ("bwd", N, H, W, dev)
+        if k not in self._work:
+            self._work[k] = torch.empty(self.lib.dcpt_restormer_bwd_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
+        pp = _l.ptr_array([p.data_ptr() for p in params])
+        gp = _l.ptr_array([g.data_ptr() for g in grads])
+        _l.check(self.lib.dcpt_restormer_bwd(self.plan, pp, _p(self.packed_for(params)), _p(saved), _p(inp), _p(dout.contiguous().float()),
+                                             gp, _p(self._work[k]), N, H, W, _stream()), "restormer_bwd")
+        return grads
+
+
+class _RestormerFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, inp, *params):
+        dparams = [p.detach() for p in params]
+        inp_c = inp.detach().contiguous().float()
+        out, saved = engine.forward_train(dparams, inp_c)
+        ctx.engine, ctx.inp, ctx.saved, ctx.params = engine, inp_c, saved, dparams
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = ctx.engine.backward(ctx.params, ctx.inp, ctx.saved, dout)
+        ctx.saved = None
+        return (None, None) + tuple(grads)     # the input image receives no gradient (as for NAFNet: it is data)
+
+
+def restormer_apply(engine, inp, params):
+    return _RestormerFunction.apply(engine, inp, *params)

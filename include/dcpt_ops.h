@@ -284,6 +284,18 @@ int dcpt_restormer_block_bwd(const dcpt_restormer_plan* plan, int stage, int j, 
                              const void* saved, const float* x, const float* dout, float* dx, float* const* host_grads,
                              void* workspace, int N, int H, int W, dcpt_stream_t stream);
 
+/* Training path of the whole Restormer (what autograd does for Restormer.forward, restormer_arch.py:376-422, hook == False):
+ * dcpt_restormer_fwd_train keeps every block's intermediates in `saved` (dcpt_restormer_saved_bytes; `workspace` as for
+ * dcpt_restormer_fwd), dcpt_restormer_bwd turns dout = d(loss)/d(out) (fp32 NCHW) into the gradients of all parameters
+ * (accumulated += into host_grads, named_parameters() order; workspace: dcpt_restormer_bwd_workspace_bytes). */
+size_t dcpt_restormer_saved_bytes(const dcpt_restormer_plan* plan, int N, int H, int W);
+size_t dcpt_restormer_bwd_workspace_bytes(const dcpt_restormer_plan* plan, int N, int H, int W);
+int dcpt_restormer_fwd_train(const dcpt_restormer_plan* plan, const float* const* host_params, const void* packed, const float* inp,
+                             float* out, void* saved, void* workspace, int N, int H, int W, dcpt_stream_t stream);
+int dcpt_restormer_bwd(const dcpt_restormer_plan* plan, const float* const* host_params, const void* packed, const void* saved,
+                       const float* inp, const float* dout, float* const* host_grads, void* workspace, int N, int H, int W,
+                       dcpt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -275,11 +275,37 @@ def test_restormer_full_vs_oracle():
     assert e < 8e-2 and eq < 4e-2
 
 
+def test_restormer_train_step_golden(golden_dir):
+    """SRModel.optimize_parameters for Restormer (sr_model.py:132-174): forward, L1 loss, backward of ALL parameters through
+    the public module + autograd, against the gradients the REAL reference produced (golden) on the 7-block network.
+    The parameter-gradient bar follows the block-level test (attention-side gradients 3-6e-2 on BiasFree blocks, see there)."""
+    z = load(golden_dir, "restormer_tiny.npz")
+    cfg = dict(dim=int(z["cfg_dim"]), num_blocks=z["cfg_blocks"].tolist(), num_refinement_blocks=int(z["cfg_refine"]),
+               heads=z["cfg_heads"].tolist())
+    net = _net(cfg)
+    net.load_state_dict(RO.random_restormer_state_dict(seed=int(z["seed"]), **cfg), strict=True)
+    out = net(z["inp"].cuda())
+    loss = (out - z["gt"].cuda()).abs().mean()
+    loss.backward()
+    assert rel(out, z["out"]) < 2.5e-2 and abs(float(loss) - float(z["loss"])) < 2e-2 * float(z["loss"])
+    errs = {k: rel(p_.grad, z["g." + k]) for k, p_ in net.named_parameters()}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    med = float(np.median(list(errs.values())))
+    print(f"Restormer tiny train step: loss {float(loss):.5f} vs {float(z['loss']):.5f}; param grads median {med:.2e}, worst {worst}")
+    assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in net.parameters())
+    assert med < 4e-2 and worst[0][1] < 0.25
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
+    opt.step()                                                               # :169; parameters changed in place -> re-packed
+    with torch.no_grad():
+        out2 = net(z["inp"].cuda())
+    assert torch.isfinite(out2).all() and 0 < rel(out2, out) < 1.0
+
+
 def test_restormer_refuses_cpu_and_training():
     from dcpt_b200.lib import DcptError
     net = _net(dict(dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, heads=[1, 2, 4, 8]))
     with pytest.raises(DcptError):
-        net(torch.rand(1, 3, 16, 16).cuda())            # gradients enabled: backward not built
+        net(torch.rand(1, 3, 16, 16).cuda(), hook=True)  # gradients through the DCPT hooks: not built
     with torch.no_grad(), pytest.raises(DcptError):
         net(torch.rand(1, 3, 16, 16))                   # CPU tensor
     with torch.no_grad(), pytest.raises(DcptError):
