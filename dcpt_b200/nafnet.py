@@ -5,6 +5,7 @@
 ``autograd.Function``), so ``loss.backward()``, DDP and optimizers work as with the reference.
 """
 import ctypes as C
+import operator
 import os
 import weakref
 
@@ -70,7 +71,7 @@ class NAFNetEngine:
 
     def packed_for(self, params):
         """bf16 operand cache; refreshed whenever a parameter was modified in place or replaced."""
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (params[0].data_ptr(), params[-1].data_ptr(), len(params), tuple(p._version for p in params))
         if self._packed is None or self._packed.device != params[0].device:
             self._packed = torch.empty(self.lib.dcpt_nafnet_packed_bytes(self.plan), dtype=torch.uint8,
                                        device=params[0].device)
@@ -148,6 +149,33 @@ class NAFNetEngine:
         return grads
 
 
+class _ParamView:
+    """Per-engine cache of everything derived from the parameter list that is costly to rebuild every step for 664
+    tensors (detached views, pointer table, storage key): ~2.5 ms of host time per forward otherwise, during which the
+    GPU idles before the graph launch.  Valid while the same Parameter objects keep their storage (in-place optimizer
+    updates and load_state_dict do; .to() / .cuda() re-allocate and are detected through the probe pointers)."""
+
+    def __init__(self, eng, params):
+        self.params = list(params)
+        self.n = len(params)
+        self.dparams = [p.detach() for p in params]
+        eng._check_params(self.dparams)
+        self.ptrs = tuple(p.data_ptr() for p in self.dparams)
+        self.probe = (self.ptrs[0], self.ptrs[self.n // 2], self.ptrs[-1])
+        self.pp = _l.ptr_array(list(self.ptrs))
+
+    def matches(self, params):
+        return (len(params) == self.n and all(map(operator.is_, params, self.params))
+                and (params[0].data_ptr(), params[self.n // 2].data_ptr(), params[-1].data_ptr()) == self.probe)
+
+
+def _param_view(eng, params):
+    pv = getattr(eng, "_pview", None)
+    if pv is None or not pv.matches(params):
+        pv = eng._pview = _ParamView(eng, list(params))
+    return pv
+
+
 class _GraphSlot:
     """Static buffers and captured CUDA graphs of one (shape, hook, feats, parameter storage) signature.
 
@@ -180,11 +208,12 @@ class _GraphSlot:
         self.busy = False
 
 
-def _graph_forward(eng, params, inp, hook, want_feats, need_grad):
+def _graph_forward(eng, pv, inp, hook, want_feats, need_grad):
     """Returns (out, feats, slot) or None when no slot is free (caller falls back to eager launches)."""
+    params = pv.dparams
     inp = inp.contiguous().float()
     N, _, H, W = inp.shape
-    key = (N, H, W, inp.device, bool(hook), bool(want_feats), tuple(p.data_ptr() for p in params))
+    key = (N, H, W, inp.device, bool(hook), bool(want_feats), pv.ptrs)
     slots = eng._gslots.setdefault(key, [])
     slot = next((s for s in slots if not s.busy), None)
     if slot is None:
@@ -194,7 +223,7 @@ def _graph_forward(eng, params, inp, hook, want_feats, need_grad):
         slots.append(slot)
     packed = eng.packed_for(params)   # re-packed eagerly when a parameter changed; its address is static
     slot.inp.copy_(inp)
-    pp = _l.ptr_array([p.data_ptr() for p in params])
+    pp = pv.pp
     fp = _l.ptr_array([f.data_ptr() for f in slot.feats]) if slot.feats else None
 
     def run():
@@ -214,7 +243,8 @@ def _graph_forward(eng, params, inp, hook, want_feats, need_grad):
     return out, feats, slot
 
 
-def _graph_backward(eng, params, slot, dout, dfeats):
+def _graph_backward(eng, pv, slot, dout, dfeats):
+    params = pv.dparams
     N, H, W = slot.N, slot.H, slot.W
     dev = slot.inp.device
     if slot.flat is None:
@@ -224,6 +254,8 @@ def _graph_backward(eng, params, slot, dout, dfeats):
             off += (p.numel() + 63) // 64 * 64
         slot.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         slot.grads = [slot.flat[o:o + p.numel()].view(p.shape) for o, p in zip(slot.offs, params)]
+        slot.gp = _l.ptr_array([g.data_ptr() for g in slot.grads])
+        slot.shapes = [(o, p.numel(), p.shape) for o, p in zip(slot.offs, params)]
     mask = (dout is not None, tuple(d is not None for d in dfeats) if dfeats else None)
     if dout is not None:
         if slot.dout is None:
@@ -240,8 +272,7 @@ def _graph_backward(eng, params, slot, dout, dfeats):
         eng._scratch[k] = torch.empty(eng.lib.dcpt_nafnet_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
     work = eng._scratch[k]
     packed = eng.packed_for(params)
-    pp = _l.ptr_array([p.data_ptr() for p in params])
-    gp = _l.ptr_array([g.data_ptr() for g in slot.grads])
+    pp, gp = pv.pp, slot.gp
     dfp = None
     if mask[1] and any(mask[1]):
         dfp = _l.ptr_array([s_.data_ptr() if m else 0 for s_, m in zip(slot.dfeats, mask[1])])
@@ -261,7 +292,7 @@ def _graph_backward(eng, params, slot, dout, dfeats):
         slot.bgraphs[mask].replay()
     slot.busy = False
     flat = slot.flat.clone()            # autograd owns the returned gradients; the slot's buffer is rewritten next step
-    return [flat[o:o + p.numel()].view(p.shape) for o, p in zip(slot.offs, params)]
+    return [flat[o:o + n].view(shp) for o, n, shp in slot.shapes]
 
 
 class _NAFNetFunction(torch.autograd.Function):
@@ -272,12 +303,12 @@ class _NAFNetFunction(torch.autograd.Function):
         # need_grad is decided by the caller: grad mode is always OFF inside Function.forward, and a forward whose
         # activations are needed by a later backward must own its saved-activation arena (DCPT runs two forwards
         # before one backward).
-        dparams = [p.detach() for p in params]
+        pv = _param_view(engine, params)
+        dparams = pv.dparams
         inp_c = inp.detach().contiguous().float()
         res = None
         if engine.use_graphs and inp_c.is_cuda and not torch.cuda.is_current_stream_capturing():
-            engine._check_params(dparams)
-            res = _graph_forward(engine, dparams, inp_c, hook, want_feats, need_grad)
+            res = _graph_forward(engine, pv, inp_c, hook, want_feats, need_grad)
         if res is not None:
             out, feats, saved = res
             if need_grad:
@@ -288,7 +319,7 @@ class _NAFNetFunction(torch.autograd.Function):
         else:
             out, feats, saved = engine.forward(dparams, inp_c, hook=hook, want_feats=want_feats, keep_for_backward=need_grad)
         ctx.engine, ctx.hook, ctx.n_feats = engine, hook, len(feats) if feats else 0
-        ctx.inp, ctx.saved, ctx.params = inp_c, saved, dparams
+        ctx.inp, ctx.saved, ctx.params, ctx.pv = inp_c, saved, dparams, pv
         outs = []
         if out is None:
             out = inp_c.new_zeros(())  # placeholder (hook=True returns None to the caller)
@@ -305,7 +336,7 @@ class _NAFNetFunction(torch.autograd.Function):
         if ctx.n_feats:
             dfe = [None if d is None else d.permute(0, 2, 3, 1).contiguous() for d in dfeats]
         if isinstance(ctx.saved, _GraphSlot):
-            grads = _graph_backward(eng, ctx.params, ctx.saved, None if ctx.hook else dout, dfe)
+            grads = _graph_backward(eng, ctx.pv, ctx.saved, None if ctx.hook else dout, dfe)
         else:
             grads = eng.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
         ctx.saved = None
