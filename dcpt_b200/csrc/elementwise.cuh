@@ -35,7 +35,7 @@ int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, 
 int scale_rows_launch(const bf16* g, const float* s, bf16* gs, int N, int HW, int C, cudaStream_t st);
 int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int HW, int C, cudaStream_t st);
 int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t, float* dw, float* db, int N, int C, int HW,
-                   cudaStream_t st);
+                   cudaStream_t st, cudaStream_t st_w = nullptr);
 
 // TLC (test-time local converter, arch_util.py:339-398): P = replicate-padded k1 x k2 box mean of g; I = fp32 scratch [N,H,W,C]
 int tlc_boxmean_launch(const bf16* g, float* I, bf16* P, int N, int H, int W, int C, int k1, int k2, cudaStream_t st);

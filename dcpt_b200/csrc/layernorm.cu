@@ -360,13 +360,13 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
   const int nv = ceil_div(C / 4, lpr);
   const int rows_per_block = kWarps * (32 / lpr);
   // U row groups per warp iteration (see the kernel); the grid is sized so that every warp gets its U groups
-  const int U = nv <= 1 ? 4 : (nv <= 2 ? 2 : 1);
+  const int U = nv <= 1 ? 8 : (nv <= 2 ? 4 : 1);
   long long grid = ceil_div_ll(M, (long long)rows_per_block * U);
   if (grid < 1) grid = 1;
   DCPT_PROF(dcpt_prof_tag2("ln_fwd", M, C), 8.0 * M * C, 6.0 * M * C, st);
 #define LN_FWD(NVV, UU) DCPT_CUDA(dcpt_launch_pdl(ln_fwd_kernel<NVV, UU>, dim3((unsigned)grid), dim3(kWarps * 32), 0, st, x, w, b, n_out, stats, M, C, lpr, eps, center))
-  if (nv <= 1) LN_FWD(1, 4);
-  else if (nv <= 2) LN_FWD(2, 2);
+  if (nv <= 1) LN_FWD(1, 8);
+  else if (nv <= 2) LN_FWD(2, 4);
   else if (nv <= 4) LN_FWD(4, 1);
   else LN_FWD(8, 1);
 #undef LN_FWD

@@ -440,12 +440,17 @@ int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int H
 }
 
 int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t, float* dw, float* db, int N, int C, int HW,
-                   cudaStream_t st) {
+                   cudaStream_t st, cudaStream_t st_w) {
+  // t (needed by the gate backward) on `st`; the parameter gradients dW, db on `st_w` (the caller's weight-gradient stream,
+  // already ordered after the producer of ds)
+  if (st_w == nullptr) st_w = st;
   const long long total = (long long)C * C + C;
-  DCPT_PROF("sca_bwd", 4.0 * N * C * C, 12.0 * C * C, st);
-  DCPT_CUDA(dcpt_launch_pdl(sca_bwd_w_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, st, ds, pool, dw, db, N, C, 1.f / (float)HW));
-  DCPT_LAUNCH_CHECK();
+  {
+    DCPT_PROF("sca_bwd_w", 2.0 * N * C * C, 8.0 * C * C, st_w);
+    DCPT_CUDA(dcpt_launch_pdl(sca_bwd_w_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, st_w, ds, pool, dw, db, N, C, 1.f / (float)HW));
+  }
   dim3 grid(ceil_div(C, 32), N);
+  DCPT_PROF("sca_bwd_t", 2.0 * N * C * C, 4.0 * C * C, st);
   DCPT_CUDA(dcpt_launch_pdl(sca_bwd_t_kernel, grid, dim3(256), 0, st, ds, w, t, C, 1.f / (float)HW));
   DCPT_LAUNCH_CHECK();
   return 0;

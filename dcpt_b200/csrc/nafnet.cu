@@ -226,15 +226,50 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
   return 0;
 }
 
+// Side stream for the weight-gradient work of a block backward.  The four wgrad GEMMs and their finishing kernels only
+// produce parameter gradients: nothing on the activation-gradient chain waits for them, and every kernel of that chain is
+// short and latency-bound at C = 512 (tensor pipe ~33 % busy, ncu), so they are forked onto a second stream and run in the
+// chain's idle slots.  Fork / join are events on the caller's stream (capturable: the side stream joins the CUDA graph);
+// the side stream is joined before the block returns, so the ABI contract ("everything is ordered on `stream`") holds.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ok = false;
+};
+SideStream& side_stream() {
+  static SideStream ss;
+  static bool tried = false;
+  if (!tried) {  // created on the first (eager, un-captured) use
+    tried = true;
+    const char* e = getenv("DCPT_WGRAD_STREAM");
+    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess) {
+      ss.ok = true;
+      for (auto& ev : ss.ev) ss.ok = ss.ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    }
+  }
+  return ss;
+}
+
 int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockSaved& sv, const float* x, const float* dout,
                       const bf16* doutT, const float* Sout, float* dx, bf16* dxT, float* Sx, float* const* G, const BlockWork& wk,
                       int N, int H, int W, int C, cudaStream_t st) {
   const int HW = H * W, M = N * HW;
   const size_t cc = (size_t)C * C;
+  SideStream& ss = side_stream();
+  const bool fork = ss.ok && !g_dcpt_prof_on;   // per-kernel profiling keeps everything on one stream
+  cudaStream_t sw = fork ? ss.s : st;           // stream of the weight-gradient work
+  auto fork_here = [&](int i) -> int {          // side stream waits for everything issued on `st` so far
+    if (fork) {
+      DCPT_CUDA(cudaEventRecord(ss.ev[i], st));
+      DCPT_CUDA(cudaStreamWaitEvent(sw, ss.ev[i], 0));
+    }
+    return 0;
+  };
   // ---- conv5 (gamma folded): wgrad, dgamma, dbias; dgrad fused with SimpleGate backward ----
-  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), st));
-  DCPT_TRY(wgrad_gemm(doutT, C, sv.sg, C, wk.G, M, st));
-  DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C5W], P[P_C5B], P[P_GAMMA], Sout, G[P_C5W], G[P_C5B], G[P_GAMMA], C, C, st));
+  DCPT_TRY(fork_here(0));
+  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), sw));
+  DCPT_TRY(wgrad_gemm(doutT, C, sv.sg, C, wk.G, M, sw));
+  DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C5W], P[P_C5B], P[P_GAMMA], Sout, G[P_C5W], G[P_C5B], G[P_GAMMA], C, C, sw));
   {
     GemmArgs g = gemm_args(M, C, C, doutT, C, pk.w5gt, C, EPI_GATE_BWD);
     g.ep.out_bf16 = wk.dx4; g.ep.ldo = 2 * C; g.ep.aux = sv.x4; g.ep.ldaux = 2 * C; g.ep.C = C;
@@ -242,7 +277,8 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
     DCPT_TRY(gemm_launch(g, st));
   }
   // ---- conv4: wgrad, dgrad ----
-  DCPT_TRY(wgrad_gemm(wk.dx4, 2 * C, sv.n2, C, G[P_C4W], M, st));
+  DCPT_TRY(fork_here(1));
+  DCPT_TRY(wgrad_gemm(wk.dx4, 2 * C, sv.n2, C, G[P_C4W], M, sw));
   {
     GemmArgs g = gemm_args(M, C, 2 * C, wk.dx4, 2 * C, pk.w4t, 2 * C, EPI_STORE);
     g.ep.out_bf16 = wk.dn; g.ep.ldo = C;
@@ -252,9 +288,10 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   DCPT_CUDA(cudaMemsetAsync(wk.Sy, 0, C * sizeof(float), st));
   DCPT_TRY(ln_bwd_launch(wk.dn, sv.y, sv.stats2, P[P_N2W], dout, wk.dy, wk.dyT, G[P_N2W], G[P_N2B], wk.Sy, M, C, st));
   // ---- conv3 (beta folded) ----
-  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), st));
-  DCPT_TRY(wgrad_gemm(wk.dyT, C, sv.gs, C, wk.G, M, st));
-  DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C3W], P[P_C3B], P[P_BETA], wk.Sy, G[P_C3W], G[P_C3B], G[P_BETA], C, C, st));
+  DCPT_TRY(fork_here(2));
+  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), sw));
+  DCPT_TRY(wgrad_gemm(wk.dyT, C, sv.gs, C, wk.G, M, sw));
+  DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C3W], P[P_C3B], P[P_BETA], wk.Sy, G[P_C3W], G[P_C3B], G[P_BETA], C, C, sw));
   DCPT_CUDA(cudaMemsetAsync(wk.ds, 0, (size_t)N * C * sizeof(float), st));
   {  // dgrad, with the SCA backward's ds[n, c] = sum_px d(g*s) * g reduced in the GEMM epilogue
     GemmArgs g = gemm_args(M, C, C, wk.dyT, C, pk.w3bt, C, EPI_STORE);
@@ -263,12 +300,14 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
     DCPT_TRY(gemm_launch(g, st));
   }
   // ---- SCA backward ----
-  DCPT_TRY(sca_bwd_launch(wk.ds, sv.pool, P[P_SCAW], wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st));
+  DCPT_TRY(fork_here(5));
+  DCPT_TRY(sca_bwd_launch(wk.ds, sv.pool, P[P_SCAW], wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st, sw));
   // ---- SimpleGate + depthwise conv backward ----
   DCPT_TRY(dwgate_bwd_a_launch(wk.dgs, sv.s, wk.t, sv.u, P[P_C2W], P[P_C2B], wk.du2, G[P_C2W], G[P_C2B], N, H, W, C, st));
   DCPT_TRY(dwconv_bwd_data_launch(wk.du2, P[P_C2W], wk.du, G[P_C1B], N, H, W, 2 * C, st));
   // ---- conv1 ----
-  DCPT_TRY(wgrad_gemm(wk.du, 2 * C, sv.n1, C, G[P_C1W], M, st));
+  DCPT_TRY(fork_here(3));
+  DCPT_TRY(wgrad_gemm(wk.du, 2 * C, sv.n1, C, G[P_C1W], M, sw));
   {
     GemmArgs g = gemm_args(M, C, 2 * C, wk.du, 2 * C, pk.w1t, 2 * C, EPI_STORE);
     g.ep.out_bf16 = wk.dn; g.ep.ldo = C;
@@ -276,6 +315,10 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   }
   // ---- norm1 backward + residual: dx = dy + LN'(dn1) ----
   DCPT_TRY(ln_bwd_launch(wk.dn, x, sv.stats1, P[P_N1W], wk.dy, dx, dxT, G[P_N1W], G[P_N1B], Sx, M, C, st));
+  if (fork) {  // join: the block's buffers (dx4, dyT, du, G, Sy) are reused by the next block
+    DCPT_CUDA(cudaEventRecord(ss.ev[4], sw));
+    DCPT_CUDA(cudaStreamWaitEvent(st, ss.ev[4], 0));
+  }
   return 0;
 }
 

@@ -99,6 +99,16 @@ def main():
             ms = timeit(lambda: rnet(xr), args.iters)
         res[f"C3_restormer_infer_b{B}_128"] = {"ms": round(ms, 3), "MPix/s": round(B * 128 * 128 / ms / 1e3, 3),
                                                "TFLOP/s": round(B * 77.44e9 / (ms * 1e-3) / 1e12, 1)}
+    # Restormer fine-tune step (not a BASELINE config; recorded for the training path): fwd + L1 + bwd, 128 x 128, batch 4
+    xr = torch.rand(4, 3, 128, 128, device=dev, generator=g)
+    tr = torch.rand(4, 3, 128, 128, device=dev, generator=g)
+
+    def r_step():
+        rnet.zero_grad(set_to_none=True)
+        F.l1_loss(rnet(xr), tr).backward()
+    ms = timeit(r_step, max(3, args.iters // 2))
+    res["restormer_train_step_b4_128"] = {"ms": round(ms, 3), "MPix/s": round(4 * 128 * 128 / ms / 1e3, 3),
+                                          "note": "eager launches (the Restormer training path is not CUDA-graphed yet)"}
     print(json.dumps(res, indent=1))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
