@@ -80,6 +80,9 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long rows, long long col
 // Epilogue tiles: row-major [rows, cols] of fp32 (elem_bytes 4, 128-byte swizzle) or bf16 (elem_bytes 2, 64-byte swizzle),
 // box = 32 columns x 32 rows.
 int make_tmap_epi(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int elem_bytes);
+// PixelShuffle(2) view of an NHWC tensor [NH, 2, W, 2, Cseg] (= [N, 2H, 2W, Cseg]) as a 5-D map (c, j, w, i, nh); box = 32 channels x
+// 1 x bw x 1 x bh with bw * bh = 32: the 32 GEMM rows (consecutive input pixels) of one (i, j) sub-pixel.
+int make_tmap_pixshuf(CUtensorMap* tm, const void* ptr, long long NH, int W, int Cseg, int elem_bytes);
 // 4-D: bf16 NHWC [N, H, W, CH], box 64 x box_w x box_h x 1 (stencil tiles / implicit-GEMM conv operands, zero-filled halo).
 int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH, int box_w, int box_h, int swizzle128 = 0);
 
@@ -199,6 +202,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// 5-D forms (PixelShuffle scatter: the 32-row slab of a GEMM tile is a strided box of the NHWC output)
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
