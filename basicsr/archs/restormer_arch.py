@@ -166,17 +166,25 @@ class Restormer(nn.Module):
         targets = self._hook_targets()
         want = any(len(t) > 0 for t in targets)
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            # training step (SRModel.optimize_parameters, sr_model.py:132-174): autograd Function over the C-ABI fwd / bwd
-            if hook or want:
-                raise DcptError("Restormer: gradients through the DCPT feature hooks (hook=True / forward hooks on "
-                                "decoder_level*) are not built yet; the DCPT pretraining step runs with the NAFNet backbone")
+            # training step (SRModel.optimize_parameters, sr_model.py:132-174; DCPTModel.optimize_parameters,
+            # degradation_classification_pretrain_model.py:133-169): autograd Function over the C-ABI fwd / bwd; the hooked
+            # decoder features are differentiable outputs, so the classifier's gradient flows back into the backbone
             if not inp_img.is_cuda:
                 raise DcptError("dcpt_b200 has no CPU path: input is on %s" % inp_img.device)
-            return restormer_apply(self.engine(), inp_img, params)
+            dead = [i for i, (k, _) in enumerate(self.named_parameters()) if k.startswith(("refinement.", "output."))] if hook else ()
+            out, feats = restormer_apply(self.engine(), inp_img, params, hook=bool(hook), want_feats=want, dead=dead)
+            self._fire_hooks(targets, feats)
+            return None if hook else out
         out, feats = self.engine().forward([p.detach() for p in params], inp_img, hook=bool(hook), want_feats=want)
         if want:
-            for mods, f in zip(targets, feats):
-                for m in mods:
-                    for fn in list(m._forward_hooks.values()):
-                        fn(m, (None,), f.permute(0, 3, 1, 2))
+            self._fire_hooks(targets, [f.permute(0, 3, 1, 2) for f in feats])
         return None if hook else out
+
+    @staticmethod
+    def _fire_hooks(targets, feats):
+        if not feats:
+            return
+        for mods, f in zip(targets, feats):
+            for m in mods:
+                for fn in list(m._forward_hooks.values()):
+                    fn(m, (None,), f)

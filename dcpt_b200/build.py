@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcpt_sm100.so")
-SOURCES = ["gemm_sm100.cu", "gemm_simt.cu", "layernorm.cu", "dwconv.cu", "misc.cu", "conv3x3_img.cu", "dchead.cu", "restormer.cu", "nafnet.cu"]
+SOURCES = ["gemm_sm100.cu", "gemm_simt.cu", "layernorm.cu", "dwconv.cu", "misc.cu", "conv3x3_img.cu", "dchead.cu", "restormer.cu", "nafnet.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 

@@ -974,10 +974,12 @@ size_t dcpt_restormer_bwd_workspace_bytes(const dcpt_restormer_plan* plan, int N
 }
 
 int dcpt_restormer_fwd_train(const dcpt_restormer_plan* p, const float* const* P, const void* packed, const float* inp, float* out,
-                             void* saved, void* workspace, int N, int H, int W, dcpt_stream_t stream) {
+                             void* saved, void* workspace, float* const* host_feats, int hook, int N, int H, int W,
+                             dcpt_stream_t stream) {
   DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, DCPT_E_SHAPE, "restormer: H=%d W=%d must be positive multiples of 8", H, W);
   DCPT_CHECK_ARG((long long)N * H * W * 6 * p->dim < (1ll << 31), DCPT_E_SHAPE, "restormer: batch too large for 32-bit pixel index");
-  DCPT_CHECK_ARG(P && packed && inp && out && saved && workspace, DCPT_E_ARG, "restormer_fwd_train: null argument");
+  DCPT_CHECK_ARG(P && packed && inp && saved && workspace, DCPT_E_ARG, "restormer_fwd_train: null argument");
+  DCPT_CHECK_ARG(hook || out != nullptr, DCPT_E_ARG, "restormer_fwd_train: out is NULL but hook == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena ap(const_cast<void*>(packed));
   NetPacked pk(p, ap);
@@ -1001,6 +1003,7 @@ int dcpt_restormer_fwd_train(const dcpt_restormer_plan* p, const float* const* P
     x = sv.xout[ST_ENC2 + l].back();
   }
   static const int enc_stage[3] = {ST_ENC1, ST_ENC2, ST_ENC3};
+  const float* feats[3] = {nullptr, nullptr, nullptr};  // outputs of decoder_level3, 2, 1 (the DCPT hook targets)
   for (int l = 2; l >= 0; --l) {
     DCPT_TRY(cast_f32_bf16_launch(x, sv.xm_up[l], (long long)N * h * w * d, st));
     DCPT_TRY(conv3_fwd_from(sv.xm_up[l], pk.up[l], ws.conv, N, h, w, d, 2 * d, st));
@@ -1018,14 +1021,24 @@ int dcpt_restormer_fwd_train(const dcpt_restormer_plan* p, const float* const* P
       DCPT_TRY(gemm_launch(g, st));
       DCPT_TRY(stage_fwd_train(p, l == 2 ? ST_DEC3 : ST_DEC2, P, pk, sv.dec_in[ri], sv, N, h, w, st));
       x = sv.xout[l == 2 ? ST_DEC3 : ST_DEC2].back();
+      feats[2 - l] = x;
     } else {
       pixel_shuffle_cat_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, skip, sv.dec_in[2], nullptr, total, h, w, Cs);
       DCPT_LAUNCH_CHECK();
       h *= 2; w *= 2;
       DCPT_TRY(stage_fwd_train(p, ST_DEC1, P, pk, sv.dec_in[2], sv, N, h, w, st));
       x = sv.xout[ST_DEC1].back();
+      feats[2] = x;
     }
   }
+  if (host_feats) {
+    const int fd[3] = {4 * dim, 2 * dim, 2 * dim}, fs[3] = {4, 2, 1};
+    for (int i = 0; i < 3; ++i)
+      if (host_feats[i])
+        DCPT_CUDA(cudaMemcpyAsync(host_feats[i], feats[i], (size_t)N * (H / fs[i]) * (W / fs[i]) * fd[i] * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  if (hook) return 0;  // restormer_arch.py:403 - the DCPT pretraining pass stops after decoder_level1
   if (p->nref > 0) {
     DCPT_TRY(stage_fwd_train(p, ST_REF, P, pk, x, sv, N, H, W, st));
     x = sv.xout[ST_REF].back();
@@ -1034,8 +1047,11 @@ int dcpt_restormer_fwd_train(const dcpt_restormer_plan* p, const float* const* P
 }
 
 int dcpt_restormer_bwd(const dcpt_restormer_plan* p, const float* const* P, const void* packed, const void* saved, const float* inp,
-                       const float* dout, float* const* G, void* workspace, int N, int H, int W, dcpt_stream_t stream) {
-  DCPT_CHECK_ARG(P && packed && saved && inp && dout && G && workspace, DCPT_E_ARG, "restormer_bwd: null argument");
+                       const float* dout, const float* const* dfeats, float* const* G, void* workspace, int N, int H, int W,
+                       dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(P && packed && saved && inp && G && workspace, DCPT_E_ARG, "restormer_bwd: null argument");
+  DCPT_CHECK_ARG(dout || (dfeats && (dfeats[0] || dfeats[1] || dfeats[2])), DCPT_E_ARG, "restormer_bwd: no incoming gradient");
+  DCPT_CHECK_ARG((long long)N * H * W * 2 * p->dim < (1ll << 31), DCPT_E_SHAPE, "restormer_bwd: batch too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena ap(const_cast<void*>(packed));
   NetPacked pk(p, ap);
@@ -1044,14 +1060,25 @@ int dcpt_restormer_bwd(const dcpt_restormer_plan* p, const float* const* P, cons
   Arena aw(workspace);
   NetWorkB wk(p, aw, N, H, W);
   const int dim = p->dim, C2 = 2 * dim;
-  // ---- output conv (restormer_arch.py:413): bias / weight gradients, gradient of its input ----
-  const float* xref = p->nref > 0 ? sv.xout[ST_REF].back() : sv.xout[ST_DEC1].back();
-  DCPT_CUDA(cudaMemsetAsync(wk.cscr, 0, (size_t)27 * C2 * sizeof(float), st));
-  DCPT_TRY(conv3x3_small_wgrad_launch(xref, dout, wk.cscr, p->bias ? G[p->p_out + 1] : nullptr, 1, N, H, W, C2, st));
-  DCPT_TRY(wgrad_finish_perm_launch(wk.cscr, G[p->p_out], C2, 27, FIN_CN_TO_C3, st));
   float *cur = wk.ga[0], *other = wk.gb[0];
-  DCPT_TRY(conv3x3_img_to_feat_launch(dout, P[p->p_out], nullptr, 1, cur, nullptr, nullptr, N, H, W, C2, st));
-  if (p->nref > 0) DCPT_TRY(stage_bwd(p, ST_REF, P, pk, sv, sv.xout[ST_DEC1].back(), cur, other, G, wk, N, H, W, st));
+  // gradient injected at a decoder level's output by the DCPT classifier (the forward hooks of
+  // degradation_classification_pretrain_model.py:60-68, 154-155); i = 0, 1, 2 -> decoder_level3, 2, 1
+  auto add_dfeat = [&](int i, float* g, long long n) -> int {
+    return dfeats && dfeats[i] ? axpy_launch(g, dfeats[i], (int)n, st) : 0;
+  };
+  if (dout) {
+    // ---- output conv (restormer_arch.py:413): bias / weight gradients, gradient of its input ----
+    const float* xref = p->nref > 0 ? sv.xout[ST_REF].back() : sv.xout[ST_DEC1].back();
+    DCPT_CUDA(cudaMemsetAsync(wk.cscr, 0, (size_t)27 * C2 * sizeof(float), st));
+    DCPT_TRY(conv3x3_small_wgrad_launch(xref, dout, wk.cscr, p->bias ? G[p->p_out + 1] : nullptr, 1, N, H, W, C2, st));
+    DCPT_TRY(wgrad_finish_perm_launch(wk.cscr, G[p->p_out], C2, 27, FIN_CN_TO_C3, st));
+    DCPT_TRY(conv3x3_img_to_feat_launch(dout, P[p->p_out], nullptr, 1, cur, nullptr, nullptr, N, H, W, C2, st));
+    if (p->nref > 0) DCPT_TRY(stage_bwd(p, ST_REF, P, pk, sv, sv.xout[ST_DEC1].back(), cur, other, G, wk, N, H, W, st));
+  } else {
+    // hook pass (:403): the forward stopped after decoder_level1, refinement / output receive no gradient
+    DCPT_CUDA(cudaMemsetAsync(cur, 0, (size_t)N * H * W * C2 * sizeof(float), st));
+  }
+  DCPT_TRY(add_dfeat(2, cur, (long long)N * H * W * C2));
   DCPT_TRY(stage_bwd(p, ST_DEC1, P, pk, sv, sv.dec_in[2], cur, other, G, wk, N, H, W, st));
   // ---- decoder: cat split, PixelShuffle^T, up conv dgrad / wgrad, reduce conv ----
   int d = 2 * dim, h = H / 2, w = W / 2;  // d, h, w of the level that feeds the up conv (level l + 1)
@@ -1067,6 +1094,7 @@ int dcpt_restormer_bwd(const dcpt_restormer_plan* p, const float* const* P, cons
     cur = wk.ga[l + 1]; other = wk.gb[l + 1];
     DCPT_TRY(conv3_fwd_from(wk.dconv, pk.up_d[l], cur, N, h, w, 2 * d, d, st));
     if (l == 2) break;  // cur = gradient of the latent stage output
+    DCPT_TRY(add_dfeat(1 - l, cur, (long long)N * h * w * d));  // cur = gradient of decoder_level{l + 2}'s output [N, h, w, d]
     DCPT_TRY(stage_bwd(p, dec_stage[l + 1], P, pk, sv, sv.dec_in[l == 0 ? 1 : 0], cur, other, G, wk, N, h, w, st));
     // reduce_chan conv (2d -> d, 1x1) at level l + 1: cur = gradient of its output [M, d]
     const int ri = l == 0 ? 1 : 0, Mh = N * h * w;

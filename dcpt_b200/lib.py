@@ -90,8 +90,15 @@ PROTOTYPES = {
     "dcpt_restormer_block_bwd": (_I, [_VP, _I, _I, _PP, _VP, _VP, _VP, _VP, _VP, _PP, _VP, _I, _I, _I, _VP]),
     "dcpt_restormer_saved_bytes": (_SZ, [_VP, _I, _I, _I]),
     "dcpt_restormer_bwd_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
-    "dcpt_restormer_fwd_train": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
-    "dcpt_restormer_bwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _VP, _I, _I, _I, _VP]),
+    "dcpt_restormer_fwd_train": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _VP, _PP, _I, _I, _I, _I, _VP]),
+    "dcpt_restormer_bwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _PP, _VP, _I, _I, _I, _VP]),
+    "dcpt_optim_create": (_VP, [C.POINTER(_LL), _I]),
+    "dcpt_optim_destroy": (None, [_VP]),
+    "dcpt_optim_workspace_bytes": (_SZ, [_VP]),
+    "dcpt_optim_num_chunks": (_LL, [_VP]),
+    "dcpt_optim_bind": (_I, [_VP, _VP, _PP, _PP, _PP, _PP, _PP, _VP]),
+    "dcpt_optim_grad_norm": (_I, [_VP, _VP, _VP, _VP]),
+    "dcpt_optim_step": (_I, [_VP, _VP, _I, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _LL, C.c_double, C.c_double, _VP]),
     "dcpt_restormer_fwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _I, _I, _I, _I, _VP]),
 }
 

@@ -303,6 +303,7 @@ class _NAFNetFunction(torch.autograd.Function):
         # need_grad is decided by the caller: grad mode is always OFF inside Function.forward, and a forward whose
         # activations are needed by a later backward must own its saved-activation arena (DCPT runs two forwards
         # before one backward).
+        ctx.set_materialize_grads(False)  # unused outputs (the pixel pass's decoder features in DCPT) arrive as None, not zeros
         pv = _param_view(engine, params)
         dparams = pv.dparams
         inp_c = inp.detach().contiguous().float()

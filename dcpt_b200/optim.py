@@ -1,0 +1,157 @@
+"""Fused parameter update for the training step — host side of ``dcpt_optim_*``.
+
+Replaces, in the reference's ``SRModel.optimize_parameters`` (basicsr/models/sr_model.py:164-174) and
+``DCPTModel.optimize_parameters`` (degradation_classification_pretrain_model.py:163-165):
+
+    torch.nn.utils.clip_grad_norm_(net_g.parameters(), grad_clip)     # :166-167 (optional)
+    optimizer_g.step()                                                # :169, torch.optim.Adam / AdamW (base_model.py:120-139)
+    self.model_ema(decay)                                             # :173-174, a Python loop over 664 tensors (base_model.py:86-95)
+
+by ``FusedAdam.step(grad_clip=..., ema_params=..., ema_decay=...)``: two multi-tensor sm_100a kernels through the C ABI.
+``FusedAdam`` is a ``torch.optim.Optimizer`` whose ``param_groups`` / ``state`` (``step``, ``exp_avg``, ``exp_avg_sq``) are
+those of ``torch.optim.Adam`` / ``AdamW``, so the reference's ``.state`` resume files (base_model.py:413-430) load, and the
+reference's LR schedulers (which edit ``param_groups[i]['lr']``) keep working.  No CPU path: parameters must be CUDA fp32.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as _l
+from .ops import _stream
+
+
+class _Plan:
+    """C plan + device workspace for one list of tensors (a param group's parameters that currently have gradients)."""
+
+    def __init__(self, lib, numels, device):
+        self.lib = lib
+        arr = (C.c_longlong * len(numels))(*numels)
+        h = lib.dcpt_optim_create(arr, len(numels))
+        if not h:
+            raise _l.DcptError("dcpt_optim_create: " + lib.dcpt_last_error().decode())
+        self.h = C.c_void_p(h)
+        self.work = torch.empty(lib.dcpt_optim_workspace_bytes(self.h), dtype=torch.uint8, device=device)
+        self.bound = None
+
+    def bind(self, ptrs):
+        """ptrs: tuple of 5 tuples of device addresses (params, grads, exp_avg, exp_avg_sq, ema or None)."""
+        if ptrs == self.bound:
+            return
+        arrs = [None if p is None else _l.ptr_array(list(p)) for p in ptrs]
+        _l.check(self.lib.dcpt_optim_bind(self.h, C.c_void_p(self.work.data_ptr()), *arrs, _stream()), "optim_bind")
+        self.bound = ptrs
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.dcpt_optim_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (``decoupled_weight_decay=False``) / AdamW (``True``) on the sm_100a fused kernel.
+
+    ``step(grad_clip=None, ema_params=None, ema_decay=0.0)``: ``grad_clip`` = ``max_norm`` of ``clip_grad_norm_`` over ALL
+    parameters of the optimizer (the reference clips ``net_g.parameters()``, which is what ``optimizer_g`` holds);
+    ``ema_params`` = the EMA network's parameters in the same order as the optimizer's (``net_g_ema.parameters()``).
+    Returns the total gradient norm (a 0-dim CUDA tensor, no host sync) when clipping, else None."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled_weight_decay=False,
+                 amsgrad=False, maximize=False):
+        if amsgrad or maximize:
+            raise _l.DcptError("FusedAdam: amsgrad / maximize are not built (the reference never sets them)")
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameters")   # torch.optim.Adam raises ValueError for these
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay,
+                                      decoupled_weight_decay=decoupled_weight_decay, amsgrad=False, maximize=False))
+        self._lib = _l.load_library()
+        self._plans = {}
+
+    def _plan(self, key, numels, device):
+        if key not in self._plans:
+            self._plans[key] = _Plan(self._lib, numels, device)
+        return self._plans[key]
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_clip=None, ema_params=None, ema_decay=0.0):
+        if closure is not None:
+            raise _l.DcptError("FusedAdam.step: closures are not supported")
+        all_params = [p for g in self.param_groups for p in g["params"]]
+        ema_of = {}
+        if ema_params is not None and ema_decay > 0:
+            ema_list = list(ema_params)
+            if len(ema_list) != len(all_params):
+                raise _l.DcptError(f"ema_params has {len(ema_list)} tensors, the optimizer {len(all_params)}")
+            for p, e in zip(all_params, ema_list):
+                if e.shape != p.shape or e.dtype != torch.float32 or not e.is_cuda or not e.is_contiguous():
+                    raise _l.DcptError("ema parameter does not match its parameter (shape / fp32 / CUDA / contiguous)")
+                ema_of[id(p)] = e
+        jobs = []
+        for gi, group in enumerate(self.param_groups):
+            by_step = {}
+            for pi, p in enumerate(group["params"]):
+                if p.grad is None:
+                    continue                                        # torch skips parameters without a gradient
+                if not p.is_cuda:
+                    raise _l.DcptError("dcpt_b200 has no CPU path: parameter is on %s" % p.device)
+                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
+                    raise _l.DcptError("FusedAdam: parameters and gradients must be dense contiguous fp32")
+                st = self.state[p]
+                if len(st) == 0:                                    # torch.optim.adam._init_group
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                by_step.setdefault(float(st["step"]), []).append((pi, p))
+            for step0, items in by_step.items():
+                jobs.append((gi, group, step0, items))
+        if not jobs:
+            return None
+        # clip_grad_norm_ is over every parameter of the model: with one job (the normal case: one group, one step count)
+        # the norm lives in that job's workspace; several jobs share the norm through the host-free path below
+        total_norm = None
+        plans = []
+        for gi, group, step0, items in jobs:
+            ps = [p for _, p in items]
+            gs = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
+            key = (gi, tuple(pi for pi, _ in items))
+            plan = self._plan(key, [p.numel() for p in ps], ps[0].device)
+            emas = tuple(ema_of[id(p)].data_ptr() for p in ps) if ema_of else None
+            plan.bind((tuple(p.data_ptr() for p in ps), tuple(g.data_ptr() for g in gs),
+                       tuple(self.state[p]["exp_avg"].data_ptr() for p in ps),
+                       tuple(self.state[p]["exp_avg_sq"].data_ptr() for p in ps), emas))
+            plans.append((plan, group, step0, ps, gs))
+        if grad_clip is not None and grad_clip > 0:
+            if len(plans) > 1:
+                raise _l.DcptError("FusedAdam: grad_clip with several param groups / step counts is not built")
+            total_norm = torch.empty((), dtype=torch.float32, device=plans[0][3][0].device)
+            _l.check(self._lib.dcpt_optim_grad_norm(plans[0][0].h, C.c_void_p(plans[0][0].work.data_ptr()),
+                                                    C.c_void_p(total_norm.data_ptr()), _stream()), "optim_grad_norm")
+        for plan, group, step0, ps, gs in plans:
+            step = int(step0) + 1
+            b1, b2 = group["betas"]
+            _l.check(self._lib.dcpt_optim_step(plan.h, C.c_void_p(plan.work.data_ptr()), int(bool(group["decoupled_weight_decay"])),
+                                               float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                               float(group["weight_decay"]), step, float(grad_clip or 0.0),
+                                               float(ema_decay if ema_of else 0.0), _stream()), "optim_step")
+            for p in ps:
+                self.state[p]["step"] += 1
+        return total_norm
+
+
+class FusedAdamW(FusedAdam):
+    """torch.optim.AdamW: decoupled weight decay, default 1e-2."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False, maximize=False):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled_weight_decay=True,
+                         amsgrad=amsgrad, maximize=maximize)
+
+
+def get_optimizer(optim_type, params, lr, **kwargs):
+    """Drop-in for BaseModel.get_optimizer (base_model.py:120-139) for the two types the DCPT configs use."""
+    if optim_type == "Adam":
+        return FusedAdam(params, lr, **kwargs)
+    if optim_type == "AdamW":
+        return FusedAdamW(params, lr, **kwargs)
+    raise NotImplementedError(f"optimizer {optim_type} is not on the B200 hot path (Adam / AdamW are)")

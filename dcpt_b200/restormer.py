@@ -125,8 +125,14 @@ class RestormerEngine:
         return out, feats
 
     # ---- training -----------------------------------------------------------------------------------------------
-    def forward_train(self, params, inp):
-        """Returns (out, saved arena).  inp fp32 NCHW on CUDA."""
+    def _feat_buffers(self, N, H, W, dev):
+        d = self.dim                                     # decoder_level3, 2, 1 outputs, NHWC fp32
+        return [torch.empty(N, H // 4, W // 4, 4 * d, dtype=torch.float32, device=dev),
+                torch.empty(N, H // 2, W // 2, 2 * d, dtype=torch.float32, device=dev),
+                torch.empty(N, H, W, 2 * d, dtype=torch.float32, device=dev)]
+
+    def forward_train(self, params, inp, hook=False, want_feats=False):
+        """Returns (out or None, feats or None, saved arena).  inp fp32 NCHW on CUDA."""
         self._check_params(params)
         inp = inp.contiguous().float()
         N, _, H, W = inp.shape
@@ -136,14 +142,17 @@ class RestormerEngine:
         if k not in self._work:
             self._work[k] = torch.empty(self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
         saved = torch.empty(self.lib.dcpt_restormer_saved_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
-        out = torch.empty_like(inp)
+        out = None if hook else torch.empty_like(inp)
+        feats = self._feat_buffers(N, H, W, dev) if want_feats else None
+        fp = _l.ptr_array([f.data_ptr() for f in feats]) if feats else None
         pp = _l.ptr_array([p.data_ptr() for p in params])
-        _l.check(self.lib.dcpt_restormer_fwd_train(self.plan, pp, _p(packed), _p(inp), _p(out), _p(saved), _p(self._work[k]), N, H, W,
-                                                   _stream()), "restormer_fwd_train")
-        return out, saved
+        _l.check(self.lib.dcpt_restormer_fwd_train(self.plan, pp, _p(packed), _p(inp), _p(out), _p(saved), _p(self._work[k]), fp,
+                                                   int(bool(hook)), N, H, W, _stream()), "restormer_fwd_train")
+        return out, feats, saved
 
-    def backward(self, params, inp, saved, dout):
-        """Parameter gradients (one flat fp32 buffer, views per parameter) of a forward_train call."""
+    def backward(self, params, inp, saved, dout, dfeats=None):
+        """Parameter gradients (one flat fp32 buffer, views per parameter) of a forward_train call.  dout: fp32 NCHW or None
+        (hook pass); dfeats: gradients of the decoder-level features (NHWC fp32, entries may be None) or None."""
         N, _, H, W = inp.shape
         dev = inp.device
         offs, off = [], 0
@@ -157,26 +166,49 @@ class RestormerEngine:
             self._work[k] = torch.empty(self.lib.dcpt_restormer_bwd_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
         pp = _l.ptr_array([p.data_ptr() for p in params])
         gp = _l.ptr_array([g.data_ptr() for g in grads])
-        _l.check(self.lib.dcpt_restormer_bwd(self.plan, pp, _p(self.packed_for(params)), _p(saved), _p(inp), _p(dout.contiguous().float()),
+        dout = None if dout is None else dout.contiguous().float()
+        dfe = dfp = None
+        if dfeats and any(d is not None for d in dfeats):
+            dfe = [None if d is None else d.contiguous().float() for d in dfeats]
+            dfp = _l.ptr_array([0 if d is None else d.data_ptr() for d in dfe])
+        if dout is None and dfp is None:
+            return grads                                  # nothing reached this forward: all-zero gradients
+        _l.check(self.lib.dcpt_restormer_bwd(self.plan, pp, _p(self.packed_for(params)), _p(saved), _p(inp), _p(dout), dfp,
                                              gp, _p(self._work[k]), N, H, W, _stream()), "restormer_bwd")
         return grads
 
 
 class _RestormerFunction(torch.autograd.Function):
+    """out, feat_0..2 = Restormer(inp; params).  feats (decoder_level3, 2, 1) are NHWC storage viewed as logical NCHW."""
+
     @staticmethod
-    def forward(ctx, engine, inp, *params):
+    def forward(ctx, engine, inp, hook, want_feats, dead, *params):
+        ctx.set_materialize_grads(False)                  # unused outputs (e.g. the pixel pass's features) arrive as None
         dparams = [p.detach() for p in params]
         inp_c = inp.detach().contiguous().float()
-        out, saved = engine.forward_train(dparams, inp_c)
-        ctx.engine, ctx.inp, ctx.saved, ctx.params = engine, inp_c, saved, dparams
-        return out
+        out, feats, saved = engine.forward_train(dparams, inp_c, hook=hook, want_feats=want_feats)
+        ctx.engine, ctx.inp, ctx.saved, ctx.params, ctx.hook, ctx.n_feats = engine, inp_c, saved, dparams, hook, len(feats) if feats else 0
+        ctx.dead = frozenset(dead) if hook else frozenset()
+        outs = []
+        if out is None:
+            out = inp_c.new_zeros(())                     # placeholder (hook=True returns None to the caller)
+            ctx.mark_non_differentiable(out)
+        outs.append(out)
+        if feats:
+            outs.extend(f.permute(0, 3, 1, 2) for f in feats)
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, dout):
-        grads = ctx.engine.backward(ctx.params, ctx.inp, ctx.saved, dout)
+    def backward(ctx, dout, *dfeats):
+        dfe = [None if d is None else d.permute(0, 2, 3, 1) for d in dfeats] if ctx.n_feats else None
+        grads = ctx.engine.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
         ctx.saved = None
-        return (None, None) + tuple(grads)     # the input image receives no gradient (as for NAFNet: it is data)
+        # a hook pass stops after decoder_level1 (restormer_arch.py:403): refinement / output get NO gradient (None), as in
+        # the reference; the input image receives none either (as for NAFNet: it is data)
+        return (None, None, None, None, None) + tuple(None if i in ctx.dead else g for i, g in enumerate(grads))
 
 
-def restormer_apply(engine, inp, params):
-    return _RestormerFunction.apply(engine, inp, *params)
+def restormer_apply(engine, inp, params, hook=False, want_feats=False, dead=()):
+    """dead: indices (named_parameters() order) of the parameters a hook=True pass never reaches."""
+    res = _RestormerFunction.apply(engine, inp, bool(hook), bool(want_feats), tuple(dead), *params)
+    return (None if hook else res[0]), list(res[1:])

@@ -284,17 +284,55 @@ int dcpt_restormer_block_bwd(const dcpt_restormer_plan* plan, int stage, int j, 
                              const void* saved, const float* x, const float* dout, float* dx, float* const* host_grads,
                              void* workspace, int N, int H, int W, dcpt_stream_t stream);
 
-/* Training path of the whole Restormer (what autograd does for Restormer.forward, restormer_arch.py:376-422, hook == False):
+/* Training path of the whole Restormer (what autograd does for Restormer.forward, restormer_arch.py:376-422):
  * dcpt_restormer_fwd_train keeps every block's intermediates in `saved` (dcpt_restormer_saved_bytes; `workspace` as for
  * dcpt_restormer_fwd), dcpt_restormer_bwd turns dout = d(loss)/d(out) (fp32 NCHW) into the gradients of all parameters
- * (accumulated += into host_grads, named_parameters() order; workspace: dcpt_restormer_bwd_workspace_bytes). */
+ * (accumulated += into host_grads, named_parameters() order; workspace: dcpt_restormer_bwd_workspace_bytes).
+ * DCPT pretraining (models/degradation_classification_pretrain_model.py:60-68, 133-169): host_feats (may be NULL) is a
+ * HOST array of 3 device pointers (entries may be NULL) receiving the outputs of decoder_level3, 2, 1 as fp32 NHWC
+ * ([N,H/4,W/4,4dim], [N,H/2,W/2,2dim], [N,H,W,2dim]) - what the reference's forward hooks collect; hook != 0 stops after
+ * decoder_level1 (restormer_arch.py:403; `out` may then be NULL).  dcpt_restormer_bwd takes the classifier's gradients
+ * w.r.t. those features in dfeats (same layout; NULL or NULL entries = none) and adds them where the features were
+ * taken; dout == NULL is the backward of a hook pass (refinement / output conv gradients are left untouched). */
 size_t dcpt_restormer_saved_bytes(const dcpt_restormer_plan* plan, int N, int H, int W);
 size_t dcpt_restormer_bwd_workspace_bytes(const dcpt_restormer_plan* plan, int N, int H, int W);
 int dcpt_restormer_fwd_train(const dcpt_restormer_plan* plan, const float* const* host_params, const void* packed, const float* inp,
-                             float* out, void* saved, void* workspace, int N, int H, int W, dcpt_stream_t stream);
+                             float* out, void* saved, void* workspace, float* const* host_feats, int hook, int N, int H, int W,
+                             dcpt_stream_t stream);
 int dcpt_restormer_bwd(const dcpt_restormer_plan* plan, const float* const* host_params, const void* packed, const void* saved,
-                       const float* inp, const float* dout, float* const* host_grads, void* workspace, int N, int H, int W,
-                       dcpt_stream_t stream);
+                       const float* inp, const float* dout, const float* const* dfeats, float* const* host_grads, void* workspace,
+                       int N, int H, int W, dcpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Parameter update of the training step — SURVEY.md §8(f) row 1.  Replaces, in SRModel.optimize_parameters
+ * (basicsr/models/sr_model.py:164-174): torch.nn.utils.clip_grad_norm_(net_g.parameters(), grad_clip) (:166-167),
+ * optimizer_g.step() (:169; torch.optim.Adam / AdamW built by BaseModel.get_optimizer, base_model.py:120-139) and
+ * BaseModel.model_ema (base_model.py:86-95: ema.mul_(decay).add_(param, alpha=1-decay) for each of the 664 tensors).
+ * All tensors fp32; one plan covers a list of n_tensors parameter tensors (a param group) through a chunk table, so the
+ * whole update is two multi-tensor launches + one tiny reduction regardless of the number of tensors.
+ *   dcpt_optim_create          host_numels[n_tensors] (HOST array).  NULL on error.
+ *   dcpt_optim_workspace_bytes device workspace (pointer table, chunk table, per-chunk partial sums, total_norm).
+ *   dcpt_optim_bind            uploads the pointer tables (HOST arrays of DEVICE pointers: params, grads, exp_avg,
+ *                              exp_avg_sq, ema; host_ema may be NULL) into the workspace.  H2D copies: not graph-capturable;
+ *                              call again whenever a pointer changes (e.g. autograd handed out new .grad tensors).
+ *   dcpt_optim_grad_norm       total_norm = ||all gradients||_2 (deterministic two-level reduction) kept in the workspace
+ *                              for dcpt_optim_step and, if total_norm != NULL, written there (clip_grad_norm_'s return value).
+ *   dcpt_optim_step            g' = g * min(1, max_norm / (total_norm + 1e-6)) when max_norm > 0 (needs a preceding
+ *                              dcpt_optim_grad_norm; gradients themselves are NOT rewritten), then torch's Adam
+ *                              (decoupled_weight_decay == 0: g' += wd * p) or AdamW (p *= 1 - lr * wd) update in torch's
+ *                              operation order with bias corrections for `step` (the 1-based count of this update), then,
+ *                              when ema_decay > 0 and an ema pointer was bound, ema = ema * decay + (1 - decay) * p.
+ *                              amsgrad / maximize are not supported. */
+typedef struct dcpt_optim_plan dcpt_optim_plan;
+dcpt_optim_plan* dcpt_optim_create(const long long* host_numels, int n_tensors);
+void dcpt_optim_destroy(dcpt_optim_plan* plan);
+size_t dcpt_optim_workspace_bytes(const dcpt_optim_plan* plan);
+long long dcpt_optim_num_chunks(const dcpt_optim_plan* plan);
+int dcpt_optim_bind(const dcpt_optim_plan* plan, void* workspace, float* const* host_params, const float* const* host_grads,
+                    float* const* host_exp_avg, float* const* host_exp_avg_sq, float* const* host_ema, dcpt_stream_t stream);
+int dcpt_optim_grad_norm(const dcpt_optim_plan* plan, void* workspace, float* total_norm, dcpt_stream_t stream);
+int dcpt_optim_step(const dcpt_optim_plan* plan, void* workspace, int decoupled_weight_decay, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, long long step, double max_norm, double ema_decay, dcpt_stream_t stream);
 
 #ifdef __cplusplus
 }

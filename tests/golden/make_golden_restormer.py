@@ -81,5 +81,50 @@ def main():
     npz(os.path.join(HERE, "restormer_tiny.npz"), **arrays)
 
 
+def dcpt_case():
+    """The backbone side of DCPTModel.optimize_parameters with a Restormer (degradation_classification_pretrain_model.py:
+    133-169): the hooked pass on lq (hook=True -> None, restormer_arch.py:403) whose decoder features receive the classifier's
+    gradient.  The classifier is replaced by fixed functionals of the hooked features so that the golden gradients test
+    exactly what the backbone must do with an injected gradient (the head has its own golden):
+      gs.*  l = 0.5 * sum_i mean(feat_i^2)            (smooth gradient, every reachable parameter)
+      gw.*  l = sum_i <feat_i, white noise / sqrt(n)>  (decoder_level1 parameters only: they see feat_2's gradient alone)."""
+    import_reference()
+    from basicsr.archs.restormer_arch import Restormer
+
+    torch.set_num_threads(4)
+    cfg = dict(dim=16, num_blocks=[1, 2, 1, 1], num_refinement_blocks=1, heads=[1, 2, 4, 8])
+    net = Restormer(**cfg)
+    net.load_state_dict(RO.random_restormer_state_dict(seed=7, **cfg), strict=True)
+    g = torch.Generator().manual_seed(21)
+    gt, lq = torch.rand(2, 3, 32, 48, generator=g), torch.rand(2, 3, 32, 48, generator=g)
+    hook_outputs = []
+    for name, m in net.named_modules():       # :65-68 with hook_names = 'decoder'
+        if "decoder" in name and name.count(".") == 1:
+            m.register_forward_hook(lambda mod, i, o: hook_outputs.append(o))
+    assert net(lq, hook=True) is None         # :154
+    assert len(hook_outputs) == 3
+    (0.5 * sum((f ** 2).mean() for f in hook_outputs)).backward()
+    arrays = {"seed": 7, "cfg_dim": 16, "cfg_blocks": [1, 2, 1, 1], "cfg_refine": 1, "cfg_heads": [1, 2, 4, 8]}
+    for i, f in enumerate(hook_outputs):
+        arrays[f"feat{i}"] = f                # gt, lq and the white noise are regenerated by the test from the same generator
+    for k, p in net.named_parameters():       # refinement / output are never reached: no gradient at all
+        assert (p.grad is None) == (k.startswith("refinement.") or k.startswith("output.")), k
+        if p.grad is not None:
+            arrays["gs." + k] = p.grad
+    dfe = [torch.randn(f.shape, generator=g) / f.numel() ** 0.5 for f in hook_outputs]
+    net.zero_grad(set_to_none=True)
+    hook_outputs.clear()
+    net(lq, hook=True)
+    sum((f * d).sum() for f, d in zip(hook_outputs, dfe)).backward()
+    for k, p in net.named_parameters():
+        if k.startswith("decoder_level1."):
+            arrays["gw." + k] = p.grad
+    npz(os.path.join(HERE, "restormer_dcpt_tiny.npz"), **arrays)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "dcpt":
+        dcpt_case()
+    else:
+        main()
+        dcpt_case()

@@ -301,11 +301,90 @@ def test_restormer_train_step_golden(golden_dir):
     assert torch.isfinite(out2).all() and 0 < rel(out2, out) < 1.0
 
 
-def test_restormer_refuses_cpu_and_training():
+def test_restormer_dcpt_hook_gradients_golden(golden_dir):
+    """DCPTModel.optimize_parameters with a Restormer backbone (degradation_classification_pretrain_model.py:133-169): pixel
+    pass on gt (hook=False), hooked pass on lq (hook=True -> None, restormer_arch.py:403), the classifier's gradient enters at
+    the hooked decoder features, ONE backward.  Golden gradients of the hooked pass come from the REAL reference
+    (tests/golden/make_golden_restormer.py::dcpt_case): a smooth functional of the features for every reachable parameter
+    (bar as in the train-step test: median 4e-2, worst 0.25 - the bf16 q / k sensitivity documented there), white-noise feature
+    gradients for decoder_level1 (measured: white-noise gradients pushed through the whole U-Net come out at 5-9e-2, the
+    smooth ones at 1-4e-2, the pixel loss alone at 5-7e-2 on this random-init net).  The combined step is checked through the
+    exact property that backward is additive over the two passes."""
+    z = load(golden_dir, "restormer_dcpt_tiny.npz")
+    cfg = dict(dim=int(z["cfg_dim"]), num_blocks=z["cfg_blocks"].tolist(), num_refinement_blocks=int(z["cfg_refine"]),
+               heads=z["cfg_heads"].tolist())
+    net = _net(cfg)
+    net.load_state_dict(RO.random_restormer_state_dict(seed=int(z["seed"]), **cfg), strict=True)
+    g = torch.Generator().manual_seed(21)
+    gt, lq = torch.rand(2, 3, 32, 48, generator=g), torch.rand(2, 3, 32, 48, generator=g)
+    dfe = [torch.randn(tuple(z[f"feat{i}"].shape), generator=g) / z[f"feat{i}"].numel() ** 0.5 for i in range(3)]
+    hook_outputs = []
+    hooks = [m.register_forward_hook(lambda mod, i, o: hook_outputs.append(o)) for n, m in net.named_modules()
+             if "decoder" in n and n.count(".") == 1]                       # :65-68
+    assert len(hooks) == 3
+    dead = lambda k: k.startswith("refinement.") or k.startswith("output.")  # noqa: E731
+    smooth = lambda fs: 0.5 * sum((f ** 2).mean() for f in fs)               # noqa: E731
+    grads = lambda: {k: (None if p_.grad is None else p_.grad.detach().clone()) for k, p_ in net.named_parameters()}  # noqa: E731
+
+    # (1) hooked pass alone, smooth feature functional
+    assert net(lq.cuda(), hook=True) is None                                # :154
+    assert len(hook_outputs) == 3
+    for i, f in enumerate(hook_outputs):
+        assert tuple(f.shape) == tuple(z[f"feat{i}"].shape) and rel(f, z[f"feat{i}"]) < 2.5e-2, i
+    smooth(hook_outputs).backward()
+    gs = grads()
+    for k in gs:                                                            # never reached -> None, as in the reference
+        assert (gs[k] is None) == dead(k), k
+    errs = {k: rel(v, z["gs." + k]) for k, v in gs.items() if v is not None}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    med = float(np.median(list(errs.values())))
+    print(f"Restormer hooked pass, smooth feature gradient: param grads median {med:.2e}, worst {worst}")
+    assert med < 4e-2 and worst[0][1] < 0.25
+    # (2) white-noise feature gradients, decoder_level1
+    net.zero_grad(set_to_none=True)
+    hook_outputs.clear()
+    net(lq.cuda(), hook=True)
+    sum((f * d.cuda()).sum() for f, d in zip(hook_outputs, dfe)).backward()
+    # (the temperature gradient - one scalar per head, a sum of zero-mean noise terms - is ~0 in the reference here: skipped)
+    ew = [rel(p_.grad, z["gw." + k]) for k, p_ in net.named_parameters() if "gw." + k in z and not k.endswith("temperature")]
+    print(f"white-noise feature gradient: decoder_level1 grads median {float(np.median(ew)):.2e}, max {max(ew):.2e}")
+    assert float(np.median(ew)) < 4e-2 and max(ew) < 0.25
+    # (3) the DCPT step: both passes, one backward == pixel pass alone + hooked pass alone
+    net.zero_grad(set_to_none=True)
+    pix = net(gt.cuda(), hook=False)                                        # :140
+    ((pix - gt.cuda()) ** 2).mean().backward()
+    gp = grads()
+    net.zero_grad(set_to_none=True)
+    pix = net(gt.cuda(), hook=False)
+    hook_outputs.clear()                                                    # :141
+    l_pix = ((pix - gt.cuda()) ** 2).mean()
+    assert net(lq.cuda(), hook=True) is None
+    (l_pix + smooth(hook_outputs)).backward()                               # :163
+    ea = max(rel(p_.grad, gp[k] + (0 if gs[k] is None else gs[k])) for k, p_ in net.named_parameters())
+    print(f"DCPT step additivity (pixel + hooked pass): max rel {ea:.2e}")
+    assert ea < 2e-3
+    # (4) with the real classifier head on the hooked features (fine -> coarse = [2d, 2d, 4d]); both optimizers step
+    from basicsr.archs import build_network
+    d = cfg["dim"]
+    head = build_network(dict(type="PromptIR_NoImg_DC", feature_dims=[2 * d, 2 * d, 4 * d], num_res_blocks=2, num_classes=5)).cuda()
+    opt_g, opt_h = torch.optim.AdamW(net.parameters(), lr=1e-4), torch.optim.AdamW(head.parameters(), lr=1e-4)
+    opt_g.zero_grad(); opt_h.zero_grad()
+    pix = net(gt.cuda(), hook=False)
+    hook_outputs.clear()
+    net(lq.cuda(), hook=True)
+    cls = head(lq.cuda(), hook_outputs[::-1])                               # :155
+    (F.l1_loss(pix, gt.cuda()) + F.cross_entropy(cls, torch.tensor([4, 1]).cuda())).backward()
+    assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in list(net.parameters()) + list(head.parameters()))
+    opt_g.step(); opt_h.step()
+    for h in hooks:
+        h.remove()
+
+
+def test_restormer_refuses_cpu():
     from dcpt_b200.lib import DcptError
     net = _net(dict(dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, heads=[1, 2, 4, 8]))
     with pytest.raises(DcptError):
-        net(torch.rand(1, 3, 16, 16).cuda(), hook=True)  # gradients through the DCPT hooks: not built
+        net(torch.rand(1, 3, 16, 16))                   # CPU tensor, training mode
     with torch.no_grad(), pytest.raises(DcptError):
         net(torch.rand(1, 3, 16, 16))                   # CPU tensor
     with torch.no_grad(), pytest.raises(DcptError):
