@@ -146,8 +146,28 @@ class NAFNetBaseline(nn.Module):
                                     "last block) is materialised by the fused forward")
         return targets
 
+    def _param_list(self):
+        """list(self.parameters()) without the module-tree walk (0.4 ms per call for 664 tensors, paid while the GPU idles
+        before the graph launch): the (module, name) slots are cached, the Parameter objects are read fresh every call."""
+        slots = self.__dict__.get("_pslots")
+        if slots is None:
+            slots = [(m, n) for m in self.modules() for n in m._parameters if m._parameters[n] is not None]
+            self.__dict__["_pslots"] = slots
+        return [m._parameters[n] for m, n in slots]
+
+    def zero_grad(self, set_to_none=True):
+        """nn.Module.zero_grad over the cached parameter slots (same semantics; 0.85 -> 0.1 ms for 664 tensors)."""
+        for p in self._param_list():
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.detach_()
+                    p.grad.requires_grad_(False)
+                    p.grad.zero_()
+
     def forward(self, inp, hook=False):
-        params = list(self.parameters())
+        params = self._param_list()
         targets = self._decoder_hook_targets()
         want_feats = any(len(t) > 0 for t in targets)
         out, feats = nafnet_apply(self.engine(), inp, params, hook=bool(hook), want_feats=want_feats)

@@ -339,6 +339,11 @@ def run_ours(args):
            "api": "basicsr.archs.build_network(NAFNetBaseline) -> net(lq); l1_loss; loss.backward(); loss.item()"
                   + ("; DistributedDataParallel" if world > 1 else "")}
 
+    # ---------------- parameter update, reported beside the step, NOT inside the metric ----------------
+    optim = None
+    if rank == 0 and not args.no_optimizer:
+        optim = bench_optimizer(net, pk, e0, e1)
+
     if rank == 0:
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": round(value, 3), "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
@@ -351,10 +356,57 @@ def run_ours(args):
                            "precision": "bf16 tensor-core operands, fp32 accumulate, fp32 residual stream / params / grads",
                            "l2": "per-step working set (~10 GB of activations) >> 126 MB L2; no explicit flush needed",
                            "launch": "eager launches" if graph is None else "whole fwd+bwd replayed from one CUDA graph"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "optimizer_step": optim}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_optimizer(net, pk, e0, e1, iters=10):
+    """clip_grad_norm_ + AdamW + EMA over the network's 664 tensors (sr_model.py:164-174 after backward): the fused
+    dcpt_optim_* kernels vs the reference's own sequence (torch clip_grad_norm_, torch.optim.AdamW, BaseModel.model_ema's
+    per-tensor loop, base_model.py:86-95) on the same GPU.  Gradients are the last e2e step's."""
+    import torch
+    from dcpt_b200.optim import FusedAdamW
+    params = [p for p in net.parameters() if p.grad is not None]
+    n = sum(p.numel() for p in params)
+    ema = [p.detach().clone() for p in params]
+    kw = dict(lr=1e-4, betas=(0.9, 0.9), weight_decay=1e-4)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    fused = FusedAdamW(params, **kw)
+    ms_f = timed(lambda: fused.step(grad_clip=0.01, ema_params=ema, ema_decay=0.999))
+    # the two multi-tensor launches alone (device time; the roofline figure)
+    plan = fused._fast[0]["jobs"][0][0]
+    lib, ws, st = fused._lib, ctypes.c_void_p(plan.work.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def kernels():
+        lib.dcpt_optim_grad_norm(plan.h, ws, None, st)
+        lib.dcpt_optim_step(plan.h, ws, 1, 1e-4, 0.9, 0.9, 1e-8, 1e-4, 100, 0.01, 0.999, st)
+    ms_k = timed(kernels)
+    ref = torch.optim.AdamW(params, **kw)
+
+    def ref_step():
+        torch.nn.utils.clip_grad_norm_(params, 0.01)
+        ref.step()
+        for e, p in zip(ema, params):
+            e.data.mul_(0.999).add_(p.data, alpha=1 - 0.999)
+    ms_r = timed(ref_step)
+    gbs = 40.0 * n / (ms_k * 1e-3) / 1e9       # 4 B/param gradient-norm pass + 36 B/param update pass (p, g, m, v, ema)
+    return {"what": "clip_grad_norm_(0.01) + AdamW + EMA(0.999), %d tensors / %d parameters, wall per update incl. host" % (len(params), n),
+            "fused_ms": round(ms_f, 3), "fused_kernels_ms": round(ms_k, 3), "torch_ms": round(ms_r, 3), "speedup": round(ms_r / ms_f, 2),
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4),
+                         "bytes_per_param": 40}}
 
 
 def main():
@@ -366,6 +418,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE.json configs[1]: 16)")
     ap.add_argument("--breakdown", action="store_true", help="write gpurun_out/kernel_breakdown.tsv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true", help="skip the (untimed-by-the-metric) parameter-update measurement")
     ap.add_argument("--shapes", action="store_true", help="per-shape GEMM tags in the breakdown")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -343,6 +343,68 @@ ln_bwd_wide_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, con
   }
 }
 
+// C = 512 (the 29 L4 blocks of NAFNet-w64: 16 K rows of 2 KiB): the one-shot kernel above needs 2048 CTAs whose warps each
+// handle ONE row, and spends its time on CTA turnover and on the dependent (load -> 2 shuffle reductions -> w / b reload ->
+// store) chain of that row.  Here CTAs are persistent (2 per SM), the affine parameters live in registers, and a warp loads
+// its NEXT row before it reduces the current one, so the L2 / HBM latency of row i + 1 hides behind the math of row i.
+// Per-row arithmetic (summation order included) is that of ln_fwd_kernel<4, 1>: results are bit-identical.
+__global__ void __launch_bounds__(kWarps * 32, 2)
+ln_fwd_wide_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
+                   float* __restrict__ stats, int M, float eps, int center) {
+  constexpr int C = 512, NV = 4;
+  pdl_sync();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float invC = 1.f / (float)C;
+  float4 wv[NV], bv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    wv[i] = __ldg(reinterpret_cast<const float4*>(w) + lane + i * 32);
+    bv[i] = b ? __ldg(reinterpret_cast<const float4*>(b) + lane + i * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int stride = gridDim.x * kWarps;
+  int row = blockIdx.x * kWarps + warp;
+  float4 cur[NV], nxt[NV];
+  if (row < M) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur[i] = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * C) + lane + i * 32);
+  }
+  for (; row < M; row += stride) {
+    const int rn = row + stride;
+    if (rn < M) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) nxt[i] = __ldg(reinterpret_cast<const float4*>(x + (size_t)rn * C) + lane + i * 32);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sum += cur[i].x + cur[i].y + cur[i].z + cur[i].w;
+    const float mean = group_sum(sum, 32) * invC;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = cur[i].x - mean, bb = cur[i].y - mean, c = cur[i].z - mean, d = cur[i].w - mean;
+      sq += a * a + bb * bb + c * c + d * d;
+    }
+    const float var = group_sum(sq, 32) * invC;
+    const float rstd = 1.f / sqrtf(var + eps);
+    const float shift = center ? mean : 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float o0 = (cur[i].x - shift) * rstd * wv[i].x + bv[i].x;
+      const float o1 = (cur[i].y - shift) * rstd * wv[i].y + bv[i].y;
+      const float o2 = (cur[i].z - shift) * rstd * wv[i].z + bv[i].z;
+      const float o3 = (cur[i].w - shift) * rstd * wv[i].w + bv[i].w;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *(reinterpret_cast<uint2*>(out + (size_t)row * C) + lane + i * 32) = pk;
+    }
+    if (stats && lane == 0) *reinterpret_cast<float2*>(stats + (size_t)row * 2) = make_float2(mean, rstd);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
+  }
+}
+
 inline int pick_lpr(int C) {
   const int nvec = C / 4;
   int lpr = 2;
@@ -364,6 +426,16 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
   long long grid = ceil_div_ll(M, (long long)rows_per_block * U);
   if (grid < 1) grid = 1;
   DCPT_PROF(dcpt_prof_tag2("ln_fwd", M, C), 8.0 * M * C, 6.0 * M * C, st);
+  static const int wide_mode = getenv("DCPT_LN_FWD_WIDE") ? atoi(getenv("DCPT_LN_FWD_WIDE")) : 2;  // CTAs per SM; 0 = one-shot kernel
+  if (C == 512 && M >= 2048 && wide_mode > 0) {
+    int g = wide_mode * dcpt_num_sms();
+    if (g > ceil_div(M, kWarps)) g = ceil_div(M, kWarps);
+    DCPT_CUDA(dcpt_launch_pdl(ln_fwd_wide_kernel, dim3(g), dim3(kWarps * 32), 0, st, x, w, b, n_out, stats, M, eps, center));
+    DCPT_LAUNCH_CHECK();
+    return 0;
+  }
+  static const int cap = getenv("DCPT_LN_FWD_CAP") ? atoi(getenv("DCPT_LN_FWD_CAP")) : 0;  // resident-CTA cap per SM (experiment)
+  if (cap > 0 && grid > (long long)cap * dcpt_num_sms()) grid = (long long)cap * dcpt_num_sms();
 #define LN_FWD(NVV, UU) DCPT_CUDA(dcpt_launch_pdl(ln_fwd_kernel<NVV, UU>, dim3((unsigned)grid), dim3(kWarps * 32), 0, st, x, w, b, n_out, stats, M, C, lpr, eps, center))
   if (nv <= 1) LN_FWD(1, 8);
   else if (nv <= 2) LN_FWD(2, 4);

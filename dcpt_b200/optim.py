@@ -68,75 +68,95 @@ class FusedAdam(torch.optim.Optimizer):
                                       decoupled_weight_decay=decoupled_weight_decay, amsgrad=False, maximize=False))
         self._lib = _l.load_library()
         self._plans = {}
+        self._fast = {}
 
     def _plan(self, key, numels, device):
         if key not in self._plans:
             self._plans[key] = _Plan(self._lib, numels, device)
         return self._plans[key]
 
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._fast = {}                                             # moments / step counts were replaced
+
+    def _prepare(self, gi, group, sig, ema_list):
+        """Slow path, taken when the set of (parameter, gradient, ema) addresses of a group changed: validate, create the
+        optimizer state like torch.optim.adam._init_group, split by step count, (re)bind the C plans."""
+        jobs, by_step = [], {}
+        for pi, p in enumerate(group["params"]):
+            if p.grad is None:
+                continue                                            # torch skips parameters without a gradient
+            if not p.is_cuda:
+                raise _l.DcptError("dcpt_b200 has no CPU path: parameter is on %s" % p.device)
+            if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse \
+                    or not p.grad.is_contiguous():
+                raise _l.DcptError("FusedAdam: parameters and gradients must be dense contiguous fp32")
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            by_step.setdefault(int(st["step"]), []).append(pi)
+        for step0, idx in by_step.items():
+            ps = [group["params"][pi] for pi in idx]
+            plan = self._plan((gi, tuple(idx)), [p.numel() for p in ps], ps[0].device)
+            emas = None
+            if ema_list is not None:
+                emas = []
+                for pi, p in zip(idx, ps):
+                    e = ema_list[pi]
+                    if e.shape != p.shape or e.dtype != torch.float32 or not e.is_cuda or not e.is_contiguous():
+                        raise _l.DcptError("ema parameter does not match its parameter (shape / fp32 / CUDA / contiguous)")
+                    emas.append(e.data_ptr())
+                emas = tuple(emas)
+            plan.bind((tuple(p.data_ptr() for p in ps), tuple(p.grad.data_ptr() for p in ps),
+                       tuple(self.state[p]["exp_avg"].data_ptr() for p in ps),
+                       tuple(self.state[p]["exp_avg_sq"].data_ptr() for p in ps), emas))
+            jobs.append([plan, step0, [self.state[p]["step"] for p in ps]])
+        return {"sig": sig, "jobs": jobs}
+
     @torch.no_grad()
     def step(self, closure=None, grad_clip=None, ema_params=None, ema_decay=0.0):
         if closure is not None:
             raise _l.DcptError("FusedAdam.step: closures are not supported")
-        all_params = [p for g in self.param_groups for p in g["params"]]
-        ema_of = {}
+        ema_all = None
         if ema_params is not None and ema_decay > 0:
-            ema_list = list(ema_params)
-            if len(ema_list) != len(all_params):
-                raise _l.DcptError(f"ema_params has {len(ema_list)} tensors, the optimizer {len(all_params)}")
-            for p, e in zip(all_params, ema_list):
-                if e.shape != p.shape or e.dtype != torch.float32 or not e.is_cuda or not e.is_contiguous():
-                    raise _l.DcptError("ema parameter does not match its parameter (shape / fp32 / CUDA / contiguous)")
-                ema_of[id(p)] = e
-        jobs = []
+            ema_all = list(ema_params)
+            if len(ema_all) != sum(len(g["params"]) for g in self.param_groups):
+                raise _l.DcptError(f"ema_params has {len(ema_all)} tensors, the optimizer "
+                                   f"{sum(len(g['params']) for g in self.param_groups)}")
+        prepared, off = [], 0
         for gi, group in enumerate(self.param_groups):
-            by_step = {}
-            for pi, p in enumerate(group["params"]):
-                if p.grad is None:
-                    continue                                        # torch skips parameters without a gradient
-                if not p.is_cuda:
-                    raise _l.DcptError("dcpt_b200 has no CPU path: parameter is on %s" % p.device)
-                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
-                    raise _l.DcptError("FusedAdam: parameters and gradients must be dense contiguous fp32")
-                st = self.state[p]
-                if len(st) == 0:                                    # torch.optim.adam._init_group
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                by_step.setdefault(float(st["step"]), []).append((pi, p))
-            for step0, items in by_step.items():
-                jobs.append((gi, group, step0, items))
-        if not jobs:
+            ps = group["params"]
+            ema_list = ema_all[off:off + len(ps)] if ema_all is not None else None
+            off += len(ps)
+            # per-step host work is one pass collecting addresses; everything else is cached until an address changes
+            sig = (tuple(p.data_ptr() for p in ps), tuple(0 if p.grad is None else p.grad.data_ptr() for p in ps),
+                   None if ema_list is None else tuple(e.data_ptr() for e in ema_list))
+            fast = self._fast.get(gi)
+            if fast is None or fast["sig"] != sig:
+                fast = self._fast[gi] = self._prepare(gi, group, sig, ema_list)
+            prepared.extend((group, job) for job in fast["jobs"])
+        if not prepared:
             return None
-        # clip_grad_norm_ is over every parameter of the model: with one job (the normal case: one group, one step count)
-        # the norm lives in that job's workspace; several jobs share the norm through the host-free path below
         total_norm = None
-        plans = []
-        for gi, group, step0, items in jobs:
-            ps = [p for _, p in items]
-            gs = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
-            key = (gi, tuple(pi for pi, _ in items))
-            plan = self._plan(key, [p.numel() for p in ps], ps[0].device)
-            emas = tuple(ema_of[id(p)].data_ptr() for p in ps) if ema_of else None
-            plan.bind((tuple(p.data_ptr() for p in ps), tuple(g.data_ptr() for g in gs),
-                       tuple(self.state[p]["exp_avg"].data_ptr() for p in ps),
-                       tuple(self.state[p]["exp_avg_sq"].data_ptr() for p in ps), emas))
-            plans.append((plan, group, step0, ps, gs))
         if grad_clip is not None and grad_clip > 0:
-            if len(plans) > 1:
+            # clip_grad_norm_ is over every parameter of the model = one job in the normal case (one group, one step count)
+            if len(prepared) > 1:
                 raise _l.DcptError("FusedAdam: grad_clip with several param groups / step counts is not built")
-            total_norm = torch.empty((), dtype=torch.float32, device=plans[0][3][0].device)
-            _l.check(self._lib.dcpt_optim_grad_norm(plans[0][0].h, C.c_void_p(plans[0][0].work.data_ptr()),
-                                                    C.c_void_p(total_norm.data_ptr()), _stream()), "optim_grad_norm")
-        for plan, group, step0, ps, gs in plans:
-            step = int(step0) + 1
+            plan = prepared[0][1][0]
+            total_norm = torch.empty((), dtype=torch.float32, device=plan.work.device)
+            _l.check(self._lib.dcpt_optim_grad_norm(plan.h, C.c_void_p(plan.work.data_ptr()), C.c_void_p(total_norm.data_ptr()),
+                                                    _stream()), "optim_grad_norm")
+        for group, job in prepared:
+            plan, step0, step_tensors = job
             b1, b2 = group["betas"]
             _l.check(self._lib.dcpt_optim_step(plan.h, C.c_void_p(plan.work.data_ptr()), int(bool(group["decoupled_weight_decay"])),
                                                float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                               float(group["weight_decay"]), step, float(grad_clip or 0.0),
-                                               float(ema_decay if ema_of else 0.0), _stream()), "optim_step")
-            for p in ps:
-                self.state[p]["step"] += 1
+                                               float(group["weight_decay"]), step0 + 1, float(grad_clip or 0.0),
+                                               float(ema_decay if ema_all is not None else 0.0), _stream()), "optim_step")
+            torch._foreach_add_(step_tensors, 1.0)                  # the per-parameter `step` tensors of torch's state layout
+            job[1] = step0 + 1
         return total_norm
 
 

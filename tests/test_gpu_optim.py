@@ -4,6 +4,7 @@ Compared with: the golden vectors made by torch.optim.Adam / AdamW + clip_grad_n
 (tests/golden/optim_step.npz), the numpy oracle on ragged / unaligned tensors, and at the full NAFNet-w64 size through the
 oracle and through size-independent properties.  Tolerance 2e-6 of the tensor's max magnitude: fp32 arithmetic whose only
 freedom against torch is FMA contraction and the summation order of the gradient norm."""
+import copy
 import os
 import sys
 
@@ -110,13 +111,13 @@ def test_state_dict_interchange_with_torch():
             p.grad = gr.clone()
         opt.step()
     step(ta, a, 0); step(ta, a, 1)
-    fb.load_state_dict(ta.state_dict())                          # torch -> fused
+    fb.load_state_dict(copy.deepcopy(ta.state_dict()))           # torch -> fused (state_dict() hands out references)
     for p, q in zip(a, b):
         q.data.copy_(p.data)
     step(ta, a, 2); step(fb, b, 2)
     assert max(err(q, p.detach().cpu().numpy()) for p, q in zip(a, b)) < TOL
     ta2 = torch.optim.AdamW(a, **kw)
-    ta2.load_state_dict(fb.state_dict())                         # fused -> torch
+    ta2.load_state_dict(copy.deepcopy(fb.state_dict()))          # fused -> torch
     step(ta2, a, 3); step(fb, b, 3)
     assert max(err(q, p.detach().cpu().numpy()) for p, q in zip(a, b)) < TOL
     assert float(fb.state[b[0]]["step"]) == 4
