@@ -305,7 +305,9 @@ def run_ours(args):
     net.load_state_dict(sd, strict=True)
     model = net
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
+        # base_model.py:111-115 constructs DDP with its defaults (25 MB buckets); DCPT_DDP_BUCKET_MB overrides for experiments
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
+                                                          bucket_cap_mb=int(os.getenv("DCPT_DDP_BUCKET_MB", "25")))
     gcpu = torch.Generator().manual_seed(7 + rank)
     h_inp = torch.rand(B, 3, H, W, generator=gcpu).pin_memory()
     h_gt = torch.rand(B, 3, H, W, generator=gcpu).pin_memory()

@@ -30,7 +30,10 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
   const int sub = lane % lpr, gr = lane / lpr;
   const int nvec = C >> 2;
   const float invC = 1.f / (float)C;
-  const long long row_stride = (long long)gridDim.x * kWarps * rpw;
+  // a warp's U row groups are CONSECUTIVE in memory (U * rpw * C * 4 contiguous bytes per warp iteration, neighbouring warps
+  // adjacent): with the groups a whole grid apart every load instruction of a warp opened a different DRAM page
+  const long long row_stride = rpw;
+  const long long iter_stride = (long long)gridDim.x * kWarps * rpw * U;
   constexpr bool kHoist = NV <= 2;  // wide rows reload the affine parameters per row (L1 hits) to keep 4 blocks per SM
   float4 wv[NV], bv[NV];
 #pragma unroll
@@ -39,7 +42,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
     wv[i] = (kHoist && v < nvec) ? __ldg(reinterpret_cast<const float4*>(w) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
     bv[i] = (kHoist && b && v < nvec) ? __ldg(reinterpret_cast<const float4*>(b) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (long long row0 = ((long long)blockIdx.x * kWarps + warp) * rpw + gr; row0 - gr < M; row0 += row_stride * U) {
+  for (long long row0 = ((long long)blockIdx.x * kWarps + warp) * rpw * U + gr; row0 - gr < M; row0 += iter_stride) {
     float4 xv[U][NV];
 #pragma unroll
     for (int u = 0; u < U; ++u) {

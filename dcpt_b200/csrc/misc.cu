@@ -14,28 +14,49 @@ __global__ void sca_fwd_kernel(const float* __restrict__ pool, const float* __re
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= N * C) return;
   const int n = gw / C, co = gw - n * C;
-  float acc = 0.f;
-  for (int ci = lane; ci < C; ci += 32) acc = fmaf(w[(size_t)co * C + ci], pool[(size_t)n * C + ci], acc);
-  acc = warp_sum(acc);
+  // 4 independent chains per lane, combined in a fixed order
+  float a4[4] = {0.f, 0.f, 0.f, 0.f};
+  int ci = lane;
+  for (; ci + 96 < C; ci += 128) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a4[k] = fmaf(__ldg(w + (size_t)co * C + ci + 32 * k), __ldg(pool + (size_t)n * C + ci + 32 * k), a4[k]);
+  }
+  for (; ci < C; ci += 32) a4[0] = fmaf(__ldg(w + (size_t)co * C + ci), __ldg(pool + (size_t)n * C + ci), a4[0]);
+  float acc = warp_sum((a4[0] + a4[1]) + (a4[2] + a4[3]));
   if (lane == 0) s[gw] = b[co] + acc * inv_hw;
 }
 
-__global__ void scale_rows_kernel(const bf16* __restrict__ g, const float* __restrict__ s, bf16* __restrict__ gs, long long nvec,
-                                  int HW, int C) {
+// four 16-byte vectors per thread (a block covers 1024 consecutive vectors): all loads are issued before the first use
+__global__ void __launch_bounds__(256) scale_rows_kernel(const bf16* __restrict__ g, const float* __restrict__ s, bf16* __restrict__ gs,
+                                                         long long nvec, int HW, int C) {
   pdl_sync();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nvec) return;
   const int CV = C >> 3;
-  const long long px = i / CV;
-  const int c = (int)(i - px * CV) * 8;
-  const int n = (int)(px / HW);
-  float v[8];
-  unpack8(ldg16(g + i * 8), v);
-  const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (size_t)n * C + c));
-  const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + (size_t)n * C + c + 4));
-  v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
-  v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-  stg16(gs + i * 8, pack8(v));
+  const long long base = (long long)blockIdx.x * 1024 + threadIdx.x;
+  uint4 raw[4];
+  float4 s0[4], s1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256;
+    if (i < nvec) {
+      const long long px = i / CV;
+      const int c = (int)(i - px * CV) * 8;
+      const int n = (int)(px / HW);
+      raw[k] = ldg16(g + i * 8);
+      s0[k] = __ldg(reinterpret_cast<const float4*>(s + (size_t)n * C + c));
+      s1[k] = __ldg(reinterpret_cast<const float4*>(s + (size_t)n * C + c + 4));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256;
+    if (i < nvec) {
+      float v[8];
+      unpack8(raw[k], v);
+      v[0] *= s0[k].x; v[1] *= s0[k].y; v[2] *= s0[k].z; v[3] *= s0[k].w;
+      v[4] *= s1[k].x; v[5] *= s1[k].y; v[6] *= s1[k].z; v[7] *= s1[k].w;
+      stg16(gs + i * 8, pack8(v));
+    }
+  }
 }
 
 // ds[n][c] += sum_{px in image n} dgs[px][c] * g[px][c]
@@ -94,8 +115,18 @@ sca_bwd_t_kernel(const float* __restrict__ ds, const float* __restrict__ w, floa
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ci = blockIdx.x * 32 + lane, n = blockIdx.y;
   float acc = 0.f;
-  if (ci < C)
-    for (int co = warp; co < C; co += 8) acc = fmaf(__ldg(w + (size_t)co * C + ci), __ldg(ds + (size_t)n * C + co), acc);
+  if (ci < C) {
+    // 4 independent chains (the loads of 4 rows of W in flight at once); the final order of additions is fixed
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    int co = warp;
+    for (; co + 24 < C; co += 32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        a4[k] = fmaf(__ldg(w + (size_t)(co + 8 * k) * C + ci), __ldg(ds + (size_t)n * C + co + 8 * k), a4[k]);
+    }
+    for (; co < C; co += 8) a4[0] = fmaf(__ldg(w + (size_t)co * C + ci), __ldg(ds + (size_t)n * C + co), a4[0]);
+    acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+  }
   s_part[warp][lane] = acc;
   __syncthreads();
   if (warp == 0 && ci < C) {
@@ -417,7 +448,7 @@ int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, 
 int scale_rows_launch(const bf16* g, const float* s, bf16* gs, int N, int HW, int C, cudaStream_t st) {
   const long long nvec = (long long)N * HW * (C / 8);
   DCPT_PROF("scale_rows", (double)N * HW * C, 4.0 * N * HW * C, st);
-  DCPT_CUDA(dcpt_launch_pdl(scale_rows_kernel, dim3((unsigned)ceil_div_ll(nvec, 256)), dim3(256), 0, st, g, s, gs, nvec, HW, C));
+  DCPT_CUDA(dcpt_launch_pdl(scale_rows_kernel, dim3((unsigned)ceil_div_ll(nvec, 1024)), dim3(256), 0, st, g, s, gs, nvec, HW, C));
   DCPT_LAUNCH_CHECK();
   return 0;
 }

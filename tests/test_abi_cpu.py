@@ -93,3 +93,32 @@ def test_registry_surface():
     assert list(net.state_dict().keys()) == [k for k, _ in got]
     with pytest.raises(AssertionError):
         ARCH_REGISTRY.register(type(net))                                 # duplicate names rejected (registry.py:42-45)
+
+
+def test_cached_parameter_slots_follow_the_module():
+    """NAFNetBaseline._param_list (the per-call replacement for list(self.parameters())) returns the live Parameter objects
+    in named_parameters() order, also after a Parameter was replaced, and zero_grad keeps nn.Module's semantics."""
+    import torch
+    from basicsr.archs import build_network
+    net = build_network(dict(type="NAFNetBaseline", width=8, enc_blk_nums=[1, 1], middle_blk_num=1, dec_blk_nums=[1, 1]))
+    a, b = net._param_list(), list(net.parameters())
+    assert len(a) == len(b) and all(x is y for x, y in zip(a, b))
+    net.intro.weight = torch.nn.Parameter(torch.zeros_like(net.intro.weight))     # replaced object is picked up
+    assert all(x is y for x, y in zip(net._param_list(), net.parameters()))
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    net.zero_grad(set_to_none=False)
+    assert all(p.grad is not None and float(p.grad.abs().sum()) == 0 for p in net.parameters())
+    net.zero_grad()
+    assert all(p.grad is None for p in net.parameters())
+
+
+def test_optim_plan_chunks_need_no_gpu(lib):
+    numels = (ctypes.c_longlong * 5)(1, 8192, 8193, 0, 100003)
+    plan = ctypes.c_void_p(lib.dcpt_optim_create(numels, 5))
+    assert plan.value
+    assert lib.dcpt_optim_num_chunks(plan) == 1 + 1 + 2 + 0 + 13                  # 8192-element chunks, never across tensors
+    assert lib.dcpt_optim_workspace_bytes(plan) > 0
+    assert lib.dcpt_optim_step(plan, None, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 0.0, 0.0, None) == -1   # null workspace -> code
+    lib.dcpt_optim_destroy(plan)
+    assert not lib.dcpt_optim_create(numels, 0) and b"optim_create" in lib.dcpt_last_error()
