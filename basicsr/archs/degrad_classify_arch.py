@@ -76,6 +76,9 @@ class PromptIR_NoImg_DC(nn.Module):
         self._engine = DCHeadEngine(self.feature_dims, num_res_blocks, num_classes)
         assert [k for k, _ in self.named_parameters()] == self._engine.names, "parameter order differs from the C-side plan"
 
+    def engine(self):
+        return self._engine
+
     def forward(self, lq, features):
         """``lq`` is unused, as in the reference (:622-641).  features: fine -> coarse, logical NCHW CUDA tensors."""
         return dchead_apply(self._engine, list(features), list(self.parameters()))

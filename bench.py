@@ -305,9 +305,13 @@ def run_ours(args):
     net.load_state_dict(sd, strict=True)
     model = net
     if world > 1:
-        # base_model.py:111-115 constructs DDP with its defaults (25 MB buckets); DCPT_DDP_BUCKET_MB overrides for experiments
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
-                                                          bucket_cap_mb=int(os.getenv("DCPT_DDP_BUCKET_MB", "25")))
+        if args.ddp == "torch":
+            # base_model.py:111-115 constructs DDP with its defaults (25 MB buckets); DCPT_DDP_BUCKET_MB overrides for experiments
+            model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
+                                                              bucket_cap_mb=int(os.getenv("DCPT_DDP_BUCKET_MB", "25")))
+        else:
+            from dcpt_b200.dist import FlatGradDataParallel
+            model = FlatGradDataParallel(net)               # the package's DDP replacement: one all-reduce of the flat buffer
     gcpu = torch.Generator().manual_seed(7 + rank)
     h_inp = torch.rand(B, 3, H, W, generator=gcpu).pin_memory()
     h_gt = torch.rand(B, 3, H, W, generator=gcpu).pin_memory()
@@ -339,7 +343,8 @@ def run_ours(args):
     e2e = {"value": round(world * B * H * W / (ms_e2e * 1e-3) / 1e6, 3), "unit": "MPix/s",
            "h2d_bytes_per_step": int(2 * h_inp.numel() * 4), "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3),
            "api": "basicsr.archs.build_network(NAFNetBaseline) -> net(lq); l1_loss; loss.backward(); loss.item()"
-                  + ("; DistributedDataParallel" if world > 1 else "")}
+                  + (("; torch DistributedDataParallel" if args.ddp == "torch" else "; dcpt_b200.dist.FlatGradDataParallel")
+                     if world > 1 else "")}
 
     # ---------------- parameter update, reported beside the step, NOT inside the metric ----------------
     optim = None
@@ -420,6 +425,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE.json configs[1]: 16)")
     ap.add_argument("--breakdown", action="store_true", help="write gpurun_out/kernel_breakdown.tsv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
+                    help="N > 1, e2e arm: dcpt_b200.dist.FlatGradDataParallel (default) or torch DistributedDataParallel")
     ap.add_argument("--no-optimizer", action="store_true", help="skip the (untimed-by-the-metric) parameter-update measurement")
     ap.add_argument("--shapes", action="store_true", help="per-shape GEMM tags in the breakdown")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")

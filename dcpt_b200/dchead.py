@@ -28,6 +28,7 @@ class DCHeadEngine:
         self.dims = list(feature_dims)
         self.nb = num_res_blocks
         self.k = num_classes
+        self.grad_sync = None      # set by dcpt_b200.dist.FlatGradDataParallel: callable(flat fp32 gradient buffer)
         # parameter order == reference named_parameters() (degrad_classify_arch.py:577-620)
         names = ["mixing_weights"]
         for i in range(len(self.dims)):
@@ -170,7 +171,12 @@ class DCHeadEngine:
         """Returns (dfeats list of fp32 NHWC, grads list in parameter order)."""
         pk = self._pack(params)
         dev = dlogits.device
-        grads = [torch.zeros_like(p, dtype=torch.float32) for p in params]
+        offs, off = [], 0
+        for p in params:                                   # one flat buffer (256-byte aligned views): one all-reduce under DP
+            offs.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
         maxw = max(2 * d for d in self.dims)
         scratch = torch.empty(self.lib.dcpt_conv3x3_packed_elems(maxw, maxw, 0), dtype=torch.float32, device=dev)
         N, h, w, Cn = ctx["shp"]
@@ -197,7 +203,9 @@ class DCHeadEngine:
                      "mix_bwd")
             # dx (= d z_in) is also the gradient of the previous stage's pooled output (z = prev + mw * feat)
         mw = ctx["mw"]
-        grads[0] = (mw * (dmw - (dmw * mw).sum())).to(grads[0].dtype)          # softmax backward on len(dims) scalars
+        grads[0].copy_((mw * (dmw - (dmw * mw).sum())).view(grads[0].shape))   # softmax backward on len(dims) scalars
+        if self.grad_sync is not None:
+            self.grad_sync(flat)
         return dfeats, grads
 
 

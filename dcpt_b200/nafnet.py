@@ -40,6 +40,7 @@ class NAFNetEngine:
         # CUDA-graph replay of the autograd path (nafnet_apply): DCPT_CUDA_GRAPH=0 launches every kernel from the host
         self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0"
         self._gslots = {}
+        self.grad_sync = None      # set by dcpt_b200.dist.FlatGradDataParallel: callable(flat fp32 gradient buffer)
         self.tlc = False
 
     def set_tlc(self, kernels):
@@ -128,8 +129,9 @@ class NAFNetEngine:
         """Accumulates parameter gradients into ``grads`` (list of fp32 tensors; allocated zeroed if None)."""
         N, _, H, W = inp.shape
         dev = inp.device
+        flat = None
         if grads is None:
-            grads = self.alloc_flat_grads(params)[1]
+            flat, grads = self.alloc_flat_grads(params)
         k = ("work", N, H, W, dev)
         if k not in self._scratch:
             self._scratch[k] = torch.empty(self.lib.dcpt_nafnet_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8,
@@ -146,6 +148,8 @@ class NAFNetEngine:
         packed = self.packed_for(params)
         _l.check(self.lib.dcpt_nafnet_bwd(self.plan, pp, _p(packed), _p(saved), _p(inp), _p(dout), dfp, gp, _p(work), N, H,
                                           W, _stream()), "nafnet_bwd")
+        if flat is not None and self.grad_sync is not None:
+            self.grad_sync(flat)            # data-parallel wrapper (dcpt_b200.dist.FlatGradDataParallel): one all-reduce
         return grads
 
 
@@ -291,6 +295,8 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
     else:
         slot.bgraphs[mask].replay()
     slot.busy = False
+    if eng.grad_sync is not None:
+        eng.grad_sync(slot.flat)            # data-parallel wrapper: ONE mean all-reduce of the flat gradient buffer
     flat = slot.flat.clone()            # autograd owns the returned gradients; the slot's buffer is rewritten next step
     return [flat[o:o + n].view(shp) for o, n, shp in slot.shapes]
 

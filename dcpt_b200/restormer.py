@@ -35,6 +35,7 @@ class RestormerEngine:
         # whole-forward CUDA-graph replay (~700 launches per 128x128 tile become one); DCPT_CUDA_GRAPH=0 launches eagerly
         self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0"
         self._graphs = {}
+        self.grad_sync = None      # set by dcpt_b200.dist.FlatGradDataParallel: callable(flat fp32 gradient buffer)
 
     def __del__(self):
         try:
@@ -175,6 +176,8 @@ class RestormerEngine:
             return grads                                  # nothing reached this forward: all-zero gradients
         _l.check(self.lib.dcpt_restormer_bwd(self.plan, pp, _p(self.packed_for(params)), _p(saved), _p(inp), _p(dout), dfp,
                                              gp, _p(self._work[k]), N, H, W, _stream()), "restormer_bwd")
+        if self.grad_sync is not None:
+            self.grad_sync(flat)
         return grads
 
 

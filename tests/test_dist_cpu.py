@@ -41,6 +41,52 @@ def _worker(rank, world, port, q):
     torch.distributed.destroy_process_group()
 
 
+def _worker_wrapper(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from basicsr.archs import build_network
+    from dcpt_b200 import dist as D
+    D.init_dist("gloo", timeout_s=120)
+    torch.manual_seed(100 + rank)                                         # ranks construct different weights ...
+    net = build_network(dict(type="NAFNetBaseline", width=8, enc_blk_nums=[1], middle_blk_num=1, dec_blk_nums=[1]))
+    dp = D.FlatGradDataParallel(net)                                      # ... rank 0's are broadcast (as DDP does)
+    assert dp.module is net and net.engine().grad_sync is not None
+    chk = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    gathered = [torch.empty_like(chk) for _ in range(world)]
+    torch.distributed.all_gather(gathered, chk)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    flat = torch.full((1000,), float(rank + 1))
+    net.engine().grad_sync(flat)                                          # what the engine calls after its backward kernels
+    mean_ok = bool(torch.allclose(flat, torch.full((1000,), (1 + world) / 2)))
+    flat2 = torch.full((10,), float(rank))
+    with dp.no_sync():
+        net.engine().grad_sync(flat2)
+    skip_ok = bool(torch.equal(flat2, torch.full((10,), float(rank))))
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    dp.zero_grad()
+    zg_ok = all(p.grad is None for p in net.parameters())
+    if rank == 0:
+        q.put((same, mean_ok, skip_ok, zg_ok))
+    torch.distributed.destroy_process_group()
+
+
+def test_flat_grad_data_parallel_gloo_world2():
+    """dcpt_b200.dist.FlatGradDataParallel: broadcast at construction, the engine's grad_sync hook = mean all-reduce,
+    no_sync(), zero_grad; the CUDA engine itself is exercised by bench.py --gpus 2 on the GPU box."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker_wrapper, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == (True, True, True, True)
+
+
 def test_data_parallel_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
