@@ -109,6 +109,28 @@ def main():
     ms = timeit(r_step, max(3, args.iters // 2))
     res["restormer_train_step_b4_128"] = {"ms": round(ms, 3), "MPix/s": round(4 * 128 * 128 / ms / 1e3, 3),
                                           "note": "eager launches (the Restormer training path is not CUDA-graphed yet)"}
+    # DCPT pretrain step with the Restormer backbone (hook_names: decoder -> decoder_level{3,2,1}.body), 128 x 128, batch 4
+    d = rcfg["dim"]
+    rhead = build_network(dict(type="PromptIR_NoImg_DC", feature_dims=[2 * d, 2 * d, 4 * d], num_res_blocks=2, num_classes=5)).to(dev)
+    r_hooked = []
+    rhooks = [m.register_forward_hook(lambda mod, i, o: r_hooked.append(o)) for n, m in rnet.named_modules()
+              if "decoder" in n and n.count(".") == 1]
+    rl = torch.randint(0, 5, (4,), device=dev, generator=g)
+
+    def r_dcpt_step():
+        rnet.zero_grad(set_to_none=True); rhead.zero_grad(set_to_none=True)
+        pix = rnet(tr, hook=False)
+        r_hooked.clear()
+        l_pix = F.l1_loss(pix, tr)
+        rnet(xr, hook=True)
+        cls = rhead(xr, r_hooked[::-1])
+        (l_pix + F.cross_entropy(cls, rl)).backward()
+        r_hooked.clear()
+    ms = timeit(r_dcpt_step, max(3, args.iters // 2))
+    res["restormer_dcpt_pretrain_step_b4_128"] = {"ms": round(ms, 3), "MPix/s": round(4 * 128 * 128 / ms / 1e3, 3),
+                                                  "note": "2 Restormer forwards (one hooked) + classifier head + one backward, eager launches"}
+    for h in rhooks:
+        h.remove()
     print(json.dumps(res, indent=1))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
