@@ -207,9 +207,17 @@ class _GraphSlot:
         self.fgraph = None
         self.bgraphs = {}
         self.busy = False
+        self.owner = None
 
-    def release(self):
-        self.busy = False
+    def acquire(self):
+        """Marks the slot busy for one forward; the returned token releases it only while that forward still owns it (the
+        finalizer of an OLD autograd node may fire after a newer forward has taken the slot)."""
+        self.busy, self.owner = True, object()
+        return self.owner
+
+    def release(self, token=None):
+        if token is None or token is self.owner:
+            self.busy, self.owner = False, None
 
 
 def _graph_forward(eng, pv, inp, hook, want_feats, need_grad):
@@ -241,7 +249,7 @@ def _graph_forward(eng, pv, inp, hook, want_feats, need_grad):
         slot.fgraph = g
     else:
         slot.fgraph.replay()
-    slot.busy = bool(need_grad)
+    slot.token = slot.acquire() if need_grad else None
     out = None if hook else slot.out.clone()
     feats = [f.clone() for f in slot.feats] if slot.feats else None
     return out, feats, slot
@@ -294,7 +302,7 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
         slot.bgraphs[mask] = g
     else:
         slot.bgraphs[mask].replay()
-    slot.busy = False
+    slot.release()
     if eng.grad_sync is not None:
         eng.grad_sync(slot.flat)            # data-parallel wrapper: ONE mean all-reduce of the flat gradient buffer
     flat = slot.flat.clone()            # autograd owns the returned gradients; the slot's buffer is rewritten next step
@@ -320,7 +328,7 @@ class _NAFNetFunction(torch.autograd.Function):
             out, feats, saved = res
             if need_grad:
                 try:
-                    weakref.finalize(ctx, saved.release)   # a forward whose backward never runs must not pin the slot
+                    weakref.finalize(ctx, saved.release, saved.token)   # a forward whose backward never runs must not pin the slot
                 except TypeError:
                     pass
         else:

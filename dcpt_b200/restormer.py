@@ -7,6 +7,8 @@ no CPU path.
 """
 import ctypes as C
 import os
+import warnings
+import weakref
 
 import torch
 
@@ -36,6 +38,10 @@ class RestormerEngine:
         self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0"
         self._graphs = {}
         self.grad_sync = None      # set by dcpt_b200.dist.FlatGradDataParallel: callable(flat fp32 gradient buffer)
+        # training path: CUDA-graph replay of forward-with-save and of backward (~1900 launches per step otherwise);
+        # DCPT_RESTORMER_TRAIN_GRAPH=0 keeps eager launches
+        self.use_train_graphs = self.use_graphs and os.getenv("DCPT_RESTORMER_TRAIN_GRAPH", "1") != "0"
+        self._tslots = {}
 
     def __del__(self):
         try:
@@ -181,6 +187,135 @@ class RestormerEngine:
         return grads
 
 
+class _TrainSlot:
+    """Static buffers and captured graphs of one (shape, hook, feats, parameter storage) training signature.  The slot owns
+    the saved-activation arena: it is busy from a forward until its backward ran (DCPT: two forwards before one backward
+    take two slots)."""
+
+    MAX_PER_KEY = 3
+
+    def __init__(self, eng, N, H, W, dev, hook, want_feats):
+        self.N, self.H, self.W, self.hook = N, H, W, hook
+        self.inp = torch.empty(N, 3, H, W, dtype=torch.float32, device=dev)
+        self.out = None if hook else torch.empty_like(self.inp)
+        self.saved = torch.empty(eng.lib.dcpt_restormer_saved_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
+        self.feats = eng._feat_buffers(N, H, W, dev) if want_feats else None
+        self.dout = self.dfeats = self.flat = self.shapes = self.gp = None
+        self.graphs = {}            # "fwd" / backward mask -> captured graph
+        self.busy = False
+        self.owner = None
+
+    def acquire(self):
+        """Marks the slot busy for one forward; the returned token releases it only while that forward still owns it (the
+        finalizer of an OLD autograd node may fire after a newer forward has taken the slot)."""
+        self.busy, self.owner = True, object()
+        return self.owner
+
+    def release(self, token=None):
+        if token is None or token is self.owner:
+            self.busy, self.owner = False, None
+
+
+def _run_or_replay(eng, slot, key, run):
+    """First use: launch eagerly (one-time initialisation inside the library must not be captured; the results of this run
+    are the ones used), then capture for the following steps.  If the runtime refuses the capture, keep launching eagerly."""
+    g = slot.graphs.get(key)
+    if g is not None:
+        g.replay()
+        return
+    run()
+    if not eng.use_train_graphs:
+        return
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            run()
+        slot.graphs[key] = g
+    except RuntimeError as e:
+        warnings.warn(f"dcpt_b200: CUDA-graph capture of the Restormer training path failed ({e}); launching eagerly")
+        eng.use_train_graphs = False
+
+
+def _train_graph_forward(eng, params, inp, hook, want_feats):
+    """(out, feats, slot), or None when no slot is free / capture is unavailable (caller launches eagerly)."""
+    eng._check_params(params)
+    N, _, H, W = inp.shape
+    dev = inp.device
+    key = (N, H, W, dev, hook, want_feats, tuple(p.data_ptr() for p in params))
+    slots = eng._tslots.setdefault(key, [])
+    slot = next((s_ for s_ in slots if not s_.busy), None)
+    if slot is None:
+        if len(slots) >= _TrainSlot.MAX_PER_KEY:
+            return None
+        slot = _TrainSlot(eng, N, H, W, dev, hook, want_feats)
+        slots.append(slot)
+    packed = eng.packed_for(params)                       # re-packed eagerly when a parameter changed; static address
+    k = (N, H, W, dev)
+    if k not in eng._work:
+        eng._work[k] = torch.empty(eng.lib.dcpt_restormer_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
+    work = eng._work[k]
+    slot.inp.copy_(inp)
+    pp = _l.ptr_array([p.data_ptr() for p in params])
+    fp = _l.ptr_array([f.data_ptr() for f in slot.feats]) if slot.feats else None
+
+    def run():
+        _l.check(eng.lib.dcpt_restormer_fwd_train(eng.plan, pp, _p(packed), _p(slot.inp), _p(slot.out), _p(slot.saved), _p(work), fp,
+                                                  int(hook), N, H, W, _stream()), "restormer_fwd_train")
+    token = slot.acquire()
+    _run_or_replay(eng, slot, "fwd", run)
+    out = None if hook else slot.out.clone()
+    feats = [f.clone() for f in slot.feats] if slot.feats else None
+    return out, feats, slot, token
+
+
+def _train_graph_backward(eng, params, slot, dout, dfeats):
+    N, H, W = slot.N, slot.H, slot.W
+    dev = slot.inp.device
+    if slot.flat is None:
+        offs, off = [], 0
+        for p in params:
+            offs.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        slot.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        slot.shapes = [(o, p.numel(), p.shape) for o, p in zip(offs, params)]
+        slot.gp = _l.ptr_array([slot.flat[o:o + n].data_ptr() for o, n, _ in slot.shapes])
+    has_df = bool(dfeats) and any(d is not None for d in dfeats)
+    mask = (dout is not None, tuple(d is not None for d in dfeats) if has_df else None)
+    if mask[0]:
+        if slot.dout is None:
+            slot.dout = torch.empty_like(slot.inp)
+        slot.dout.copy_(dout)
+    if has_df:
+        if slot.dfeats is None:
+            slot.dfeats = [torch.empty_like(f) for f in slot.feats]
+        for s_, d in zip(slot.dfeats, dfeats):
+            if d is not None:
+                s_.copy_(d)
+    if not mask[0] and not has_df:
+        slot.release()
+        flat = torch.zeros_like(slot.flat)                 # nothing reached this forward: all-zero gradients
+        return [flat[o:o + n].view(shp) for o, n, shp in slot.shapes]
+    k = ("bwd", N, H, W, dev)
+    if k not in eng._work:
+        eng._work[k] = torch.empty(eng.lib.dcpt_restormer_bwd_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
+    work = eng._work[k]
+    packed = eng.packed_for(params)
+    pp = _l.ptr_array([p.data_ptr() for p in params])
+    dfp = _l.ptr_array([s_.data_ptr() if m else 0 for s_, m in zip(slot.dfeats, mask[1])]) if has_df else None
+    dptr = _p(slot.dout) if mask[0] else None
+
+    def run():
+        slot.flat.zero_()
+        _l.check(eng.lib.dcpt_restormer_bwd(eng.plan, pp, _p(packed), _p(slot.saved), _p(slot.inp), dptr, dfp, slot.gp, _p(work),
+                                            N, H, W, _stream()), "restormer_bwd")
+    _run_or_replay(eng, slot, mask, run)
+    slot.release()
+    if eng.grad_sync is not None:
+        eng.grad_sync(slot.flat)                           # data-parallel wrapper: ONE mean all-reduce of the flat buffer
+    flat = slot.flat.clone()                               # autograd owns the returned gradients; the slot's buffer is reused
+    return [flat[o:o + n].view(shp) for o, n, shp in slot.shapes]
+
+
 class _RestormerFunction(torch.autograd.Function):
     """out, feat_0..2 = Restormer(inp; params).  feats (decoder_level3, 2, 1) are NHWC storage viewed as logical NCHW."""
 
@@ -189,7 +324,17 @@ class _RestormerFunction(torch.autograd.Function):
         ctx.set_materialize_grads(False)                  # unused outputs (e.g. the pixel pass's features) arrive as None
         dparams = [p.detach() for p in params]
         inp_c = inp.detach().contiguous().float()
-        out, feats, saved = engine.forward_train(dparams, inp_c, hook=hook, want_feats=want_feats)
+        res = None
+        if engine.use_train_graphs and inp_c.is_cuda and not torch.cuda.is_current_stream_capturing():
+            res = _train_graph_forward(engine, dparams, inp_c, hook, want_feats)
+        if res is not None:
+            out, feats, saved, token = res
+            try:
+                weakref.finalize(ctx, saved.release, token)   # a forward whose backward never runs must not pin the slot
+            except TypeError:
+                pass
+        else:
+            out, feats, saved = engine.forward_train(dparams, inp_c, hook=hook, want_feats=want_feats)
         ctx.engine, ctx.inp, ctx.saved, ctx.params, ctx.hook, ctx.n_feats = engine, inp_c, saved, dparams, hook, len(feats) if feats else 0
         ctx.dead = frozenset(dead) if hook else frozenset()
         outs = []
@@ -204,7 +349,10 @@ class _RestormerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, *dfeats):
         dfe = [None if d is None else d.permute(0, 2, 3, 1) for d in dfeats] if ctx.n_feats else None
-        grads = ctx.engine.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
+        if isinstance(ctx.saved, _TrainSlot):
+            grads = _train_graph_backward(ctx.engine, ctx.params, ctx.saved, None if ctx.hook else dout, dfe)
+        else:
+            grads = ctx.engine.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
         ctx.saved = None
         # a hook pass stops after decoder_level1 (restormer_arch.py:403): refinement / output get NO gradient (None), as in
         # the reference; the input image receives none either (as for NAFNet: it is data)

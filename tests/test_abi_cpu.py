@@ -122,3 +122,21 @@ def test_optim_plan_chunks_need_no_gpu(lib):
     assert lib.dcpt_optim_step(plan, None, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 0.0, 0.0, None) == -1   # null workspace -> code
     lib.dcpt_optim_destroy(plan)
     assert not lib.dcpt_optim_create(numels, 0) and b"optim_create" in lib.dcpt_last_error()
+
+
+def test_graph_slot_ownership_tokens():
+    """A slot released by the finalizer of an OLD autograd node must not be freed under a newer forward that owns it."""
+    from dcpt_b200.nafnet import _GraphSlot
+    from dcpt_b200.restormer import _TrainSlot
+    for cls in (_GraphSlot, _TrainSlot):
+        s = object.__new__(cls)
+        s.busy, s.owner = False, None
+        t1 = s.acquire()
+        assert s.busy
+        s.release()                      # backward of forward 1 ran
+        assert not s.busy
+        t2 = s.acquire()                 # forward 2 takes the slot
+        s.release(t1)                    # ... then forward 1's node is garbage-collected: stale token, no effect
+        assert s.busy and s.owner is t2
+        s.release(t2)                    # forward 2 dropped without backward
+        assert not s.busy
