@@ -437,8 +437,6 @@ int ln_fwd_launch(const float* x, const float* w, const float* b, bf16* n_out, f
     DCPT_LAUNCH_CHECK();
     return 0;
   }
-  static const int cap = getenv("DCPT_LN_FWD_CAP") ? atoi(getenv("DCPT_LN_FWD_CAP")) : 0;  // resident-CTA cap per SM (experiment)
-  if (cap > 0 && grid > (long long)cap * dcpt_num_sms()) grid = (long long)cap * dcpt_num_sms();
 #define LN_FWD(NVV, UU) DCPT_CUDA(dcpt_launch_pdl(ln_fwd_kernel<NVV, UU>, dim3((unsigned)grid), dim3(kWarps * 32), 0, st, x, w, b, n_out, stats, M, C, lpr, eps, center))
   if (nv <= 1) LN_FWD(1, 8);
   else if (nv <= 2) LN_FWD(2, 4);
