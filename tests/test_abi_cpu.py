@@ -140,3 +140,41 @@ def test_graph_slot_ownership_tokens():
         assert s.busy and s.owner is t2
         s.release(t2)                    # forward 2 dropped without backward
         assert not s.busy
+
+
+def test_restormer_module_hook_plumbing_without_gpu(monkeypatch):
+    """Host logic of the Restormer mirror in a DCPT step (degradation_classification_pretrain_model.py:60-68, 140, 154): forward
+    hooks registered on the one-dot `decoder_level{k}.body` modules fire in the order level 3, 2, 1 with the engine's feature
+    outputs, hook=True returns None, and the parameters a hooked pass never reaches are named to the autograd glue.  The
+    engine call is stubbed (no GPU here); the CUDA path is covered by tests/test_gpu_restormer.py."""
+    import torch
+    import basicsr.archs.restormer_arch as RA
+    from dcpt_b200.lib import DcptError
+    net = RA.Restormer(dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, heads=[1, 2, 4, 8])
+    calls = []
+
+    def fake_apply(engine, inp, params, hook=False, want_feats=False, dead=()):
+        calls.append(dict(hook=hook, want_feats=want_feats, dead=list(dead), n=len(params)))
+        N, _, H, W = inp.shape
+        feats = [torch.full((N, 64, H // 4, W // 4), 3.0), torch.full((N, 32, H // 2, W // 2), 2.0), torch.full((N, 32, H, W), 1.0)]
+        return (None if hook else inp + 1), (feats if want_feats else [])
+    monkeypatch.setattr(RA, "restormer_apply", fake_apply)
+    monkeypatch.setattr(RA.Restormer, "engine", lambda self: None)
+    got = []
+    names = [n for n, m in net.named_modules() if "decoder" in n and n.count(".") == 1]
+    assert names == ["decoder_level3.body", "decoder_level2.body", "decoder_level1.body"]
+    for n, m in net.named_modules():
+        if n in names:
+            m.register_forward_hook(lambda mod, i, o: got.append(float(o.flatten()[0])))
+    x = torch.rand(1, 3, 16, 16)
+    with pytest.raises(DcptError):
+        net(x)                                             # CPU tensor in training mode: no CPU path
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    out = net(x, hook=False)
+    assert out is not None and got == [3.0, 2.0, 1.0] and calls[-1]["want_feats"] and calls[-1]["dead"] == []
+    got.clear()
+    assert net(x, hook=True) is None and got == [3.0, 2.0, 1.0]
+    keys = [k for k, _ in net.named_parameters()]
+    dead = [keys[i] for i in calls[-1]["dead"]]
+    assert dead and all(k.startswith(("refinement.", "output.")) for k in dead)
+    assert len(dead) == sum(k.startswith(("refinement.", "output.")) for k in keys) and calls[-1]["n"] == len(keys)
