@@ -126,6 +126,60 @@ def cpu_baseline(budget_s=12.0, max_steps=8):
                       f"({med * 1e3:.0f} ms/step), torch {torch.__version__} threads={torch.get_num_threads()}"}
 
 
+def torch_gpu_baseline(dev, B, iters=5):
+    """SURVEY.md §8(d) "the real bar": the reference's PyTorch path (as restated by oracle/nafnet_oracle.py: the same
+    F.conv2d / mean / pow / chunk / pixel_shuffle ops, cuDNN + ATen kernels, autograd backward) on the SAME B200, same
+    batch, same metric: (1) eager fp32 NCHW with torch's defaults as basicsr/test.py:25-27 leaves them (cudnn.benchmark on,
+    TF32 lines commented out -> cuDNN conv TF32 allowed by torch's default, matmul TF32 off); (2) bf16 autocast +
+    channels_last.  Timed with CUDA events after warm-up, outside the timed region of the product arm; never part of `value`."""
+    import torch
+    from oracle import nafnet_oracle as O
+    torch.backends.cudnn.benchmark = True
+    sd = {k: v.to(dev) for k, v in O.random_nafnet_state_dict(seed=0, **CFG).items()}
+    g = torch.Generator(device=dev).manual_seed(1)
+    inp = torch.rand(B, 3, H, W, device=dev, generator=g)
+    gt = torch.rand(B, 3, H, W, device=dev, generator=g)
+    out = {}
+
+    def run(tag, autocast, chl):
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+        if chl:
+            leaves = {k: (v.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True) if v.dim() == 4 else v)
+                      for k, v in leaves.items()}
+        x = inp.contiguous(memory_format=torch.channels_last) if chl else inp
+
+        def step():
+            for v in leaves.values():
+                v.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                o = O.nafnet_fwd(x, leaves, CFG["enc_blk_nums"], CFG["middle_blk_num"], CFG["dec_blk_nums"])
+                loss = (o.float() - gt).abs().mean()
+            loss.backward()
+        try:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); step(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            ms = ts[len(ts) // 2]
+            out[tag] = {"value": round(B * H * W / (ms * 1e-3) / 1e6, 3), "unit": "MPix/s", "ms_per_step": round(ms, 2)}
+        except Exception as e:  # an OOM or a missing cuDNN engine must not take the product line down
+            out[tag] = {"value": None, "error": f"{type(e).__name__}: {str(e)[:120]}"}
+        del leaves
+        torch.cuda.empty_cache()
+    run("eager_fp32", False, False)
+    run("bf16_autocast_channels_last", True, True)
+    out["what"] = (f"oracle/nafnet_oracle.py (functional restatement of the reference's PyTorch ops) on this GPU, batch {B}x3x{H}x{W}, "
+                   f"fwd + L1 + autograd bwd, median of {iters} steps after 3 warm-ups, torch {torch.__version__}, cudnn.benchmark=True, "
+                   "torch-default TF32 policy")
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port) on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -352,6 +406,14 @@ def run_ours(args):
         optim = bench_optimizer(net, pk, e0, e1)
 
     if rank == 0:
+        torch_arm = None
+        if world == 1 and not args.no_torch_arm:
+            del net, model
+            torch.cuda.empty_cache()
+            torch_arm = torch_gpu_baseline(dev, B)
+            for k in ("eager_fp32", "bf16_autocast_channels_last"):
+                if torch_arm[k].get("value"):
+                    torch_arm[k]["ours_over_this"] = round(value / torch_arm[k]["value"], 2)
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": round(value, 3), "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
@@ -364,7 +426,7 @@ def run_ours(args):
                            "l2": "per-step working set (~10 GB of activations) >> 126 MB L2; no explicit flush needed",
                            "launch": "eager launches" if graph is None else "whole fwd+bwd replayed from one CUDA graph"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "optimizer_step": optim}
+                "optimizer_step": optim, "torch_gpu_baseline": torch_arm}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -425,6 +487,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE.json configs[1]: 16)")
     ap.add_argument("--breakdown", action="store_true", help="write gpurun_out/kernel_breakdown.tsv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-arm", action="store_true", help="skip the same-GPU PyTorch (eager fp32 / bf16 autocast) baseline arms")
     ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
                     help="N > 1, e2e arm: dcpt_b200.dist.FlatGradDataParallel (default) or torch DistributedDataParallel")
     ap.add_argument("--no-optimizer", action="store_true", help="skip the (untimed-by-the-metric) parameter-update measurement")

@@ -30,16 +30,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=True):
-    if not force and not needs_build():
+def build(force=False, verbose=True, trace=False):
+    """trace=True builds the debug variant libdcpt_sm100_trace.so (-DDCPT_TRACE: per-CTA GEMM event timeline, tools/gemm_trace.py)."""
+    if not trace and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    out = LIB.replace(".so", "_trace.so") if trace else LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DDCPT_TRACE"] if trace else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     if verbose:
         print("[dcpt_b200] " + " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True, cwd=CSRC)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
-    print(LIB)
+    print(build(force="--force" in sys.argv, trace="--trace" in sys.argv))

@@ -20,6 +20,25 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 
+#ifdef DCPT_TRACE
+// Debug build only (python -m dcpt_b200.build --trace -> libdcpt_sm100_trace.so): per-CTA event timeline of the GEMM kernel,
+// 16 slots x (globaltimer ns, clock64) per CTA, written by one thread per event (tools/gemm_trace.py reads it).
+__device__ unsigned long long* g_dcpt_trace = nullptr;
+extern "C" int dcpt_debug_set_trace(void* buf) {
+  return (int)cudaMemcpyToSymbol(g_dcpt_trace, &buf, sizeof(buf));
+}
+#define TRACE(slot)                                                       \
+  do {                                                                    \
+    unsigned long long* _t = g_dcpt_trace;                                \
+    if (_t) {                                                             \
+      _t[(blockIdx.x * 16 + (slot)) * 2] = globaltimer_ns();              \
+      _t[(blockIdx.x * 16 + (slot)) * 2 + 1] = (unsigned long long)clock64(); \
+    }                                                                     \
+  } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 namespace {
 
 // batched problems in one launch (GemmArgs::m_per_batch / k_per_batch); all zero = plain GEMM
@@ -97,6 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int M, int N, int K, int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep, ConvGeom cg, BatchGeom bg) {
   using C = Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) TRACE(0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)C::STAGES * A_STAGE_BYTES;
@@ -149,6 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's tail
   pdl_sync();
+  if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -253,6 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (tile == blockIdx.x && kb == kb0) TRACE(2);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * C::B_STAGE_BYTES);
@@ -271,6 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         umma_commit(&tfull[acc]);  // accumulator ready for the epilogue
+        TRACE(tile == blockIdx.x ? 3 : 4);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -409,6 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (has_r) issue_in(ebuf + b * 4096, &rf[b], n0, m0);
             }
             mbar_wait(&tfull[acc], acc_phase);
+            if (ew == 0 && lane == 0) TRACE(tile == blockIdx.x ? 5 : 7);
             tc_fence_after();
             first = false;
           }
@@ -529,12 +553,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (ew == 0 && lane == 0) TRACE(tile == blockIdx.x ? 6 : 8);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
       if (lane == 0) bulk_wait_all();
+      if (ew == 0 && lane == 0) TRACE(9);
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_t = tile % tiles_n;
@@ -674,6 +700,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(10);
   if constexpr (EPI == EPI_GATE_BWD_TMA) {
     if (ep.colsum)
       for (int i = threadIdx.x; i < 2 * ep.C; i += kThreads) {

@@ -176,6 +176,29 @@ __global__ void __launch_bounds__(THREADS) adam_ema_kernel(const TensorPtrs* __r
   }
 }
 
+// Order-independent 64-bit fingerprint of the bound PARAMETER tensors: sum over all elements of bits(p_i) * odd(position) mod 2^64.
+// Any single changed bit changes the sum; used by the engines to notice parameter writes that bypass torch's version counter
+// (`p.data.mul_()` in the reference's model_ema, base_model.py:86-95) before re-using the packed bf16 operand cache.
+__global__ void __launch_bounds__(THREADS) param_hash_kernel(const TensorPtrs* __restrict__ T, const Chunk* __restrict__ Cn,
+                                                             unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long s_h[THREADS / 32];
+  const Chunk c = Cn[blockIdx.x];
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(T[c.tensor].p + c.start);
+  const unsigned long long base = ((unsigned long long)c.tensor << 40) + (unsigned long long)c.start;
+  unsigned long long h = 0;
+  for (int i = threadIdx.x; i < c.count; i += THREADS)
+    h += (unsigned long long)p[i] * (((base + (unsigned long long)i) * 0x9E3779B97F4A7C15ull) | 1ull);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0) s_h[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < THREADS / 32; ++w) t += s_h[w];
+    atomicAdd(out, t);
+  }
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -258,6 +281,29 @@ int dcpt_optim_grad_norm(const dcpt_optim_plan* plan, void* workspace, float* to
     DCPT_LAUNCH_CHECK();
   }
   grad_norm_final_kernel<<<1, THREADS, 0, st>>>(partial, nc, norm, total_norm);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int dcpt_optim_set_norm(const dcpt_optim_plan* plan, void* workspace, const float* total_norm, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(plan && workspace && total_norm, DCPT_E_ARG, "optim_set_norm: null argument");
+  DCPT_CUDA(cudaMemcpyAsync(static_cast<char*>(workspace) + plan->off_norm, total_norm, sizeof(float), cudaMemcpyDeviceToDevice,
+                            static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int dcpt_optim_param_hash(const dcpt_optim_plan* plan, void* workspace, unsigned long long* hash, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(plan && workspace && hash, DCPT_E_ARG, "optim_param_hash: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* w = static_cast<char*>(workspace);
+  const int nc = (int)plan->chunks.size();
+  DCPT_CUDA(cudaMemsetAsync(hash, 0, sizeof(unsigned long long), st));
+  if (nc == 0) return 0;
+  long long total = 0;
+  for (long long v : plan->numels) total += v;
+  DCPT_PROF("optim_param_hash", 0.0, 4.0 * total, st);
+  param_hash_kernel<<<nc, THREADS, 0, st>>>(reinterpret_cast<const TensorPtrs*>(w + plan->off_tensors),
+                                            reinterpret_cast<const Chunk*>(w + plan->off_chunks), hash);
   DCPT_LAUNCH_CHECK();
   return 0;
 }

@@ -13,6 +13,7 @@ import torch
 
 from . import lib as _l
 from .ops import _p, _stream, gemm
+from .params import PackedCacheKey
 
 BF = torch.bfloat16
 
@@ -41,12 +42,11 @@ class DCHeadEngine:
         self.names = names
         self.index = {n: i for i, n in enumerate(names)}
         self._packed = None
-        self._packed_key = None
+        self._packed_key = PackedCacheKey()
 
     # ---- packed bf16 operand cache ---------------------------------------------------------------
     def _pack(self, params):
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if key == self._packed_key:
+        if self._packed is not None and not self._packed_key.stale(params):  # dcpt_b200/params.py
             return self._packed
         dev = params[0].device
         P = lambda n: params[self.index[n]]
@@ -75,7 +75,7 @@ class DCHeadEngine:
                 conv3(n)
             elif n.endswith("conv1.weight") or n.endswith("conv3.weight") or n.startswith("downsample_layers"):
                 mat(n)
-        self._packed, self._packed_key = pk, key
+        self._packed = pk
         return pk
 
     # ---- one BottleneckBlock (degrad_classify_arch.py:227-243) ------------------------------------

@@ -63,8 +63,10 @@ def broadcast_params_(params, src=0, group=None):
     """Make every rank start from rank `src`'s weights (what DDP does at construction)."""
     _, world = get_dist_info()
     if world > 1:
-        for p in params:
-            dist.broadcast(p.data if hasattr(p, "data") else p, src=src, group=group)
+        with torch.no_grad():
+            for p in params:
+                # p.detach() shares p's version counter (p.data does not): the engines' packed-operand caches see the write
+                dist.broadcast(p.detach(), src=src, group=group)
     return params
 
 

@@ -98,6 +98,8 @@ PROTOTYPES = {
     "dcpt_optim_num_chunks": (_LL, [_VP]),
     "dcpt_optim_bind": (_I, [_VP, _VP, _PP, _PP, _PP, _PP, _PP, _VP]),
     "dcpt_optim_grad_norm": (_I, [_VP, _VP, _VP, _VP]),
+    "dcpt_optim_set_norm": (_I, [_VP, _VP, _VP, _VP]),
+    "dcpt_optim_param_hash": (_I, [_VP, _VP, _VP, _VP]),
     "dcpt_optim_step": (_I, [_VP, _VP, _I, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _LL, C.c_double, C.c_double, _VP]),
     "dcpt_restormer_fwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _I, _I, _I, _I, _VP]),
 }
@@ -110,7 +112,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.getenv("DCPT_LIB") or LIB_PATH  # DCPT_LIB: debug builds (libdcpt_sm100_trace.so)
     if not os.path.exists(path) and os.getenv("BASICSR_JIT") == "True":
         from .build import build
         build()

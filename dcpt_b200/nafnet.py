@@ -13,6 +13,7 @@ import torch
 
 from . import lib as _l
 from .ops import _p, _stream
+from .params import LRUCache, PackedCacheKey
 
 
 class NAFNetEngine:
@@ -35,11 +36,14 @@ class NAFNetEngine:
             self.lib.dcpt_nafnet_param_shape(self.plan, i, dims)
             self.shapes.append(tuple(dims))
         self._packed = None
-        self._packed_key = None
-        self._scratch = {}
+        self._packed_key = PackedCacheKey()
+        # per-shape resources are LRU-bounded (params.py): workspaces / inference arenas of the eager path, and the CUDA-graph
+        # slots (each owns a saved-activation arena, ~12 KB per pixel at width 64) of the autograd path
+        self._scratch = LRUCache()
         # CUDA-graph replay of the autograd path (nafnet_apply): DCPT_CUDA_GRAPH=0 launches every kernel from the host
         self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0"
-        self._gslots = {}
+        self._gslots = LRUCache(can_evict=lambda slots: not any(s.busy for s in slots))
+        self._seen_nograd = LRUCache(cap=64)
         self.grad_sync = None      # set by dcpt_b200.dist.FlatGradDataParallel: callable(flat fp32 gradient buffer)
         self.tlc = False
 
@@ -50,7 +54,7 @@ class NAFNetEngine:
         kw = (C.c_int * max(n, 1))(*[k[1] for k in kernels])
         _l.check(self.lib.dcpt_nafnet_set_tlc(self.plan, kh, kw, n), "nafnet_set_tlc")
         self.tlc = n > 0
-        self._gslots = {}
+        self._gslots.clear()
 
     def __del__(self):
         try:
@@ -71,17 +75,20 @@ class NAFNetEngine:
                 raise _l.DcptError("parameters must be contiguous fp32 (master weights)")
 
     def packed_for(self, params):
-        """bf16 operand cache; refreshed whenever a parameter was modified in place or replaced."""
-        key = (params[0].data_ptr(), params[-1].data_ptr(), len(params), tuple(p._version for p in params))
+        """bf16 operand cache; refreshed whenever a parameter was modified or replaced (dcpt_b200/params.py: version
+        counters, plus a device fingerprint of the weights on no-grad forwards for writes through ``p.data``)."""
         if self._packed is None or self._packed.device != params[0].device:
             self._packed = torch.empty(self.lib.dcpt_nafnet_packed_bytes(self.plan), dtype=torch.uint8,
                                        device=params[0].device)
-            self._packed_key = None
-        if key != self._packed_key:
+            self._packed_key.invalidate()
+        if self._packed_key.stale(params):
             pp = _l.ptr_array([p.data_ptr() for p in params])
             _l.check(self.lib.dcpt_nafnet_pack(self.plan, pp, _p(self._packed), _stream()), "nafnet_pack")
-            self._packed_key = key
         return self._packed
+
+    def invalidate_packed(self):
+        """Force a re-pack on the next call (for writers that bypass both torch's version counters and no-grad forwards)."""
+        self._packed_key.invalidate()
 
     @staticmethod
     def alloc_flat_grads(params, align=64):
@@ -108,10 +115,7 @@ class NAFNetEngine:
         if keep_for_backward:
             saved = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         else:  # inference: one reusable arena per shape
-            k = ("saved", N, H, W, dev)
-            if k not in self._scratch:
-                self._scratch[k] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            saved = self._scratch[k]
+            saved = self._scratch.setdefault(("saved", N, H, W, dev), lambda: torch.empty(nbytes, dtype=torch.uint8, device=dev))
         out = None if hook else torch.empty_like(inp)
         feats = fp = None
         if want_feats:
@@ -132,11 +136,8 @@ class NAFNetEngine:
         flat = None
         if grads is None:
             flat, grads = self.alloc_flat_grads(params)
-        k = ("work", N, H, W, dev)
-        if k not in self._scratch:
-            self._scratch[k] = torch.empty(self.lib.dcpt_nafnet_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8,
-                                           device=dev)
-        work = self._scratch[k]
+        work = self._scratch.setdefault(("work", N, H, W, dev), lambda: torch.empty(
+            self.lib.dcpt_nafnet_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev))
         pp = _l.ptr_array([p.data_ptr() for p in params])
         gp = _l.ptr_array([g.data_ptr() for g in grads])
         dfp = None
@@ -204,6 +205,7 @@ class _GraphSlot:
         self.dout = None
         self.dfeats = None
         self.flat = self.grads = None
+        self.work = None     # backward workspace: owned by the slot, so that evicting the slot frees everything its graphs point to
         self.fgraph = None
         self.bgraphs = {}
         self.busy = False
@@ -226,7 +228,13 @@ def _graph_forward(eng, pv, inp, hook, want_feats, need_grad):
     inp = inp.contiguous().float()
     N, _, H, W = inp.shape
     key = (N, H, W, inp.device, bool(hook), bool(want_feats), pv.ptrs)
-    slots = eng._gslots.setdefault(key, [])
+    if not need_grad and key not in eng._gslots:
+        # inference over images of many sizes (validation sets): a shape earns a graph slot (static buffers + a saved-activation
+        # arena + a capture) only when it comes back; the first sighting launches eagerly through the shared scratch arena
+        if eng._seen_nograd.get(key) is None:
+            eng._seen_nograd.put(key, True)
+            return None
+    slots = eng._gslots.setdefault(key, list)
     slot = next((s for s in slots if not s.busy), None)
     if slot is None:
         if len(slots) >= _GraphSlot.MAX_PER_KEY:
@@ -279,10 +287,9 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
         for s_, d in zip(slot.dfeats, dfeats):
             if d is not None:
                 s_.copy_(d)
-    k = ("work", N, H, W, dev)
-    if k not in eng._scratch:
-        eng._scratch[k] = torch.empty(eng.lib.dcpt_nafnet_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
-    work = eng._scratch[k]
+    if slot.work is None:
+        slot.work = torch.empty(eng.lib.dcpt_nafnet_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
+    work = slot.work
     packed = eng.packed_for(params)
     pp, gp = pv.pp, slot.gp
     dfp = None

@@ -141,13 +141,23 @@ class FusedAdam(torch.optim.Optimizer):
             return None
         total_norm = None
         if grad_clip is not None and grad_clip > 0:
-            # clip_grad_norm_ is over every parameter of the model = one job in the normal case (one group, one step count)
-            if len(prepared) > 1:
-                raise _l.DcptError("FusedAdam: grad_clip with several param groups / step counts is not built")
-            plan = prepared[0][1][0]
-            total_norm = torch.empty((), dtype=torch.float32, device=plan.work.device)
-            _l.check(self._lib.dcpt_optim_grad_norm(plan.h, C.c_void_p(plan.work.data_ptr()), C.c_void_p(total_norm.data_ptr()),
-                                                    _stream()), "optim_grad_norm")
+            # clip_grad_norm_ is over every parameter of the optimizer: one job in the normal case (one group, one step count);
+            # with several jobs (param groups, or parameters that got their first gradient later) the per-job norms are
+            # combined on the device, sqrt(sum n_i^2), and handed back to every job before its update
+            dev = prepared[0][1][0].work.device
+            norms = torch.empty(len(prepared), dtype=torch.float32, device=dev)
+            for i, (_, job) in enumerate(prepared):
+                plan = job[0]
+                _l.check(self._lib.dcpt_optim_grad_norm(plan.h, C.c_void_p(plan.work.data_ptr()),
+                                                        C.c_void_p(norms.data_ptr() + 4 * i), _stream()), "optim_grad_norm")
+            if len(prepared) == 1:
+                total_norm = norms[0]
+            else:
+                total_norm = torch.linalg.vector_norm(norms.double()).float()
+                for _, job in prepared:
+                    plan = job[0]
+                    _l.check(self._lib.dcpt_optim_set_norm(plan.h, C.c_void_p(plan.work.data_ptr()),
+                                                           C.c_void_p(total_norm.data_ptr()), _stream()), "optim_set_norm")
         for group, job in prepared:
             plan, step0, step_tensors = job
             b1, b2 = group["betas"]
@@ -157,6 +167,12 @@ class FusedAdam(torch.optim.Optimizer):
                                                float(ema_decay if ema_all is not None else 0.0), _stream()), "optim_step")
             torch._foreach_add_(step_tensors, 1.0)                  # the per-parameter `step` tensors of torch's state layout
             job[1] = step0 + 1
+        # The kernels wrote through raw device pointers: tell torch (and the engines' packed-operand caches, which key on the
+        # version counters) that the parameters and the EMA copies changed, as an in-place torch op would have.
+        touched = [p for group, _ in prepared for p in group["params"] if p.grad is not None]
+        if ema_all is not None:
+            touched += ema_all
+        torch.autograd.graph.increment_version(touched)
         return total_norm
 
 

@@ -14,6 +14,7 @@ import torch
 
 from . import lib as _l
 from .ops import _p, _stream
+from .params import LRUCache, PackedCacheKey
 
 
 class RestormerEngine:
@@ -32,16 +33,17 @@ class RestormerEngine:
         dims = (C.c_int * 4)()
         self.numels = [self.lib.dcpt_restormer_param_shape(self.plan, i, dims) for i in range(self.num_params)]
         self._packed = None
-        self._packed_key = None
-        self._work = {}
+        self._packed_key = PackedCacheKey()
+        self._work = LRUCache()       # eager-path workspaces per shape (graph entries / train slots own theirs)
         # whole-forward CUDA-graph replay (~700 launches per 128x128 tile become one); DCPT_CUDA_GRAPH=0 launches eagerly
         self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0"
-        self._graphs = {}
+        self._graphs = LRUCache()
+        self._seen = LRUCache(cap=64)
         self.grad_sync = None      # set by dcpt_b200.dist.FlatGradDataParallel: callable(flat fp32 gradient buffer)
         # training path: CUDA-graph replay of forward-with-save and of backward (~1900 launches per step otherwise);
         # DCPT_RESTORMER_TRAIN_GRAPH=0 keeps eager launches
         self.use_train_graphs = self.use_graphs and os.getenv("DCPT_RESTORMER_TRAIN_GRAPH", "1") != "0"
-        self._tslots = {}
+        self._tslots = LRUCache(can_evict=lambda slots: not any(s_.busy for s_ in slots))
 
     def __del__(self):
         try:
@@ -61,15 +63,16 @@ class RestormerEngine:
                 raise _l.DcptError("parameters must be contiguous fp32")
 
     def packed_for(self, params):
-        key = tuple((p.data_ptr(), p._version) for p in params)
         if self._packed is None or self._packed.device != params[0].device:
             self._packed = torch.empty(self.lib.dcpt_restormer_packed_bytes(self.plan), dtype=torch.uint8, device=params[0].device)
-            self._packed_key = None
-        if key != self._packed_key:
+            self._packed_key.invalidate()
+        if self._packed_key.stale(params):     # version counters + no-grad weight fingerprint, dcpt_b200/params.py
             pp = _l.ptr_array([p.data_ptr() for p in params])
             _l.check(self.lib.dcpt_restormer_pack(self.plan, pp, _p(self._packed), _stream()), "restormer_pack")
-            self._packed_key = key
         return self._packed
+
+    def invalidate_packed(self):
+        self._packed_key.invalidate()
 
     def forward(self, params, inp, hook=False, want_feats=False):
         """inp fp32 NCHW [N,3,H,W] -> (out or None, feats [decoder_level3, 2, 1] as NHWC fp32 or None)."""
@@ -80,11 +83,14 @@ class RestormerEngine:
         N, _, H, W = inp.shape
         dev = inp.device
         packed = self.packed_for(params)
-        k = (N, H, W, dev)
-        if k not in self._work:
-            self._work[k] = torch.empty(self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
         if self.use_graphs and not torch.cuda.is_current_stream_capturing():
-            return self._graph_forward(params, packed, inp, bool(hook), bool(want_feats))
+            # a shape earns a graph entry (static buffers + workspace + capture) when it comes back; first sighting is eager
+            gkey = (N, H, W, dev, bool(hook), bool(want_feats), tuple(p.data_ptr() for p in params))
+            if gkey in self._graphs or self._seen.get(gkey) is not None:
+                return self._graph_forward(params, packed, inp, bool(hook), bool(want_feats), gkey)
+            self._seen.put(gkey, True)
+        work = self._work.setdefault((N, H, W, dev), lambda: torch.empty(
+            self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev))
         out = None if hook else torch.empty_like(inp)
         feats = fp = None
         if want_feats:
@@ -94,25 +100,25 @@ class RestormerEngine:
                      torch.empty(N, H, W, 2 * d, dtype=torch.float32, device=dev)]
             fp = _l.ptr_array([f.data_ptr() for f in feats])
         pp = _l.ptr_array([p.data_ptr() for p in params])
-        _l.check(self.lib.dcpt_restormer_fwd(self.plan, pp, _p(packed), _p(inp), _p(out), _p(self._work[k]), fp, int(bool(hook)),
+        _l.check(self.lib.dcpt_restormer_fwd(self.plan, pp, _p(packed), _p(inp), _p(out), _p(work), fp, int(bool(hook)),
                                              N, H, W, _stream()), "restormer_fwd")
         return out, feats
 
-    def _graph_forward(self, params, packed, inp, hook, want_feats):
+    def _graph_forward(self, params, packed, inp, hook, want_feats, key):
         N, _, H, W = inp.shape
         dev = inp.device
-        key = (N, H, W, dev, hook, want_feats, tuple(p.data_ptr() for p in params))
         ent = self._graphs.get(key)
         if ent is None:
             d = self.dim
-            ent = {"inp": torch.empty_like(inp), "out": None if hook else torch.empty_like(inp), "feats": None, "graph": None}
+            ent = {"inp": torch.empty_like(inp), "out": None if hook else torch.empty_like(inp), "feats": None, "graph": None,
+                   "work": torch.empty(self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)}
             if want_feats:
                 ent["feats"] = [torch.empty(N, H // 4, W // 4, 4 * d, dtype=torch.float32, device=dev),
                                 torch.empty(N, H // 2, W // 2, 2 * d, dtype=torch.float32, device=dev),
                                 torch.empty(N, H, W, 2 * d, dtype=torch.float32, device=dev)]
-            self._graphs[key] = ent
+            self._graphs.put(key, ent)
         ent["inp"].copy_(inp)
-        work = self._work[(N, H, W, dev)]
+        work = ent["work"]
         pp = _l.ptr_array([p.data_ptr() for p in params])
         fp = _l.ptr_array([f.data_ptr() for f in ent["feats"]]) if ent["feats"] else None
 
@@ -145,15 +151,14 @@ class RestormerEngine:
         N, _, H, W = inp.shape
         dev = inp.device
         packed = self.packed_for(params)
-        k = (N, H, W, dev)
-        if k not in self._work:
-            self._work[k] = torch.empty(self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
+        work = self._work.setdefault((N, H, W, dev), lambda: torch.empty(
+            self.lib.dcpt_restormer_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev))
         saved = torch.empty(self.lib.dcpt_restormer_saved_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
         out = None if hook else torch.empty_like(inp)
         feats = self._feat_buffers(N, H, W, dev) if want_feats else None
         fp = _l.ptr_array([f.data_ptr() for f in feats]) if feats else None
         pp = _l.ptr_array([p.data_ptr() for p in params])
-        _l.check(self.lib.dcpt_restormer_fwd_train(self.plan, pp, _p(packed), _p(inp), _p(out), _p(saved), _p(self._work[k]), fp,
+        _l.check(self.lib.dcpt_restormer_fwd_train(self.plan, pp, _p(packed), _p(inp), _p(out), _p(saved), _p(work), fp,
                                                    int(bool(hook)), N, H, W, _stream()), "restormer_fwd_train")
         return out, feats, saved
 
@@ -168,9 +173,8 @@ class RestormerEngine:
             off += (p.numel() + 63) // 64 * 64
         flat = torch.zeros(off, dtype=torch.float32, device=dev)
         grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
-        k = ("bwd", N, H, W, dev)
-        if k not in self._work:
-            self._work[k] = torch.empty(self.lib.dcpt_restormer_bwd_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev)
+        bwork = self._work.setdefault(("bwd", N, H, W, dev), lambda: torch.empty(
+            self.lib.dcpt_restormer_bwd_workspace_bytes(self.plan, N, H, W), dtype=torch.uint8, device=dev))
         pp = _l.ptr_array([p.data_ptr() for p in params])
         gp = _l.ptr_array([g.data_ptr() for g in grads])
         dout = None if dout is None else dout.contiguous().float()
@@ -181,7 +185,7 @@ class RestormerEngine:
         if dout is None and dfp is None:
             return grads                                  # nothing reached this forward: all-zero gradients
         _l.check(self.lib.dcpt_restormer_bwd(self.plan, pp, _p(self.packed_for(params)), _p(saved), _p(inp), _p(dout), dfp,
-                                             gp, _p(self._work[k]), N, H, W, _stream()), "restormer_bwd")
+                                             gp, _p(bwork), N, H, W, _stream()), "restormer_bwd")
         if self.grad_sync is not None:
             self.grad_sync(flat)
         return grads
@@ -200,6 +204,9 @@ class _TrainSlot:
         self.out = None if hook else torch.empty_like(self.inp)
         self.saved = torch.empty(eng.lib.dcpt_restormer_saved_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
         self.feats = eng._feat_buffers(N, H, W, dev) if want_feats else None
+        # the slot owns the workspaces its captured graphs point to: evicting the slot (LRU) frees everything together
+        self.work = torch.empty(eng.lib.dcpt_restormer_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
+        self.bwork = None
         self.dout = self.dfeats = self.flat = self.shapes = self.gp = None
         self.graphs = {}            # "fwd" / backward mask -> captured graph
         self.busy = False
@@ -242,7 +249,7 @@ def _train_graph_forward(eng, params, inp, hook, want_feats):
     N, _, H, W = inp.shape
     dev = inp.device
     key = (N, H, W, dev, hook, want_feats, tuple(p.data_ptr() for p in params))
-    slots = eng._tslots.setdefault(key, [])
+    slots = eng._tslots.setdefault(key, list)
     slot = next((s_ for s_ in slots if not s_.busy), None)
     if slot is None:
         if len(slots) >= _TrainSlot.MAX_PER_KEY:
@@ -250,10 +257,7 @@ def _train_graph_forward(eng, params, inp, hook, want_feats):
         slot = _TrainSlot(eng, N, H, W, dev, hook, want_feats)
         slots.append(slot)
     packed = eng.packed_for(params)                       # re-packed eagerly when a parameter changed; static address
-    k = (N, H, W, dev)
-    if k not in eng._work:
-        eng._work[k] = torch.empty(eng.lib.dcpt_restormer_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
-    work = eng._work[k]
+    work = slot.work
     slot.inp.copy_(inp)
     pp = _l.ptr_array([p.data_ptr() for p in params])
     fp = _l.ptr_array([f.data_ptr() for f in slot.feats]) if slot.feats else None
@@ -295,10 +299,9 @@ def _train_graph_backward(eng, params, slot, dout, dfeats):
         slot.release()
         flat = torch.zeros_like(slot.flat)                 # nothing reached this forward: all-zero gradients
         return [flat[o:o + n].view(shp) for o, n, shp in slot.shapes]
-    k = ("bwd", N, H, W, dev)
-    if k not in eng._work:
-        eng._work[k] = torch.empty(eng.lib.dcpt_restormer_bwd_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
-    work = eng._work[k]
+    if slot.bwork is None:
+        slot.bwork = torch.empty(eng.lib.dcpt_restormer_bwd_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
+    work = slot.bwork
     packed = eng.packed_for(params)
     pp = _l.ptr_array([p.data_ptr() for p in params])
     dfp = _l.ptr_array([s_.data_ptr() if m else 0 for s_, m in zip(slot.dfeats, mask[1])]) if has_df else None

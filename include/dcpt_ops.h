@@ -322,7 +322,13 @@ int dcpt_restormer_bwd(const dcpt_restormer_plan* plan, const float* const* host
  *                              (decoupled_weight_decay == 0: g' += wd * p) or AdamW (p *= 1 - lr * wd) update in torch's
  *                              operation order with bias corrections for `step` (the 1-based count of this update), then,
  *                              when ema_decay > 0 and an ema pointer was bound, ema = ema * decay + (1 - decay) * p.
- *                              amsgrad / maximize are not supported. */
+ *                              amsgrad / maximize are not supported.
+ *   dcpt_optim_set_norm        overrides the workspace's total_norm with *total_norm (DEVICE pointer): clip_grad_norm_ over
+ *                              SEVERAL plans (param groups / step counts) = sqrt(sum of the per-plan norms squared), which
+ *                              the caller combines and hands to each plan before its dcpt_optim_step.
+ *   dcpt_optim_param_hash      *hash (DEVICE u64) = order-independent fingerprint of the bound PARAMETER tensors' bits; lets the
+ *                              host notice writes that bypass torch's version counter (BaseModel.model_ema's
+ *                              `ema.data.mul_().add_()`, base_model.py:86-95) before re-using a packed bf16 operand cache. */
 typedef struct dcpt_optim_plan dcpt_optim_plan;
 dcpt_optim_plan* dcpt_optim_create(const long long* host_numels, int n_tensors);
 void dcpt_optim_destroy(dcpt_optim_plan* plan);
@@ -331,6 +337,8 @@ long long dcpt_optim_num_chunks(const dcpt_optim_plan* plan);
 int dcpt_optim_bind(const dcpt_optim_plan* plan, void* workspace, float* const* host_params, const float* const* host_grads,
                     float* const* host_exp_avg, float* const* host_exp_avg_sq, float* const* host_ema, dcpt_stream_t stream);
 int dcpt_optim_grad_norm(const dcpt_optim_plan* plan, void* workspace, float* total_norm, dcpt_stream_t stream);
+int dcpt_optim_set_norm(const dcpt_optim_plan* plan, void* workspace, const float* total_norm, dcpt_stream_t stream);
+int dcpt_optim_param_hash(const dcpt_optim_plan* plan, void* workspace, unsigned long long* hash, dcpt_stream_t stream);
 int dcpt_optim_step(const dcpt_optim_plan* plan, void* workspace, int decoupled_weight_decay, double lr, double beta1, double beta2,
                     double eps, double weight_decay, long long step, double max_norm, double ema_decay, dcpt_stream_t stream);
 

@@ -169,3 +169,103 @@ def test_full_size_nafnet_w64_update():
     o3.step()
     assert all(torch.equal(p, q) for p, q in zip(params, p0))                 # lr = 0: no decay, no step
     assert all(float(o3.state[p]["exp_avg"].flatten()[0]) > 0 for p in params[:5])
+
+
+def _small_net(seed=0):
+    from basicsr.archs import build_network
+    from oracle import nafnet_oracle as O
+    cfg = dict(width=16, enc_blk_nums=[1, 1], middle_blk_num=1, dec_blk_nums=[1, 1])
+    sd = O.random_nafnet_state_dict(seed=seed, **cfg)
+    net = build_network(dict(type="NAFNetBaseline", window_size=16, **cfg)).cuda()
+    net.load_state_dict(sd, strict=True)
+    return net, cfg
+
+
+def _oracle_out(net, cfg, inp):
+    from oracle import nafnet_oracle as O
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    return O.nafnet_fwd(inp, sd, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"])
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def test_forward_after_fused_step_uses_updated_weights():
+    """FusedAdam writes the parameters through raw pointers; the engines' packed bf16 operand cache must be
+    rebuilt for the next forward (optim.py bumps the version counters).  forward -> FusedAdam.step -> forward, each forward
+    against the oracle run on the weights the module holds at that moment."""
+    from dcpt_b200.optim import FusedAdamW
+    net, cfg = _small_net()
+    g = torch.Generator().manual_seed(3)
+    inp, gt = torch.rand(2, 3, 32, 32, generator=g), torch.rand(2, 3, 32, 32, generator=g)
+    opt = FusedAdamW(net.parameters(), lr=5e-2, betas=(0.9, 0.9), weight_decay=0.0)   # a large step: stale weights would show
+    out0 = net(inp.cuda())
+    ref0 = _oracle_out(net, cfg, inp)
+    assert _rel(out0, ref0) < 2e-3
+    ((out0 - gt.cuda()) ** 2).mean().backward()
+    opt.step()
+    out1 = net(inp.cuda())
+    ref1 = _oracle_out(net, cfg, inp)
+    moved = _rel(ref1, ref0)
+    e1 = _rel(out1, ref1)
+    print(f"update moved the output by {moved:.2e}; forward after the step vs oracle with the updated weights: {e1:.2e}")
+    assert moved > 2e-2, "the test's update is too small to detect stale packed weights"
+    assert e1 < 2e-3
+    # and the backward of that second forward uses the fresh weights as well (dgrad operands are packed too)
+    net.zero_grad()
+    ((out1 - gt.cuda()) ** 2).mean().backward()
+    from oracle import nafnet_oracle as O
+    leaves = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    ro = O.nafnet_fwd(inp, leaves, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"])
+    ((ro - gt) ** 2).mean().backward()
+    errs = sorted(_rel(p.grad, leaves[k].grad) for k, p in net.named_parameters())
+    assert errs[len(errs) // 2] < 1.5e-2, errs[len(errs) // 2]
+
+
+def test_no_grad_forward_sees_data_writes():
+    """The reference's model_ema (base_model.py:86-95) writes `ema.data.mul_(decay).add_(p.data, alpha=1-decay)`, which bumps no
+    version counter; net_g_ema is then run under no_grad (sr_model.py:176-185).  The no-grad weight fingerprint
+    (dcpt_b200/params.py) must catch it."""
+    ema_net, cfg = _small_net(seed=0)
+    src_net, _ = _small_net(seed=1)
+    g = torch.Generator().manual_seed(4)
+    inp = torch.rand(1, 3, 32, 32, generator=g)
+    with torch.no_grad():
+        out0 = ema_net(inp.cuda())
+    ref0 = _oracle_out(ema_net, cfg, inp)
+    assert _rel(out0, ref0) < 2e-3
+    versions = [p._version for p in ema_net.parameters()]
+    for e, p in zip(ema_net.parameters(), src_net.parameters()):
+        e.data.mul_(0.5).add_(p.data, alpha=0.5)                    # model_ema with decay 0.5
+    assert versions == [p._version for p in ema_net.parameters()]   # the premise: torch did not notice
+    with torch.no_grad():
+        out1 = ema_net(inp.cuda())
+    ref1 = _oracle_out(ema_net, cfg, inp)
+    assert _rel(ref1, ref0) > 2e-2
+    assert _rel(out1, ref1) < 2e-3
+
+
+def test_grad_clip_over_several_param_groups():
+    """clip_grad_norm_ over every parameter when the optimizer has several jobs (two param groups here): the per-plan norms
+    are combined on the device."""
+    from dcpt_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(5)
+    shapes = [(300,), (17, 9), (4096,), (33,)]
+    P = [torch.randn(s, generator=g) for s in shapes]
+    G = [torch.randn(s, generator=g) for s in shapes]
+    net = [torch.nn.Parameter(p.clone().cuda()) for p in P]
+    for p, gg in zip(net, G):
+        p.grad = gg.clone().cuda()
+    opt = FusedAdam([{"params": net[:2], "lr": 1e-2}, {"params": net[2:], "lr": 3e-2}], betas=(0.9, 0.99))
+    n = float(opt.step(grad_clip=0.5))
+    ref = [torch.nn.Parameter(p.clone()) for p in P]
+    for p, gg in zip(ref, G):
+        p.grad = gg.clone()
+    ropt = torch.optim.Adam([{"params": ref[:2], "lr": 1e-2}, {"params": ref[2:], "lr": 3e-2}], betas=(0.9, 0.99))
+    rn = float(torch.nn.utils.clip_grad_norm_(ref, 0.5))
+    ropt.step()
+    assert abs(n - rn) < 2e-6 * rn
+    for a, b in zip(net, ref):
+        assert err(a, b.detach().numpy()) < TOL

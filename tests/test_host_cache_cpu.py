@@ -1,0 +1,37 @@
+"""Host-side cache logic (dcpt_b200/params.py): no GPU, no compute calls."""
+import torch
+
+from dcpt_b200.params import LRUCache, PackedCacheKey
+
+
+def test_lru_evicts_oldest_but_never_busy_entries():
+    class Slot:
+        def __init__(self, busy):
+            self.busy = busy
+    c = LRUCache(cap=2, can_evict=lambda slots: not any(s.busy for s in slots))
+    c.put("a", [Slot(True)])
+    c.put("b", [Slot(False)])
+    c.put("c", [Slot(False)])          # over capacity: "a" is oldest but busy -> "b" goes
+    assert "a" in c and "c" in c and "b" not in c
+    c.get("a")                         # refresh "a"
+    c.d["a"][0].busy = False
+    c.put("d", [])
+    assert "c" not in c and "a" in c and "d" in c and len(c) == 2
+    assert c.setdefault("a", list) is c.get("a")
+
+
+def test_packed_cache_key_tracks_versions_and_storage():
+    p = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.ones(3))]
+    d = [q.detach() for q in p]
+    k = PackedCacheKey()
+    assert k.stale(d)                  # first use: pack
+    assert not k.stale(d)
+    with torch.no_grad():
+        p[1].add_(1.0)                 # an in-place torch write bumps the shared version counter
+    assert k.stale(d) and not k.stale(d)
+    torch.autograd.graph.increment_version(p)   # what FusedAdam.step does after its raw-pointer update
+    assert k.stale(d) and not k.stale(d)
+    p[0].data = torch.zeros(4)         # re-allocated storage (.to(), load with assign)
+    assert k.stale([q.detach() for q in p])
+    k.invalidate()
+    assert k.stale([q.detach() for q in p])
