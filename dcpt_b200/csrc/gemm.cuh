@@ -44,7 +44,19 @@ struct EpiParams {
   int ldgaux;
   int rows_per_img;
   long long out_batch_stride;  // ATOMIC with GemmArgs::k_per_batch: element offset of out_f32 between batches
+  // Fused channel LayerNorm of the OUTPUT rows (STORE, TMA-tiled epilogue, N <= 512 so that a CTA holds whole rows in TMEM):
+  // with v = acc + bias + resid the row being written to out_f32, also ln_out[m, :] = bf16((v - mean) * rstd * ln_w + ln_b) and
+  // ln_stats[m] = (mean, rstd) - the LayerNorm2d forward of the CONSUMER of this tensor (nafnet_arch.py:27-35: norm2 after
+  // conv3's residual add, norm1 of the next block after conv5's), which otherwise re-reads the fp32 rows in its own launch.
+  const float* ln_w;
+  const float* ln_b;
+  bf16* ln_out;
+  int ld_ln;
+  float* ln_stats;
+  float ln_eps;
 };
+// true when gemm_tc_launch can fuse the LayerNorm of the output rows for this N (else the caller runs ln_fwd_launch)
+inline bool gemm_ln_fusable(int N) { return N >= 8 && N % 8 == 0 && N <= 512; }
 
 struct GemmArgs {
   int M, N, K;

@@ -51,6 +51,10 @@ struct EpiMaps {
   // EPI_STORE_TMA: fp32 output, bf16 output, fp32 residual.  EPI_GATE_BWD_TMA: o16 = d(x4), r32 = x4 (bf16 [M, 2C]).
   // EPI_GATE_TMA: o16 = x4 (bf16 [M, 2C]), o2 = sg (bf16 [M, C]).  Unused by the register-staged epilogues.
   CUtensorMap o32, o16, r32, o2;
+  // bf16 outputs written as 64-column boxes (128-byte rows, 128B swizzle).  A TMA store costs ~5 cycles per box ROW whatever
+  // its width (r02c/r02d traces: 2 KiB boxes of 64-byte rows drained at ~11 B/clk per SM), so narrow rows halve the store rate.
+  CUtensorMap o16w;  // EPI_STORE_TMA, bf16-only output
+  CUtensorMap ln;    // EPI_STORE_TMA with a fused LayerNorm of the output rows: normalised bf16 output [M, N]
 };
 
 constexpr int BM = 128;
@@ -68,7 +72,9 @@ struct Cfg {
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two >= 32)
   static constexpr uint32_t EPI_BYTES = 8 * (TMA_EPI ? 8192 : 4096);  // starts 1024-byte aligned (STAGE_BYTES % 1024 == 0)
-  static constexpr uint32_t COLSUM_BYTES = EPI == EPI_GATE_BWD_TMA ? 8192 : 0;  // per-CTA column sums of d(x4): 2C <= 2048 floats
+  // EPI_GATE_BWD_TMA: per-CTA column sums of d(x4) (2C <= 2048 floats); EPI_STORE_TMA: row-statistics exchange of the fused
+  // LayerNorm (2 slab parities x 8 warps x 32 lanes x float4)
+  static constexpr uint32_t COLSUM_BYTES = EPI == EPI_GATE_BWD_TMA ? 8192 : (EPI == EPI_STORE_TMA ? 8192 : 0);
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 512 /*barriers*/ + COLSUM_BYTES;
 };
 
@@ -113,7 +119,8 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 template <int BN, int EPI, bool A_MN, bool B_MN, int CONV>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ EpiMaps em,
-               int M, int N, int K, int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep, ConvGeom cg, BatchGeom bg) {
+               int M, int N, int K, int tiles_m, int tiles_n, int splits, int kb_per_split, EpiParams ep, ConvGeom cg, BatchGeom bg,
+               int pf_mode) {
   using C = Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   if (threadIdx.x == 0) TRACE(0);
@@ -138,6 +145,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int num_kb = (K + BK - 1) / BK;
   const int total_tiles = tiles_m * tiles_n * splits;
+  // Tile schedule: tile t = (split, m_t, n_t) round-robin over the CTAs; with a fused LayerNorm over rows wider than one tile
+  // (N = 512) a CTA takes whole 128-row SLABS: its tiles_n (= 2) tiles of a slab back to back, one per accumulator buffer.
+  bool slab_mode = false;
+  if constexpr (EPI == EPI_STORE_TMA) slab_mode = ep.ln_out != nullptr && tiles_n > 1;
+  auto tile_of = [&](int it) -> int {
+    if (slab_mode) {
+      const int slab = (int)blockIdx.x + (it / tiles_n) * (int)gridDim.x;
+      return slab < tiles_m ? slab * tiles_n + it % tiles_n : -1;
+    }
+    const int t = (int)blockIdx.x + it * (int)gridDim.x;
+    return t < total_tiles ? t : -1;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -156,6 +175,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&em.o16);
       tma_prefetch_desc(&em.r32);
       tma_prefetch_desc(&em.o2);
+      if constexpr (EPI == EPI_STORE_TMA) {
+        tma_prefetch_desc(&em.ln);
+        tma_prefetch_desc(&em.o16w);
+      }
     }
     fence_mbar_init();
   }
@@ -187,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int c = 0; c < BN / 64; ++c) tma_prefetch_2d(&tmB, n_t * BN + c * 64, pk * BK);
         }
       };
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
         const int n_t = tile % tiles_n;
         const int m_t = (tile / tiles_n) % tiles_m;
         const int sp = tile / (tiles_n * tiles_m);
@@ -202,10 +225,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // L2 prefetch of the HBM-streamed operand(s), PF_DIST k-blocks ahead of the smem ring (which can hold
           // only STAGES blocks in flight: not enough to cover DRAM latency for a short-K tile).
           if constexpr (CONV == 0) {
-            if (kb == kb0) {
-              for (int pk = kb0; pk < min(kb1, kb0 + PF_DIST); ++pk) prefetch_kb(pk, m_t, n_t);
-            } else if (kb + PF_DIST - 1 < kb1) {
-              prefetch_kb(kb + PF_DIST - 1, m_t, n_t);
+            if (pf_mode == 1) {
+              if (kb == kb0) {
+                for (int pk = kb0; pk < min(kb1, kb0 + PF_DIST); ++pk) prefetch_kb(pk, m_t, n_t);
+              } else if (kb + PF_DIST - 1 < kb1) {
+                prefetch_kb(kb + PF_DIST - 1, m_t, n_t);
+              }
             }
           }
           mbar_wait(&empty[stage], phase ^ 1);
@@ -245,6 +270,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, &tmB, &full[stage], n_t * BN + c * 64, kb * BK);
             }
           }
+          if constexpr (CONV == 0) {
+            if (pf_mode == 2) {  // prefetch behind the real loads: the first operands of a tile never queue behind a prefetch burst
+              if (kb == kb0) {
+                for (int pk = kb0 + C::STAGES; pk < min(kb1, kb0 + PF_DIST); ++pk) prefetch_kb(pk, m_t, n_t);
+              } else if (kb + PF_DIST - 1 < kb1 && kb + PF_DIST - 1 >= kb0 + C::STAGES) {
+                prefetch_kb(kb + PF_DIST - 1, m_t, n_t);
+              }
+            }
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -260,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
         const int sp = tile / (tiles_n * tiles_m);
         int kb0 = sp * kb_per_split;
         int kb1 = min(num_kb, kb0 + kb_per_split);
@@ -274,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
-          if (tile == blockIdx.x && kb == kb0) TRACE(2);
+          if (it == 0 && kb == kb0) TRACE(2);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * C::B_STAGE_BYTES);
@@ -293,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         umma_commit(&tfull[acc]);  // accumulator ready for the epilogue
-        TRACE(tile == blockIdx.x ? 3 : 4);
+        TRACE(it == 0 ? 3 : 4);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -358,7 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---- SimpleGate forward on 32-wide pair packing: accumulator chunks (2p, 2p + 1) = (a, b) halves of channels
         // [32p, 32p + 32): x4[:, 32p..] = a, x4[:, C + 32p..] = b, sg[:, 32p..] = a * b (all bf16, rounded before the product
         // like the register-staged epilogue).  A warp takes alternate chunk PAIRS; three 2 KiB tiles per pair.
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
           const int n_t = tile % tiles_n;
           const int m_t = (tile / tiles_n) % tiles_m;
           const int m0 = m_t * BM + q * 32;
@@ -414,12 +448,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             acc_phase ^= 1;
           }
         }
-      } else
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      } else {
+      // fused LayerNorm of the output rows (ep.ln_out): per-lane (= per row) shifted sums over this warp's chunks
+      bool ln_on = false, wide16 = false;
+      if constexpr (EPI == EPI_STORE_TMA) {
+        ln_on = ep.ln_out != nullptr;
+        wide16 = ep.out_bf16 != nullptr && ep.out_f32 == nullptr && !has_r && ep.Cseg == 0 && !ln_on;
+      }
+      float ln_k = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;
+      int ln_n = 0, ln_par = 0;
+      for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
         const int n_t = tile % tiles_n;
         const int m_t = (tile / tiles_n) % tiles_m;
         const int m0 = m_t * BM + q * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        if constexpr (EPI == EPI_STORE_TMA) {
+          if (wide16) {
+            // ---- bf16-only output (conv1, the conv4 / conv1 dgrads, ...): a warp takes alternate 64-column chunk PAIRS and
+            // writes each as ONE 4 KiB box of 128-byte rows; two stores in flight ----
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int pr = chalf; pr < BN / 64; pr += 2) {
+              const int n0 = n_t * BN + pr * 64;
+              if (n0 >= N) break;  // warp-uniform
+              float va[32], vb[32];
+              tmem_ld32(taddr + pr * 64, va);
+              tmem_ld32(taddr + pr * 64 + 32, vb);
+              const int b = ci & 1;
+              if (lane == 0) bulk_wait_read<1>();  // the store that read buffer b two pairs ago has drained it
+              __syncwarp();
+              tmem_ld_wait();
+              if (ep.bias) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (n0 + 4 * j < N) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+                    va[4 * j] += bv.x; va[4 * j + 1] += bv.y; va[4 * j + 2] += bv.z; va[4 * j + 3] += bv.w;
+                  }
+                  if (n0 + 32 + 4 * j < N) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + 32) + j);
+                    vb[4 * j] += bv.x; vb[4 * j + 1] += bv.y; vb[4 * j + 2] += bv.z; vb[4 * j + 3] += bv.w;
+                  }
+                }
+              }
+              const uint32_t buf = smem_u32(ebuf + b * 4096);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float t8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t8[k] = va[8 * j + k];
+                sts_u4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), pack8(t8));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t8[k] = vb[8 * j + k];
+                sts_u4(buf + (uint32_t)(lane * 128 + (((4 + j) ^ (lane & 7)) << 4)), pack8(t8));
+              }
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&em.o16w, ebuf + b * 4096, n0, m0);
+                bulk_commit();
+              }
+              ++ci;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (ew == 0 && lane == 0) TRACE(it == 0 ? 6 : 8);
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1;
+            }
+            continue;
+          }
+        }
         bool first = true;
 #pragma unroll 1
         for (int c = chalf; c < BN / 32; c += 2) {
@@ -432,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (has_r) issue_in(ebuf + b * 4096, &rf[b], n0, m0);
             }
             mbar_wait(&tfull[acc], acc_phase);
-            if (ew == 0 && lane == 0) TRACE(tile == blockIdx.x ? 5 : 7);
+            if (ew == 0 && lane == 0) TRACE(it == 0 ? 5 : 7);
             tc_fence_after();
             first = false;
           }
@@ -496,10 +598,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (has_r && !has_g) {
+            float4 r[8];  // all eight loads in flight before the first use (the asm loads keep program order)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = lds_f4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)));
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 r = lds_f4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)));
-              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+              v[4 * j] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w;
+            }
+          }
+          if constexpr (EPI == EPI_STORE_TMA) {
+            if (ln_on) {  // v = the finished output row piece: statistics, and back into the accumulator columns for pass 2
+              const int nv = min(32, N - n0);
+              if (ln_n == 0) ln_k = v[0];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < nv) {
+                  const float d = v[j] - ln_k;
+                  ln_s1 += d;
+                  ln_s2 = fmaf(d, d, ln_s2);
+                }
+              }
+              ln_n += nv;
+              tmem_st32(taddr + c * 32, v);
             }
           }
           if (ep.out_f32) {
@@ -550,19 +670,118 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&tfull[acc], acc_phase);
           tc_fence_after();
         }
+        if constexpr (EPI == EPI_STORE_TMA) {
+          if (ln_on) {
+            if (n_t == tiles_n - 1) {
+              // ---- the CTA now holds the whole rows of this slab in TMEM: finish the statistics, normalise, store ----
+              tmem_st_wait();
+              if (ew == 0 && lane == 0) TRACE(11);
+              const float na = (float)ln_n;
+              const float mean_a = ln_n ? ln_k + ln_s1 / na : 0.f;
+              const float m2_a = ln_n ? fmaxf(ln_s2 - ln_s1 * ln_s1 / na, 0.f) : 0.f;
+              float4* xch = reinterpret_cast<float4*>(s_colsum) + ln_par * 256;  // [2 parities][8 warps][32 lanes]
+              xch[ew * 32 + lane] = make_float4(na, mean_a, m2_a, 0.f);
+              tc_fence_before();
+              named_bar_sync(1 + q, 64);  // the two warps of this lane quarter
+              tc_fence_after();
+              const float4 pb = xch[(ew ^ 4) * 32 + lane];
+              if (ew == 0 && lane == 0) TRACE(12);
+              ln_par ^= 1;
+              const float nt = na + pb.x;
+              const float mean = (na * mean_a + pb.x * pb.y) / nt;  // Chan et al. merge of the two column halves
+              const float dm = pb.y - mean_a;
+              const float var = ((m2_a + pb.z) + dm * dm * (na * pb.x / nt)) / nt;
+              const float rstd = 1.f / sqrtf(var + ep.ln_eps);
+              if (chalf == 0 && m0 + lane < M) *reinterpret_cast<float2*>(ep.ln_stats + (size_t)(m0 + lane) * 2) = make_float2(mean, rstd);
+              if (lane == 0) bulk_wait_read<0>();  // pass 1's stores have drained the staging buffers pass 2 re-partitions
+              __syncwarp();
+              ci = 0;
+              // pass 2: 64-column pairs (a pair straddles the two partner warps' pass-1 chunks: their TMEM write-backs are
+              // ordered by the fences around the named barrier above), one 4 KiB box of 128-byte rows per store
+              for (int h = 0; h < tiles_n; ++h) {
+                const int hacc = tiles_n > 1 ? h : acc;
+                const uint32_t th = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hacc * BN);
+#pragma unroll 1
+                for (int pr = chalf; pr < BN / 64; pr += 2) {
+                  const int n0 = h * BN + pr * 64;
+                  if (n0 >= N) break;
+                  float va[32], vb[32];
+                  tmem_ld32(th + pr * 64, va);
+                  tmem_ld32(th + pr * 64 + 32, vb);
+                  const int b = ci & 1;
+                  if (lane == 0) bulk_wait_read<1>();  // the store that read buffer b two pairs ago has drained it
+                  __syncwarp();
+                  tmem_ld_wait();
+                  const uint32_t buf = smem_u32(ebuf + b * 4096);
+                  // all 32 parameter loads of the pair are issued before the first shared-memory store: the stores are
+                  // volatile asm, and a load placed after one waits for it (r02e: 2700 cycles per pair interleaved)
+                  uint4 pk[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k += 4) {
+                      const int col = n0 + 8 * j + k;
+                      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), bv = wv;
+                      if (col < N) {
+                        wv = __ldg(reinterpret_cast<const float4*>(ep.ln_w + col));
+                        bv = __ldg(reinterpret_cast<const float4*>(ep.ln_b + col));
+                      }
+                      const float* src = j < 4 ? &va[8 * j + k] : &vb[8 * (j - 4) + k];
+                      o[k] = (src[0] - mean) * rstd * wv.x + bv.x;
+                      o[k + 1] = (src[1] - mean) * rstd * wv.y + bv.y;
+                      o[k + 2] = (src[2] - mean) * rstd * wv.z + bv.z;
+                      o[k + 3] = (src[3] - mean) * rstd * wv.w + bv.w;
+                    }
+                    pk[j] = pack8(o);
+                  }
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) sts_u4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), pk[j]);
+                  fence_async_smem();
+                  __syncwarp();
+                  if (lane == 0) {
+                    tma_store_2d(&em.ln, ebuf + b * 4096, n0, m0);
+                    bulk_commit();
+                  }
+                  ++ci;
+                }
+              }
+              // (pass 1 of the next tile starts with bulk_wait_read<0>, so any ci parity is fine there)
+              ln_k = ln_s1 = ln_s2 = 0.f;
+              ln_n = 0;
+              if (ew == 0 && lane == 0) TRACE(13);
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (tiles_n > 1) {
+                  mbar_arrive(&tempty[0]);
+                  mbar_arrive(&tempty[1]);
+                } else {
+                  mbar_arrive(&tempty[acc]);
+                }
+              }
+            }
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1;
+            }
+            continue;
+          }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
-        if (ew == 0 && lane == 0) TRACE(tile == blockIdx.x ? 6 : 8);
+        if (ew == 0 && lane == 0) TRACE(it == 0 ? 6 : 8);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
+      }
       if (lane == 0) bulk_wait_all();
       if (ew == 0 && lane == 0) TRACE(9);
     } else
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
       const int n_t = tile % tiles_n;
       const int m_t = (tile / tiles_n) % tiles_m;
       const int m_base = m_t * BM + q * 32;
@@ -808,6 +1027,17 @@ int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int CH
 
 namespace {
 
+// L2 prefetch policy of the TMA producer (DCPT_GEMM_PF): 0 none, 1 a burst of PF_DIST k-blocks before the first load of a tile,
+// 2 the same distance but issued behind the real loads
+int gemm_pf_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DCPT_GEMM_PF");
+    mode = e ? atoi(e) : 0;  // r02b: 47.8 (none) vs 45.9 (burst) vs 46.4 (behind the loads) MPix/s
+  }
+  return mode;
+}
+
 template <int BN, int EPI, bool A_MN, bool B_MN>
 int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   const ConvGeom cg0 = {};
@@ -827,6 +1057,16 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     if (g.ep.resid) DCPT_TRY(make_tmap_epi(&em.r32, g.ep.resid, g.M, g.N, g.ep.ldr, 4));
     }
     if (g.ep.gaux) DCPT_TRY(make_tmap_epi(&em.o2, g.ep.gaux, g.M, g.N, g.ep.ldgaux, 2));
+    if (g.ep.ln_out) {
+      DCPT_CHECK_ARG(g.ep.Cseg == 0 && !g.ep.gaux && g.N <= 2 * BN && g.ep.ln_w && g.ep.ln_b && g.ep.ln_stats && g.m_per_batch == 0 &&
+                         ((reinterpret_cast<uintptr_t>(g.ep.ln_w) | reinterpret_cast<uintptr_t>(g.ep.ln_b)) & 15) == 0,
+                     DCPT_E_ARG, "gemm: fused LayerNorm needs a plain STORE epilogue with N <= %d and 16-byte aligned ln_w / ln_b (N=%d)",
+                     2 * BN, g.N);
+      DCPT_CHECK_ARG(g.ep.ld_ln % 8 == 0, DCPT_E_ALIGN, "gemm: ld_ln=%d must be a multiple of 8", g.ep.ld_ln);
+      DCPT_TRY(make_tmap_2d(&em.ln, g.ep.ln_out, g.M, g.N, g.ep.ld_ln, 32));  // 64-column x 32-row boxes, 128B swizzle
+    }
+    if (g.ep.out_bf16 && !g.ep.out_f32 && g.ep.Cseg == 0 && g.ep.ldo % 8 == 0)
+      DCPT_TRY(make_tmap_2d(&em.o16w, g.ep.out_bf16, g.M, g.N, g.ep.ldo, 32));
   } else if constexpr (EPI == EPI_GATE_BWD_TMA) {
     DCPT_TRY(make_tmap_epi(&em.r32, g.ep.aux, g.M, 2 * g.ep.C, g.ep.ldaux, 2));
     DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, 2 * g.ep.C, g.ep.ldo, 2));
@@ -864,7 +1104,8 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     bg.b_rows_per_batch = g.b_rows_per_batch;
   }
   const int total = tiles_m * tiles_n * splits;
-  const int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
+  int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
+  if (EPI == EPI_STORE_TMA && g.ep.ln_out && tiles_n > 1) grid = tiles_m < dcpt_num_sms() ? tiles_m : dcpt_num_sms();  // whole slabs per CTA
 
   auto kern = gemm_tc_kernel<BN, EPI, A_MN, B_MN, 0>;
   static bool attr_set = false;  // per template instantiation
@@ -888,7 +1129,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
                                                 (EPI == EPI_GATE_BWD || EPI == EPI_GATE_BWD_TMA ? 4.0 : 0.0));
   DCPT_PROF(tag, 2.0 * g.M * g.N * g.K, 2.0 * ((double)g.M * g.K + (double)g.N * g.K) + out_bytes, stream);
   DCPT_CUDA(dcpt_launch_pdl(kern, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, em, g.M, g.N, g.K, tiles_m, tiles_n, splits,
-                            kbps, g.ep, cg0, bg));
+                            kbps, g.ep, cg0, bg, gemm_pf_mode()));
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -934,7 +1175,7 @@ int conv_fwd_cfg(const Conv3x3Args& a, cudaStream_t stream) {
   const double Mpx = (double)a.N * a.H * a.W;
   DCPT_PROF(BN == 256 ? "conv3x3_tc<256>" : (BN == 128 ? "conv3x3_tc<128>" : "conv3x3_tc<64>"), 2.0 * Mpx * a.Cout * 9 * a.Cin,
             2.0 * Mpx * (a.Cin + a.Cout), stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, a.N * a.H * a.W, a.Cout, num_kb * BK, tiles_m, tiles_n, 1, num_kb, a.ep, cg, BatchGeom{});
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, a.N * a.H * a.W, a.Cout, num_kb * BK, tiles_m, tiles_n, 1, num_kb, a.ep, cg, BatchGeom{}, 0);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -966,7 +1207,7 @@ int conv_wgrad_cfg(const bf16* dY, const bf16* X, float* G, int N, int H, int W,
   }
   const double Mpx = (double)N * H * W;
   DCPT_PROF("conv3x3_wgrad_tc", 2.0 * Mpx * Cout * 9 * Cin, 2.0 * Mpx * (Cin + Cout), stream);
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, Cout, 9 * cin_pad, num_kb * BK, tiles_m, tiles_n, splits, kbps, ep, cg, BatchGeom{});
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, em, Cout, 9 * cin_pad, num_kb * BK, tiles_m, tiles_n, splits, kbps, ep, cg, BatchGeom{}, 0);
   DCPT_LAUNCH_CHECK();
   return 0;
 }
@@ -1015,6 +1256,8 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
       const bool want_g = g.ep.gaux != nullptr && g.ep.colsum != nullptr;
       const bool fuse_g = want_g && tma && !g.ep.resid && !g.ep.out_f32 && g.ep.out_bf16 && g.ep.rows_per_img > 0 &&
                           g.ep.rows_per_img % 32 == 0 && ok(g.ep.gaux, g.ep.ldgaux, 2);
+      DCPT_CHECK_ARG(g.ep.ln_out == nullptr || (tma && gemm_ln_fusable(g.N) && g.ep.out_f32), DCPT_E_ARG,
+                     "gemm: fused LayerNorm needs the TMA-tiled fp32 STORE epilogue and N <= 512 (N=%d)", g.N);
       GemmArgs gg = g;
       gg.ep.Cseg = 0;  // PixelShuffle addressing belongs to EPI_PIXSHUF only
       if (!fuse_g) gg.ep.gaux = nullptr;

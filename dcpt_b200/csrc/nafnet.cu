@@ -125,6 +125,21 @@ struct BlockSaved {
   }
 };
 
+// Accumulators a block backward adds into (split-K wgrad scratch for conv5 / conv3, column sums, the SCA ds): they must
+// start at zero.  The network backward hands every block its own slice of ONE region cleared by ONE memset per pass
+// (6 memset nodes per block on the captured graph otherwise); zeros == nullptr: the block clears wk's own buffers itself.
+struct BlockZeros {
+  float *G5, *G3, *Sy, *ds;
+  static size_t floats(int N, int C) { return 2 * ((size_t)C * C + 64) + (size_t)C + 64 + (size_t)N * C + 64; }
+  BlockZeros(float* base, int N, int C) {
+    auto up = [](size_t v) { return (v + 63) / 64 * 64; };
+    G5 = base; base += up((size_t)C * C);
+    G3 = base; base += up((size_t)C * C);
+    Sy = base; base += up((size_t)C);
+    ds = base;
+  }
+};
+
 struct BlockWork {
   float *G, *dy, *Sy, *ds, *t;
   bf16 *dx4, *dn, *dyT, *dgs, *du2, *du;
@@ -176,19 +191,47 @@ int nafblock_pack_impl(const float* const* P, BlockPacked& pk, int C, cudaStream
   return 0;
 }
 
+// A LayerNorm2d forward fused into the epilogue of the GEMM that PRODUCES its input rows (gemm.cuh, EpiParams::ln_*): the
+// consumer's affine parameters and where its normalised bf16 rows / (mean, rstd) go.  n == nullptr: not fused.
+struct LnFuse {
+  const float* w;
+  const float* b;
+  bf16* n;
+  float* stats;
+};
+constexpr float kLnEps = 1e-6f;  // LayerNorm2d default (nafnet_arch.py:57)
+
+bool ln_fuse_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DCPT_LN_FUSE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+// can the GEMM writing a [*, C] fp32 tensor also run its consumer's LayerNorm?
+bool ln_fusable(int C) { return ln_fuse_enabled() && gemm_ln_fusable(C) && C % 8 == 0; }
+
+void set_ln_epilogue(GemmArgs& g, const LnFuse& f, int C) {
+  g.ep.ln_w = f.w; g.ep.ln_b = f.b; g.ep.ln_out = f.n; g.ep.ld_ln = C; g.ep.ln_stats = f.stats; g.ep.ln_eps = kLnEps;
+}
+
+// ln1_done: the producer of `x` already wrote sv.n1 / sv.stats1 (fused LayerNorm epilogue); next: the LayerNorm of the
+// consumer of `out` (the following block's norm1), fused into conv5's epilogue when supported.
 int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float* x, float* out, bf16* out_bf16,
-                      const BlockSaved& sv, int N, int H, int W, int C, cudaStream_t st, int tlc_kh = 0, int tlc_kw = 0) {
+                      const BlockSaved& sv, int N, int H, int W, int C, cudaStream_t st, int tlc_kh = 0, int tlc_kw = 0,
+                      bool ln1_done = false, const LnFuse* next = nullptr, bool pool_zeroed = false) {
   const int HW = H * W, M = N * HW;
-  constexpr float eps = 1e-6f;  // LayerNorm2d default (nafnet_arch.py:57)
+  constexpr float eps = kLnEps;
   // norm1 -> conv1 (+bias)
-  DCPT_TRY(ln_fwd_launch(x, P[P_N1W], P[P_N1B], sv.n1, sv.stats1, M, C, eps, st));
+  if (!ln1_done) DCPT_TRY(ln_fwd_launch(x, P[P_N1W], P[P_N1B], sv.n1, sv.stats1, M, C, eps, st));
   {
     GemmArgs g = gemm_args(M, 2 * C, C, sv.n1, C, pk.w1, C, EPI_STORE);
     g.ep.out_bf16 = sv.u; g.ep.ldo = 2 * C; g.ep.bias = P[P_C1B];
     DCPT_TRY(gemm_launch(g, st));
   }
   // conv2 (dw 3x3) + SimpleGate, global average pool partial sums
-  DCPT_CUDA(cudaMemsetAsync(sv.pool, 0, (size_t)N * C * sizeof(float), st));
+  if (!pool_zeroed) DCPT_CUDA(cudaMemsetAsync(sv.pool, 0, (size_t)N * C * sizeof(float), st));
   DCPT_TRY(dwgate_fwd_launch(sv.u, P[P_C2W], P[P_C2B], sv.g, sv.pool, N, H, W, C, st));
   if (tlc_kh > 0 && (tlc_kh < H || tlc_kw < W)) {
     // TLC inference (NAFNet / Local_Base, arch_util.py:339-398): the pooled vector is a per-pixel box mean, so SCA becomes
@@ -208,10 +251,11 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
   {
     GemmArgs g = gemm_args(M, C, C, sv.gs, C, pk.w3b, C, EPI_STORE);
     g.ep.out_f32 = sv.y; g.ep.ldo = C; g.ep.bias = pk.b3b; g.ep.resid = x; g.ep.ldr = C;
+    if (ln_fusable(C)) set_ln_epilogue(g, LnFuse{P[P_N2W], P[P_N2B], sv.n2, sv.stats2}, C);  // norm2 in conv3's epilogue
     DCPT_TRY(gemm_launch(g, st));
   }
   // norm2 -> conv4 -> SimpleGate
-  DCPT_TRY(ln_fwd_launch(sv.y, P[P_N2W], P[P_N2B], sv.n2, sv.stats2, M, C, eps, st));
+  if (!ln_fusable(C)) DCPT_TRY(ln_fwd_launch(sv.y, P[P_N2W], P[P_N2B], sv.n2, sv.stats2, M, C, eps, st));
   {
     GemmArgs g = gemm_args(M, 2 * C, C, sv.n2, C, pk.w4p, C, C % 32 == 0 ? EPI_GATE_TMA : EPI_GATE);
     g.ep.out_bf16 = sv.x4; g.ep.ldo = 2 * C; g.ep.out2 = sv.sg; g.ep.ldo2 = C; g.ep.C = C; g.ep.bias = pk.b4p;
@@ -221,6 +265,7 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
   {
     GemmArgs g = gemm_args(M, C, C, sv.sg, C, pk.w5g, C, EPI_STORE);
     g.ep.out_f32 = out; g.ep.out_bf16 = out_bf16; g.ep.ldo = C; g.ep.bias = pk.b5g; g.ep.resid = sv.y; g.ep.ldr = C;
+    if (next && next->n) set_ln_epilogue(g, *next, C);  // the next block's norm1
     DCPT_TRY(gemm_launch(g, st));
   }
   return 0;
@@ -252,9 +297,13 @@ SideStream& side_stream() {
 
 int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockSaved& sv, const float* x, const float* dout,
                       const bf16* doutT, const float* Sout, float* dx, bf16* dxT, float* Sx, float* const* G, const BlockWork& wk,
-                      int N, int H, int W, int C, cudaStream_t st) {
+                      int N, int H, int W, int C, cudaStream_t st, const BlockZeros* zeros = nullptr) {
   const int HW = H * W, M = N * HW;
   const size_t cc = (size_t)C * C;
+  float* const G5 = zeros ? zeros->G5 : wk.G;
+  float* const G3 = zeros ? zeros->G3 : wk.G;
+  float* const Sy = zeros ? zeros->Sy : wk.Sy;
+  float* const ds = zeros ? zeros->ds : wk.ds;
   SideStream& ss = side_stream();
   const bool fork = ss.ok && !g_dcpt_prof_on;   // per-kernel profiling keeps everything on one stream
   cudaStream_t sw = fork ? ss.s : st;           // stream of the weight-gradient work
@@ -267,9 +316,9 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   };
   // ---- conv5 (gamma folded): wgrad, dgamma, dbias; dgrad fused with SimpleGate backward ----
   DCPT_TRY(fork_here(0));
-  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), sw));
-  DCPT_TRY(wgrad_gemm(doutT, C, sv.sg, C, wk.G, M, sw));
-  DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C5W], P[P_C5B], P[P_GAMMA], Sout, G[P_C5W], G[P_C5B], G[P_GAMMA], C, C, sw));
+  if (!zeros) DCPT_CUDA(cudaMemsetAsync(G5, 0, cc * sizeof(float), sw));
+  DCPT_TRY(wgrad_gemm(doutT, C, sv.sg, C, G5, M, sw));
+  DCPT_TRY(wgrad_finish_resid_launch(G5, P[P_C5W], P[P_C5B], P[P_GAMMA], Sout, G[P_C5W], G[P_C5B], G[P_GAMMA], C, C, sw));
   {
     GemmArgs g = gemm_args(M, C, C, doutT, C, pk.w5gt, C, EPI_GATE_BWD);
     g.ep.out_bf16 = wk.dx4; g.ep.ldo = 2 * C; g.ep.aux = sv.x4; g.ep.ldaux = 2 * C; g.ep.C = C;
@@ -285,23 +334,23 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
     DCPT_TRY(gemm_launch(g, st));
   }
   // ---- norm2 backward + residual: dy = dout + LN'(dn2) ----
-  DCPT_CUDA(cudaMemsetAsync(wk.Sy, 0, C * sizeof(float), st));
-  DCPT_TRY(ln_bwd_launch(wk.dn, sv.y, sv.stats2, P[P_N2W], dout, wk.dy, wk.dyT, G[P_N2W], G[P_N2B], wk.Sy, M, C, st));
+  if (!zeros) DCPT_CUDA(cudaMemsetAsync(Sy, 0, C * sizeof(float), st));
+  DCPT_TRY(ln_bwd_launch(wk.dn, sv.y, sv.stats2, P[P_N2W], dout, wk.dy, wk.dyT, G[P_N2W], G[P_N2B], Sy, M, C, st));
   // ---- conv3 (beta folded) ----
   DCPT_TRY(fork_here(2));
-  DCPT_CUDA(cudaMemsetAsync(wk.G, 0, cc * sizeof(float), sw));
-  DCPT_TRY(wgrad_gemm(wk.dyT, C, sv.gs, C, wk.G, M, sw));
-  DCPT_TRY(wgrad_finish_resid_launch(wk.G, P[P_C3W], P[P_C3B], P[P_BETA], wk.Sy, G[P_C3W], G[P_C3B], G[P_BETA], C, C, sw));
-  DCPT_CUDA(cudaMemsetAsync(wk.ds, 0, (size_t)N * C * sizeof(float), st));
+  if (!zeros) DCPT_CUDA(cudaMemsetAsync(G3, 0, cc * sizeof(float), sw));
+  DCPT_TRY(wgrad_gemm(wk.dyT, C, sv.gs, C, G3, M, sw));
+  DCPT_TRY(wgrad_finish_resid_launch(G3, P[P_C3W], P[P_C3B], P[P_BETA], Sy, G[P_C3W], G[P_C3B], G[P_BETA], C, C, sw));
+  if (!zeros) DCPT_CUDA(cudaMemsetAsync(ds, 0, (size_t)N * C * sizeof(float), st));
   {  // dgrad, with the SCA backward's ds[n, c] = sum_px d(g*s) * g reduced in the GEMM epilogue
     GemmArgs g = gemm_args(M, C, C, wk.dyT, C, pk.w3bt, C, EPI_STORE);
     g.ep.out_bf16 = wk.dgs; g.ep.ldo = C;
-    g.ep.gaux = sv.g; g.ep.ldgaux = C; g.ep.colsum = wk.ds; g.ep.rows_per_img = HW;
+    g.ep.gaux = sv.g; g.ep.ldgaux = C; g.ep.colsum = ds; g.ep.rows_per_img = HW;
     DCPT_TRY(gemm_launch(g, st));
   }
   // ---- SCA backward ----
   DCPT_TRY(fork_here(5));
-  DCPT_TRY(sca_bwd_launch(wk.ds, sv.pool, P[P_SCAW], wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st, sw));
+  DCPT_TRY(sca_bwd_launch(ds, sv.pool, P[P_SCAW], wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st, sw));
   // ---- SimpleGate + depthwise conv backward ----
   DCPT_TRY(dwgate_bwd_a_launch(wk.dgs, sv.s, wk.t, sv.u, P[P_C2W], P[P_C2B], wk.du2, G[P_C2W], G[P_C2B], N, H, W, C, st));
   DCPT_TRY(dwconv_bwd_data_launch(wk.du2, P[P_C2W], wk.du, G[P_C1B], N, H, W, 2 * C, st));
@@ -414,7 +463,27 @@ struct NetSaved {
         dec_out[i].push_back(a.take<float>((size_t)N * h * w * C));
       }
     }
+    // the SCA pooling sums of ALL blocks in one contiguous region, cleared by one memset per forward (they are accumulated
+    // with atomics by dwgate_fwd); the per-block `pool` slots carved above stay unused
+    size_t total = 0;
+    auto count = [&](std::vector<BlockSaved>& v, int c) { total += v.size() * (((size_t)N * c + 63) / 64 * 64); };
+    C = p->width;
+    for (int i = 0; i < ne; ++i) { count(enc_sv[i], C); C *= 2; }
+    count(mid_sv, C);
+    for (int i = 0; i < nd; ++i) { C /= 2; count(dec_sv[i], C); }
+    pools = a.take<float>(total);
+    pool_floats = total;
+    float* q = pools;
+    auto assign = [&](std::vector<BlockSaved>& v, int c) {
+      for (auto& b : v) { b.pool = q; if (q) q += ((size_t)N * c + 63) / 64 * 64; }
+    };
+    C = p->width;
+    for (int i = 0; i < ne; ++i) { assign(enc_sv[i], C); C *= 2; }
+    assign(mid_sv, C);
+    for (int i = 0; i < nd; ++i) { C /= 2; assign(dec_sv[i], C); }
   }
+  float* pools = nullptr;
+  size_t pool_floats = 0;
 };
 
 struct NetPacked {
@@ -484,7 +553,17 @@ struct NetWork {
     G = a.take<float>(max_g);
     Pd = a.take<bf16>((size_t)N * H * W * 32);
     psum = a.take<float>(32);
+    // per-block accumulators (BlockZeros) + each block's column-sum output Sx, one region cleared once per backward
+    zero_floats = 0;
+    int Cz = p->width;
+    auto add = [&](int nblk, int c) { zero_floats += (size_t)nblk * (BlockZeros::floats(N, c) + ((size_t)c + 63) / 64 * 64); };
+    for (int i = 0; i < ne; ++i) { add(p->enc[i], Cz); Cz *= 2; }
+    add(p->middle_blk_num, Cz);
+    for (size_t i = 0; i < p->dec.size(); ++i) { Cz /= 2; add(p->dec[i], Cz); }
+    zeros = a.take<float>(zero_floats);
   }
+  float* zeros = nullptr;
+  size_t zero_floats = 0;
 };
 
 int check_ptrs16(const void* const* ptrs, int n, const char* what) {
@@ -579,6 +658,8 @@ int dcpt_gemm_ex(const dcpt_gemm_desc* d, int impl, dcpt_stream_t stream) {
   g.ep.out2 = static_cast<bf16*>(d->out2_bf16); g.ep.ldo2 = d->ldo2;
   g.ep.aux = static_cast<const bf16*>(d->aux_bf16); g.ep.ldaux = d->ldaux;
   g.ep.C = d->C; g.ep.H = d->H; g.ep.W = d->W; g.ep.Cseg = d->Cseg;
+  g.ep.ln_w = d->ln_weight; g.ep.ln_b = d->ln_bias; g.ep.ln_out = static_cast<bf16*>(d->ln_out); g.ep.ld_ln = d->ld_ln;
+  g.ep.ln_stats = d->ln_stats; g.ep.ln_eps = d->ln_eps;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return impl == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
 }
@@ -773,19 +854,41 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   auto tkh = [&](int lvl) { return lvl < (int)p->tlc_kh.size() ? p->tlc_kh[lvl] : 0; };
   auto tkw = [&](int lvl) { return lvl < (int)p->tlc_kw.size() ? p->tlc_kw[lvl] : 0; };
 
+  // The norm1 of a block is computed by the epilogue of the GEMM that writes the block's input (intro conv, down conv, the
+  // previous block's conv5) whenever that GEMM holds whole rows (C <= 512): `fused` says the next block finds n1 / stats1 ready.
+  auto ln1_of = [&](const dcpt_nafnet_plan::Blk& b, const BlockSaved& bsv) -> LnFuse {
+    if (!ln_fusable(b.C)) return LnFuse{nullptr, nullptr, nullptr, nullptr};
+    return LnFuse{P[b.pidx + P_N1W], P[b.pidx + P_N1B], bsv.n1, bsv.stats1};
+  };
+  const LnFuse no_ln = {nullptr, nullptr, nullptr, nullptr};
+  // first block after the encoder level i's down conv (or after the intro conv for i = -1)
+  auto first_after = [&](int i) -> LnFuse {
+    for (int k = i + 1; k < ne; ++k) {
+      if (p->enc[k] > 0) return k == i + 1 ? ln1_of(p->enc_blks[k][0], sv.enc_sv[k][0]) : no_ln;
+      return no_ln;  // an empty level: its down conv consumes the tensor
+    }
+    return (i + 1 == ne && p->middle_blk_num > 0) ? ln1_of(p->mid_blks[0], sv.mid_sv[0]) : no_ln;
+  };
+  bool fused = false;
+  DCPT_CUDA(cudaMemsetAsync(sv.pools, 0, sv.pool_floats * sizeof(float), st));  // every block's SCA pooling sums
   // intro (nafnet_arch.py:252)
   {  // x0 = im2col(inp) * Wi^T + b on the tensor cores
     DCPT_TRY(im2col3_launch(inp, sv.P, nullptr, 0, 1, N, h, w, st));
     GemmArgs g = gemm_args(N * h * w, C, 64, sv.P, 64, pk.wi_p, 64, EPI_STORE);  // [P | P] x [W_hi | W_lo]
     g.ep.out_f32 = sv.x0; g.ep.ldo = C; g.ep.bias = P[1];
+    const LnFuse f = first_after(-1);
+    fused = f.n != nullptr;
+    if (fused) set_ln_epilogue(g, f, C);
     DCPT_TRY(gemm_launch(g, st));
   }
   const float* x = sv.x0;
   // encoders + downs (:256-259)
   for (int i = 0; i < ne; ++i) {
     for (int j = 0; j < p->enc[i]; ++j) {
+      const LnFuse nx = j + 1 < p->enc[i] ? ln1_of(p->enc_blks[i][j + 1], sv.enc_sv[i][j + 1]) : no_ln;
       DCPT_TRY(nafblock_fwd_impl(P + p->enc_blks[i][j].pidx, pk.enc_pk[i][j], x, sv.enc_out[i][j], nullptr, sv.enc_sv[i][j], N, h,
-                                 w, C, st, tkh(i), tkw(i)));
+                                 w, C, st, tkh(i), tkw(i), fused, &nx, true));
+      fused = nx.n != nullptr;
       x = sv.enc_out[i][j];
     }
     DCPT_TRY(unshuffle_cast_launch(x, sv.xu[i], N, h / 2, w / 2, C, st));
@@ -793,6 +896,9 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     GemmArgs g = gemm_args(N * h * w, 2 * C, 4 * C, sv.xu[i], 4 * C, pk.down[i], 4 * C, EPI_STORE);
     g.ep.out_f32 = sv.xd[i]; g.ep.ldo = 2 * C; g.ep.bias = P[p->down_pidx[i] + 1];
     if (i == ne - 1 && p->middle_blk_num == 0 && nd > 0) g.ep.out_bf16 = sv.up_in[0];
+    const LnFuse f = first_after(i);
+    fused = f.n != nullptr;
+    if (fused) set_ln_epilogue(g, f, 2 * C);
     DCPT_TRY(gemm_launch(g, st));
     C *= 2;
     x = sv.xd[i];
@@ -800,8 +906,10 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   // middle (:261)
   for (int j = 0; j < p->middle_blk_num; ++j) {
     bf16* mirror = (j == p->middle_blk_num - 1 && nd > 0) ? sv.up_in[0] : nullptr;
+    const LnFuse nx = j + 1 < p->middle_blk_num ? ln1_of(p->mid_blks[j + 1], sv.mid_sv[j + 1]) : no_ln;
     DCPT_TRY(nafblock_fwd_impl(P + p->mid_blks[j].pidx, pk.mid_pk[j], x, sv.mid_out[j], mirror, sv.mid_sv[j], N, h, w, C, st, tkh(ne),
-                               tkw(ne)));
+                               tkw(ne), fused, &nx, true));
+    fused = nx.n != nullptr;
     x = sv.mid_out[j];
   }
   if (ne == 0 && p->middle_blk_num == 0 && nd > 0) { dcpt_set_error("nafnet_fwd: degenerate network"); return DCPT_E_UNSUPPORTED; }
@@ -814,10 +922,13 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     DCPT_TRY(gemm_launch(g, st));
     h *= 2; w *= 2; C /= 2;
     x = sv.xup[i];
+    fused = false;  // the up conv's pixel-shuffle epilogue scatters rows: the first decoder block runs its own norm1
     for (int j = 0; j < p->dec[i]; ++j) {
       bf16* mirror = (j == p->dec[i] - 1) ? (i + 1 < nd ? sv.up_in[i + 1] : sv.xlast_bf16) : nullptr;
+      const LnFuse nx = j + 1 < p->dec[i] ? ln1_of(p->dec_blks[i][j + 1], sv.dec_sv[i][j + 1]) : no_ln;
       DCPT_TRY(nafblock_fwd_impl(P + p->dec_blks[i][j].pidx, pk.dec_pk[i][j], x, sv.dec_out[i][j], mirror, sv.dec_sv[i][j], N, h, w,
-                                 C, st, tkh(ne - 1 - i), tkw(ne - 1 - i)));
+                                 C, st, tkh(ne - 1 - i), tkw(ne - 1 - i), fused, &nx, true));
+      fused = nx.n != nullptr;
       x = sv.dec_out[i][j];
     }
     if (host_feats && host_feats[i])
@@ -852,6 +963,7 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   // column sums (bias / beta / gamma gradients).  Two slots, ping-pong.
   struct Slot { float* f; bf16* t; float* s; };
   Slot slot[2] = {{wk.dxa, wk.dta, wk.Sa}, {wk.dxb, wk.dtb, wk.Sb}};
+  float* const Sorig[2] = {wk.Sa, wk.Sb};
   int ci = 0;
   bool have = false;
 #define CUR slot[ci]
@@ -885,13 +997,19 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     }
     have = true;
   }
+  // one memset for every block's accumulators (BlockZeros) and column-sum outputs
+  DCPT_CUDA(cudaMemsetAsync(wk.zeros, 0, wk.zero_floats * sizeof(float), st));
+  float* zcur = wk.zeros;
   auto block_bwd = [&](const dcpt_nafnet_plan::Blk& b, const BlockPacked& bpk, const BlockSaved& bsv, const float* x, int hh,
                        int ww) -> int {
     DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient reaches a block (dout and dfeats all NULL?)");
     Arena a(wk.blk_base);
     BlockWork bw(a, N, hh, ww, b.C);
-    DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, b.C * sizeof(float), st));
-    DCPT_TRY(nafblock_bwd_impl(P + b.pidx, bpk, bsv, x, CUR.f, CUR.t, CUR.s, NXT.f, NXT.t, NXT.s, G + b.pidx, bw, N, hh, ww, b.C, st));
+    const BlockZeros bz(zcur, N, b.C);
+    zcur += BlockZeros::floats(N, b.C);
+    NXT.s = zcur;  // this block's Sx (column sums of dx): its own pre-cleared slice, read by the next block / conv backward
+    zcur += ((size_t)b.C + 63) / 64 * 64;
+    DCPT_TRY(nafblock_bwd_impl(P + b.pidx, bpk, bsv, x, CUR.f, CUR.t, CUR.s, NXT.f, NXT.t, NXT.s, G + b.pidx, bw, N, hh, ww, b.C, st, &bz));
     ci ^= 1;
     return 0;
   };
@@ -900,6 +1018,7 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   for (int i = nd - 1; i >= 0; --i) {
     const float* ext = host_dfeats ? host_dfeats[i] : nullptr;
     if (ext) {  // gradient injected by the DCPT head into this decoder level's output
+      NXT.s = Sorig[ci ^ 1];  // (a block backward may have pointed the slot at its own pre-cleared slice)
       DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, C * sizeof(float), st));
       DCPT_TRY(grad_prepare_launch(have ? CUR.f : nullptr, ext, NXT.f, NXT.t, NXT.s, N * h * w, C, st));
       ci ^= 1;
@@ -921,6 +1040,7 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
       GemmArgs g = gemm_args(Min, Cin, 2 * Cin, wk.dconv, 2 * Cin, pk.up_t[i], 2 * Cin, EPI_STORE);
       g.ep.out_f32 = NXT.f; g.ep.out_bf16 = NXT.t; g.ep.ldo = Cin;
       DCPT_TRY(gemm_launch(g, st));
+      NXT.s = Sorig[ci ^ 1];
       DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, Cin * sizeof(float), st));
       DCPT_TRY(grad_prepare_launch(NXT.f, nullptr, nullptr, nullptr, NXT.s, Min, Cin, st));
       ci ^= 1;
@@ -944,6 +1064,7 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
       g.ep.out_f32 = NXT.f; g.ep.out_bf16 = NXT.t; g.ep.resid = wk.dskip[i];  // + gradient of the decoder skip
       g.ep.H = h; g.ep.W = w; g.ep.Cseg = Cl;
       DCPT_TRY(gemm_launch(g, st));
+      NXT.s = Sorig[ci ^ 1];
       DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, Cl * sizeof(float), st));
       DCPT_TRY(grad_prepare_launch(NXT.f, nullptr, nullptr, nullptr, NXT.s, N * hl * wl, Cl, st));
       ci ^= 1;

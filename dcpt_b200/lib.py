@@ -23,7 +23,9 @@ class GemmDesc(C.Structure):
                 ("bias", C.c_void_p), ("resid", C.c_void_p), ("ldr", C.c_int),
                 ("out2_bf16", C.c_void_p), ("ldo2", C.c_int),
                 ("aux_bf16", C.c_void_p), ("ldaux", C.c_int),
-                ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cseg", C.c_int)]
+                ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cseg", C.c_int),
+                ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p), ("ln_out", C.c_void_p), ("ld_ln", C.c_int),
+                ("ln_stats", C.c_void_p), ("ln_eps", C.c_float)]
 
 
 _VP, _I, _F, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong

@@ -96,6 +96,12 @@ typedef struct dcpt_gemm_desc {
   const void* aux_bf16; int ldaux;
   int C;
   int H, W, Cseg;
+  /* STORE only, optional (ln_out != NULL; needs out_f32, 16-byte pitched rows and N <= 512): the channel LayerNorm of the
+   * finished output rows v = acc + bias + resid (LayerNorm2d forward, nafnet_arch.py:27-35; the norm that CONSUMES this tensor)
+   * computed in the same epilogue: ln_out[m,:] = bf16((v - mean) * rstd * ln_weight + ln_bias), ln_stats[m] = (mean, rstd). */
+  const float* ln_weight; const float* ln_bias;
+  void* ln_out; int ld_ln;
+  float* ln_stats; float ln_eps;
 } dcpt_gemm_desc;
 int dcpt_gemm_ex(const dcpt_gemm_desc* desc, int impl, dcpt_stream_t stream);
 

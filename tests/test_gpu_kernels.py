@@ -56,6 +56,49 @@ def test_gemm_store(ops, impl, M, N, K):
     assert out.dtype == torch.bfloat16 and rel(out.float(), ref + bias) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,mirror", [(1000, 512, 512, False), (16384, 512, 512, False), (4099, 256, 256, True), (33000, 128, 64, False),
+                                          (70000, 64, 64, True), (130, 72, 40, False), (300, 24, 16, False), (257, 8, 8, False),
+                                          (2048, 384, 128, False), (16500, 512, 1024, True)])
+def test_gemm_store_fused_layernorm(ops, M, N, K, mirror):
+    """STORE epilogue with the consumer's LayerNorm2d fused (EpiParams::ln_*): out = A B^T + bias + resid (fp32), and the channel
+    LayerNorm of those rows (nafnet_arch.py:27-35) as bf16 + (mean, rstd), against fp32 torch math on the GEMM's own fp32 output:
+    statistics 1e-5 (fp32 sums in another order), normalised rows one bf16 rounding (4e-3).  N = 512 exercises the whole-slab
+    schedule (two accumulator buffers per row slab), N % 32 != 0 the column masking, M % 128 != 0 the row clipping."""
+    from dcpt_b200.lib import GemmDesc
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = bf(torch.randn(M, K, device="cuda", generator=g))
+    B = bf(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) + 0.7          # un-centred rows: the shifted sums must cope
+    lw = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    lb = 0.3 * torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ln = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stats = torch.full((M, 2), float("nan"), device="cuda")
+    mir = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if mirror else None
+    d = GemmDesc()
+    for k, v in dict(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=out, out_bf16=mir, ldo=N, bias=bias, resid=resid,
+                     ldr=N, ln_weight=lw, ln_bias=lb, ln_out=ln, ld_ln=N, ln_stats=stats, ln_eps=1e-6).items():
+        setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+    ops.gemm_ex(d)
+    ref = A.float() @ B.float().t() + bias + resid
+    assert rel(out, ref) < 2e-5
+    if mirror:
+        assert rel(mir.float(), ref) < 4e-3
+    x = out.double()
+    mu = x.mean(1)
+    var = (x - mu[:, None]).pow(2).mean(1)
+    rstd = 1.0 / (var + 1e-6).sqrt()
+    assert rel(stats[:, 0], mu) < 1e-5 and rel(stats[:, 1], rstd) < 1e-5
+    ref_ln = (x - mu[:, None]) * rstd[:, None] * lw.double() + lb.double()
+    assert torch.isfinite(ln.float()).all()
+    assert rel(ln.float(), ref_ln) < 4e-3
+    # bit-level agreement with the standalone LayerNorm kernel on the same fp32 rows (both round the same fp32 formula once)
+    n_ref, st_ref = ops.layernorm2d_fwd(out, lw, lb)
+    assert rel(stats, st_ref) < 1e-5
+    assert (ln.float() - n_ref.float()).abs().max() <= 2 ** -7 * ref_ln.abs().max()
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 512, 512), (130, 72, 40), (33000, 96, 48)])
 def test_gemm_store_both_outputs(ops, M, N, K):
     """fp32 output + bf16 mirror + residual in one launch (the level-boundary GEMMs of the networks)."""

@@ -16,11 +16,13 @@ from dcpt_b200.lib import GemmDesc, load_library  # noqa: E402
 
 NAMES = ["entry", "prologue done", "first operands landed (MMA warp)", "tile0 MMAs issued", "last tile MMAs issued",
          "tile0 accumulator ready (epi warp)", "tile0 epilogue done", "last tile accumulator ready", "last tile epilogue done",
-         "stores drained", "exit"]
+         "stores drained", "exit", "LN: pass 1 of the slab done", "LN: statistics exchanged", "LN: pass 2 done"]
 
 
 def main():
-    M, N, K = (int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (16384, 512, 512)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    M, N, K = (int(v) for v in args[:3]) if len(args) >= 3 else (16384, 512, 512)
+    with_ln = "--ln" in sys.argv
     dev = torch.device("cuda", 0)
     lib = load_library()
     lib.dcpt_debug_set_trace.argtypes = [ctypes.c_void_p]
@@ -32,6 +34,13 @@ def main():
     d = GemmDesc()
     for k, v in dict(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=out, ldo=N, resid=res, ldr=N, bias=bias).items():
         setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+    if with_ln:   # fused LayerNorm of the output rows (EpiParams::ln_*)
+        lw, lb = torch.ones(N, device=dev), torch.zeros(N, device=dev)
+        ln = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        stats = torch.empty(M, 2, device=dev)
+        for k, v in dict(ln_weight=lw, ln_bias=lb, ln_out=ln, ld_ln=N, ln_stats=stats).items():
+            setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+        d.ln_eps = 1e-6
     tr = torch.zeros(148 * 16 * 2, dtype=torch.int64, device=dev)
     for _ in range(3):
         ops.gemm_ex(d)
@@ -43,7 +52,7 @@ def main():
         ops.gemm_ex(d)
     e1.record()
     torch.cuda.synchronize()
-    print(f"GEMM {M}x{N}x{K} store+resid: {e0.elapsed_time(e1) / 20 * 1e3:.2f} us per launch back to back (eager)")
+    print(f"GEMM {M}x{N}x{K} store+resid{'+LN' if with_ln else ''}: {e0.elapsed_time(e1) / 20 * 1e3:.2f} us per launch back to back (eager)")
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(20):
