@@ -131,20 +131,28 @@ class NAFNetBaseline(nn.Module):
         return self._engine
 
     def _decoder_hook_targets(self):
-        """Sub-modules with forward hooks that the fused forward must serve: decoder{i} and its last
-        block (DCPT registers on ``decoder{i}.0`` unwrapped / ``module.decoder{i}`` under DDP,
-        degradation_classification_pretrain_model.py:60-68)."""
+        """Sub-modules with forward hooks that the fused forward must serve, per decoder level: (modules, block index).
+        DCPT registers on every module whose name contains ``hook_names`` and has exactly one dot
+        (degradation_classification_pretrain_model.py:64-67): ``decoder{i}.0`` - the level's FIRST block - for an unwrapped
+        network, ``module.decoder{i}`` - the whole level - under DDP.  One tap per level: the container (= its last block) or
+        one block ``decoder{i}.{j}``; the engine materialises that block's output and routes the gradient back into it."""
         n_dec = len(self._cfg[4])
-        targets = []
+        targets, blocks = [], []
         for i in range(n_dec):
             seq = getattr(self, f"decoder{i}")
-            mods = [seq] + ([seq[len(seq) - 1]] if len(seq) > 0 else [])
-            targets.append([m for m in mods if len(m._forward_hooks) > 0])
-            for j in range(max(len(seq) - 1, 0)):
-                if len(seq[j]._forward_hooks) > 0:
-                    raise DcptError(f"forward hook on decoder{i}.{j}: only a decoder level's output (decoder{i} or its "
-                                    "last block) is materialised by the fused forward")
-        return targets
+            last = len(seq) - 1
+            hooked = [j for j in range(len(seq)) if len(seq[j]._forward_hooks) > 0]
+            if len(seq._forward_hooks) > 0 and last >= 0 and last not in hooked:
+                hooked.append(last)
+            if len(set(hooked)) > 1:
+                raise DcptError(f"forward hooks on several blocks of decoder{i} ({sorted(set(hooked))}): the fused forward "
+                                "materialises one feature per decoder level")
+            j = hooked[0] if hooked else -1
+            mods = ([seq] if len(seq._forward_hooks) > 0 and (j == last or last < 0) else []) + \
+                   ([seq[j]] if j >= 0 and len(seq[j]._forward_hooks) > 0 else [])
+            targets.append(mods)
+            blocks.append(j if j != last else -1)
+        return targets, blocks
 
     def _param_list(self):
         """list(self.parameters()) without the module-tree walk (0.4 ms per call for 664 tensors, paid while the GPU idles
@@ -168,9 +176,12 @@ class NAFNetBaseline(nn.Module):
 
     def forward(self, inp, hook=False):
         params = self._param_list()
-        targets = self._decoder_hook_targets()
+        targets, blocks = self._decoder_hook_targets()
         want_feats = any(len(t) > 0 for t in targets)
-        out, feats = nafnet_apply(self.engine(), inp, params, hook=bool(hook), want_feats=want_feats)
+        eng = self.engine()
+        if want_feats:
+            eng.set_hook_blocks(blocks)
+        out, feats = nafnet_apply(eng, inp, params, hook=bool(hook), want_feats=want_feats)
         if want_feats:
             for mods, f in zip(targets, feats):
                 for m in mods:

@@ -22,20 +22,23 @@ def _nvcc():
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(lib=None):
+    lib = lib or LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "dcpt_ops.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=True, trace=False):
-    """trace=True builds the debug variant libdcpt_sm100_trace.so (-DDCPT_TRACE: per-CTA GEMM event timeline, tools/gemm_trace.py)."""
-    if not trace and not force and not needs_build():
-        return LIB
-    out = LIB.replace(".so", "_trace.so") if trace else LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-DDCPT_TRACE"] if trace else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
+def build(force=False, verbose=True, trace=False, fp16=False):
+    """trace=True builds the debug variant libdcpt_sm100_trace.so (-DDCPT_TRACE: per-CTA GEMM event timeline, tools/gemm_trace.py);
+    fp16=True the parity variant libdcpt_sm100_fp16.so (-DDCPT_OPERAND_FP16: IEEE-half tensor-core operands, DCPT_OPERAND=fp16)."""
+    out = LIB.replace(".so", "_trace.so") if trace else (LIB.replace(".so", "_fp16.so") if fp16 else LIB)
+    if not trace and not force and not needs_build(out):
+        return out
+    defs = (["-DDCPT_TRACE"] if trace else []) + (["-DDCPT_OPERAND_FP16"] if fp16 else [])
+    cmd = [_nvcc()] + NVCC_FLAGS + defs + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     if verbose:
         print("[dcpt_b200] " + " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True, cwd=CSRC)
@@ -43,4 +46,4 @@ def build(force=False, verbose=True, trace=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, trace="--trace" in sys.argv))
+    print(build(force="--force" in sys.argv, trace="--trace" in sys.argv, fp16="--fp16" in sys.argv))

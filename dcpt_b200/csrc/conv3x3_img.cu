@@ -345,13 +345,13 @@ __global__ void pack_w27_kernel(const float* __restrict__ w, bf16* __restrict__ 
       const float hi = bf16_round(wv);
       v = jj < 32 ? hi : wv - hi;
     }
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = OP_FROM_F32(v);
   } else {
     if (i >= C * 32) return;
     const int r = i >> 5, j = i & 31;
     float v = 0.f;
     if (j < 27) v = w[((size_t)(j / 9) * C + r) * 9 + (j % 9)];
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = OP_FROM_F32(v);
   }
 }
 
@@ -432,7 +432,7 @@ ending_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmF, const float* __re
     for (int x = 0; x < EHW; ++x) {
 #pragma unroll
       for (int rr = 0; rr < 3; ++rr)
-        A[rr][x % 3] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sF + ((warp + rr) * EHW + x) * 64));
+        A[rr][x % 3] = OP2_TO_F32(*reinterpret_cast<const op16x2*>(sF + ((warp + rr) * EHW + x) * 64));
       if (x >= 2) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll

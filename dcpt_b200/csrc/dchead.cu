@@ -18,12 +18,12 @@ __device__ __forceinline__ float group_sum(float v, int lpr) {
 }
 __device__ __forceinline__ float4 ld4_bf16(const bf16* p) {
   const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  const float2 a = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&u.x));
+  const float2 b = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&u.y));
   return make_float4(a.x, a.y, b.x, b.y);
 }
 __device__ __forceinline__ void st4_bf16(bf16* p, float4 v) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+  op16x2 p0 = OP2_FROM_F32(v.x, v.y), p1 = OP2_FROM_F32(v.z, v.w);
   uint2 u;
   u.x = *reinterpret_cast<uint32_t*>(&p0);
   u.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -289,7 +289,7 @@ meanpool_kernel(const bf16* __restrict__ x, float* __restrict__ pooled, int HW, 
   float2 acc = make_float2(0.f, 0.f);
   if (c2 < C)
     for (int px = warp; px < HW; px += 8) {
-      const float2 v = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(x + ((size_t)n * HW + px) * C + c2)));
+      const float2 v = OP2_TO_F32(__ldg(reinterpret_cast<const op16x2*>(x + ((size_t)n * HW + px) * C + c2)));
       acc.x += v.x;
       acc.y += v.y;
     }
@@ -370,7 +370,7 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, bf16* __restric
   const int t = rem / cpad, c = rem - t * cpad;
   float v = 0.f;
   if (c < Cc) v = dgrad ? w[(((size_t)c * Cin + r) * 9) + (8 - t)] : w[(((size_t)r * Cin + c) * 9) + t];
-  out[i] = __float2bfloat16_rn(v);
+  out[i] = OP_FROM_F32(v);
 }
 // dw[co][ci][t] += G[co][t * cin_pad + ci]
 __global__ void finish_conv3x3_kernel(const float* __restrict__ G, float* __restrict__ dw, int Cout, int Cin) {

@@ -26,12 +26,12 @@ constexpr int DG_ELEMS = TH * TW * 64;         // interior box (no halo)
 constexpr int DG_BYTES = DG_ELEMS * 2;         // 16384
 
 __device__ __forceinline__ float2 lds_bf2(const bf16* p) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+  return OP2_TO_F32(*reinterpret_cast<const op16x2*>(p));
 }
 __device__ __forceinline__ void st_bf2(bf16* p, float2 v) {
-  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<op16x2*>(p) = OP2_FROM_F32(v.x, v.y);
 }
-__device__ __forceinline__ float2 round_bf2(float2 v) { return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y)); }
+__device__ __forceinline__ float2 round_bf2(float2 v) { return OP2_TO_F32(OP2_FROM_F32(v.x, v.y)); }
 __device__ __forceinline__ void fma2(float2& acc, float2 a, float2 b) {
   acc.x = fmaf(a.x, b.x, acc.x);
   acc.y = fmaf(a.y, b.y, acc.y);

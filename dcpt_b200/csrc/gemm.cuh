@@ -128,15 +128,15 @@ int gemm_launch(const GemmArgs& g, cudaStream_t stream);       // dispatch (DCPT
 // of fp32 output: every global access below is coalesced.  All N on this path are multiples of 8.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+  op16x2 p0 = OP2_FROM_F32(a, b), p1 = OP2_FROM_F32(c, d);
   uint2 u;
   u.x = *reinterpret_cast<uint32_t*>(&p0);
   u.y = *reinterpret_cast<uint32_t*>(&p1);
   return u;
 }
 __device__ __forceinline__ float4 unpack4_bf16(uint2 u) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  const float2 a = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&u.x));
+  const float2 b = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&u.y));
   return make_float4(a.x, a.y, b.x, b.y);
 }
 

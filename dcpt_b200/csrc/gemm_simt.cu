@@ -19,12 +19,12 @@ __global__ void gemm_simt_kernel(GemmArgs g, int k0, int k1, int chunks_n) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
   for (int k = k0; k < k1; ++k) {
-    const float a = __bfloat162float(g.a_mn ? g.A[(size_t)k * g.lda + m] : g.A[(size_t)m * g.lda + k]);
+    const float a = OP_TO_F32(g.a_mn ? g.A[(size_t)k * g.lda + m] : g.A[(size_t)m * g.lda + k]);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int n = n0 + j;
       if (n < g.N) {
-        const float b = __bfloat162float(g.b_mn ? g.B[(size_t)k * g.ldb + n] : g.B[(size_t)n * g.ldb + k]);
+        const float b = OP_TO_F32(g.b_mn ? g.B[(size_t)k * g.ldb + n] : g.B[(size_t)n * g.ldb + k]);
         acc[j] = fmaf(a, b, acc[j]);
       }
     }

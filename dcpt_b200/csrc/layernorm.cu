@@ -89,7 +89,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
             const float o1 = (xv[u][i].y - shift) * rstd * wv[i].y + bv[i].y;
             const float o2 = (xv[u][i].z - shift) * rstd * wv[i].z + bv[i].z;
             const float o3 = (xv[u][i].w - shift) * rstd * wv[i].w + bv[i].w;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+            op16x2 p0 = OP2_FROM_F32(o0, o1), p1 = OP2_FROM_F32(o2, o3);
             uint2 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&p0);
             pk.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -158,8 +158,8 @@ ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const fl
       if (valid && v < nvec) {
         const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * C) + v);
         const uint2 pk = __ldg(reinterpret_cast<const uint2*>(dn + row * C) + v);
-        const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
-        const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+        const float2 d01 = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&pk.x));
+        const float2 d23 = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&pk.y));
         const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + v);
         d[i] = make_float4(d01.x, d01.y, d23.x, d23.y);
         yh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
@@ -190,7 +190,7 @@ ln_bwd_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, const fl
           o.x += rs[i].x; o.y += rs[i].y; o.z += rs[i].z; o.w += rs[i].w;
           *(reinterpret_cast<float4*>(dx + row * C) + v) = o;
           if (dx_bf16) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+            op16x2 p0 = OP2_FROM_F32(o.x, o.y), p1 = OP2_FROM_F32(o.z, o.w);
             uint2 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&p0);
             pk.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -292,8 +292,8 @@ ln_bwd_wide_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, con
         const int v = lane + 32 * i;
         const float4 xv = sx[v];
         const uint2 pk = sd[v];
-        const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
-        const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+        const float2 d01 = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&pk.x));
+        const float2 d23 = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&pk.y));
         yh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
         g[i] = make_float4(d01.x * wv[i].x, d01.y * wv[i].y, d23.x * wv[i].z, d23.y * wv[i].w);
         sg += g[i].x + g[i].y + g[i].z + g[i].w;
@@ -317,7 +317,7 @@ ln_bwd_wide_kernel(const bf16* __restrict__ dn, const float* __restrict__ x, con
         }
         *(reinterpret_cast<float4*>(dx + row * C) + v) = o;
         if (dx_bf16) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+          op16x2 p0 = OP2_FROM_F32(o.x, o.y), p1 = OP2_FROM_F32(o.z, o.w);
           uint2 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&p0);
           pk.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -396,7 +396,7 @@ ln_fwd_wide_kernel(const float* __restrict__ x, const float* __restrict__ w, con
       const float o1 = (cur[i].y - shift) * rstd * wv[i].y + bv[i].y;
       const float o2 = (cur[i].z - shift) * rstd * wv[i].z + bv[i].z;
       const float o3 = (cur[i].w - shift) * rstd * wv[i].w + bv[i].w;
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+      op16x2 p0 = OP2_FROM_F32(o0, o1), p1 = OP2_FROM_F32(o2, o3);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&p0);
       pk.y = *reinterpret_cast<uint32_t*>(&p1);

@@ -326,7 +326,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
   }
   float v = w[(size_t)o * I + i];
   if (row_scale) v *= row_scale[o];
-  out[idx] = __float2bfloat16_rn(v);
+  out[idx] = OP_FROM_F32(v);
 }
 
 __global__ void pack_bias_kernel(const float* __restrict__ bias, const float* __restrict__ scale, float* __restrict__ out, int O,

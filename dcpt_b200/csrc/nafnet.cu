@@ -396,6 +396,10 @@ struct dcpt_nafnet_plan {
   std::vector<Blk> mid_blks;
   std::vector<int> up_pidx, down_pidx;  // ups.i.0.weight ; downs.i.weight (bias = +1)
   int mid_C;
+  // which block of decoder level i delivers host_feats[i] / receives host_dfeats[i] (-1 = the level's last block).  DCPT's
+  // one-dot rule hooks `decoder{i}.0`, the FIRST block (degradation_classification_pretrain_model.py:64-67).
+  std::vector<int> hook_blk;
+  int hook_block(int i) const { return (i < (int)hook_blk.size() && hook_blk[i] >= 0) ? hook_blk[i] : dec[i] - 1; }
 };
 
 namespace {
@@ -591,6 +595,8 @@ int check_net_shape(const dcpt_nafnet_plan* p, int N, int H, int W) {
 extern "C" {
 
 int dcpt_abi_version(void) { return DCPT_ABI_VERSION; }
+
+int dcpt_operand_dtype(void) { return DCPT_OPERAND_ID; }
 
 long long dcpt_launch_count(void) { return g_dcpt_launches; }
 
@@ -792,6 +798,15 @@ int dcpt_nafnet_set_tlc(dcpt_nafnet_plan* plan, const int* kh, const int* kw, in
     DCPT_CHECK_ARG(kh[i] >= 1 && kw[i] >= 1, DCPT_E_ARG, "nafnet_set_tlc: kernel of level %d must be positive", i);
   return 0;
 }
+int dcpt_nafnet_set_hook_blocks(dcpt_nafnet_plan* plan, const int* block_idx, int n_levels) {
+  DCPT_CHECK_ARG(plan != nullptr && n_levels >= 0 && n_levels <= (int)plan->dec.size() && (n_levels == 0 || block_idx), DCPT_E_ARG,
+                 "nafnet_set_hook_blocks: bad arguments");
+  for (int i = 0; i < n_levels; ++i)
+    DCPT_CHECK_ARG(block_idx[i] < plan->dec[i] || plan->dec[i] == 0, DCPT_E_ARG, "nafnet_set_hook_blocks: decoder%d has %d blocks, got index %d", i,
+                   plan->dec[i], block_idx[i]);
+  plan->hook_blk.assign(block_idx, block_idx + n_levels);
+  return 0;
+}
 int dcpt_nafnet_num_params(const dcpt_nafnet_plan* plan) { return (int)plan->params.size(); }
 long long dcpt_nafnet_param_shape(const dcpt_nafnet_plan* plan, int i, int dims[4]) {
   if (i < 0 || i >= (int)plan->params.size()) return -1;
@@ -930,8 +945,10 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
                                  C, st, tkh(ne - 1 - i), tkw(ne - 1 - i), fused, &nx, true));
       fused = nx.n != nullptr;
       x = sv.dec_out[i][j];
+      if (host_feats && host_feats[i] && j == p->hook_block(i))
+        DCPT_CUDA(cudaMemcpyAsync(host_feats[i], x, (size_t)N * h * w * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    if (host_feats && host_feats[i])
+    if (host_feats && host_feats[i] && p->dec[i] == 0)
       DCPT_CUDA(cudaMemcpyAsync(host_feats[i], x, (size_t)N * h * w * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   // ending + global residual (:271-272)
@@ -1017,16 +1034,21 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   // ---------------- decoders (reverse) ----------------
   for (int i = nd - 1; i >= 0; --i) {
     const float* ext = host_dfeats ? host_dfeats[i] : nullptr;
-    if (ext) {  // gradient injected by the DCPT head into this decoder level's output
+    auto inject = [&]() -> int {  // gradient injected by the DCPT head where the hooked feature was taken
       NXT.s = Sorig[ci ^ 1];  // (a block backward may have pointed the slot at its own pre-cleared slice)
       DCPT_CUDA(cudaMemsetAsync(NXT.s, 0, C * sizeof(float), st));
       DCPT_TRY(grad_prepare_launch(have ? CUR.f : nullptr, ext, NXT.f, NXT.t, NXT.s, N * h * w, C, st));
       ci ^= 1;
       have = true;
+      return 0;
+    };
+    if (ext && p->dec[i] == 0) DCPT_TRY(inject());
+    for (int j = p->dec[i] - 1; j >= 0; --j) {
+      if (ext && j == p->hook_block(i)) DCPT_TRY(inject());  // output of block j of this level
+      if (!have) continue;  // hook pass: the blocks behind the hooked one of the last level receive no gradient (stay zero)
+      DCPT_TRY(block_bwd(p->dec_blks[i][j], pk.dec_pk[i][j], sv.dec_sv[i][j], j > 0 ? sv.dec_out[i][j - 1] : sv.xup[i], h, w));
     }
     DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient at decoder level %d", i);
-    for (int j = p->dec[i] - 1; j >= 0; --j)
-      DCPT_TRY(block_bwd(p->dec_blks[i][j], pk.dec_pk[i][j], sv.dec_sv[i][j], j > 0 ? sv.dec_out[i][j - 1] : sv.xup[i], h, w));
     // CUR = d(xup_i): it is also the gradient of the encoder skip (x = up(x) + enc_skip, :264-265)
     const int lvl = ne - 1 - i;
     DCPT_CUDA(cudaMemcpyAsync(wk.dskip[lvl], CUR.f, (size_t)N * h * w * C * sizeof(float), cudaMemcpyDeviceToDevice, st));

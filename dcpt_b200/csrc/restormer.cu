@@ -54,7 +54,7 @@ __global__ void pack_cols_kernel(const float* __restrict__ w, bf16* __restrict__
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)O * hidp) return;
   const int o = (int)(idx / hidp), c = (int)(idx % hidp);
-  out[idx] = __float2bfloat16_rn(c < hid ? w[(size_t)o * hid + c] : 0.f);
+  out[idx] = OP_FROM_F32(c < hid ? w[(size_t)o * hid + c] : 0.f);
 }
 
 // W_eff[n][o][h*c + j] = sum_i Wout[o][h*c + i] * relu(temp[h] * G[n][h*c+i][h*c+j] / (max(|q_i|, eps) * max(|k_j|, eps)))
@@ -80,8 +80,8 @@ mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, cons
     const float* wr = wout + (size_t)o * d + h * c;
     float acc = 0.f;
     for (int i = 0; i < c; ++i) acc = fmaf(__ldg(wr + i), s_attn[i * (c + 1) + j], acc);
-    out[(size_t)o * d + h * c + j] = __float2bfloat16_rn(acc);
-    if (weffT) weffT[(size_t)n * d * d + (size_t)(h * c + j) * d + o] = __float2bfloat16_rn(acc);  // dgrad operand (training)
+    out[(size_t)o * d + h * c + j] = OP_FROM_F32(acc);
+    if (weffT) weffT[(size_t)n * d * d + (size_t)(h * c + j) * d + o] = OP_FROM_F32(acc);  // dgrad operand (training)
   }
 }
 
@@ -169,9 +169,9 @@ mdta_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, co
   bf16* Bl = BmatLo + (size_t)n * 4 * d * d;
   const int D2 = 2 * d;
   auto put = [&](size_t off, float val) {
-    const bf16 hi = __float2bfloat16_rn(val);
+    const bf16 hi = OP_FROM_F32(val);
     Bn[off] = hi;
-    Bl[off] = __float2bfloat16_rn(val - __bfloat162float(hi));
+    Bl[off] = OP_FROM_F32(val - OP_TO_F32(hi));
   };
   for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
     const int i = idx / c, j = idx - i * c;
@@ -245,7 +245,7 @@ __global__ void pixel_shuffle_cat_kernel(const float* __restrict__ conv, const f
   if (co < Cs) v = __ldg(conv + (((size_t)n * h + (y >> 1)) * w + (x >> 1)) * (4 * Cs) + co * 4 + (y & 1) * 2 + (x & 1));
   else v = __ldg(skip + (size_t)px * Cs + (co - Cs));
   if (out_f32) out_f32[idx] = v;
-  if (out_bf16) out_bf16[idx] = __float2bfloat16_rn(v);
+  if (out_bf16) out_bf16[idx] = OP_FROM_F32(v);
 }
 
 // backward of pixel_shuffle_cat: dcat [N, 2h, 2w, 2Cs] -> dconv bf16 [N, h, w, 4Cs] (PixelShuffle^T), dskip fp32 [N, 2h, 2w, Cs]
@@ -261,7 +261,7 @@ __global__ void pixel_shuffle_cat_bwd_kernel(const float* __restrict__ dcat, bf1
   const long long t = px / W2;
   const int y = (int)(t % H2), n = (int)(t / H2);
   const float v = dcat[idx];
-  if (co < Cs) dconv[(((size_t)n * h + (y >> 1)) * w + (x >> 1)) * (4 * Cs) + co * 4 + (y & 1) * 2 + (x & 1)] = __float2bfloat16_rn(v);
+  if (co < Cs) dconv[(((size_t)n * h + (y >> 1)) * w + (x >> 1)) * (4 * Cs) + co * 4 + (y & 1) * 2 + (x & 1)] = OP_FROM_F32(v);
   else dskip[(size_t)px * Cs + (co - Cs)] = v;
 }
 // backward of pixel_unshuffle: dout [N, H/2, W/2, 4Cc] -> dconv bf16 [N, H, W, Cc]
@@ -276,7 +276,7 @@ __global__ void pixel_unshuffle_bwd_kernel(const float* __restrict__ dout, bf16*
   const long long t = px / W2;
   const int h2 = (int)(t % H2), n = (int)(t / H2);
   const int c = co >> 2, i = (co >> 1) & 1, j = co & 1;
-  dconv[(((size_t)n * H + 2 * h2 + i) * W + 2 * w2 + j) * Cc + c] = __float2bfloat16_rn(dout[idx]);
+  dconv[(((size_t)n * H + 2 * h2 + i) * W + 2 * w2 + j) * Cc + c] = OP_FROM_F32(dout[idx]);
 }
 
 inline unsigned blocks_for(long long total, int threads = 256) { return (unsigned)((total + threads - 1) / threads); }

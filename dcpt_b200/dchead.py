@@ -13,9 +13,8 @@ import torch
 
 from . import lib as _l
 from .ops import _p, _stream, gemm
-from .params import PackedCacheKey
+from .params import PackedCacheKey, fp16_grad_scale
 
-BF = torch.bfloat16
 
 
 def _bottleneck_names(prefix):
@@ -55,8 +54,8 @@ class DCHeadEngine:
         def mat(name):
             w = P(name)
             O, I = w.shape[0], w.shape[1]
-            a = torch.empty(O, I, dtype=BF, device=dev)
-            b = torch.empty(I, O, dtype=BF, device=dev)
+            a = torch.empty(O, I, dtype=_l.operand_dtype(), device=dev)
+            b = torch.empty(I, O, dtype=_l.operand_dtype(), device=dev)
             _l.check(self.lib.dcpt_pack_matrix(_p(w), _p(a), O, I, 0, _stream()), "pack_matrix")
             _l.check(self.lib.dcpt_pack_matrix(_p(w), _p(b), O, I, 1, _stream()), "pack_matrix")
             pk[name] = (a, b)
@@ -64,8 +63,8 @@ class DCHeadEngine:
         def conv3(name):
             w = P(name)
             O, I = w.shape[0], w.shape[1]
-            a = torch.empty(self.lib.dcpt_conv3x3_packed_elems(O, I, 0), dtype=BF, device=dev)
-            b = torch.empty(self.lib.dcpt_conv3x3_packed_elems(O, I, 1), dtype=BF, device=dev)
+            a = torch.empty(self.lib.dcpt_conv3x3_packed_elems(O, I, 0), dtype=_l.operand_dtype(), device=dev)
+            b = torch.empty(self.lib.dcpt_conv3x3_packed_elems(O, I, 1), dtype=_l.operand_dtype(), device=dev)
             _l.check(self.lib.dcpt_conv3x3_pack(_p(w), _p(a), O, I, 0, _stream()), "conv3x3_pack")
             _l.check(self.lib.dcpt_conv3x3_pack(_p(w), _p(b), O, I, 1, _stream()), "conv3x3_pack")
             pk[name] = (a, b)
@@ -139,7 +138,7 @@ class DCHeadEngine:
         for i, f in enumerate(feats):
             N, H, W, Cc = f.shape
             assert Cc == self.dims[i] and f.dtype == torch.float32 and f.is_contiguous()
-            zin = torch.empty(N * H * W, Cc, dtype=BF, device=f.device)
+            zin = torch.empty(N * H * W, Cc, dtype=_l.operand_dtype(), device=f.device)
             _l.check(self.lib.dcpt_mix_fwd(_p(z), _p(f), _p(mw[i:i + 1]), _p(zin), f.numel(), _stream()), "mix_fwd")
             x, blocks = zin, []
             for j in range(self.nb):
@@ -148,7 +147,7 @@ class DCHeadEngine:
             wname = f"downsample_layers.{i}.0.weight"
             t = gemm(x, pk[wname][0])
             Cn = t.shape[1]
-            y = torch.empty(N * (H // 2) * (W // 2), Cn, dtype=BF, device=f.device)
+            y = torch.empty(N * (H // 2) * (W // 2), Cn, dtype=_l.operand_dtype(), device=f.device)
             _l.check(self.lib.dcpt_maxpool2_relu_fwd(_p(t), _p(y), N, H // 2, W // 2, Cn, _stream()), "maxpool_fwd")
             ctx["stages"].append((blocks, x, t, (N, H, W, Cc, Cn)))
             z = y
@@ -181,6 +180,9 @@ class DCHeadEngine:
         scratch = torch.empty(self.lib.dcpt_conv3x3_packed_elems(maxw, maxw, 0), dtype=torch.float32, device=dev)
         N, h, w, Cn = ctx["shp"]
         dx = torch.empty(N * h * w, Cn, dtype=torch.float32, device=dev)
+        sc = fp16_grad_scale([dlogits])                    # IEEE-half operand build only (params.py)
+        if sc is not None:
+            dlogits = dlogits * sc[0]
         _l.check(self.lib.dcpt_meanpool_fc_bwd(_p(dlogits.contiguous().float()), _p(ctx["pooled"]), _p(params[self.index["fc.weight"]]),
                                                _p(grads[self.index["fc.weight"]]), _p(grads[self.index["fc.bias"]]), _p(dx), N, h * w,
                                                Cn, self.k, _stream()), "meanpool_fc_bwd")
@@ -204,6 +206,9 @@ class DCHeadEngine:
             # dx (= d z_in) is also the gradient of the previous stage's pooled output (z = prev + mw * feat)
         mw = ctx["mw"]
         grads[0].copy_((mw * (dmw - (dmw * mw).sum())).view(grads[0].shape))   # softmax backward on len(dims) scalars
+        if sc is not None:
+            flat.mul_(sc[1])
+            torch._foreach_mul_(dfeats, sc[1])
         if self.grad_sync is not None:
             self.grad_sync(flat)
         return dfeats, grads

@@ -6,6 +6,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcpt_sm100.so")
+LIB_PATH_FP16 = os.path.join(HERE, "libdcpt_sm100_fp16.so")
 
 _lib = None
 
@@ -35,6 +36,7 @@ _PP = C.POINTER(C.c_void_p)
 # tests/test_abi_cpu.py checks the two stay in sync.
 PROTOTYPES = {
     "dcpt_abi_version": (_I, []),
+    "dcpt_operand_dtype": (_I, []),
     "dcpt_last_error": (C.c_char_p, []),
     "dcpt_launch_count": (_LL, []),
     "dcpt_prof_enable": (_I, [_I]),
@@ -53,6 +55,7 @@ PROTOTYPES = {
     "dcpt_nafnet_create": (_VP, [_I, _I, _I, C.POINTER(_I), _I, C.POINTER(_I), _I]),
     "dcpt_nafnet_destroy": (None, [_VP]),
     "dcpt_nafnet_set_tlc": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), _I]),
+    "dcpt_nafnet_set_hook_blocks": (_I, [_VP, C.POINTER(_I), _I]),
     "dcpt_nafnet_num_params": (_I, [_VP]),
     "dcpt_nafnet_param_shape": (_LL, [_VP, _I, C.POINTER(_I)]),
     "dcpt_nafnet_packed_bytes": (_SZ, [_VP]),
@@ -114,7 +117,8 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or os.getenv("DCPT_LIB") or LIB_PATH  # DCPT_LIB: debug builds (libdcpt_sm100_trace.so)
+    # DCPT_LIB: debug builds (libdcpt_sm100_trace.so); DCPT_OPERAND=fp16: the parity build with IEEE-half operands
+    path = path or os.getenv("DCPT_LIB") or (LIB_PATH_FP16 if os.getenv("DCPT_OPERAND", "bf16").lower() == "fp16" else LIB_PATH)
     if not os.path.exists(path) and os.getenv("BASICSR_JIT") == "True":
         from .build import build
         build()
@@ -130,6 +134,12 @@ def load_library(path=None):
         raise DcptError(f"ABI version mismatch: library {lib.dcpt_abi_version()} != binding 1")
     _lib = lib
     return lib
+
+
+def operand_dtype():
+    """torch dtype of the 16-bit operand tensors of the loaded library (bf16 by default, fp16 with DCPT_OPERAND=fp16)."""
+    import torch
+    return torch.float16 if load_library().dcpt_operand_dtype() == 1 else torch.bfloat16
 
 
 def check(rc, what=""):

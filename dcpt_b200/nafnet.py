@@ -13,7 +13,7 @@ import torch
 
 from . import lib as _l
 from .ops import _p, _stream
-from .params import LRUCache, PackedCacheKey
+from .params import LRUCache, PackedCacheKey, fp16_grad_scale
 
 
 class NAFNetEngine:
@@ -46,6 +46,16 @@ class NAFNetEngine:
         self._seen_nograd = LRUCache(cap=64)
         self.grad_sync = None      # set by dcpt_b200.dist.FlatGradDataParallel: callable(flat fp32 gradient buffer)
         self.tlc = False
+
+    def set_hook_blocks(self, idx):
+        """idx[i]: block of decoder level i whose output is the hooked feature (-1 = the level's output)."""
+        idx = tuple(int(v) for v in idx)
+        if idx == getattr(self, "_hook_blocks", None):
+            return
+        arr = (C.c_int * max(len(idx), 1))(*idx)
+        _l.check(self.lib.dcpt_nafnet_set_hook_blocks(self.plan, arr, len(idx)), "nafnet_set_hook_blocks")
+        self._hook_blocks = idx
+        self._gslots.clear()            # captured graphs baked the old feature taps in
 
     def set_tlc(self, kernels):
         """kernels: [(kh, kw)] per resolution level (0 = full resolution .. n_enc) - NAFNet's test-time local converter."""
@@ -146,9 +156,26 @@ class NAFNetEngine:
             dfp = _l.ptr_array([0 if d is None else d.data_ptr() for d in dfeats])
         if dout is not None:
             dout = dout.contiguous().float()
+        sc = fp16_grad_scale([dout] + (dfeats or []))            # IEEE-half operand build only (params.py)
+        acc_into = None
+        if sc is not None:
+            if dout is not None:
+                dout = dout * sc[0]
+            if dfp is not None:
+                dfeats = [None if d is None else d * sc[0] for d in dfeats]
+                dfp = _l.ptr_array([0 if d is None else d.data_ptr() for d in dfeats])
+            if flat is None:                                     # caller's buffers accumulate: scale back a private copy
+                acc_into = grads
+                flat, grads = self.alloc_flat_grads(params)
+                gp = _l.ptr_array([g.data_ptr() for g in grads])
         packed = self.packed_for(params)
         _l.check(self.lib.dcpt_nafnet_bwd(self.plan, pp, _p(packed), _p(saved), _p(inp), _p(dout), dfp, gp, _p(work), N, H,
                                           W, _stream()), "nafnet_bwd")
+        if sc is not None:
+            flat.mul_(sc[1])
+            if acc_into is not None:
+                torch._foreach_add_(acc_into, grads)
+                return acc_into
         if flat is not None and self.grad_sync is not None:
             self.grad_sync(flat)            # data-parallel wrapper (dcpt_b200.dist.FlatGradDataParallel): one all-reduce
         return grads
@@ -277,16 +304,21 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
         slot.gp = _l.ptr_array([g.data_ptr() for g in slot.grads])
         slot.shapes = [(o, p.numel(), p.shape) for o, p in zip(slot.offs, params)]
     mask = (dout is not None, tuple(d is not None for d in dfeats) if dfeats else None)
+    sc = fp16_grad_scale([dout] + list(dfeats or []))            # IEEE-half operand build only (params.py)
     if dout is not None:
         if slot.dout is None:
             slot.dout = torch.empty_like(slot.inp)
         slot.dout.copy_(dout)
+        if sc is not None:
+            slot.dout.mul_(sc[0])
     if dfeats and any(d is not None for d in dfeats):
         if slot.dfeats is None:
             slot.dfeats = [torch.empty_like(f) for f in slot.feats]
         for s_, d in zip(slot.dfeats, dfeats):
             if d is not None:
                 s_.copy_(d)
+                if sc is not None:
+                    s_.mul_(sc[0])
     if slot.work is None:
         slot.work = torch.empty(eng.lib.dcpt_nafnet_workspace_bytes(eng.plan, N, H, W), dtype=torch.uint8, device=dev)
     work = slot.work
@@ -310,6 +342,8 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
     else:
         slot.bgraphs[mask].replay()
     slot.release()
+    if sc is not None:
+        slot.flat.mul_(sc[1])
     if eng.grad_sync is not None:
         eng.grad_sync(slot.flat)            # data-parallel wrapper: ONE mean all-reduce of the flat gradient buffer
     flat = slot.flat.clone()            # autograd owns the returned gradients; the slot's buffer is rewritten next step

@@ -35,7 +35,7 @@ def layernorm2d_fwd(x, weight, bias, eps=1e-6):
     """x fp32 [M, C] -> (out bf16 [M, C], stats fp32 [M, 2]).  nafnet_arch.py:27-35."""
     _need_cuda(x, weight, bias)
     M, Cc = x.shape
-    out = torch.empty(M, Cc, dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(M, Cc, dtype=_l.operand_dtype(), device=x.device)
     stats = torch.empty(M, 2, dtype=torch.float32, device=x.device)
     _l.check(_lib().dcpt_layernorm2d_fwd(_p(x), _p(weight), _p(bias), _p(out), _p(stats), M, Cc, eps, _stream()),
              "layernorm2d_fwd")
@@ -47,7 +47,7 @@ def layernorm2d_bwd(dn, x, stats, weight, dres=None, want_mirror=True):
     _need_cuda(dn, x, stats, weight, dres)
     M, Cc = x.shape
     dx = torch.empty_like(x)
-    dxb = torch.empty(M, Cc, dtype=torch.bfloat16, device=x.device) if want_mirror else None
+    dxb = torch.empty(M, Cc, dtype=_l.operand_dtype(), device=x.device) if want_mirror else None
     dw = torch.zeros(Cc, dtype=torch.float32, device=x.device)
     db = torch.zeros_like(dw)
     cs = torch.zeros_like(dw)
@@ -56,7 +56,7 @@ def layernorm2d_bwd(dn, x, stats, weight, dres=None, want_mirror=True):
     return dx, dxb, dw, db, cs
 
 
-def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, resid=None, out_dtype=torch.bfloat16, splits=1, accumulate_into=None,
+def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, resid=None, out_dtype=None, splits=1, accumulate_into=None,
          impl=0):
     """D[M,N] = A * B^T with bf16 operands.  K-major: A [M,K], B [N,K]; MN-major: A [K,M], B [K,N]."""
     _need_cuda(A, B)
@@ -74,7 +74,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, bias=None, resid=None, out_dtype=torch
     elif out_dtype == torch.float32:
         out_f32 = torch.empty(M, N, dtype=torch.float32, device=A.device)
     else:
-        out_bf16 = torch.empty(M, N, dtype=torch.bfloat16, device=A.device)
+        out_bf16 = torch.empty(M, N, dtype=_l.operand_dtype(), device=A.device)
     _l.check(_lib().dcpt_gemm_bf16(_p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), M, N, K, _p(out_f32),
                                    _p(out_bf16), N, _p(bias), _p(resid), splits, acc, impl, _stream()), "gemm_bf16")
     return out_f32 if out_f32 is not None else out_bf16
@@ -89,7 +89,7 @@ def dwconv3x3_gate_fwd(u, weight, bias):
     _need_cuda(u, weight, bias)
     N, H, W, C2 = u.shape
     Cc = C2 // 2
-    g = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device=u.device)
+    g = torch.empty(N, H, W, Cc, dtype=_l.operand_dtype(), device=u.device)
     pool = torch.zeros(N, Cc, dtype=torch.float32, device=u.device)
     _l.check(_lib().dcpt_dwconv3x3_gate_fwd(_p(u), _p(weight), _p(bias), _p(g), _p(pool), N, H, W, Cc, _stream()),
              "dwconv3x3_gate_fwd")
@@ -121,7 +121,7 @@ class NAFBlockOp:
         N, H, W, Cc = x.shape
         assert Cc == self.C and x.dtype == torch.float32
         out = torch.empty_like(x)
-        mirror = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_mirror else None
+        mirror = torch.empty(x.shape, dtype=_l.operand_dtype(), device=x.device) if want_mirror else None
         saved = torch.empty(_lib().dcpt_nafblock_saved_bytes(N, H, W, Cc), dtype=torch.uint8, device=x.device)
         _l.check(_lib().dcpt_nafblock_fwd(self._pp, _p(self.packed), _p(x), _p(out), _p(mirror), _p(saved), N, H, W, Cc,
                                           _stream()), "nafblock_fwd")
@@ -131,7 +131,7 @@ class NAFBlockOp:
         N, H, W, Cc = x.shape
         dev = x.device
         dout = dout.contiguous()
-        dout_b = dout.to(torch.bfloat16)
+        dout_b = dout.to(_l.operand_dtype())
         dout_cs = dout.reshape(-1, Cc).sum(0).float().contiguous()
         dx = torch.empty_like(x)
         grads = [torch.zeros_like(p) for p in self.params]

@@ -120,3 +120,17 @@ class LRUCache:
 
     def clear(self):
         self.d.clear()
+
+
+def fp16_grad_scale(tensors, target=256.0):
+    """IEEE-half operand build (DCPT_OPERAND=fp16) only: the gradients entering a backward pass are tiny (a mean L1 loss over
+    16x3x256x256 pixels hands out +-3e-7, below fp16's normal range), so the pass runs on gradients multiplied by a power of two
+    that brings the largest incoming magnitude to ~`target`, and its results are multiplied back (the backward is linear in the
+    incoming gradient; powers of two are exact).  Computed on the device, no host sync.  Returns (scale, 1/scale) 0-dim
+    tensors, or None for the bf16 build (8 exponent bits: no scaling needed)."""
+    ts = [t for t in tensors if t is not None]
+    if not ts or _l.operand_dtype() != torch.float16:
+        return None
+    amax = torch.stack([t.detach().abs().max().float() for t in ts]).max().clamp_min(1e-30)
+    k = torch.floor(torch.log2(target / amax))
+    return torch.exp2(k), torch.exp2(-k)

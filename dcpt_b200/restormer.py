@@ -14,7 +14,7 @@ import torch
 
 from . import lib as _l
 from .ops import _p, _stream
-from .params import LRUCache, PackedCacheKey
+from .params import LRUCache, PackedCacheKey, fp16_grad_scale
 
 
 class RestormerEngine:
@@ -184,8 +184,16 @@ class RestormerEngine:
             dfp = _l.ptr_array([0 if d is None else d.data_ptr() for d in dfe])
         if dout is None and dfp is None:
             return grads                                  # nothing reached this forward: all-zero gradients
+        sc = fp16_grad_scale([dout] + (dfe or []))        # IEEE-half operand build only (params.py)
+        if sc is not None:
+            dout = None if dout is None else dout * sc[0]
+            if dfp is not None:
+                dfe = [None if d is None else d * sc[0] for d in dfe]
+                dfp = _l.ptr_array([0 if d is None else d.data_ptr() for d in dfe])
         _l.check(self.lib.dcpt_restormer_bwd(self.plan, pp, _p(self.packed_for(params)), _p(saved), _p(inp), _p(dout), dfp,
                                              gp, _p(bwork), N, H, W, _stream()), "restormer_bwd")
+        if sc is not None:
+            flat.mul_(sc[1])
         if self.grad_sync is not None:
             self.grad_sync(flat)
         return grads
@@ -285,16 +293,21 @@ def _train_graph_backward(eng, params, slot, dout, dfeats):
         slot.gp = _l.ptr_array([slot.flat[o:o + n].data_ptr() for o, n, _ in slot.shapes])
     has_df = bool(dfeats) and any(d is not None for d in dfeats)
     mask = (dout is not None, tuple(d is not None for d in dfeats) if has_df else None)
+    sc = fp16_grad_scale([dout] + (list(dfeats) if has_df else []))   # IEEE-half operand build only (params.py)
     if mask[0]:
         if slot.dout is None:
             slot.dout = torch.empty_like(slot.inp)
         slot.dout.copy_(dout)
+        if sc is not None:
+            slot.dout.mul_(sc[0])
     if has_df:
         if slot.dfeats is None:
             slot.dfeats = [torch.empty_like(f) for f in slot.feats]
         for s_, d in zip(slot.dfeats, dfeats):
             if d is not None:
                 s_.copy_(d)
+                if sc is not None:
+                    s_.mul_(sc[0])
     if not mask[0] and not has_df:
         slot.release()
         flat = torch.zeros_like(slot.flat)                 # nothing reached this forward: all-zero gradients
@@ -313,6 +326,8 @@ def _train_graph_backward(eng, params, slot, dout, dfeats):
                                             N, H, W, _stream()), "restormer_bwd")
     _run_or_replay(eng, slot, mask, run)
     slot.release()
+    if sc is not None:
+        slot.flat.mul_(sc[1])
     if eng.grad_sync is not None:
         eng.grad_sync(slot.flat)                           # data-parallel wrapper: ONE mean all-reduce of the flat buffer
     flat = slot.flat.clone()                               # autograd owns the returned gradients; the slot's buffer is reused

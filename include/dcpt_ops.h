@@ -40,6 +40,10 @@ extern "C" {
 typedef void* dcpt_stream_t; /* cudaStream_t */
 
 int dcpt_abi_version(void);
+/* Storage type of the 16-bit tensor-core operands (every `*_bf16` argument and the packed weights) this library was built for:
+ * 0 = bfloat16 (libdcpt_sm100.so, the fast path), 1 = IEEE half (libdcpt_sm100_fp16.so, built with -DDCPT_OPERAND_FP16: the
+ * parity mode - 8x smaller operand rounding; callers pass fp16 tensors wherever the header says bf16). */
+int dcpt_operand_dtype(void);
 const char* dcpt_last_error(void);
 
 /* Instrumentation for bench.py (no reference counterpart; the reference's SRModel.nondist_profile,
@@ -154,6 +158,11 @@ void dcpt_nafnet_destroy(dcpt_nafnet_plan* plan);
  * input (arch_util.py:341-347, 450-455).  A level whose map fits inside its kernel keeps the global mean (:352-353); otherwise
  * the pooled vector becomes a per-pixel replicate-padded box mean (:379-396).  Inference only; n_levels = 0 switches it off. */
 int dcpt_nafnet_set_tlc(dcpt_nafnet_plan* plan, const int* kh, const int* kw, int n_levels);
+/* Which block of decoder level i (0-based, < dec_blk_nums[i]) delivers host_feats[i] in dcpt_nafnet_fwd and receives
+ * host_dfeats[i] in dcpt_nafnet_bwd; -1 (default) = the level's last block, i.e. the output of `decoder{i}`.  The reference's
+ * DCPTModel hooks the modules whose name contains hook_names and has exactly one dot (models/
+ * degradation_classification_pretrain_model.py:64-67): `decoder{i}.0`, the FIRST block, for an unwrapped NAFNetBaseline. */
+int dcpt_nafnet_set_hook_blocks(dcpt_nafnet_plan* plan, const int* block_idx, int n_levels);
 int dcpt_nafnet_num_params(const dcpt_nafnet_plan* plan);
 /* shape of parameter i as up to 4 dims (unused dims = 1); returns number of elements */
 long long dcpt_nafnet_param_shape(const dcpt_nafnet_plan* plan, int i, int dims[4]);

@@ -12,6 +12,9 @@ import os
 import numpy as np
 import pytest
 import torch
+
+from dcpt_b200.lib import operand_dtype as OPD  # bf16 by default; fp16 for the DCPT_OPERAND=fp16 parity build
+from tol import FP16, report, tol  # noqa: F401
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
@@ -43,22 +46,22 @@ def _p(t):
 def test_conv3x3_fwd_dgrad_wgrad(lib, N, H, W, Cin, Cout):
     from dcpt_b200.lib import check
     g = torch.Generator(device="cuda").manual_seed(Cin + Cout + H)
-    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(OPD())
     w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
-    wq = w.bfloat16().float()
-    wp = torch.empty(lib.dcpt_conv3x3_packed_elems(Cout, Cin, 0), dtype=torch.bfloat16, device="cuda")
-    wd = torch.empty(lib.dcpt_conv3x3_packed_elems(Cout, Cin, 1), dtype=torch.bfloat16, device="cuda")
+    wq = w.to(OPD()).float()
+    wp = torch.empty(lib.dcpt_conv3x3_packed_elems(Cout, Cin, 0), dtype=OPD(), device="cuda")
+    wd = torch.empty(lib.dcpt_conv3x3_packed_elems(Cout, Cin, 1), dtype=OPD(), device="cuda")
     check(lib.dcpt_conv3x3_pack(_p(w), _p(wp), Cout, Cin, 0, _st()), "pack")
     check(lib.dcpt_conv3x3_pack(_p(w), _p(wd), Cout, Cin, 1, _st()), "pack")
     # forward
     y32 = torch.empty(N, H, W, Cout, device="cuda")
-    y16 = torch.empty(N, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+    y16 = torch.empty(N, H, W, Cout, dtype=OPD(), device="cuda")
     check(lib.dcpt_conv3x3_fwd(_p(x), _p(wp), _p(y16), _p(y32), N, H, W, Cin, Cout, _st()), "conv fwd")
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wq, padding=1).permute(0, 2, 3, 1)
     assert rel(y32, ref) < 3e-5
     assert rel(y16.float(), ref) < 4e-3
     # dgrad = conv of dy with the flipped/transposed operand
-    dy = torch.randn(N, H, W, Cout, device="cuda", generator=g).bfloat16()
+    dy = torch.randn(N, H, W, Cout, device="cuda", generator=g).to(OPD())
     dx = torch.empty(N, H, W, Cin, device="cuda")
     check(lib.dcpt_conv3x3_fwd(_p(dy), _p(wd), None, _p(dx), N, H, W, Cout, Cin, _st()), "conv dgrad")
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
@@ -76,10 +79,10 @@ def test_conv3x3_fwd_dgrad_wgrad(lib, N, H, W, Cin, Cout):
 def test_ln_act(lib, M, C, relu, use_res):
     from dcpt_b200.lib import check
     g = torch.Generator().manual_seed(C)
-    x = (torch.randn(M, C, generator=g) * 1.3 + 0.2).bfloat16()
-    res = torch.randn(M, C, generator=g).bfloat16() if use_res else None
+    x = (torch.randn(M, C, generator=g) * 1.3 + 0.2).to(OPD())
+    res = torch.randn(M, C, generator=g).to(OPD()) if use_res else None
     w, b = 1 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
-    dy = torch.randn(M, C, generator=g).bfloat16()
+    dy = torch.randn(M, C, generator=g).to(OPD())
     xr = x.float().requires_grad_(True)
     wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     rr = res.float().requires_grad_(True) if use_res else None
@@ -88,12 +91,12 @@ def test_ln_act(lib, M, C, relu, use_res):
         y = y + rr
     if relu:
         y = F.relu(y)
-    xc, yc = x.cuda(), torch.empty(M, C, dtype=torch.bfloat16, device="cuda")
+    xc, yc = x.cuda(), torch.empty(M, C, dtype=OPD(), device="cuda")
     wc, bc, rc, dyc = w.cuda(), b.cuda(), (res.cuda() if use_res else None), dy.float().cuda()   # keep device copies alive
     stats = torch.empty(M, 2, device="cuda")
     check(lib.dcpt_ln_act_fwd(_p(xc), _p(wc), _p(bc), _p(rc), _p(yc), _p(stats), M, C, relu, 1e-6, _st()), "ln_act_fwd")
     assert rel(yc.float(), y) < 4e-3
-    dx = torch.empty(M, C, dtype=torch.bfloat16, device="cuda")
+    dx = torch.empty(M, C, dtype=OPD(), device="cuda")
     dres = torch.empty(M, C, dtype=torch.float32, device="cuda") if use_res else None
     dw, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     check(lib.dcpt_ln_act_bwd(_p(dyc), _p(yc), _p(xc), _p(stats), _p(wc), _p(dx), _p(dres), _p(dw), _p(db), M, C, relu, _st()),
@@ -113,12 +116,12 @@ def test_maxpool_mix_meanpool(lib):
     from dcpt_b200.lib import check
     g = torch.Generator().manual_seed(0)
     N, Ho, Wo, Cc, K = 2, 5, 7, 24, 5
-    x = torch.randn(N, 2 * Ho, 2 * Wo, Cc, generator=g).bfloat16()
+    x = torch.randn(N, 2 * Ho, 2 * Wo, Cc, generator=g).to(OPD())
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     y = F.relu(F.max_pool2d(xr, 2, 2))
-    dy = torch.randn(N, Ho, Wo, Cc, generator=g).bfloat16()
+    dy = torch.randn(N, Ho, Wo, Cc, generator=g).to(OPD())
     y.backward(dy.float().permute(0, 3, 1, 2))
-    yc = torch.empty(N, Ho, Wo, Cc, dtype=torch.bfloat16, device="cuda")
+    yc = torch.empty(N, Ho, Wo, Cc, dtype=OPD(), device="cuda")
     xg, dyg = x.cuda(), dy.float().cuda()
     check(lib.dcpt_maxpool2_relu_fwd(_p(xg), _p(yc), N, Ho, Wo, Cc, _st()), "maxpool")
     assert torch.equal(yc.cpu().float(), y.detach().permute(0, 2, 3, 1))
@@ -126,20 +129,20 @@ def test_maxpool_mix_meanpool(lib):
     check(lib.dcpt_maxpool2_relu_bwd(_p(xg), _p(dyg), _p(dxc), N, Ho, Wo, Cc, _st()), "maxpool bwd")
     assert rel(dxc.float(), xr.grad.permute(0, 2, 3, 1)) < 1e-6
     # mix
-    prev = torch.randn(N * Ho * Wo, Cc, generator=g).bfloat16()
+    prev = torch.randn(N * Ho * Wo, Cc, generator=g).to(OPD())
     feat = torch.randn(N, Ho, Wo, Cc, generator=g)
     mw = torch.tensor([0.37])
-    z = torch.empty(N * Ho * Wo, Cc, dtype=torch.bfloat16, device="cuda")
+    z = torch.empty(N * Ho * Wo, Cc, dtype=OPD(), device="cuda")
     prevg, featg, mwg = prev.cuda(), feat.cuda(), mw.cuda()
     check(lib.dcpt_mix_fwd(_p(prevg), _p(featg), _p(mwg), _p(z), feat.numel(), _st()), "mix")
     assert rel(z.float(), prev.float() + 0.37 * feat.reshape(-1, Cc)) < 4e-3
-    dz = torch.randn(N * Ho * Wo, Cc, generator=g).bfloat16()
+    dz = torch.randn(N * Ho * Wo, Cc, generator=g).to(OPD())
     dfeat, dmw, dzg = torch.empty_like(feat, device="cuda"), torch.zeros(1, device="cuda"), dz.float().cuda()
     check(lib.dcpt_mix_bwd(_p(dzg), _p(featg), _p(mwg), _p(dfeat), _p(dmw), feat.numel(), _st()), "mix bwd")
     assert rel(dfeat, 0.37 * dz.float().reshape(feat.shape)) < 1e-6
     assert abs(float(dmw) - float((dz.float() * feat.reshape(-1, Cc)).sum())) < 1e-3 * float(dz.float().abs().sum())
     # mean pool + fc
-    xm = torch.randn(N, Ho * Wo, Cc, generator=g).bfloat16()
+    xm = torch.randn(N, Ho * Wo, Cc, generator=g).to(OPD())
     w, b = torch.randn(K, Cc, generator=g), torch.randn(K, generator=g)
     pooled, logits = torch.empty(N, Cc, device="cuda"), torch.empty(N, K, device="cuda")
     xmg, wg, bg = xm.cuda(), w.cuda(), b.cuda()
@@ -215,7 +218,7 @@ def test_dchead_golden(golden_dir):
     dlogits = (torch.softmax(logits, 1) - F.one_hot(labels.cuda(), 5).float()) / logits.shape[0]   # d CE(mean) / d logits
     dfeats, grads = eng.backward(params, ctx, dlogits)
     # oracle on the same branch, same storage roundings
-    lh = {k: (v.bfloat16().float() if v.dim() == 4 else v).clone().requires_grad_(True) for k, v in sd.items()}
+    lh = {k: (v.to(OPD()).float() if v.dim() == 4 else v).clone().requires_grad_(True) for k, v in sd.items()}
     fe = [f.clone().requires_grad_(True) for f in feats_cpu]
     o_logits = D.dchead_fwd(fe, lh, q=bf16_ste, acts=ReplayActs(ctx, dims, 2))
     assert rel(logits, o_logits) < 4e-3
@@ -227,6 +230,23 @@ def test_dchead_golden(golden_dir):
           (max(errs.values()), float(np.median(list(errs.values()))), max(rel(g, z["g." + k]) for k, g in zip(eng.names, grads))))
     assert max(errs.values()) < 4e-2, {k: v for k, v in errs.items() if v > 2e-2}
     assert float(np.median(list(errs.values()))) < 1.5e-2
+    # Against the reference's own fp32 golden gradients (no replay): per parameter group
+    eg = {k: rel(g, z["g." + k]) for k, g in zip(eng.names, grads)}
+    groups = {}
+    for k, v in eg.items():
+        gname = ".".join(k.split(".")[:2]) if k[0] in "bl" else k.split(".")[0]
+        groups.setdefault(gname, []).append(v)
+    for gname, vs in groups.items():
+        report(f"DC head grads vs fp32 golden [{gname}]", worst=max(vs), median=float(np.median(vs)))
+    # Asserted where few ReLU / max-pool decisions lie downstream, so that flipped decisions cannot dominate:
+    # the classifier and the last stage.  Earlier stages sit behind up to 24 ReLU layers: every 16-bit rounding of an
+    # activation near zero flips a decision of the piecewise-linear network, and their deviation is the reported, branch-
+    # dependent figure above (bf16 build 0.16-0.65; the replayed-branch comparison above is the kernel check for them).
+    assert max(groups["fc"]) < tol(1e-2, 1e-3), groups["fc"]   # measured 2.9e-3 / 2.6e-4
+    assert max(groups["last_stage.0"] + groups["last_stage.1"]) < tol(8e-2, 3e-2)   # measured 4.0e-2 (bf16 build) / 1.8e-2 (fp16 build)
+    report("DC head vs fp32 golden", logits=rel(logits, z["logits"]),
+           dfeats_worst=max(rel(dfeats[i].permute(0, 3, 1, 2), torch.from_numpy(z[f"dfeat{i}"])) for i in range(len(dims)))
+           if "dfeat0" in z.files else float("nan"))
 
 
 def test_dcpt_pretrain_step():

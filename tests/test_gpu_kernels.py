@@ -13,6 +13,8 @@ import numpy as np
 import pytest
 import torch
 
+from dcpt_b200.lib import operand_dtype as OPD  # bf16 by default; fp16 for the DCPT_OPERAND=fp16 parity build
+
 pytestmark = pytest.mark.gpu
 
 from oracle import nafnet_oracle as O  # noqa: E402
@@ -31,7 +33,7 @@ def ops():
 
 
 def bf(t):
-    return t.to(torch.bfloat16)
+    return t.to(OPD())
 
 
 # ------------------------------------------------------------------ GEMM engine
@@ -53,7 +55,7 @@ def test_gemm_store(ops, impl, M, N, K):
     out = ops.gemm(A, B, bias=bias, resid=resid, out_dtype=torch.float32, impl=impl)
     assert rel(out, ref + bias + resid) < 2e-5
     out = ops.gemm(A, B, bias=bias, impl=impl)
-    assert out.dtype == torch.bfloat16 and rel(out.float(), ref + bias) < 4e-3
+    assert out.dtype == OPD() and rel(out.float(), ref + bias) < 4e-3
 
 
 @pytest.mark.parametrize("M,N,K,mirror", [(1000, 512, 512, False), (16384, 512, 512, False), (4099, 256, 256, True), (33000, 128, 64, False),
@@ -73,9 +75,9 @@ def test_gemm_store_fused_layernorm(ops, M, N, K, mirror):
     lw = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
     lb = 0.3 * torch.randn(N, device="cuda", generator=g)
     out = torch.full((M, N), float("nan"), device="cuda")
-    ln = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ln = torch.full((M, N), float("nan"), device="cuda", dtype=OPD())
     stats = torch.full((M, 2), float("nan"), device="cuda")
-    mir = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if mirror else None
+    mir = torch.empty(M, N, device="cuda", dtype=OPD()) if mirror else None
     d = GemmDesc()
     for k, v in dict(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=out, out_bf16=mir, ldo=N, bias=bias, resid=resid,
                      ldr=N, ln_weight=lw, ln_bias=lb, ln_out=ln, ld_ln=N, ln_stats=stats, ln_eps=1e-6).items():
@@ -109,7 +111,7 @@ def test_gemm_store_both_outputs(ops, M, N, K):
     bias = torch.randn(N, device="cuda", generator=g)
     resid = torch.randn(M, N, device="cuda", generator=g)
     o32 = torch.empty(M, N, device="cuda")
-    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o16 = torch.empty(M, N, device="cuda", dtype=OPD())
     d = GemmDesc()
     for k, v in dict(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=o32, out_bf16=o16, ldo=N, bias=bias,
                      resid=resid, ldr=N).items():
@@ -165,8 +167,8 @@ def test_gemm_gate_epilogue(ops, impl, M, C):
     p = torch.arange(2 * C, device="cuda")
     orig = ((p % 16) // 8) * C + (p // 16) * 8 + (p % 8)  # packed row -> original out-channel
     W4p, b4p = W4[orig].contiguous(), b4[orig].contiguous()
-    x4 = torch.empty(M, 2 * C, dtype=torch.bfloat16, device="cuda")
-    sg = torch.empty(M, C, dtype=torch.bfloat16, device="cuda")
+    x4 = torch.empty(M, 2 * C, dtype=OPD(), device="cuda")
+    sg = torch.empty(M, C, dtype=OPD(), device="cuda")
     d = _desc(ops, M=M, N=2 * C, K=C, A=n2, lda=C, B=W4p, ldb=C, splits=1, epilogue=1, out_bf16=x4, ldo=2 * C, bias=b4p,
               out2_bf16=sg, ldo2=C, C=C)
     ops.gemm_ex(d, impl)
@@ -186,8 +188,8 @@ def test_gemm_gate32_epilogue(ops, M, C):
     p = torch.arange(2 * C, device="cuda")
     orig = ((p % 64) // 32) * C + (p // 64) * 32 + (p % 32)  # packed row -> original out-channel
     W4p, b4p = W4[orig].contiguous(), b4[orig].contiguous()
-    x4 = torch.full((M, 2 * C), float("nan"), dtype=torch.bfloat16, device="cuda")
-    sg = torch.full((M, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    x4 = torch.full((M, 2 * C), float("nan"), dtype=OPD(), device="cuda")
+    sg = torch.full((M, C), float("nan"), dtype=OPD(), device="cuda")
     d = _desc(ops, M=M, N=2 * C, K=C, A=n2, lda=C, B=W4p, ldb=C, splits=1, epilogue=7, out_bf16=x4, ldo=2 * C, bias=b4p,
               out2_bf16=sg, ldo2=C, C=C)
     ops.gemm_ex(d, 0)
@@ -204,7 +206,7 @@ def test_gemm_gate_bwd_epilogue(ops, impl, M, C):
     dout = bf(torch.randn(M, C, device="cuda", generator=g))
     W5t = bf(torch.randn(C, C, device="cuda", generator=g) / C ** 0.5)  # [in, out]
     x4 = bf(torch.randn(M, 2 * C, device="cuda", generator=g))
-    dx4 = torch.empty(M, 2 * C, dtype=torch.bfloat16, device="cuda")
+    dx4 = torch.empty(M, 2 * C, dtype=OPD(), device="cuda")
     d = _desc(ops, M=M, N=C, K=C, A=dout, lda=C, B=W5t, ldb=C, splits=1, epilogue=2, out_bf16=dx4, ldo=2 * C, aux_bf16=x4,
               ldaux=2 * C, C=C)
     ops.gemm_ex(d, impl)
@@ -227,7 +229,7 @@ def test_gemm_pixshuf_epilogue(ops, impl, N, H, W, Cin):
     orig = (p % Cseg) * 4 + p // Cseg
     Wp = Wu[orig].contiguous()
     out = torch.empty_like(skip)
-    mirror = torch.empty(skip.shape, dtype=torch.bfloat16, device="cuda")
+    mirror = torch.empty(skip.shape, dtype=OPD(), device="cuda")
     d = _desc(ops, M=N * H * W, N=2 * Cin, K=Cin, A=x, lda=Cin, B=Wp, ldb=Cin, splits=1, epilogue=3, out_f32=out,
               out_bf16=mirror, resid=skip, H=H, W=W, Cseg=Cseg)
     ops.gemm_ex(d, impl)
@@ -244,7 +246,7 @@ def test_layernorm_fwd_bwd(ops, M, C):
     x = torch.randn(M, C, generator=g) * 1.7 + 0.4
     w = 1 + 0.2 * torch.randn(C, generator=g)
     b = 0.2 * torch.randn(C, generator=g)
-    dn = torch.randn(M, C, generator=g).bfloat16()
+    dn = torch.randn(M, C, generator=g).to(OPD())
     dres = torch.randn(M, C, generator=g)
     x4 = x.t().reshape(1, C, M, 1)  # NCHW view of the same rows
     y, y_hat, var = O.layernorm2d_fwd(x4, w, b)
@@ -271,7 +273,7 @@ def test_layernorm_golden(ops, golden_dir):
     rows = lambda t: torch.as_tensor(t).permute(0, 2, 3, 1).reshape(-1, C).contiguous().cuda()
     out, stats = ops.layernorm2d_fwd(rows(x), torch.from_numpy(z["weight"]).cuda(), torch.from_numpy(z["bias"]).cuda())
     assert rel(out.float(), rows(z["y"])) < 4e-3
-    dy = rows(z["dy"]).bfloat16()
+    dy = rows(z["dy"]).to(OPD())
     dx, _, dw, db, _ = ops.layernorm2d_bwd(dy, rows(x), stats, torch.from_numpy(z["weight"]).cuda())
     # dy was rounded to bf16 (the kernel's input type) -> compare against the oracle on the rounded dy
     dyr = dy.float().reshape(N, H, W, C).permute(0, 3, 1, 2).cpu()
@@ -286,7 +288,7 @@ def test_layernorm_golden(ops, golden_dir):
 def test_dwconv_gate_fwd(ops, N, H, W, C):
     import torch.nn.functional as F
     g = torch.Generator().manual_seed(C + H)
-    u = torch.randn(N, H, W, 2 * C, generator=g).bfloat16()
+    u = torch.randn(N, H, W, 2 * C, generator=g).to(OPD())
     w2 = torch.randn(2 * C, 1, 3, 3, generator=g) / 3
     b2 = torch.randn(2 * C, generator=g) * 0.1
     v = F.conv2d(u.float().permute(0, 3, 1, 2), w2, b2, padding=1, groups=2 * C)

@@ -18,9 +18,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import nafnet_oracle as O  # noqa: E402
+from tol import report, tol  # noqa: E402
 
-TOL_OUT, TOL_DX, TOL_G = 1e-3, 3e-3, 2e-2
-TOL_NET = 2e-3   # whole-network output: the per-block bf16-operand error accumulates over the depth (DESIGN.md numerics)
+# bf16-operand build: measured operand-rounding error with margin; fp16-operand (parity) build: the north-star 1e-3 on every
+# forward output, measured figures with margin on gradients (tests/tol.py)
+TOL_OUT, TOL_DX, TOL_G = 1e-3, tol(3e-3, 1e-3), tol(2e-2, 5e-3)
+TOL_NET = tol(2e-3)   # whole-network output: the per-block bf16-operand error accumulates over the depth (DESIGN.md numerics)
 
 
 def rel(a, b):
@@ -44,10 +47,11 @@ def test_nafblock_golden(golden_dir, name):
     op = NAFBlockOp(params)
     x = nhwc(torch.from_numpy(z["x"])).cuda()
     out, saved, _ = op.forward(x)
-    assert rel(nchw(out), z["y"]) < TOL_OUT
     dx, grads = op.backward(x, saved, nhwc(torch.from_numpy(z["dy"])).cuda())
-    assert rel(nchw(dx), z["dx"]) < TOL_DX
     errs = {k: rel(g, z["g." + k]) for k, g in zip(NAFBLOCK_PARAM_ORDER, grads)}
+    report(f"NAFBlock {name} vs reference golden", out=rel(nchw(out), z["y"]), dx=rel(nchw(dx), z["dx"]), grads_worst=max(errs.values()))
+    assert rel(nchw(out), z["y"]) < TOL_OUT
+    assert rel(nchw(dx), z["dx"]) < TOL_DX
     bad = {k: v for k, v in errs.items() if v > TOL_G}
     assert not bad, errs
 
@@ -105,22 +109,26 @@ def test_nafnet_golden_engine(golden_dir):
     inp = torch.from_numpy(z["inp"]).cuda()
     gt = torch.from_numpy(z["gt"]).cuda()
     out, feats, saved = eng.forward(params, inp, want_feats=True)
-    assert rel(out, z["out"]) < TOL_NET
-    for i, f in enumerate(feats):
-        # decoder features sit before the `+ inp` of the output: no large fp32 term dilutes the bf16-operand
-        # error.  The oracle's rounding hook predicts 3.4-3.7e-3 for this net (DESIGN.md numerics table).
-        assert rel(nchw(f), z[f"feat{i}"]) < 6e-3, i
-    dout = torch.sign(out - gt) / out.numel()          # d/dout of L1Loss(mean) (losses/basic_loss.py:57-86)
+    fe = [rel(nchw(f), z[f"feat{i}"]) for i, f in enumerate(feats)]
+    # the reference's own L1 gradient sign(out_ref - gt) (losses/basic_loss.py:57-86): the backward operator is checked on the
+    # same incoming gradient as the golden run (sign() of the CUDA output flips wherever |out - gt| is below the forward error)
+    dout = torch.sign(torch.from_numpy(z["out"]).cuda() - gt) / out.numel()
     grads = eng.backward(params, inp, saved, dout)
     errs = {k: rel(g, z["g." + k]) for k, g in zip(names, grads)}
-    bad = {k: v for k, v in errs.items() if v > 3e-2}
+    report("NAFNet w8 vs reference golden", out=rel(out, z["out"]), feats_worst=max(fe), grads_median=float(np.median(list(errs.values()))),
+           grads_worst=max(errs.values()))
+    assert rel(out, z["out"]) < TOL_NET
+    # decoder features sit before the `+ inp` of the output: no large fp32 term dilutes the operand-rounding error.  The
+    # oracle's bf16 rounding hook predicts 3.4-3.7e-3 for this net (DESIGN.md numerics table).
+    assert max(fe) < tol(6e-3), fe
+    bad = {k: v for k, v in errs.items() if v > tol(3e-2, 1e-2)}
     assert not bad, bad
-    assert float(np.median(list(errs.values()))) < 1.5e-2
+    assert float(np.median(list(errs.values()))) < tol(1.5e-2, 3e-3)
     # hook=True: no ending conv, features identical
     out2, feats2, _ = eng.forward(params, inp, hook=True, want_feats=True, keep_for_backward=False)
     assert out2 is None
     for a, b in zip(feats, feats2):
-        assert torch.equal(a, b)
+        assert rel(a, b) < 1e-4       # (not bit-equal: the SCA pooling sums are fp32 atomics)
 
 
 def test_nafnet_module_matches_oracle_and_trains(golden_dir):
@@ -137,7 +145,8 @@ def test_nafnet_module_matches_oracle_and_trains(golden_dir):
     loss = (out - gt).abs().mean()
     loss.backward()
     errs = {k: rel(p.grad, z["g." + k]) for k, p in net.named_parameters()}
-    assert max(errs.values()) < 3e-2, errs
+    report("NAFNet w8 module, L1 loss on the CUDA output", grads_worst=max(errs.values()))
+    assert max(errs.values()) < 3e-2, errs   # sign(out - gt) flips where |out - gt| < forward error: same bar in both builds
     opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
     opt.step()
     out2 = net(inp)                                     # packed weights must refresh after the step
@@ -164,7 +173,8 @@ def test_nafnet_module_matches_oracle_and_trains(golden_dir):
     sum((f * w).sum() for f, w in zip(ofe, ws)).backward()
     errs = {k: rel(p.grad, leaves[k].grad) for k, p in net.named_parameters() if leaves[k].grad is not None
             and p.grad is not None and float(leaves[k].grad.abs().max()) > 0}
-    assert len(errs) > 50 and max(errs.values()) < 3e-2, errs
+    report("NAFNet w8 module, decoder-feature (hook) gradients vs oracle", grads_worst=max(errs.values()))
+    assert len(errs) > 50 and max(errs.values()) < tol(3e-2, 1e-2), errs
     assert net.ending.weight.grad is None or float(net.ending.weight.grad.abs().max()) == 0.0
 
 
@@ -188,9 +198,11 @@ def test_nafnet_w32_vs_oracle_256():
     params = [v.cuda().contiguous() for v in sd.values()]
     out, _, _ = eng.forward(params, inp.cuda(), keep_for_backward=False)
     e = rel(out, ref)
-    assert e < 5e-3, e
     psnr = lambda a, b: float(10 * torch.log10(1.0 / ((a.clamp(0, 1) - b) ** 2).mean()))
-    assert abs(psnr(out.cpu(), gt) - psnr(ref, gt)) < 0.01
+    dp = abs(psnr(out.cpu(), gt) - psnr(ref, gt))
+    report("NAFNet w32 36 blocks 256x256 (C1) vs oracle", out=e, dpsnr_db=dp)
+    assert e < tol(5e-3), e
+    assert dp < 0.01
 
 
 def test_nafnet_w64_full_config_properties():
@@ -217,8 +229,8 @@ def test_nafnet_w64_full_config_properties():
     e = rel(out[:1], ref0)
     psnr = lambda a, b: float(10 * torch.log10(1.0 / ((a.clamp(0, 1) - b) ** 2).mean()))
     dp = abs(psnr(out[:1].cpu(), gt[:1]) - psnr(ref0, gt[:1]))
-    print(f"w64 image 0 vs oracle: rel-L2 {e:.2e}, |dPSNR| {dp:.4f} dB")
-    assert e < 5e-3 and dp < 0.01
+    report("NAFNet w64 b16 (C2) image 0 vs oracle", out=e, dpsnr_db=dp)
+    assert e < tol(5e-3) and dp < 0.01
     # (b)
     # (two runs are never bit-identical: the SCA pool sums are fp32 atomics, and a 1e-7 difference decorrelates the bf16
     #  rounding decisions of 36 blocks -> agreement at the rounding-noise floor, the same ~1e-3 as against the oracle)
@@ -267,7 +279,65 @@ def test_nafnet_tlc_golden(golden_dir):
         base = O.nafnet_fwd(inp, sd, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"])   # global pooling
     e, e_small, e_base = rel(out, z_t(z["out"])), rel(out_small, z_t(z["out_small"])), rel(out, base)
     print(f"NAFNet TLC: rel-L2 {e:.2e} vs reference golden (global-pooling oracle: {e_base:.2e}); small input {e_small:.2e}")
-    assert e < 2.5e-3 and e_small < 2.5e-3 and e_base > 2 * e
+    report("NAFNet TLC vs reference golden", out=e, out_small=e_small)
+    assert e < tol(2.5e-3) and e_small < tol(2.5e-3) and e_base > 2 * e
     from dcpt_b200.lib import DcptError
     with pytest.raises(DcptError):
         net(inp.cuda())                                  # gradients enabled: TLC is inference only
+
+
+def test_dcpt_hooks_on_first_decoder_block():
+    """the reference's one-dot rule (degradation_classification_pretrain_model.py:64-67) hooks
+    `decoder{i}.0`, the FIRST block of each decoder level.  With dec_blk_nums = [2, 2] that is not the level output: the
+    fused forward must hand out block 0's tensor, the gradient of a loss on it must flow back through block 0 only, and the
+    blocks behind the tap in the last level (unreached under hook=True) must get no gradient."""
+    from basicsr.archs import build_network
+    cfg = dict(width=16, enc_blk_nums=[1, 1], middle_blk_num=1, dec_blk_nums=[2, 2])
+    sd = O.random_nafnet_state_dict(seed=5, **cfg)
+    net = build_network(dict(type="NAFNetBaseline", **cfg)).cuda()
+    net.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(6)
+    lq = torch.rand(2, 3, 32, 32, generator=g)
+    feats = []
+    names = [n for n, m in net.named_modules() if "decoder" in n and n.count(".") == 1]      # the reference's rule, verbatim
+    assert names == ["decoder0.0", "decoder0.1", "decoder1.0", "decoder1.1"]
+    # (with `hook_names: decoder` the reference would hook all four and hand the head two features per resolution, which its
+    # stage-wise downsampling cannot consume; the meaningful taps are one block per level - here the first blocks, the ones
+    # the rule selects for the shipped one-block levels)
+    hooks = [m.register_forward_hook(lambda mod, i, o: feats.append(o)) for n, m in net.named_modules()
+             if n in ("decoder0.0", "decoder1.0")]
+    assert net(lq.cuda(), hook=True) is None and len(feats) == 2
+    ws = [torch.randn(f.shape, generator=g) for f in feats]
+    sum((f * w.cuda()).sum() for f, w in zip(feats, ws)).backward()
+    for h in hooks:
+        h.remove()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ofe = []
+    O.nafnet_fwd(lq, leaves, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"], hook=True, decoder_feats=ofe,
+                 decoder_feat_block=0)
+    for f, o in zip(feats, ofe):
+        assert rel(f, o) < tol(6e-3), rel(f, o)
+    sum((f * w).sum() for f, w in zip(ofe, ws)).backward()
+    errs = {}
+    for k, p in net.named_parameters():
+        og = leaves[k].grad
+        dead = og is None or float(og.abs().max()) == 0.0
+        if dead:   # decoder1.1 (behind the last tap) and the ending conv: unreached
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        else:
+            errs[k] = rel(p.grad, og)
+    assert any(k.startswith("decoder0.1.") for k in errs) and not any(k.startswith("decoder1.1.") for k in errs)
+    report("NAFNet dec [2,2], hooks on decoder{i}.0: gradients vs oracle", worst=max(errs.values()), median=float(np.median(list(errs.values()))))
+    assert max(errs.values()) < tol(3e-2, 1e-2), sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    # hooks on the level container still deliver the level output (what `module.decoder{i}` selects under DDP)
+    feats.clear()
+    hooks = [getattr(net, f"decoder{i}").register_forward_hook(lambda mod, i_, o: feats.append(o)) for i in range(2)]
+    with torch.no_grad():
+        net(lq.cuda(), hook=True)
+    ofe2 = []
+    with torch.no_grad():
+        O.nafnet_fwd(lq, sd, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"], hook=True, decoder_feats=ofe2)
+    for f, o in zip(feats, ofe2):
+        assert rel(f, o) < tol(6e-3)
+    for h in hooks:
+        h.remove()

@@ -13,6 +13,9 @@ import os
 import numpy as np
 import pytest
 import torch
+
+from dcpt_b200.lib import operand_dtype as OPD  # bf16 by default; fp16 for the DCPT_OPERAND=fp16 parity build
+from tol import FP16, tol  # noqa: F401
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
@@ -56,7 +59,7 @@ def test_layernorm_rows(lib, C_, center):
     ref = RO.layernorm_chan(x.t().reshape(1, C_, M, 1), w, b).reshape(C_, M).t()
     xd, wd = x.cuda(), w.cuda()
     bd = b.cuda() if center else None
-    out = torch.empty(M, C_, dtype=torch.bfloat16, device="cuda")
+    out = torch.empty(M, C_, dtype=OPD(), device="cuda")
     L.check(lib.dcpt_layernorm_rows_fwd(_ptr(xd), _ptr(wd), _ptr(bd) if center else None, _ptr(out), None, M, C_, 1e-6, center, _stream()))
     assert rel(out.float(), ref) < 4e-3  # bf16 output rounding
 
@@ -65,7 +68,7 @@ def test_layernorm_rows(lib, C_, center):
 def test_dwconv3x3_and_norms(lib, N, H, W, CH, sq):
     from dcpt_b200 import lib as L
     g = torch.Generator().manual_seed(CH + H)
-    x = torch.randn(N, CH, H, W, generator=g).bfloat16()
+    x = torch.randn(N, CH, H, W, generator=g).to(OPD())
     w = torch.randn(CH, 1, 3, 3, generator=g) / 3
     ref = F.conv2d(x.float(), w, None, padding=1, groups=CH)
     xd = x.permute(0, 2, 3, 1).contiguous().cuda()
@@ -81,12 +84,12 @@ def test_dwconv3x3_and_norms(lib, N, H, W, CH, sq):
 def test_gelu_gate(lib, N, H, W, Cc):
     from dcpt_b200 import lib as L
     g = torch.Generator().manual_seed(Cc)
-    u = torch.randn(N, 2 * Cc, H, W, generator=g).bfloat16()
+    u = torch.randn(N, 2 * Cc, H, W, generator=g).to(OPD())
     w = torch.randn(2 * Cc, 1, 3, 3, generator=g) / 3
     y = F.conv2d(u.float(), w, None, padding=1, groups=2 * Cc)
     ref = F.gelu(y[:, :Cc]) * y[:, Cc:]
     ud = u.permute(0, 2, 3, 1).contiguous().cuda()
-    out = torch.empty(N, H, W, Cc, dtype=torch.bfloat16, device="cuda")
+    out = torch.empty(N, H, W, Cc, dtype=OPD(), device="cuda")
     L.check(lib.dcpt_dwconv3x3_gelu_gate_fwd(_ptr(ud), _ptr(w.cuda().contiguous()), _ptr(out), N, H, W, Cc, _stream()))
     assert rel(out.float().permute(0, 3, 1, 2), ref) < 4e-3
 
@@ -129,7 +132,7 @@ def test_transformer_block_golden(lib, golden_dir, dim):
     y = xd.permute(0, 3, 1, 2).cpu()
     e = rel(y, z["y"])
     print(f"TransformerBlock d={dim}: rel-L2 {e:.2e}")
-    assert e < 6e-3
+    assert e < tol(6e-3)          # TransformerBlock forward: bf16 build 2.7-3.8e-3; fp16 (parity) build 3.4-4.9e-4 -> 1e-3 bar
 
 
 @pytest.mark.parametrize("dim", [48, 96, 32])
@@ -171,16 +174,16 @@ def test_transformer_block_backward_golden(lib, golden_dir, dim):
     L.check(lib.dcpt_restormer_block_bwd(eng.plan, st, 0, pp, _ptr(packed), _ptr(saved), _ptr(xd), _ptr(dyd), _ptr(dxd), gp, _ptr(work),
                                          N, H, W, _stream()), "block_bwd")
     torch.cuda.synchronize()
-    assert rel(yd.permute(0, 3, 1, 2), z["y"]) < 6e-3
+    assert rel(yd.permute(0, 3, 1, 2), z["y"]) < tol(6e-3)
     e_dx = rel(dxd.permute(0, 3, 1, 2), z["dx"])
     errs = {k[len(pref):]: rel(g_, z["g." + k[len(pref):]]) for k, g_ in zip(names, grads) if k.startswith(pref)}
     print(f"TransformerBlock d={dim} backward: dx rel-L2 {e_dx:.2e}; param grads worst {max(errs.values()):.2e} "
           f"({max(errs, key=errs.get)}), median {float(np.median(list(errs.values()))):.2e}")
     print("   " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
-    assert e_dx < 3e-2
-    assert max(errs.values()) < 6e-2 and float(np.median(list(errs.values()))) < 1.5e-2, errs
+    assert e_dx < tol(3e-2, 8e-3)   # fp16 build: 5e-4 (d=48, 32), 5.7e-3 (d=96: F.normalize's projection amplifies the q,k rounding)
+    assert max(errs.values()) < tol(6e-2, 2e-2) and float(np.median(list(errs.values()))) < tol(1.5e-2, 2e-3), errs   # fp16: worst 1.0e-3 / 1.3e-2 (d=96), median 7-9e-4
     gdfn = [v for k, v in errs.items() if k.startswith("ffn.") or k.startswith("norm2.") or "project_out" in k or "temperature" in k]
-    assert max(gdfn) < 1.2e-2, errs
+    assert max(gdfn) < tol(1.2e-2, 2e-3), errs
     for k, g_ in zip(names, grads):      # nothing outside the block is touched
         if not k.startswith(pref):
             assert float(g_.abs().max()) == 0.0, k
@@ -191,7 +194,7 @@ def _net(cfg):
     return build_network(dict(type="Restormer", window_size=8, **cfg)).cuda()
 
 
-BF16 = lambda t: t.bfloat16().float()  # noqa: E731  (the oracle's rounding hook: same rounding points as the kernels)
+BF16 = lambda t: t.to(OPD()).float()  # noqa: E731  (the oracle's rounding hook: same rounding points as the kernels)
 
 
 def test_restormer_tiny_golden(golden_dir):
@@ -213,11 +216,11 @@ def test_restormer_tiny_golden(golden_dir):
     e, eq = rel(out, z["out"]), rel(out, rq)
     print(f"Restormer tiny: out rel-L2 {e:.2e} vs reference golden, {eq:.2e} vs bf16-rounded oracle "
           f"(rounded oracle vs golden: {rel(rq, z['out']):.2e})")
-    assert e < 2.5e-2 and eq < 8e-3
+    assert e < tol(2.5e-2, 3e-3) and eq < 8e-3   # 7-block net with O(1) random weights: fp16 build 1.6e-3 (bf16: 1e-2)
     assert len(feats) == 3
     for i, f in enumerate(feats):
         assert tuple(f.shape) == tuple(z[f"feat{i}"].shape)
-        assert rel(f, z[f"feat{i}"]) < 2.5e-2 and rel(f, fq[i]) < 8e-3, i
+        assert rel(f, z[f"feat{i}"]) < tol(2.5e-2, 3e-3) and rel(f, fq[i]) < 8e-3, i
     feats.clear()
     with torch.no_grad():
         assert net(z["inp"].cuda(), hook=True) is None
@@ -272,7 +275,7 @@ def test_restormer_full_vs_oracle():
     print(f"Restormer 128x128, N(0, 0.49/fan_in) weights: out rel-L2 {e:.2e} vs exact oracle, {eq:.2e} vs bf16-rounded oracle "
           f"(rounded vs exact oracle {rel(rq, ref):.2e})")
     assert torch.isfinite(out).all()
-    assert e < 8e-2 and eq < 4e-2
+    assert e < tol(8e-2, 1e-2) and eq < 4e-2   # 48 blocks, every branch as large as the residual: fp16 build 4.9e-3 (bf16: 5.9e-2)
 
 
 def test_restormer_train_step_golden(golden_dir):
@@ -287,13 +290,13 @@ def test_restormer_train_step_golden(golden_dir):
     out = net(z["inp"].cuda())
     loss = (out - z["gt"].cuda()).abs().mean()
     loss.backward()
-    assert rel(out, z["out"]) < 2.5e-2 and abs(float(loss) - float(z["loss"])) < 2e-2 * float(z["loss"])
+    assert rel(out, z["out"]) < tol(2.5e-2, 3e-3) and abs(float(loss) - float(z["loss"])) < tol(2e-2, 2e-3) * float(z["loss"])
     errs = {k: rel(p_.grad, z["g." + k]) for k, p_ in net.named_parameters()}
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
     med = float(np.median(list(errs.values())))
     print(f"Restormer tiny train step: loss {float(loss):.5f} vs {float(z['loss']):.5f}; param grads median {med:.2e}, worst {worst}")
     assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in net.parameters())
-    assert med < 4e-2 and worst[0][1] < 0.25
+    assert med < tol(4e-2, 1.5e-2) and worst[0][1] < tol(0.25, 5e-2)   # fp16 build: median 9e-3 / 2e-3, worst 2.6e-2 / 1.9e-2
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
     opt.step()                                                               # :169; parameters changed in place -> re-packed
     with torch.no_grad():
@@ -330,7 +333,7 @@ def test_restormer_dcpt_hook_gradients_golden(golden_dir):
     assert net(lq.cuda(), hook=True) is None                                # :154
     assert len(hook_outputs) == 3
     for i, f in enumerate(hook_outputs):
-        assert tuple(f.shape) == tuple(z[f"feat{i}"].shape) and rel(f, z[f"feat{i}"]) < 2.5e-2, i
+        assert tuple(f.shape) == tuple(z[f"feat{i}"].shape) and rel(f, z[f"feat{i}"]) < tol(2.5e-2, 3e-3), i
     smooth(hook_outputs).backward()
     gs = grads()
     for k in gs:                                                            # never reached -> None, as in the reference
@@ -339,7 +342,7 @@ def test_restormer_dcpt_hook_gradients_golden(golden_dir):
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
     med = float(np.median(list(errs.values())))
     print(f"Restormer hooked pass, smooth feature gradient: param grads median {med:.2e}, worst {worst}")
-    assert med < 4e-2 and worst[0][1] < 0.25
+    assert med < tol(4e-2, 1.5e-2) and worst[0][1] < tol(0.25, 5e-2)   # fp16 build: median 9e-3 / 2e-3, worst 2.6e-2 / 1.9e-2
     # (2) white-noise feature gradients, decoder_level1
     net.zero_grad(set_to_none=True)
     hook_outputs.clear()
@@ -348,7 +351,7 @@ def test_restormer_dcpt_hook_gradients_golden(golden_dir):
     # (the temperature gradient - one scalar per head, a sum of zero-mean noise terms - is ~0 in the reference here: skipped)
     ew = [rel(p_.grad, z["gw." + k]) for k, p_ in net.named_parameters() if "gw." + k in z and not k.endswith("temperature")]
     print(f"white-noise feature gradient: decoder_level1 grads median {float(np.median(ew)):.2e}, max {max(ew):.2e}")
-    assert float(np.median(ew)) < 4e-2 and max(ew) < 0.25
+    assert float(np.median(ew)) < tol(4e-2, 1e-2) and max(ew) < tol(0.25, 5e-2)   # fp16 build: 2.2e-3 / 2.5e-3 (varies run to run with the split-K atomics)
     # (3) the DCPT step: both passes, one backward == pixel pass alone + hooked pass alone
     net.zero_grad(set_to_none=True)
     pix = net(gt.cuda(), hook=False)                                        # :140
