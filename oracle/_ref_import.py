@@ -31,10 +31,12 @@ def _stub(name, **attrs):
     return m
 
 
-def import_reference():
-    """Returns the reference's ``basicsr`` package (imported from REFERENCE_ROOT)."""
+def import_reference(root=None):
+    """Returns the reference's ``basicsr`` package, imported from REFERENCE_ROOT (or from ``root``: a directory holding a
+    ``basicsr`` tree, e.g. the reference checkout with this repo's arch files dropped in - tests/boundary_overlay_check.py)."""
     if not reference_available():
         raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    root = root or REFERENCE_ROOT
     import torch
     from torch import nn
 
@@ -77,9 +79,9 @@ def import_reference():
     # reference wins inside this process.
     for k in [k for k in sys.modules if k == "basicsr" or k.startswith("basicsr.")]:
         del sys.modules[k]
-    if REFERENCE_ROOT in sys.path:
-        sys.path.remove(REFERENCE_ROOT)
-    sys.path.insert(0, REFERENCE_ROOT)
+    if root in sys.path:
+        sys.path.remove(root)
+    sys.path.insert(0, root)
     import basicsr  # noqa: F401  (the reference's)
-    assert os.path.abspath(basicsr.__file__).startswith(os.path.abspath(REFERENCE_ROOT)), basicsr.__file__
+    assert os.path.abspath(basicsr.__file__).startswith(os.path.abspath(root)), basicsr.__file__
     return basicsr

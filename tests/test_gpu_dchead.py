@@ -304,3 +304,65 @@ def test_dcpt_pretrain_step():
     opt_g.step(); opt_h.step()                                              # :164-165
     for h in hooks:
         h.remove()
+
+
+def test_dcpt_step_full_width_one_image():
+    """BASELINE.json configs[3] (C4) at full WIDTH on one image: DCPTModel.optimize_parameters (models/
+    degradation_classification_pretrain_model.py:133-169) with NAFNet-w64 (36 blocks) + PromptIR_NoImg_DC over the decoder
+    features f = [64, 128, 256, 512] at 256x256, the reference's L1 pixel loss + cross entropy, ONE backward - against the fp32
+    CPU oracle.  As in test_dcpt_pretrain_step the classifier's feature gradients are taken from the CUDA run (the head is
+    only comparable on a fixed ReLU branch), so the check is: logits and pixel output vs oracle, the L1 loss value, and all 664
+    backbone gradients given (L1 gradient at the reference's output + those feature gradients)."""
+    from basicsr.archs import build_network
+    from oracle import nafnet_oracle as O
+    cfg = dict(width=64, enc_blk_nums=[1, 1, 1, 28], middle_blk_num=1, dec_blk_nums=[1, 1, 1, 1])
+    dims = [64, 128, 256, 512]
+    sd_g = O.random_nafnet_state_dict(seed=0, **cfg)
+    sd_h = D.random_dchead_state_dict(dims, 2, 5, seed=1)
+    net = build_network(dict(type="NAFNetBaseline", **cfg)).cuda()
+    head = build_network(dict(type="PromptIR_NoImg_DC", feature_dims=dims, num_res_blocks=2, num_classes=5)).cuda()
+    net.load_state_dict(sd_g, strict=True)
+    head.load_state_dict(sd_h, strict=True)
+    g = torch.Generator().manual_seed(7)
+    gt = torch.rand(1, 3, 256, 256, generator=g)
+    lq = (gt + 0.1 * torch.randn(gt.shape, generator=g)).clamp(0, 1)
+    labels = torch.tensor([3])
+    hook_outputs = []
+    hooks = [m.register_forward_hook(lambda mod, i, o: hook_outputs.append(o)) for n, m in net.named_modules()
+             if "decoder" in n and n.count(".") == 1]                       # :64-67
+    assert len(hooks) == 4
+    # oracle first: its pixel output defines the L1 gradient both sides use
+    lg = {k: v.clone().requires_grad_(True) for k, v in sd_g.items()}
+    o_pix = O.nafnet_fwd(gt, lg, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"])
+    fe = []
+    O.nafnet_fwd(lq, lg, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"], hook=True, decoder_feats=fe)
+    with torch.no_grad():
+        o_cls = D.dchead_fwd(fe[::-1], sd_h)
+    d_pix = torch.sign(o_pix.detach() - gt) / o_pix.numel()
+    # CUDA step
+    pix = net(gt.cuda(), hook=False)                                        # :140
+    hook_outputs.clear()                                                    # :141
+    l_pix = F.l1_loss(pix, gt.cuda())                                       # :145-148 (L1Loss, mean)
+    assert net(lq.cuda(), hook=True) is None                                # :154
+    kept = list(hook_outputs)
+    for h in kept:
+        h.retain_grad()
+    cls = head(lq.cuda(), hook_outputs[::-1])                               # :155
+    l_cls = F.cross_entropy(cls, labels.cuda())                             # :158-161
+    # one backward (:163); the pixel branch enters with the L1 gradient evaluated at the reference's output
+    torch.autograd.backward([pix, l_cls], [d_pix.cuda(), torch.ones((), device="cuda")])
+    dfe = [h.grad.detach().cpu() for h in kept]
+    (o_pix * d_pix).sum().backward(retain_graph=True)
+    sum((f * d).sum() for f, d in zip(fe, dfe)).backward()
+    e_pix, e_cls = rel(pix, o_pix), rel(cls, o_cls)
+    l_ref = float((o_pix.detach() - gt).abs().mean())
+    eg = {k: rel(p.grad, lg[k].grad) for k, p in net.named_parameters()}
+    vals = np.array(list(eg.values()))
+    report("DCPT step, NAFNet-w64 + head f=[64..512], 1x256x256 (C4 width)", pix=e_pix, logits=e_cls, l1_loss_rel=abs(float(l_pix) - l_ref) / l_ref,
+           grads_median=float(np.median(vals)), grads_p95=float(np.percentile(vals, 95)), grads_worst=float(vals.max()))
+    assert e_pix < tol(5e-3) and e_cls < tol(2e-2, 3e-3) and abs(float(l_pix) - l_ref) < tol(2e-3) * l_ref
+    assert float(np.median(vals)) < tol(2e-2, 3e-3) and float(np.percentile(vals, 95)) < tol(6e-2, 1e-2), sorted(eg.items(), key=lambda kv: -kv[1])[:5]
+    for k, p in head.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, k
+    for h in hooks:
+        h.remove()

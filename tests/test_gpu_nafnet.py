@@ -341,3 +341,33 @@ def test_dcpt_hooks_on_first_decoder_block():
         assert rel(f, o) < tol(6e-3)
     for h in hooks:
         h.remove()
+
+
+def test_nafnet_w64_backward_one_image_vs_oracle():
+    """the BACKWARD of the full-width network (NAFNet-w64, enc [1,1,1,28], 36 blocks, 664 tensors) against
+    the fp32 CPU oracle on one 256x256 image, with the reference's L1 loss (losses/basic_loss.py:57-86).  Both sides get the
+    same incoming gradient sign(out_ref - gt) / numel (the L1 gradient at the reference's output), so the comparison is of the
+    backward operator and not of sign() decisions at |out - gt| < forward error."""
+    from dcpt_b200.nafnet import NAFNetEngine
+    cfg = dict(width=64, enc_blk_nums=[1, 1, 1, 28], middle_blk_num=1, dec_blk_nums=[1, 1, 1, 1])
+    sd = O.random_nafnet_state_dict(seed=0, **cfg)
+    g = torch.Generator().manual_seed(33)
+    inp = torch.rand(1, 3, 256, 256, generator=g)
+    gt = (inp + 0.05 * torch.randn(inp.shape, generator=g)).clamp(0, 1)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.nafnet_fwd(inp, leaves, cfg["enc_blk_nums"], cfg["middle_blk_num"], cfg["dec_blk_nums"])
+    dout = torch.sign(ref.detach() - gt) / ref.numel()
+    ref.backward(dout)
+    eng = NAFNetEngine(3, cfg["width"], cfg["middle_blk_num"], cfg["enc_blk_nums"], cfg["dec_blk_nums"])
+    params = [v.cuda().contiguous() for v in sd.values()]
+    out, _, saved = eng.forward(params, inp.cuda())
+    grads = eng.backward(params, inp.cuda(), saved, dout.cuda())
+    l_ref, l_out = float((ref.detach() - gt).abs().mean()), float((out.cpu() - gt).abs().mean())
+    errs = {k: rel(gv, leaves[k].grad) for k, gv in zip(sd.keys(), grads)}
+    vals = np.array(list(errs.values()))
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    report("NAFNet w64 1x256x256 fwd+bwd vs oracle (664 gradients)", out=rel(out, ref), l1_loss_rel=abs(l_out - l_ref) / l_ref,
+           grads_median=float(np.median(vals)), grads_p95=float(np.percentile(vals, 95)), grads_worst=float(vals.max()))
+    print("   worst:", worst)
+    assert rel(out, ref) < tol(5e-3) and abs(l_out - l_ref) < tol(2e-3) * l_ref
+    assert float(np.median(vals)) < tol(1.5e-2, 2e-3) and float(np.percentile(vals, 95)) < tol(4e-2, 5e-3) and vals.max() < tol(0.1, 2e-2), worst
