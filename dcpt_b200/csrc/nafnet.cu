@@ -398,6 +398,12 @@ struct dcpt_nafnet_plan {
   int mid_C;
   // which block of decoder level i delivers host_feats[i] / receives host_dfeats[i] (-1 = the level's last block).  DCPT's
   // one-dot rule hooks `decoder{i}.0`, the FIRST block (degradation_classification_pretrain_model.py:64-67).
+  // Optional CUDA event recorded by dcpt_nafnet_bwd on its stream as soon as the gradients of the deepest encoder level, the
+  // middle blocks, the up convs, every decoder and the ending conv are final (i.e. after the backward of encoders.{n_enc-1}.*):
+  // a data-parallel caller starts the all-reduce of that contiguous 90 % slice of the flat gradient buffer on a second
+  // stream while the shallower levels are still being differentiated (base_model.py:107-118: what DDP's buckets do).
+  void* split_event = nullptr;
+  bool split_event_external = true;  // inside a stream capture: external-event node (waited on from outside the graph) or plain
   std::vector<int> hook_blk;
   int hook_block(int i) const { return (i < (int)hook_blk.size() && hook_blk[i] >= 0) ? hook_blk[i] : dec[i] - 1; }
 };
@@ -807,6 +813,12 @@ int dcpt_nafnet_set_hook_blocks(dcpt_nafnet_plan* plan, const int* block_idx, in
   plan->hook_blk.assign(block_idx, block_idx + n_levels);
   return 0;
 }
+int dcpt_nafnet_set_bwd_split_event(dcpt_nafnet_plan* plan, void* cuda_event, int external) {
+  DCPT_CHECK_ARG(plan != nullptr, DCPT_E_ARG, "nafnet_set_bwd_split_event: null plan");
+  plan->split_event = cuda_event;
+  plan->split_event_external = external != 0;
+  return 0;
+}
 int dcpt_nafnet_num_params(const dcpt_nafnet_plan* plan) { return (int)plan->params.size(); }
 long long dcpt_nafnet_param_shape(const dcpt_nafnet_plan* plan, int i, int dims[4]) {
   if (i < 0 || i >= (int)plan->params.size()) return -1;
@@ -1095,6 +1107,13 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     for (int j = p->enc[i] - 1; j >= 0; --j)
       DCPT_TRY(block_bwd(p->enc_blks[i][j], pk.enc_pk[i][j], sv.enc_sv[i][j],
                          j > 0 ? sv.enc_out[i][j - 1] : (i > 0 ? sv.xd[i - 1] : sv.x0), h, w));
+    if (i == ne - 1 && p->split_event) {  // deepest level done: its slice of the gradient buffer is final (see split_event)
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      DCPT_CUDA(cudaStreamIsCapturing(st, &cap));
+      DCPT_CUDA(cudaEventRecordWithFlags(static_cast<cudaEvent_t>(p->split_event), st,
+                                         (cap == cudaStreamCaptureStatusActive && p->split_event_external) ? cudaEventRecordExternal
+                                                                                                           : cudaEventRecordDefault));
+    }
   }
   // ---------------- intro: wgrad + bias grad (the input image needs no gradient) ----------------
   DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient reached the intro conv");

@@ -59,6 +59,30 @@ def allreduce_mean_(flat, group=None):
     return flat
 
 
+def allreduce_grads_overlapped_(engine, flat, group=None, comm_stream=None):
+    """Mean all-reduce of a NAFNet engine's flat gradient buffer, overlapped with the tail of the backward that is still
+    running: the slice that was final when ``engine.split_event`` fired (deepest encoder level + middle + ups, ~90 % of the
+    bytes) is reduced on ``comm_stream`` as soon as the event fires, the rest on the current stream after the backward.
+    Falls back to one plain all-reduce when the engine has no split event (or on CPU / a single rank)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat
+    ev = getattr(engine, "split_event", None)
+    if ev is None or not flat.is_cuda or comm_stream is None:
+        return allreduce_mean_(flat, group)
+    a, b = engine.early_grad_range()
+    if not (0 <= a < b <= flat.numel()):
+        return allreduce_mean_(flat, group)
+    comm_stream.wait_event(ev)
+    with torch.cuda.stream(comm_stream):
+        allreduce_mean_(flat[a:b], group)
+    if a > 0:
+        allreduce_mean_(flat[:a], group)
+    if b < flat.numel():
+        allreduce_mean_(flat[b:], group)
+    torch.cuda.current_stream().wait_stream(comm_stream)
+    return flat
+
+
 def broadcast_params_(params, src=0, group=None):
     """Make every rank start from rank `src`'s weights (what DDP does at construction)."""
     _, world = get_dist_info()
@@ -83,7 +107,7 @@ class FlatGradDataParallel(torch.nn.Module):
     (gradient accumulation).  Parameters a pass does not reach simply get no gradient on every rank alike
     (``find_unused_parameters`` has no meaning here)."""
 
-    def __init__(self, module, process_group=None, broadcast=True):
+    def __init__(self, module, process_group=None, broadcast=True, overlap=True):
         super().__init__()
         if not hasattr(module, "engine"):
             raise TypeError("FlatGradDataParallel wraps the dcpt_b200 networks (NAFNetBaseline, Restormer, PromptIR_NoImg_DC)")
@@ -92,11 +116,20 @@ class FlatGradDataParallel(torch.nn.Module):
         self._sync_enabled = True
         if broadcast:
             broadcast_params_(list(module.parameters()) + list(module.buffers()), group=process_group)
-        module.engine().grad_sync = self._sync
+        eng = module.engine()
+        eng.grad_sync = self._sync
+        # overlap the all-reduce with the backward's tail where the engine supports it (NAFNet; bf16 build: the parity build
+        # rescales the whole buffer after the backward) - DCPT_DP_OVERLAP=0 turns it off
+        self._comm = None
+        if overlap and hasattr(eng, "enable_grad_overlap") and torch.cuda.is_available() and os.getenv("DCPT_DP_OVERLAP", "1") != "0":
+            from .lib import operand_dtype
+            if operand_dtype() == torch.bfloat16 and get_dist_info()[1] > 1:
+                eng.enable_grad_overlap(True)
+                self._comm = torch.cuda.Stream()
 
     def _sync(self, flat):
         if self._sync_enabled:
-            allreduce_mean_(flat, group=self.process_group)
+            allreduce_grads_overlapped_(self.module.engine(), flat, group=self.process_group, comm_stream=self._comm)
 
     def no_sync(self):
         import contextlib

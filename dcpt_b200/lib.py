@@ -56,6 +56,7 @@ PROTOTYPES = {
     "dcpt_nafnet_destroy": (None, [_VP]),
     "dcpt_nafnet_set_tlc": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), _I]),
     "dcpt_nafnet_set_hook_blocks": (_I, [_VP, C.POINTER(_I), _I]),
+    "dcpt_nafnet_set_bwd_split_event": (_I, [_VP, _VP, _I]),
     "dcpt_nafnet_num_params": (_I, [_VP]),
     "dcpt_nafnet_param_shape": (_LL, [_VP, _I, C.POINTER(_I)]),
     "dcpt_nafnet_packed_bytes": (_SZ, [_VP]),

@@ -29,6 +29,8 @@ class NAFNetEngine:
         self.n_dec = len(dec_blk_nums)
         self.n_enc = len(enc_blk_nums)
         self.width = width
+        self.blk_nums = (tuple(enc_blk_nums), int(middle_blk_num), tuple(dec_blk_nums))
+        self.split_event = None     # data-parallel overlap (enable_grad_overlap)
         self.num_params = self.lib.dcpt_nafnet_num_params(self.plan)
         self.shapes = []
         dims = (C.c_int * 4)()
@@ -56,6 +58,43 @@ class NAFNetEngine:
         _l.check(self.lib.dcpt_nafnet_set_hook_blocks(self.plan, arr, len(idx)), "nafnet_set_hook_blocks")
         self._hook_blocks = idx
         self._gslots.clear()            # captured graphs baked the old feature taps in
+
+    # ---- data-parallel overlap ----------------------------------------------------------------
+    def enable_grad_overlap(self, on=True, external=True):
+        """The backward records ``self.split_event`` once the gradients of the deepest encoder level, the middle blocks, the up
+        convs, the decoders and the ending conv are final (dcpt_nafnet_set_bwd_split_event); dcpt_b200.dist starts the
+        all-reduce of that slice (``early_grad_range``) on a second stream while the shallower levels are still differentiated."""
+        """external: inside a stream capture the record becomes an external-event node (the all-reduce is issued OUTSIDE the
+        captured graph, as FlatGradDataParallel does); external=False when the all-reduce is captured into the same graph."""
+        if on:
+            if self.split_event is None:
+                ev = torch.cuda.Event()
+                ev.record()                                    # instantiates the cudaEvent_t handle
+                self.split_event = ev
+            _l.check(self.lib.dcpt_nafnet_set_bwd_split_event(self.plan, C.c_void_p(self.split_event.cuda_event), int(external)),
+                     "set_bwd_split_event")
+            self._gslots.clear()                               # captured backward graphs do not contain the record node yet
+        elif self.split_event is not None:
+            _l.check(self.lib.dcpt_nafnet_set_bwd_split_event(self.plan, None, 1), "set_bwd_split_event")
+            self.split_event = None
+            self._gslots.clear()
+
+    def early_grad_range(self, align=64):
+        """[a, b) element range, in the flat gradient buffer of ``alloc_flat_grads`` / the graph slots, of the parameters whose
+        gradients are final when ``split_event`` fires: encoders.{n_enc-1}.*, middle_blks.*, ups.* - contiguous in
+        named_parameters() order (nafnet_arch.py:202-248) and ~90 % of NAFNet-w64's 67.9 M parameters."""
+        enc, mid, dec = self.blk_nums
+        first = 4 + 18 * sum(enc[:-1]) if enc else 4
+        last = 4 + 18 * (sum(enc) + mid) + len(dec)          # exclusive: first downs.* parameter
+        offs, off = [], 0
+        for shp in self.shapes:
+            offs.append(off)
+            n = 1
+            for d in shp:
+                n *= d
+            off += (n + align - 1) // align * align
+        offs.append(off)
+        return offs[first], offs[last]
 
     def set_tlc(self, kernels):
         """kernels: [(kh, kw)] per resolution level (0 = full resolution .. n_enc) - NAFNet's test-time local converter."""

@@ -163,6 +163,13 @@ int dcpt_nafnet_set_tlc(dcpt_nafnet_plan* plan, const int* kh, const int* kw, in
  * DCPTModel hooks the modules whose name contains hook_names and has exactly one dot (models/
  * degradation_classification_pretrain_model.py:64-67): `decoder{i}.0`, the FIRST block, for an unwrapped NAFNetBaseline. */
 int dcpt_nafnet_set_hook_blocks(dcpt_nafnet_plan* plan, const int* block_idx, int n_levels);
+/* Data-parallel overlap: cuda_event (a cudaEvent_t, or NULL to turn it off) is recorded by dcpt_nafnet_bwd on its stream once
+ * the gradients of encoders.{n_enc-1}.*, middle_blks.*, ups.*, decoder*.* and ending.* are final, so the caller can all-reduce
+ * that slice on another stream while the shallower encoder levels are still being differentiated (what DDP's bucketed
+ * all-reduce does in the reference, models/base_model.py:107-118).  Inside a stream capture the record is an external-event
+ * node when external != 0 (a stream OUTSIDE the captured graph waits on it), else an ordinary captured dependency (the
+ * waiting stream - e.g. the one NCCL is captured on - belongs to the same capture). */
+int dcpt_nafnet_set_bwd_split_event(dcpt_nafnet_plan* plan, void* cuda_event, int external);
 int dcpt_nafnet_num_params(const dcpt_nafnet_plan* plan);
 /* shape of parameter i as up to 4 dims (unused dims = 1); returns number of elements */
 long long dcpt_nafnet_param_shape(const dcpt_nafnet_plan* plan, int i, int dims[4]);
