@@ -110,32 +110,40 @@ class Restormer(nn.Module):
     """restormer_arch.py:234-422.  ``window_size`` is accepted and ignored by the arch, as in the reference."""
 
     def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4, heads=[1, 2, 4, 8],
-                 ffn_expansion_factor=2.66, bias=False, LayerNorm_type="BiasFree", dual_pixel_task=False, scale=1, window_size=8):
+                 ffn_expansion_factor=2.66, bias=False, LayerNorm_type="BiasFree", dual_pixel_task=False, scale=1, window_size=8,
+                 _plain_stages=False):
         super().__init__()
         if dual_pixel_task or scale != 1:
             raise DcptError("dual_pixel_task / scale > 1 are not on the hot path (no shipped config uses them)")
         a = (ffn_expansion_factor, bias, LayerNorm_type)
+        # a stage is `SequentialTransformerBlock` (blocks under `.body`, restormer_arch.py:205-231) for Restormer and a plain
+        # nn.Sequential of blocks for Restormer_origin (:444-470): same parameters in the same order, different state_dict keys
+        if _plain_stages:
+            stage = lambda d, h, n: nn.Sequential(*[TransformerBlock(d, h, *a) for _ in range(n)])   # noqa: E731
+        else:
+            stage = lambda d, h, n: SequentialTransformerBlock(d, h, n, *a)                          # noqa: E731
         self.patch_embed = OverlapPatchEmbed(inp_channels, dim)
-        self.encoder_level1 = SequentialTransformerBlock(dim, heads[0], num_blocks[0], *a)
+        self.encoder_level1 = stage(dim, heads[0], num_blocks[0])
         self.down1_2 = Downsample(dim)
-        self.encoder_level2 = SequentialTransformerBlock(dim * 2, heads[1], num_blocks[1], *a)
+        self.encoder_level2 = stage(dim * 2, heads[1], num_blocks[1])
         self.down2_3 = Downsample(dim * 2)
-        self.encoder_level3 = SequentialTransformerBlock(dim * 4, heads[2], num_blocks[2], *a)
+        self.encoder_level3 = stage(dim * 4, heads[2], num_blocks[2])
         self.down3_4 = Downsample(dim * 4)
-        self.latent = SequentialTransformerBlock(dim * 8, heads[3], num_blocks[3], *a)
+        self.latent = stage(dim * 8, heads[3], num_blocks[3])
         self.up4_3 = Upsample(dim * 8)
         self.reduce_chan_level3 = nn.Conv2d(dim * 8, dim * 4, kernel_size=1, bias=bias)
-        self.decoder_level3 = SequentialTransformerBlock(dim * 4, heads[2], num_blocks[2], *a)
+        self.decoder_level3 = stage(dim * 4, heads[2], num_blocks[2])
         self.up3_2 = Upsample(dim * 4)
         self.reduce_chan_level2 = nn.Conv2d(dim * 4, dim * 2, kernel_size=1, bias=bias)
-        self.decoder_level2 = SequentialTransformerBlock(dim * 2, heads[1], num_blocks[1], *a)
+        self.decoder_level2 = stage(dim * 2, heads[1], num_blocks[1])
         self.up2_1 = Upsample(dim * 2)
-        self.decoder_level1 = SequentialTransformerBlock(dim * 2, heads[0], num_blocks[0], *a)
-        self.refinement = SequentialTransformerBlock(dim * 2, heads[0], num_refinement_blocks, *a)
+        self.decoder_level1 = stage(dim * 2, heads[0], num_blocks[0])
+        self.refinement = stage(dim * 2, heads[0], num_refinement_blocks)
         self.dual_pixel_task = dual_pixel_task
         self.scale = scale
         self.output = nn.Conv2d(dim * 2, out_channels, kernel_size=3, stride=1, padding=1, bias=bias)
-        self.apply(self._init_weights)
+        if not _plain_stages:
+            self.apply(self._init_weights)   # (Restormer_origin keeps torch's default init, as in the reference)
         self._cfg = dict(inp_channels=inp_channels, out_channels=out_channels, dim=dim, num_blocks=tuple(num_blocks),
                          num_refinement_blocks=num_refinement_blocks, heads=tuple(heads), ffn_expansion_factor=ffn_expansion_factor,
                          bias=bias, ln_with_bias=LayerNorm_type != "BiasFree")
@@ -158,7 +166,8 @@ class Restormer(nn.Module):
         out = []
         for k in (3, 2, 1):
             st = getattr(self, f"decoder_level{k}")
-            out.append([m for m in (st, st.body) if len(m._forward_hooks) > 0])
+            mods = (st, st.body) if hasattr(st, "body") else (st,)
+            out.append([m for m in mods if len(m._forward_hooks) > 0])
         return out
 
     def forward(self, inp_img, hook=None):
@@ -188,3 +197,21 @@ class Restormer(nn.Module):
             for m in mods:
                 for fn in list(m._forward_hooks.values()):
                     fn(m, (None,), f)
+
+
+@ARCH_REGISTRY.register()
+class Restormer_origin(Restormer):
+    """restormer_arch.py:425-518 - the original Restormer: plain ``nn.Sequential`` stages (state_dict keys
+    ``encoder_level1.0.attn...`` instead of ``encoder_level1.body.0.attn...``), ``WithBias`` LayerNorm by default, no ``scale`` /
+    ``hook`` arguments, torch's default initialisation.  Same parameters in the same order as ``Restormer``, hence the same
+    engine (dcpt_restormer_*) underneath."""
+
+    def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4, heads=[1, 2, 4, 8],
+                 ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias", dual_pixel_task=False, window_size=8):
+        super().__init__(inp_channels=inp_channels, out_channels=out_channels, dim=dim, num_blocks=num_blocks,
+                         num_refinement_blocks=num_refinement_blocks, heads=heads, ffn_expansion_factor=ffn_expansion_factor, bias=bias,
+                         LayerNorm_type=LayerNorm_type, dual_pixel_task=dual_pixel_task, scale=1, window_size=window_size,
+                         _plain_stages=True)
+
+    def forward(self, inp_img):   # :481 - no hook argument
+        return super().forward(inp_img, hook=None)

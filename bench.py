@@ -299,11 +299,17 @@ def run_ours(args):
         sampler.start()
     l0 = lib.dcpt_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]   # per-step spread (median / p10 / p90)
     e0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         step()
+        marks[i + 1].record()
     e1.record()
     barrier()
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+    pct = lambda q: per_step[min(len(per_step) - 1, int(q * len(per_step)))]  # noqa: E731
+    step_ms = {"median": round(pct(0.5), 3), "p10": round(pct(0.1), 3), "p90": round(pct(0.9), 3), "n": len(per_step)}
     launches = lib.dcpt_launch_count() - l0
     if launches_per_step is not None:
         launches = launches_per_step * args.steps           # replayed from the graph: count the captured kernel nodes
@@ -318,7 +324,7 @@ def run_ours(args):
     # ---------------- per-kernel attribution (one extra, untimed, profiled step) ----------------
     roof = None
     if rank == 0:
-        lib.dcpt_prof_enable(2 if args.shapes else 1)
+        lib.dcpt_prof_enable(2)     # per-shape GEMM tags: the dominant KERNEL (one shape), not a blend of shapes
         (eager_step if graph is not None else step)(comm=False)                                   # rank-0 only: must not enter a collective
         rows = prof_table(lib)
         lib.dcpt_prof_enable(0)
@@ -334,12 +340,12 @@ def run_ours(args):
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"kernel": top["tag"], "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
                     "frac": round(ach / pk["hbm"], 4), "traffic": None}
-        try:  # DRAM traffic of the same kernel from the committed ncu --set full capture (per launch), else null
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            key = top["tag"].split(" ")[0]
+        try:  # DRAM traffic of the same kernel + shape from the newest committed ncu --set full capture (per launch), else null
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))     # written by tools/ncu_traffic.py
+            key = " ".join(top["tag"].split(" ")[:2])                                 # "<kernel tag> <MxNxK>"
             if key in tr:
                 roof["traffic"] = tr[key]["bytes"]
-                roof["traffic_note"] = tr[key]["launch"] + "; " + tr["_how"]
+                roof["traffic_note"] = tr[key].get("note", "") + "; " + tr["_how"]
         except Exception:
             pass
         roof.update({"peak_source": pk["src"] + (", sustained (kernel timed inside the step)" if is_gemm else ""),
@@ -423,7 +429,7 @@ def run_ours(args):
                     torch_arm[k]["ours_over_this"] = round(value / torch_arm[k]["value"], 2)
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": round(value, 3), "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": round(ms, 3), "step_ms": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"NAFNet-w64 (enc [1,1,1,28], mid 1, dec [1,1,1,1]) fwd + L1 loss + bwd, "
                                        f"batch {B}x3x256x256 per GPU, all parameter gradients"
@@ -490,8 +496,8 @@ def bench_optimizer(net, pk, e0, e1, iters=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)     # >= 50 timed iterations, median + p10 / p90 reported
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU (BASELINE.json configs[1]: 16)")
     ap.add_argument("--breakdown", action="store_true", help="write gpurun_out/kernel_breakdown.tsv")

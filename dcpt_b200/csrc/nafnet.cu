@@ -279,32 +279,40 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
 struct SideStream {
   cudaStream_t s = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool ok = false;
-};
-SideStream& side_stream() {
-  static SideStream ss;
-  static bool tried = false;
-  if (!tried) {  // created on the first (eager, un-captured) use
+  bool ok = false, tried = false;
+  // created on the first (eager, un-captured) use; owned by a plan (one per engine: two engines on two streams never share
+  // events) or, for the plan-less block ABI, by the calling thread
+  void ensure() {
+    if (tried) return;
     tried = true;
     const char* e = getenv("DCPT_WGRAD_STREAM");
-    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess) {
-      ss.ok = true;
-      for (auto& ev : ss.ev) ss.ok = ss.ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) {
+      ok = true;
+      for (auto& v : ev) ok = ok && cudaEventCreateWithFlags(&v, cudaEventDisableTiming) == cudaSuccess;
     }
   }
+  ~SideStream() {
+    for (auto& v : ev)
+      if (v) cudaEventDestroy(v);
+    if (s) cudaStreamDestroy(s);
+  }
+};
+SideStream& thread_side_stream() {
+  static thread_local SideStream ss;
   return ss;
 }
 
 int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockSaved& sv, const float* x, const float* dout,
                       const bf16* doutT, const float* Sout, float* dx, bf16* dxT, float* Sx, float* const* G, const BlockWork& wk,
-                      int N, int H, int W, int C, cudaStream_t st, const BlockZeros* zeros = nullptr) {
+                      int N, int H, int W, int C, cudaStream_t st, const BlockZeros* zeros = nullptr, SideStream* side = nullptr) {
   const int HW = H * W, M = N * HW;
   const size_t cc = (size_t)C * C;
   float* const G5 = zeros ? zeros->G5 : wk.G;
   float* const G3 = zeros ? zeros->G3 : wk.G;
   float* const Sy = zeros ? zeros->Sy : wk.Sy;
   float* const ds = zeros ? zeros->ds : wk.ds;
-  SideStream& ss = side_stream();
+  SideStream& ss = side ? *side : thread_side_stream();
+  ss.ensure();
   const bool fork = ss.ok && !g_dcpt_prof_on;   // per-kernel profiling keeps everything on one stream
   cudaStream_t sw = fork ? ss.s : st;           // stream of the weight-gradient work
   auto fork_here = [&](int i) -> int {          // side stream waits for everything issued on `st` so far
@@ -402,6 +410,7 @@ struct dcpt_nafnet_plan {
   // middle blocks, the up convs, every decoder and the ending conv are final (i.e. after the backward of encoders.{n_enc-1}.*):
   // a data-parallel caller starts the all-reduce of that contiguous 90 % slice of the flat gradient buffer on a second
   // stream while the shallower levels are still being differentiated (base_model.py:107-118: what DDP's buckets do).
+  mutable SideStream side;  // weight-gradient side stream of this plan's backward (nafblock_bwd_impl)
   void* split_event = nullptr;
   bool split_event_external = true;  // inside a stream capture: external-event node (waited on from outside the graph) or plain
   std::vector<int> hook_blk;
@@ -1038,7 +1047,7 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     zcur += BlockZeros::floats(N, b.C);
     NXT.s = zcur;  // this block's Sx (column sums of dx): its own pre-cleared slice, read by the next block / conv backward
     zcur += ((size_t)b.C + 63) / 64 * 64;
-    DCPT_TRY(nafblock_bwd_impl(P + b.pidx, bpk, bsv, x, CUR.f, CUR.t, CUR.s, NXT.f, NXT.t, NXT.s, G + b.pidx, bw, N, hh, ww, b.C, st, &bz));
+    DCPT_TRY(nafblock_bwd_impl(P + b.pidx, bpk, bsv, x, CUR.f, CUR.t, CUR.s, NXT.f, NXT.t, NXT.s, G + b.pidx, bw, N, hh, ww, b.C, st, &bz, &p->side));
     ci ^= 1;
     return 0;
   };

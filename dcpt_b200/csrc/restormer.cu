@@ -57,11 +57,12 @@ __global__ void pack_cols_kernel(const float* __restrict__ w, bf16* __restrict__
   out[idx] = OP_FROM_F32(c < hid ? w[(size_t)o * hid + c] : 0.f);
 }
 
-// W_eff[n][o][h*c + j] = sum_i Wout[o][h*c + i] * relu(temp[h] * G[n][h*c+i][h*c+j] / (max(|q_i|, eps) * max(|k_j|, eps)))
+// W_eff[n][o][h*c + j] = sum_i Wout[o][h*c + i] * act(temp[h] * G[n][h*c+i][h*c+j] / (max(|q_i|, eps) * max(|k_j|, eps)))
+// act = ReLU (Restormer, restormer_arch.py:136) or a row softmax over j (the PromptIR blocks, promptir_arch.py:139-140)
 // block = (head, image); the c x c attention tile lives in shared memory.
 __global__ void __launch_bounds__(256)
 mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, const float* __restrict__ temp,
-                 const float* __restrict__ wout, bf16* __restrict__ weff, bf16* __restrict__ weffT, int d, int heads) {
+                 const float* __restrict__ wout, bf16* __restrict__ weff, bf16* __restrict__ weffT, int d, int heads, int softmax) {
   extern __shared__ float s_attn[];  // [c][c + 1]
   const int c = d / heads, h = blockIdx.x, n = blockIdx.y;
   const float* Gn = G + (size_t)n * d * d;
@@ -71,9 +72,25 @@ mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, cons
     const int i = idx / c, j = idx - i * c;
     const float nq = fmaxf(sqrtf(sqn[h * c + i]), 1e-12f), nk = fmaxf(sqrtf(sqn[d + h * c + j]), 1e-12f);  // F.normalize eps
     const float a = Gn[(size_t)(h * c + i) * d + h * c + j] / (nq * nk) * t;
-    s_attn[i * (c + 1) + j] = fmaxf(a, 0.f);
+    s_attn[i * (c + 1) + j] = softmax ? a : fmaxf(a, 0.f);   // ReLU: restormer_arch.py:136; softmax: promptir_arch.py:140
   }
   __syncthreads();
+  if (softmax) {  // attn.softmax(dim=-1): one thread per row of the c x c tile
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      float* row = s_attn + i * (c + 1);
+      float m = row[0];
+      for (int j = 1; j < c; ++j) m = fmaxf(m, row[j]);
+      float sum = 0.f;
+      for (int j = 0; j < c; ++j) {
+        const float e = expf(row[j] - m);
+        row[j] = e;
+        sum += e;
+      }
+      const float inv = 1.f / sum;
+      for (int j = 0; j < c; ++j) row[j] *= inv;
+    }
+    __syncthreads();
+  }
   bf16* out = weff + (size_t)n * d * d;
   for (int idx = threadIdx.x; idx < d * c; idx += blockDim.x) {
     const int o = idx / c, j = idx - o * c;
@@ -96,7 +113,7 @@ mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, cons
 __global__ void __launch_bounds__(256)
 mdta_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, const float* __restrict__ sq,
                 const float* __restrict__ temp, const float* __restrict__ wout, float* __restrict__ dwout, float* __restrict__ dtemp,
-                bf16* __restrict__ Bmat, bf16* __restrict__ BmatLo, int d, int heads) {
+                bf16* __restrict__ Bmat, bf16* __restrict__ BmatLo, int d, int heads, int softmax) {
   extern __shared__ float sm[];
   const int c = d / heads, h = blockIdx.x, n = blockIdx.y, hc = h * c;
   float* s_gh = sm;                 // Ghat   [c][c]
@@ -120,10 +137,26 @@ mdta_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, co
     const int i = idx / c, j = idx - i * c;
     const float gh = Gn[(size_t)(hc + i) * d + hc + j] / (s_nq[i] * s_nk[j]);
     s_gh[idx] = gh;
-    s_at[idx] = fmaxf(gh * T, 0.f);
+    s_at[idx] = softmax ? gh * T : fmaxf(gh * T, 0.f);
     s_da[idx] = 0.f;
   }
   __syncthreads();
+  if (softmax) {  // recompute attn = softmax_j(A_ij)
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      float* row = s_at + i * c;
+      float m = row[0];
+      for (int j = 1; j < c; ++j) m = fmaxf(m, row[j]);
+      float sum = 0.f;
+      for (int j = 0; j < c; ++j) {
+        const float e = expf(row[j] - m);
+        row[j] = e;
+        sum += e;
+      }
+      const float inv = 1.f / sum;
+      for (int j = 0; j < c; ++j) row[j] *= inv;
+    }
+    __syncthreads();
+  }
   // dattn and dWout, streaming 64 output channels o at a time through shared memory
   for (int o0 = 0; o0 < d; o0 += 64) {
     const int no = min(64, d - o0);
@@ -149,10 +182,23 @@ mdta_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, co
   }
   // dA, dT, dGhat (in place of attn)
   float dt = 0.f;
-  for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
-    const float dA = s_at[idx] > 0.f ? s_da[idx] : 0.f;
-    dt = fmaf(dA, s_gh[idx], dt);
-    s_at[idx] = dA * T;
+  if (softmax) {  // dA_ij = attn_ij (dattn_ij - sum_k dattn_ik attn_ik): rows are independent
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      float dot = 0.f;
+      for (int j = 0; j < c; ++j) dot = fmaf(s_da[i * c + j], s_at[i * c + j], dot);
+      for (int j = 0; j < c; ++j) {
+        const float dA = s_at[i * c + j] * (s_da[i * c + j] - dot);
+        dt = fmaf(dA, s_gh[i * c + j], dt);
+        s_at[i * c + j] = dA * T;
+      }
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
+      const float dA = s_at[idx] > 0.f ? s_da[idx] : 0.f;
+      dt = fmaf(dA, s_gh[idx], dt);
+      s_at[idx] = dA * T;
+    }
   }
   dt = warp_sum(dt);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dt;
@@ -286,6 +332,7 @@ inline unsigned blocks_for(long long total, int threads = 256) { return (unsigne
 // ------------------------------------ plan ------------------------------------
 struct dcpt_restormer_plan {
   int inp_ch, out_ch, dim, nref, bias, ln_bias;
+  int attn_softmax = 0;  // 0: relu(attn) (Restormer, restormer_arch.py:136); 1: attn.softmax(dim=-1) (PromptIR's blocks, promptir_arch.py:140)
   int nb[4], heads[4];
   double ffn;
   struct ParamInfo { int dims[4]; long long numel; };
@@ -521,7 +568,7 @@ int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
     DCPT_CHECK_ARG(d % b.heads == 0 && smem <= 200 * 1024, DCPT_E_SHAPE, "mdta: dim %d / heads %d unsupported", d, b.heads);
     if (smem > 48 * 1024) DCPT_CUDA(cudaFuncSetAttribute(mdta_weff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DCPT_PROF("mdta_weff", 2.0 * N * d * d * c, 4.0 * N * d * d, st);
-    mdta_weff_kernel<<<dim3(b.heads, N), 256, smem, st>>>(bf.G, bf.sq, P[ix.temp], P[ix.pout], bf.weff, bf.weffT, d, b.heads);
+    mdta_weff_kernel<<<dim3(b.heads, N), 256, smem, st>>>(bf.G, bf.sq, P[ix.temp], P[ix.pout], bf.weff, bf.weffT, d, b.heads, p->attn_softmax);
     DCPT_LAUNCH_CHECK();
   }
   // x2 = x + v * W_eff[image]^T
@@ -596,7 +643,7 @@ int block_bwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
     if (smem > 48 * 1024) DCPT_CUDA(cudaFuncSetAttribute(mdta_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DCPT_PROF("mdta_bwd", 4.0 * N * d * d * c, 12.0 * N * d * d, st);
     mdta_bwd_kernel<<<dim3(b.heads, N), 256, smem, st>>>(wk.dWeff, sv.G, sv.sq, P[ix.temp], P[ix.pout], G[ix.pout], G[ix.temp], wk.Bmat,
-                                                        BmatLo, d, b.heads);
+                                                        BmatLo, d, b.heads, p->attn_softmax);
     DCPT_LAUNCH_CHECK();
   }
   // [dq | dk] = [q | k] (Bmat_hi + Bmat_lo)[n]^T: two passes, fp32 in between
@@ -693,6 +740,11 @@ dcpt_restormer_plan* dcpt_restormer_create(int inp_channels, int out_channels, i
 }
 
 void dcpt_restormer_destroy(dcpt_restormer_plan* plan) { delete plan; }
+int dcpt_restormer_set_attention(dcpt_restormer_plan* plan, int softmax) {
+  DCPT_CHECK_ARG(plan != nullptr, DCPT_E_ARG, "restormer_set_attention: null plan");
+  plan->attn_softmax = softmax != 0;
+  return 0;
+}
 int dcpt_restormer_num_params(const dcpt_restormer_plan* plan) { return (int)plan->params.size(); }
 long long dcpt_restormer_param_shape(const dcpt_restormer_plan* plan, int i, int dims[4]) {
   if (i < 0 || i >= (int)plan->params.size()) return -1;

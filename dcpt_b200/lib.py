@@ -84,6 +84,7 @@ PROTOTYPES = {
     "dcpt_dwconv3x3_gelu_gate_fwd": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "dcpt_restormer_create": (_VP, [_I, _I, _I, C.POINTER(_I), _I, C.POINTER(_I), C.c_double, _I, _I]),
     "dcpt_restormer_destroy": (None, [_VP]),
+    "dcpt_restormer_set_attention": (_I, [_VP, _I]),
     "dcpt_restormer_num_params": (_I, [_VP]),
     "dcpt_restormer_param_shape": (_LL, [_VP, _I, C.POINTER(_I)]),
     "dcpt_restormer_packed_bytes": (_SZ, [_VP]),

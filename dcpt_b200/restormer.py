@@ -19,7 +19,9 @@ from .params import LRUCache, PackedCacheKey, fp16_grad_scale
 
 class RestormerEngine:
     def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=(4, 6, 6, 8), num_refinement_blocks=4, heads=(1, 2, 4, 8),
-                 ffn_expansion_factor=2.66, bias=False, ln_with_bias=False):
+                 ffn_expansion_factor=2.66, bias=False, ln_with_bias=False, attn_softmax=False):
+        """attn_softmax: the transposed attention map goes through softmax(dim=-1) (PromptIR's transformer blocks,
+        promptir_arch.py:140) instead of the fork's ReLU (restormer_arch.py:136)."""
         self.lib = _l.load_library()
         nb = (C.c_int * 4)(*num_blocks)
         hd = (C.c_int * 4)(*heads)
@@ -29,6 +31,8 @@ class RestormerEngine:
             raise _l.DcptError("dcpt_restormer_create: " + self.lib.dcpt_last_error().decode())
         self.plan = C.c_void_p(plan)
         self.dim = dim
+        if attn_softmax:
+            _l.check(self.lib.dcpt_restormer_set_attention(self.plan, 1), "restormer_set_attention")
         self.num_params = self.lib.dcpt_restormer_num_params(self.plan)
         dims = (C.c_int * 4)()
         self.numels = [self.lib.dcpt_restormer_param_shape(self.plan, i, dims) for i in range(self.num_params)]

@@ -271,6 +271,10 @@ dcpt_restormer_plan* dcpt_restormer_create(int inp_channels, int out_channels, i
                                            int num_refinement_blocks, const int* heads, double ffn_expansion_factor, int bias,
                                            int ln_with_bias);
 void dcpt_restormer_destroy(dcpt_restormer_plan* plan);
+/* Activation of the transposed attention map of every block of the plan: 0 (default) relu(attn) as in the fork's Restormer
+ * (restormer_arch.py:135-136: the softmax is commented out), 1 attn.softmax(dim=-1) as in the PromptIR transformer blocks
+ * (promptir_arch.py:108-149, softmax at :140) and the original Restormer.  Forward and backward. */
+int dcpt_restormer_set_attention(dcpt_restormer_plan* plan, int softmax);
 int dcpt_restormer_num_params(const dcpt_restormer_plan* plan);
 long long dcpt_restormer_param_shape(const dcpt_restormer_plan* plan, int i, int dims[4]);
 size_t dcpt_restormer_packed_bytes(const dcpt_restormer_plan* plan);

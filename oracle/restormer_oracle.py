@@ -70,8 +70,9 @@ def _ln(x: Tensor, P: Dict[str, Tensor], prefix: str) -> Tensor:
 # --------------------------------------------------------------------------
 # MDTA — restormer_arch.py:103-145
 # --------------------------------------------------------------------------
-def mdta(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int) -> Tensor:
-    """Transposed (channel) attention with ReLU instead of softmax (:135-136)."""
+def mdta(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int, softmax: bool = False) -> Tensor:
+    """Transposed (channel) attention with ReLU instead of softmax (:135-136).  ``softmax=True``: the PromptIR transformer
+    blocks' variant (promptir_arch.py:108-149: identical but for ``attn.softmax(dim=-1)`` at :140)."""
     b, c, h, w = x.shape
     qkv = _q(F.conv2d(x, _q(P[prefix + ".qkv.weight"]), P.get(prefix + ".qkv.bias")))                 # :124 1x1, d -> 3d
     qkv = _q(F.conv2d(qkv, P[prefix + ".qkv_dwconv.weight"], P.get(prefix + ".qkv_dwconv.bias"), padding=1,
@@ -84,7 +85,7 @@ def mdta(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int) -> Tensor:
     q = F.normalize(q, dim=-1)                                                                         # :131-132 (eps 1e-12)
     k = F.normalize(k, dim=-1)
     attn = (q @ k.transpose(-2, -1)) * P[prefix + ".temperature"].view(1, heads, 1, 1)                 # :134
-    attn = F.relu(attn)                                                                                # :136
+    attn = attn.softmax(dim=-1) if softmax else F.relu(attn)                                           # :136 / promptir_arch.py:140
     if _Q is not None:  # the kernels fold attn into the projection: W_eff = W_out * blockdiag(attn), rounded to bf16
         wo = P[prefix + ".project_out.weight"].reshape(c, heads, ch)                                   # [o, head, i]
         weff = _q(torch.einsum("ohi,bhij->bohj", wo, attn).reshape(b, c, c))
@@ -105,9 +106,9 @@ def gdfn(x: Tensor, P: Dict[str, Tensor], prefix: str) -> Tensor:
     return F.conv2d(y, _q(P[prefix + ".project_out.weight"]), P.get(prefix + ".project_out.bias"))     # :99
 
 
-def transformer_block(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int) -> Tensor:
-    """restormer_arch.py:156-159."""
-    x = x + mdta(_ln(x, P, prefix + ".norm1"), P, prefix + ".attn", heads)
+def transformer_block(x: Tensor, P: Dict[str, Tensor], prefix: str, heads: int, softmax: bool = False) -> Tensor:
+    """restormer_arch.py:156-159 (``softmax=True``: promptir_arch.py:171-186, the same block around the softmax attention)."""
+    x = x + mdta(_ln(x, P, prefix + ".norm1"), P, prefix + ".attn", heads, softmax)
     x = x + gdfn(_ln(x, P, prefix + ".norm2"), P, prefix + ".ffn")
     return x
 

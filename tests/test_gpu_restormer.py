@@ -189,6 +189,68 @@ def test_transformer_block_backward_golden(lib, golden_dir, dim):
             assert float(g_.abs().max()) == 0.0, k
 
 
+def _softmax_case(dim):
+    if dim == 48:
+        return dict(dim=48, num_blocks=(1, 1, 1, 1), heads=(1, 2, 4, 8), ln_with_bias=True), 0
+    if dim == 96:
+        return dict(dim=48, num_blocks=(1, 1, 1, 1), heads=(1, 2, 4, 8), ln_with_bias=True), 1
+    return dict(dim=32, num_blocks=(1, 1, 1, 1), heads=(1, 4, 4, 8)), 1
+
+
+@pytest.mark.parametrize("dim", [48, 96, 64])
+def test_promptir_softmax_block_golden(lib, golden_dir, dim):
+    """the PromptIR transformer block = Restormer's block with `attn.softmax(dim=-1)` instead of ReLU
+    (promptir_arch.py:108-186, softmax at :140), forward + backward against the REAL reference's outputs / autograd gradients
+    (tests/golden/promptir_block_d*.npz).  Same kernels as MDTA with the plan's attention flag set
+    (dcpt_restormer_set_attention): softmax of the c x c map in mdta_weff, its Jacobian in mdta_bwd."""
+    from dcpt_b200 import lib as L
+    from dcpt_b200.restormer import RestormerEngine
+    z = load(golden_dir, f"promptir_block_d{dim}.npz")
+    cfg, st = _softmax_case(dim)
+    eng = RestormerEngine(num_refinement_blocks=1, attn_softmax=True, **cfg)
+    shapes = RO.restormer_param_shapes(dim=cfg["dim"], num_blocks=cfg["num_blocks"], num_refinement_blocks=1, heads=cfg["heads"],
+                                       LayerNorm_type="WithBias" if cfg.get("ln_with_bias") else "BiasFree")
+    pref = f"{['encoder_level1', 'encoder_level2'][st]}.body.0."
+    sd = {k: torch.zeros(s_) for k, s_ in shapes.items()}
+    for k in z:
+        if k.startswith("p."):
+            assert tuple(sd[pref + k[2:]].shape) == tuple(z[k].shape), k
+            sd[pref + k[2:]] = z[k].clone()
+    names = list(sd.keys())
+    params = [v.cuda().contiguous() for v in sd.values()]
+    grads = [torch.zeros_like(p_) for p_ in params]
+    packed = eng.packed_for(params)
+    x = z["x"]
+    N, _, H, W = x.shape
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    dyd = z["dy"].permute(0, 2, 3, 1).contiguous().cuda()
+    yd, dxd = torch.empty_like(xd), torch.empty_like(xd)
+    saved = torch.empty(lib.dcpt_restormer_block_saved_bytes(eng.plan, st, 0, N, H, W), dtype=torch.uint8, device="cuda")
+    work = torch.empty(lib.dcpt_restormer_block_workspace_bytes(eng.plan, st, 0, N, H, W), dtype=torch.uint8, device="cuda")
+    pp = L.ptr_array([p_.data_ptr() for p_ in params])
+    gp = L.ptr_array([g_.data_ptr() for g_ in grads])
+    L.check(lib.dcpt_restormer_block_fwd_train(eng.plan, st, 0, pp, _ptr(packed), _ptr(xd), _ptr(yd), _ptr(saved), N, H, W, _stream()), "fwd_train")
+    L.check(lib.dcpt_restormer_block_bwd(eng.plan, st, 0, pp, _ptr(packed), _ptr(saved), _ptr(xd), _ptr(dyd), _ptr(dxd), gp, _ptr(work),
+                                         N, H, W, _stream()), "block_bwd")
+    torch.cuda.synchronize()
+    e_y, e_dx = rel(yd.permute(0, 3, 1, 2), z["y"]), rel(dxd.permute(0, 3, 1, 2), z["dx"])
+    errs = {k[len(pref):]: rel(g_, z["g." + k[len(pref):]]) for k, g_ in zip(names, grads) if k.startswith(pref)}
+    # and the ReLU plan on the same weights is a different function (the flag is live)
+    eng_relu = RestormerEngine(num_refinement_blocks=1, **cfg)
+    y2 = xd.clone()
+    ws = torch.empty(eng_relu.lib.dcpt_restormer_workspace_bytes(eng_relu.plan, N, H << st, W << st), dtype=torch.uint8, device="cuda")
+    L.check(lib.dcpt_restormer_block_fwd(eng_relu.plan, st, 0, pp, _ptr(eng_relu.packed_for(params)), _ptr(y2), _ptr(ws), N, H, W, _stream()), "block_fwd")
+    print(f"PromptIR softmax block d={dim}: out {e_y:.2e}, dx {e_dx:.2e}; param grads worst {max(errs.values()):.2e} "
+          f"({max(errs, key=errs.get)}), median {float(np.median(list(errs.values()))):.2e}; ReLU plan differs by {rel(y2, yd):.2e}")
+    assert e_y < tol(6e-3) and rel(y2, yd) > 1e-2
+    assert e_dx < tol(3e-2, 8e-3)
+    # (the temperature gradient is ONE scalar per head - a sum of signed terms over the c x c map: 6.9e-2 on the single-head
+    #  fixture in the bf16 build, 8e-3 in the fp16 build)
+    others = {k: v for k, v in errs.items() if not k.endswith("temperature")}
+    assert errs["attn.temperature"] < tol(0.15, 2e-2)
+    assert max(others.values()) < tol(3e-2, 5e-3) and float(np.median(list(errs.values()))) < tol(1.5e-2, 3e-3), errs
+
+
 def _net(cfg):
     from basicsr.archs import build_network
     return build_network(dict(type="Restormer", window_size=8, **cfg)).cuda()
@@ -384,6 +446,33 @@ def test_restormer_dcpt_hook_gradients_golden(golden_dir):
     opt_g.step(); opt_h.step()
     for h in hooks:
         h.remove()
+
+
+def test_restormer_origin_vs_oracle():
+    """`Restormer_origin` (restormer_arch.py:425-518; WithBias LayerNorm, plain nn.Sequential stages): registry-built, weights
+    loaded under ITS key names, forward vs the fp32 oracle (keys mapped to Restormer's `.body.` form) - and identical to the
+    `Restormer(LayerNorm_type="WithBias")` mirror holding the same weights (same engine underneath)."""
+    import re
+    from basicsr.archs import build_network
+    cfg = dict(dim=32, num_blocks=[1, 1, 1, 2], num_refinement_blocks=2, heads=[1, 2, 4, 8])
+    sd = RO.random_restormer_state_dict(seed=5, gain=0.6, LayerNorm_type="WithBias", **cfg)
+    net = build_network(dict(type="Restormer_origin", **cfg)).cuda()
+    strip = lambda k: re.sub(r"\.body\.(\d+)\.", r".\1.", k) if not k.startswith(("down", "up")) else k   # noqa: E731
+    net.load_state_dict({strip(k): v for k, v in sd.items()}, strict=True)
+    twin = build_network(dict(type="Restormer", LayerNorm_type="WithBias", **cfg)).cuda()
+    twin.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(2, 3, 32, 48, generator=g)
+    with torch.no_grad():
+        out, out_twin = net(x.cuda()), twin(x.cuda())
+        ref = RO.restormer_fwd(x, sd, cfg["num_blocks"], cfg["num_refinement_blocks"], cfg["heads"])
+    e, et = rel(out - x.cuda(), ref - x), rel(out, out_twin)
+    print(f"Restormer_origin: rel-L2 of (out - inp) {e:.2e} vs oracle; vs the Restormer(WithBias) mirror {et:.2e}")
+    assert rel(out, ref) < tol(5e-3) and e < tol(3e-2, 4e-3) and et < 1e-4
+    # training step through the same autograd Function
+    loss = (net(x.cuda()) - 0.5).abs().mean()
+    loss.backward()
+    assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in net.parameters())
 
 
 def test_restormer_refuses_cpu():

@@ -85,3 +85,57 @@ print("REL", float((a - b).norm() / b.norm()))
     assert r.returncode == 0, r.stderr[-2000:]
     v = float(r.stdout.strip().split("REL")[-1])
     assert v < RTOL, v
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/basicsr"), reason="reference not present")
+def test_restormer_origin_contract_vs_live_reference():
+    """`Restormer_origin` (restormer_arch.py:425-518): this repo's mirror exposes exactly the reference's state_dict keys and
+    shapes (strict loading both ways), and the reference's forward equals the oracle once the keys are mapped to Restormer's
+    (`stage.j.*` -> `stage.body.j.*`): same network, different containers."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import json, re, sys, torch
+sys.path.insert(0, %r)
+import basicsr.archs as ours_archs                       # this repo's mirror first
+from basicsr.archs.restormer_arch import Restormer_origin as Mine
+cfg = dict(dim=24, num_blocks=[1, 1, 1, 2], num_refinement_blocks=2, heads=[1, 2, 4, 8])
+mine = {k: tuple(v.shape) for k, v in Mine(**cfg).state_dict().items()}
+from oracle._ref_import import import_reference
+from oracle import restormer_oracle as RO
+import_reference()
+from basicsr.archs.restormer_arch import Restormer_origin as Ref
+net = Ref(**cfg)
+ref = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+stages = "encoder_level1|encoder_level2|encoder_level3|latent|decoder_level3|decoder_level2|decoder_level1|refinement"
+to_body = lambda k: re.sub(r"^(%%s)\.(\d+)\." %% stages, r"\1.body.\2.", k)
+sd = RO.random_restormer_state_dict(seed=5, LayerNorm_type="WithBias", **cfg)
+net.load_state_dict({k: sd[to_body(k)] for k in ref}, strict=True)
+x = torch.rand(1, 3, 16, 24)
+with torch.no_grad():
+    a = net(x)
+    b = RO.restormer_fwd(x, sd, cfg["num_blocks"], cfg["num_refinement_blocks"], cfg["heads"])
+print("RESULT " + json.dumps({"same_keys": list(mine.items()) == list(ref.items()), "n": len(ref), "rel": float((a - b).norm() / b.norm())}))
+''' % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert res["same_keys"] and res["n"] > 100 and res["rel"] < RTOL, res
+
+
+@pytest.mark.parametrize("dim", [48, 96, 64])
+def test_promptir_softmax_block_golden(golden_dir, dim):
+    """The softmax-MDTA transformer block of PromptIR (promptir_arch.py:108-186; SURVEY.md §8(f) row 3): the oracle with
+    ``softmax=True`` against outputs / gradients of the reference's own module (tests/golden/make_golden_promptir.py)."""
+    z = load(golden_dir, f"promptir_block_d{dim}.npz")
+    sd = {"blk." + k[2:]: v.clone().requires_grad_(True) for k, v in z.items() if k.startswith("p.")}
+    x = z["x"].clone().requires_grad_(True)
+    y = RO.transformer_block(x, sd, "blk", int(z["heads"]), softmax=True)
+    assert rel(y, z["y"]) < RTOL
+    assert rel(RO.transformer_block(z["x"], {k: v.detach() for k, v in sd.items()}, "blk", int(z["heads"])), z["y"]) > 1e-3   # ReLU differs
+    y.backward(z["dy"])
+    assert rel(x.grad, z["dx"]) < RTOL
+    for k, v in sd.items():
+        assert rel(v.grad, z["g." + k[4:]]) < 1e-4, k
