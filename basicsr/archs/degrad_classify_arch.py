@@ -82,3 +82,31 @@ class PromptIR_NoImg_DC(nn.Module):
     def forward(self, lq, features):
         """``lq`` is unused, as in the reference (:622-641).  features: fine -> coarse, logical NCHW CUDA tensors."""
         return dchead_apply(self._engine, list(features), list(self.parameters()))
+
+
+@ARCH_REGISTRY.register()
+class PromptIR_DC(PromptIR_NoImg_DC):
+    """degrad_classify_arch.py:480-556: the classifier variant that embeds the degraded image itself,
+    ``lq_feats = conv_embed(lq)`` with ``conv_embed = Conv2d(3, f0, 7, stride 2, pad 3) + LayerNorm(f0)`` (:497-500), before the
+    same feature-mixing trunk.  ``features[0]`` therefore lives at half the image resolution (the reference pairs this head
+    with token backbones whose features are resampled; NAFNet / Restormer decoder features at full resolution go with
+    ``PromptIR_NoImg_DC``)."""
+
+    def __init__(self, feature_dims, num_res_blocks=2, num_classes=3):
+        nn.Module.__init__(self)
+        self.feature_dims = list(feature_dims)
+        self.conv_embed = nn.Sequential(nn.Conv2d(3, self.feature_dims[0], 7, 2, 3), LayerNorm(self.feature_dims[0]))
+        self.bottleneck_layers = nn.ModuleList()
+        self.downsample_layers = nn.ModuleList()
+        for l, f in enumerate(self.feature_dims):
+            self.bottleneck_layers.append(nn.Sequential(*_make_stage(num_res_blocks, f)))
+            nxt = self.feature_dims[l + 1] if l < len(self.feature_dims) - 1 else f
+            self.downsample_layers.append(nn.Sequential(nn.Conv2d(f, nxt, 1, bias=False), nn.MaxPool2d(2, 2), nn.ReLU()))
+        self.last_stage = nn.Sequential(*_make_stage(num_res_blocks, self.feature_dims[-1]))
+        self.mixing_weights = nn.Parameter(torch.ones(len(self.bottleneck_layers)), requires_grad=True)
+        self.fc = nn.Linear(self.feature_dims[-1], num_classes)
+        self._engine = DCHeadEngine(self.feature_dims, num_res_blocks, num_classes, img_embed=True)
+        assert [k for k, _ in self.named_parameters()] == self._engine.names, "parameter order differs from the C-side plan"
+
+    def forward(self, lq, features):
+        return dchead_apply(self._engine, list(features), list(self.parameters()), lq=lq)

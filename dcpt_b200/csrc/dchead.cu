@@ -385,6 +385,32 @@ __global__ void finish_conv3x3_kernel(const float* __restrict__ G, float* __rest
 
 }  // namespace
 
+// im2col of conv_embed's 7x7 stride-2 pad-3 convolution on the 3-channel image (PromptIR_DC, degrad_classify_arch.py:497-500):
+// P[(n, ho, wo)][ci * 49 + ky * 7 + kx] = img[n][ci][2 ho + ky - 3][2 wo + kx - 3] (zero outside), columns 147..159 zero, so the
+// conv is the GEMM P [M, 160] x W [f0, 160]^T with W = weight.view(f0, 147) zero-padded - same column order as the parameter.
+__global__ void __launch_bounds__(256)
+im2col7s2_kernel(const float* __restrict__ img, bf16* __restrict__ P, int N, int H, int W, int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * 20;  // 20 vectors of 8 columns per output pixel
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % 20);
+    const long long px = idx / 20;
+    const int wo = (int)(px % Wo), ho = (int)((px / Wo) % Ho), n = (int)(px / ((long long)Wo * Ho));
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int col = v * 8 + k;
+      float x = 0.f;
+      if (col < 147) {
+        const int ci = col / 49, r = col - ci * 49, ky = r / 7, kx = r - ky * 7;
+        const int y = 2 * ho + ky - 3, xx = 2 * wo + kx - 3;
+        if (y >= 0 && y < H && xx >= 0 && xx < W) x = __ldg(img + (((size_t)n * 3 + ci) * H + y) * W + xx);
+      }
+      f[k] = x;
+    }
+    stg16(P + px * 160 + v * 8, pack8(f));
+  }
+}
+
 int ln_act_fwd_launch(const bf16* x, const float* w, const float* b, const bf16* resid, bf16* y, float* stats, int M, int C, int relu,
                       float eps, cudaStream_t st) {
   DCPT_CHECK_ARG(M > 0 && C >= 8 && C % 8 == 0 && C <= 1024, DCPT_E_SHAPE, "ln_act: need C %% 8 == 0 and 8 <= C <= 1024 (C=%d)", C);
@@ -488,6 +514,18 @@ int finish_conv3x3_launch(const float* G, float* dw, int Cout, int Cin, cudaStre
   const long long total = (long long)Cout * Cin * 9;
   DCPT_PROF("finish_conv3x3", 1.0 * total, 12.0 * total, st);
   finish_conv3x3_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(G, dw, Cout, Cin);
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int im2col7s2_launch(const float* img, bf16* P, int N, int H, int W, cudaStream_t st) {
+  DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "im2col7s2: bad shape");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * 20;
+  DCPT_PROF("im2col7s2", 0.0, 4.0 * 3 * N * H * W + 320.0 * N * Ho * Wo, st);
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col7s2_kernel<<<(unsigned)blocks, 256, 0, st>>>(img, P, N, H, W, Ho, Wo);
   DCPT_LAUNCH_CHECK();
   return 0;
 }

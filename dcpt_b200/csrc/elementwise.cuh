@@ -95,3 +95,4 @@ int meanpool_fc_bwd_launch(const float* dlogits, const float* pooled, const floa
 int add_bf16_launch(const bf16* a, const bf16* b, bf16* out, long long n, cudaStream_t st);
 int pack_conv3x3_launch(const float* w, bf16* out, int Cout, int Cin, int dgrad, cudaStream_t st);
 int finish_conv3x3_launch(const float* G, float* dw, int Cout, int Cin, cudaStream_t st);
+int im2col7s2_launch(const float* img, bf16* P, int N, int H, int W, cudaStream_t st);  // PromptIR_DC conv_embed patches [M, 160]

@@ -1193,6 +1193,9 @@ int dcpt_meanpool_fc_bwd(const float* dlogits, const float* pooled, const float*
                          int N, int HW, int C, int K, dcpt_stream_t stream) {
   return meanpool_fc_bwd_launch(dlogits, pooled, weight, dweight, dbias, dx, N, HW, C, K, ST(stream));
 }
+int dcpt_im2col7x7s2(const float* img, void* patches_bf16, int N, int H, int W, dcpt_stream_t stream) {
+  return im2col7s2_launch(img, BF(patches_bf16), N, H, W, ST(stream));
+}
 int dcpt_add_bf16(const void* a, const void* b, void* out, long long n, dcpt_stream_t stream) {
   return add_bf16_launch(CBF(a), CBF(b), BF(out), n, ST(stream));
 }

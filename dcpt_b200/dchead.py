@@ -23,14 +23,20 @@ def _bottleneck_names(prefix):
 
 
 class DCHeadEngine:
-    def __init__(self, feature_dims, num_res_blocks=2, num_classes=3):
+    def __init__(self, feature_dims, num_res_blocks=2, num_classes=3, img_embed=False):
+        """img_embed: the `PromptIR_DC` variant (degrad_classify_arch.py:480-556): the trunk starts from
+        conv_embed(lq) = LayerNorm(Conv2d(3, f0, 7, stride 2, pad 3)(lq)) instead of nothing, so features[i] live at
+        H/2^(i+1) (token backbones); `PromptIR_NoImg_DC` (:558-641) ignores lq."""
         self.lib = _l.load_library()
         self.dims = list(feature_dims)
         self.nb = num_res_blocks
         self.k = num_classes
+        self.embed = bool(img_embed)
         self.grad_sync = None      # set by dcpt_b200.dist.FlatGradDataParallel: callable(flat fp32 gradient buffer)
-        # parameter order == reference named_parameters() (degrad_classify_arch.py:577-620)
+        # parameter order == reference named_parameters() (degrad_classify_arch.py:497-547 / :577-620)
         names = ["mixing_weights"]
+        if self.embed:
+            names += ["conv_embed.0.weight", "conv_embed.0.bias", "conv_embed.1.weight", "conv_embed.1.bias"]
         for i in range(len(self.dims)):
             for j in range(self.nb):
                 names += _bottleneck_names(f"bottleneck_layers.{i}.{j}.")
@@ -74,6 +80,13 @@ class DCHeadEngine:
                 conv3(n)
             elif n.endswith("conv1.weight") or n.endswith("conv3.weight") or n.startswith("downsample_layers"):
                 mat(n)
+        if self.embed:     # conv_embed weight as a GEMM operand [f0, 160]: weight.view(f0, 147) zero-padded (dcpt_im2col7x7s2 columns)
+            w = P("conv_embed.0.weight")
+            wp = torch.zeros(w.shape[0], 160, dtype=torch.float32, device=dev)
+            wp[:, :147] = w.reshape(w.shape[0], 147)
+            a = torch.empty(w.shape[0], 160, dtype=_l.operand_dtype(), device=dev)
+            _l.check(self.lib.dcpt_pack_matrix(_p(wp), _p(a), w.shape[0], 160, 0, _stream()), "pack_matrix")
+            pk["conv_embed.0.weight"] = (a, None)
         self._packed = pk
         return pk
 
@@ -86,11 +99,11 @@ class DCHeadEngine:
                  "ln_act_fwd")
         return y, stats
 
-    def _ln_bwd(self, dy, y, x, stats, w, gw, gb, want_dres):
+    def _ln_bwd(self, dy, y, x, stats, w, gw, gb, want_dres, relu=True):
         M, Cc = x.shape
         dx = torch.empty_like(x)                                   # bf16: operand of the following dgrad / wgrad GEMMs
         dres = torch.empty(M, Cc, dtype=torch.float32, device=x.device) if want_dres else None
-        _l.check(self.lib.dcpt_ln_act_bwd(_p(dy), _p(y), _p(x), _p(stats), _p(w), _p(dx), _p(dres), _p(gw), _p(gb), M, Cc, 1,
+        _l.check(self.lib.dcpt_ln_act_bwd(_p(dy), _p(y), _p(x), _p(stats), _p(w), _p(dx), _p(dres), _p(gw), _p(gb), M, Cc, int(relu),
                                           _stream()), "ln_act_bwd")
         return dx, dres
 
@@ -126,8 +139,9 @@ class DCHeadEngine:
         return gemm(dt1, pk[prefix + "conv1.weight"][1], resid=dres, out_dtype=torch.float32)   # + shortcut gradient, fused
 
     # ---- whole head ---------------------------------------------------------------------------------
-    def forward(self, params, feats):
-        """feats[i]: fp32 NHWC [N, H>>i, W>>i, dims[i]] (contiguous).  Returns (logits fp32 [N, K], ctx)."""
+    def forward(self, params, feats, lq=None):
+        """feats[i]: fp32 NHWC [N, H>>i, W>>i, dims[i]] (contiguous).  Returns (logits fp32 [N, K], ctx).
+        lq (fp32 NCHW) is read only by the img_embed (PromptIR_DC) variant."""
         for p in params:
             if not p.is_cuda:
                 raise _l.DcptError("dcpt_b200 has no CPU path: move the classifier head to a CUDA device")
@@ -135,6 +149,19 @@ class DCHeadEngine:
         mw = torch.softmax(params[0].detach().float(), dim=0).contiguous()     # 1-D softmax of len(dims) scalars (:633)
         ctx = {"mw": mw, "stages": [], "feats": feats}
         z = None
+        if self.embed:      # lq_feats = conv_embed(lq) (:549): 7x7 stride-2 conv as im2col + GEMM (+ bias), then channel LayerNorm
+            if lq is None or not lq.is_cuda:
+                raise _l.DcptError("PromptIR_DC needs the degraded image `lq` on the CUDA device")
+            lq = lq.detach().contiguous().float()
+            N, _, H, W = lq.shape
+            Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            patches = torch.empty(N * Ho * Wo, 160, dtype=_l.operand_dtype(), device=lq.device)
+            _l.check(self.lib.dcpt_im2col7x7s2(_p(lq), _p(patches), N, H, W, _stream()), "im2col7x7s2")
+            t0 = gemm(patches, pk["conv_embed.0.weight"][0], bias=params[self.index["conv_embed.0.bias"]])
+            z, s0 = self._ln(t0, params[self.index["conv_embed.1.weight"]], params[self.index["conv_embed.1.bias"]], None, False)
+            ctx["embed"] = (patches, t0, z, s0)
+            if tuple(feats[0].shape[:3]) != (N, Ho, Wo):
+                raise _l.DcptError(f"PromptIR_DC: features[0] must be {Ho}x{Wo} (conv_embed halves the resolution), got {tuple(feats[0].shape)}")
         for i, f in enumerate(feats):
             N, H, W, Cc = f.shape
             assert Cc == self.dims[i] and f.dtype == torch.float32 and f.is_contiguous()
@@ -204,6 +231,16 @@ class DCHeadEngine:
             _l.check(self.lib.dcpt_mix_bwd(_p(dx), _p(f), _p(ctx["mw"][i:i + 1]), _p(dfeats[i]), _p(dmw[i:i + 1]), f.numel(), _stream()),
                      "mix_bwd")
             # dx (= d z_in) is also the gradient of the previous stage's pooled output (z = prev + mw * feat)
+        if self.embed:      # dx = d(z_in of stage 0) = d(conv_embed output): LayerNorm', then the conv's weight / bias gradients
+            patches, t0, z0, s0 = ctx["embed"]
+            gi = self.index
+            dt0, _ = self._ln_bwd(dx, z0, t0, s0, params[gi["conv_embed.1.weight"]], grads[gi["conv_embed.1.weight"]],
+                                  grads[gi["conv_embed.1.bias"]], False, relu=False)
+            f0 = t0.shape[1]
+            gw = torch.zeros(f0, 160, dtype=torch.float32, device=dev)
+            gemm(dt0, patches, a_mn=True, b_mn=True, accumulate_into=gw, splits=0)
+            grads[gi["conv_embed.0.weight"]].add_(gw[:, :147].reshape(grads[gi["conv_embed.0.weight"]].shape))
+            grads[gi["conv_embed.0.bias"]].add_(dt0.float().sum(0))
         mw = ctx["mw"]
         grads[0].copy_((mw * (dmw - (dmw * mw).sum())).view(grads[0].shape))   # softmax backward on len(dims) scalars
         if sc is not None:
@@ -216,12 +253,12 @@ class DCHeadEngine:
 
 class _DCHeadFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, n_feats, *args):
+    def forward(ctx, engine, n_feats, lq, *args):
         feats, params = args[:n_feats], args[n_feats:]
         # features arrive as logical NCHW (channels_last memory from the NAFNet function, or plain NCHW): make NHWC fp32
         fh = [f.detach().permute(0, 2, 3, 1).contiguous().float() for f in feats]
         dparams = [p.detach().contiguous() for p in params]
-        logits, c = engine.forward(dparams, fh)
+        logits, c = engine.forward(dparams, fh, lq=lq)
         ctx.engine, ctx.c, ctx.params, ctx.n_feats = engine, c, dparams, n_feats
         return logits
 
@@ -229,8 +266,8 @@ class _DCHeadFunction(torch.autograd.Function):
     def backward(ctx, dlogits):
         dfeats, grads = ctx.engine.backward(ctx.params, ctx.c, dlogits)
         ctx.c = None
-        return (None, None) + tuple(d.permute(0, 3, 1, 2) for d in dfeats) + tuple(grads)
+        return (None, None, None) + tuple(d.permute(0, 3, 1, 2) for d in dfeats) + tuple(grads)   # (lq is data: no gradient)
 
 
-def dchead_apply(engine, feats, params):
-    return _DCHeadFunction.apply(engine, len(feats), *feats, *params)
+def dchead_apply(engine, feats, params, lq=None):
+    return _DCHeadFunction.apply(engine, len(feats), lq if engine.embed else None, *feats, *params)

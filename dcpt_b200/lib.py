@@ -78,6 +78,7 @@ PROTOTYPES = {
     "dcpt_maxpool2_relu_bwd": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "dcpt_meanpool_fc_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "dcpt_meanpool_fc_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "dcpt_im2col7x7s2": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "dcpt_add_bf16": (_I, [_VP, _VP, _VP, _LL, _VP]),
     "dcpt_layernorm_rows_fwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _F, _I, _VP]),
     "dcpt_dwconv3x3_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),

@@ -239,6 +239,10 @@ int dcpt_meanpool_fc_bwd(const float* dlogits, const float* pooled, const float*
                          int N, int HW, int C, int K, dcpt_stream_t stream);
 
 /* out = a + b (bf16, n elements): sums the two gradient paths of a residual block. */
+/* Patch matrix of `conv_embed` = Conv2d(3, f0, 7, stride 2, padding 3) of PromptIR_DC (degrad_classify_arch.py:497-500):
+ * img fp32 NCHW [N,3,H,W] -> patches bf16 [N*Ho*Wo, 160], Ho = (H-1)/2+1, column ci*49 + ky*7 + kx (= the layout of
+ * weight.view(f0, 147)), columns 147..159 zero; the convolution is then dcpt_gemm_bf16 against the weight padded to 160. */
+int dcpt_im2col7x7s2(const float* img, void* patches_bf16, int N, int H, int W, dcpt_stream_t stream);
 int dcpt_add_bf16(const void* a, const void* b, void* out, long long n, dcpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -366,3 +366,38 @@ def test_dcpt_step_full_width_one_image():
         assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, k
     for h in hooks:
         h.remove()
+
+
+def test_promptir_dc_img_golden(golden_dir):
+    """`PromptIR_DC` (degrad_classify_arch.py:480-556, row a11): registry-built, strict load of the reference's keys,
+    conv_embed = 7x7 stride-2 conv (im2col + tcgen05 GEMM) + LayerNorm on lq, then the shared trunk - logits and the gradients of
+    the late layers / fc / conv_embed against the REAL reference's fp32 golden (tests/golden/dchead_img.npz)."""
+    from basicsr.archs import build_network
+    z = np.load(os.path.join(golden_dir, "dchead_img.npz"))
+    dims = z["dims"].tolist()
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p.")}
+    head = build_network(dict(type="PromptIR_DC", feature_dims=dims, num_res_blocks=2, num_classes=5)).cuda()
+    head.load_state_dict(sd, strict=True)
+    lq = torch.from_numpy(z["lq"]).cuda()
+    feats = [torch.from_numpy(z[f"feat{i}"]).cuda().requires_grad_(True) for i in range(len(dims))]
+    logits = head(lq, feats)
+    F.cross_entropy(logits, torch.from_numpy(z["labels"]).cuda()).backward()
+    e_log = rel(logits, z["logits"])
+    eg = {k: rel(p.grad, z["g." + k]) for k, p in head.named_parameters()}
+    groups = {}
+    for k, v in eg.items():
+        gname = ".".join(k.split(".")[:2]) if k[0] in "bl" else k.split(".")[0]
+        groups.setdefault(gname, []).append(v)
+    for gname, vs in groups.items():
+        report(f"PromptIR_DC grads vs fp32 golden [{gname}]", worst=max(vs), median=float(np.median(vs)))
+    report("PromptIR_DC vs fp32 golden", logits=e_log, dfeats_worst=max(rel(f.grad, z[f"dfeat{i}"]) for i, f in enumerate(feats)))
+    assert e_log < tol(1e-2, 1e-3)
+    assert max(groups["fc"]) < tol(1e-2, 1e-3) and max(groups["last_stage.0"] + groups["last_stage.1"]) < tol(8e-2, 3e-2)
+    assert all(torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0 for p in head.parameters())
+    # the embedding path in isolation: head(lq, zero features) depends on lq only through conv_embed
+    with torch.no_grad():
+        a = head(lq, [torch.zeros_like(f) for f in feats])
+        b = head(lq.flip(3), [torch.zeros_like(f) for f in feats])
+        from oracle import dchead_oracle as D
+        ref = D.dchead_fwd([torch.zeros(f.shape) for f in feats], sd, lq=torch.from_numpy(z["lq"]))
+    assert rel(a, ref) < tol(1e-2, 1e-3) and rel(a, b) > 1e-3

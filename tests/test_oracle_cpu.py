@@ -148,3 +148,21 @@ def test_nafnet_tlc_golden(golden_dir):
     assert rel(out, z["out"]) < RTOL and rel(small, z["out_small"]) < RTOL
     assert rel(base, z["out"]) > 5e-3          # the fixture separates local from global pooling
     assert O.tlc_kernels((1, 3, 128, 128), 5) == [(192, 192), (96, 96), (48, 48), (24, 24), (12, 12)]
+
+
+def test_dchead_img_golden(golden_dir):
+    """PromptIR_DC (conv_embed 7x7 stride 2 + LayerNorm on lq, degrad_classify_arch.py:480-556): the oracle against logits /
+    gradients of the reference's own module (tests/golden/make_golden_dchead_img.py)."""
+    from oracle import dchead_oracle as D
+    z = load(golden_dir, "dchead_img.npz")
+    dims = z["dims"].tolist()
+    sd = {k[2:]: v.clone().requires_grad_(True) for k, v in z.items() if k.startswith("p.")}
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == D.dchead_param_shapes(dims, 2, 5, img_embed=True)
+    feats = [z[f"feat{i}"].clone().requires_grad_(True) for i in range(len(dims))]
+    logits = D.dchead_fwd(feats, sd, lq=z["lq"])
+    assert rel(logits, z["logits"]) < RTOL
+    torch.nn.functional.cross_entropy(logits, z["labels"]).backward()
+    for i, f in enumerate(feats):
+        assert rel(f.grad, z[f"dfeat{i}"]) < 1e-4
+    for k, v in sd.items():
+        assert rel(v.grad, z["g." + k]) < 2e-4, k
