@@ -20,6 +20,7 @@ enum GemmEpilogue {
   EPI_STORE_TMA = 5, // internal: EPI_STORE with the residual tile TMA-loaded and the output tile TMA-stored (gemm_sm100.cu)
   EPI_GATE_BWD_TMA = 6,  // internal: EPI_GATE_BWD with x4 tiles TMA-loaded and d(x4) tiles TMA-stored (C % 32 == 0)
   EPI_GATE_TMA = 7,      // internal: EPI_GATE on 32-wide pair packing (PACK_PAIR32), x4 / sg tiles TMA-stored (C % 32 == 0)
+  EPI_LNBWD_TMA = 8,     // internal: EPI_STORE whose accumulator is d(LN output): the LayerNorm backward runs in the epilogue (ep.lnb_*)
 };
 
 struct EpiParams {
@@ -54,6 +55,20 @@ struct EpiParams {
   int ld_ln;
   float* ln_stats;
   float ln_eps;
+  // Fused LayerNorm BACKWARD (STORE, TMA-tiled epilogue, N <= 512; selected by lnb_x != nullptr): the accumulator is
+  // dn = d(loss)/d(LN output) (a dgrad GEMM: conv4's or conv1's), and the epilogue turns it into the gradient of the LN INPUT
+  // with the reference's hand-written backward (nafnet_arch.py:38-53):  g = dn * w,  xhat = (x - mean) * rstd,
+  //   dx = (g - xhat * mean_c(g * xhat) - mean_c(g)) * rstd (+ dres)   -> out_f32 (+ out_bf16 mirror),
+  //   lnb_dw[c] += sum_m dn * xhat,  lnb_db[c] += sum_m dn,  lnb_cs[c] += sum_m dx  (nullable)
+  // - what ln_bwd_launch computes from a materialised bf16 dn, without the dn round trip and the second launch.
+  const float* lnb_x;      // fp32 [M, ld_lnb]: the LayerNorm's input rows
+  int ld_lnb;
+  const float* lnb_stats;  // [M, 2] (mean, rstd) saved by the forward
+  const float* lnb_w;      // LayerNorm weight [N]
+  const float* lnb_dres;   // fp32 [M, ld_lnb] gradient of the residual branch, added to dx (nullable)
+  float* lnb_dw;
+  float* lnb_db;
+  float* lnb_cs;
 };
 // true when gemm_tc_launch can fuse the LayerNorm of the output rows for this N (else the caller runs ln_fwd_launch)
 inline bool gemm_ln_fusable(int N) { return N >= 8 && N % 8 == 0 && N <= 512; }

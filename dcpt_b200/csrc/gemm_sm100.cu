@@ -66,7 +66,7 @@ constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 // runs with one pipeline stage fewer than the register-staged epilogues (one 4 KiB transpose tile per warp).
 template <int BN, int EPI>
 struct Cfg {
-  static constexpr bool TMA_EPI = EPI == EPI_STORE_TMA || EPI == EPI_GATE_BWD_TMA || EPI == EPI_GATE_TMA;
+  static constexpr bool TMA_EPI = EPI == EPI_STORE_TMA || EPI == EPI_GATE_BWD_TMA || EPI == EPI_GATE_TMA || EPI == EPI_LNBWD_TMA;
   static constexpr int STAGES = TMA_EPI ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -74,7 +74,8 @@ struct Cfg {
   static constexpr uint32_t EPI_BYTES = 8 * (TMA_EPI ? 8192 : 4096);  // starts 1024-byte aligned (STAGE_BYTES % 1024 == 0)
   // EPI_GATE_BWD_TMA: per-CTA column sums of d(x4) (2C <= 2048 floats); EPI_STORE_TMA: row-statistics exchange of the fused
   // LayerNorm (2 slab parities x 8 warps x 32 lanes x float4)
-  static constexpr uint32_t COLSUM_BYTES = EPI == EPI_GATE_BWD_TMA ? 8192 : (EPI == EPI_STORE_TMA ? 8192 : 0);
+  // EPI_LNBWD_TMA: the same exchange buffer + three per-CTA column accumulators of N <= 512 floats (dw, db, column sums of dx)
+  static constexpr uint32_t COLSUM_BYTES = EPI == EPI_GATE_BWD_TMA ? 8192 : (EPI == EPI_STORE_TMA ? 8192 : (EPI == EPI_LNBWD_TMA ? 8192 + 6144 : 0));
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 512 /*barriers*/ + COLSUM_BYTES;
 };
 
@@ -140,6 +141,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (ep.colsum)
       for (int i = threadIdx.x; i < 2 * ep.C; i += kThreads) s_colsum[i] = 0.f;
   }
+  if constexpr (EPI == EPI_LNBWD_TMA) {
+    for (int i = threadIdx.x; i < 1536; i += kThreads) s_colsum[2048 + i] = 0.f;
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -149,6 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (N = 512) a CTA takes whole 128-row SLABS: its tiles_n (= 2) tiles of a slab back to back, one per accumulator buffer.
   bool slab_mode = false;
   if constexpr (EPI == EPI_STORE_TMA) slab_mode = ep.ln_out != nullptr && tiles_n > 1;
+  if constexpr (EPI == EPI_LNBWD_TMA) slab_mode = tiles_n > 1;
   auto tile_of = [&](int it) -> int {
     if (slab_mode) {
       const int slab = (int)blockIdx.x + (it / tiles_n) * (int)gridDim.x;
@@ -388,6 +393,226 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_store_2d(tmap, src, n0, m0);
         }
       };
+      if constexpr (EPI == EPI_LNBWD_TMA) {
+        // ---- LayerNorm backward in the epilogue of the dgrad GEMM that produces d(LN output) (EpiParams::lnb_*) ----
+        // The CTA holds whole rows (one tile for N <= 256, the two accumulator buffers of a slab for N = 512).  Pass 1, per
+        // 32 x 32 chunk: x tile TMA-loaded (one chunk ahead), g = dn * w, xhat = (x - mean) * rstd, per-row sums of g and
+        // g * xhat (lane = row: thread-local), column sums dn * xhat / dn (shuffle transpose-reduce -> per-CTA shared
+        // accumulators), and (g, xhat) packed as two 16-bit values back into the accumulator's own TMEM column.  The two
+        // warps of a lane quarter exchange their row sums; pass 2: dx = (g - xhat * c1 - c2) * rstd + dres (dres tile
+        // TMA-loaded in place, result tile TMA-stored), bf16 mirror, column sums of dx.
+        float* s_dw = s_colsum + 2048;
+        float* s_db = s_dw + 512;
+        float* s_cs = s_db + 512;
+        const bool has_dres = ep.lnb_dres != nullptr;
+        const float invN = 1.f / (float)N;
+        float r_g = 0.f, r_gx = 0.f;
+        int par = 0;
+        for (int it = 0, tile; (tile = tile_of(it)) >= 0; ++it) {
+          const int n_t = tile % tiles_n;
+          const int m_t = (tile / tiles_n) % tiles_m;
+          const int m0 = m_t * BM + q * 32;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+          float mean = 0.f, rstd = 0.f;
+          if (m0 + lane < M) {
+            const float2 st = __ldg(reinterpret_cast<const float2*>(ep.lnb_stats + (size_t)(m0 + lane) * 2));
+            mean = st.x;
+            rstd = st.y;
+          }
+          bool first = true;
+#pragma unroll 1
+          for (int c = chalf; c < BN / 32; c += 2) {
+            const int n0 = n_t * BN + c * 32;
+            if (n0 >= N) break;  // warp-uniform
+            const int b = ci & 1;
+            if (first) {
+              if (lane == 0) {
+                bulk_wait_read<0>();
+                mbar_arrive_expect_tx(&rf[b], 4096);
+                tma_load_2d(ebuf + b * 4096, &em.r32, &rf[b], n0, m0);
+              }
+              mbar_wait(&tfull[acc], acc_phase);
+              tc_fence_after();
+              first = false;
+            }
+            float v[32];
+            tmem_ld32(taddr + c * 32, v);
+            if (lane == 0) {
+              bulk_wait_read<0>();
+              const int nn = n0 + 64;
+              if (c + 2 < BN / 32 && nn < N) {
+                mbar_arrive_expect_tx(&rf[b ^ 1], 4096);
+                tma_load_2d(ebuf + (b ^ 1) * 4096, &em.r32, &rf[b ^ 1], nn, m0);
+              }
+            }
+            float4 wv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              wv[j] = (n0 + 4 * j < N) ? __ldg(reinterpret_cast<const float4*>(ep.lnb_w + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            const uint32_t buf = smem_u32(ebuf + b * 4096);
+            mbar_wait(&rf[b], (rphase >> b) & 1u);
+            rphase ^= 1u << b;
+            float4 xr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xr[j] = lds_f4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)));
+            tmem_ld_wait();
+            float pa[32];
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float xs[4] = {xr[j].x, xr[j].y, xr[j].z, xr[j].w};
+              const float ws[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float xh = (xs[k] - mean) * rstd;
+                const float dn = v[4 * j + k];
+                const float g = dn * ws[k];   // columns beyond N: dn = 0 (zero-filled weights rows), w = 0
+                r_g += g;
+                r_gx = fmaf(g, xh, r_gx);
+                pa[4 * j + k] = dn * xh;
+                const op16x2 pr = OP2_FROM_F32(g, xh);
+                pk[4 * j + k] = *reinterpret_cast<const uint32_t*>(&pr);
+              }
+            }
+            tmem_st32(taddr + c * 32, *reinterpret_cast<float(*)[32]>(pk));
+            const float sa = warp_colsum32(pa, lane);
+            const float sb = warp_colsum32(v, lane);
+            if (n0 + lane < N) {
+              atomicAdd(&s_dw[n0 + lane], sa);
+              atomicAdd(&s_db[n0 + lane], sb);
+            }
+            ++ci;
+          }
+          if (first) {
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+          }
+          if (n_t == tiles_n - 1) {
+            tmem_st_wait();
+            float4* xch = reinterpret_cast<float4*>(s_colsum) + par * 256;
+            xch[ew * 32 + lane] = make_float4(r_g, r_gx, 0.f, 0.f);
+            tc_fence_before();
+            named_bar_sync(1 + q, 64);
+            tc_fence_after();
+            const float4 pb = xch[(ew ^ 4) * 32 + lane];
+            par ^= 1;
+            const float c2 = (r_g + pb.x) * invN;    // mean_c(g)
+            const float c1 = (r_gx + pb.y) * invN;   // mean_c(g * xhat)
+            r_g = r_gx = 0.f;
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            for (int h = 0; h < tiles_n; ++h) {
+              const int hacc = tiles_n > 1 ? h : acc;
+              const uint32_t th = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hacc * BN);
+              bool first2 = true;
+#pragma unroll 1
+              for (int c = chalf; c < BN / 32; c += 2) {
+                const int n0 = h * BN + c * 32;
+                if (n0 >= N) break;
+                const int b = ci & 1;
+                if (first2) {
+                  if (lane == 0) {
+                    bulk_wait_read<0>();
+                    if (has_dres) {
+                      mbar_arrive_expect_tx(&rf[b], 4096);
+                      tma_load_2d(ebuf + b * 4096, &em.o2, &rf[b], n0, m0);
+                    }
+                  }
+                  first2 = false;
+                }
+                float pkf[32];
+                tmem_ld32(th + c * 32, pkf);
+                if (lane == 0) {
+                  bulk_wait_read<0>();
+                  const int nn = n0 + 64;
+                  if (has_dres && c + 2 < BN / 32 && nn < N) {
+                    mbar_arrive_expect_tx(&rf[b ^ 1], 4096);
+                    tma_load_2d(ebuf + (b ^ 1) * 4096, &em.o2, &rf[b ^ 1], nn, m0);
+                  }
+                }
+                __syncwarp();
+                const uint32_t buf = smem_u32(ebuf + b * 4096);
+                float4 dr[8];
+                if (has_dres) {
+                  mbar_wait(&rf[b], (rphase >> b) & 1u);
+                  rphase ^= 1u << b;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) dr[j] = lds_f4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) dr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                tmem_ld_wait();
+                float dx[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float ds4[4] = {dr[j].x, dr[j].y, dr[j].z, dr[j].w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 gx = OP2_TO_F32(*reinterpret_cast<const op16x2*>(&pkf[4 * j + k]));
+                    dx[4 * j + k] = fmaf(gx.x - gx.y * c1 - c2, rstd, ds4[k]);
+                  }
+                }
+                if (ep.out_f32) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    sts_f4(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), make_float4(dx[4 * j], dx[4 * j + 1], dx[4 * j + 2], dx[4 * j + 3]));
+                  fence_async_smem();
+                  __syncwarp();
+                  if (lane == 0) {
+                    tma_store_2d(&em.o32, ebuf + b * 4096, n0, m0);
+                    bulk_commit();
+                    if (ep.out_bf16) bulk_wait_read<0>();
+                  }
+                  __syncwarp();
+                }
+                if (ep.out_bf16) {
+                  // (tried: the mirror as four 16-byte st.global per lane instead of a second TMA tile + store-drain wait: slower,
+                  //  50.3 vs 46.5 us per launch at C = 512 - 32 partial-sector writes per instruction)
+                  __syncwarp();
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float t8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) t8[k] = dx[8 * j + k];
+                    sts_u4(buf + (uint32_t)(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)), pack8(t8));
+                  }
+                  fence_async_smem();
+                  __syncwarp();
+                  if (lane == 0) {
+                    tma_store_2d(&em.o16, ebuf + b * 4096, n0, m0);
+                    bulk_commit();
+                  }
+                }
+                if (ep.lnb_cs) {
+                  if (m0 + lane >= M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dx[j] = 0.f;   // rows beyond M carry dres = 0 but -c2 * rstd garbage: mask
+                  }
+                  const float sc = warp_colsum32(dx, lane);
+                  if (n0 + lane < N) atomicAdd(&s_cs[n0 + lane], sc);
+                }
+                ++ci;
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (tiles_n > 1) {
+                mbar_arrive(&tempty[0]);
+                mbar_arrive(&tempty[1]);
+              } else {
+                mbar_arrive(&tempty[acc]);
+              }
+            }
+          }
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      } else
       if constexpr (EPI == EPI_GATE_TMA) {
         // ---- SimpleGate forward on 32-wide pair packing: accumulator chunks (2p, 2p + 1) = (a, b) halves of channels
         // [32p, 32p + 32): x4[:, 32p..] = a, x4[:, C + 32p..] = b, sg[:, 32p..] = a * b (all bf16, rounded before the product
@@ -927,6 +1152,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (sv != 0.f) atomicAdd(ep.colsum + i, sv);
       }
   }
+  if constexpr (EPI == EPI_LNBWD_TMA) {
+    for (int i = threadIdx.x; i < N; i += kThreads) {
+      const float a = s_colsum[2048 + i], b = s_colsum[2048 + 512 + i], c = s_colsum[2048 + 1024 + i];
+      if (a != 0.f) atomicAdd(ep.lnb_dw + i, a);
+      if (b != 0.f) atomicAdd(ep.lnb_db + i, b);
+      if (ep.lnb_cs && c != 0.f) atomicAdd(ep.lnb_cs + i, c);
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -1073,6 +1306,14 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   } else if constexpr (EPI == EPI_GATE_TMA) {
     DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, 2 * g.ep.C, g.ep.ldo, 2));
     DCPT_TRY(make_tmap_epi(&em.o2, g.ep.out2, g.M, g.ep.C, g.ep.ldo2, 2));
+  } else if constexpr (EPI == EPI_LNBWD_TMA) {
+    DCPT_CHECK_ARG(g.N <= 2 * BN && g.N <= 512 && g.ep.lnb_stats && g.ep.lnb_w && g.ep.lnb_dw && g.ep.lnb_db && (g.ep.out_f32 || g.ep.out_bf16) &&
+                       !g.ep.bias && !g.ep.resid && g.m_per_batch == 0 && (reinterpret_cast<uintptr_t>(g.ep.lnb_w) & 15) == 0,
+                   DCPT_E_ARG, "gemm: fused LayerNorm backward needs N <= 512, stats / weight / dw / db and no bias / residual (N=%d)", g.N);
+    if (g.ep.out_f32) DCPT_TRY(make_tmap_epi(&em.o32, g.ep.out_f32, g.M, g.N, g.ep.ldo, 4));
+    if (g.ep.out_bf16) DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, g.N, g.ep.ldo, 2));
+    DCPT_TRY(make_tmap_epi(&em.r32, g.ep.lnb_x, g.M, g.N, g.ep.ld_lnb, 4));
+    if (g.ep.lnb_dres) DCPT_TRY(make_tmap_epi(&em.o2, g.ep.lnb_dres, g.M, g.N, g.ep.ld_lnb, 4));
   }
   if (!g.a_mn) DCPT_TRY(make_tmap_2d(&tmA, g.A, g.M, g.K, g.lda, BM));
   else DCPT_TRY(make_tmap_2d(&tmA, g.A, g.K, g.M, g.lda, 64));
@@ -1105,7 +1346,8 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   }
   const int total = tiles_m * tiles_n * splits;
   int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
-  if (EPI == EPI_STORE_TMA && g.ep.ln_out && tiles_n > 1) grid = tiles_m < dcpt_num_sms() ? tiles_m : dcpt_num_sms();  // whole slabs per CTA
+  if ((EPI == EPI_STORE_TMA && g.ep.ln_out && tiles_n > 1) || (EPI == EPI_LNBWD_TMA && tiles_n > 1))
+    grid = tiles_m < dcpt_num_sms() ? tiles_m : dcpt_num_sms();  // whole slabs per CTA
 
   auto kern = gemm_tc_kernel<BN, EPI, A_MN, B_MN, 0>;
   static bool attr_set = false;  // per template instantiation
@@ -1115,7 +1357,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   }
   static char base_tag[48] = "";
   if (!base_tag[0]) {
-    static const char* epi_names[] = {"store", "gate", "gate_bwd", "pixshuf", "atomic", "store_tma", "gate_bwd_tma", "gate_tma"};
+    static const char* epi_names[] = {"store", "gate", "gate_bwd", "pixshuf", "atomic", "store_tma", "gate_bwd_tma", "gate_tma", "lnbwd_tma"};
     snprintf(base_tag, sizeof(base_tag), "gemm_tc<%d,%s,%s>", BN, epi_names[EPI], A_MN ? "mn" : "k");
   }
   const char* tag = base_tag;
@@ -1256,6 +1498,12 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
       const bool want_g = g.ep.gaux != nullptr && g.ep.colsum != nullptr;
       const bool fuse_g = want_g && tma && !g.ep.resid && !g.ep.out_f32 && g.ep.out_bf16 && g.ep.rows_per_img > 0 &&
                           g.ep.rows_per_img % 32 == 0 && ok(g.ep.gaux, g.ep.ldgaux, 2);
+      if (g.ep.lnb_x) {  // the accumulator is d(LN output): LayerNorm backward in the epilogue
+        DCPT_CHECK_ARG(!no_tma && gemm_ln_fusable(g.N) && ok(g.ep.out_f32, g.ep.ldo, 4) && ok(g.ep.out_bf16, g.ep.ldo, 2) &&
+                           ok(g.ep.lnb_x, g.ep.ld_lnb, 4) && ok(g.ep.lnb_dres, g.ep.ld_lnb, 4) && !g.ep.ln_out && !g.ep.gaux,
+                       DCPT_E_ARG, "gemm: fused LayerNorm backward needs 16-byte pitched rows and N <= 512 (N=%d)", g.N);
+        return launch_bn<EPI_LNBWD_TMA, false, false>(g, stream);
+      }
       DCPT_CHECK_ARG(g.ep.ln_out == nullptr || (tma && gemm_ln_fusable(g.N) && g.ep.out_f32), DCPT_E_ARG,
                      "gemm: fused LayerNorm needs the TMA-tiled fp32 STORE epilogue and N <= 512 (N=%d)", g.N);
       GemmArgs gg = g;

@@ -212,6 +212,18 @@ bool ln_fuse_enabled() {
 // can the GEMM writing a [*, C] fp32 tensor also run its consumer's LayerNorm?
 bool ln_fusable(int C) { return ln_fuse_enabled() && gemm_ln_fusable(C) && C % 8 == 0; }
 
+// ... and its backward into the epilogue of the dgrad GEMM that produces d(LN output) (DCPT_LNB_FUSE=0: separate ln_bwd kernel)
+bool lnb_fusable(int C) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DCPT_LNB_FUSE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  // C = 64: one 32-column chunk per epilogue warp and tile - the two passes cannot overlap anything and the fused launch is
+  // slower than GEMM + ln_bwd (r02q: 268 vs 258 us at 1 M pixels); from C = 128 on it wins (121 vs 151, 68 vs 88, 46 vs 55 us)
+  return on != 0 && gemm_ln_fusable(C) && C >= 128;
+}
+
 void set_ln_epilogue(GemmArgs& g, const LnFuse& f, int C) {
   g.ep.ln_w = f.w; g.ep.ln_b = f.b; g.ep.ln_out = f.n; g.ep.ld_ln = C; g.ep.ln_stats = f.stats; g.ep.ln_eps = kLnEps;
 }
@@ -336,14 +348,20 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   // ---- conv4: wgrad, dgrad ----
   DCPT_TRY(fork_here(1));
   DCPT_TRY(wgrad_gemm(wk.dx4, 2 * C, sv.n2, C, G[P_C4W], M, sw));
+  const bool fuse_lnb = lnb_fusable(C);  // LayerNorm backward in the dgrad GEMM's epilogue (no dn round trip, one launch less)
+  if (!zeros) DCPT_CUDA(cudaMemsetAsync(Sy, 0, C * sizeof(float), st));
   {
     GemmArgs g = gemm_args(M, C, 2 * C, wk.dx4, 2 * C, pk.w4t, 2 * C, EPI_STORE);
-    g.ep.out_bf16 = wk.dn; g.ep.ldo = C;
+    if (fuse_lnb) {  // ---- conv4 dgrad + norm2 backward + residual: dy = dout + LN'(dn2) ----
+      g.ep.out_f32 = wk.dy; g.ep.out_bf16 = wk.dyT; g.ep.ldo = C;
+      g.ep.lnb_x = sv.y; g.ep.ld_lnb = C; g.ep.lnb_stats = sv.stats2; g.ep.lnb_w = P[P_N2W]; g.ep.lnb_dres = dout;
+      g.ep.lnb_dw = G[P_N2W]; g.ep.lnb_db = G[P_N2B]; g.ep.lnb_cs = Sy;
+    } else {
+      g.ep.out_bf16 = wk.dn; g.ep.ldo = C;
+    }
     DCPT_TRY(gemm_launch(g, st));
   }
-  // ---- norm2 backward + residual: dy = dout + LN'(dn2) ----
-  if (!zeros) DCPT_CUDA(cudaMemsetAsync(Sy, 0, C * sizeof(float), st));
-  DCPT_TRY(ln_bwd_launch(wk.dn, sv.y, sv.stats2, P[P_N2W], dout, wk.dy, wk.dyT, G[P_N2W], G[P_N2B], Sy, M, C, st));
+  if (!fuse_lnb) DCPT_TRY(ln_bwd_launch(wk.dn, sv.y, sv.stats2, P[P_N2W], dout, wk.dy, wk.dyT, G[P_N2W], G[P_N2B], Sy, M, C, st));
   // ---- conv3 (beta folded) ----
   DCPT_TRY(fork_here(2));
   if (!zeros) DCPT_CUDA(cudaMemsetAsync(G3, 0, cc * sizeof(float), sw));
@@ -367,11 +385,16 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   DCPT_TRY(wgrad_gemm(wk.du, 2 * C, sv.n1, C, G[P_C1W], M, sw));
   {
     GemmArgs g = gemm_args(M, C, 2 * C, wk.du, 2 * C, pk.w1t, 2 * C, EPI_STORE);
-    g.ep.out_bf16 = wk.dn; g.ep.ldo = C;
+    if (fuse_lnb) {  // ---- conv1 dgrad + norm1 backward + residual: dx = dy + LN'(dn1) ----
+      g.ep.out_f32 = dx; g.ep.out_bf16 = dxT; g.ep.ldo = C;
+      g.ep.lnb_x = x; g.ep.ld_lnb = C; g.ep.lnb_stats = sv.stats1; g.ep.lnb_w = P[P_N1W]; g.ep.lnb_dres = wk.dy;
+      g.ep.lnb_dw = G[P_N1W]; g.ep.lnb_db = G[P_N1B]; g.ep.lnb_cs = Sx;
+    } else {
+      g.ep.out_bf16 = wk.dn; g.ep.ldo = C;
+    }
     DCPT_TRY(gemm_launch(g, st));
   }
-  // ---- norm1 backward + residual: dx = dy + LN'(dn1) ----
-  DCPT_TRY(ln_bwd_launch(wk.dn, x, sv.stats1, P[P_N1W], wk.dy, dx, dxT, G[P_N1W], G[P_N1B], Sx, M, C, st));
+  if (!fuse_lnb) DCPT_TRY(ln_bwd_launch(wk.dn, x, sv.stats1, P[P_N1W], wk.dy, dx, dxT, G[P_N1W], G[P_N1B], Sx, M, C, st));
   if (fork) {  // join: the block's buffers (dx4, dyT, du, G, Sy) are reused by the next block
     DCPT_CUDA(cudaEventRecord(ss.ev[4], sw));
     DCPT_CUDA(cudaStreamWaitEvent(st, ss.ev[4], 0));
@@ -681,6 +704,8 @@ int dcpt_gemm_ex(const dcpt_gemm_desc* d, int impl, dcpt_stream_t stream) {
   g.ep.C = d->C; g.ep.H = d->H; g.ep.W = d->W; g.ep.Cseg = d->Cseg;
   g.ep.ln_w = d->ln_weight; g.ep.ln_b = d->ln_bias; g.ep.ln_out = static_cast<bf16*>(d->ln_out); g.ep.ld_ln = d->ld_ln;
   g.ep.ln_stats = d->ln_stats; g.ep.ln_eps = d->ln_eps;
+  g.ep.lnb_x = d->lnb_x; g.ep.ld_lnb = d->ld_lnb; g.ep.lnb_stats = d->lnb_stats; g.ep.lnb_w = d->lnb_weight; g.ep.lnb_dres = d->lnb_dres;
+  g.ep.lnb_dw = d->lnb_dweight; g.ep.lnb_db = d->lnb_dbias; g.ep.lnb_cs = d->lnb_colsum;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return impl == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
 }

@@ -106,6 +106,14 @@ typedef struct dcpt_gemm_desc {
   const float* ln_weight; const float* ln_bias;
   void* ln_out; int ld_ln;
   float* ln_stats; float ln_eps;
+  /* STORE only, optional (lnb_x != NULL; N <= 512, no bias / resid): the GEMM result is dn = d(loss)/d(LN output) and the epilogue
+   * applies the reference's hand-written LayerNorm backward (LayerNormFunction.backward, nafnet_arch.py:38-53):
+   * out_f32 / out_bf16 = (g - xhat * mean_c(g * xhat) - mean_c(g)) * rstd + lnb_dres, g = dn * lnb_weight,
+   * xhat = (lnb_x - mean) * rstd with (mean, rstd) = lnb_stats[m]; lnb_dweight[c] += sum_m dn * xhat, lnb_dbias[c] += sum_m dn,
+   * lnb_colsum[c] += sum_m out (nullable).  lnb_x / lnb_dres are fp32 [M, ld_lnb]. */
+  const float* lnb_x; int ld_lnb;
+  const float* lnb_stats; const float* lnb_weight; const float* lnb_dres;
+  float* lnb_dweight; float* lnb_dbias; float* lnb_colsum;
 } dcpt_gemm_desc;
 int dcpt_gemm_ex(const dcpt_gemm_desc* desc, int impl, dcpt_stream_t stream);
 

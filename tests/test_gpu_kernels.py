@@ -101,6 +101,49 @@ def test_gemm_store_fused_layernorm(ops, M, N, K, mirror):
     assert (ln.float() - n_ref.float()).abs().max() <= 2 ** -7 * ref_ln.abs().max()
 
 
+@pytest.mark.parametrize("M,N,K,dres,mirror", [(1000, 512, 1024, True, True), (16384, 512, 1024, True, True), (4099, 256, 512, True, False),
+                                                (33000, 128, 256, False, True), (70000, 64, 128, True, True), (130, 72, 40, True, True),
+                                                (300, 24, 16, False, False), (2048, 384, 128, True, True)])
+def test_gemm_fused_layernorm_backward(ops, M, N, K, dres, mirror):
+    """STORE epilogue with the LayerNorm BACKWARD fused (EpiParams::lnb_*): the GEMM result is dn = d(loss)/d(LN output) and the
+    epilogue applies LayerNormFunction.backward (nafnet_arch.py:38-53) + the residual gradient, against double-precision torch
+    math on the fp32 product of the same operands.  g and xhat travel between the two epilogue passes as 16-bit values (the
+    separate ln_bwd kernel reads a 16-bit dn too): dx within one operand rounding of the LN part; the column sums to 2e-3."""
+    from dcpt_b200.lib import GemmDesc
+    from tol import tol
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = bf(torch.randn(M, K, device="cuda", generator=g))
+    B = bf(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    x = torch.randn(M, N, device="cuda", generator=g) * 1.3 + 0.4
+    w = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    dr = torch.randn(M, N, device="cuda", generator=g) if dres else None
+    xd = x.double()
+    mu = xd.mean(1, keepdim=True)
+    rstd = 1.0 / ((xd - mu).pow(2).mean(1, keepdim=True) + 1e-6).sqrt()
+    stats = torch.cat([mu, rstd], 1).float().contiguous()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    mir = torch.full((M, N), float("nan"), device="cuda", dtype=OPD()) if mirror else None
+    dw, db, cs = (torch.zeros(N, device="cuda") for _ in range(3))
+    d = GemmDesc()
+    for k, v in dict(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=out, out_bf16=mir, ldo=N, lnb_x=x, ld_lnb=N,
+                     lnb_stats=stats, lnb_weight=w, lnb_dres=dr, lnb_dweight=dw, lnb_dbias=db, lnb_colsum=cs).items():
+        setattr(d, k, (v.data_ptr() if torch.is_tensor(v) else v) if v is not None else None)
+    ops.gemm_ex(d)
+    dn = (A.float() @ B.float().t()).double()
+    xhat = (xd - mu) * rstd
+    gg = dn * w.double()
+    ref = (gg - xhat * (gg * xhat).mean(1, keepdim=True) - gg.mean(1, keepdim=True)) * rstd
+    ln_part = rel(out.double() - (dr.double() if dres else 0.0), ref)
+    if dres:
+        ref = ref + dr.double()
+    assert torch.isfinite(out).all()
+    assert ln_part < tol(4e-3, 6e-4), ln_part
+    assert rel(out, ref) < tol(4e-3, 6e-4)
+    if mirror:
+        assert rel(mir.float(), ref) < tol(5e-3, 8e-4)
+    assert rel(dw, (dn * xhat).sum(0)) < 2e-3 and rel(db, dn.sum(0)) < 2e-3 and rel(cs, ref.sum(0)) < tol(5e-3, 2e-3)
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 512, 512), (130, 72, 40), (33000, 96, 48)])
 def test_gemm_store_both_outputs(ops, M, N, K):
     """fp32 output + bf16 mirror + residual in one launch (the level-boundary GEMMs of the networks)."""
