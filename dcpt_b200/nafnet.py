@@ -389,6 +389,14 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
     return [flat[o:o + n].view(shp) for o, n, shp in slot.shapes]
 
 
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class _NAFNetFunction(torch.autograd.Function):
     """out, feat_0..feat_{n-1} = NAFNet(inp; params).  feats are NHWC storage viewed as logical NCHW."""
 
@@ -430,16 +438,22 @@ class _NAFNetFunction(torch.autograd.Function):
         dfe = None
         if ctx.n_feats:
             dfe = [None if d is None else d.permute(0, 2, 3, 1).contiguous() for d in dfeats]
-        if isinstance(ctx.saved, _GraphSlot):
-            grads = _graph_backward(eng, ctx.pv, ctx.saved, None if ctx.hook else dout, dfe)
-        else:
-            grads = eng.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
+        with torch.cuda.device(ctx.inp.device):
+            if isinstance(ctx.saved, _GraphSlot):
+                grads = _graph_backward(eng, ctx.pv, ctx.saved, None if ctx.hook else dout, dfe)
+            else:
+                grads = eng.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
         ctx.saved = None
         return (None, None, None, None, None) + tuple(grads)
 
 
 def nafnet_apply(engine, inp, params, hook=False, want_feats=False):
     need_grad = torch.is_grad_enabled() and (inp.requires_grad or any(p.requires_grad for p in params))
-    res = _NAFNetFunction.apply(engine, inp, hook, want_feats, need_grad, *params)
+    if inp.is_cuda and params[0].device != inp.device:
+        raise _l.DcptError(f"input on {inp.device} but the network's parameters on {params[0].device}")
+    # the C library launches on the CURRENT device: make it the tensors' device for the forward and, through autograd's
+    # device guard of the node, for the backward (a model living on a non-current device)
+    with torch.cuda.device(inp.device) if inp.is_cuda else _null_ctx():
+        res = _NAFNetFunction.apply(engine, inp, hook, want_feats, need_grad, *params)
     out = None if hook else res[0]
     return out, list(res[1:])

@@ -88,6 +88,8 @@ class FusedAdam(torch.optim.Optimizer):
                 continue                                            # torch skips parameters without a gradient
             if not p.is_cuda:
                 raise _l.DcptError("dcpt_b200 has no CPU path: parameter is on %s" % p.device)
+            if p.device != group["params"][0].device or p.grad.device != p.device:
+                raise _l.DcptError("FusedAdam: all parameters and gradients of a param group must live on one device")
             if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse \
                     or not p.grad.is_contiguous():
                 raise _l.DcptError("FusedAdam: parameters and gradients must be dense contiguous fp32")
@@ -161,6 +163,9 @@ class FusedAdam(torch.optim.Optimizer):
         for group, job in prepared:
             plan, step0, step_tensors = job
             b1, b2 = group["betas"]
+            if plan.work.device.index != torch.cuda.current_device():
+                raise _l.DcptError(f"FusedAdam: parameters live on {plan.work.device} but the current CUDA device is "
+                                   f"{torch.cuda.current_device()} (the library launches on the current device: use torch.cuda.device)")
             _l.check(self._lib.dcpt_optim_step(plan.h, C.c_void_p(plan.work.data_ptr()), int(bool(group["decoupled_weight_decay"])),
                                                float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                                float(group["weight_decay"]), step0 + 1, float(grad_clip or 0.0),

@@ -92,6 +92,24 @@ def run_ln(M, N, K):
     return keep
 
 
+def run_lnb(M, N, K):
+    """dgrad GEMM with the LayerNorm backward fused (EpiParams::lnb_*): conv4 dgrad -> norm2', conv1 dgrad -> norm1'."""
+    A = torch.randn(M, K, device=dev).bfloat16()
+    B = torch.randn(N, K, device=dev).bfloat16()
+    x = torch.randn(M, N, device=dev)
+    dres = torch.randn(M, N, device=dev)
+    stats = torch.stack([x.mean(1), 1.0 / (x.var(1, unbiased=False) + 1e-6).sqrt()], 1).contiguous()
+    w = torch.ones(N, device=dev)
+    out = torch.empty(M, N, device=dev)
+    mir = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    dw, db, cs = (torch.zeros(N, device=dev) for _ in range(3))
+    d = desc(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=out, out_bf16=mir, ldo=N, lnb_x=x, ld_lnb=N, lnb_stats=stats,
+             lnb_weight=w, lnb_dres=dres, lnb_dweight=dw, lnb_dbias=db, lnb_colsum=cs)
+    keep = (A, B, x, dres, stats, w, out, mir, dw, db, cs, d)
+    bench(f"dgrad+LN-bwd {M}x{N}x{K}", lambda: ops.gemm_ex(d), 2.0 * M * N * K, 2 * (M * K + N * K) + 18 * M * N)
+    return keep
+
+
 if ncu:   # one launch per shape, in this order: tools/ncu_traffic.py pairs the capture's launches with this manifest
     import json
     man = [dict(tag="gemm_tc<256,store_tma,k>", shape="16384x512x512", note="conv3 / conv5 at C=512: fp32 residual in, fp32 out"),
@@ -99,11 +117,13 @@ if ncu:   # one launch per shape, in this order: tools/ncu_traffic.py pairs the 
            dict(tag="gemm_tc<256,store_tma,k>", shape="16384x1024x512", note="conv1 at C=512: bf16 out, 128-byte-row store boxes"),
            dict(tag="gemm_tc<256,store_tma,k>", shape="16384x512x1024", note="conv4 / conv1 dgrad at C=512: bf16 out"),
            dict(tag="gemm_tc<256,gate_tma,k>", shape="16384x1024x512", note="conv4 + SimpleGate epilogue"),
-           dict(tag="gemm_tc<256,gate_bwd_tma,k>", shape="16384x512x512", note="conv5 dgrad + SimpleGate backward")]
+           dict(tag="gemm_tc<256,gate_bwd_tma,k>", shape="16384x512x512", note="conv5 dgrad + SimpleGate backward"),
+           dict(tag="gemm_tc<256,lnbwd_tma,k>", shape="16384x512x1024", note="conv4 / conv1 dgrad at C=512 + fused LayerNorm backward (fp32 x, dres in; fp32 + bf16 dx out)")]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(man, open(os.path.join(ROOT, "gpurun_out", "gemm_bench_manifest.json"), "w"), indent=1)
     keep_all = [run(16384, 512, 512, "store_resid"), run_ln(16384, 512, 512), run(16384, 1024, 512, "store_bf16"),
-                run(16384, 512, 1024, "store_bf16"), run(16384, 1024, 512, "gate"), run(16384, 512, 512, "gate_bwd")]
+                run(16384, 512, 1024, "store_bf16"), run(16384, 1024, 512, "gate"), run(16384, 512, 512, "gate_bwd"),
+                run_lnb(16384, 512, 1024)]
     sys.exit(0)
 
 shapes = [(16384, 512, 512, "store_resid"), (16384, 512, 512, "store_bf16"), (16384, 1024, 512, "store_bf16"),
@@ -114,3 +134,5 @@ for s in shapes:
     run(*s)
 run_ln(16384, 512, 512)
 run_ln(1048576, 64, 64)
+run_lnb(16384, 512, 1024)
+run_lnb(262144, 128, 256)
