@@ -25,16 +25,31 @@ constexpr int BOX_BYTES = BOX_ELEMS * 2;       // 23040
 constexpr int DG_ELEMS = TH * TW * 64;         // interior box (no halo)
 constexpr int DG_BYTES = DG_ELEMS * 2;         // 16384
 
-__device__ __forceinline__ float2 lds_bf2(const bf16* p) {
-  return OP2_TO_F32(*reinterpret_cast<const op16x2*>(p));
+// Operand tiles live in dynamic shared memory behind an aligned-up uintptr_t, which makes every pointer derived from it GENERIC to
+// the compiler: the stencil loads compiled to LD.E (r01_w_ncu_bwd_elementwise_hotspots.txt: dispatch stalls, issue-bound kernels).
+// SBf carries the 32-bit shared-window address instead, and lds_bf2 is an explicit ld.shared (LDS with an immediate offset).
+struct SBf {
+  uint32_t addr;
+  __device__ __forceinline__ SBf operator+(int elems) const { return SBf{addr + 2u * (uint32_t)elems}; }
+};
+__device__ __forceinline__ SBf sbf(const void* generic_smem_ptr) { return SBf{smem_u32(generic_smem_ptr)}; }
+__device__ __forceinline__ float2 lds_bf2(SBf p) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(p.addr));
+  return OP2_TO_F32(*reinterpret_cast<const op16x2*>(&v));
 }
 __device__ __forceinline__ void st_bf2(bf16* p, float2 v) {
   *reinterpret_cast<op16x2*>(p) = OP2_FROM_F32(v.x, v.y);
 }
 __device__ __forceinline__ float2 round_bf2(float2 v) { return OP2_TO_F32(OP2_FROM_F32(v.x, v.y)); }
+// Two fp32 FMAs in ONE issue slot: Blackwell's packed FFMA2 (fma.rn.f32x2).  The stencil kernels are issue-bound (r02s: ~1700
+// instructions per tile row, a third of them FFMA), and every accumulation here is already a float2 = two adjacent channels.
 __device__ __forceinline__ void fma2(float2& acc, float2 a, float2 b) {
-  acc.x = fmaf(a.x, b.x, acc.x);
-  acc.y = fmaf(a.y, b.y, acc.y);
+  unsigned long long c = *reinterpret_cast<unsigned long long*>(&acc);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(c)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  acc = *reinterpret_cast<float2*>(&c);
 }
 // nine taps of two consecutive channels: w[c][tap] fp32, c = c0, c0+1
 __device__ __forceinline__ void load_taps(float2 (&wt)[9], const float* __restrict__ w, int c0) {
@@ -128,8 +143,8 @@ dwgate_fwd_kernel(const __grid_constant__ CUtensorMap tmU, const float* __restri
       cur_n = n;
     }
     mbar_wait(&full[s], (it >> 1) & 1);
-    const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * 2 * BOX_BYTES) + lane * 2;
-    const bf16* sB = sA + BOX_ELEMS;
+    const SBf sA = sbf(smem + (size_t)s * 2 * BOX_BYTES) + lane * 2;
+    const SBf sB = sA + BOX_ELEMS;
     const int h = h0 + warp;  // warp = tile row (TH == NWARP)
     bf16* grow = g + (((size_t)n * H + h) * W + w0) * C + ca;
     float2 A[3][3], B[3][3];
@@ -230,7 +245,7 @@ dwconv3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
       cur_n = n;
     }
     mbar_wait(&full[s], (it >> 1) & 1);
-    const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * BOX_BYTES) + lane * 2;
+    const SBf sA = sbf(smem + (size_t)s * BOX_BYTES) + lane * 2;
     const int h = h0 + warp;
     bf16* orow = out + (((size_t)n * H + h) * W + w0) * CH + c0;
     float2 A[3][3];
@@ -321,9 +336,9 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
       tv = make_float2(__ldg(t_sca + (size_t)n * C + ca), __ldg(t_sca + (size_t)n * C + ca + 1));
     }
     mbar_wait(&full[s], (it >> 1) & 1);
-    const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * STAGE_BYTES) + lane * 2;
-    const bf16* sB = sA + BOX_ELEMS;
-    const bf16* sD = sA + 2 * BOX_ELEMS;
+    const SBf sA = sbf(smem + (size_t)s * STAGE_BYTES) + lane * 2;
+    const SBf sB = sA + BOX_ELEMS;
+    const SBf sD = sA + 2 * BOX_ELEMS;
     const int h = h0 + warp;
     bf16* orow = du2 + (((size_t)n * H + h) * W + w0) * C2;
     float2 A[3][3], B[3][3];
@@ -455,7 +470,7 @@ dwconv_bwd_data_kernel(const __grid_constant__ CUtensorMap tmG, const float* __r
     int n, h0, w0;
     T.decode(t, n, h0, w0);
     mbar_wait(&full[s], (it >> 1) & 1);
-    const bf16* sA = reinterpret_cast<const bf16*>(smem + (size_t)s * BOX_BYTES) + lane * 2;
+    const SBf sA = sbf(smem + (size_t)s * BOX_BYTES) + lane * 2;
     const int h = h0 + warp;
     bf16* orow = du + (((size_t)n * H + h) * W + w0) * CH + c0;
     float2 A[3][3];
