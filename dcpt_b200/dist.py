@@ -150,6 +150,65 @@ class FlatGradDataParallel(torch.nn.Module):
         return self.module(*args, **kwargs)
 
 
+def _grad_segments(grads, max_gap=512):
+    """Group gradient tensors into runs that sit back to back (alignment gaps <= max_gap bytes) inside ONE storage.
+    Host cost matters here - the GPU idles while this runs - so it is two cheap calls per tensor and numpy for the rest."""
+    import numpy as np
+    ptr = np.fromiter((g.data_ptr() for g in grads), dtype=np.int64, count=len(grads))
+    size = np.fromiter((g.numel() * g.element_size() for g in grads), dtype=np.int64, count=len(grads))
+    order = np.argsort(ptr, kind="stable")
+    p, e = ptr[order], ptr[order] + size[order]
+    gap = p[1:] - e[:-1]
+    cuts = np.flatnonzero((gap < 0) | (gap > max_gap)) + 1
+    runs, stray = [], []
+    for lo, hi in zip(np.concatenate(([0], cuts)), np.concatenate((cuts, [len(grads)]))):
+        idx = order[lo:hi]
+        first, last = grads[idx[0]], grads[idx[-1]]
+        # every rank must cut the same runs: only the engines' flat buffers qualify (one storage, parameter order, >= 1 MiB);
+        # allocations that merely happen to be neighbours on this rank never share a storage
+        ok = hi - lo > 1 and int(e[hi - 1] - p[lo]) >= (1 << 20) and bool(np.all(np.diff(idx) == 1)) and first.dtype == last.dtype and \
+            first.is_contiguous() and last.is_contiguous() and first.untyped_storage().data_ptr() == last.untyped_storage().data_ptr()
+        if ok:
+            n = int(e[hi - 1] - p[lo]) // first.element_size()
+            runs.append((int(idx[0]), first.new_empty(0).set_(first.untyped_storage(), first.storage_offset(), (n,))))
+        else:
+            stray.extend(int(i) for i in idx)
+    runs = [r for _, r in sorted(runs, key=lambda t: t[0])]        # rank-independent order: by first parameter index
+    stray = [grads[i] for i in sorted(stray)]
+    return runs, stray
+
+
+def exchange_accumulated_grads_(nets, group=None):
+    """Mean all-reduce of the ``.grad`` tensors of ``nets`` after a backward run under ``no_sync()`` - the exchange of a step
+    whose networks are reached by SEVERAL backward nodes (the DCPT step runs net_g twice,
+    degradation_classification_pretrain_model.py:141-162), where a per-node exchange would move the same buffer more than once.
+
+    The engines hand autograd views of one flat fp32 buffer per backward node; autograd keeps (aliases of) the first node's
+    views as ``.grad`` and accumulates later nodes into them in place.  So after the backward a network's gradients sit back to
+    back in one storage - possibly two, when the node that ran first did not reach every parameter (the hooked pass never
+    reaches ``ending``).  Each such run is all-reduced in place as one tensor; what is left over (isolated tensors, a network
+    reached through plain autograd) is coalesced into one temporary and copied back.  Returns the number of all-reduce calls."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return 0
+    calls = 0
+    for net in nets:
+        grads = [p.grad for p in net.parameters()]
+        grads = [g for g in grads if g is not None]
+        if not grads:
+            continue
+        runs, stray = _grad_segments(grads)
+        for r in runs:
+            allreduce_mean_(r, group)
+            calls += 1
+        if stray:
+            flat = torch.cat([g.reshape(-1) for g in stray])
+            allreduce_mean_(flat, group)
+            calls += 1
+            torch._foreach_copy_(stray, [c.view(g.shape) for c, g in zip(flat.split([g.numel() for g in stray]), stray)])
+    return calls
+
+
 def reduce_loss_dict(loss_dict):
     """Average the logged losses onto rank 0 (basicsr/models/base_model.py:432-457) with ONE host sync."""
     rank, world = get_dist_info()

@@ -129,8 +129,59 @@ def scenario_dcpt(basicsr, sd_g, sd_h):
             "after_h_norm": float(after_h.norm())}
 
 
+def scenario_sr_train(basicsr, sd_g):
+    """SRModel.optimize_parameters x 3 (sr_model.py:132-174): L1, top-level grad_clip, Adam, EMA 0.9, cosine-restart schedule
+    advanced by update_learning_rate as basicsr/train.py does each iteration."""
+    from basicsr.models import build_model
+    from basicsr.models.base_model import BaseModel
+    BaseModel.print_network = lambda self, *a, **k: None
+    opt = base_opt("SRModel", True)
+    opt["grad_clip"] = 0.05
+    opt["train"] = {"ema_decay": 0.9, "optim_g": {"type": "Adam", "lr": 2e-3, "weight_decay": 0, "betas": [0.9, 0.99]},
+                    "scheduler": {"type": "CosineAnnealingRestartLR", "periods": [2, 4], "restart_weights": [1, 0.5], "eta_min": [1e-5, 2e-5]},
+                    "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0, "reduction": "mean"}}
+    model = build_model(opt)
+    model.get_bare_model(model.net_g).load_state_dict(sd_g, strict=True)
+    model.model_ema(0)
+    g = torch.Generator().manual_seed(13)
+    logs, lrs = [], []
+    for it in range(1, 5):
+        model.update_learning_rate(it, warmup_iter=-1)
+        lrs.append(model.get_current_learning_rate()[0])
+        model.feed_data({"lq": torch.rand(2, 3, 32, 32, generator=g), "gt": torch.rand(2, 3, 32, 32, generator=g)})
+        model.optimize_parameters(it)
+        logs.append(float(model.get_current_log()["l_pix"]))
+    after = torch.cat([p.detach().flatten() for p in model.net_g.parameters()])
+    ema = torch.cat([p.detach().flatten() for p in model.net_g_ema.parameters()])
+    model.feed_data({"lq": torch.rand(1, 3, 32, 32, generator=g)})
+    model.test()                                               # the EMA network answers (sr_model.py:176-180)
+    return {"logs": logs, "lrs": lrs, "after": after[::10007].tolist(), "after_norm": float(after.norm()), "ema": ema[::10007].tolist(),
+            "ema_norm": float(ema.norm()), "test_norm": float(model.output.norm())}
+
+
+def scenario_schedules(basicsr):
+    """Learning-rate trajectories of the two schedule families under warm-up (base_model.py:141-186; lr_scheduler.py)."""
+    from basicsr.models.base_model import BaseModel
+    out = {}
+    for name, sched in (("multistep", {"type": "MultiStepLR", "milestones": [3, 6], "gamma": 0.5}),
+                        ("cosine", {"type": "CosineAnnealingRestartLR", "periods": [4, 4, 6], "restart_weights": [1, 0.5, 0.25], "eta_min": [1e-6, 1e-6, 2e-6]})):
+        m = BaseModel({"num_gpu": 0, "is_train": True, "dist": False, "train": {"scheduler": dict(sched)}})
+        m.optimizers = [torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)]
+        m.setup_schedulers()
+        traj = []
+        for it in range(1, 13):
+            m.update_learning_rate(it, warmup_iter=3)
+            traj.append(m.get_current_learning_rate()[0])
+            m.optimizers[0].step()
+        out[name] = traj
+    return out
+
+
 def run(root, overlay):
-    basicsr = R.import_reference(root)
+    if root == "mirror":                 # this repo's own basicsr package (arch files + the model / loss mirrors)
+        import basicsr
+    else:
+        basicsr = R.import_reference(root)
     if overlay:
         stub_engines()
     from oracle import dchead_oracle as D
@@ -142,12 +193,14 @@ def run(root, overlay):
         torch.save({"params": {k: torch.zeros_like(v) for k, v in sd_g.items()}, "params_ema": sd_g}, ckpt)   # the yml loads params_ema
         sr = scenario_sr(basicsr, ckpt)
     dc = scenario_dcpt(basicsr, sd_g, sd_h)
-    return {"sr": sr, "dcpt": dc}
+    return {"sr": sr, "dcpt": dc, "sr_train": scenario_sr_train(basicsr, sd_g), "schedules": scenario_schedules(basicsr)}
 
 
 if __name__ == "__main__":
     which = sys.argv[1]
-    if which == "overlay":
+    if which == "mirror":
+        res = run("mirror", True)
+    elif which == "overlay":
         with tempfile.TemporaryDirectory() as td:
             res = run(make_overlay(td), True)
     else:

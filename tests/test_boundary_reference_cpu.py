@@ -44,3 +44,28 @@ def test_reference_models_run_on_the_dropped_in_archs():
     # both networks after the step: AdamW moves every parameter by ~lr on step 1 whatever the gradient's scale, so agreement to
     # 1e-4 of the parameter scale means the gradients agree in sign and the plumbing (two passes, one backward, two steps) matches
     assert close(d["after_g"], q["after_g"], 1e-4) and close(d["after_h"], q["after_h"], 1e-4)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference is not present (GPU box): the boundary proof runs in the build container")
+def test_model_mirrors_step_like_the_reference_models():
+    """This repo's SRModel / DCPTModel (basicsr/models/) against the reference's own classes on the same options, weights and
+    data (CPU, engines stubbed with the oracle functional as above): test path, DCPT step, four SRModel iterations with
+    grad_clip + Adam + EMA + cosine-restart schedule, and the learning-rate trajectories of both schedule families."""
+    ours, ref = _run("mirror"), _run("reference")
+    close = lambda a, b, tol: float(np.abs(np.asarray(a) - np.asarray(b)).max()) <= tol * max(float(np.abs(np.asarray(b)).max()), 1e-30)  # noqa: E731
+    s, r = ours["sr"], ref["sr"]
+    assert s["padded"] == r["padded"] and s["out_shape"] == r["out_shape"] and s["keys"] == r["keys"]
+    assert close(s["out"], r["out"], 2e-5)
+    d, q = ours["dcpt"], ref["dcpt"]
+    assert d["hooked"] == q["hooked"] and d["n_hook_outputs"] == q["n_hook_outputs"] == 4 and d["hook_true_returns_none"]
+    assert d["optimizer_order_is_named_parameters_order"] and d["n_opt_params"] == q["n_opt_params"]
+    for k in q["log"]:
+        assert abs(d["log"][k] - q["log"][k]) < 2e-5 * abs(q["log"][k]), (k, d["log"], q["log"])
+    assert close(d["after_g"], q["after_g"], 1e-4) and close(d["after_h"], q["after_h"], 1e-4)
+    t, u = ours["sr_train"], ref["sr_train"]
+    assert np.allclose(t["lrs"], u["lrs"], rtol=1e-9, atol=0), (t["lrs"], u["lrs"])
+    assert np.allclose(t["logs"], u["logs"], rtol=5e-5), (t["logs"], u["logs"])
+    assert close(t["after"], u["after"], 2e-4) and close(t["ema"], u["ema"], 2e-4)
+    assert abs(t["test_norm"] - u["test_norm"]) < 2e-4 * u["test_norm"]
+    for k in ("multistep", "cosine"):
+        assert np.allclose(ours["schedules"][k], ref["schedules"][k], rtol=1e-9, atol=0), (k, ours["schedules"][k], ref["schedules"][k])

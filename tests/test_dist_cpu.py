@@ -101,3 +101,91 @@ def test_data_parallel_gloo_world2():
     assert err < 1e-5, err            # fp32: mean of half-batch grads == full-batch grads
     assert loss_err < 1e-6
     assert seed0 == 10 and info == (0, 2)
+
+
+def _dcpt_opt(dist):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from boundary_overlay_check import CFG, DIMS
+    return {"name": "dp", "model_type": "DCPTModel", "scale": 1, "num_gpu": 0, "dist": dist, "is_train": True, "rank": 0, "world_size": 1,
+            "network_g": dict(type="NAFNetBaseline", window_size=16, **CFG),
+            "network_dc": dict(type="PromptIR_NoImg_DC", feature_dims=DIMS, num_res_blocks=2, num_classes=5), "hook_names": "decoder",
+            "path": {"pretrain_network_g": None}, "train": {
+                "optim_g": {"type": "AdamW", "lr": 1e-3, "weight_decay": 1e-4, "betas": [0.9, 0.9]},
+                "optim_dc": {"type": "AdamW", "lr": 1e-3, "weight_decay": 1e-4, "betas": [0.9, 0.9]},
+                "scheduler": {"type": "MultiStepLR", "milestones": [100], "gamma": 0.5},
+                "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0, "reduction": "mean"},
+                "classify_opt": {"type": "CrossEntropyLoss", "loss_weight": 1.0}}}
+
+
+def _dcpt_step(model, sd_g, sd_h, idx):
+    model.get_bare_model(model.net_g).load_state_dict(sd_g, strict=True)
+    model.get_bare_model(model.net_dc).load_state_dict(sd_h, strict=True)
+    g = torch.Generator().manual_seed(21)
+    gt, lq = torch.rand(4, 3, 32, 32, generator=g), torch.rand(4, 3, 32, 32, generator=g)
+    labels = torch.tensor([4, 1, 0, 2])
+    model.feed_data({"lq": lq[idx], "gt": gt[idx], "dataset_idx": labels[idx]})
+    model.optimize_parameters(1)
+    flat = lambda net: torch.cat([p.grad.reshape(-1) for p in model.get_bare_model(net).parameters()])  # noqa: E731
+    return flat(model.net_g), flat(model.net_dc), model.get_current_log()
+
+
+def _worker_dcpt_model(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from basicsr.models import build_model
+    from dcpt_b200 import dist as D
+    from oracle import dchead_oracle as DH
+    from oracle import nafnet_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from boundary_overlay_check import CFG, DIMS, stub_engines
+    stub_engines()                                                        # no GPU here: the engines' math is the oracle's
+    D.init_dist("gloo", timeout_s=120)
+    sd_g = O.random_nafnet_state_dict(seed=3, **CFG)
+    sd_h = DH.random_dchead_state_dict(DIMS, 2, 5, seed=4)
+    calls = []
+    real = D.allreduce_mean_
+    D.allreduce_mean_ = lambda flat, group=None: (calls.append(flat.numel()), real(flat, group))[1]
+    model = build_model(_dcpt_opt(True))
+    wrapped = type(model.net_g).__name__ == "FlatGradDataParallel" and type(model.net_dc).__name__ == "FlatGradDataParallel"
+    hooked = sorted(n for n, m in model.net_g.named_modules() if len(m._forward_hooks) > 0)
+    gg, gh, log = _dcpt_step(model, sd_g, sd_h, D.shard_batch(4))
+    # a flat-buffer network: views of one base are exchanged as ONE all-reduce of the base
+    lin = torch.nn.Linear(600, 500)                                       # 1.2 MB: above the run threshold
+    base = torch.full((300500 + 16,), float(rank + 1))                    # 16 elements of alignment padding between the two views
+    lin.weight.grad = base[:300000].view(500, 600).detach()               # aliases without ._base, as autograd keeps them
+    lin.bias.grad = base[300016:].detach()
+    n_before = len(calls)
+    D.exchange_accumulated_grads_([lin])
+    base_ok = len(calls) == n_before + 1 and calls[-1] == 300516 and bool(torch.allclose(base, torch.full_like(base, (1 + world) / 2)))
+    if rank == 0:
+        D.allreduce_mean_ = real
+        torch.distributed.destroy_process_group()
+        single = build_model(_dcpt_opt(False))
+        fg, fh, flog = _dcpt_step(single, sd_g, sd_h, list(range(4)))
+        q.put((wrapped, hooked, len(calls) - 1, float((gg - fg).norm() / fg.norm()), float((gh - fh).norm() / fh.norm()),
+               abs(log["l_pix"] - flog["l_pix"]), abs(log["l_classify"] - flog["l_classify"]), base_ok))
+    else:
+        torch.distributed.destroy_process_group()
+
+
+def test_dcpt_model_data_parallel_gloo_world2():
+    """The DCPTModel mirror under ``dist: true`` (world 2, gloo): both networks wrapped, hooks found through the wrapper's
+    ``module.`` prefix exactly as with the reference's DDP (one-dot rule -> the decoder containers), the two net_g backward
+    nodes + the classifier exchanged ONCE per network after the backward, and the averaged gradients / logged losses equal to
+    the single-process step on the full batch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_worker_dcpt_model, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=400)
+        assert p.exitcode == 0
+    wrapped, hooked, n_calls, eg, eh, el, ec, base_ok = q.get(timeout=5)
+    assert wrapped and base_ok
+    assert hooked == ["module.decoder0", "module.decoder1", "module.decoder2", "module.decoder3"]
+    assert n_calls == 2, n_calls                       # one exchange per network for the whole two-pass step
+    assert eg < 1e-4 and eh < 1e-4, (eg, eh)
+    assert el < 1e-6 and ec < 1e-6
