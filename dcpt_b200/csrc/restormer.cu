@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/dcpt_ops.h"
@@ -338,13 +339,17 @@ struct dcpt_restormer_plan {
   struct ParamInfo { int dims[4]; long long numel; };
   std::vector<ParamInfo> params;
   struct Blk { int pidx, d, heads, hid, hidp; };
-  std::vector<Blk> stage[8];  // enc1, enc2, enc3, latent, dec3, dec2, dec1, refinement
+  std::vector<Blk> stage[11];  // enc1, enc2, enc3, latent, dec3, dec2, dec1, refinement; PromptIR: noise_level3, 2, 1
+  // PromptIR (promptir_arch.py:267-478): prompt{1,2,3} parameter indices / sizes, reduce_noise_level{1,2,3}
+  int variant = 0;
+  struct Prompt { int p_param, p_lw, p_lb, p_conv, D, L, S, lin; } prompt[3];
+  int p_rnoise[3];
   int p_embed, p_down[3], p_up[3], p_reduce[2], p_out;
 };
 
 namespace {
 
-enum { ST_ENC1 = 0, ST_ENC2, ST_ENC3, ST_LAT, ST_DEC3, ST_DEC2, ST_DEC1, ST_REF };
+enum { ST_ENC1 = 0, ST_ENC2, ST_ENC3, ST_LAT, ST_DEC3, ST_DEC2, ST_DEC1, ST_REF, ST_NOISE3, ST_NOISE2, ST_NOISE1, NST };
 
 int add_param(dcpt_restormer_plan* p, int d0, int d1 = 1, int d2 = 1, int d3 = 1) {
   dcpt_restormer_plan::ParamInfo pi;
@@ -436,12 +441,13 @@ struct BlkWork {
 };
 
 struct NetPacked {
-  std::vector<BlkPacked> blk[8];
+  std::vector<BlkPacked> blk[11];
   bf16 *down[3], *up[3], *reduce[2];
   bf16 *down_d[3], *up_d[3], *reduce_t[2];  // dgrad operands (flipped / transposed), used by the backward
   NetPacked(const dcpt_restormer_plan* p, Arena& a) {
-    for (int s = 0; s < 8; ++s)
+    for (int s = 0; s < 11; ++s)
       for (auto& b : p->stage[s]) blk[s].emplace_back(a, b);
+    if (p->variant) return;  // PromptIR keeps its resampling / reduce operands in PNetPacked
     int d = p->dim;
     for (int i = 0; i < 3; ++i) {  // down_i: d -> d/2 ; up_i (from level i+1 to i): 2d -> 4d
       down[i] = a.take<bf16>(dcpt_conv3x3_packed_elems(d / 2, d, 0));
@@ -679,6 +685,25 @@ int conv_fwd(const float* x, const bf16* wp, const NetWork& ws, int N, int H, in
   return conv3x3_tc_launch(a, st);
 }
 
+// bf16 operand images of every TransformerBlock of the plan (all stages)
+int pack_blocks(const dcpt_restormer_plan* p, const float* const* P, const NetPacked& pk, cudaStream_t st) {
+  for (int s = 0; s < NST; ++s)
+    for (size_t j = 0; j < p->stage[s].size(); ++j) {
+      const auto& b = p->stage[s][j];
+      const BlkIdx ix = blk_idx(p, b.pidx);
+      const BlkPacked& bp = pk.blk[s][j];
+      DCPT_TRY(pack_weight_launch(P[ix.qkv], nullptr, bp.wqkv, 3 * b.d, b.d, PACK_PLAIN, st));
+      pack_halves_kernel<bf16><<<blocks_for((long long)2 * b.hidp * b.d), 256, 0, st>>>(P[ix.pin], bp.wpin, b.hid, b.hidp, b.d);
+      pack_halves_kernel<float><<<blocks_for((long long)2 * b.hidp * 9), 256, 0, st>>>(P[ix.dw], bp.dwp, b.hid, b.hidp, 9);
+      pack_cols_kernel<<<blocks_for((long long)b.d * b.hidp), 256, 0, st>>>(P[ix.ffn_out], bp.wpout, b.d, b.hid, b.hidp);
+      DCPT_TRY(pack_weight_launch(P[ix.qkv], nullptr, bp.wqkv_t, 3 * b.d, b.d, PACK_T, st));
+      transpose_bf16_kernel<<<blocks_for((long long)2 * b.hidp * b.d), 256, 0, st>>>(bp.wpin, bp.wpin_t, 2 * b.hidp, b.d);
+      transpose_bf16_kernel<<<blocks_for((long long)b.d * b.hidp), 256, 0, st>>>(bp.wpout, bp.wpout_t, b.d, b.hidp);
+      DCPT_LAUNCH_CHECK();
+    }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -764,23 +789,11 @@ size_t dcpt_restormer_workspace_bytes(const dcpt_restormer_plan* plan, int N, in
 
 int dcpt_restormer_pack(const dcpt_restormer_plan* p, const float* const* P, void* packed, dcpt_stream_t stream) {
   DCPT_CHECK_ARG(P != nullptr && packed != nullptr, DCPT_E_ARG, "restormer_pack: null argument");
+  DCPT_CHECK_ARG(p->variant == 0, DCPT_E_ARG, "restormer_pack: PromptIR plans are packed by dcpt_promptir_pack");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena a(packed);
   NetPacked pk(p, a);
-  for (int s = 0; s < 8; ++s)
-    for (size_t j = 0; j < p->stage[s].size(); ++j) {
-      const auto& b = p->stage[s][j];
-      const BlkIdx ix = blk_idx(p, b.pidx);
-      const BlkPacked& bp = pk.blk[s][j];
-      DCPT_TRY(pack_weight_launch(P[ix.qkv], nullptr, bp.wqkv, 3 * b.d, b.d, PACK_PLAIN, st));
-      pack_halves_kernel<bf16><<<blocks_for((long long)2 * b.hidp * b.d), 256, 0, st>>>(P[ix.pin], bp.wpin, b.hid, b.hidp, b.d);
-      pack_halves_kernel<float><<<blocks_for((long long)2 * b.hidp * 9), 256, 0, st>>>(P[ix.dw], bp.dwp, b.hid, b.hidp, 9);
-      pack_cols_kernel<<<blocks_for((long long)b.d * b.hidp), 256, 0, st>>>(P[ix.ffn_out], bp.wpout, b.d, b.hid, b.hidp);
-      DCPT_TRY(pack_weight_launch(P[ix.qkv], nullptr, bp.wqkv_t, 3 * b.d, b.d, PACK_T, st));
-      transpose_bf16_kernel<<<blocks_for((long long)2 * b.hidp * b.d), 256, 0, st>>>(bp.wpin, bp.wpin_t, 2 * b.hidp, b.d);
-      transpose_bf16_kernel<<<blocks_for((long long)b.d * b.hidp), 256, 0, st>>>(bp.wpout, bp.wpout_t, b.d, b.hidp);
-      DCPT_LAUNCH_CHECK();
-    }
+  DCPT_TRY(pack_blocks(p, P, pk, st));
   int d = p->dim;
   for (int i = 0; i < 3; ++i) {
     DCPT_TRY(pack_conv3x3_launch(P[p->p_down[i]], pk.down[i], d / 2, d, 0, st));
@@ -951,6 +964,7 @@ int dcpt_restormer_fwd(const dcpt_restormer_plan* p, const float* const* P, cons
   DCPT_CHECK_ARG((long long)N * H * W * 6 * p->dim < (1ll << 31), DCPT_E_SHAPE, "restormer: batch too large for 32-bit pixel index");
   DCPT_CHECK_ARG(hook || out != nullptr, DCPT_E_ARG, "restormer_fwd: out is NULL but hook == 0");
   DCPT_CHECK_ARG(P && packed && inp && workspace, DCPT_E_ARG, "restormer_fwd: null argument");
+  DCPT_CHECK_ARG(p->variant == 0, DCPT_E_ARG, "restormer_fwd: PromptIR plans run through dcpt_promptir_fwd");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena ap(const_cast<void*>(packed));
   NetPacked pk(p, ap);
@@ -1031,6 +1045,7 @@ int dcpt_restormer_fwd_train(const dcpt_restormer_plan* p, const float* const* P
   DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, DCPT_E_SHAPE, "restormer: H=%d W=%d must be positive multiples of 8", H, W);
   DCPT_CHECK_ARG((long long)N * H * W * 6 * p->dim < (1ll << 31), DCPT_E_SHAPE, "restormer: batch too large for 32-bit pixel index");
   DCPT_CHECK_ARG(P && packed && inp && saved && workspace, DCPT_E_ARG, "restormer_fwd_train: null argument");
+  DCPT_CHECK_ARG(p->variant == 0, DCPT_E_UNSUPPORTED, "restormer_fwd_train: the PromptIR network is inference-only");
   DCPT_CHECK_ARG(hook || out != nullptr, DCPT_E_ARG, "restormer_fwd_train: out is NULL but hook == 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Arena ap(const_cast<void*>(packed));
@@ -1182,6 +1197,390 @@ int dcpt_restormer_bwd(const dcpt_restormer_plan* p, const float* const* P, cons
   DCPT_CUDA(cudaMemsetAsync(wk.cscr, 0, (size_t)27 * dim * sizeof(float), st));
   DCPT_TRY(conv3x3_small_wgrad_launch(cur, inp, wk.cscr, nullptr, 0, N, H, W, dim, st));
   return wgrad_finish_perm_launch(wk.cscr, G[p->p_embed], dim, 27, FIN_C3_TO_CN, st);
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// PromptIR (reference: basicsr/archs/promptir_arch.py:238-518) - inference.  The Restormer trunk with softmax attention
+// (:140), three PromptGenBlocks (:238-263) whose output is concatenated to the decoder stream, a "noise" TransformerBlock on
+// the widened stream and a 1x1 reduce conv after each (:480-505).  Everything reuses the block / conv / GEMM machinery above;
+// new here: the prompt generator (global mean -> linear -> softmax -> weighted prompt sum -> bilinear resize -> 3x3 conv) and
+// a PixelShuffle + concat whose two halves have different widths (up4_3 brings 2*dim channels to a 4*dim skip).
+// =====================================================================================================================
+namespace {
+
+// emb[n][c] += sum over a slice of the pixels of image n (emb pre-zeroed); grid (slices, N), block = C threads rounded up to 32
+__global__ void prompt_emb_kernel(const float* __restrict__ x, float* __restrict__ emb, int HW, int C) {
+  const int n = blockIdx.y, c = threadIdx.x;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int px = p0; px < p1; ++px) acc += __ldg(x + ((size_t)n * HW + px) * C + c);
+  atomicAdd(emb + (size_t)n * C + c, acc);
+}
+
+// pw[n][:] = softmax(lin_w [L, C] * (emb[n] / HW) + lin_b)   (promptir_arch.py:254-255); one block of 32 * L threads per image
+__global__ void prompt_weights_kernel(const float* __restrict__ emb, const float* __restrict__ lw, const float* __restrict__ lb,
+                                      float* __restrict__ pw, int C, int L, float inv_hw) {
+  __shared__ float logit[32];
+  const int n = blockIdx.x, l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(lw + (size_t)l * C + c), __ldg(emb + (size_t)n * C + c) * inv_hw, acc);
+  acc = warp_sum(acc);
+  if (lane == 0) logit[l] = acc + lb[l];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = logit[0];
+    for (int k = 1; k < L; ++k) m = fmaxf(m, logit[k]);
+    float sum = 0.f;
+    for (int k = 0; k < L; ++k) sum += expf(logit[k] - m);
+    for (int k = 0; k < L; ++k) pw[(size_t)n * L + k] = expf(logit[k] - m) / sum;
+  }
+}
+
+// mix[n][y][x][c] = sum_l pw[n][l] * param[l][c][y][x]   (:256-259; param is [1, L, D, S, S]), NHWC fp32 out
+__global__ void prompt_mix_kernel(const float* __restrict__ param, const float* __restrict__ pw, float* __restrict__ mix, long long total,
+                                  int L, int D, int S) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % D);
+  const long long t = idx / D;
+  const int xy = (int)(t % (S * S)), n = (int)(t / (S * S));
+  float acc = 0.f;
+  for (int l = 0; l < L; ++l) acc = fmaf(__ldg(pw + (size_t)n * L + l), __ldg(param + ((size_t)l * D + c) * S * S + xy), acc);
+  mix[idx] = acc;
+}
+
+// F.interpolate(mode="bilinear", align_corners=False) of NHWC fp32 [N, S, S, D] to [N, H, W, D], 16-bit out (:260)
+__global__ void bilinear_nhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long total, int S, int H, int W, int D) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % D);
+  long long t = idx / D;
+  const int x = (int)(t % W);
+  t /= W;
+  const int y = (int)(t % H), n = (int)(t / H);
+  const float sy = fmaxf(0.f, ((float)S / (float)H) * ((float)y + 0.5f) - 0.5f);
+  const float sx = fmaxf(0.f, ((float)S / (float)W) * ((float)x + 0.5f) - 0.5f);
+  const int y0 = min((int)sy, S - 1), x0 = min((int)sx, S - 1);
+  const int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float* b = in + (size_t)n * S * S * D + c;
+  const float v00 = __ldg(b + ((size_t)y0 * S + x0) * D), v01 = __ldg(b + ((size_t)y0 * S + x1) * D);
+  const float v10 = __ldg(b + ((size_t)y1 * S + x0) * D), v11 = __ldg(b + ((size_t)y1 * S + x1) * D);
+  const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  out[idx] = OP_FROM_F32(v);
+}
+
+// PixelShuffle(2) of conv [N, h, w, 4*Cc] followed by cat with skip [N, 2h, 2w, Cskip] -> [N, 2h, 2w, Cc + Cskip] (:485-486, :496-497)
+__global__ void pixel_shuffle_cat2_kernel(const float* __restrict__ conv, const float* __restrict__ skip, float* __restrict__ out_f32,
+                                          bf16* __restrict__ out_bf16, long long total, int h, int w, int Cc, int Cskip) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Ct = Cc + Cskip;
+  const int co = (int)(idx % Ct);
+  const long long px = idx / Ct;
+  const int W2 = 2 * w, H2 = 2 * h;
+  const int x = (int)(px % W2);
+  const long long t = px / W2;
+  const int y = (int)(t % H2), n = (int)(t / H2);
+  float v;
+  if (co < Cc) v = __ldg(conv + (((size_t)n * h + (y >> 1)) * w + (x >> 1)) * (4 * Cc) + co * 4 + (y & 1) * 2 + (x & 1));
+  else v = __ldg(skip + (size_t)px * Cskip + (co - Cc));
+  if (out_f32) out_f32[idx] = v;
+  if (out_bf16) out_bf16[idx] = OP_FROM_F32(v);
+}
+
+struct PNetPacked : NetPacked {
+  bf16 *pdown[3], *pup[3], *preduce[2], *prnoise[3], *pconv[3];
+  PNetPacked(const dcpt_restormer_plan* p, Arena& a) : NetPacked(p, a) {
+    const int dim = p->dim;
+    int d = dim;
+    for (int i = 0; i < 3; ++i) {  // down_i: d -> d/2 (then PixelUnshuffle)
+      pdown[i] = a.take<bf16>(dcpt_conv3x3_packed_elems(d / 2, d, 0));
+      d *= 2;
+    }
+    pup[2] = a.take<bf16>(dcpt_conv3x3_packed_elems(8 * dim, 4 * dim, 0));  // up4_3 = Upsample(4 dim)
+    pup[1] = a.take<bf16>(dcpt_conv3x3_packed_elems(8 * dim, 4 * dim, 0));  // up3_2 = Upsample(4 dim)
+    pup[0] = a.take<bf16>(dcpt_conv3x3_packed_elems(4 * dim, 2 * dim, 0));  // up2_1 = Upsample(2 dim)
+    preduce[0] = a.take<bf16>((size_t)4 * dim * (2 * dim + 192));
+    preduce[1] = a.take<bf16>((size_t)2 * dim * 4 * dim);
+    prnoise[2] = a.take<bf16>((size_t)4 * dim * (4 * dim + 512));
+    prnoise[1] = a.take<bf16>((size_t)4 * dim * (2 * dim + 224));
+    prnoise[0] = a.take<bf16>((size_t)2 * dim * (2 * dim + 64));
+    for (int i = 0; i < 3; ++i) pconv[i] = a.take<bf16>(dcpt_conv3x3_packed_elems(p->prompt[i].D, p->prompt[i].D, 0));
+  }
+};
+
+struct PNetWork {
+  float *e[4], *dx[3], *cat[3], *rx, *tmp, *conv, *G, *sq, *emb, *pw, *mix;
+  bf16 *n, *a, *b, *xm, *weff, *pint;
+  PNetWork(const dcpt_restormer_plan* p, Arena& ar, int N, int H, int W) {
+    const int dim = p->dim;
+    size_t M[4];
+    for (int l = 0; l < 4; ++l) M[l] = (size_t)N * (H >> l) * (W >> l);
+    size_t maxn = 0, maxa = 0, maxb = 0, maxg = 0, maxsq = 0, maxx = 0;
+    auto use = [&](int l, int d) {  // a TransformerBlock of width d at level l
+      const int hidp = ((int)(d * p->ffn) + 7) / 8 * 8;
+      const size_t wa = (size_t)(3 * d > 2 * hidp ? 3 * d : 2 * hidp), wb = (size_t)(3 * d > hidp ? 3 * d : hidp);
+      maxn = std::max(maxn, M[l] * d); maxa = std::max(maxa, M[l] * wa); maxb = std::max(maxb, M[l] * wb);
+      maxg = std::max(maxg, (size_t)N * d * d); maxsq = std::max(maxsq, (size_t)N * 2 * d); maxx = std::max(maxx, M[l] * d);
+    };
+    const int catd[3] = {2 * dim + 64, 2 * dim + 224, 4 * dim + 512};  // noise_level1 (level 1), 2 (level 2), 3 (level 3)
+    use(0, dim); use(0, 2 * dim); use(1, 2 * dim); use(2, 4 * dim); use(3, 8 * dim);
+    use(1, catd[0]); use(2, catd[1]); use(3, catd[2]);
+    maxx = std::max(maxx, M[2] * (size_t)(2 * dim + 192));  // cat of up4_3 and the level-3 skip
+    for (int l = 0; l < 4; ++l) e[l] = ar.take<float>(M[l] * (size_t)(dim << l));
+    dx[2] = ar.take<float>(M[2] * 4 * dim); dx[1] = ar.take<float>(M[1] * 2 * dim); dx[0] = ar.take<float>(M[0] * 2 * dim);
+    for (int i = 0; i < 3; ++i) cat[i] = ar.take<float>(M[i + 1] * (size_t)catd[i]);
+    rx = ar.take<float>(std::max(M[3] * 4 * dim, std::max(M[2] * 4 * dim, M[1] * 2 * dim)));
+    tmp = ar.take<float>(maxx);
+    conv = ar.take<float>(std::max(std::max(M[3] * 8 * dim, M[2] * 8 * dim), std::max(M[1] * 4 * dim, M[0] * (size_t)(dim / 2))));
+    n = ar.take<bf16>(maxn); a = ar.take<bf16>(maxa); b = ar.take<bf16>(maxb); xm = ar.take<bf16>(maxx);
+    G = ar.take<float>(maxg); sq = ar.take<float>(maxsq); weff = ar.take<bf16>(maxg);
+    emb = ar.take<float>((size_t)N * 8 * dim); pw = ar.take<float>((size_t)N * 8);
+    size_t maxmix = 0, maxpint = 0;
+    for (int i = 0; i < 3; ++i) {
+      maxmix = std::max(maxmix, (size_t)N * p->prompt[i].S * p->prompt[i].S * p->prompt[i].D);
+      maxpint = std::max(maxpint, M[i + 1] * (size_t)p->prompt[i].D);
+    }
+    mix = ar.take<float>(maxmix);
+    pint = ar.take<bf16>(maxpint);
+  }
+  BlkBufs bufs() const {
+    BlkBufs bf;
+    bf.n1 = bf.n2 = n; bf.qkv = bf.u = a; bf.qkvd = bf.g = b; bf.weff = weff; bf.weffT = nullptr;
+    bf.G = G; bf.sq = sq; bf.x2 = tmp; bf.stats1 = bf.stats2 = nullptr;
+    return bf;
+  }
+};
+
+int pstage(const dcpt_restormer_plan* p, int s, const float* const* P, const PNetPacked& pk, float* x, const PNetWork& ws, int N, int H,
+           int W, cudaStream_t st) {
+  const BlkBufs bf = ws.bufs();
+  for (size_t j = 0; j < p->stage[s].size(); ++j) DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, x, bf, N, H, W, st));
+  return 0;
+}
+
+// 1x1 conv of the fp32 stream x [M, Cin] -> out fp32 [M, Cout] (+bias)
+int pconv1x1(const float* x, const bf16* wp, const float* bias, float* out, const PNetWork& ws, int M, int Cin, int Cout, cudaStream_t st) {
+  DCPT_TRY(cast_f32_bf16_launch(x, ws.xm, (long long)M * Cin, st));
+  GemmArgs g = make_gemm_args(M, Cout, Cin, ws.xm, Cin, wp, Cin, EPI_STORE);
+  g.ep.out_f32 = out; g.ep.ldo = Cout; g.ep.bias = bias;
+  return gemm_launch(g, st);
+}
+
+// x [N, h, w, d] -> cat[i] = [x | PromptGenBlock_i(x)] -> noise block -> reduce_noise 1x1 -> ws.rx [N, h, w, dout]
+int prompt_stage(const dcpt_restormer_plan* p, int i, int noise_stage, const float* const* P, const PNetPacked& pk, const float* x,
+                 const PNetWork& ws, int N, int h, int w, int d, int dout, cudaStream_t st) {
+  const auto& pr = p->prompt[i];
+  const int HW = h * w, M = N * HW, dc = d + pr.D;
+  DCPT_CHECK_ARG(pr.lin == d && p->stage[noise_stage].size() == 1 && p->stage[noise_stage][0].d == dc, DCPT_E_SHAPE,
+                 "promptir: prompt %d expects %d channels, stream has %d", i + 1, pr.lin, d);
+  DCPT_CUDA(cudaMemsetAsync(ws.emb, 0, (size_t)N * d * sizeof(float), st));
+  const int slices = std::max(1, std::min(64, HW / 64));
+  prompt_emb_kernel<<<dim3(slices, N), (d + 31) / 32 * 32, 0, st>>>(x, ws.emb, HW, d);
+  prompt_weights_kernel<<<N, 32 * pr.L, 0, st>>>(ws.emb, P[pr.p_lw], P[pr.p_lb], ws.pw, d, pr.L, 1.f / (float)HW);
+  const long long tmix = (long long)N * pr.S * pr.S * pr.D;
+  prompt_mix_kernel<<<blocks_for(tmix), 256, 0, st>>>(P[pr.p_param], ws.pw, ws.mix, tmix, pr.L, pr.D, pr.S);
+  const long long tint = (long long)M * pr.D;
+  bilinear_nhwc_kernel<<<blocks_for(tint), 256, 0, st>>>(ws.mix, ws.pint, tint, pr.S, h, w, pr.D);
+  DCPT_LAUNCH_CHECK();
+  float* cat = ws.cat[i];
+  DCPT_CUDA(cudaMemcpy2DAsync(cat, (size_t)dc * sizeof(float), x, (size_t)d * sizeof(float), (size_t)d * sizeof(float), M,
+                              cudaMemcpyDeviceToDevice, st));
+  {  // conv3x3 of the resized prompt, written into the prompt half of the concatenated stream (:261, :481)
+    Conv3x3Args a;
+    memset(&a, 0, sizeof(a));
+    a.X = ws.pint; a.N = N; a.H = h; a.W = w; a.Cin = pr.D; a.Wp = pk.pconv[i]; a.Cout = pr.D;
+    a.ep.out_f32 = cat + d; a.ep.ldo = dc;
+    DCPT_TRY(conv3x3_tc_launch(a, st));
+  }
+  DCPT_TRY(pstage(p, noise_stage, P, pk, cat, ws, N, h, w, st));
+  return pconv1x1(cat, pk.prnoise[i], p->bias ? P[p->p_rnoise[i] + 1] : nullptr, ws.rx, ws, M, dc, dout, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+dcpt_restormer_plan* dcpt_promptir_create(int inp_channels, int out_channels, int dim, const int* num_blocks, int num_refinement_blocks,
+                                          const int* heads, double ffn_expansion_factor, int bias, int ln_with_bias) {
+  // the prompt widths (64 / 128 / 320), their linear inputs (96 / 192 / 384) and the "+192 / +512 / +224 / +64" channel counts are
+  // literals in the reference (promptir_arch.py:290-299, 366-415): the module only assembles for dim = 48
+  if (inp_channels != 3 || out_channels != 3 || dim != 48 || !num_blocks || !heads || num_refinement_blocks < 0 || ffn_expansion_factor <= 0) {
+    dcpt_set_error("promptir_create: need inp/out channels 3 and dim 48 (dim=%d inp=%d out=%d)", dim, inp_channels, out_channels);
+    return nullptr;
+  }
+  for (int l = 0; l < 4; ++l)
+    if (heads[l] <= 0 || ((dim << l) % heads[l]) != 0 || num_blocks[l] < 0) {
+      dcpt_set_error("promptir_create: level %d: dim %d not divisible by heads %d", l, dim << l, heads[l]);
+      return nullptr;
+    }
+  if ((4 * dim + 512) % heads[2] || (2 * dim + 224) % heads[2] || (2 * dim + 64) % heads[2]) {
+    dcpt_set_error("promptir_create: the noise blocks' widths are not divisible by heads[2] = %d", heads[2]);
+    return nullptr;
+  }
+  dcpt_restormer_plan* p = new dcpt_restormer_plan();
+  p->variant = 1;
+  p->attn_softmax = 1;
+  p->inp_ch = inp_channels; p->out_ch = out_channels; p->dim = dim; p->nref = num_refinement_blocks;
+  p->bias = bias != 0; p->ln_bias = ln_with_bias != 0; p->ffn = ffn_expansion_factor;
+  for (int l = 0; l < 4; ++l) { p->nb[l] = num_blocks[l]; p->heads[l] = heads[l]; }
+  // named_parameters() order = registration order of PromptIR.__init__ (promptir_arch.py:284-462)
+  p->p_embed = add_param(p, dim, inp_channels, 3, 3);
+  const int PD[3] = {64, 128, 320}, PS[3] = {64, 32, 16}, PL[3] = {96, 192, 384};
+  for (int i = 0; i < 3; ++i) {
+    auto& pr = p->prompt[i];
+    pr.D = PD[i]; pr.L = 5; pr.S = PS[i]; pr.lin = PL[i];
+    pr.p_param = add_param(p, pr.L * pr.D, pr.S, pr.S);  // [1, 5, D, S, S]
+    pr.p_lw = add_param(p, pr.L, pr.lin);
+    pr.p_lb = add_param(p, pr.L);
+    pr.p_conv = add_param(p, pr.D, pr.D, 3, 3);
+  }
+  add_stage(p, ST_ENC1, dim, heads[0], num_blocks[0]);
+  p->p_down[0] = add_param(p, dim / 2, dim, 3, 3);
+  add_stage(p, ST_ENC2, dim * 2, heads[1], num_blocks[1]);
+  p->p_down[1] = add_param(p, dim, dim * 2, 3, 3);
+  add_stage(p, ST_ENC3, dim * 4, heads[2], num_blocks[2]);
+  p->p_down[2] = add_param(p, dim * 2, dim * 4, 3, 3);
+  add_stage(p, ST_LAT, dim * 8, heads[3], num_blocks[3]);
+  p->p_up[2] = add_param(p, dim * 8, dim * 4, 3, 3);
+  p->p_reduce[0] = add_param(p, dim * 4, dim * 2 + 192, 1, 1);
+  if (p->bias) add_param(p, dim * 4);
+  add_stage(p, ST_NOISE3, dim * 4 + 512, heads[2], 1);
+  p->p_rnoise[2] = add_param(p, dim * 4, dim * 4 + 512, 1, 1);
+  if (p->bias) add_param(p, dim * 4);
+  add_stage(p, ST_DEC3, dim * 4, heads[2], num_blocks[2]);
+  p->p_up[1] = add_param(p, dim * 8, dim * 4, 3, 3);
+  p->p_reduce[1] = add_param(p, dim * 2, dim * 4, 1, 1);
+  if (p->bias) add_param(p, dim * 2);
+  add_stage(p, ST_NOISE2, dim * 2 + 224, heads[2], 1);
+  p->p_rnoise[1] = add_param(p, dim * 4, dim * 2 + 224, 1, 1);
+  if (p->bias) add_param(p, dim * 4);
+  add_stage(p, ST_DEC2, dim * 2, heads[1], num_blocks[1]);
+  p->p_up[0] = add_param(p, dim * 4, dim * 2, 3, 3);
+  add_stage(p, ST_NOISE1, dim * 2 + 64, heads[2], 1);
+  p->p_rnoise[0] = add_param(p, dim * 2, dim * 2 + 64, 1, 1);
+  if (p->bias) add_param(p, dim * 2);
+  add_stage(p, ST_DEC1, dim * 2, heads[0], num_blocks[0]);
+  add_stage(p, ST_REF, dim * 2, heads[0], num_refinement_blocks);
+  p->p_out = add_param(p, out_channels, dim * 2, 3, 3);
+  if (p->bias) add_param(p, out_channels);
+  return p;
+}
+
+size_t dcpt_promptir_packed_bytes(const dcpt_restormer_plan* plan) {
+  if (!plan || plan->variant != 1) return 0;
+  Arena a(nullptr);
+  PNetPacked pk(plan, a);
+  return a.size();
+}
+
+size_t dcpt_promptir_workspace_bytes(const dcpt_restormer_plan* plan, int N, int H, int W) {
+  if (!plan || plan->variant != 1) return 0;
+  Arena a(nullptr);
+  PNetWork ws(plan, a, N, H, W);
+  return a.size();
+}
+
+int dcpt_promptir_pack(const dcpt_restormer_plan* p, const float* const* P, void* packed, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(p && p->variant == 1 && P && packed, DCPT_E_ARG, "promptir_pack: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena a(packed);
+  PNetPacked pk(p, a);
+  DCPT_TRY(pack_blocks(p, P, pk, st));
+  const int dim = p->dim;
+  int d = dim;
+  for (int i = 0; i < 3; ++i) {
+    DCPT_TRY(pack_conv3x3_launch(P[p->p_down[i]], pk.pdown[i], d / 2, d, 0, st));
+    d *= 2;
+  }
+  DCPT_TRY(pack_conv3x3_launch(P[p->p_up[2]], pk.pup[2], 8 * dim, 4 * dim, 0, st));
+  DCPT_TRY(pack_conv3x3_launch(P[p->p_up[1]], pk.pup[1], 8 * dim, 4 * dim, 0, st));
+  DCPT_TRY(pack_conv3x3_launch(P[p->p_up[0]], pk.pup[0], 4 * dim, 2 * dim, 0, st));
+  DCPT_TRY(pack_weight_launch(P[p->p_reduce[0]], nullptr, pk.preduce[0], 4 * dim, 2 * dim + 192, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[p->p_reduce[1]], nullptr, pk.preduce[1], 2 * dim, 4 * dim, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[p->p_rnoise[2]], nullptr, pk.prnoise[2], 4 * dim, 4 * dim + 512, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[p->p_rnoise[1]], nullptr, pk.prnoise[1], 4 * dim, 2 * dim + 224, PACK_PLAIN, st));
+  DCPT_TRY(pack_weight_launch(P[p->p_rnoise[0]], nullptr, pk.prnoise[0], 2 * dim, 2 * dim + 64, PACK_PLAIN, st));
+  for (int i = 0; i < 3; ++i) DCPT_TRY(pack_conv3x3_launch(P[p->prompt[i].p_conv], pk.pconv[i], p->prompt[i].D, p->prompt[i].D, 0, st));
+  return 0;
+}
+
+int dcpt_promptir_fwd(const dcpt_restormer_plan* p, const float* const* P, const void* packed, const float* inp, float* out, void* workspace,
+                      int N, int H, int W, dcpt_stream_t stream) {
+  DCPT_CHECK_ARG(p && p->variant == 1 && P && packed && inp && out && workspace, DCPT_E_ARG, "promptir_fwd: bad argument");
+  DCPT_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0, DCPT_E_SHAPE,
+                 "promptir: H=%d W=%d must be positive multiples of 8 (SRModel.pre_test pads to window_size)", H, W);
+  DCPT_CHECK_ARG((long long)N * H * W * 6 * p->dim < (1ll << 31), DCPT_E_SHAPE, "promptir: batch too large for 32-bit pixel index");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Arena ap(const_cast<void*>(packed));
+  PNetPacked pk(p, ap);
+  Arena aw(workspace);
+  PNetWork ws(p, aw, N, H, W);
+  const int dim = p->dim;
+  auto conv3 = [&](const float* x, const bf16* wp, int h, int w, int Cin, int Cout) -> int {  // -> ws.conv fp32
+    DCPT_TRY(cast_f32_bf16_launch(x, ws.xm, (long long)N * h * w * Cin, st));
+    return conv3_fwd_from(ws.xm, wp, ws.conv, N, h, w, Cin, Cout, st);
+  };
+  // encoder (:465-476)
+  DCPT_TRY(conv3x3_img_to_feat_launch(inp, P[p->p_embed], nullptr, 0, ws.e[0], nullptr, nullptr, N, H, W, dim, st));
+  DCPT_TRY(pstage(p, ST_ENC1, P, pk, ws.e[0], ws, N, H, W, st));
+  int d = dim, h = H, w = W;
+  for (int l = 0; l < 3; ++l) {
+    DCPT_TRY(conv3(ws.e[l], pk.pdown[l], h, w, d, d / 2));
+    const long long total = (long long)N * h * w * (d / 2);
+    pixel_unshuffle_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, ws.e[l + 1], total, h, w, d / 2);
+    DCPT_LAUNCH_CHECK();
+    d *= 2; h /= 2; w /= 2;
+    DCPT_TRY(pstage(p, ST_ENC2 + l, P, pk, ws.e[l + 1], ws, N, h, w, st));
+  }
+  // level 4 -> 3 (:478-490): prompt3 + noise_level3 + reduce, up4_3, cat with the level-3 skip, reduce, decoder_level3
+  DCPT_TRY(prompt_stage(p, 2, ST_NOISE3, P, pk, ws.e[3], ws, N, h, w, 8 * dim, 4 * dim, st));
+  DCPT_TRY(conv3(ws.rx, pk.pup[2], h, w, 4 * dim, 8 * dim));
+  {
+    const int Cc = 2 * dim, Cs = 4 * dim;
+    const long long total = (long long)N * h * w * 4 * (Cc + Cs);
+    pixel_shuffle_cat2_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, ws.e[2], nullptr, ws.xm, total, h, w, Cc, Cs);
+    DCPT_LAUNCH_CHECK();
+    h *= 2; w *= 2;
+    GemmArgs g = make_gemm_args(N * h * w, 4 * dim, Cc + Cs, ws.xm, Cc + Cs, pk.preduce[0], Cc + Cs, EPI_STORE);
+    g.ep.out_f32 = ws.dx[2]; g.ep.ldo = 4 * dim;
+    if (p->bias) g.ep.bias = P[p->p_reduce[0] + 1];
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  DCPT_TRY(pstage(p, ST_DEC3, P, pk, ws.dx[2], ws, N, h, w, st));
+  // level 3 -> 2 (:491-501)
+  DCPT_TRY(prompt_stage(p, 1, ST_NOISE2, P, pk, ws.dx[2], ws, N, h, w, 4 * dim, 4 * dim, st));
+  DCPT_TRY(conv3(ws.rx, pk.pup[1], h, w, 4 * dim, 8 * dim));
+  {
+    const int Cc = 2 * dim, Cs = 2 * dim;
+    const long long total = (long long)N * h * w * 4 * (Cc + Cs);
+    pixel_shuffle_cat2_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, ws.e[1], nullptr, ws.xm, total, h, w, Cc, Cs);
+    DCPT_LAUNCH_CHECK();
+    h *= 2; w *= 2;
+    GemmArgs g = make_gemm_args(N * h * w, 2 * dim, Cc + Cs, ws.xm, Cc + Cs, pk.preduce[1], Cc + Cs, EPI_STORE);
+    g.ep.out_f32 = ws.dx[1]; g.ep.ldo = 2 * dim;
+    if (p->bias) g.ep.bias = P[p->p_reduce[1] + 1];
+    DCPT_TRY(gemm_launch(g, st));
+  }
+  DCPT_TRY(pstage(p, ST_DEC2, P, pk, ws.dx[1], ws, N, h, w, st));
+  // level 2 -> 1 (:502-512): prompt1 + noise_level1 + reduce, up2_1, cat with the level-1 skip (no reduce conv)
+  DCPT_TRY(prompt_stage(p, 0, ST_NOISE1, P, pk, ws.dx[1], ws, N, h, w, 2 * dim, 2 * dim, st));
+  DCPT_TRY(conv3(ws.rx, pk.pup[0], h, w, 2 * dim, 4 * dim));
+  {
+    const long long total = (long long)N * h * w * 4 * (2 * dim);
+    pixel_shuffle_cat2_kernel<<<blocks_for(total), 256, 0, st>>>(ws.conv, ws.e[0], ws.dx[0], nullptr, total, h, w, dim, dim);
+    DCPT_LAUNCH_CHECK();
+    h *= 2; w *= 2;
+  }
+  DCPT_TRY(pstage(p, ST_DEC1, P, pk, ws.dx[0], ws, N, h, w, st));
+  DCPT_TRY(pstage(p, ST_REF, P, pk, ws.dx[0], ws, N, h, w, st));
+  // output conv + global residual (:514)
+  return conv3x3_feat_to_img_launch(ws.dx[0], P[p->p_out], p->bias ? P[p->p_out + 1] : nullptr, inp, out, N, H, W, 2 * dim, st);
 }
 
 }  // extern "C"

@@ -112,6 +112,11 @@ PROTOTYPES = {
     "dcpt_optim_param_hash": (_I, [_VP, _VP, _VP, _VP]),
     "dcpt_optim_step": (_I, [_VP, _VP, _I, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _LL, C.c_double, C.c_double, _VP]),
     "dcpt_restormer_fwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _I, _I, _I, _I, _VP]),
+    "dcpt_promptir_create": (_VP, [_I, _I, _I, C.POINTER(_I), _I, C.POINTER(_I), C.c_double, _I, _I]),
+    "dcpt_promptir_packed_bytes": (_SZ, [_VP]),
+    "dcpt_promptir_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
+    "dcpt_promptir_pack": (_I, [_VP, _PP, _VP, _VP]),
+    "dcpt_promptir_fwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
 }
 
 

@@ -18,6 +18,11 @@ from .params import LRUCache, PackedCacheKey, fp16_grad_scale
 
 
 class RestormerEngine:
+    _ABI = "dcpt_restormer"     # prefix of the create / packed_bytes / workspace_bytes / pack entry points (PromptIREngine: dcpt_promptir)
+
+    def _fn(self, name):
+        return getattr(self.lib, f"{self._ABI}_{name}")
+
     def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=(4, 6, 6, 8), num_refinement_blocks=4, heads=(1, 2, 4, 8),
                  ffn_expansion_factor=2.66, bias=False, ln_with_bias=False, attn_softmax=False):
         """attn_softmax: the transposed attention map goes through softmax(dim=-1) (PromptIR's transformer blocks,
@@ -25,10 +30,10 @@ class RestormerEngine:
         self.lib = _l.load_library()
         nb = (C.c_int * 4)(*num_blocks)
         hd = (C.c_int * 4)(*heads)
-        plan = self.lib.dcpt_restormer_create(inp_channels, out_channels, dim, nb, num_refinement_blocks, hd,
+        plan = self._fn("create")(inp_channels, out_channels, dim, nb, num_refinement_blocks, hd,
                                               float(ffn_expansion_factor), int(bool(bias)), int(bool(ln_with_bias)))
         if not plan:
-            raise _l.DcptError("dcpt_restormer_create: " + self.lib.dcpt_last_error().decode())
+            raise _l.DcptError(f"{self._ABI}_create: " + self.lib.dcpt_last_error().decode())
         self.plan = C.c_void_p(plan)
         self.dim = dim
         if attn_softmax:
@@ -68,11 +73,11 @@ class RestormerEngine:
 
     def packed_for(self, params):
         if self._packed is None or self._packed.device != params[0].device:
-            self._packed = torch.empty(self.lib.dcpt_restormer_packed_bytes(self.plan), dtype=torch.uint8, device=params[0].device)
+            self._packed = torch.empty(self._fn("packed_bytes")(self.plan), dtype=torch.uint8, device=params[0].device)
             self._packed_key.invalidate()
         if self._packed_key.stale(params):     # version counters + no-grad weight fingerprint, dcpt_b200/params.py
             pp = _l.ptr_array([p.data_ptr() for p in params])
-            _l.check(self.lib.dcpt_restormer_pack(self.plan, pp, _p(self._packed), _stream()), "restormer_pack")
+            _l.check(self._fn("pack")(self.plan, pp, _p(self._packed), _stream()), f"{self._ABI}_pack")
         return self._packed
 
     def invalidate_packed(self):

@@ -341,6 +341,22 @@ int dcpt_restormer_bwd(const dcpt_restormer_plan* plan, const float* const* host
                        const float* inp, const float* dout, const float* const* dfeats, float* const* host_grads, void* workspace,
                        int N, int H, int W, dcpt_stream_t stream);
 
+/* PromptIR (basicsr/archs/promptir_arch.py:267-518), inference: the Restormer trunk with softmax attention (:140), three
+ * PromptGenBlocks (:238-263: global mean -> Linear -> softmax -> weighted sum of the prompt components -> bilinear resize
+ * -> 3x3 conv) concatenated to the decoder stream, a "noise" TransformerBlock and a 1x1 reduce conv after each (:478-505).
+ * The plan is a dcpt_restormer_plan (destroy / num_params / param_shape as above; parameters in PromptIR.named_parameters()
+ * order, `prompt_param` [1,5,D,S,S] reported as [5*D, S, S, 1]); dim must be 48 (the prompt widths are literals in the
+ * reference), LayerNorm "WithBias" = ln_with_bias 1 is the reference's default.  Replaces PromptIR.forward(inp_img) (:465-518)
+ * as called by SRModel.test (sr_model.py:176-185) for options/all_in_one/test/test_PromptIR_5d.yml. */
+dcpt_restormer_plan* dcpt_promptir_create(int inp_channels, int out_channels, int dim, const int* num_blocks,
+                                          int num_refinement_blocks, const int* heads, double ffn_expansion_factor, int bias,
+                                          int ln_with_bias);
+size_t dcpt_promptir_packed_bytes(const dcpt_restormer_plan* plan);
+size_t dcpt_promptir_workspace_bytes(const dcpt_restormer_plan* plan, int N, int H, int W);
+int dcpt_promptir_pack(const dcpt_restormer_plan* plan, const float* const* host_params, void* packed, dcpt_stream_t stream);
+int dcpt_promptir_fwd(const dcpt_restormer_plan* plan, const float* const* host_params, const void* packed, const float* inp,
+                      float* out, void* workspace, int N, int H, int W, dcpt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Parameter update of the training step — SURVEY.md §8(f) row 1.  Replaces, in SRModel.optimize_parameters
  * (basicsr/models/sr_model.py:164-174): torch.nn.utils.clip_grad_norm_(net_g.parameters(), grad_clip) (:166-167),

@@ -14,7 +14,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SUITES = ["tests/test_gpu_kernels.py", "tests/test_gpu_nafnet.py", "tests/test_gpu_restormer.py", "tests/test_gpu_dchead.py"]
+SUITES = ["tests/test_gpu_kernels.py", "tests/test_gpu_nafnet.py", "tests/test_gpu_restormer.py", "tests/test_gpu_dchead.py",
+          "tests/test_gpu_promptir.py", "tests/test_gpu_models.py"]
 
 
 @pytest.mark.skipif(os.getenv("DCPT_OPERAND", "bf16").lower() == "fp16", reason="already inside the fp16 child run")

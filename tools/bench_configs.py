@@ -99,6 +99,15 @@ def main():
             ms = timeit(lambda: rnet(xr), args.iters)
         res[f"C3_restormer_infer_b{B}_128"] = {"ms": round(ms, 3), "MPix/s": round(B * 128 * 128 / ms / 1e3, 3),
                                                "TFLOP/s": round(B * 77.44e9 / (ms * 1e-3) / 1e12, 1)}
+    # PromptIR (options/all_in_one/test/test_PromptIR_5d.yml: default ctor, 35.4 M parameters), inference on 128 x 128 tiles
+    pnet = build_network(dict(type="PromptIR", window_size=8)).to(dev)
+    for B in (1, 16):
+        xp = torch.rand(B, 3, 128, 128, device=dev, generator=g)
+        with torch.no_grad():
+            ms = timeit(lambda: pnet(xp), args.iters)
+        res[f"promptir_infer_b{B}_128"] = {"ms": round(ms, 3), "MPix/s": round(B * 128 * 128 / ms / 1e3, 3)}
+    del pnet
+    torch.cuda.empty_cache()
     # Restormer fine-tune step (not a BASELINE config; recorded for the training path): fwd + L1 + bwd, 128 x 128, batch 4
     xr = torch.rand(4, 3, 128, 128, device=dev, generator=g)
     tr = torch.rand(4, 3, 128, 128, device=dev, generator=g)
