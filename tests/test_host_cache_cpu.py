@@ -35,3 +35,10 @@ def test_packed_cache_key_tracks_versions_and_storage():
     assert k.stale([q.detach() for q in p])
     k.invalidate()
     assert k.stale([q.detach() for q in p])
+
+
+def test_cuda_prefetcher_has_no_cpu_path():
+    from dcpt_b200.prefetch import CUDAPrefetcher
+    import pytest as _pytest
+    with _pytest.raises(Exception, match="no CPU path"):
+        CUDAPrefetcher([{"lq": torch.zeros(1)}], {"num_gpu": 0})
