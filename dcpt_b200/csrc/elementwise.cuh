@@ -33,6 +33,9 @@ int dwconv_bwd_data_launch(const bf16* du2, const float* w2, bf16* du, float* co
 // Simplified channel attention (nafnet_arch.py:116-127).
 int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, int N, int C, int HW, cudaStream_t st);
 int scale_rows_launch(const bf16* g, const float* s, bf16* gs, int N, int HW, int C, cudaStream_t st);
+// both in one launch: s as sca_fwd_launch (bit-identical), gs = g * s
+int sca_scale_launch(const float* pool, const float* w, const float* b, const bf16* g, float* s, bf16* gs, int N, int C, int HW,
+                     cudaStream_t st);
 int sca_ds_reduce_launch(const bf16* dgs, const bf16* g, float* ds, int N, int HW, int C, cudaStream_t st);
 int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t, float* dw, float* db, int N, int C, int HW,
                    cudaStream_t st, cudaStream_t st_w = nullptr);

@@ -26,6 +26,83 @@ __global__ void sca_fwd_kernel(const float* __restrict__ pool, const float* __re
   if (lane == 0) s[gw] = b[co] + acc * inv_hw;
 }
 
+// SCA in ONE launch (nafnet_arch.py:171-173: x * sca(x)): a CTA owns (image n, 64-channel group, pixel slice).  It first computes
+// its 64 values of s - every CTA of a group recomputes them (64 x C MACs, the weight rows come from L2), so no grid-wide
+// dependency is needed between "s is known" and "rows are scaled" - then scales its pixels.  The per-row summation order is
+// sca_fwd_kernel's (four chains per lane, fixed combine), so s is bit-identical to the two-kernel path; eight rows are in
+// flight per warp.  Slice 0 writes s (saved for the backward).
+__global__ void __launch_bounds__(256)
+sca_scale_kernel(const float* __restrict__ pool, const float* __restrict__ w, const float* __restrict__ b, const bf16* __restrict__ g,
+                 float* __restrict__ s, bf16* __restrict__ gs, int C, int HW, float inv_hw) {
+  __shared__ float s_s[64];
+  pdl_sync();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 64, n = blockIdx.y;
+  {
+    float a4[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a4[r][0] = a4[r][1] = a4[r][2] = a4[r][3] = 0.f;
+    const float* prow = pool + (size_t)n * C;
+    int ci = lane;
+    for (; ci + 96 < C; ci += 128) {
+      float pv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pv[k] = __ldg(prow + ci + 32 * k);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int co = min(c0 + warp * 8 + r, C - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a4[r][k] = fmaf(__ldg(w + (size_t)co * C + ci + 32 * k), pv[k], a4[r][k]);
+      }
+    }
+    for (; ci < C; ci += 32) {
+      const float pv = __ldg(prow + ci);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int co = min(c0 + warp * 8 + r, C - 1);
+        a4[r][0] = fmaf(__ldg(w + (size_t)co * C + ci), pv, a4[r][0]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float acc = warp_sum((a4[r][0] + a4[r][1]) + (a4[r][2] + a4[r][3]));
+      const int co = c0 + warp * 8 + r;
+      if (lane == 0) {
+        const float v = co < C ? b[co] + acc * inv_hw : 0.f;
+        s_s[warp * 8 + r] = v;
+        if (co < C && blockIdx.z == 0) s[(size_t)n * C + co] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // 8 threads x 16 bytes cover the group's 64 channels of one pixel; 32 pixels per pass, 4 passes in flight
+  // (requesting the first rows before the mat-vec, or 4 CTAs per SM, measured no better / worse: r03b, r03c)
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c8 = c0 + sub * 8;
+  if (c8 >= C) return;
+  float sv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sv[k] = s_s[sub * 8 + k];
+  const int per = (HW + gridDim.z - 1) / gridDim.z;
+  const int p0 = blockIdx.z * per, p1 = min(HW, p0 + per);
+  const size_t img = (size_t)n * HW;
+  for (int px = p0 + pl; px < p1; px += 128) {
+    uint4 raw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (px + 32 * k < p1) raw[k] = ldg16(g + (img + px + 32 * k) * C + c8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (px + 32 * k < p1) {
+        float v[8];
+        unpack8(raw[k], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= sv[j];
+        stg16(gs + (img + px + 32 * k) * C + c8, pack8(v));
+      }
+  }
+}
+
 // four 16-byte vectors per thread (a block covers 1024 consecutive vectors): all loads are issued before the first use
 __global__ void __launch_bounds__(256) scale_rows_kernel(const bf16* __restrict__ g, const float* __restrict__ s, bf16* __restrict__ gs,
                                                          long long nvec, int HW, int C) {
@@ -441,6 +518,19 @@ int sca_fwd_launch(const float* pool, const float* w, const float* b, float* s, 
   const long long threads = (long long)N * C * 32;
   DCPT_PROF("sca_fwd", 2.0 * N * C * C, 4.0 * C * C, st);
   DCPT_CUDA(dcpt_launch_pdl(sca_fwd_kernel, dim3((unsigned)ceil_div_ll(threads, 256)), dim3(256), 0, st, pool, w, b, s, N, C, 1.f / (float)HW));
+  DCPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int sca_scale_launch(const float* pool, const float* w, const float* b, const bf16* g, float* s, bf16* gs, int N, int C, int HW,
+                     cudaStream_t st) {
+  DCPT_CHECK_ARG(C % 8 == 0 && C >= 8, DCPT_E_SHAPE, "sca_scale: C=%d must be a multiple of 8", C);
+  const int groups = ceil_div(C, 64);
+  int slices = (2 * dcpt_num_sms()) / (groups * N);  // ~2 CTAs per SM; every slice recomputes its group's 64 x C mat-vec
+  if (slices < 1) slices = 1;
+  if (slices > HW / 128) slices = HW / 128 > 0 ? HW / 128 : 1;
+  DCPT_PROF("sca_scale", 2.0 * N * C * C * slices + (double)N * HW * C, 4.0 * N * HW * C + 4.0 * C * C, st);
+  DCPT_CUDA(dcpt_launch_pdl(sca_scale_kernel, dim3(groups, N, slices), dim3(256), 0, st, pool, w, b, g, s, gs, C, HW, 1.f / (float)HW));
   DCPT_LAUNCH_CHECK();
   return 0;
 }

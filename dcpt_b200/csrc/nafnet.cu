@@ -201,6 +201,16 @@ struct LnFuse {
 };
 constexpr float kLnEps = 1e-6f;  // LayerNorm2d default (nafnet_arch.py:57)
 
+// SCA mat-vec and the row scaling in one launch (sca_scale_launch); DCPT_SCA_FUSE=0 keeps the two kernels
+bool sca_fused() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DCPT_SCA_FUSE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 bool ln_fuse_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -256,8 +266,12 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
     DCPT_TRY(mul_bf16_launch(sv.g, sv.u, sv.gs, (long long)M * C, st));
   } else {
     // sca, x * sca(x)
-    DCPT_TRY(sca_fwd_launch(sv.pool, P[P_SCAW], P[P_SCAB], sv.s, N, C, HW, st));
-    DCPT_TRY(scale_rows_launch(sv.g, sv.s, sv.gs, N, HW, C, st));
+    if (sca_fused()) {
+      DCPT_TRY(sca_scale_launch(sv.pool, P[P_SCAW], P[P_SCAB], sv.g, sv.s, sv.gs, N, C, HW, st));
+    } else {
+      DCPT_TRY(sca_fwd_launch(sv.pool, P[P_SCAW], P[P_SCAB], sv.s, N, C, HW, st));
+      DCPT_TRY(scale_rows_launch(sv.g, sv.s, sv.gs, N, HW, C, st));
+    }
   }
   // conv3, y = inp + x*beta
   {
