@@ -117,7 +117,7 @@ def main():
         F.l1_loss(rnet(xr), tr).backward()
     ms = timeit(r_step, max(3, args.iters // 2))
     res["restormer_train_step_b4_128"] = {"ms": round(ms, 3), "MPix/s": round(4 * 128 * 128 / ms / 1e3, 3),
-                                          "note": "eager launches (the Restormer training path is not CUDA-graphed yet)"}
+                                          "note": "public API (autograd Function), forward-with-save and backward replayed from CUDA graphs"}
     # DCPT pretrain step with the Restormer backbone (hook_names: decoder -> decoder_level{3,2,1}.body), 128 x 128, batch 4
     d = rcfg["dim"]
     rhead = build_network(dict(type="PromptIR_NoImg_DC", feature_dims=[2 * d, 2 * d, 4 * d], num_res_blocks=2, num_classes=5)).to(dev)
@@ -137,7 +137,7 @@ def main():
         r_hooked.clear()
     ms = timeit(r_dcpt_step, max(3, args.iters // 2))
     res["restormer_dcpt_pretrain_step_b4_128"] = {"ms": round(ms, 3), "MPix/s": round(4 * 128 * 128 / ms / 1e3, 3),
-                                                  "note": "2 Restormer forwards (one hooked) + classifier head + one backward, eager launches"}
+                                                  "note": "2 Restormer forwards (one hooked) + classifier head + one backward; backbone passes replayed from CUDA graphs"}
     for h in rhooks:
         h.remove()
     print(json.dumps(res, indent=1))
