@@ -55,6 +55,7 @@ struct EpiParams {
   int ld_ln;
   float* ln_stats;
   float ln_eps;
+  int ln_nocenter;  // 1: (v * rstd) * ln_w, rstd still from the variance about the mean, ln_b may be NULL (Restormer's BiasFree_LayerNorm, restormer_arch.py:26-40)
   // Fused LayerNorm BACKWARD (STORE, TMA-tiled epilogue, N <= 512; selected by lnb_x != nullptr): the accumulator is
   // dn = d(loss)/d(LN output) (a dgrad GEMM: conv4's or conv1's), and the epilogue turns it into the gradient of the LN INPUT
   // with the reference's hand-written backward (nafnet_arch.py:38-53):  g = dn * w,  xhat = (x - mean) * rstd,

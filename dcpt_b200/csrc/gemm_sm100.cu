@@ -917,6 +917,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float dm = pb.y - mean_a;
               const float var = ((m2_a + pb.z) + dm * dm * (na * pb.x / nt)) / nt;
               const float rstd = 1.f / sqrtf(var + ep.ln_eps);
+              const float mu = ep.ln_nocenter ? 0.f : mean;  // Restormer's BiasFree LayerNorm divides the un-centred row by sqrt(var + eps)
               if (chalf == 0 && m0 + lane < M) *reinterpret_cast<float2*>(ep.ln_stats + (size_t)(m0 + lane) * 2) = make_float2(mean, rstd);
               if (lane == 0) bulk_wait_read<0>();  // pass 1's stores have drained the staging buffers pass 2 re-partitions
               __syncwarp();
@@ -950,13 +951,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                       float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), bv = wv;
                       if (col < N) {
                         wv = __ldg(reinterpret_cast<const float4*>(ep.ln_w + col));
-                        bv = __ldg(reinterpret_cast<const float4*>(ep.ln_b + col));
+                        if (ep.ln_b) bv = __ldg(reinterpret_cast<const float4*>(ep.ln_b + col));
                       }
                       const float* src = j < 4 ? &va[8 * j + k] : &vb[8 * (j - 4) + k];
-                      o[k] = (src[0] - mean) * rstd * wv.x + bv.x;
-                      o[k + 1] = (src[1] - mean) * rstd * wv.y + bv.y;
-                      o[k + 2] = (src[2] - mean) * rstd * wv.z + bv.z;
-                      o[k + 3] = (src[3] - mean) * rstd * wv.w + bv.w;
+                      o[k] = (src[0] - mu) * rstd * wv.x + bv.x;
+                      o[k + 1] = (src[1] - mu) * rstd * wv.y + bv.y;
+                      o[k + 2] = (src[2] - mu) * rstd * wv.z + bv.z;
+                      o[k + 3] = (src[3] - mu) * rstd * wv.w + bv.w;
                     }
                     pk[j] = pack8(o);
                   }
@@ -1291,7 +1292,8 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     }
     if (g.ep.gaux) DCPT_TRY(make_tmap_epi(&em.o2, g.ep.gaux, g.M, g.N, g.ep.ldgaux, 2));
     if (g.ep.ln_out) {
-      DCPT_CHECK_ARG(g.ep.Cseg == 0 && !g.ep.gaux && g.N <= 2 * BN && g.ep.ln_w && g.ep.ln_b && g.ep.ln_stats && g.m_per_batch == 0 &&
+      // (per-image B operands are fine: a 128-row slab never straddles two images, m_per_batch % 128 == 0)
+      DCPT_CHECK_ARG(g.ep.Cseg == 0 && !g.ep.gaux && g.N <= 2 * BN && g.ep.ln_w && g.ep.ln_stats &&
                          ((reinterpret_cast<uintptr_t>(g.ep.ln_w) | reinterpret_cast<uintptr_t>(g.ep.ln_b)) & 15) == 0,
                      DCPT_E_ARG, "gemm: fused LayerNorm needs a plain STORE epilogue with N <= %d and 16-byte aligned ln_w / ln_b (N=%d)",
                      2 * BN, g.N);

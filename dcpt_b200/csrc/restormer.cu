@@ -420,7 +420,7 @@ struct BlkSaved : BlkBufs {
     n1 = a.take<bf16>(M * d); qkv = a.take<bf16>(M * 3 * d); qkvd = a.take<bf16>(M * 3 * d);
     n2 = a.take<bf16>(M * d); u = a.take<bf16>(M * 2 * b.hidp); g = a.take<bf16>(M * b.hidp);
     weff = a.take<bf16>((size_t)N * d * d); weffT = a.take<bf16>((size_t)N * d * d);
-    G = a.take<float>((size_t)N * d * d); sq = a.take<float>((size_t)N * 2 * d);
+    sq = a.take<float>((size_t)N * 2 * d); G = a.take<float>((size_t)N * d * d);  // neighbours, sq first: one memset (block_fwd)
     x2 = a.take<float>(M * d); stats1 = a.take<float>(M * 2); stats2 = a.take<float>(M * 2);
   }
 };
@@ -470,9 +470,10 @@ struct NetPacked {
 struct NetWork {
   float *e[4], *t[4], *d1, *t1;  // residual stream: encoder level outputs (also decoder levels 3, 2), temporaries
   bf16 *n, *a, *b, *xm;
-  float *conv, *G, *sq;
+  float *conv, *G, *sq, *stats;
   bf16* weff;
   NetWork(const dcpt_restormer_plan* p, Arena& ar, int N, int H, int W) {
+    stats = ar.take<float>((size_t)N * H * W * 2);
     size_t maxn = 0, maxa = 0, maxb = 0, maxconv = 0, maxg = 0, maxsq = 0;
     int d = p->dim, h = H, w = W;
     for (int l = 0; l < 4; ++l) {
@@ -494,7 +495,7 @@ struct NetWork {
     d1 = ar.take<float>(M0 * 2 * p->dim);
     t1 = ar.take<float>(M0 * 2 * p->dim);
     n = ar.take<bf16>(maxn); a = ar.take<bf16>(maxa); b = ar.take<bf16>(maxb); xm = ar.take<bf16>(maxn);
-    conv = ar.take<float>(maxconv); G = ar.take<float>(maxg); sq = ar.take<float>(maxsq);
+    conv = ar.take<float>(maxconv); sq = ar.take<float>(maxsq); G = ar.take<float>(maxg);
     weff = ar.take<bf16>(maxg);
   }
 };
@@ -532,12 +533,35 @@ int pix_gemm_per_image(const bf16* A, int O, int lda, const bf16* B, int I, int 
 }
 
 // out[n] = A[n] * Bm[n]^T (+ resid) with a per-image [Nout, K] matrix Bm[n]; A rows [N*HW, lda]
+// LayerNorm of a GEMM's output rows fused into its epilogue (gemm.cuh: ln_*): the consumer's norm, written as the 16-bit operand
+// `n` plus (mean, rstd) `stats`; `w == nullptr` = not fused.  center = 0: BiasFree_LayerNorm (restormer_arch.py:26-40).
+struct LnEpi {
+  const float *w = nullptr, *b = nullptr;
+  bf16* n = nullptr;
+  float* stats = nullptr;
+  int center = 1;
+};
+bool ln_fuse_r(int d) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DCPT_LN_FUSE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0 && gemm_ln_fusable(d);
+}
+void set_ln(GemmArgs& g, const LnEpi* ln, int d, size_t row0 = 0) {
+  if (!ln || !ln->w) return;
+  g.ep.ln_w = ln->w; g.ep.ln_b = ln->center ? ln->b : nullptr; g.ep.ln_out = ln->n + row0 * d; g.ep.ld_ln = d;
+  g.ep.ln_stats = ln->stats + row0 * 2; g.ep.ln_eps = 1e-6f; g.ep.ln_nocenter = ln->center ? 0 : 1;
+}
+
 int gemm_per_image(const bf16* A, int lda, const bf16* Bm, int Nout, int K, float* out_f32, bf16* out_bf16, int ldo, const float* resid,
-                   int ldr, int N, int HW, cudaStream_t st) {
+                   int ldr, int N, int HW, cudaStream_t st, const LnEpi* ln = nullptr) {
   if (N > 1 && HW % 128 == 0 && !getenv("DCPT_RESTORMER_NO_BATCH")) {
     GemmArgs g = make_gemm_args(N * HW, Nout, K, A, lda, Bm, K, EPI_STORE);
     g.m_per_batch = HW; g.b_rows_per_batch = Nout;
     g.ep.out_f32 = out_f32; g.ep.out_bf16 = out_bf16; g.ep.ldo = ldo; g.ep.resid = resid; g.ep.ldr = ldr;
+    set_ln(g, ln, Nout);
     return gemm_launch(g, st);
   }
   for (int n = 0; n < N; ++n) {
@@ -545,28 +569,43 @@ int gemm_per_image(const bf16* A, int lda, const bf16* Bm, int Nout, int K, floa
     GemmArgs g = make_gemm_args(HW, Nout, K, A + r0 * lda, lda, Bm + (size_t)n * Nout * K, K, EPI_STORE);
     g.ep.out_f32 = out_f32 ? out_f32 + r0 * ldo : nullptr; g.ep.out_bf16 = out_bf16 ? out_bf16 + r0 * ldo : nullptr; g.ep.ldo = ldo;
     g.ep.resid = resid ? resid + r0 * ldr : nullptr; g.ep.ldr = ldr;
+    set_ln(g, ln, Nout, r0);
     DCPT_TRY(gemm_launch(g, st));
   }
   return 0;
 }
 
 // TransformerBlock forward (restormer_arch.py:156-159): xout = x2 + GDFN(LN(x2)), x2 = x + MDTA(LN(x)).  x == xout is allowed.
+// ln1_done: the producer of x already wrote bf.n1 / bf.stats1 (fused epilogue); next: the norm1 of the block that consumes xout.
 int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, const float* const* P, const BlkPacked& pk, const float* x,
-              float* xout, const BlkBufs& bf, int N, int H, int W, cudaStream_t st) {
+              float* xout, const BlkBufs& bf, int N, int H, int W, cudaStream_t st, bool ln1_done = false, const LnEpi* next = nullptr) {
   const int d = b.d, HW = H * W, M = N * HW;
   const BlkIdx ix = blk_idx(p, b.pidx);
   constexpr float eps = 1e-6f;
   float* x2 = bf.x2;
+  const bool fuse = ln_fuse_r(d) && bf.stats2 != nullptr;
   // ---- x2 = x + MDTA(LN(x)) ----
-  DCPT_TRY(ln_fwd_launch(x, P[ix.n1w], ix.n1b >= 0 ? P[ix.n1b] : nullptr, bf.n1, bf.stats1, M, d, eps, st, p->ln_bias));
+  if (!ln1_done) DCPT_TRY(ln_fwd_launch(x, P[ix.n1w], ix.n1b >= 0 ? P[ix.n1b] : nullptr, bf.n1, bf.stats1, M, d, eps, st, p->ln_bias));
   {
     GemmArgs g = make_gemm_args(M, 3 * d, d, bf.n1, d, pk.wqkv, d, EPI_STORE);
     g.ep.out_bf16 = bf.qkv; g.ep.ldo = 3 * d;
     DCPT_TRY(gemm_launch(g, st));
   }
-  DCPT_CUDA(cudaMemsetAsync(bf.sq, 0, (size_t)N * 2 * d * sizeof(float), st));
+  {
+    // the two accumulators (row norms, then Gram matrices) are neighbours in every arena: one memset node over both (the gap
+    // between them is the unused tail of the row-norm buffer at narrower levels, a few KB)
+    const char* sq_b = reinterpret_cast<const char*>(bf.sq);
+    const char* sq_end = reinterpret_cast<const char*>(bf.sq + (size_t)N * 2 * d);
+    const char* g_b = reinterpret_cast<const char*>(bf.G);
+    const char* g_end = reinterpret_cast<const char*>(bf.G + (size_t)N * d * d);
+    if (g_b >= sq_end && g_b - sq_end <= 128 * 1024) {
+      DCPT_CUDA(cudaMemsetAsync(bf.sq, 0, (size_t)(g_end - sq_b), st));
+    } else {
+      DCPT_CUDA(cudaMemsetAsync(bf.sq, 0, (size_t)N * 2 * d * sizeof(float), st));
+      DCPT_CUDA(cudaMemsetAsync(bf.G, 0, (size_t)N * d * d * sizeof(float), st));
+    }
+  }
   DCPT_TRY(dwconv3_fwd_launch(bf.qkv, P[ix.qkv_dw], bf.qkvd, bf.sq, 2 * d, N, H, W, 3 * d, st));
-  DCPT_CUDA(cudaMemsetAsync(bf.G, 0, (size_t)N * d * d * sizeof(float), st));
   DCPT_TRY(pix_gemm_per_image(bf.qkvd, d, 3 * d, bf.qkvd + d, d, 3 * d, bf.G, N, HW, st));  // G[n] = q^T k over the pixels of image n
   {
     const int c = d / b.heads;
@@ -577,10 +616,12 @@ int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
     mdta_weff_kernel<<<dim3(b.heads, N), 256, smem, st>>>(bf.G, bf.sq, P[ix.temp], P[ix.pout], bf.weff, bf.weffT, d, b.heads, p->attn_softmax);
     DCPT_LAUNCH_CHECK();
   }
-  // x2 = x + v * W_eff[image]^T
-  DCPT_TRY(gemm_per_image(bf.qkvd + 2 * d, 3 * d, bf.weff, d, d, x2, nullptr, d, x, d, N, HW, st));
+  // x2 = x + v * W_eff[image]^T, norm2 of the result in the same epilogue
+  LnEpi ln2;
+  if (fuse) { ln2.w = P[ix.n2w]; ln2.b = ix.n2b >= 0 ? P[ix.n2b] : nullptr; ln2.n = bf.n2; ln2.stats = bf.stats2; ln2.center = p->ln_bias; }
+  DCPT_TRY(gemm_per_image(bf.qkvd + 2 * d, 3 * d, bf.weff, d, d, x2, nullptr, d, x, d, N, HW, st, &ln2));
   // ---- xout = x2 + GDFN(LN(x2)) ----
-  DCPT_TRY(ln_fwd_launch(x2, P[ix.n2w], ix.n2b >= 0 ? P[ix.n2b] : nullptr, bf.n2, bf.stats2, M, d, eps, st, p->ln_bias));
+  if (!fuse) DCPT_TRY(ln_fwd_launch(x2, P[ix.n2w], ix.n2b >= 0 ? P[ix.n2b] : nullptr, bf.n2, bf.stats2, M, d, eps, st, p->ln_bias));
   {
     GemmArgs g = make_gemm_args(M, 2 * b.hidp, d, bf.n2, d, pk.wpin, d, EPI_STORE);
     g.ep.out_bf16 = bf.u; g.ep.ldo = 2 * b.hidp;
@@ -590,16 +631,27 @@ int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
   {
     GemmArgs g = make_gemm_args(M, d, b.hidp, bf.g, b.hidp, pk.wpout, b.hidp, EPI_STORE);
     g.ep.out_f32 = xout; g.ep.ldo = d; g.ep.resid = x2; g.ep.ldr = d;
+    set_ln(g, next, d);  // the next block's norm1
     DCPT_TRY(gemm_launch(g, st));
   }
   return 0;
+}
+
+// norm1 of block j + 1 of a stage, to be fused into block j's last GEMM (nullptr-w when there is no next block / not fusable)
+LnEpi next_ln(const dcpt_restormer_plan* p, int s, size_t j, const float* const* P, bf16* n, float* stats) {
+  LnEpi e;
+  if (j + 1 < p->stage[s].size() && ln_fuse_r(p->stage[s][j].d) && stats != nullptr) {
+    const BlkIdx ix = blk_idx(p, p->stage[s][j + 1].pidx);
+    e.w = P[ix.n1w]; e.b = ix.n1b >= 0 ? P[ix.n1b] : nullptr; e.n = n; e.stats = stats; e.center = p->ln_bias;
+  }
+  return e;
 }
 
 // inference: every block of the network shares one set of scratch buffers
 BlkBufs scratch_bufs(const NetWork& ws, float* tmp) {
   BlkBufs bf;
   bf.n1 = bf.n2 = ws.n; bf.qkv = bf.u = ws.a; bf.qkvd = bf.g = ws.b; bf.weff = ws.weff; bf.weffT = nullptr;
-  bf.G = ws.G; bf.sq = ws.sq; bf.x2 = tmp; bf.stats1 = bf.stats2 = nullptr;
+  bf.G = ws.G; bf.sq = ws.sq; bf.x2 = tmp; bf.stats1 = bf.stats2 = ws.stats;  // (the fused LayerNorm epilogue always writes them)
   return bf;
 }
 
@@ -671,7 +723,12 @@ int block_bwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
 int stage_fwd(const dcpt_restormer_plan* p, int s, const float* const* P, const NetPacked& pk, float* x, float* tmp, const NetWork& ws,
               int N, int H, int W, cudaStream_t st) {
   const BlkBufs bf = scratch_bufs(ws, tmp);
-  for (size_t j = 0; j < p->stage[s].size(); ++j) DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, x, bf, N, H, W, st));
+  bool done = false;
+  for (size_t j = 0; j < p->stage[s].size(); ++j) {
+    const LnEpi nx = next_ln(p, s, j, P, bf.n1, bf.stats1);
+    DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, x, bf, N, H, W, st, done, &nx));
+    done = nx.w != nullptr;
+  }
   return 0;
 }
 
@@ -930,8 +987,12 @@ int stage_fwd_train(const dcpt_restormer_plan* p, int s, const float* const* P, 
                     int H, int W, cudaStream_t st) {
   DCPT_CHECK_ARG(!p->stage[s].empty(), DCPT_E_UNSUPPORTED, "restormer training: stage %d has no blocks", s);
   const float* x = xin;
+  bool done = false;
   for (size_t j = 0; j < p->stage[s].size(); ++j) {
-    DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, sv.xout[s][j], sv.sv[s][j], N, H, W, st));
+    LnEpi nx;
+    if (j + 1 < p->stage[s].size()) nx = next_ln(p, s, j, P, sv.sv[s][j + 1].n1, sv.sv[s][j + 1].stats1);  // the next block's saved tensors
+    DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, sv.xout[s][j], sv.sv[s][j], N, H, W, st, done, &nx));
+    done = nx.w != nullptr;
     x = sv.xout[s][j];
   }
   return 0;
@@ -1315,7 +1376,7 @@ struct PNetPacked : NetPacked {
 };
 
 struct PNetWork {
-  float *e[4], *dx[3], *cat[3], *rx, *tmp, *conv, *G, *sq, *emb, *pw, *mix;
+  float *e[4], *dx[3], *cat[3], *rx, *tmp, *conv, *G, *sq, *emb, *pw, *mix, *stats;
   bf16 *n, *a, *b, *xm, *weff, *pint;
   PNetWork(const dcpt_restormer_plan* p, Arena& ar, int N, int H, int W) {
     const int dim = p->dim;
@@ -1339,7 +1400,7 @@ struct PNetWork {
     tmp = ar.take<float>(maxx);
     conv = ar.take<float>(std::max(std::max(M[3] * 8 * dim, M[2] * 8 * dim), std::max(M[1] * 4 * dim, M[0] * (size_t)(dim / 2))));
     n = ar.take<bf16>(maxn); a = ar.take<bf16>(maxa); b = ar.take<bf16>(maxb); xm = ar.take<bf16>(maxx);
-    G = ar.take<float>(maxg); sq = ar.take<float>(maxsq); weff = ar.take<bf16>(maxg);
+    sq = ar.take<float>(maxsq); G = ar.take<float>(maxg); weff = ar.take<bf16>(maxg);
     emb = ar.take<float>((size_t)N * 8 * dim); pw = ar.take<float>((size_t)N * 8);
     size_t maxmix = 0, maxpint = 0;
     for (int i = 0; i < 3; ++i) {
@@ -1348,11 +1409,12 @@ struct PNetWork {
     }
     mix = ar.take<float>(maxmix);
     pint = ar.take<bf16>(maxpint);
+    stats = ar.take<float>(M[0] * 2);
   }
   BlkBufs bufs() const {
     BlkBufs bf;
     bf.n1 = bf.n2 = n; bf.qkv = bf.u = a; bf.qkvd = bf.g = b; bf.weff = weff; bf.weffT = nullptr;
-    bf.G = G; bf.sq = sq; bf.x2 = tmp; bf.stats1 = bf.stats2 = nullptr;
+    bf.G = G; bf.sq = sq; bf.x2 = tmp; bf.stats1 = bf.stats2 = stats;
     return bf;
   }
 };
@@ -1360,7 +1422,12 @@ struct PNetWork {
 int pstage(const dcpt_restormer_plan* p, int s, const float* const* P, const PNetPacked& pk, float* x, const PNetWork& ws, int N, int H,
            int W, cudaStream_t st) {
   const BlkBufs bf = ws.bufs();
-  for (size_t j = 0; j < p->stage[s].size(); ++j) DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, x, bf, N, H, W, st));
+  bool done = false;
+  for (size_t j = 0; j < p->stage[s].size(); ++j) {
+    const LnEpi nx = next_ln(p, s, j, P, bf.n1, bf.stats1);
+    DCPT_TRY(block_fwd(p, p->stage[s][j], P, pk.blk[s][j], x, x, bf, N, H, W, st, done, &nx));
+    done = nx.w != nullptr;
+  }
   return 0;
 }
 
