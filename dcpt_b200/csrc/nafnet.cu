@@ -717,7 +717,7 @@ int dcpt_gemm_ex(const dcpt_gemm_desc* d, int impl, dcpt_stream_t stream) {
   g.ep.aux = static_cast<const bf16*>(d->aux_bf16); g.ep.ldaux = d->ldaux;
   g.ep.C = d->C; g.ep.H = d->H; g.ep.W = d->W; g.ep.Cseg = d->Cseg;
   g.ep.ln_w = d->ln_weight; g.ep.ln_b = d->ln_bias; g.ep.ln_out = static_cast<bf16*>(d->ln_out); g.ep.ld_ln = d->ld_ln;
-  g.ep.ln_stats = d->ln_stats; g.ep.ln_eps = d->ln_eps;
+  g.ep.ln_stats = d->ln_stats; g.ep.ln_eps = d->ln_eps; g.ep.ln_nocenter = d->ln_nocenter;
   g.ep.lnb_x = d->lnb_x; g.ep.ld_lnb = d->ld_lnb; g.ep.lnb_stats = d->lnb_stats; g.ep.lnb_w = d->lnb_weight; g.ep.lnb_dres = d->lnb_dres;
   g.ep.lnb_dw = d->lnb_dweight; g.ep.lnb_db = d->lnb_dbias; g.ep.lnb_cs = d->lnb_colsum;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

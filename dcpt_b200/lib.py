@@ -28,7 +28,8 @@ class GemmDesc(C.Structure):
                 ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p), ("ln_out", C.c_void_p), ("ld_ln", C.c_int),
                 ("ln_stats", C.c_void_p), ("ln_eps", C.c_float),
                 ("lnb_x", C.c_void_p), ("ld_lnb", C.c_int), ("lnb_stats", C.c_void_p), ("lnb_weight", C.c_void_p),
-                ("lnb_dres", C.c_void_p), ("lnb_dweight", C.c_void_p), ("lnb_dbias", C.c_void_p), ("lnb_colsum", C.c_void_p)]
+                ("lnb_dres", C.c_void_p), ("lnb_dweight", C.c_void_p), ("lnb_dbias", C.c_void_p), ("lnb_colsum", C.c_void_p),
+                ("ln_nocenter", C.c_int)]
 
 
 _VP, _I, _F, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong

@@ -114,6 +114,9 @@ typedef struct dcpt_gemm_desc {
   const float* lnb_x; int ld_lnb;
   const float* lnb_stats; const float* lnb_weight; const float* lnb_dres;
   float* lnb_dweight; float* lnb_dbias; float* lnb_colsum;
+  /* with ln_out: 1 = Restormer's BiasFree_LayerNorm (restormer_arch.py:26-40): ln_out = bf16(v * rstd * ln_weight), rstd still from
+   * the variance about the mean, ln_bias may be NULL; 0 = the centred form above. */
+  int ln_nocenter;
 } dcpt_gemm_desc;
 int dcpt_gemm_ex(const dcpt_gemm_desc* desc, int impl, dcpt_stream_t stream);
 

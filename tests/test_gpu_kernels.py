@@ -101,6 +101,34 @@ def test_gemm_store_fused_layernorm(ops, M, N, K, mirror):
     assert (ln.float() - n_ref.float()).abs().max() <= 2 ** -7 * ref_ln.abs().max()
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 48, 48), (4096, 96, 96), (260, 192, 192), (2048, 384, 384)])
+def test_gemm_store_fused_biasfree_layernorm(ops, M, N, K):
+    """The BiasFree form of the fused LayerNorm epilogue (Restormer's BiasFree_LayerNorm, restormer_arch.py:26-40: x / sqrt(var + eps)
+    * weight, var about the mean, no centring, no bias) at Restormer's widths.  (The per-image-B GEMM it rides on in the network
+    is exercised by the TransformerBlock goldens in tests/test_gpu_restormer.py.)"""
+    from dcpt_b200.lib import GemmDesc
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = bf(torch.randn(M, K, device="cuda", generator=g))
+    B = bf(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    resid = torch.randn(M, N, device="cuda", generator=g) + 0.5
+    lw = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ln = torch.full((M, N), float("nan"), device="cuda", dtype=OPD())
+    stats = torch.full((M, 2), float("nan"), device="cuda")
+    d = GemmDesc()
+    for k, v in dict(M=M, N=N, K=K, A=A, lda=K, B=B, ldb=K, splits=1, epilogue=0, out_f32=out, ldo=N, resid=resid, ldr=N, ln_weight=lw,
+                     ln_out=ln, ld_ln=N, ln_stats=stats, ln_eps=1e-6, ln_nocenter=1).items():
+        setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+    ops.gemm_ex(d)
+    ref = A.float() @ B.float().t() + resid
+    assert rel(out, ref) < 2e-5
+    x = out.double()
+    mu = x.mean(1)
+    rstd = 1.0 / ((x - mu[:, None]).pow(2).mean(1) + 1e-6).sqrt()
+    assert rel(stats[:, 0], mu) < 1e-5 and rel(stats[:, 1], rstd) < 1e-5
+    assert rel(ln.float(), x * rstd[:, None] * lw.double()) < 4e-3
+
+
 @pytest.mark.parametrize("M,N,K,dres,mirror", [(1000, 512, 1024, True, True), (16384, 512, 1024, True, True), (4099, 256, 512, True, False),
                                                 (33000, 128, 256, False, True), (70000, 64, 128, True, True), (130, 72, 40, True, True),
                                                 (300, 24, 16, False, False), (2048, 384, 128, True, True)])
