@@ -283,7 +283,8 @@ template <int MODE>
 __global__ void __launch_bounds__(NWARP * 32)
 dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmD, const float* __restrict__ s_sca,
                     const float* __restrict__ t_sca, const float* __restrict__ w2, const float* __restrict__ b2,
-                    bf16* __restrict__ du2, float* __restrict__ dw2, float* __restrict__ db2, int N, int H, int W, int C) {
+                    bf16* __restrict__ du2, float* __restrict__ dw2, float* __restrict__ db2, int N, int H, int W, int C,
+                    const float* __restrict__ ds_sca = nullptr, const float* __restrict__ w_sca = nullptr, float inv_hw = 0.f) {
   pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -325,6 +326,8 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
   };
   if (threadIdx.x == 0 && T.t0 < T.t1) issue(T.t0, 0);
   int it = 0;
+  int t_n = -1;            // image whose SCA shift t_cur belongs to (MODE 0, in-kernel mat-vec)
+  float2 t_cur = zero2;
   for (int t = T.t0; t < T.t1; ++t, ++it) {
     const int s = it & 1;
     if (threadIdx.x == 0 && t + 1 < T.t1) issue(t + 1, s ^ 1);
@@ -333,7 +336,47 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
     float2 sv = make_float2(1.f, 1.f), tv = zero2;
     if constexpr (MODE == 0) {
       sv = make_float2(__ldg(s_sca + (size_t)n * C + ca), __ldg(s_sca + (size_t)n * C + ca + 1));
-      tv = make_float2(__ldg(t_sca + (size_t)n * C + ca), __ldg(t_sca + (size_t)n * C + ca + 1));
+      if (t_sca) {
+        tv = make_float2(__ldg(t_sca + (size_t)n * C + ca), __ldg(t_sca + (size_t)n * C + ca + 1));
+      } else {
+        // SCA backward folded in (nafnet_arch.py:173 backward: the pooled branch hands every pixel of image n the same shift
+        // t[n][c] = (1/HW) sum_co W_sca[co][c] ds[n][co]): the CTA needs it for its 64 channels only, once per image it visits
+        // (1-2 per launch), and the first tile's TMA is already in flight.  Warps split the rows of W_sca, a lane owns its
+        // two channels' columns; CTA-uniform branch.
+        if (n != t_n) {
+          float2 a4[4] = {zero2, zero2, zero2, zero2};
+          const float* dsn = ds_sca + (size_t)n * C;
+          int co = warp;
+          for (; co + 3 * NWARP < C; co += 4 * NWARP) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 wv = __ldg(reinterpret_cast<const float2*>(w_sca + (size_t)(co + NWARP * k) * C + ca));
+              const float d = __ldg(dsn + co + NWARP * k);
+              a4[k].x = fmaf(wv.x, d, a4[k].x);
+              a4[k].y = fmaf(wv.y, d, a4[k].y);
+            }
+          }
+          for (; co < C; co += NWARP) {
+            const float2 wv = __ldg(reinterpret_cast<const float2*>(w_sca + (size_t)co * C + ca));
+            const float d = __ldg(dsn + co);
+            a4[0].x = fmaf(wv.x, d, a4[0].x);
+            a4[0].y = fmaf(wv.y, d, a4[0].y);
+          }
+          s_red[warp * 32 + lane] = make_float2((a4[0].x + a4[1].x) + (a4[2].x + a4[3].x), (a4[0].y + a4[1].y) + (a4[2].y + a4[3].y));
+          __syncthreads();
+          float2 tot = zero2;
+#pragma unroll
+          for (int k = 0; k < NWARP; ++k) {
+            const float2 e = s_red[k * 32 + lane];
+            tot.x += e.x;
+            tot.y += e.y;
+          }
+          t_cur = make_float2(tot.x * inv_hw, tot.y * inv_hw);
+          t_n = n;
+          __syncthreads();  // s_red is free again (the end-of-kernel reduction also uses it)
+        }
+        tv = t_cur;
+      }
     }
     mbar_wait(&full[s], (it >> 1) & 1);
     const SBf sA = sbf(smem + (size_t)s * STAGE_BYTES) + lane * 2;
@@ -565,7 +608,9 @@ int dwconv3_fwd_launch(const bf16* x, const float* w, bf16* out, float* sumsq, i
 }
 
 int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const bf16* u, const float* w2, const float* b2,
-                        bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st) {
+                        bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st, const float* ds,
+                        const float* w_sca) {
+  DCPT_CHECK_ARG(t != nullptr || (ds != nullptr && w_sca != nullptr && C % 2 == 0), DCPT_E_ARG, "dwgate_bwd_a: need t, or ds + the SCA weight");
   DCPT_CHECK_ARG(C % 8 == 0 && C >= 8 && N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "dwgate_bwd_a: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
   CUtensorMap tmU, tmD;
   DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
@@ -573,7 +618,8 @@ int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const b
   const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
   DCPT_TRY(set_smem(dwgate_bwd_a_kernel<0>, smem));
   DCPT_PROF(dcpt_prof_tag2("dwgate_bwd_a", (long long)N * H * W, C), 80.0 * N * H * W * C, 10.0 * N * H * W * C, st);
-  DCPT_CUDA(dcpt_launch_pdl(dwgate_bwd_a_kernel<0>, pick_grid(N, H, W, C, 1), dim3(NWARP * 32), smem, st, tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C));
+  DCPT_CUDA(dcpt_launch_pdl(dwgate_bwd_a_kernel<0>, pick_grid(N, H, W, C, 1), dim3(NWARP * 32), smem, st, tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C, ds, w_sca,
+                            1.f / (float)(H * W)));
   DCPT_LAUNCH_CHECK();
   return 0;
 }

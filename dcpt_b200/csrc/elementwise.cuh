@@ -22,8 +22,11 @@ int dwgelu_fwd_launch(const bf16* u, const float* w2, bf16* g, int N, int H, int
 int dwconv3_fwd_launch(const bf16* x, const float* w, bf16* out, float* sumsq, int sq_ch, int N, int H, int W, int CH,
                        cudaStream_t st);
 // backward part a: dg = dgs*s + t; du2 = SimpleGate'(dg); dW2 += du2 (*) u; db2 += sum du2.
+// t = the SCA backward's per-image shift (sca_bwd_launch), or nullptr with ds [N, C] + the SCA weight [C, C]: the kernel then does
+// that transposed mat-vec itself for the channels it owns
 int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const bf16* u, const float* w2, const float* b2,
-                        bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st);
+                        bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st, const float* ds = nullptr,
+                        const float* w_sca = nullptr);
 int dwgelu_bwd_a_launch(const bf16* dg, const bf16* u, const float* w2, bf16* du2, float* dw2, int N, int H, int W, int C, cudaStream_t st);
 int dwconv3_wgrad_launch(const bf16* dy, const bf16* x, float* dw, int N, int H, int W, int CH, cudaStream_t st);
 // backward part b: du = dwconv^T(du2); colsum[c] += sum_px du.

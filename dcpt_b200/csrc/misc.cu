@@ -570,6 +570,7 @@ int sca_bwd_launch(const float* ds, const float* pool, const float* w, float* t,
     DCPT_PROF("sca_bwd_w", 2.0 * N * C * C, 8.0 * C * C, st_w);
     DCPT_CUDA(dcpt_launch_pdl(sca_bwd_w_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, st_w, ds, pool, dw, db, N, C, 1.f / (float)HW));
   }
+  if (t == nullptr) return 0;  // the gate backward computes its own shift (dwgate_bwd_a_launch with ds + the SCA weight)
   dim3 grid(ceil_div(C, 32), N);
   DCPT_PROF("sca_bwd_t", 2.0 * N * C * C, 4.0 * C * C, st);
   DCPT_CUDA(dcpt_launch_pdl(sca_bwd_t_kernel, grid, dim3(256), 0, st, ds, w, t, C, 1.f / (float)HW));

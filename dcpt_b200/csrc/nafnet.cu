@@ -390,9 +390,11 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   }
   // ---- SCA backward ----
   DCPT_TRY(fork_here(5));
-  DCPT_TRY(sca_bwd_launch(ds, sv.pool, P[P_SCAW], wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st, sw));
+  const bool t_folded = sca_fused();  // the transposed SCA mat-vec runs inside the gate backward (no sca_bwd_t launch on the chain)
+  DCPT_TRY(sca_bwd_launch(ds, sv.pool, P[P_SCAW], t_folded ? nullptr : wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st, sw));
   // ---- SimpleGate + depthwise conv backward ----
-  DCPT_TRY(dwgate_bwd_a_launch(wk.dgs, sv.s, wk.t, sv.u, P[P_C2W], P[P_C2B], wk.du2, G[P_C2W], G[P_C2B], N, H, W, C, st));
+  DCPT_TRY(dwgate_bwd_a_launch(wk.dgs, sv.s, t_folded ? nullptr : wk.t, sv.u, P[P_C2W], P[P_C2B], wk.du2, G[P_C2W], G[P_C2B], N, H, W, C, st,
+                               ds, P[P_SCAW]));
   DCPT_TRY(dwconv_bwd_data_launch(wk.du2, P[P_C2W], wk.du, G[P_C1B], N, H, W, 2 * C, st));
   // ---- conv1 ----
   DCPT_TRY(fork_here(3));
