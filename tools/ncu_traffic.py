@@ -4,7 +4,7 @@ bench line's `roofline.traffic` must be reproducible from the newest capture, by
     ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -o gpurun_out/<tag>/gemm_full python tools/gemm_bench.py --ncu
     python tools/ncu_traffic.py gpurun_out/<tag>/gemm_full.ncu-rep gpurun_out/gemm_bench_manifest.json [profiles/ncu_traffic.json]
 
-gemm_bench.py --ncu launches each shape exactly twice (one warm-up, one measured... see below) in manifest order; this script pairs the
+gemm_bench.py --ncu launches each shape ONCE (cold L2) in manifest order; this script pairs the
 capture's gemm_tc_kernel launches with the manifest and writes, per "<bench tag> <MxNxK>", dram__bytes_read.sum +
 dram__bytes_write.sum of the launch (plus duration, tensor-pipe and DRAM utilisation for the record)."""
 import csv
