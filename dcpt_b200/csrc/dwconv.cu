@@ -278,7 +278,9 @@ dwconv3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restr
 // dW2[c][tap] += du2[c] * u[px+tap][c];  db2[c] += du2[c].
 // MODE 0: NAFBlock (SimpleGate, SCA scale / shift s, t, bias).  MODE 1: Restormer GDFN (gelu(a) * b, no bias, dg = dgs;
 // restormer_arch.py:97-98).  MODE 2: plain depthwise conv weight gradient (Restormer qkv_dwconv, :110-118): tmD holds the
-// output gradient of all 2C channels, nothing is recomputed or stored, only dW2 is accumulated.
+// output gradient of all 2C channels, nothing is recomputed or stored, only dW2 (and db2) is accumulated.
+// MODE 3: MODE 0 without the weight / bias gradient (18 of the 36 FMA2 per pixel and 38 accumulator registers less): the
+// NAFBlock backward runs it on its critical chain and hands dW2 / db2 to a MODE 2 launch on the weight-gradient stream.
 template <int MODE>
 __global__ void __launch_bounds__(NWARP * 32)
 dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmD, const float* __restrict__ s_sca,
@@ -334,7 +336,7 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
     int n, h0, w0;
     T.decode(t, n, h0, w0);
     float2 sv = make_float2(1.f, 1.f), tv = zero2;
-    if constexpr (MODE == 0) {
+    if constexpr (MODE == 0 || MODE == 3) {
       sv = make_float2(__ldg(s_sca + (size_t)n * C + ca), __ldg(s_sca + (size_t)n * C + ca + 1));
       if (t_sca) {
         tv = make_float2(__ldg(t_sca + (size_t)n * C + ca), __ldg(t_sca + (size_t)n * C + ca + 1));
@@ -407,7 +409,7 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
         if (chan_ok && h < H && w0 + ox < W) {
           const float2 dgv = lds_bf2(sD + (warp * TW + ox) * 64);
           float2 da, db;
-          if constexpr (MODE == 0) {
+          if constexpr (MODE == 0 || MODE == 3) {
             const float2 dg = make_float2(fmaf(dgv.x, sv.x, tv.x), fmaf(dgv.y, sv.y, tv.y));
             da = make_float2(dg.x * b.x, dg.y * b.y);
             db = make_float2(dg.x * a.x, dg.y * a.y);
@@ -425,20 +427,23 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
             st_bf2(orow + (size_t)ox * C2 + ca, da);
             st_bf2(orow + (size_t)ox * C2 + cb, db);
           }
-          dbA.x += da.x; dbA.y += da.y;
-          dbB.x += db.x; dbB.y += db.y;
+          if constexpr (MODE != 3) {
+            dbA.x += da.x; dbA.y += da.y;
+            dbB.x += db.x; dbB.y += db.y;
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              fma2(gA[r * 3 + d], da, A[r][(x - 2 + d) % 3]);
-              fma2(gB[r * 3 + d], db, B[r][(x - 2 + d) % 3]);
-            }
+              for (int d = 0; d < 3; ++d) {
+                fma2(gA[r * 3 + d], da, A[r][(x - 2 + d) % 3]);
+                fma2(gB[r * 3 + d], db, B[r][(x - 2 + d) % 3]);
+              }
+          }
         }
       }
     }
     __syncthreads();
   }
+  if constexpr (MODE != 3) {
   // CTA reduction of the 20 x 64 channel sums, then one atomic per value
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -469,6 +474,7 @@ dwgate_bwd_a_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
       atomicAdd(db2 + c, v.x);
       atomicAdd(db2 + c + 1, v.y);
     }
+  }
   }
 }
 
@@ -616,6 +622,14 @@ int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const b
   DCPT_TRY(make_tmap_nhwc(&tmU, u, N, H, W, 2 * C, HWD, HH));
   DCPT_TRY(make_tmap_nhwc(&tmD, dgs, N, H, W, C, TW, TH));
   const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
+  if (dw2 == nullptr) {  // data path only (the caller takes dW2 / db2 from dwconv3_wgrad_launch on another stream)
+    DCPT_TRY(set_smem(dwgate_bwd_a_kernel<3>, smem));
+    DCPT_PROF(dcpt_prof_tag2("dwgate_bwd_a_data", (long long)N * H * W, C), 44.0 * N * H * W * C, 10.0 * N * H * W * C, st);
+    DCPT_CUDA(dcpt_launch_pdl(dwgate_bwd_a_kernel<3>, pick_grid(N, H, W, C, 1), dim3(NWARP * 32), smem, st, tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C,
+                              ds, w_sca, 1.f / (float)(H * W)));
+    DCPT_LAUNCH_CHECK();
+    return 0;
+  }
   DCPT_TRY(set_smem(dwgate_bwd_a_kernel<0>, smem));
   DCPT_PROF(dcpt_prof_tag2("dwgate_bwd_a", (long long)N * H * W, C), 80.0 * N * H * W * C, 10.0 * N * H * W * C, st);
   DCPT_CUDA(dcpt_launch_pdl(dwgate_bwd_a_kernel<0>, pick_grid(N, H, W, C, 1), dim3(NWARP * 32), smem, st, tmU, tmD, s, t, w2, b2, du2, dw2, db2, N, H, W, C, ds, w_sca,
@@ -639,7 +653,7 @@ int dwgelu_bwd_a_launch(const bf16* dg, const bf16* u, const float* w2, bf16* du
 }
 
 // Plain depthwise 3x3 weight gradient: dw[c][tap] += sum_px dy[px][c] * x[px + tap][c] for CH = 2 * Chalf channels.
-int dwconv3_wgrad_launch(const bf16* dy, const bf16* x, float* dw, int N, int H, int W, int CH, cudaStream_t st) {
+int dwconv3_wgrad_launch(const bf16* dy, const bf16* x, float* dw, int N, int H, int W, int CH, cudaStream_t st, float* db) {
   DCPT_CHECK_ARG(CH % 16 == 0 && CH >= 16 && N > 0 && H > 0 && W > 0, DCPT_E_SHAPE, "dwconv3_wgrad: CH=%d must be a multiple of 16", CH);
   const int C = CH / 2;
   CUtensorMap tmU, tmD;
@@ -648,7 +662,7 @@ int dwconv3_wgrad_launch(const bf16* dy, const bf16* x, float* dw, int N, int H,
   const size_t smem = 128 + (size_t)2 * (2 * BOX_BYTES + 2 * DG_BYTES) + (size_t)NWARP * 20 * 32 * sizeof(float2);
   DCPT_TRY(set_smem(dwgate_bwd_a_kernel<2>, smem));
   DCPT_PROF("dwconv3_wgrad", 36.0 * N * H * W * CH, 4.0 * N * H * W * CH, st);
-  dwgate_bwd_a_kernel<2><<<pick_grid(N, H, W, C, 1), NWARP * 32, smem, st>>>(tmU, tmD, nullptr, nullptr, dw, nullptr, nullptr, dw, nullptr, N, H, W, C);
+  dwgate_bwd_a_kernel<2><<<pick_grid(N, H, W, C, 1), NWARP * 32, smem, st>>>(tmU, tmD, nullptr, nullptr, dw, nullptr, nullptr, dw, db, N, H, W, C);
   DCPT_LAUNCH_CHECK();
   return 0;
 }

@@ -28,7 +28,7 @@ int dwgate_bwd_a_launch(const bf16* dgs, const float* s, const float* t, const b
                         bf16* du2, float* dw2, float* db2, int N, int H, int W, int C, cudaStream_t st, const float* ds = nullptr,
                         const float* w_sca = nullptr);
 int dwgelu_bwd_a_launch(const bf16* dg, const bf16* u, const float* w2, bf16* du2, float* dw2, int N, int H, int W, int C, cudaStream_t st);
-int dwconv3_wgrad_launch(const bf16* dy, const bf16* x, float* dw, int N, int H, int W, int CH, cudaStream_t st);
+int dwconv3_wgrad_launch(const bf16* dy, const bf16* x, float* dw, int N, int H, int W, int CH, cudaStream_t st, float* db = nullptr);
 // backward part b: du = dwconv^T(du2); colsum[c] += sum_px du.
 int dwconv_bwd_data_launch(const bf16* du2, const float* w2, bf16* du, float* colsum, int N, int H, int W, int C2,
                            cudaStream_t st);

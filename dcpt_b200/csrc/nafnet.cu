@@ -211,6 +211,19 @@ bool sca_fused() {
   return on != 0;
 }
 
+// DCPT_DWGATE_SPLIT=1: depthwise-conv weight gradient on the side stream instead of inside the gate backward.  OFF by default:
+// measured 22.01 vs 21.38 ms per step (r03f, same box) - the chain kernel gets faster (122 instead of 174 registers, half the
+// FMAs) but the extra pass over u and du2 (66 MB per C = 512 block) does not fit into the idle SM time the weight-gradient
+// stream lives on; that budget (~4.5 ms per step) is already spent by the wgrad GEMMs.
+bool dwgate_split() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DCPT_DWGATE_SPLIT");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0;
+}
+
 bool ln_fuse_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -393,11 +406,15 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   const bool t_folded = sca_fused();  // the transposed SCA mat-vec runs inside the gate backward (no sca_bwd_t launch on the chain)
   DCPT_TRY(sca_bwd_launch(ds, sv.pool, P[P_SCAW], t_folded ? nullptr : wk.t, G[P_SCAW], G[P_SCAB], N, C, HW, st, sw));
   // ---- SimpleGate + depthwise conv backward ----
-  DCPT_TRY(dwgate_bwd_a_launch(wk.dgs, sv.s, t_folded ? nullptr : wk.t, sv.u, P[P_C2W], P[P_C2B], wk.du2, G[P_C2W], G[P_C2B], N, H, W, C, st,
-                               ds, P[P_SCAW]));
+  // the depthwise conv's weight / bias gradient leaves the chain: the gate backward writes du2 only, and dW2 / db2 come from
+  // (du2, u) on the weight-gradient stream (below, after the next fork)
+  const bool dw_split = fork && dwgate_split();
+  DCPT_TRY(dwgate_bwd_a_launch(wk.dgs, sv.s, t_folded ? nullptr : wk.t, sv.u, P[P_C2W], P[P_C2B], wk.du2, dw_split ? nullptr : G[P_C2W],
+                               dw_split ? nullptr : G[P_C2B], N, H, W, C, st, ds, P[P_SCAW]));
   DCPT_TRY(dwconv_bwd_data_launch(wk.du2, P[P_C2W], wk.du, G[P_C1B], N, H, W, 2 * C, st));
   // ---- conv1 ----
   DCPT_TRY(fork_here(3));
+  if (dw_split) DCPT_TRY(dwconv3_wgrad_launch(wk.du2, sv.u, G[P_C2W], N, H, W, 2 * C, sw, G[P_C2B]));
   DCPT_TRY(wgrad_gemm(wk.du, 2 * C, sv.n1, C, G[P_C1W], M, sw));
   {
     GemmArgs g = gemm_args(M, C, 2 * C, wk.du, 2 * C, pk.w1t, 2 * C, EPI_STORE);
