@@ -276,7 +276,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         lc0 = lib.dcpt_launch_count()
-        with torch.cuda.graph(graph):
+        from dcpt_b200.nafnet import _capture_stream
+        with torch.cuda.graph(graph, stream=_capture_stream(dev)):     # high-priority capture stream (DCPT_GRAPH_PRIORITY=0: default)
             step(comm=False)
         launches_per_step = lib.dcpt_launch_count() - lc0    # kernel nodes of ours captured in the graph
         eager_step = step

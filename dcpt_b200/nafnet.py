@@ -318,7 +318,7 @@ def _graph_forward(eng, pv, inp, hook, want_feats, need_grad):
     if slot.fgraph is None:
         run()                           # eager once: lazy one-time initialisation inside the library must not be captured
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        with torch.cuda.graph(g, stream=_capture_stream(slot.inp.device), capture_error_mode="thread_local"):
             run()
         slot.fgraph = g
     else:
@@ -375,7 +375,7 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
     if mask not in slot.bgraphs:
         run()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        with torch.cuda.graph(g, stream=_capture_stream(slot.inp.device), capture_error_mode="thread_local"):
             run()
         slot.bgraphs[mask] = g
     else:
@@ -387,6 +387,22 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
         eng.grad_sync(slot.flat)            # data-parallel wrapper: ONE mean all-reduce of the flat gradient buffer
     flat = slot.flat.clone()            # autograd owns the returned gradients; the slot's buffer is rewritten next step
     return [flat[o:o + n].view(shp) for o, n, shp in slot.shapes]
+
+
+_CAPTURE_STREAMS = {}
+
+
+def _capture_stream(dev):
+    """Stream the forward / backward graphs are captured on: a HIGH-priority stream, so that the captured chain kernels outrank
+    the library's weight-gradient side stream (default priority - the lowest CUDA has) whenever both have thread blocks
+    pending; the side stream then only fills SM time the chain leaves idle (r03g, same box: 21.07-21.26 -> 20.91 ms per
+    step).  DCPT_GRAPH_PRIORITY=0 captures on torch's default capture stream."""
+    if os.getenv("DCPT_GRAPH_PRIORITY", "1") == "0":
+        return None
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=key, priority=-1)
+    return _CAPTURE_STREAMS[key]
 
 
 class _null_ctx:
