@@ -317,7 +317,8 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
 // the side stream is joined before the block returns, so the ABI contract ("everything is ordered on `stream`") holds.
 struct SideStream {
   cudaStream_t s = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 0-3, 5: forks; 4: join; 6, 7: lagged joins
+  bool pending[2] = {false, false};  // a lagged join event (ev[6 + parity]) has been recorded and not waited for yet
   bool ok = false, tried = false;
   // created on the first (eager, un-captured) use; owned by a plan (one per engine: two engines on two streams never share
   // events) or, for the plan-less block ABI, by the calling thread
@@ -341,9 +342,31 @@ SideStream& thread_side_stream() {
   return ss;
 }
 
+// Network backward: the side stream may lag ONE block behind the chain.  Consecutive blocks use two BlockWork arenas in turn
+// (parity), a block waits at its START for the side work of the block before last (the previous user of its arena) instead
+// of waiting at its END for its own - whose last wgrad GEMM was forked only one kernel earlier and, running at the lower
+// priority, is rarely done by then.  DCPT_SIDE_LAG=0: join at the end of every block.
+bool side_lag_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DCPT_SIDE_LAG");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+int side_join_all(SideStream& ss, cudaStream_t st) {
+  for (int k = 0; k < 2; ++k)
+    if (ss.pending[k]) {
+      DCPT_CUDA(cudaStreamWaitEvent(st, ss.ev[6 + k], 0));
+      ss.pending[k] = false;
+    }
+  return 0;
+}
+
 int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockSaved& sv, const float* x, const float* dout,
                       const bf16* doutT, const float* Sout, float* dx, bf16* dxT, float* Sx, float* const* G, const BlockWork& wk,
-                      int N, int H, int W, int C, cudaStream_t st, const BlockZeros* zeros = nullptr, SideStream* side = nullptr) {
+                      int N, int H, int W, int C, cudaStream_t st, const BlockZeros* zeros = nullptr, SideStream* side = nullptr,
+                      int lag_parity = -1) {
   const int HW = H * W, M = N * HW;
   const size_t cc = (size_t)C * C;
   float* const G5 = zeros ? zeros->G5 : wk.G;
@@ -354,6 +377,11 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
   ss.ensure();
   const bool fork = ss.ok && !g_dcpt_prof_on;   // per-kernel profiling keeps everything on one stream
   cudaStream_t sw = fork ? ss.s : st;           // stream of the weight-gradient work
+  const bool lag = fork && lag_parity >= 0;
+  if (lag && ss.pending[lag_parity]) {           // the side work that last read this arena (two blocks ago) must be done
+    DCPT_CUDA(cudaStreamWaitEvent(st, ss.ev[6 + lag_parity], 0));
+    ss.pending[lag_parity] = false;
+  }
   auto fork_here = [&](int i) -> int {          // side stream waits for everything issued on `st` so far
     if (fork) {
       DCPT_CUDA(cudaEventRecord(ss.ev[i], st));
@@ -428,7 +456,10 @@ int nafblock_bwd_impl(const float* const* P, const BlockPacked& pk, const BlockS
     DCPT_TRY(gemm_launch(g, st));
   }
   if (!fuse_lnb) DCPT_TRY(ln_bwd_launch(wk.dn, x, sv.stats1, P[P_N1W], wk.dy, dx, dxT, G[P_N1W], G[P_N1B], Sx, M, C, st));
-  if (fork) {  // join: the block's buffers (dx4, dyT, du, G, Sy) are reused by the next block
+  if (lag) {   // the block after next waits for this (it reuses this block's arena)
+    DCPT_CUDA(cudaEventRecord(ss.ev[6 + lag_parity], sw));
+    ss.pending[lag_parity] = true;
+  } else if (fork) {  // join: the block's buffers (dx4, dyT, du, G, Sy) are reused by the next block
     DCPT_CUDA(cudaEventRecord(ss.ev[4], sw));
     DCPT_CUDA(cudaStreamWaitEvent(st, ss.ev[4], 0));
   }
@@ -590,6 +621,7 @@ struct NetPacked {
 
 struct NetWork {
   char* blk_base;   // BlockWork arena (sized for the largest level)
+  char* blk_base2;  // second arena: consecutive blocks alternate, so the weight-gradient stream may lag one block behind
   size_t blk_bytes;
   float* dxa; float* dxb; bf16* dta; bf16* dtb; float* Sa; float* Sb;  // ping-pong gradient stream
   std::vector<float*> dskip;                                          // per encoder level
@@ -620,6 +652,7 @@ struct NetWork {
     }
     blk_bytes = max_blk;
     blk_base = a.take<char>(max_blk);
+    blk_base2 = a.take<char>(max_blk);
     dxa = a.take<float>(max_act); dxb = a.take<float>(max_act);
     dta = a.take<bf16>(max_act); dtb = a.take<bf16>(max_act);
     Sa = a.take<float>(maxC); Sb = a.take<float>(maxC);
@@ -1093,19 +1126,23 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     }
     have = true;
   }
+  p->side.pending[0] = p->side.pending[1] = false;
   // one memset for every block's accumulators (BlockZeros) and column-sum outputs
   DCPT_CUDA(cudaMemsetAsync(wk.zeros, 0, wk.zero_floats * sizeof(float), st));
   float* zcur = wk.zeros;
+  int blk_i = 0;
   auto block_bwd = [&](const dcpt_nafnet_plan::Blk& b, const BlockPacked& bpk, const BlockSaved& bsv, const float* x, int hh,
                        int ww) -> int {
     DCPT_CHECK_ARG(have, DCPT_E_ARG, "nafnet_bwd: no gradient reaches a block (dout and dfeats all NULL?)");
-    Arena a(wk.blk_base);
+    const int parity = side_lag_enabled() ? (blk_i++ & 1) : -1;
+    Arena a(parity == 1 ? wk.blk_base2 : wk.blk_base);
     BlockWork bw(a, N, hh, ww, b.C);
     const BlockZeros bz(zcur, N, b.C);
     zcur += BlockZeros::floats(N, b.C);
     NXT.s = zcur;  // this block's Sx (column sums of dx): its own pre-cleared slice, read by the next block / conv backward
     zcur += ((size_t)b.C + 63) / 64 * 64;
-    DCPT_TRY(nafblock_bwd_impl(P + b.pidx, bpk, bsv, x, CUR.f, CUR.t, CUR.s, NXT.f, NXT.t, NXT.s, G + b.pidx, bw, N, hh, ww, b.C, st, &bz, &p->side));
+    DCPT_TRY(nafblock_bwd_impl(P + b.pidx, bpk, bsv, x, CUR.f, CUR.t, CUR.s, NXT.f, NXT.t, NXT.s, G + b.pidx, bw, N, hh, ww, b.C, st, &bz, &p->side,
+                               parity));
     ci ^= 1;
     return 0;
   };
@@ -1175,6 +1212,7 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
       DCPT_TRY(block_bwd(p->enc_blks[i][j], pk.enc_pk[i][j], sv.enc_sv[i][j],
                          j > 0 ? sv.enc_out[i][j - 1] : (i > 0 ? sv.xd[i - 1] : sv.x0), h, w));
     if (i == ne - 1 && p->split_event) {  // deepest level done: its slice of the gradient buffer is final (see split_event)
+      DCPT_TRY(side_join_all(p->side, st));  // ... once the lagging weight-gradient work of its last blocks has landed
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
       DCPT_CUDA(cudaStreamIsCapturing(st, &cap));
       DCPT_CUDA(cudaEventRecordWithFlags(static_cast<cudaEvent_t>(p->split_event), st,
@@ -1188,6 +1226,7 @@ int dcpt_nafnet_bwd(const dcpt_nafnet_plan* p, const float* const* P, const void
   DCPT_TRY(wgrad_gemm(CUR.t, C, sv.P, 32, wk.G, N * h * w, st, 64));  // dWi = dX0^T * im2col(inp)
   DCPT_TRY(finish_w27_launch(wk.G, G[0], nullptr, nullptr, C, 0, st));
   DCPT_TRY(axpy_launch(G[1], CUR.s, C, st));
+  DCPT_TRY(side_join_all(p->side, st));  // everything is ordered on `stream` when the call returns
 #undef CUR
 #undef NXT
   return 0;
