@@ -253,7 +253,7 @@ def run_ours(args):
     comm_stream = None
     if world > 1 and os.getenv("DCPT_DP_OVERLAP", "1") != "0":
         eng.enable_grad_overlap(True)      # the backward records an event once ~90 % of the gradient bytes are final
-        comm_stream = torch.cuda.Stream()
+        comm_stream = torch.cuda.Stream(priority=-1 if os.getenv("DCPT_COMM_PRIORITY", "1") != "0" else 0)
 
     def exchange():
         allreduce_grads_overlapped_(eng, flat, comm_stream=comm_stream)   # the path's one exchange step (dcpt_b200/dist.py)

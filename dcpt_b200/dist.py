@@ -125,7 +125,9 @@ class FlatGradDataParallel(torch.nn.Module):
             from .lib import operand_dtype
             if operand_dtype() == torch.bfloat16 and get_dist_info()[1] > 1:
                 eng.enable_grad_overlap(True)
-                self._comm = torch.cuda.Stream()
+                # high priority (DCPT_COMM_PRIORITY=0: default): the captured backward runs on a high-priority stream too, and the
+                # few thread blocks NCCL needs must not wait behind the weight-gradient side stream's
+                self._comm = torch.cuda.Stream(priority=-1 if os.getenv("DCPT_COMM_PRIORITY", "1") != "0" else 0)
 
     def _sync(self, flat):
         if self._sync_enabled:
