@@ -652,15 +652,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int k = 0; k < 8; ++k) sgv[k] = a[k] * b[k];
               const uint32_t off = (uint32_t)(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
-              sts_u4(buf + off, pack8(a));
-              sts_u4(buf + 2048 + off, pack8(b));
+              if (ep.out_bf16) {  // x4 = [a | b] is only needed by the backward (inference passes NULL)
+                sts_u4(buf + off, pack8(a));
+                sts_u4(buf + 2048 + off, pack8(b));
+              }
               sts_u4(buf + 4096 + off, pack8(sgv));
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&em.o16, ebuf, j0, m0);
-              tma_store_2d(&em.o16, ebuf + 2048, ep.C + j0, m0);
+              if (ep.out_bf16) {
+                tma_store_2d(&em.o16, ebuf, j0, m0);
+                tma_store_2d(&em.o16, ebuf + 2048, ep.C + j0, m0);
+              }
               tma_store_2d(&em.o2, ebuf + 4096, j0, m0);
               bulk_commit();
             }
@@ -1306,7 +1310,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     DCPT_TRY(make_tmap_epi(&em.r32, g.ep.aux, g.M, 2 * g.ep.C, g.ep.ldaux, 2));
     DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, 2 * g.ep.C, g.ep.ldo, 2));
   } else if constexpr (EPI == EPI_GATE_TMA) {
-    DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, 2 * g.ep.C, g.ep.ldo, 2));
+    if (g.ep.out_bf16) DCPT_TRY(make_tmap_epi(&em.o16, g.ep.out_bf16, g.M, 2 * g.ep.C, g.ep.ldo, 2));
     DCPT_TRY(make_tmap_epi(&em.o2, g.ep.out2, g.M, g.ep.C, g.ep.ldo2, 2));
   } else if constexpr (EPI == EPI_LNBWD_TMA) {
     DCPT_CHECK_ARG(g.N <= 2 * BN && g.N <= 512 && g.ep.lnb_stats && g.ep.lnb_w && g.ep.lnb_dw && g.ep.lnb_db && (g.ep.out_f32 || g.ep.out_bf16) &&
@@ -1521,8 +1525,8 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     }
     case EPI_GATE: return launch_bn<EPI_GATE, false, false>(g, stream);
     case EPI_GATE_TMA:  // SimpleGate forward on 32-wide pair packing (PACK_PAIR32 weights / bias)
-      DCPT_CHECK_ARG(g.ep.C % 32 == 0 && g.N == 2 * g.ep.C && g.ep.bias && g.ep.out_bf16 && g.ep.out2, DCPT_E_ARG,
-                     "gemm: the 32-wide gate epilogue needs C %% 32 == 0, N = 2C, bias and both outputs (C=%d N=%d)", g.ep.C, g.N);
+      DCPT_CHECK_ARG(g.ep.C % 32 == 0 && g.N == 2 * g.ep.C && g.ep.bias && g.ep.out2, DCPT_E_ARG,
+                     "gemm: the 32-wide gate epilogue needs C %% 32 == 0, N = 2C, bias and the gated output (C=%d N=%d)", g.ep.C, g.N);
       return launch_bn<EPI_GATE_TMA, false, false>(g, stream);
     case EPI_GATE_BWD: {
       static const bool no_tma = getenv("DCPT_GEMM_NO_TMA_EPI") != nullptr;

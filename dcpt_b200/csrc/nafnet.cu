@@ -255,7 +255,7 @@ void set_ln_epilogue(GemmArgs& g, const LnFuse& f, int C) {
 // consumer of `out` (the following block's norm1), fused into conv5's epilogue when supported.
 int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float* x, float* out, bf16* out_bf16,
                       const BlockSaved& sv, int N, int H, int W, int C, cudaStream_t st, int tlc_kh = 0, int tlc_kw = 0,
-                      bool ln1_done = false, const LnFuse* next = nullptr, bool pool_zeroed = false) {
+                      bool ln1_done = false, const LnFuse* next = nullptr, bool pool_zeroed = false, bool keep = true) {
   const int HW = H * W, M = N * HW;
   constexpr float eps = kLnEps;
   // norm1 -> conv1 (+bias)
@@ -297,7 +297,8 @@ int nafblock_fwd_impl(const float* const* P, const BlockPacked& pk, const float*
   if (!ln_fusable(C)) DCPT_TRY(ln_fwd_launch(sv.y, P[P_N2W], P[P_N2B], sv.n2, sv.stats2, M, C, eps, st));
   {
     GemmArgs g = gemm_args(M, 2 * C, C, sv.n2, C, pk.w4p, C, C % 32 == 0 ? EPI_GATE_TMA : EPI_GATE);
-    g.ep.out_bf16 = sv.x4; g.ep.ldo = 2 * C; g.ep.out2 = sv.sg; g.ep.ldo2 = C; g.ep.C = C; g.ep.bias = pk.b4p;
+    // (x4, conv4's output before the gate, is read by the backward only: an inference pass does not store it)
+    g.ep.out_bf16 = (keep || C % 32 != 0) ? sv.x4 : nullptr; g.ep.ldo = 2 * C; g.ep.out2 = sv.sg; g.ep.ldo2 = C; g.ep.C = C; g.ep.bias = pk.b4p;
     DCPT_TRY(gemm_launch(g, st));
   }
   // conv5, out = y + x*gamma
@@ -498,6 +499,8 @@ struct dcpt_nafnet_plan {
   // a data-parallel caller starts the all-reduce of that contiguous 90 % slice of the flat gradient buffer on a second
   // stream while the shallower levels are still being differentiated (base_model.py:107-118: what DDP's buckets do).
   mutable SideStream side;  // weight-gradient side stream of this plan's backward (nafblock_bwd_impl)
+  // false: the next forward is inference - tensors only the backward reads (conv4's pre-gate output) are not stored
+  mutable bool keep_activations = true;
   void* split_event = nullptr;
   bool split_event_external = true;  // inside a stream capture: external-event node (waited on from outside the graph) or plain
   std::vector<int> hook_blk;
@@ -913,6 +916,12 @@ int dcpt_nafnet_set_hook_blocks(dcpt_nafnet_plan* plan, const int* block_idx, in
   plan->hook_blk.assign(block_idx, block_idx + n_levels);
   return 0;
 }
+int dcpt_nafnet_set_keep_activations(const dcpt_nafnet_plan* plan, int keep) {
+  DCPT_CHECK_ARG(plan != nullptr, DCPT_E_ARG, "nafnet_set_keep_activations: null plan");
+  plan->keep_activations = keep != 0;
+  return 0;
+}
+
 int dcpt_nafnet_set_bwd_split_event(dcpt_nafnet_plan* plan, void* cuda_event, int external) {
   DCPT_CHECK_ARG(plan != nullptr, DCPT_E_ARG, "nafnet_set_bwd_split_event: null plan");
   plan->split_event = cuda_event;
@@ -1014,7 +1023,7 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     for (int j = 0; j < p->enc[i]; ++j) {
       const LnFuse nx = j + 1 < p->enc[i] ? ln1_of(p->enc_blks[i][j + 1], sv.enc_sv[i][j + 1]) : no_ln;
       DCPT_TRY(nafblock_fwd_impl(P + p->enc_blks[i][j].pidx, pk.enc_pk[i][j], x, sv.enc_out[i][j], nullptr, sv.enc_sv[i][j], N, h,
-                                 w, C, st, tkh(i), tkw(i), fused, &nx, true));
+                                 w, C, st, tkh(i), tkw(i), fused, &nx, true, p->keep_activations));
       fused = nx.n != nullptr;
       x = sv.enc_out[i][j];
     }
@@ -1035,7 +1044,7 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
     bf16* mirror = (j == p->middle_blk_num - 1 && nd > 0) ? sv.up_in[0] : nullptr;
     const LnFuse nx = j + 1 < p->middle_blk_num ? ln1_of(p->mid_blks[j + 1], sv.mid_sv[j + 1]) : no_ln;
     DCPT_TRY(nafblock_fwd_impl(P + p->mid_blks[j].pidx, pk.mid_pk[j], x, sv.mid_out[j], mirror, sv.mid_sv[j], N, h, w, C, st, tkh(ne),
-                               tkw(ne), fused, &nx, true));
+                               tkw(ne), fused, &nx, true, p->keep_activations));
     fused = nx.n != nullptr;
     x = sv.mid_out[j];
   }
@@ -1054,7 +1063,7 @@ int dcpt_nafnet_fwd(const dcpt_nafnet_plan* p, const float* const* P, const void
       bf16* mirror = (j == p->dec[i] - 1) ? (i + 1 < nd ? sv.up_in[i + 1] : sv.xlast_bf16) : nullptr;
       const LnFuse nx = j + 1 < p->dec[i] ? ln1_of(p->dec_blks[i][j + 1], sv.dec_sv[i][j + 1]) : no_ln;
       DCPT_TRY(nafblock_fwd_impl(P + p->dec_blks[i][j].pidx, pk.dec_pk[i][j], x, sv.dec_out[i][j], mirror, sv.dec_sv[i][j], N, h, w,
-                                 C, st, tkh(ne - 1 - i), tkw(ne - 1 - i), fused, &nx, true));
+                                 C, st, tkh(ne - 1 - i), tkw(ne - 1 - i), fused, &nx, true, p->keep_activations));
       fused = nx.n != nullptr;
       x = sv.dec_out[i][j];
       if (host_feats && host_feats[i] && j == p->hook_block(i))

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "dcpt_nafnet_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
     "dcpt_nafnet_pack": (_I, [_VP, _PP, _VP, _VP]),
     "dcpt_nafnet_fwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _I, _I, _I, _I, _VP]),
+    "dcpt_nafnet_set_keep_activations": (_I, [_VP, _I]),
     "dcpt_nafnet_bwd": (_I, [_VP, _PP, _VP, _VP, _VP, _VP, _PP, _PP, _VP, _I, _I, _I, _VP]),
     "dcpt_pack_matrix": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "dcpt_conv3x3_packed_elems": (_SZ, [_I, _I, _I]),

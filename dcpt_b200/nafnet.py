@@ -174,6 +174,8 @@ class NAFNetEngine:
                 feats.append(torch.empty(N, h, w, c, dtype=torch.float32, device=dev))
             fp = _l.ptr_array([f.data_ptr() for f in feats])
         pp = _l.ptr_array([p.data_ptr() for p in params])
+        # inference passes skip the stores only a backward would read (dcpt_nafnet_set_keep_activations)
+        _l.check(self.lib.dcpt_nafnet_set_keep_activations(self.plan, _keep(keep_for_backward)), "nafnet_set_keep_activations")
         _l.check(self.lib.dcpt_nafnet_fwd(self.plan, pp, _p(packed), _p(inp), _p(out), _p(saved), fp, int(bool(hook)), N, H,
                                           W, _stream()), "nafnet_fwd")
         return out, feats, saved
@@ -293,7 +295,8 @@ def _graph_forward(eng, pv, inp, hook, want_feats, need_grad):
     params = pv.dparams
     inp = inp.contiguous().float()
     N, _, H, W = inp.shape
-    key = (N, H, W, inp.device, bool(hook), bool(want_feats), pv.ptrs)
+    # (a no-grad slot's captured forward does not store what only a backward reads: never shared with a gradient-needing forward)
+    key = (N, H, W, inp.device, bool(hook), bool(want_feats), pv.ptrs, bool(need_grad))
     if not need_grad and key not in eng._gslots:
         # inference over images of many sizes (validation sets): a shape earns a graph slot (static buffers + a saved-activation
         # arena + a capture) only when it comes back; the first sighting launches eagerly through the shared scratch arena
@@ -313,6 +316,7 @@ def _graph_forward(eng, pv, inp, hook, want_feats, need_grad):
     fp = _l.ptr_array([f.data_ptr() for f in slot.feats]) if slot.feats else None
 
     def run():
+        _l.check(eng.lib.dcpt_nafnet_set_keep_activations(eng.plan, _keep(need_grad)), "nafnet_set_keep_activations")
         _l.check(eng.lib.dcpt_nafnet_fwd(eng.plan, pp, _p(packed), _p(slot.inp), _p(slot.out), _p(slot.saved), fp, int(slot.hook),
                                          N, H, W, _stream()), "nafnet_fwd")
     if slot.fgraph is None:
@@ -387,6 +391,11 @@ def _graph_backward(eng, pv, slot, dout, dfeats):
         eng.grad_sync(slot.flat)            # data-parallel wrapper: ONE mean all-reduce of the flat gradient buffer
     flat = slot.flat.clone()            # autograd owns the returned gradients; the slot's buffer is rewritten next step
     return [flat[o:o + n].view(shp) for o, n, shp in slot.shapes]
+
+
+def _keep(need_grad):
+    """1 = training forward (every saved tensor is written); DCPT_INFER_KEEP=1 forces it for inference passes too (A/B switch)."""
+    return int(bool(need_grad) or os.getenv("DCPT_INFER_KEEP", "0") == "1")
 
 
 _CAPTURE_STREAMS = {}

@@ -194,6 +194,11 @@ int dcpt_nafnet_pack(const dcpt_nafnet_plan* plan, const float* const* host_para
  * hook != 0: skip `ending` (nafnet_arch.py:269-274), `out` may be NULL.
  * host_feats (nullable): n_dec device pointers receiving the decoder-level outputs as fp32 NHWC
  * (what DCPT's forward hooks capture, degradation_classification_pretrain_model.py:60-72). */
+/* keep = 0: the following dcpt_nafnet_fwd calls are inference passes (torch.no_grad(): SRModel.test, sr_model.py:176-185) - tensors
+ * that only dcpt_nafnet_bwd reads (conv4's output before the SimpleGate, 2C channels per pixel and block) are not written, so `saved`
+ * must not be handed to dcpt_nafnet_bwd afterwards.  keep = 1 (default) restores the training forward.  Baked into a CUDA graph at
+ * capture time like every other argument. */
+int dcpt_nafnet_set_keep_activations(const dcpt_nafnet_plan* plan, int keep);
 int dcpt_nafnet_fwd(const dcpt_nafnet_plan* plan, const float* const* host_params, const void* packed, const float* inp,
                     float* out, void* saved, float* const* host_feats, int hook, int N, int H, int W,
                     dcpt_stream_t stream);
