@@ -92,6 +92,9 @@ struct GemmArgs {
   //    split stays inside one batch and accumulates into out_f32 + batch * ep.out_batch_stride.  `splits` = splits per batch.
   int m_per_batch, b_rows_per_batch;
   int k_per_batch;
+  // EPI_ATOMIC only: launch one CTA per (tile, split) work item instead of a persistent grid of <= #SM CTAs looping over them.
+  // Short-lived CTAs give thread-block slots back sooner when this GEMM runs on a low-priority stream beside a critical chain.
+  int fine_grid;
 };
 
 // Geometry of the implicit-GEMM 3x3 convolution modes of the tensor-core kernel (gemm_sm100.cu).

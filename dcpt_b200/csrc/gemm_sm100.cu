@@ -1352,6 +1352,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   }
   const int total = tiles_m * tiles_n * splits;
   int grid = total < dcpt_num_sms() ? total : dcpt_num_sms();
+  if (EPI == EPI_ATOMIC && g.fine_grid) grid = total;  // one work item per CTA: short-lived CTAs (wgrad on the low-priority stream)
   if ((EPI == EPI_STORE_TMA && g.ep.ln_out && tiles_n > 1) || (EPI == EPI_LNBWD_TMA && tiles_n > 1))
     grid = tiles_m < dcpt_num_sms() ? tiles_m : dcpt_num_sms();  // whole slabs per CTA
 

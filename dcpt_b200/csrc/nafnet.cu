@@ -168,6 +168,30 @@ int wgrad_gemm(const bf16* dY, int O, const bf16* X, int I, float* out, int Mpx,
   const int tiles = ceil_div(O, 128) * ceil_div(I, bn);
   const int num_kb = ceil_div(Mpx, 64);
   g.splits = gemm_auto_splits(tiles, num_kb);
+  {  // experiment knobs: DCPT_WGRAD_SPLIT_MULT=k / DCPT_WGRAD_SPLIT_DIV=k (k x, 1/k x the one-wave split factor), DCPT_WGRAD_FINE=1 (one
+     // work item per CTA).  Same-box A/B (r03k, ms per step): default 21.17-21.25; x2 21.43; x2 fine 21.6; x4 fine 23.0; /2 21.4;
+     // /3 21.8 - the one-wave split with persistent CTAs is the optimum on either side.
+    static int mult = -1, fine = -1;
+    if (mult < 0) {
+      const char* e = getenv("DCPT_WGRAD_SPLIT_MULT");
+      mult = e ? atoi(e) : 1;
+      if (mult < 1) mult = 1;
+      const char* f = getenv("DCPT_WGRAD_FINE");
+      fine = (f && f[0] == '1') ? 1 : 0;
+    }
+    g.splits *= mult;
+    {
+      static int dv = -1;
+      if (dv < 0) {
+        const char* e = getenv("DCPT_WGRAD_SPLIT_DIV");
+        dv = e ? atoi(e) : 1;
+        if (dv < 1) dv = 1;
+      }
+      g.splits = g.splits / dv > 0 ? g.splits / dv : 1;
+    }
+    if (g.splits > num_kb) g.splits = num_kb;
+    g.fine_grid = fine;
+  }
   g.ep.out_f32 = out; g.ep.ldo = I;
   return gemm_launch(g, st);
 }
