@@ -64,9 +64,10 @@ struct Tiles {
     tiles_h = (H + TH - 1) / TH;
     per_img = tiles_w * tiles_h;
     total = N * per_img;
-    const int chunk = (total + gridDim.x - 1) / gridDim.x;  // contiguous range per CTA
-    t0 = min(total, (int)blockIdx.x * chunk);
-    t1 = min(total, t0 + chunk);
+    // contiguous range per CTA, sizes differing by at most one tile (every CTA of the grid gets work: with ceil-sized chunks
+    // 128 tiles on 37 CTAs left 5 CTAs idle and gave the others 4 tiles each instead of 3-4)
+    t0 = (int)(((long long)total * blockIdx.x) / gridDim.x);
+    t1 = (int)(((long long)total * (blockIdx.x + 1)) / gridDim.x);
   }
   __device__ void decode(int t, int& n, int& h0, int& w0) const {
     n = t / per_img;
