@@ -158,13 +158,29 @@ def _worker_dcpt_model(rank, world, port, q):
     n_before = len(calls)
     D.exchange_accumulated_grads_([lin])
     base_ok = len(calls) == n_before + 1 and calls[-1] == 300516 and bool(torch.allclose(base, torch.full_like(base, (1 + world) / 2)))
+    # the mixed case of the DCPT step: the node that ran first (hooked pass) did not reach `ending`, so two small gradients alias
+    # the OTHER node's flat buffer - one whole-run all-reduce for the big buffer, one coalesced call for the leftovers
+    mix = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(500, 600)), torch.nn.Parameter(torch.zeros(500)),
+                                  torch.nn.Parameter(torch.zeros(7, 3)), torch.nn.Parameter(torch.zeros(7))])
+    flat_a = torch.full((300500 + 16,), float(rank + 1))
+    flat_b = torch.full((300500 + 64 + 21 + 64 + 7,), float(10 * (rank + 1)))
+    mix[0].grad, mix[1].grad = flat_a[:300000].view(500, 600).detach(), flat_a[300016:].detach()
+    mix[2].grad, mix[3].grad = flat_b[300564:300585].view(7, 3).detach(), flat_b[300649:300656].detach()
+    n_before = len(calls)
+    D.exchange_accumulated_grads_([mix])
+    mixed_ok = (len(calls) == n_before + 2 and sorted(calls[-2:]) == [28, 300516]
+                and bool(torch.allclose(mix[0].grad, torch.full((500, 600), (1 + world) / 2)))
+                and bool(torch.allclose(mix[2].grad, torch.full((7, 3), 10 * (1 + world) / 2)))
+                and bool(torch.allclose(mix[3].grad, torch.full((7,), 10 * (1 + world) / 2)))
+                and float(flat_b[0]) == 10 * (rank + 1))           # the rest of the second buffer is left alone
+    base_ok = base_ok and mixed_ok
     if rank == 0:
         D.allreduce_mean_ = real
         torch.distributed.destroy_process_group()
         single = build_model(_dcpt_opt(False))
         fg, fh, flog = _dcpt_step(single, sd_g, sd_h, list(range(4)))
-        q.put((wrapped, hooked, len(calls) - 1, float((gg - fg).norm() / fg.norm()), float((gh - fh).norm() / fh.norm()),
-               abs(log["l_pix"] - flog["l_pix"]), abs(log["l_classify"] - flog["l_classify"]), base_ok))
+        q.put((wrapped, hooked, len(calls) - 3, float((gg - fg).norm() / fg.norm()), float((gh - fh).norm() / fh.norm()),
+               abs(log["l_pix"] - flog["l_pix"]), abs(log["l_classify"] - flog["l_classify"]), base_ok))   # n_calls: the model's two
     else:
         torch.distributed.destroy_process_group()
 
