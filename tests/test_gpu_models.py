@@ -211,3 +211,48 @@ def test_cuda_prefetcher_matches_reference_semantics():
         assert seen == [0, 1, 2]
         pf.reset()
     assert pf.stream != torch.cuda.current_stream()
+
+
+def test_dcpt_model_with_restormer_backbone():
+    """DCPTModel on a Restormer backbone (hook_names "decoder" -> decoder_level{1,2,3}.body by the one-dot rule, collected in
+    forward order 3, 2, 1 and reversed for the classifier, degradation_classification_pretrain_model.py:64-67, 155): logged losses
+    of the first iteration against the fp32 oracle, then two more iterations stay finite and move both networks."""
+    from basicsr.models import build_model
+    from oracle import restormer_oracle as RO
+    rcfg = dict(dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, heads=[1, 2, 4, 8])
+    dims = [32, 32, 64]
+    adamw = {"type": "AdamW", "lr": 1e-3, "weight_decay": 1e-4, "betas": [0.9, 0.9]}
+    opt = {"name": "r", "model_type": "DCPTModel", "scale": 1, "num_gpu": 1, "dist": False, "is_train": True, "rank": 0, "world_size": 1,
+           "hook_names": "decoder", "path": {"pretrain_network_g": None},
+           "network_g": dict(type="Restormer", window_size=8, **rcfg),
+           "network_dc": dict(type="PromptIR_NoImg_DC", feature_dims=dims, num_res_blocks=2, num_classes=5),
+           "train": {"optim_g": dict(adamw), "optim_dc": dict(adamw), "scheduler": {"type": "MultiStepLR", "milestones": [100], "gamma": 0.5},
+                     "pixel_opt": {"type": "L1Loss", "loss_weight": 1.0, "reduction": "mean"},
+                     "classify_opt": {"type": "CrossEntropyLoss", "loss_weight": 1.0}}}
+    model = build_model(opt)
+    sd_g = RO.random_restormer_state_dict(seed=8, dim=16, num_blocks=(1, 1, 1, 1), num_refinement_blocks=1, heads=(1, 2, 4, 8))
+    sd_h = D.random_dchead_state_dict(dims, 2, 5, seed=9)
+    model.net_g.load_state_dict(sd_g, strict=True)
+    model.net_dc.load_state_dict(sd_h, strict=True)
+    assert sorted(n for n, m in model.net_g.named_modules() if len(m._forward_hooks) > 0) == [f"decoder_level{k}.body" for k in (1, 2, 3)]
+    g = torch.Generator().manual_seed(14)
+    before_g, before_h = _flat(model.net_g), _flat(model.net_dc)
+    for it in range(1, 4):
+        gt, lq = torch.rand(2, 3, 32, 48, generator=g), torch.rand(2, 3, 32, 48, generator=g)
+        idx = torch.randint(0, 5, (2,), generator=g)
+        if it == 1:
+            with torch.no_grad():
+                o_pix = RO.restormer_fwd(gt, sd_g, (1, 1, 1, 1), 1, (1, 2, 4, 8))
+                _, feats = RO.restormer_fwd(lq, sd_g, (1, 1, 1, 1), 1, (1, 2, 4, 8), hook=True, return_feats=True)
+                l_pix = float((o_pix - gt).abs().mean())
+                l_cls = float(F.cross_entropy(D.dchead_fwd(feats[::-1], sd_h), idx))
+        model.feed_data({"lq": lq, "gt": gt, "dataset_idx": idx})
+        model.optimize_parameters(it)
+        log = model.get_current_log()
+        assert np.isfinite(log["l_pix"]) and np.isfinite(log["l_classify"])
+        if it == 1:
+            e_pix, e_cls = abs(log["l_pix"] - l_pix) / l_pix, abs(log["l_classify"] - l_cls) / l_cls
+            report("DCPTModel + Restormer, iteration 1", l_pix=e_pix, l_classify=e_cls)
+            assert e_pix < tol(2e-2, 3e-3) and e_cls < tol(3e-2, 5e-3), (e_pix, e_cls)
+    assert float((_flat(model.net_g) - before_g).abs().max()) > 1e-4 and float((_flat(model.net_dc) - before_h).abs().max()) > 1e-4
+    assert model.hook_outputs == []
