@@ -8,12 +8,13 @@ sequences C-ABI calls and owns the buffers (the reference's host side is Python 
 forward / backward in ONE ``autograd.Function`` so it composes with the NAFNet function under ``loss.backward()``.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import lib as _l
 from .ops import _p, _stream, gemm
-from .params import PackedCacheKey, fp16_grad_scale
+from .params import LRUCache, PackedCacheKey, fp16_grad_scale, training_pass
 
 
 
@@ -48,6 +49,11 @@ class DCHeadEngine:
         self.index = {n: i for i, n in enumerate(names)}
         self._packed = None
         self._packed_key = PackedCacheKey()
+        # CUDA-graph replay of the whole head forward / backward (192 launches through ctypes per step otherwise: measured 10.8 ms
+        # of host enqueue for 11.2 ms of device time at the C4 size - the GPU waits for Python); DCPT_DCHEAD_GRAPH=0: eager
+        self.use_graphs = os.getenv("DCPT_CUDA_GRAPH", "1") != "0" and os.getenv("DCPT_DCHEAD_GRAPH", "1") != "0"
+        self._gslots = LRUCache(can_evict=lambda s_: not s_.busy)
+        self._seen = LRUCache(cap=64)
 
     # ---- packed bf16 operand cache ---------------------------------------------------------------
     def _pack(self, params):
@@ -55,13 +61,20 @@ class DCHeadEngine:
             return self._packed
         dev = params[0].device
         P = lambda n: params[self.index[n]]
-        pk = {}
+        # re-packing after a parameter update writes into the SAME tensors (captured graphs hold their addresses)
+        old = self._packed if (self._packed is not None and next(iter(self._packed.values()))[0].device == dev) else {}
+        pk = old
+
+        def buf(name, k, n):
+            if name in old and old[name][k] is not None and old[name][k].numel() == n:
+                return old[name][k]
+            return torch.empty(n, dtype=_l.operand_dtype(), device=dev)
 
         def mat(name):
             w = P(name)
             O, I = w.shape[0], w.shape[1]
-            a = torch.empty(O, I, dtype=_l.operand_dtype(), device=dev)
-            b = torch.empty(I, O, dtype=_l.operand_dtype(), device=dev)
+            a = buf(name, 0, O * I).view(O, I)
+            b = buf(name, 1, O * I).view(I, O)
             _l.check(self.lib.dcpt_pack_matrix(_p(w), _p(a), O, I, 0, _stream()), "pack_matrix")
             _l.check(self.lib.dcpt_pack_matrix(_p(w), _p(b), O, I, 1, _stream()), "pack_matrix")
             pk[name] = (a, b)
@@ -69,8 +82,8 @@ class DCHeadEngine:
         def conv3(name):
             w = P(name)
             O, I = w.shape[0], w.shape[1]
-            a = torch.empty(self.lib.dcpt_conv3x3_packed_elems(O, I, 0), dtype=_l.operand_dtype(), device=dev)
-            b = torch.empty(self.lib.dcpt_conv3x3_packed_elems(O, I, 1), dtype=_l.operand_dtype(), device=dev)
+            a = buf(name, 0, self.lib.dcpt_conv3x3_packed_elems(O, I, 0))
+            b = buf(name, 1, self.lib.dcpt_conv3x3_packed_elems(O, I, 1))
             _l.check(self.lib.dcpt_conv3x3_pack(_p(w), _p(a), O, I, 0, _stream()), "conv3x3_pack")
             _l.check(self.lib.dcpt_conv3x3_pack(_p(w), _p(b), O, I, 1, _stream()), "conv3x3_pack")
             pk[name] = (a, b)
@@ -84,7 +97,7 @@ class DCHeadEngine:
             w = P("conv_embed.0.weight")
             wp = torch.zeros(w.shape[0], 160, dtype=torch.float32, device=dev)
             wp[:, :147] = w.reshape(w.shape[0], 147)
-            a = torch.empty(w.shape[0], 160, dtype=_l.operand_dtype(), device=dev)
+            a = buf("conv_embed.0.weight", 0, w.shape[0] * 160).view(w.shape[0], 160)
             _l.check(self.lib.dcpt_pack_matrix(_p(wp), _p(a), w.shape[0], 160, 0, _stream()), "pack_matrix")
             pk["conv_embed.0.weight"] = (a, None)
         self._packed = pk
@@ -139,13 +152,14 @@ class DCHeadEngine:
         return gemm(dt1, pk[prefix + "conv1.weight"][1], resid=dres, out_dtype=torch.float32)   # + shortcut gradient, fused
 
     # ---- whole head ---------------------------------------------------------------------------------
-    def forward(self, params, feats, lq=None):
+    def forward(self, params, feats, lq=None, pk=None):
         """feats[i]: fp32 NHWC [N, H>>i, W>>i, dims[i]] (contiguous).  Returns (logits fp32 [N, K], ctx).
-        lq (fp32 NCHW) is read only by the img_embed (PromptIR_DC) variant."""
+        lq (fp32 NCHW) is read only by the img_embed (PromptIR_DC) variant.  pk: the packed operands when the caller already
+        validated them (graph capture: the staleness check reads back a fingerprint and must stay outside)."""
         for p in params:
             if not p.is_cuda:
                 raise _l.DcptError("dcpt_b200 has no CPU path: move the classifier head to a CUDA device")
-        pk = self._pack(params)
+        pk = self._pack(params) if pk is None else pk
         mw = torch.softmax(params[0].detach().float(), dim=0).contiguous()     # 1-D softmax of len(dims) scalars (:633)
         ctx = {"mw": mw, "stages": [], "feats": feats}
         z = None
@@ -193,9 +207,10 @@ class DCHeadEngine:
         ctx.update(last=last, shp=shp, pooled=pooled, xlast=x)
         return logits, ctx
 
-    def backward(self, params, ctx, dlogits):
-        """Returns (dfeats list of fp32 NHWC, grads list in parameter order)."""
-        pk = self._pack(params)
+    def backward(self, params, ctx, dlogits, pk=None, sync=True):
+        """Returns (dfeats list of fp32 NHWC, grads list in parameter order).  sync=False: the caller runs grad_sync itself on
+        self._last_flat (graph replay: a collective cannot sit inside the captured graph)."""
+        pk = self._pack(params) if pk is None else pk
         dev = dlogits.device
         offs, off = [], 0
         for p in params:                                   # one flat buffer (256-byte aligned views): one all-reduce under DP
@@ -246,28 +261,115 @@ class DCHeadEngine:
         if sc is not None:
             flat.mul_(sc[1])
             torch._foreach_mul_(dfeats, sc[1])
-        if self.grad_sync is not None:
+        self._last_flat, self._last_offs = flat, offs
+        if sync and self.grad_sync is not None:
             self.grad_sync(flat)
         return dfeats, grads
+
+    # ---- CUDA-graph replay -----------------------------------------------------------------------------
+    def graph_forward(self, params, feats, lq):
+        """Replay of `forward` on static buffers, or None (first sighting of a shape, slot busy, graphs off): the caller then
+        launches eagerly.  Returns (logits, slot); the slot is the backward's context and is busy until `graph_backward`."""
+        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
+            return None
+        key = (tuple(tuple(f.shape) for f in feats), None if lq is None else tuple(lq.shape), feats[0].device,
+               tuple(p.data_ptr() for p in params))
+        slot = self._gslots.get(key)
+        if slot is None:
+            if self._seen.get(key) is None:       # a shape earns a slot (static buffers + captures) when it comes back
+                self._seen.put(key, True)
+                return None
+            slot = _HeadSlot([torch.empty_like(f) for f in feats], None if lq is None else torch.empty_like(lq))
+            self._gslots.put(key, slot)
+        if slot.busy:
+            return None
+        pk = self._pack(params)                    # eager: staleness check / re-pack; the packed tensors' addresses are stable
+        for s_, f in zip(slot.feats, feats):
+            s_.copy_(f)
+        if slot.lq is not None:
+            slot.lq.copy_(lq)
+        if slot.fgraph is None:
+            self.forward(params, slot.feats, lq=slot.lq, pk=pk)     # eager once: one-time initialisation inside the library
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                slot.logits, slot.ctx = self.forward(params, slot.feats, lq=slot.lq, pk=pk)
+            slot.fgraph, slot.pk = g, pk
+            g.replay()                             # a capture records, it does not execute: fill the captured tensors
+        elif slot.pk is not pk:                    # the weights were re-packed into new tensors: the captures point at the old ones
+            self._gslots.d.pop(key, None)
+            return None
+        else:
+            slot.fgraph.replay()
+        slot.busy = True
+        return slot.logits.clone(), slot
+
+    def graph_backward(self, params, slot, dlogits):
+        pk = slot.pk
+        if slot.dlogits is None:
+            slot.dlogits = torch.empty_like(dlogits, dtype=torch.float32).contiguous()
+        slot.dlogits.copy_(dlogits)
+        if slot.bgraph is None:
+            self.backward(params, slot.ctx, slot.dlogits, pk=pk, sync=False)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=slot.fgraph.pool(), capture_error_mode="thread_local"):
+                slot.dfeats, slot.grads = self.backward(params, slot.ctx, slot.dlogits, pk=pk, sync=False)
+            slot.bgraph, slot.flat, slot.offs = g, self._last_flat, self._last_offs
+            g.replay()
+        else:
+            slot.bgraph.replay()
+        slot.busy = False
+        if self.grad_sync is not None:
+            self.grad_sync(slot.flat)
+        flat = slot.flat.clone()        # autograd owns what it is handed; the slot's buffers are rewritten by the next replay
+        grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(slot.offs, params)]
+        return [d.clone() for d in slot.dfeats], grads
+
+
+class _HeadSlot:
+    """Static inputs, captured graphs and their outputs for one (feature shapes, parameter storage) signature of the head."""
+
+    def __init__(self, feats, lq):
+        self.feats, self.lq = feats, lq
+        self.fgraph = self.bgraph = self.pk = None
+        self.logits = self.ctx = self.dlogits = self.dfeats = self.grads = self.flat = self.offs = None
+        self.busy = False
 
 
 class _DCHeadFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, n_feats, lq, *args):
+    def forward(ctx, engine, n_feats, lq, need_grad, *args):
         feats, params = args[:n_feats], args[n_feats:]
         # features arrive as logical NCHW (channels_last memory from the NAFNet function, or plain NCHW): make NHWC fp32
         fh = [f.detach().permute(0, 2, 3, 1).contiguous().float() for f in feats]
         dparams = [p.detach().contiguous() for p in params]
-        logits, c = engine.forward(dparams, fh, lq=lq)
+        with (training_pass() if need_grad else _NullCtx()):      # no weight-fingerprint sync on training passes (params.py)
+            res = engine.graph_forward(dparams, fh, lq) if need_grad else None
+            if res is None:
+                logits, c = engine.forward(dparams, fh, lq=lq)
+            else:
+                logits, c = res
         ctx.engine, ctx.c, ctx.params, ctx.n_feats = engine, c, dparams, n_feats
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        dfeats, grads = ctx.engine.backward(ctx.params, ctx.c, dlogits)
+        with training_pass():
+            if isinstance(ctx.c, _HeadSlot):
+                dfeats, grads = ctx.engine.graph_backward(ctx.params, ctx.c, dlogits)
+            else:
+                dfeats, grads = ctx.engine.backward(ctx.params, ctx.c, dlogits)
         ctx.c = None
-        return (None, None, None) + tuple(d.permute(0, 3, 1, 2) for d in dfeats) + tuple(grads)   # (lq is data: no gradient)
+        return (None, None, None, None) + tuple(d.permute(0, 3, 1, 2) for d in dfeats) + tuple(grads)   # (lq is data: no gradient)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def dchead_apply(engine, feats, params, lq=None):
-    return _DCHeadFunction.apply(engine, len(feats), lq if engine.embed else None, *feats, *params)
+    need_grad = torch.is_grad_enabled() and (any(f.requires_grad for f in feats) or any(p.requires_grad for p in params))
+    return _DCHeadFunction.apply(engine, len(feats), lq if engine.embed else None, need_grad, *feats, *params)

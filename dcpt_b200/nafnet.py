@@ -13,7 +13,7 @@ import torch
 
 from . import lib as _l
 from .ops import _p, _stream
-from .params import LRUCache, PackedCacheKey, fp16_grad_scale
+from .params import LRUCache, PackedCacheKey, fp16_grad_scale, training_pass
 
 
 class NAFNetEngine:
@@ -435,17 +435,18 @@ class _NAFNetFunction(torch.autograd.Function):
         dparams = pv.dparams
         inp_c = inp.detach().contiguous().float()
         res = None
-        if engine.use_graphs and inp_c.is_cuda and not torch.cuda.is_current_stream_capturing():
-            res = _graph_forward(engine, pv, inp_c, hook, want_feats, need_grad)
-        if res is not None:
-            out, feats, saved = res
-            if need_grad:
-                try:
-                    weakref.finalize(ctx, saved.release, saved.token)   # a forward whose backward never runs must not pin the slot
-                except TypeError:
-                    pass
-        else:
-            out, feats, saved = engine.forward(dparams, inp_c, hook=hook, want_feats=want_feats, keep_for_backward=need_grad)
+        with (training_pass() if need_grad else _null_ctx()):   # (no weight-fingerprint sync on training passes, params.py)
+            if engine.use_graphs and inp_c.is_cuda and not torch.cuda.is_current_stream_capturing():
+                res = _graph_forward(engine, pv, inp_c, hook, want_feats, need_grad)
+            if res is not None:
+                out, feats, saved = res
+                if need_grad:
+                    try:
+                        weakref.finalize(ctx, saved.release, saved.token)   # a forward whose backward never runs must not pin the slot
+                    except TypeError:
+                        pass
+            else:
+                out, feats, saved = engine.forward(dparams, inp_c, hook=hook, want_feats=want_feats, keep_for_backward=need_grad)
         ctx.engine, ctx.hook, ctx.n_feats = engine, hook, len(feats) if feats else 0
         ctx.inp, ctx.saved, ctx.params, ctx.pv = inp_c, saved, dparams, pv
         outs = []
@@ -463,7 +464,7 @@ class _NAFNetFunction(torch.autograd.Function):
         dfe = None
         if ctx.n_feats:
             dfe = [None if d is None else d.permute(0, 2, 3, 1).contiguous() for d in dfeats]
-        with torch.cuda.device(ctx.inp.device):
+        with torch.cuda.device(ctx.inp.device), training_pass():
             if isinstance(ctx.saved, _GraphSlot):
                 grads = _graph_backward(eng, ctx.pv, ctx.saved, None if ctx.hook else dout, dfe)
             else:

@@ -14,6 +14,7 @@ The engines keep bf16 GEMM-operand copies of the fp32 parameters.  They must be 
 """
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -53,6 +54,28 @@ class ParamFingerprint:
             pass
 
 
+_tls = threading.local()
+
+
+class training_pass:
+    """``with training_pass():`` around the forward / backward of a gradient-needing call.  Inside ``autograd.Function.forward``
+    and ``.backward`` grad mode is always off, so "no-grad" cannot be read from ``torch.is_grad_enabled()`` there; without this
+    marker every training forward and backward would run the weight fingerprint and its 8-byte read-back - a host sync that
+    keeps the CPU from queueing the next pass (the DCPT step has three forwards and three backwards per iteration)."""
+
+    def __enter__(self):
+        _tls.depth = getattr(_tls, "depth", 0) + 1
+        return self
+
+    def __exit__(self, *exc):
+        _tls.depth -= 1
+        return False
+
+
+def in_training_pass():
+    return getattr(_tls, "depth", 0) > 0
+
+
 class PackedCacheKey:
     """Decides when an engine's packed operand cache must be rebuilt (see the module docstring)."""
 
@@ -69,7 +92,8 @@ class PackedCacheKey:
         """True when the cache must be rebuilt for `params` (and records the new state: call the pack right after)."""
         key = tuple((p.data_ptr(), p._version) for p in params)
         h = None
-        if self.use_fp and not torch.is_grad_enabled() and params[0].is_cuda and not torch.cuda.is_current_stream_capturing():
+        if self.use_fp and not torch.is_grad_enabled() and not in_training_pass() and params[0].is_cuda and \
+                not torch.cuda.is_current_stream_capturing():
             ptrs = tuple(k[0] for k in key)
             if self.fp is None or self.fp.ptrs != ptrs:
                 self.fp = ParamFingerprint(params)

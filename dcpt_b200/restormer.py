@@ -14,7 +14,7 @@ import torch
 
 from . import lib as _l
 from .ops import _p, _stream
-from .params import LRUCache, PackedCacheKey, fp16_grad_scale
+from .params import LRUCache, PackedCacheKey, fp16_grad_scale, training_pass
 
 
 class RestormerEngine:
@@ -352,16 +352,17 @@ class _RestormerFunction(torch.autograd.Function):
         dparams = [p.detach() for p in params]
         inp_c = inp.detach().contiguous().float()
         res = None
-        if engine.use_train_graphs and inp_c.is_cuda and not torch.cuda.is_current_stream_capturing():
-            res = _train_graph_forward(engine, dparams, inp_c, hook, want_feats)
-        if res is not None:
-            out, feats, saved, token = res
-            try:
-                weakref.finalize(ctx, saved.release, token)   # a forward whose backward never runs must not pin the slot
-            except TypeError:
-                pass
-        else:
-            out, feats, saved = engine.forward_train(dparams, inp_c, hook=hook, want_feats=want_feats)
+        with training_pass():       # restormer_apply is only reached when gradients are needed (no fingerprint sync, params.py)
+            if engine.use_train_graphs and inp_c.is_cuda and not torch.cuda.is_current_stream_capturing():
+                res = _train_graph_forward(engine, dparams, inp_c, hook, want_feats)
+            if res is not None:
+                out, feats, saved, token = res
+                try:
+                    weakref.finalize(ctx, saved.release, token)   # a forward whose backward never runs must not pin the slot
+                except TypeError:
+                    pass
+            else:
+                out, feats, saved = engine.forward_train(dparams, inp_c, hook=hook, want_feats=want_feats)
         ctx.engine, ctx.inp, ctx.saved, ctx.params, ctx.hook, ctx.n_feats = engine, inp_c, saved, dparams, hook, len(feats) if feats else 0
         ctx.dead = frozenset(dead) if hook else frozenset()
         outs = []
@@ -376,10 +377,11 @@ class _RestormerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, *dfeats):
         dfe = [None if d is None else d.permute(0, 2, 3, 1) for d in dfeats] if ctx.n_feats else None
-        if isinstance(ctx.saved, _TrainSlot):
-            grads = _train_graph_backward(ctx.engine, ctx.params, ctx.saved, None if ctx.hook else dout, dfe)
-        else:
-            grads = ctx.engine.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
+        with training_pass():
+            if isinstance(ctx.saved, _TrainSlot):
+                grads = _train_graph_backward(ctx.engine, ctx.params, ctx.saved, None if ctx.hook else dout, dfe)
+            else:
+                grads = ctx.engine.backward(ctx.params, ctx.inp, ctx.saved, None if ctx.hook else dout, dfe)
         ctx.saved = None
         # a hook pass stops after decoder_level1 (restormer_arch.py:403): refinement / output get NO gradient (None), as in
         # the reference; the input image receives none either (as for NAFNet: it is data)
