@@ -79,6 +79,17 @@ class PromptIR_NoImg_DC(nn.Module):
     def engine(self):
         return self._engine
 
+    def train(self, mode=True):
+        if self.training == bool(mode):          # (no module-tree walk when the mode does not change; nothing here depends on it)
+            return self
+        return super().train(mode)
+
+    def prepack(self):
+        """Re-pack the 16-bit operand images of the weights now (see NAFNetBaseline.prepack)."""
+        params = list(self.parameters())
+        if params and params[0].is_cuda:
+            self._engine._pack([p.detach().contiguous() for p in params])
+
     def forward(self, lq, features):
         """``lq`` is unused, as in the reference (:622-641).  features: fine -> coarse, logical NCHW CUDA tensors."""
         return dchead_apply(self._engine, list(features), list(self.parameters()))

@@ -154,6 +154,24 @@ class NAFNetBaseline(nn.Module):
             blocks.append(j if j != last else -1)
         return targets, blocks
 
+    def train(self, mode=True):
+        """nn.Module.train without the walk over ~700 parameter-container sub-modules when the mode does not change (the step
+        classes call net_g.train() every iteration, sr_model.py:133: 1.3 ms of host time before the first launch of the step;
+        nothing in these containers depends on .training)."""
+        if self.training == bool(mode):
+            return self
+        return super().train(mode)
+
+    def prepack(self):
+        """Re-pack the 16-bit operand images of the weights NOW instead of at the next forward.  The step classes call it right
+        after optimizer.step(): the ~300 small pack launches then queue up behind the optimizer kernels while the GPU is still
+        busy, instead of costing 1.5 ms of host time in front of the next iteration's first kernel."""
+        params = self._param_list()
+        if params and params[0].is_cuda:
+            from dcpt_b200.nafnet import _param_view
+            eng = self.engine()
+            eng.packed_for(_param_view(eng, params).dparams)
+
     def _param_list(self):
         """list(self.parameters()) without the module-tree walk (0.4 ms per call for 664 tensors, paid while the GPU idles
         before the graph launch): the (module, name) slots are cached, the Parameter objects are read fresh every call."""

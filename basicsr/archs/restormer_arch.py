@@ -155,6 +155,18 @@ class Restormer(nn.Module):
             if m.bias is not None:
                 nn.init.constant_(m.bias, 0)
 
+    def train(self, mode=True):
+        """(as NAFNetBaseline.train: no module-tree walk when the mode does not change)"""
+        if self.training == bool(mode):
+            return self
+        return super().train(mode)
+
+    def prepack(self):
+        """(as NAFNetBaseline.prepack: re-pack the weights' operand images right after the optimizer step)"""
+        params = list(self.parameters())
+        if params and params[0].is_cuda:
+            self.engine().packed_for([p.detach() for p in params])
+
     def engine(self):
         if self._engine is None:
             self._engine = RestormerEngine(**self._cfg)

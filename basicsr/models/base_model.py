@@ -120,6 +120,16 @@ class BaseModel:
     def get_current_learning_rate(self):
         return [g["lr"] for g in self.optimizers[0].param_groups]
 
+    def prepack(self, *nets):
+        """After optimizer.step(): let the engines refresh their packed weights while the GPU is still busy with the update
+        (the arch mirrors' ``prepack``; a network without one is left alone)."""
+        if self.device.type != "cuda":
+            return
+        for net in nets:
+            fn = getattr(self.get_bare_model(net), "prepack", None)
+            if fn is not None:
+                fn()
+
     # ------------------------------------------------------------------ EMA
     def model_ema(self, decay=0.999):
         """net_g_ema = decay * net_g_ema + (1 - decay) * net_g over the parameters (base_model.py:86-95), one multi-tensor

@@ -94,6 +94,7 @@ class DCPTModel(BaseModel):
             exchange_accumulated_grads_(wrapped)
         self.optimizer_g.step()
         self.optimizer_dc.step()
+        self.prepack(self.net_g, self.net_dc)
         self.hook_outputs = []
         self.log_dict = self.reduce_loss_dict(loss_dict)
 

@@ -90,6 +90,7 @@ class SRModel(BaseModel):
             self.optimizer_g.step()
             if ema:
                 self.model_ema(decay=self.ema_decay)
+        self.prepack(self.net_g)
         self.log_dict = self.reduce_loss_dict(loss_dict)
 
     def _ema_frozen(self):

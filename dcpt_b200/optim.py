@@ -70,6 +70,16 @@ class FusedAdam(torch.optim.Optimizer):
         self._plans = {}
         self._fast = {}
 
+    def zero_grad(self, set_to_none=True):
+        """torch.optim.Optimizer.zero_grad with set_to_none=True, minus its per-call bookkeeping (hooks, per-device foreach
+        grouping): 1.7 -> 0.2 ms for 664 tensors, host time during which the GPU idles at the start of every iteration (the
+        step classes call optimizer.zero_grad() first, sr_model.py:134, degradation_classification_pretrain_model.py:139)."""
+        if not set_to_none:
+            return super().zero_grad(set_to_none=False)
+        for group in self.param_groups:
+            for p in group["params"]:
+                p.grad = None
+
     def _plan(self, key, numels, device):
         if key not in self._plans:
             self._plans[key] = _Plan(self._lib, numels, device)
