@@ -9,6 +9,7 @@ forward / backward in ONE ``autograd.Function`` so it composes with the NAFNet f
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -301,6 +302,7 @@ class DCHeadEngine:
         else:
             slot.fgraph.replay()
         slot.busy = True
+        slot.token += 1
         return slot.logits.clone(), slot
 
     def graph_backward(self, params, slot, dlogits):
@@ -333,6 +335,11 @@ class _HeadSlot:
         self.fgraph = self.bgraph = self.pk = None
         self.logits = self.ctx = self.dlogits = self.dfeats = self.grads = self.flat = self.offs = None
         self.busy = False
+        self.token = 0          # use counter: a finalizer of an OLD autograd node must not release a newer forward's claim
+
+    def release(self, token):
+        if self.token == token:
+            self.busy = False
 
 
 class _DCHeadFunction(torch.autograd.Function):
@@ -348,6 +355,10 @@ class _DCHeadFunction(torch.autograd.Function):
                 logits, c = engine.forward(dparams, fh, lq=lq)
             else:
                 logits, c = res
+                try:
+                    weakref.finalize(ctx, c.release, c.token)     # a forward whose backward never runs must not pin the slot
+                except TypeError:
+                    pass
         ctx.engine, ctx.c, ctx.params, ctx.n_feats = engine, c, dparams, n_feats
         return logits
 

@@ -401,3 +401,49 @@ def test_promptir_dc_img_golden(golden_dir):
         from oracle import dchead_oracle as D
         ref = D.dchead_fwd([torch.zeros(f.shape) for f in feats], sd, lq=torch.from_numpy(z["lq"]))
     assert rel(a, ref) < tol(1e-2, 1e-3) and rel(a, b) > 1e-3
+
+
+def test_dchead_graph_replay_matches_eager_and_survives_abandoned_forwards():
+    """The head's CUDA-graph replay (dcpt_b200/dchead.py graph_forward / graph_backward) against eager launches of the same engine
+    code on the same weights: logits, feature gradients and parameter gradients; forwards whose backward never runs (their
+    autograd nodes are dropped) must release the slot; after an in-place weight update the replays use the re-packed weights."""
+    from basicsr.archs import build_network
+    dims = [16, 32]
+    sd = D.random_dchead_state_dict(dims, 2, 5, seed=11)
+    heads = []
+    for graphs in (True, False):
+        h = build_network(dict(type="PromptIR_NoImg_DC", feature_dims=dims, num_res_blocks=2, num_classes=5)).cuda()
+        h.load_state_dict(sd, strict=True)
+        h.engine().use_graphs = graphs
+        heads.append(h)
+    g = torch.Generator().manual_seed(6)
+    lq = torch.rand(2, 3, 32, 32, generator=g).cuda()
+    labels = torch.tensor([1, 3]).cuda()
+
+    def feats():
+        gg = torch.Generator().manual_seed(7)
+        return [torch.randn(2, c, 32 >> i, 32 >> i, generator=gg).cuda().requires_grad_(True) for i, c in enumerate(dims)]
+
+    for _ in range(4):                                  # first sighting eager, then capture, then replays - all abandoned
+        out = heads[0](lq, feats())
+        del out
+    slots = list(heads[0].engine()._gslots.d.values())
+    assert len(slots) == 1 and not slots[0].busy and slots[0].fgraph is not None
+    for rnd in range(2):
+        res = []
+        for h in heads:
+            h.zero_grad(set_to_none=True)
+            fs = feats()
+            logits = h(lq, fs)
+            F.cross_entropy(logits, labels).backward()
+            res.append((logits.detach(), [f.grad for f in fs], [p.grad.clone() for p in h.parameters()]))
+        assert slots[0].bgraph is not None and not slots[0].busy
+        assert rel(res[0][0], res[1][0]) < 1e-5
+        for a, b in zip(res[0][1], res[1][1]):
+            assert rel(a, b) < 1e-4
+        worst = max(rel(a, b) for a, b in zip(res[0][2], res[1][2]) if float(b.abs().max()) > 0)
+        assert worst < 2e-3, worst                      # split-K atomics order
+        with torch.no_grad():                           # an "optimizer step": in-place update, version counters bumped
+            for h in heads:
+                for p in h.parameters():
+                    p.mul_(1.01)
