@@ -76,6 +76,35 @@ def in_training_pass():
     return getattr(_tls, "depth", 0) > 0
 
 
+class frozen_weights:
+    """``with frozen_weights():`` around a loop of no-grad forwards that THIS package drives and inside which no user code can
+    touch the parameters (the tile loop of dcpt_b200/tiling.py): the weight fingerprint - a host sync per forward - is compared
+    by the first forward of each engine inside the block and skipped by the following ones."""
+
+    def __enter__(self):
+        _tls.frozen = getattr(_tls, "frozen", 0) + 1
+        if _tls.frozen == 1:
+            _tls.frozen_seen = set()
+        return self
+
+    def __exit__(self, *exc):
+        _tls.frozen -= 1
+        if _tls.frozen == 0:
+            _tls.frozen_seen = set()
+        return False
+
+
+def _fingerprint_already_checked(cache_key_obj):
+    """Inside frozen_weights(): True from the second call on for this PackedCacheKey."""
+    if getattr(_tls, "frozen", 0) <= 0:
+        return False
+    seen = _tls.frozen_seen
+    if id(cache_key_obj) in seen:
+        return True
+    seen.add(id(cache_key_obj))
+    return False
+
+
 class PackedCacheKey:
     """Decides when an engine's packed operand cache must be rebuilt (see the module docstring)."""
 
@@ -93,7 +122,7 @@ class PackedCacheKey:
         key = tuple((p.data_ptr(), p._version) for p in params)
         h = None
         if self.use_fp and not torch.is_grad_enabled() and not in_training_pass() and params[0].is_cuda and \
-                not torch.cuda.is_current_stream_capturing():
+                not torch.cuda.is_current_stream_capturing() and not (key == self.key and _fingerprint_already_checked(self)):
             ptrs = tuple(k[0] for k in key)
             if self.fp is None or self.fp.ptrs != ptrs:
                 self.fp = ParamFingerprint(params)

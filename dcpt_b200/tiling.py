@@ -66,15 +66,17 @@ def tile_forward(net, lq, infer_size, tile_pad, scale=1, max_batch=16):
         (yp0, yp1, xp0, xp1), _ = t
         groups.setdefault((yp1 - yp0, xp1 - xp0), []).append(t)
     per = max(1, max_batch // b)                       # tiles per forward (each tile carries the image batch)
-    for tiles in groups.values():
-        for i in range(0, len(tiles), per):
-            chunk = tiles[i:i + per]
-            inp = torch.cat([lq[:, :, yp0:yp1, xp0:xp1] for (yp0, yp1, xp0, xp1), _ in chunk], dim=0)
-            res = net(inp)
-            for k, ((yp0, yp1, xp0, xp1), (y0, y1, x0, x1)) in enumerate(chunk):
-                o = res[k * b:(k + 1) * b]
-                oy, ox = (y0 - yp0) * scale, (x0 - xp0) * scale
-                out[:, :, y0 * scale:y1 * scale, x0 * scale:x1 * scale] = o[:, :, oy:oy + (y1 - y0) * scale, ox:ox + (x1 - x0) * scale]
+    from .params import frozen_weights
+    with frozen_weights():                             # nothing can change the weights inside this loop: one fingerprint check
+        for tiles in groups.values():
+            for i in range(0, len(tiles), per):
+                chunk = tiles[i:i + per]
+                inp = torch.cat([lq[:, :, yp0:yp1, xp0:xp1] for (yp0, yp1, xp0, xp1), _ in chunk], dim=0)
+                res = net(inp)
+                for k, ((yp0, yp1, xp0, xp1), (y0, y1, x0, x1)) in enumerate(chunk):
+                    o = res[k * b:(k + 1) * b]
+                    oy, ox = (y0 - yp0) * scale, (x0 - xp0) * scale
+                    out[:, :, y0 * scale:y1 * scale, x0 * scale:x1 * scale] = o[:, :, oy:oy + (y1 - y0) * scale, ox:ox + (x1 - x0) * scale]
     return out
 
 

@@ -42,3 +42,21 @@ def test_cuda_prefetcher_has_no_cpu_path():
     import pytest as _pytest
     with _pytest.raises(Exception, match="no CPU path"):
         CUDAPrefetcher([{"lq": torch.zeros(1)}], {"num_gpu": 0})
+
+
+def test_frozen_weights_skips_the_fingerprint_after_the_first_check():
+    """dcpt_b200.params.frozen_weights (the tile loop of dcpt_b200/tiling.py): per cache object the fingerprint is compared once
+    inside the block, again outside it."""
+    from dcpt_b200 import params as P
+    a, b = P.PackedCacheKey(), P.PackedCacheKey()
+    assert not P._fingerprint_already_checked(a) and not P._fingerprint_already_checked(a)      # outside: always check
+    with P.frozen_weights():
+        assert not P._fingerprint_already_checked(a)          # first forward of engine a: check
+        assert P._fingerprint_already_checked(a)              # later ones: skip
+        assert not P._fingerprint_already_checked(b)          # another engine checks for itself
+        with P.frozen_weights():
+            assert P._fingerprint_already_checked(a) and P._fingerprint_already_checked(b)
+        assert P._fingerprint_already_checked(a)
+    assert not P._fingerprint_already_checked(a)
+    with P.frozen_weights():
+        assert not P._fingerprint_already_checked(a)          # a new block starts over
