@@ -93,7 +93,10 @@ mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, cons
     __syncthreads();
   }
   bf16* out = weff + (size_t)n * d * d;
-  for (int idx = threadIdx.x; idx < d * c; idx += blockDim.x) {
+  // the output rows are split over blockIdx.z (every slice rebuilds the c x c tile above: c^2 values against (d / slices) * c * c
+  // MACs): (heads, images) alone is 1-16 CTAs on the single-head full-resolution levels
+  const int o_per = (d + gridDim.z - 1) / gridDim.z, o0 = blockIdx.z * o_per, o1 = min(d, o0 + o_per);
+  for (int idx = threadIdx.x + o0 * c; idx < o1 * c; idx += blockDim.x) {
     const int o = idx / c, j = idx - o * c;
     const float* wr = wout + (size_t)o * d + h * c;
     float acc = 0.f;
@@ -613,7 +616,11 @@ int block_fwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
     DCPT_CHECK_ARG(d % b.heads == 0 && smem <= 200 * 1024, DCPT_E_SHAPE, "mdta: dim %d / heads %d unsupported", d, b.heads);
     if (smem > 48 * 1024) DCPT_CUDA(cudaFuncSetAttribute(mdta_weff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DCPT_PROF("mdta_weff", 2.0 * N * d * d * c, 4.0 * N * d * d, st);
-    mdta_weff_kernel<<<dim3(b.heads, N), 256, smem, st>>>(bf.G, bf.sq, P[ix.temp], P[ix.pout], bf.weff, bf.weffT, d, b.heads, p->attn_softmax);
+    int slices = (2 * dcpt_num_sms()) / (b.heads * N);  // ~2 CTAs per SM
+    if (slices > d / 8) slices = d / 8;
+    if (slices < 1) slices = 1;
+    mdta_weff_kernel<<<dim3(b.heads, N, slices), 256, smem, st>>>(bf.G, bf.sq, P[ix.temp], P[ix.pout], bf.weff, bf.weffT, d, b.heads,
+                                                                 p->attn_softmax);
     DCPT_LAUNCH_CHECK();
   }
   // x2 = x + v * W_eff[image]^T, norm2 of the result in the same epilogue
