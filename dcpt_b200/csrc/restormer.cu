@@ -114,10 +114,90 @@ mdta_weff_kernel(const float* __restrict__ G, const float* __restrict__ sq, cons
 //   cq_i = -(sum_j dGhat_ij Ghat_ij) / nq_i^2,  ck_j = -(sum_i dGhat_ij Ghat_ij) / nk_j^2          (F.normalize backward)
 // so that dq[px,i] = sum_j dG_ij k[px,j] + cq_i q[px,i] and dk[px,j] = sum_i dG_ij q[px,i] + ck_j k[px,j]: both are ONE GEMM of
 // the [q | k] slab with Bmat[n] (bf16 [2d, 2d], rows = outputs [dq | dk], columns = [q | k] channels), written here.
+// Phase A of the backward when (heads, images) alone would be a handful of CTAs (the single-head full-resolution levels: 4 CTAs at
+// batch 4, 266 us per launch, 37 % of a Restormer training step): the reduction over the output channel o is split over
+// blockIdx.z.  Every slice rebuilds the c x c attention tile, takes a contiguous range of o, adds its partial
+// dattn_ij = sum_o Wout[o,hc+i] dWeff[o,hc+j] into dattn_g[n][h] (fp32 atomics, pre-zeroed) and writes the dWout rows of its range.
+// mdta_bwd_kernel then runs with dattn_g != nullptr and skips that loop.
+__global__ void __launch_bounds__(256)
+mdta_bwd_da_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, const float* __restrict__ sq,
+                   const float* __restrict__ temp, const float* __restrict__ wout, float* __restrict__ dwout,
+                   float* __restrict__ dattn_g, int d, int heads, int softmax) {
+  extern __shared__ float sm[];
+  const int c = d / heads, h = blockIdx.x, n = blockIdx.y, hc = h * c;
+  float* s_at = sm;                 // attn   [c][c]
+  float* s_da = s_at + c * c;       // partial dattn [c][c]
+  float* s_nq = s_da + c * c;       // [c]
+  float* s_nk = s_nq + c;           // [c]
+  float* s_w = s_nk + c;            // Wout chunk  [64][c]
+  float* s_e = s_w + 64 * c;        // dWeff chunk [64][c]
+  const float* Gn = G + (size_t)n * d * d;
+  const float* sqn = sq + (size_t)n * 2 * d;
+  const float* dWn = dWeff + (size_t)n * d * d;
+  const float T = __ldg(temp + h);
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    s_nq[i] = fmaxf(sqrtf(sqn[hc + i]), 1e-12f);
+    s_nk[i] = fmaxf(sqrtf(sqn[d + hc + i]), 1e-12f);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
+    const int i = idx / c, j = idx - i * c;
+    const float a = Gn[(size_t)(hc + i) * d + hc + j] / (s_nq[i] * s_nk[j]) * T;
+    s_at[idx] = softmax ? a : fmaxf(a, 0.f);
+    s_da[idx] = 0.f;
+  }
+  __syncthreads();
+  if (softmax) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      float* row = s_at + i * c;
+      float m = row[0];
+      for (int j = 1; j < c; ++j) m = fmaxf(m, row[j]);
+      float sum = 0.f;
+      for (int j = 0; j < c; ++j) {
+        const float e = expf(row[j] - m);
+        row[j] = e;
+        sum += e;
+      }
+      const float inv = 1.f / sum;
+      for (int j = 0; j < c; ++j) row[j] *= inv;
+    }
+    __syncthreads();
+  }
+  const int per = ((d + gridDim.z - 1) / gridDim.z + 15) / 16 * 16;   // rows of o per slice (multiple of 16)
+  const int ob = blockIdx.z * per, oe = min(d, ob + per);
+  for (int o0 = ob; o0 < oe; o0 += 64) {
+    const int no = min(64, oe - o0);
+    for (int idx = threadIdx.x; idx < no * c; idx += blockDim.x) {
+      const int oo = idx / c, k = idx - oo * c;
+      s_w[idx] = __ldg(wout + (size_t)(o0 + oo) * d + hc + k);
+      s_e[idx] = dWn[(size_t)(o0 + oo) * d + hc + k];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) {
+      const int i = idx / c, j = idx - i * c;
+      float acc = 0.f;
+      for (int oo = 0; oo < no; ++oo) acc = fmaf(s_w[oo * c + i], s_e[oo * c + j], acc);
+      s_da[idx] += acc;
+    }
+    for (int idx = threadIdx.x; idx < no * c; idx += blockDim.x) {
+      const int oo = idx / c, i = idx - oo * c;
+      float acc = 0.f;
+      for (int j = 0; j < c; ++j) acc = fmaf(s_e[oo * c + j], s_at[i * c + j], acc);
+      atomicAdd(dwout + (size_t)(o0 + oo) * d + hc + i, acc);
+    }
+    __syncthreads();
+  }
+  if (ob < oe) {
+    float* dst = dattn_g + ((size_t)n * heads + h) * c * c;
+    for (int idx = threadIdx.x; idx < c * c; idx += blockDim.x) atomicAdd(dst + idx, s_da[idx]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 mdta_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, const float* __restrict__ sq,
                 const float* __restrict__ temp, const float* __restrict__ wout, float* __restrict__ dwout, float* __restrict__ dtemp,
-                bf16* __restrict__ Bmat, bf16* __restrict__ BmatLo, int d, int heads, int softmax) {
+                bf16* __restrict__ Bmat, bf16* __restrict__ BmatLo, int d, int heads, int softmax,
+                const float* __restrict__ dattn_g = nullptr) {
   extern __shared__ float sm[];
   const int c = d / heads, h = blockIdx.x, n = blockIdx.y, hc = h * c;
   float* s_gh = sm;                 // Ghat   [c][c]
@@ -142,7 +222,7 @@ mdta_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, co
     const float gh = Gn[(size_t)(hc + i) * d + hc + j] / (s_nq[i] * s_nk[j]);
     s_gh[idx] = gh;
     s_at[idx] = softmax ? gh * T : fmaxf(gh * T, 0.f);
-    s_da[idx] = 0.f;
+    s_da[idx] = dattn_g ? dattn_g[((size_t)n * heads + h) * c * c + idx] : 0.f;   // phase A (mdta_bwd_da_kernel) already reduced over o
   }
   __syncthreads();
   if (softmax) {  // recompute attn = softmax_j(A_ij)
@@ -162,7 +242,7 @@ mdta_bwd_kernel(const float* __restrict__ dWeff, const float* __restrict__ G, co
     __syncthreads();
   }
   // dattn and dWout, streaming 64 output channels o at a time through shared memory
-  for (int o0 = 0; o0 < d; o0 += 64) {
+  for (int o0 = 0; o0 < (dattn_g ? 0 : d); o0 += 64) {
     const int no = min(64, d - o0);
     for (int idx = threadIdx.x; idx < no * c; idx += blockDim.x) {
       const int oo = idx / c, k = idx - oo * c;
@@ -430,13 +510,14 @@ struct BlkSaved : BlkBufs {
 
 struct BlkWork {
   bf16 *doutT, *dg, *bufA, *bufB, *dn, *dx2T, *Bmat;  // Bmat: hi [N,2d,2d] followed by lo [N,2d,2d]
-  float *dx2, *dWeff, *scratch, *tmp32;
+  float *dx2, *dWeff, *scratch, *tmp32, *dattn;
   BlkWork(Arena& a, const dcpt_restormer_plan::Blk& b, int N, int H, int W) {
     const size_t M = (size_t)N * H * W, d = b.d, wide = 2 * (size_t)b.hidp > 3 * d ? 2 * (size_t)b.hidp : 3 * d;
     doutT = a.take<bf16>(M * d); dg = a.take<bf16>(M * b.hidp);
     bufA = a.take<bf16>(M * wide); bufB = a.take<bf16>(M * wide);
     dn = a.take<bf16>(M * d); dx2T = a.take<bf16>(M * d); Bmat = a.take<bf16>((size_t)N * 8 * d * d);
     dx2 = a.take<float>(M * d); dWeff = a.take<float>((size_t)N * d * d); tmp32 = a.take<float>(M * 2 * d);
+    dattn = a.take<float>((size_t)N * d * d / b.heads);   // [N][heads][c][c]
     size_t sc = 2 * (size_t)b.hidp * d;
     if (3 * d * d > sc) sc = 3 * d * d;
     scratch = a.take<float>(sc + 2 * (size_t)b.hidp * 9);
@@ -706,9 +787,22 @@ int block_bwd(const dcpt_restormer_plan* p, const dcpt_restormer_plan::Blk& b, c
     const size_t smem = ((size_t)3 * c * c + 2 * c + 2 * 64 * c) * sizeof(float);
     DCPT_CHECK_ARG(smem <= 220 * 1024, DCPT_E_SHAPE, "mdta backward: head width %d too large", c);
     if (smem > 48 * 1024) DCPT_CUDA(cudaFuncSetAttribute(mdta_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int slices = (2 * dcpt_num_sms()) / (b.heads * N);   // split the reduction over o when (heads, images) is a handful of CTAs
+    if (slices > d / 16) slices = d / 16;
+    const float* dattn = nullptr;
+    if (slices >= 2 && !getenv("DCPT_MDTA_BWD_SPLIT0")) {
+      const size_t smem_a = ((size_t)2 * c * c + 2 * c + 2 * 64 * c) * sizeof(float);
+      if (smem_a > 48 * 1024) DCPT_CUDA(cudaFuncSetAttribute(mdta_bwd_da_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+      DCPT_CUDA(cudaMemsetAsync(wk.dattn, 0, (size_t)N * d * c * sizeof(float), st));
+      DCPT_PROF("mdta_bwd_da", 4.0 * N * d * d * c, 8.0 * N * d * d, st);
+      mdta_bwd_da_kernel<<<dim3(b.heads, N, slices), 256, smem_a, st>>>(wk.dWeff, sv.G, sv.sq, P[ix.temp], P[ix.pout], G[ix.pout], wk.dattn, d,
+                                                                       b.heads, p->attn_softmax);
+      DCPT_LAUNCH_CHECK();
+      dattn = wk.dattn;
+    }
     DCPT_PROF("mdta_bwd", 4.0 * N * d * d * c, 12.0 * N * d * d, st);
     mdta_bwd_kernel<<<dim3(b.heads, N), 256, smem, st>>>(wk.dWeff, sv.G, sv.sq, P[ix.temp], P[ix.pout], G[ix.pout], G[ix.temp], wk.Bmat,
-                                                        BmatLo, d, b.heads, p->attn_softmax);
+                                                        BmatLo, d, b.heads, p->attn_softmax, dattn);
     DCPT_LAUNCH_CHECK();
   }
   // [dq | dk] = [q | k] (Bmat_hi + Bmat_lo)[n]^T: two passes, fp32 in between
