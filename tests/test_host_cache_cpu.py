@@ -60,3 +60,28 @@ def test_frozen_weights_skips_the_fingerprint_after_the_first_check():
     assert not P._fingerprint_already_checked(a)
     with P.frozen_weights():
         assert not P._fingerprint_already_checked(a)          # a new block starts over
+
+
+def test_training_pass_marker_is_per_thread_and_nests():
+    """dcpt_b200.params.training_pass: the marker that keeps the no-grad weight fingerprint (a host sync) off the forward /
+    backward of gradient-needing calls - autograd runs backward on its own thread, so the marker must be thread-local."""
+    import threading
+    from dcpt_b200 import params as P
+    assert not P.in_training_pass()
+    seen = {}
+    with P.training_pass():
+        assert P.in_training_pass()
+        with P.training_pass():
+            assert P.in_training_pass()
+        assert P.in_training_pass()
+        t = threading.Thread(target=lambda: seen.setdefault("other", P.in_training_pass()))
+        t.start()
+        t.join()
+    assert not P.in_training_pass() and seen["other"] is False
+    # and a CPU parameter list never triggers the fingerprint path at all (no CUDA, no sync): stale() only looks at versions
+    k = P.PackedCacheKey()
+    ps = [torch.nn.Parameter(torch.zeros(3))]
+    with torch.no_grad():
+        assert k.stale(ps) and not k.stale(ps)
+        ps[0].add_(1.0)
+        assert k.stale(ps)
