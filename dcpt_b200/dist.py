@@ -44,6 +44,20 @@ def shard_batch(n_items, rank=None, world=None):
     return list(range(rank, n_items, world))
 
 
+def enlarged_indices(dataset_size, num_replicas, rank, ratio=1, epoch=0):
+    """The index list ``EnlargedSampler.__iter__`` yields (basicsr/data/data_sampler.py:8-48): a seeded permutation of
+    ``ceil(size * ratio / replicas) * replicas`` positions folded onto the dataset, every ``replicas``-th entry from ``rank``."""
+    import math
+    num_samples = math.ceil(dataset_size * ratio / num_replicas)
+    total = num_samples * num_replicas
+    g = torch.Generator()
+    g.manual_seed(epoch)
+    idx = [v % dataset_size for v in torch.randperm(total, generator=g).tolist()]
+    idx = idx[rank:total:num_replicas]
+    assert len(idx) == num_samples
+    return idx
+
+
 def allreduce_mean_(flat, group=None):
     """In-place mean all-reduce of the flat fp32 gradient buffer (DDP's bucketed all-reduce, base_model.py:111-115)."""
     if not (dist.is_available() and dist.is_initialized()):
